@@ -1,0 +1,42 @@
+"""Shared description of the golden fixtures (tests/golden/make_golden.py) for oracle and GPU tests."""
+import os
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIELD_DIMS = np.array([7, 5, 11, 4, 9, 6], dtype=np.int64)
+E = 4
+L2 = dict(l2_reg_embedding=1e-3, l2_reg_linear=1e-3, l2_reg_dnn=1e-3, l2_reg_cross=1e-3)
+T = 3
+
+# name -> (model kind, ctor kwargs, selection mode, steps)
+CASES = {
+    "ple": ("ple", dict(n_tower=T, n_expert_specific=2, n_expert_shared=1, expert_dims=((16, 8), (8,)), tower_dims=(8, 4)), "gather", 3),
+    "mmoe": ("mmoe", dict(n_tower=T, n_expert=3, expert_dims=(16, 8), tower_dims=(8, 4)), "gather", 3),
+    "dcn": ("dcn", dict(n_cross_layers=3, mlp_dims=(16, 8)), "single", 3),
+    "dcnv2_mix_parallel": ("dcnv2", dict(n_cross_layers=2, mlp_dims=(16, 8), low_rank=4, num_experts=3), "single", 3),
+    "dcnv2_mix_stacked": ("dcnv2", dict(n_cross_layers=2, mlp_dims=(16, 8), model_structure="stacked", low_rank=4, num_experts=3), "single", 2),
+    "star": ("star", dict(n_tower=T, tower_dims=(16, 8)), "gather", 3),
+    "star_grouped": ("star", dict(n_tower=T, tower_dims=(16, 8)), "star_grouped", 3),
+}
+for _base, _kw in (("ple", CASES["ple"][1]), ("mmoe", CASES["mmoe"][1]), ("star", CASES["star"][1])):
+    for _mode, _sel in (("warmup", "warmup"), ("split_domain", "split_domain"), ("split_gather", "split_gather")):
+        CASES[f"cdc_{_base}_{_mode}"] = (_base, _kw, _sel, 2)
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def state(gold, step, strip="base_model_instance."):
+    pre = f"sd{step}."
+    out = {}
+    for k, v in gold.items():
+        if k.startswith(pre):
+            kk = k[len(pre):]
+            out[kk[len(strip):] if kk.startswith(strip) else kk] = v
+    return out
+
+
+def strip(k, prefix="base_model_instance."):
+    return k[len(prefix):] if k.startswith(prefix) else k
