@@ -1,0 +1,88 @@
+// Shared helpers for libcdcmdr (sm_100a).  No torch, no CPU fallback.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/cdcmdr.h"
+
+namespace cdcmdr {
+
+extern thread_local char g_err[512];
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(const char* what, cudaError_t e, const char* file, int line) {
+  snprintf(g_err, sizeof(g_err), "%s: %s (%s:%d)", what, cudaGetErrorString(e), file, line);
+  return 1;
+}
+inline int fail_msg(const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return 2;
+}
+
+#define CDC_CHECK(call)                                                      \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return ::cdcmdr::fail(#call, e__, __FILE__, __LINE__); \
+  } while (0)
+
+// after every kernel launch: count it and surface launch-configuration errors
+#define CDC_LAUNCHED()                                                       \
+  do {                                                                       \
+    ::cdcmdr::g_launches.fetch_add(1, std::memory_order_relaxed);            \
+    cudaError_t e__ = cudaGetLastError();                                    \
+    if (e__ != cudaSuccess) return ::cdcmdr::fail("kernel launch", e__, __FILE__, __LINE__); \
+  } while (0)
+
+#define CDC_REQUIRE(cond, msg) \
+  do { if (!(cond)) return ::cdcmdr::fail_msg("cdcmdr: " msg " [" #cond "]"); } while (0)
+
+constexpr int kNumSMs = 148;
+
+inline cudaStream_t to_stream(cdcmdr_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Stateless dropout mask: keep iff hash(seed, salt, idx) >= p * 2^32.  Same bits in forward (epilogues /
+// BN kernels) and in tests/oracle; the backward never regenerates it (the stored activation is 0 where dropped).
+__host__ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t salt, uint64_t idx) {
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)salt << 32 | salt);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 32);
+}
+__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+}
+
+__device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(((uint32_t)h) << 16); }
+__device__ __forceinline__ uint16_t f32_to_bf16(float f) {
+  __nv_bfloat16 b = __float2bfloat16_rn(f);
+  return *reinterpret_cast<uint16_t*>(&b);
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  return (uint32_t)f32_to_bf16(lo) | ((uint32_t)f32_to_bf16(hi) << 16);
+}
+
+template <typename T> __device__ __forceinline__ float ld_act(const T* p);
+template <> __device__ __forceinline__ float ld_act<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_act<uint16_t>(const uint16_t* p) { return bf16_to_f32(*p); }
+template <typename T> __device__ __forceinline__ void st_act(T* p, float v);
+template <> __device__ __forceinline__ void st_act<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st_act<uint16_t>(uint16_t* p, float v) { *p = f32_to_bf16(v); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace cdcmdr

@@ -1,0 +1,422 @@
+// Sparse-field embedding: gather (a1), deterministic sorted-segment backward (a2) and the fused
+// reference-exact dense Adam sweep (a2+a7+a17).  HBM-bound integer/byte work: 128-bit accesses,
+// E/4 lanes per row so a warp touches 32/(E/4) consecutive rows of w/m/v (fully coalesced sweep).
+#include "common.cuh"
+#include <cub/cub.cuh>
+
+namespace cdcmdr {
+
+constexpr int kShortSeg = 64;        // segments up to this many entries are summed inline, in order
+constexpr int kLongThreads = 256;    // one CTA per long segment
+constexpr int kRegPartials = 2048;
+
+struct EmbedPlan {                   // lives at the start of the caller-provided workspace
+  int64_t n, V, n_long_max;
+  int E_max;
+  size_t off_keys_in, off_vals_in, off_keys, off_vals, off_uniq, off_cnt, off_start, off_nuniq,
+      off_seg_of_row, off_long_slot, off_nlong, off_long_sum, off_long_seg, off_cub, off_reg;
+  size_t cub_bytes, total;
+};
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+static int sort_bits(int64_t V) { int b = 1; while ((int64_t(1) << b) <= V) ++b; return b; }  // keys in [0, V]
+
+static size_t cub_temp_bytes(int64_t n, int64_t V) {
+  size_t a = 0, b = 0, c = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                  (int32_t*)nullptr, (int)n, 0, sort_bits(V));
+  cub::DeviceRunLengthEncode::Encode(nullptr, b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int32_t*)nullptr,
+                                     (int32_t*)nullptr, (int)n);
+  cub::DeviceScan::ExclusiveSum(nullptr, c, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n);
+  size_t m = a > b ? a : b;
+  return (m > c ? m : c) + 1024;
+}
+
+static EmbedPlan make_layout(int64_t n, int64_t V, int E_max) {
+  EmbedPlan p{};
+  p.n = n; p.V = V; p.E_max = E_max; p.n_long_max = n / kShortSeg + 1;
+  size_t o = align256(sizeof(EmbedPlan));
+  auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
+  p.off_keys_in = take(n * 4); p.off_vals_in = take(n * 4);
+  p.off_keys = take(n * 4);    p.off_vals = take(n * 4);
+  p.off_uniq = take(n * 4);    p.off_cnt = take(n * 4);   p.off_start = take((n + 1) * 4);
+  p.off_nuniq = take(16);      p.off_seg_of_row = take((size_t)V * 4);
+  p.off_long_slot = take(n * 4); p.off_nlong = take(16);
+  p.off_long_sum = take((size_t)p.n_long_max * E_max * 4);
+  p.off_long_seg = take((size_t)p.n_long_max * 4);
+  p.off_reg = take(kRegPartials * 8);
+  p.cub_bytes = cub_temp_bytes(n, V);
+  p.off_cub = take(p.cub_bytes);
+  p.total = o;
+  return p;
+}
+
+template <typename T> static T* at(const void* base, size_t off) { return (T*)((char*)base + off); }
+
+// ------------------------------------------------------------------------------------------ gather
+template <int VEC>
+__global__ void embed_gather_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ offsets,
+                                    const float* __restrict__ table, float* __restrict__ out_f32,
+                                    uint16_t* __restrict__ out_bf16, int64_t ld_bf16, int64_t B, int F, int E,
+                                    int64_t V, int* __restrict__ oob) {
+  const int lanes = E / VEC;                       // lanes per (b,f) row
+  const int64_t total = B * (int64_t)F * lanes;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % lanes);
+    const int64_t bf = i / lanes;
+    const int f = (int)(bf % F);
+    const int64_t b = bf / F;
+    const int64_t row = (int64_t)x[bf] + offsets[f];
+    float v[VEC];
+    if (row >= 0 && row < V) {
+      if (VEC == 4) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(table + row * E) + q);
+        v[0] = t.x; v[1 % VEC] = t.y; v[2 % VEC] = t.z; v[3 % VEC] = t.w;
+      } else {
+        v[0] = __ldg(table + row * E + q);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) v[j] = 0.f;
+      if (oob) *oob = 1;
+    }
+    const int64_t col = (int64_t)f * E + q * VEC;
+    if (out_f32) {
+      float* o = out_f32 + b * (int64_t)F * E + col;
+      if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1 % VEC], v[2 % VEC], v[3 % VEC]);
+      else o[0] = v[0];
+    }
+    if (out_bf16) {
+      uint16_t* o = out_bf16 + b * ld_bf16 + col;
+      if (VEC == 4) *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16x2(v[0], v[1 % VEC]), pack_bf16x2(v[2 % VEC], v[3 % VEC]));
+      else o[0] = f32_to_bf16(v[0]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ plan
+__global__ void plan_keys_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ offsets, int64_t n, int F,
+                                 int64_t V, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t row = (int64_t)x[i] + offsets[i % F];
+    keys[i] = (row >= 0 && row < V) ? (uint32_t)row : (uint32_t)V;   // out-of-range rows sort last and are ignored
+    vals[i] = (int32_t)i;
+  }
+}
+
+__global__ void plan_segments_kernel(const uint32_t* __restrict__ uniq, const int32_t* __restrict__ cnt,
+                                     const int32_t* __restrict__ nuniq, int64_t V, int32_t* __restrict__ seg_of_row,
+                                     int32_t* __restrict__ long_slot, int32_t* __restrict__ nlong,
+                                     int32_t* __restrict__ long_seg) {
+  const int nu = *nuniq;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nu; i += gridDim.x * blockDim.x) {
+    const uint32_t r = uniq[i];
+    if ((int64_t)r < V) seg_of_row[r] = i;
+    int slot = -1;
+    if (cnt[i] > kShortSeg && (int64_t)r < V) { slot = atomicAdd(nlong, 1); long_seg[slot] = i; }
+    long_slot[i] = slot;
+  }
+}
+
+// one CTA per long segment: lane-group j sums entries j, j+G, j+2G, ... in order; fixed smem tree afterwards
+template <int VEC>
+__global__ void __launch_bounds__(kLongThreads)
+long_segment_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, const int32_t* __restrict__ vals,
+                    const int32_t* __restrict__ start, const int32_t* __restrict__ cnt, const int32_t* __restrict__ long_seg,
+                    const int32_t* __restrict__ nlong, float* __restrict__ long_sum) {
+  extern __shared__ float sm[];                    // [groups][E]
+  const int lanes = E / VEC;
+  const int groups = kLongThreads / lanes;
+  const int g = threadIdx.x / lanes, q = threadIdx.x % lanes;
+  for (int ls = blockIdx.x; ls < *nlong; ls += gridDim.x) {
+    const int seg = long_seg[ls];
+    const int s0 = start[seg], c = cnt[seg];
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    if (g < groups) {
+      for (int i = g; i < c; i += groups) {
+        const int pos = vals[s0 + i];
+        const float* src = grad_out + (int64_t)(pos / F) * ldg + (int64_t)(pos % F) * E + q * VEC;
+        if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(src); acc[0] += t.x; acc[1 % VEC] += t.y; acc[2 % VEC] += t.z; acc[3 % VEC] += t.w; }
+        else acc[0] += src[0];
+      }
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) sm[g * E + q * VEC + j] = acc[j];
+    }
+    __syncthreads();
+    for (int half = 1; half < groups; half <<= 1) {      // groups is a power of two for E in {4,8,16,32,64,...}; generic otherwise
+      if (g < groups && (g % (2 * half)) == 0 && g + half < groups) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) sm[g * E + q * VEC + j] += sm[(g + half) * E + q * VEC + j];
+      }
+      __syncthreads();
+    }
+    if (g == 0) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) long_sum[(int64_t)ls * E + q * VEC + j] = sm[q * VEC + j];
+    }
+    __syncthreads();
+  }
+}
+
+template <int VEC>
+__device__ __forceinline__ void segment_sum(float (&acc)[VEC], const float* __restrict__ grad_out, int64_t ldg, int F, int E,
+                                            int q, int seg, const int32_t* __restrict__ vals, const int32_t* __restrict__ start,
+                                            const int32_t* __restrict__ cnt, const int32_t* __restrict__ long_slot,
+                                            const float* __restrict__ long_sum) {
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  if (seg < 0) return;
+  const int c = cnt[seg];
+  if (c > kShortSeg) {
+    const float* src = long_sum + (int64_t)long_slot[seg] * E + q * VEC;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = src[j];
+    return;
+  }
+  const int s0 = start[seg];
+  for (int i = 0; i < c; ++i) {
+    const int pos = vals[s0 + i];
+    const float* src = grad_out + (int64_t)(pos / F) * ldg + (int64_t)(pos % F) * E + q * VEC;
+    if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(src); acc[0] += t.x; acc[1 % VEC] += t.y; acc[2 % VEC] += t.z; acc[3 % VEC] += t.w; }
+    else acc[0] += src[0];
+  }
+}
+
+template <int VEC>
+__global__ void embed_dense_grad_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, int64_t V,
+                                        const int32_t* __restrict__ seg_of_row, const int32_t* __restrict__ vals,
+                                        const int32_t* __restrict__ start, const int32_t* __restrict__ cnt,
+                                        const int32_t* __restrict__ long_slot, const float* __restrict__ long_sum,
+                                        float* __restrict__ grad_table) {
+  const int lanes = E / VEC;
+  const int64_t total = V * lanes;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % lanes);
+    const int64_t r = i / lanes;
+    float acc[VEC];
+    segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg_of_row[r], vals, start, cnt, long_slot, long_sum);
+    float* o = grad_table + r * E + q * VEC;
+    if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    else o[0] = acc[0];
+  }
+}
+
+struct AdamK { float lr_t, b1, b2, eps, wd, l2x2, bc2_sqrt; };
+
+__device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, const AdamK& k) {
+  g = g + k.l2x2 * w;                    // gradient of l2 * sum(w^2)                 layer.py:106-108
+  g = g + k.wd * w;                      // Adam weight_decay (L2 style)              run.py:720
+  m = m + (1.f - k.b1) * (g - m);        // exp_avg.lerp_(grad, 1-beta1)
+  v = k.b2 * v + (1.f - k.b2) * g * g;   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1-beta2)
+  const float denom = sqrtf(v) / k.bc2_sqrt + k.eps;
+  w = w - k.lr_t * (m / denom);          // param.addcdiv_(exp_avg, denom, value=-lr/bc1)
+}
+
+template <int VEC, bool DENSE>
+__global__ void __launch_bounds__(256)
+embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, int64_t V,
+                  const int32_t* __restrict__ seg_of_row, const uint32_t* __restrict__ uniq, const int32_t* __restrict__ nuniq,
+                  const int32_t* __restrict__ vals, const int32_t* __restrict__ start, const int32_t* __restrict__ cnt,
+                  const int32_t* __restrict__ long_slot, const float* __restrict__ long_sum,
+                  float* __restrict__ table, float* __restrict__ mom, float* __restrict__ var, AdamK k,
+                  double* __restrict__ reg_partials) {
+  const int lanes = E / VEC;
+  const int64_t rows = DENSE ? V : (int64_t)(*nuniq);
+  const int64_t total = rows * lanes;
+  double sq = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int q = (int)(i % lanes);
+    int64_t r; int seg;
+    if (DENSE) { r = i / lanes; seg = seg_of_row[r]; }
+    else { seg = (int)(i / lanes); r = uniq[seg]; if (r >= V) continue; }
+    float acc[VEC];
+    segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg, vals, start, cnt, long_slot, long_sum);
+    const int64_t o = r * E + q * VEC;
+    if (VEC == 4) {
+      float4 w = *reinterpret_cast<float4*>(table + o), m = *reinterpret_cast<float4*>(mom + o), v = *reinterpret_cast<float4*>(var + o);
+      sq += (double)w.x * w.x + (double)w.y * w.y + (double)w.z * w.z + (double)w.w * w.w;
+      adam_elem(w.x, m.x, v.x, acc[0], k); adam_elem(w.y, m.y, v.y, acc[1 % VEC], k);
+      adam_elem(w.z, m.z, v.z, acc[2 % VEC], k); adam_elem(w.w, m.w, v.w, acc[3 % VEC], k);
+      *reinterpret_cast<float4*>(table + o) = w; *reinterpret_cast<float4*>(mom + o) = m; *reinterpret_cast<float4*>(var + o) = v;
+    } else {
+      float w = table[o], m = mom[o], v = var[o];
+      sq += (double)w * w;
+      adam_elem(w, m, v, acc[0], k);
+      table[o] = w; mom[o] = m; var[o] = v;
+    }
+  }
+  if (reg_partials) {                              // deterministic: fixed grid, fixed in-block tree
+    __shared__ double red[8];
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; reg_partials[blockIdx.x] = t; }
+  }
+}
+
+__global__ void reg_finalize_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double t = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) t += partials[i];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w]; *out = s; }
+}
+
+static AdamK make_adam(const cdcmdr_adam_t* h) {
+  const double bc1 = 1.0 - pow((double)h->beta1, (double)h->step);
+  const double bc2 = 1.0 - pow((double)h->beta2, (double)h->step);
+  AdamK k;
+  k.lr_t = (float)((double)h->lr / bc1); k.b1 = h->beta1; k.b2 = h->beta2; k.eps = h->eps; k.wd = h->weight_decay;
+  k.l2x2 = 2.f * h->l2; k.bc2_sqrt = (float)sqrt(bc2);
+  return k;
+}
+
+static int grid_for(int64_t work, int threads, int max_ctas_per_sm = 8) {
+  int64_t g = ceil_div(work, threads);
+  const int64_t cap = (int64_t)kNumSMs * max_ctas_per_sm;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+}  // namespace cdcmdr
+
+using namespace cdcmdr;
+
+extern "C" int cdcmdr_embed_gather_fwd(const int32_t* x, const int64_t* offsets, const float* table, float* out_f32,
+                                       uint16_t* out_bf16, int64_t ld_bf16, int64_t B, int F, int E, int64_t V,
+                                       int* oob_flag, cdcmdr_stream_t s) {
+  CDC_REQUIRE(B >= 0 && F > 0 && E > 0 && V > 0, "bad gather shape");
+  if (B == 0) return 0;
+  CDC_REQUIRE(out_f32 || out_bf16, "gather needs an output");
+  if (E % 4 == 0 && (!out_bf16 || ld_bf16 % 4 == 0)) {
+    const int64_t work = B * F * (E / 4);
+    embed_gather_kernel<4><<<grid_for(work, 256), 256, 0, to_stream(s)>>>(x, offsets, table, out_f32, out_bf16, ld_bf16, B, F, E, V, oob_flag);
+  } else {
+    const int64_t work = B * F * (int64_t)E;
+    embed_gather_kernel<1><<<grid_for(work, 256), 256, 0, to_stream(s)>>>(x, offsets, table, out_f32, out_bf16, ld_bf16, B, F, E, V, oob_flag);
+  }
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t cdcmdr_embed_plan_bytes(int64_t n_idx, int64_t V, int E_max) {
+  if (n_idx <= 0) n_idx = 1;
+  return make_layout(n_idx, V, E_max).total;
+}
+
+extern "C" int cdcmdr_embed_plan_build(const int32_t* x, const int64_t* offsets, int64_t B, int F, int64_t V, int E_max,
+                                       void* plan, size_t plan_bytes, cdcmdr_stream_t s) {
+  const int64_t n = B * F;
+  CDC_REQUIRE(n > 0 && n < (int64_t(1) << 31) && V < (int64_t(1) << 31) - 1, "plan size out of int32 range");
+  EmbedPlan L = make_layout(n, V, E_max);
+  CDC_REQUIRE(plan_bytes >= L.total, "plan workspace too small");
+  cudaStream_t st = to_stream(s);
+  CDC_CHECK(cudaMemcpyAsync(plan, &L, sizeof(L), cudaMemcpyHostToDevice, st));
+  uint32_t* keys_in = at<uint32_t>(plan, L.off_keys_in); int32_t* vals_in = at<int32_t>(plan, L.off_vals_in);
+  uint32_t* keys = at<uint32_t>(plan, L.off_keys); int32_t* vals = at<int32_t>(plan, L.off_vals);
+  uint32_t* uniq = at<uint32_t>(plan, L.off_uniq); int32_t* cnt = at<int32_t>(plan, L.off_cnt);
+  int32_t* start = at<int32_t>(plan, L.off_start); int32_t* nuniq = at<int32_t>(plan, L.off_nuniq);
+  int32_t* seg_of_row = at<int32_t>(plan, L.off_seg_of_row);
+  plan_keys_kernel<<<grid_for(n, 256), 256, 0, st>>>(x, offsets, n, F, V, keys_in, vals_in);
+  CDC_LAUNCHED();
+  size_t tb = L.cub_bytes;
+  void* tmp = at<void>(plan, L.off_cub);
+  CDC_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tb, keys_in, keys, vals_in, vals, (int)n, 0, sort_bits(V), st));
+  tb = L.cub_bytes;
+  CDC_CHECK(cudaMemsetAsync(cnt, 0, n * 4, st));
+  CDC_CHECK(cub::DeviceRunLengthEncode::Encode(tmp, tb, keys, uniq, cnt, nuniq, (int)n, st));
+  tb = L.cub_bytes;
+  CDC_CHECK(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, start, (int)n, st));
+  g_launches.fetch_add(4, std::memory_order_relaxed);   // CUB: sort passes + RLE + scan (lower bound)
+  CDC_CHECK(cudaMemsetAsync(seg_of_row, 0xFF, (size_t)V * 4, st));
+  CDC_CHECK(cudaMemsetAsync(at<void>(plan, L.off_nlong), 0, 16, st));
+  plan_segments_kernel<<<grid_for(n, 256), 256, 0, st>>>(uniq, cnt, nuniq, V, seg_of_row, at<int32_t>(plan, L.off_long_slot),
+                                                         at<int32_t>(plan, L.off_nlong), at<int32_t>(plan, L.off_long_seg));
+  CDC_LAUNCHED();
+  return 0;
+}
+
+namespace cdcmdr {
+// host copy of the layout is recomputed from (B*F, V, E_max) - the plan header on the device is informational
+static int launch_long(const float* grad_out, int64_t ldg, const void* plan, const EmbedPlan& L, int F, int E, cudaStream_t st) {
+  const int lanes = (E % 4 == 0) ? E / 4 : E;
+  CDC_REQUIRE(lanes <= kLongThreads, "embed_dim too large for the long-segment kernel");
+  const size_t smem = (size_t)(kLongThreads / lanes) * E * sizeof(float);
+  CDC_REQUIRE(smem <= 48 * 1024, "embed_dim too large for the long-segment kernel");
+  const int grid = (int)(L.n_long_max < 4 * kNumSMs ? L.n_long_max : 4 * kNumSMs);
+  if (E % 4 == 0)
+    long_segment_kernel<4><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
+        at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_nlong), at<float>(plan, L.off_long_sum));
+  else
+    long_segment_kernel<1><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
+        at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_nlong), at<float>(plan, L.off_long_sum));
+  CDC_LAUNCHED();
+  return 0;
+}
+}  // namespace cdcmdr
+
+extern "C" int cdcmdr_embed_bwd_dense(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F, int E,
+                                      int64_t V, float* grad_table, cdcmdr_stream_t s) {
+  CDC_REQUIRE(E <= E_max, "E exceeds the plan's E_max");
+  EmbedPlan L = make_layout(B * F, V, E_max);
+  cudaStream_t st = to_stream(s);
+  if (int rc = launch_long(grad_out, ldg, plan, L, F, E, st)) return rc;
+  const int lanes = (E % 4 == 0) ? E / 4 : E;
+  const int grid = grid_for(V * lanes, 256);
+#define ARGS grad_out, ldg, F, E, V, at<int32_t>(plan, L.off_seg_of_row), at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start), \
+             at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_slot), at<float>(plan, L.off_long_sum), grad_table
+  if (E % 4 == 0) embed_dense_grad_kernel<4><<<grid, 256, 0, st>>>(ARGS);
+  else embed_dense_grad_kernel<1><<<grid, 256, 0, st>>>(ARGS);
+#undef ARGS
+  CDC_LAUNCHED();
+  return 0;
+}
+
+static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F, int E,
+                           int64_t V, float* table, float* m, float* v, const cdcmdr_adam_t* h, double* reg_sumsq,
+                           cdcmdr_stream_t s) {
+  CDC_REQUIRE(E <= E_max, "E exceeds the plan's E_max");
+  CDC_REQUIRE(h && h->step >= 1, "Adam step must be >= 1");
+  EmbedPlan L = make_layout(B * F, V, E_max);
+  cudaStream_t st = to_stream(s);
+  if (int rc = launch_long(grad_out, ldg, plan, L, F, E, st)) return rc;
+  const AdamK k = make_adam(h);
+  const int lanes = (E % 4 == 0) ? E / 4 : E;
+  const int64_t rows = dense ? V : B * F;
+  int grid = grid_for(rows * lanes, 256);
+  if (grid > kRegPartials) grid = kRegPartials;
+  double* partials = (reg_sumsq && dense) ? at<double>(plan, L.off_reg) : nullptr;
+#define ARGS grad_out, ldg, F, E, V, at<int32_t>(plan, L.off_seg_of_row), at<uint32_t>(plan, L.off_uniq), at<int32_t>(plan, L.off_nuniq), \
+             at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start), at<int32_t>(plan, L.off_cnt),                                  \
+             at<int32_t>(plan, L.off_long_slot), at<float>(plan, L.off_long_sum), table, m, v, k, partials
+  if (dense) {
+    if (E % 4 == 0) embed_adam_kernel<4, true><<<grid, 256, 0, st>>>(ARGS);
+    else embed_adam_kernel<1, true><<<grid, 256, 0, st>>>(ARGS);
+  } else {
+    if (E % 4 == 0) embed_adam_kernel<4, false><<<grid, 256, 0, st>>>(ARGS);
+    else embed_adam_kernel<1, false><<<grid, 256, 0, st>>>(ARGS);
+  }
+#undef ARGS
+  CDC_LAUNCHED();
+  if (partials) {
+    reg_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, reg_sumsq);
+    CDC_LAUNCHED();
+  }
+  return 0;
+}
+
+extern "C" int cdcmdr_embed_bwd_adam_dense_exact(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
+                                                 int E, int64_t V, float* table, float* m, float* v, const cdcmdr_adam_t* h,
+                                                 double* reg_sumsq, cdcmdr_stream_t s) {
+  return embed_adam_impl(true, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, h, reg_sumsq, s);
+}
+extern "C" int cdcmdr_embed_bwd_adam_sparse_lazy(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
+                                                 int E, int64_t V, float* table, float* m, float* v, const cdcmdr_adam_t* h,
+                                                 cdcmdr_stream_t s) {
+  return embed_adam_impl(false, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, h, nullptr, s);
+}
