@@ -1,0 +1,171 @@
+"""ctypes binding of libcdcmdr.so (include/cdcmdr.h).  This is the ONLY compute backend of the package: if the
+shared library is missing the import of any model fails loudly - there is no CPU or PyTorch fallback.
+
+Every wrapper takes raw device addresses (ints) and sizes exactly as the C-ABI does; `check()` turns a non-zero
+status into a RuntimeError carrying cdcmdr_last_error().
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libcdcmdr.so")
+
+P = C.c_void_p
+I64 = C.c_int64
+I32 = C.c_int32
+F32 = C.c_float
+U64 = C.c_uint64
+U32 = C.c_uint32
+SZ = C.c_size_t
+INT = C.c_int
+
+
+class GemmF32(C.Structure):
+    _fields_ = [("A", P), ("Bt", P), ("C", P),
+                ("M", I64), ("N", I64), ("K", I64),
+                ("a_rs", I64), ("a_cs", I64), ("b_rs", I64), ("b_cs", I64), ("c_rs", I64),
+                ("G", I32), ("a_gs", I64), ("b_gs", I64), ("c_gs", I64),
+                ("bias", P), ("bias_gs", I64),
+                ("act", I32),
+                ("mask", P), ("mask_rs", I64), ("mask_gs", I64), ("mask_scale", F32),
+                ("drop_p", F32), ("seed_dev", P), ("salt", U32),
+                ("accumulate", I32),
+                ("split_k", I32), ("workspace", P)]
+
+
+class GemmBf16(C.Structure):
+    _fields_ = [("A", P), ("lda", I64), ("a_rows", I64),
+                ("Bt", P), ("ldb", I64), ("b_rows", I64),
+                ("M", I64), ("N", I64), ("K", I64),
+                ("G", I32), ("a_gk", I64), ("a_gm", I64), ("b_gn", I64), ("b_gk", I64),
+                ("a_mn_major", I32), ("b_mn_major", I32),
+                ("bias", P), ("bias_gs", I64),
+                ("n_main", I64),
+                ("out_main", P), ("ld_main", I64), ("main_gn", I64),
+                ("out_aux", P), ("ld_aux", I64), ("aux_gn", I64),
+                ("act", I32),
+                ("mask", P), ("ld_mask", I64), ("mask_gn", I64), ("mask_scale", F32),
+                ("drop_p", F32), ("seed_dev", P), ("salt", U32),
+                ("split_k", I32), ("aux_split_stride", I64),
+                ("block_n", I32)]
+
+
+class MixDesc(C.Structure):
+    _fields_ = [("n_gates", I32), ("n_experts", I32), ("h", I32), ("max_sel", I32),
+                ("gate_col", P), ("gate_n", P), ("gate_sel", P)]
+
+
+class BnDesc(C.Structure):
+    _fields_ = [("gamma", P), ("beta", P), ("gamma2", P), ("beta2", P),
+                ("running_mean", P), ("running_var", P),
+                ("save_mean", P), ("save_invstd", P),
+                ("train", I32), ("relu", I32),
+                ("drop_p", F32), ("seed_dev", P), ("salt", U32)]
+
+
+STEP_STATE_BYTES = 48
+STEP_STATE_SEED_OFFSET = 8
+
+# name -> (restype, argtypes).  Must list every symbol include/cdcmdr.h declares (tests check this).
+SIGNATURES = {
+    "cdcmdr_last_error": (C.c_char_p, []),
+    "cdcmdr_version": (INT, []),
+    "cdcmdr_launch_count": (I64, []),
+    "cdcmdr_launch_count_reset": (None, []),
+    "cdcmdr_step_state_init": (INT, [P, I64, P]),
+    "cdcmdr_step_tick": (INT, [P, F32, F32, F32, F32, F32, U64, P]),
+    "cdcmdr_embed_gather_fwd": (INT, [P, P, P, P, P, I64, I64, INT, INT, I64, P, P]),
+    "cdcmdr_embed_plan_bytes": (SZ, [I64, I64, INT]),
+    "cdcmdr_embed_plan_build": (INT, [P, P, I64, INT, I64, INT, P, SZ, P]),
+    "cdcmdr_embed_bwd_dense": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P]),
+    "cdcmdr_embed_bwd_adam_dense_exact": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P, P]),
+    "cdcmdr_embed_bwd_adam_sparse_lazy": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P]),
+    "cdcmdr_gemm_f32": (INT, [C.POINTER(GemmF32), P]),
+    "cdcmdr_gate_mix_fwd": (INT, [C.POINTER(MixDesc), P, I64, P, I64, P, I64, P, I64, INT, P]),
+    "cdcmdr_gate_mix_bwd": (INT, [C.POINTER(MixDesc), P, I64, P, P, I64, P, I64, F32, P, I64, I64, INT, P]),
+    "cdcmdr_bn_scratch_bytes": (SZ, [I64]),
+    "cdcmdr_bn_fwd": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, I64, I64, P, P]),
+    "cdcmdr_bn_bwd": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, P, I64, P, I64, P, P, INT, I64, I64, P, P]),
+    "cdcmdr_sigmoid_select_bce": (INT, [P, P, I64, I64, I32, I32, P, I32, P, INT, P, P, P, P, P, I64, F32, P, P]),
+    "cdcmdr_sigmoid_bwd": (INT, [P, P, P, P, I64, I64, I32, P]),
+    "cdcmdr_reg_l2_sum": (INT, [P, P, F32, I64, P, P, P]),
+    "cdcmdr_reduce_scratch_bytes": (SZ, []),
+    "cdcmdr_reg_l2_grad": (INT, [P, P, F32, F32, P, INT, I64, P]),
+    "cdcmdr_relu_mask_f32": (INT, [P, I64, P, I64, P, I64, I64, I64, F32, P]),
+    "cdcmdr_adam_dense": (INT, [P, P, P, P, P, P, I64, P, P]),
+    "cdcmdr_colsum": (INT, [P, I64, INT, I64, I64, P, INT, P, P]),
+    "cdcmdr_colsum_scratch_bytes": (SZ, [I64]),
+    "cdcmdr_cast_f32_bf16": (INT, [P, I64, P, I64, I64, I64, P]),
+    "cdcmdr_cast_bf16_f32": (INT, [P, I64, P, I64, I64, I64, INT, P]),
+    "cdcmdr_ewise_f32": (INT, [P, P, P, I64, INT, P]),
+    "cdcmdr_add2d_f32": (INT, [P, I64, P, I64, I64, I64, INT, P]),
+    "cdcmdr_cross_fuse_fwd": (INT, [P, P, P, INT, P, P, I64, I64, P]),
+    "cdcmdr_cross_fuse_bwd": (INT, [P, P, INT, P, P, P, I64, I64, P]),
+    "cdcmdr_crossmix_combine_fwd": (INT, [P, P, P, P, P, P, I64, I64, INT, P]),
+    "cdcmdr_crossmix_combine_bwd": (INT, [P, P, P, P, P, P, P, P, I64, I64, INT, P]),
+    "cdcmdr_tanh_fwd": (INT, [P, I64, P]),
+    "cdcmdr_tanh_bwd": (INT, [P, P, I64, P]),
+    "cdcmdr_softmax_rows_fwd": (INT, [P, I64, P, I64, I64, INT, P]),
+    "cdcmdr_softmax_rows_bwd": (INT, [P, I64, P, I64, P, I64, I64, INT, P]),
+    "cdcmdr_route_scratch_bytes": (SZ, [I64, INT]),
+    "cdcmdr_route_partition": (INT, [P, I64, INT, P, P, P, P, P]),
+    "cdcmdr_permute_rows": (INT, [P, I64, P, I64, I64, INT, P, I64, INT, P]),
+    "cdcmdr_domain_to_group": (INT, [P, I64, INT, INT, P, INT, P, P]),
+}
+
+# entry points that return a status code (everything that launches work)
+_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is INT and k != "cdcmdr_version"}
+
+
+class CdcmdrError(RuntimeError):
+    pass
+
+
+class Lib:
+    """Thin object over the loaded shared library: `lib.<name-without-prefix>(*args)` calls the C entry point and
+    raises CdcmdrError on a non-zero status."""
+
+    def __init__(self, path: str = LIB_PATH):
+        if not os.path.exists(path):
+            raise CdcmdrError(
+                f"{path} is missing: build it with `python __graft_entry__.py build` (nvcc, sm_100a). "
+                "This package has no CPU / PyTorch fallback.")
+        self.path = path
+        self._dll = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(self._dll, name)          # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+            short = name[len("cdcmdr_"):]
+            setattr(self, short, self._wrap(name, fn) if name in _STATUS else fn)
+
+    def _wrap(self, name, fn):
+        last_error = self._dll.cdcmdr_last_error
+
+        def call(*args):
+            rc = fn(*args)
+            if rc != 0:
+                raise CdcmdrError(f"{name} failed ({rc}): {last_error().decode(errors='replace')}")
+            return rc
+        call.__name__ = name
+        return call
+
+
+_LIB = None
+
+
+def load() -> Lib:
+    """The process-wide library handle (tests may install an emulator with `install`)."""
+    global _LIB
+    if _LIB is None:
+        _LIB = Lib()
+    return _LIB
+
+
+def install(lib) -> None:
+    """Replace the process-wide handle.  Used ONLY by tests/ to run the host logic against the host-memory
+    emulator of the C-ABI (oracle/host_abi.py); never called by the package."""
+    global _LIB
+    _LIB = lib

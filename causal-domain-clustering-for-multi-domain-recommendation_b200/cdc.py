@@ -1,0 +1,137 @@
+"""CDC model part (reference model/cdc.py:24-119, 343-357) on libcdcmdr.so: a base multi-tower model (PLE / MMoE / STAR)
+plus the domain -> cluster routing of its towers.
+
+  forward(x, mode='warmup')                 mean over towers                            cdc.py:99-102
+  forward(x, mode='split', domain_i=None)   per-sample tower domain2group[x[:, domain_idx]]   cdc.py:104-107
+  forward(x, mode='split', domain_i=d)      fixed tower domain2group_list[d]            cdc.py:108-111
+  train_step(...)                           the same three modes fused into the sigmoid+BCE kernel (run.py:635-640)
+
+The clustering itself (update_group: affinity matrices -> causal kernel -> k-means / regrouping, cdc.py:121-341) is
+host-side float64 NumPy in the reference, runs once per `update_interval` steps and is a "next" row;
+it is not part of this package yet - `update_group` raises."""
+from __future__ import annotations
+
+import copy
+import re
+
+import torch
+
+from .layer import BaseModel
+from .mmoe import MMoE
+from .ple import PLE
+
+
+class CDC(BaseModel):
+    def __init__(self, feature_dims, embed_dim, n_tower, n_domain, base_model, expert_dims, tower_dims, domain_idx,
+                 domain_cnt_weight=None, n_causal_mask=50, use_metric='loss', device='cpu', dropout=0.2, config=None,
+                 savefig_folder='', l2_reg_embedding=1e-5, l2_reg_linear=1e-5, l2_reg_dnn=1e-5, l2_reg_cross=1e-5):
+        super(BaseModel, self).__init__()          # like the reference: CDC owns no embedding of its own (cdc.py:29)
+        self.model_name = 'cdc'
+        self.base_model = base_model
+        if base_model == 'mmoe':
+            self.base_model_instance = MMoE(feature_dims, embed_dim, n_tower, config.mmoe_n_expert, expert_dims, tower_dims,
+                                            dropout, config, l2_reg_embedding, l2_reg_linear, l2_reg_dnn, l2_reg_cross,
+                                            model_name=self.model_name)
+        elif base_model == 'ple':
+            self.base_model_instance = PLE(feature_dims, embed_dim, n_tower, config.ple_n_expert_specific,
+                                           config.ple_n_expert_shared, expert_dims, tower_dims, dropout, config,
+                                           l2_reg_embedding, l2_reg_linear, l2_reg_dnn, l2_reg_cross,
+                                           model_name=self.model_name)
+        elif base_model == 'star':
+            from .star import STAR
+            self.base_model_instance = STAR(feature_dims, embed_dim, n_tower, tower_dims, domain_idx, dropout, config,
+                                            l2_reg_embedding, l2_reg_linear, l2_reg_dnn, l2_reg_cross, device)
+        else:
+            raise NotImplementedError(f"CDC base model '{base_model}' is outside the hot path (SURVEY §2: pepnet/epnet)")
+        self.device = device
+        self.config = config
+        self.n_cluster = n_tower
+        self.n_causal_mask = n_causal_mask
+        self.n_domain = n_domain
+        self.domain_idx = domain_idx
+        dcw = domain_cnt_weight if domain_cnt_weight is not None else [1.0 / n_domain] * n_domain
+        self.domain_cnt_weight = torch.tensor(dcw, dtype=torch.float32, device=device)
+        self.domain2group = torch.zeros(n_domain, dtype=torch.int64, device=device)
+        self.domain2group_list = [0] * n_domain
+        self.s_group2domain_list = [list(range(n_domain))]
+        self.t_group2domain_list = [list(range(n_domain))]
+        self.matrix_A = torch.zeros((n_domain + 1, n_domain), dtype=torch.float32, device=device)
+        self.matrix_B = torch.zeros((n_domain + self.n_cluster, n_domain), dtype=torch.float32, device=device)
+        self.matrix_mask = torch.zeros((n_causal_mask, n_domain), dtype=torch.float32, device=device)
+        self.matrix_causal = torch.zeros((n_causal_mask, n_domain), dtype=torch.float32, device=device)
+        self.use_metric = use_metric
+        self.model_state = None
+
+    # ---------------------------------------------------------------- grouping state
+    def set_groups(self, domain2group_list):
+        """Install a domain -> cluster assignment (what update_group computes, cdc.py:236-238)."""
+        d2g = [int(g) for g in domain2group_list]
+        if len(d2g) != self.n_domain or min(d2g) < 0 or max(d2g) >= self.n_cluster:
+            raise ValueError("domain2group must map every domain to a cluster in [0, n_cluster)")
+        self.domain2group_list = d2g
+        self.domain2group = torch.tensor(d2g, dtype=torch.int64, device=self.domain2group.device)
+
+    def _apply(self, fn, recurse=True):
+        out = torch.nn.Module._apply(self, fn)
+        dev = next(self.base_model_instance.parameters()).device
+        for k in ("domain2group", "domain_cnt_weight", "matrix_A", "matrix_B", "matrix_mask", "matrix_causal"):
+            setattr(self, k, getattr(self, k).to(dev))            # plain attributes in the reference (cdc.py:66-76)
+        return out
+
+    # ---------------------------------------------------------------- forward (cdc.py:95-111)
+    def forward(self, x, mode='split', domain_i=None):
+        base = self.base_model_instance
+        y_cat = base._call(x)
+        if mode == 'warmup':
+            return torch.mean(y_cat, dim=1)
+        if mode == 'split':
+            if domain_i is None:
+                return y_cat.gather(1, self._groups_of(x).unsqueeze(1))
+            return y_cat[:, self.domain2group_list[domain_i]]
+        raise ValueError(f"unknown CDC mode {mode!r}")
+
+    def _groups_of(self, x):
+        base = self.base_model_instance
+        rt = base._rt
+        B = x.shape[0]
+        groups = torch.empty(B, dtype=torch.int64, device=x.device)
+        d2g = self.domain2group.to(x.device)
+        rt.ops.lib.domain_to_group(x.data_ptr(), B, x.shape[1], self.domain_idx, d2g.data_ptr(), self.n_domain,
+                                   groups.data_ptr(), rt.ops.stream)
+        return groups
+
+    def train_step(self, x, y, optimizer, mode='split', domain_i=None):
+        """run.py:616-622 (warmup) / 635-640 (split), fused."""
+        base = self.base_model_instance
+        if not self.training:
+            raise RuntimeError("train_step() needs model.train()")
+        if mode == 'warmup':
+            return base.train_step(x, y, optimizer, mode="mean")
+        if mode != 'split':
+            raise ValueError(f"unknown CDC mode {mode!r}")
+        if domain_i is None:
+            base._check_device(x)
+            return base.train_step(x, y, optimizer, mode="gather", sel=self._groups_of(x.contiguous()))
+        return base.train_step(x, y, optimizer, mode="col", col=self.domain2group_list[domain_i])
+
+    step_losses = staticmethod(BaseModel.step_losses)
+
+    def get_regularization_loss(self, device=None):
+        return self.base_model_instance.get_regularization_loss(device)
+
+    def get_matrix_metric(self, preds, targets):
+        if self.use_metric != 'loss':
+            raise NotImplementedError("use_metric='auc' runs sklearn on the host in the reference (cdc.py:116-119)")
+        return torch.nn.functional.binary_cross_entropy(preds, targets).detach()
+
+    # ---------------------------------------------------------------- snapshot / restore (cdc.py:343-354)
+    def save_model_state(self):
+        pattern = re.compile('^(base_model_instance)')
+        self.model_state = copy.deepcopy({k: v for k, v in self.state_dict().items() if pattern.match(k)})
+
+    def load_model_state(self):
+        self.load_state_dict(self.model_state, strict=False)
+
+    def update_group(self, mode='iterative'):
+        raise NotImplementedError("CDC.update_group (host-side clustering, cdc.py:121-341) is a 'next' row (SURVEY §8f N4); "
+                                  "install assignments with set_groups()")

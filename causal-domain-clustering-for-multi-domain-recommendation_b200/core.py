@@ -1,0 +1,238 @@
+"""Host-side runtime shared by every model: matrix views over torch storage (device memory only - torch is used for
+allocation, streams and state_dict plumbing, never for arithmetic), the per-batch-size workspace, and typed wrappers
+that marshal arguments for the C-ABI of libcdcmdr.so.
+
+Nothing in this file computes: every wrapper ends in exactly one `lib.<entry point>` call.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import BnDesc, GemmF32, MixDesc
+
+
+def _addr(t: torch.Tensor, off: int = 0) -> int:
+    return t.data_ptr() + off * t.element_size()
+
+
+@dataclass(frozen=True)
+class Mat:
+    """A row-major [rows, cols] window into a flat tensor: element (r, c) lives at t[off + r*ld + c]."""
+    t: torch.Tensor
+    off: int
+    ld: int
+
+    @property
+    def ptr(self) -> int:
+        return _addr(self.t, self.off)
+
+    def cols(self, c0: int) -> "Mat":
+        return Mat(self.t, self.off + c0, self.ld)
+
+    def rows(self, r0: int) -> "Mat":
+        return Mat(self.t, self.off + r0 * self.ld, self.ld)
+
+    @property
+    def is_bf16(self) -> bool:
+        return self.t.dtype == torch.bfloat16
+
+
+class Workspace:
+    """Named device buffers for one batch size; allocated once, reused by every step (graph-capturable)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.bufs = {}
+
+    def get(self, name, shape, dtype=torch.float32, zero=False) -> torch.Tensor:
+        key = name
+        t = self.bufs.get(key)
+        n = 1
+        for s in shape:
+            n *= int(s)
+        if t is None or t.numel() < n or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(max(n, 1), dtype=dtype, device=self.device)
+            self.bufs[key] = t
+        return t
+
+    def mat(self, name, rows, cols, dtype=torch.float32, zero=False) -> Mat:
+        return Mat(self.get(name, (rows, cols), dtype, zero), 0, cols)
+
+    def nbytes(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.bufs.values())
+
+
+class Ops:
+    """Argument marshalling for the C-ABI.  One instance per model (holds the device, the current stream getter
+    and the shared scratch buffers)."""
+
+    def __init__(self, device):
+        self.lib = _lib.load()
+        self.device = torch.device(device)
+        self._scratch = {}
+        self.launches = 0
+
+    # ---------------------------------------------------------------- plumbing
+    @property
+    def stream(self) -> int:
+        if self.device.type == "cuda":
+            return torch.cuda.current_stream(self.device).cuda_stream
+        return 0
+
+    def scratch(self, name, nbytes) -> torch.Tensor:
+        t = self._scratch.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+            self._scratch[name] = t
+        return t
+
+    # ---------------------------------------------------------------- step state
+    def step_state_new(self) -> torch.Tensor:
+        st = torch.zeros(_lib.STEP_STATE_BYTES, dtype=torch.uint8, device=self.device)
+        self.lib.step_state_init(st.data_ptr(), 0, self.stream)
+        return st
+
+    def step_state_set(self, st, step: int):
+        self.lib.step_state_init(st.data_ptr(), int(step), self.stream)
+
+    def step_tick(self, st, lr, betas, eps, wd, base_seed):
+        self.lib.step_tick(st.data_ptr(), lr, betas[0], betas[1], eps, wd, int(base_seed) & (2 ** 64 - 1), self.stream)
+
+    @staticmethod
+    def seed_ptr(st) -> int:
+        return st.data_ptr() + _lib.STEP_STATE_SEED_OFFSET
+
+    # ---------------------------------------------------------------- embedding
+    def embed_gather(self, x, offsets, table, out_f32: Mat | None, out_bf16: Mat | None, B, F, E, V, oob=None):
+        self.lib.embed_gather_fwd(x.data_ptr(), offsets.data_ptr(), table.data_ptr(),
+                                  out_f32.ptr if out_f32 is not None else None,
+                                  out_bf16.ptr if out_bf16 is not None else None,
+                                  out_bf16.ld if out_bf16 is not None else 0,
+                                  B, F, E, V, oob.data_ptr() if oob is not None else None, self.stream)
+
+    def embed_plan(self, x, offsets, B, F, V, E) -> torch.Tensor:
+        nbytes = self.lib.embed_plan_bytes(B * F, V, E)
+        plan = self.scratch(f"embed_plan_{B}", nbytes)
+        self.lib.embed_plan_build(x.data_ptr(), offsets.data_ptr(), B, F, V, E, plan.data_ptr(), plan.numel(), self.stream)
+        return plan
+
+    def embed_bwd_dense(self, grad_out: Mat, plan, B, F, E, V, grad_table):
+        self.lib.embed_bwd_dense(grad_out.ptr, grad_out.ld, plan.data_ptr(), E, B, F, E, V, grad_table.data_ptr(), self.stream)
+
+    def embed_bwd_adam(self, grad_out: Mat, plan, B, F, E, V, table, m, v, l2, st, reg_sumsq=None, lazy=False):
+        if lazy:
+            self.lib.embed_bwd_adam_sparse_lazy(grad_out.ptr, grad_out.ld, plan.data_ptr(), E, B, F, E, V, table.data_ptr(),
+                                                m.data_ptr(), v.data_ptr(), l2, st.data_ptr(), self.stream)
+        else:
+            self.lib.embed_bwd_adam_dense_exact(grad_out.ptr, grad_out.ld, plan.data_ptr(), E, B, F, E, V, table.data_ptr(),
+                                                m.data_ptr(), v.data_ptr(), l2, st.data_ptr(),
+                                                reg_sumsq.data_ptr() if reg_sumsq is not None else None, self.stream)
+
+    # ---------------------------------------------------------------- fp32 GEMM
+    def gemm_f32(self, *, A, a_rs, a_cs, Bt, b_rs, b_cs, Cm, c_rs, M, N, K, G=1, a_gs=0, b_gs=0, c_gs=0,
+                 bias=None, bias_gs=0, act=0, mask=None, mask_rs=0, mask_gs=0, mask_scale=1.0,
+                 drop_p=0.0, seed_ptr=None, salt=0, accumulate=0, split_k=1):
+        """A, Bt, Cm, bias, mask are raw addresses (ints)."""
+        if M <= 0 or N <= 0 or G <= 0:
+            return
+        wsp = None
+        if split_k > 1:
+            wsp = self.scratch("splitk", 4 * split_k * G * M * N).data_ptr()
+        d = GemmF32(A, Bt, Cm, M, N, K, a_rs, a_cs, b_rs, b_cs, c_rs, G, a_gs, b_gs, c_gs, bias, bias_gs, act,
+                    mask, mask_rs, mask_gs, mask_scale, drop_p, seed_ptr if drop_p > 0 else None, salt, accumulate,
+                    split_k, wsp)
+        self.lib.gemm_f32(C.byref(d), self.stream)
+
+    @staticmethod
+    def pick_split(M, N, G, K, target_ctas=592, min_k=256):
+        ctas = ((M + 63) // 64) * ((N + 63) // 64) * G
+        if ctas >= target_ctas or K < 2 * min_k:
+            return 1
+        s = min((target_ctas + ctas - 1) // ctas, K // min_k, 64)
+        return max(1, int(s))
+
+    # ---------------------------------------------------------------- gate mix
+    def mix_desc(self, n_gates, n_experts, h, max_sel, desc_t: torch.Tensor) -> MixDesc:
+        """desc_t: int32 device tensor laid out [gate_col(n_gates) | gate_n(n_gates) | gate_sel(n_gates*max_sel)]."""
+        base = desc_t.data_ptr()
+        return MixDesc(n_gates, n_experts, h, max_sel, base, base + 4 * n_gates, base + 8 * n_gates)
+
+    def gate_mix_fwd(self, d: MixDesc, H: Mat, logits: Mat, out: Mat, probs: torch.Tensor, B):
+        self.lib.gate_mix_fwd(C.byref(d), H.ptr, H.ld, logits.ptr, logits.ld, out.ptr, out.ld, probs.data_ptr(), B,
+                              1 if H.is_bf16 else 0, self.stream)
+
+    def gate_mix_bwd(self, d: MixDesc, H: Mat, probs, dOut: Mat, dH: Mat, relu_scale, dlogits: Mat, B):
+        self.lib.gate_mix_bwd(C.byref(d), H.ptr, H.ld, probs.data_ptr(), dOut.ptr, dOut.ld, dH.ptr, dH.ld, relu_scale,
+                              dlogits.ptr, dlogits.ld, B, 1 if H.is_bf16 else 0, self.stream)
+
+    # ---------------------------------------------------------------- batch norm
+    def bn_desc(self, gamma, beta, rmean, rvar, save_mean, save_invstd, train, relu, gamma2=None, beta2=None,
+                drop_p=0.0, seed_ptr=None, salt=0) -> BnDesc:
+        return BnDesc(gamma, beta, gamma2, beta2, rmean, rvar, save_mean, save_invstd, 1 if train else 0,
+                      1 if relu else 0, drop_p, seed_ptr if drop_p > 0 else None, salt)
+
+    def bn_fwd(self, d: BnDesc, Z: Mat, A: Mat, B, Cn):
+        sc = self.scratch("bn", self.lib.bn_scratch_bytes(Cn))
+        self.lib.bn_fwd(C.byref(d), Z.ptr, Z.ld, A.ptr, A.ld, 1 if A.is_bf16 else 0, B, Cn, sc.data_ptr(), self.stream)
+
+    def bn_bwd(self, d: BnDesc, Z: Mat, A: Mat | None, dA: Mat, dZ: Mat, dgamma, dbeta, accumulate, B, Cn):
+        sc = self.scratch("bn", self.lib.bn_scratch_bytes(Cn))
+        self.lib.bn_bwd(C.byref(d), Z.ptr, Z.ld, A.ptr if A is not None else None, A.ld if A is not None else 0,
+                        1 if (A is not None and A.is_bf16) else 0, dA.ptr, dA.ld, dZ.ptr, dZ.ld, dgamma, dbeta,
+                        1 if accumulate else 0, B, Cn, sc.data_ptr(), self.stream)
+
+    # ---------------------------------------------------------------- loss
+    def sigmoid_select_bce(self, logits, lin: Mat | None, B, T, mode, sel, col, target, pred, psel, loss_sum, dlogits,
+                           dlin: Mat | None, inv_batch):
+        sc = self.scratch("reduce", self.lib.reduce_scratch_bytes())
+        tf32 = 0
+        tptr = None
+        if target is not None:
+            if target.dtype == torch.float32:
+                tf32 = 1
+            elif target.dtype != torch.int16:
+                raise TypeError("targets must be int16 or float32")
+            tptr = target.data_ptr()
+        self.lib.sigmoid_select_bce(logits.data_ptr(), lin.ptr if lin is not None else None, lin.ld if lin is not None else 0,
+                                    B, T, mode, sel.data_ptr() if sel is not None else None, col, tptr, tf32,
+                                    pred.data_ptr(), psel.data_ptr() if psel is not None else None,
+                                    loss_sum.data_ptr() if loss_sum is not None else None,
+                                    dlogits.data_ptr() if dlogits is not None else None,
+                                    dlin.ptr if dlin is not None else None, dlin.ld if dlin is not None else 0,
+                                    inv_batch, sc.data_ptr(), self.stream)
+
+    def sigmoid_bwd(self, pred, dpred, dlogits, dlin: Mat | None, B, T):
+        self.lib.sigmoid_bwd(pred.data_ptr(), dpred.data_ptr(), dlogits.data_ptr(), dlin.ptr if dlin is not None else None,
+                             dlin.ld if dlin is not None else 0, B, T, self.stream)
+
+    # ---------------------------------------------------------------- regulariser / optimiser / reductions
+    def reg_l2_sum(self, w, coef, coef_scalar, n, out):
+        sc = self.scratch("reduce", self.lib.reduce_scratch_bytes())
+        self.lib.reg_l2_sum(w.data_ptr(), coef.data_ptr() if coef is not None else None, coef_scalar, n, out.data_ptr(),
+                            sc.data_ptr(), self.stream)
+
+    def reg_l2_grad(self, w, coef, coef_scalar, scale, grad, accumulate, n):
+        self.lib.reg_l2_grad(w.data_ptr(), coef.data_ptr() if coef is not None else None, coef_scalar, scale, grad.data_ptr(),
+                             1 if accumulate else 0, n, self.stream)
+
+    def relu_mask(self, dA: Mat, A: Mat, out: Mat, rows, cols, scale):
+        self.lib.relu_mask_f32(dA.ptr, dA.ld, A.ptr, A.ld, out.ptr, out.ld, rows, cols, scale, self.stream)
+
+    def adam_dense(self, w, grad, m, v, l2coef, present, n, st):
+        self.lib.adam_dense(w.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(),
+                            l2coef.data_ptr() if l2coef is not None else None,
+                            present.data_ptr() if present is not None else None, n, st.data_ptr(), self.stream)
+
+    def colsum(self, X: Mat, B, Cn, out_addr, accumulate=0):
+        sc = self.scratch("colsum", self.lib.colsum_scratch_bytes(Cn))
+        self.lib.colsum(X.ptr, X.ld, 1 if X.is_bf16 else 0, B, Cn, out_addr, accumulate, sc.data_ptr(), self.stream)
+
+    def ewise(self, a, b, out, n, op):
+        self.lib.ewise_f32(a, b, out, n, op, self.stream)
+
+    def add2d(self, a: Mat, out: Mat, rows, cols, accumulate):
+        self.lib.add2d_f32(a.ptr, a.ld, out.ptr, out.ld, rows, cols, 1 if accumulate else 0, self.stream)

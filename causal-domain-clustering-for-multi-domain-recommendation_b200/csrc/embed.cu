@@ -205,6 +205,10 @@ __global__ void embed_dense_grad_kernel(const float* __restrict__ grad_out, int6
 }
 
 struct AdamK { float lr_t, b1, b2, eps, wd, l2x2, bc2_sqrt; };
+__device__ __forceinline__ AdamK load_adam(const cdcmdr_step_state_t* st, float l2) {
+  AdamK k; k.lr_t = st->lr_t; k.b1 = st->beta1; k.b2 = st->beta2; k.eps = st->eps; k.wd = st->weight_decay;
+  k.l2x2 = 2.f * l2; k.bc2_sqrt = st->bc2_sqrt; return k;
+}
 
 __device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g, const AdamK& k) {
   g = g + k.l2x2 * w;                    // gradient of l2 * sum(w^2)                 layer.py:106-108
@@ -221,8 +225,9 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
                   const int32_t* __restrict__ seg_of_row, const uint32_t* __restrict__ uniq, const int32_t* __restrict__ nuniq,
                   const int32_t* __restrict__ vals, const int32_t* __restrict__ start, const int32_t* __restrict__ cnt,
                   const int32_t* __restrict__ long_slot, const float* __restrict__ long_sum,
-                  float* __restrict__ table, float* __restrict__ mom, float* __restrict__ var, AdamK k,
-                  double* __restrict__ reg_partials) {
+                  float* __restrict__ table, float* __restrict__ mom, float* __restrict__ var,
+                  const cdcmdr_step_state_t* __restrict__ st, float l2, double* __restrict__ reg_partials) {
+  const AdamK k = load_adam(st, l2);
   const int lanes = E / VEC;
   const int64_t rows = DENSE ? V : (int64_t)(*nuniq);
   const int64_t total = rows * lanes;
@@ -267,15 +272,6 @@ __global__ void reg_finalize_kernel(const double* __restrict__ partials, int n, 
   if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w]; *out = s; }
 }
 
-static AdamK make_adam(const cdcmdr_adam_t* h) {
-  const double bc1 = 1.0 - pow((double)h->beta1, (double)h->step);
-  const double bc2 = 1.0 - pow((double)h->beta2, (double)h->step);
-  AdamK k;
-  k.lr_t = (float)((double)h->lr / bc1); k.b1 = h->beta1; k.b2 = h->beta2; k.eps = h->eps; k.wd = h->weight_decay;
-  k.l2x2 = 2.f * h->l2; k.bc2_sqrt = (float)sqrt(bc2);
-  return k;
-}
-
 static int grid_for(int64_t work, int threads, int max_ctas_per_sm = 8) {
   int64_t g = ceil_div(work, threads);
   const int64_t cap = (int64_t)kNumSMs * max_ctas_per_sm;
@@ -316,7 +312,6 @@ extern "C" int cdcmdr_embed_plan_build(const int32_t* x, const int64_t* offsets,
   EmbedPlan L = make_layout(n, V, E_max);
   CDC_REQUIRE(plan_bytes >= L.total, "plan workspace too small");
   cudaStream_t st = to_stream(s);
-  CDC_CHECK(cudaMemcpyAsync(plan, &L, sizeof(L), cudaMemcpyHostToDevice, st));
   uint32_t* keys_in = at<uint32_t>(plan, L.off_keys_in); int32_t* vals_in = at<int32_t>(plan, L.off_vals_in);
   uint32_t* keys = at<uint32_t>(plan, L.off_keys); int32_t* vals = at<int32_t>(plan, L.off_vals);
   uint32_t* uniq = at<uint32_t>(plan, L.off_uniq); int32_t* cnt = at<int32_t>(plan, L.off_cnt);
@@ -378,14 +373,13 @@ extern "C" int cdcmdr_embed_bwd_dense(const float* grad_out, int64_t ldg, const 
 }
 
 static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F, int E,
-                           int64_t V, float* table, float* m, float* v, const cdcmdr_adam_t* h, double* reg_sumsq,
+                           int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h, double* reg_sumsq,
                            cdcmdr_stream_t s) {
   CDC_REQUIRE(E <= E_max, "E exceeds the plan's E_max");
-  CDC_REQUIRE(h && h->step >= 1, "Adam step must be >= 1");
+  CDC_REQUIRE(h, "Adam needs the device step state");
   EmbedPlan L = make_layout(B * F, V, E_max);
   cudaStream_t st = to_stream(s);
   if (int rc = launch_long(grad_out, ldg, plan, L, F, E, st)) return rc;
-  const AdamK k = make_adam(h);
   const int lanes = (E % 4 == 0) ? E / 4 : E;
   const int64_t rows = dense ? V : B * F;
   int grid = grid_for(rows * lanes, 256);
@@ -393,7 +387,7 @@ static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const
   double* partials = (reg_sumsq && dense) ? at<double>(plan, L.off_reg) : nullptr;
 #define ARGS grad_out, ldg, F, E, V, at<int32_t>(plan, L.off_seg_of_row), at<uint32_t>(plan, L.off_uniq), at<int32_t>(plan, L.off_nuniq), \
              at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start), at<int32_t>(plan, L.off_cnt),                                  \
-             at<int32_t>(plan, L.off_long_slot), at<float>(plan, L.off_long_sum), table, m, v, k, partials
+             at<int32_t>(plan, L.off_long_slot), at<float>(plan, L.off_long_sum), table, m, v, h, l2, partials
   if (dense) {
     if (E % 4 == 0) embed_adam_kernel<4, true><<<grid, 256, 0, st>>>(ARGS);
     else embed_adam_kernel<1, true><<<grid, 256, 0, st>>>(ARGS);
@@ -411,12 +405,12 @@ static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const
 }
 
 extern "C" int cdcmdr_embed_bwd_adam_dense_exact(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
-                                                 int E, int64_t V, float* table, float* m, float* v, const cdcmdr_adam_t* h,
+                                                 int E, int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h,
                                                  double* reg_sumsq, cdcmdr_stream_t s) {
-  return embed_adam_impl(true, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, h, reg_sumsq, s);
+  return embed_adam_impl(true, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, h, reg_sumsq, s);
 }
 extern "C" int cdcmdr_embed_bwd_adam_sparse_lazy(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
-                                                 int E, int64_t V, float* table, float* m, float* v, const cdcmdr_adam_t* h,
+                                                 int E, int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h,
                                                  cdcmdr_stream_t s) {
-  return embed_adam_impl(false, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, h, nullptr, s);
+  return embed_adam_impl(false, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, h, nullptr, s);
 }

@@ -12,7 +12,7 @@ struct EpiF32 {
   const float* bias; int64_t bias_gs;
   int act;
   const float* mask; int64_t mask_rs, mask_gs; float mask_scale;
-  float drop_p; uint64_t seed; uint32_t salt;
+  float drop_p; const uint64_t* seed_dev; uint32_t salt;
   int accumulate;
 };
 
@@ -22,7 +22,7 @@ __device__ __forceinline__ void epilogue_store(const EpiF32& e, int g, int64_t m
   if (e.mask) v = (e.mask[g * e.mask_gs + m * e.mask_rs + n] > 0.f) ? v * e.mask_scale : 0.f;
   if (e.drop_p > 0.f) {
     const uint64_t idx = (uint64_t)(g * e.c_gs + m * e.c_rs + n);
-    v = (mix_hash(e.seed, e.salt, idx) >= drop_threshold(e.drop_p)) ? v * (1.f / (1.f - e.drop_p)) : 0.f;
+    v = (mix_hash(*e.seed_dev, e.salt, idx) >= drop_threshold(e.drop_p)) ? v * (1.f / (1.f - e.drop_p)) : 0.f;
   }
   float* c = e.C + g * e.c_gs + m * e.c_rs + n;
   *c = e.accumulate ? (*c + v) : v;
@@ -114,8 +114,9 @@ extern "C" int cdcmdr_gemm_f32(const cdcmdr_gemm_f32_t* p, cdcmdr_stream_t s) {
   if (p->M == 0 || p->N == 0) return 0;
   const int split = p->split_k > 1 ? p->split_k : 1;
   CDC_REQUIRE(split == 1 || p->workspace, "split-K needs a workspace");
+  CDC_REQUIRE(p->drop_p <= 0.f || p->seed_dev, "dropout needs a device seed");
   EpiF32 e{p->C, p->c_rs, p->c_gs, p->bias, p->bias_gs, p->act, p->mask, p->mask_rs, p->mask_gs, p->mask_scale,
-           p->drop_p, p->seed, p->salt, p->accumulate};
+           p->drop_p, p->seed_dev, p->salt, p->accumulate};
   dim3 grid((unsigned)ceil_div(p->N, BN), (unsigned)ceil_div(p->M, BM), (unsigned)(p->G * split));
   CDC_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
   gemm_f32_kernel<<<grid, 256, 0, to_stream(s)>>>(p->A, p->Bt, p->M, p->N, p->K, p->a_rs, p->a_cs, p->b_rs, p->b_cs, p->a_gs, p->b_gs,

@@ -1,0 +1,725 @@
+// HBM-bound stages of the dense path: gate softmax + expert mix (a5/a9), BatchNorm (+ReLU, dropout) (a4/a8/a14),
+// sigmoid + tower selection + BCE (a8/a15/a17), L2 regulariser (a7), fused Adam over the parameter arena (a17),
+// column sums (bias gradients) and casts.  Every reduction is two-stage with a fixed partition -> deterministic.
+#include "common.cuh"
+
+namespace cdcmdr {
+
+// ------------------------------------------------------------------------------------------ vector helpers
+template <typename T, int VEC> struct VecIO;
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) {
+    const float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <> struct VecIO<float, 1> {
+  static __device__ __forceinline__ void load(const float* p, float (&v)[1]) { v[0] = *p; }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[1]) { *p = v[0]; }
+};
+template <> struct VecIO<uint16_t, 4> {
+  static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[4]) {
+    const uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void store(uint16_t* p, const float (&v)[4]) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  }
+};
+template <> struct VecIO<uint16_t, 1> {
+  static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[1]) { v[0] = bf16_to_f32(*p); }
+  static __device__ __forceinline__ void store(uint16_t* p, const float (&v)[1]) { *p = f32_to_bf16(v[0]); }
+};
+
+static int grid_1d(int64_t work, int threads, int max_per_sm = 8) {
+  int64_t g = ceil_div(work, threads);
+  const int64_t cap = (int64_t)kNumSMs * max_per_sm;
+  if (g > cap) g = cap;
+  return g < 1 ? 1 : (int)g;
+}
+
+constexpr int kReducePartials = 1024;       // fixed upper bound on stage-1 blocks of scalar reductions
+
+__device__ __forceinline__ double block_sum_256(double v) {   // deterministic: warp tree + ordered warp sum
+  __shared__ double red[8];
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = 0;
+  if (threadIdx.x == 0) for (int w = 0; w < 8; ++w) t += red[w];
+  return t;                                                     // valid on thread 0
+}
+
+__global__ void reduce_finalize_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  double t = 0;
+  for (int i = threadIdx.x; i < n; i += 256) t += partials[i];
+  t = block_sum_256(t);
+  if (threadIdx.x == 0) *out = t;
+}
+
+// ------------------------------------------------------------------------------------------ gate mix
+struct MixK { int n_gates, n_experts, h, max_sel; const int32_t* gate_col; const int32_t* gate_n; const int32_t* gate_sel; };
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+gate_mix_fwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* __restrict__ logits, int64_t ldl,
+                    T* __restrict__ out, int64_t ldo, float* __restrict__ probs, int64_t B) {
+  extern __shared__ float dyn[];
+  __shared__ int s_col[32], s_n[32], s_sel[1024];
+  const int np = d.n_gates * d.max_sel;
+  for (int i = threadIdx.x; i < d.n_gates; i += blockDim.x) { s_col[i] = d.gate_col[i]; s_n[i] = d.gate_n[i]; }
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s_sel[i] = d.gate_sel[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sp = dyn + warp * np;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < B; row += (int64_t)gridDim.x * 8) {
+    if (lane < d.n_gates) {
+      const int n = s_n[lane];
+      const float* lg = logits + row * ldl + s_col[lane];
+      float mx = -INFINITY;
+      for (int s = 0; s < n; ++s) mx = fmaxf(mx, lg[s]);
+      float sum = 0.f;
+      for (int s = 0; s < n; ++s) { const float e = expf(lg[s] - mx); sp[lane * d.max_sel + s] = e; sum += e; }
+      float* pr = probs + row * np + lane * d.max_sel;
+      for (int s = 0; s < d.max_sel; ++s) {
+        const float p = s < n ? sp[lane * d.max_sel + s] / sum : 0.f;
+        sp[lane * d.max_sel + s] = p; pr[s] = p;
+      }
+    }
+    __syncwarp();
+    for (int c = lane * VEC; c < d.h; c += 32 * VEC) {
+      for (int j = 0; j < d.n_gates; ++j) {
+        float acc[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+        const int n = s_n[j];
+        for (int s = 0; s < n; ++s) {
+          float hv[VEC];
+          VecIO<T, VEC>::load(H + row * ldh + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
+          const float p = sp[j * d.max_sel + s];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] = fmaf(p, hv[q], acc[q]);
+        }
+        VecIO<T, VEC>::store(out + row * ldo + (int64_t)j * d.h + c, acc);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* __restrict__ probs,
+                    const T* __restrict__ dOut, int64_t ldo, T* __restrict__ dH, int64_t lddh, float relu_scale,
+                    float* __restrict__ dlogits, int64_t lddl, int64_t B) {
+  extern __shared__ float dyn[];
+  __shared__ int s_col[32], s_n[32], s_sel[1024], s_inv_cnt[64], s_inv[64 * 32];
+  const int np = d.n_gates * d.max_sel;
+  for (int i = threadIdx.x; i < d.n_gates; i += blockDim.x) { s_col[i] = d.gate_col[i]; s_n[i] = d.gate_n[i]; }
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s_sel[i] = d.gate_sel[i];
+  __syncthreads();
+  if (threadIdx.x < d.n_experts) {                       // inverse map expert -> (gate, slot) pairs, gate-ascending
+    int cnt = 0;
+    for (int j = 0; j < d.n_gates; ++j)
+      for (int s = 0; s < s_n[j]; ++s)
+        if (s_sel[j * d.max_sel + s] == (int)threadIdx.x) s_inv[threadIdx.x * 32 + cnt++] = j * d.max_sel + s;
+    s_inv_cnt[threadIdx.x] = cnt;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* sp = dyn + (warp * 2) * np;
+  float* sd = sp + np;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < B; row += (int64_t)gridDim.x * 8) {
+    for (int k = lane; k < np; k += 32) sp[k] = probs[row * np + k];
+    __syncwarp();
+    for (int j = 0; j < d.n_gates; ++j) {
+      const int n = s_n[j];
+      for (int s = 0; s < n; ++s) {
+        float part = 0.f;
+        for (int c = lane * VEC; c < d.h; c += 32 * VEC) {
+          float dv[VEC], hv[VEC];
+          VecIO<T, VEC>::load(dOut + row * ldo + (int64_t)j * d.h + c, dv);
+          VecIO<T, VEC>::load(H + row * ldh + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) part = fmaf(dv[q], hv[q], part);
+        }
+        part = warp_sum(part);
+        if (lane == 0) sd[j * d.max_sel + s] = part;
+      }
+    }
+    __syncwarp();
+    if (lane < d.n_gates) {
+      const int n = s_n[lane];
+      float dot = 0.f;
+      for (int s = 0; s < n; ++s) dot = fmaf(sp[lane * d.max_sel + s], sd[lane * d.max_sel + s], dot);
+      float* dz = dlogits + row * lddl + s_col[lane];
+      for (int s = 0; s < n; ++s) dz[s] = sp[lane * d.max_sel + s] * (sd[lane * d.max_sel + s] - dot);
+    }
+    for (int c = lane * VEC; c < d.h; c += 32 * VEC) {
+      for (int e = 0; e < d.n_experts; ++e) {
+        float acc[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+        const int cnt = s_inv_cnt[e];
+        for (int i = 0; i < cnt; ++i) {
+          const int k = s_inv[e * 32 + i];
+          float dv[VEC];
+          VecIO<T, VEC>::load(dOut + row * ldo + (int64_t)(k / d.max_sel) * d.h + c, dv);
+          const float p = sp[k];
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] = fmaf(p, dv[q], acc[q]);
+        }
+        if (relu_scale > 0.f) {
+          float hv[VEC];
+          VecIO<T, VEC>::load(H + row * ldh + (int64_t)e * d.h + c, hv);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[q] = hv[q] > 0.f ? acc[q] * relu_scale : 0.f;
+        }
+        VecIO<T, VEC>::store(dH + row * lddh + (int64_t)e * d.h + c, acc);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------ column reductions
+constexpr int kMaxChunks = 64;
+
+static int pick_chunks(int64_t B, int64_t C) {
+  const int64_t col_tiles = ceil_div(C, 32);
+  int64_t ch = ceil_div(2 * kNumSMs, col_tiles);
+  if (ch > kMaxChunks) ch = kMaxChunks;
+  const int64_t by_rows = ceil_div(B, 8);
+  if (ch > by_rows) ch = by_rows;
+  return ch < 1 ? 1 : (int)ch;
+}
+
+// F::operator()(row, col, acc[NV]) accumulates one element's contribution.  Block = (32 cols) x (8 row lanes).
+template <int NV, typename F>
+__global__ void __launch_bounds__(256)
+col_partial_kernel(int64_t B, int64_t C, int chunks, double* __restrict__ partial, F f) {
+  __shared__ double sm[NV][8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  const int chunk = blockIdx.y;
+  const int64_t rpc = ceil_div(B, chunks);
+  const int64_t r0 = chunk * rpc, r1 = (r0 + rpc < B) ? r0 + rpc : B;
+  double acc[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) acc[v] = 0.0;
+  if (c < C) for (int64_t r = r0 + ty; r < r1; r += 8) f(r, c, acc);
+#pragma unroll
+  for (int v = 0; v < NV; ++v) sm[v][ty][tx] = acc[v];
+  __syncthreads();
+  if (ty == 0 && c < C) {
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      double t = 0;
+      for (int y = 0; y < 8; ++y) t += sm[v][y][tx];
+      partial[((int64_t)v * chunks + chunk) * C + c] = t;
+    }
+  }
+}
+
+template <typename T> struct ColSumF {
+  const T* X; int64_t ld;
+  __device__ __forceinline__ void operator()(int64_t r, int64_t c, double (&a)[1]) const { a[0] += (double)ld_act<T>(X + r * ld + c); }
+};
+
+__global__ void colsum_finalize_kernel(const double* __restrict__ partial, int chunks, int64_t C, float* __restrict__ out, int accumulate) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t = 0;
+  for (int k = 0; k < chunks; ++k) t += partial[(int64_t)k * C + c];
+  out[c] = accumulate ? out[c] + (float)t : (float)t;
+}
+
+// ------------------------------------------------------------------------------------------ batch norm
+struct BnStatF {
+  const float* Z; int64_t ldz;
+  __device__ __forceinline__ void operator()(int64_t r, int64_t c, double (&a)[2]) const {
+    const double x = (double)Z[r * ldz + c]; a[0] += x; a[1] += x * x;
+  }
+};
+
+constexpr float kBnEps = 1e-5f, kBnMom = 0.1f;
+
+__global__ void bn_fwd_finalize_kernel(const double* __restrict__ partial, int chunks, int64_t B, int64_t C, int train,
+                                       float* __restrict__ rmean, float* __restrict__ rvar,
+                                       float* __restrict__ save_mean, float* __restrict__ save_invstd) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (!train) {
+    save_mean[c] = rmean[c];
+    save_invstd[c] = 1.0f / sqrtf(rvar[c] + kBnEps);
+    return;
+  }
+  double s = 0, q = 0;
+  for (int k = 0; k < chunks; ++k) { s += partial[(int64_t)k * C + c]; q += partial[((int64_t)chunks + k) * C + c]; }
+  const double mean = s / (double)B;
+  double var = q / (double)B - mean * mean;
+  if (var < 0) var = 0;
+  save_mean[c] = (float)mean;
+  save_invstd[c] = (float)(1.0 / sqrt(var + (double)kBnEps));
+  if (rmean) {
+    const double unb = B > 1 ? var * ((double)B / (double)(B - 1)) : var;
+    rmean[c] = (1.f - kBnMom) * rmean[c] + kBnMom * (float)mean;
+    rvar[c] = (1.f - kBnMom) * rvar[c] + kBnMom * (float)unb;
+  }
+}
+
+template <typename T>
+__global__ void bn_apply_kernel(const float* __restrict__ Z, int64_t ldz, T* __restrict__ A, int64_t lda, int64_t B, int64_t C,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ gamma2, const float* __restrict__ beta2,
+                                const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                                float drop_p, const uint64_t* __restrict__ seed_dev, uint32_t salt) {
+  const int64_t total = B * C;
+  const uint64_t seed = drop_p > 0.f ? *seed_dev : 0;
+  const uint32_t thr = drop_threshold(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % C, r = i / C;
+    float g = gamma[c], b = beta[c];
+    if (gamma2) { g *= gamma2[c]; b += beta2[c]; }
+    float v = (Z[r * ldz + c] - mean[c]) * invstd[c] * g + b;
+    if (relu) v = fmaxf(v, 0.f);
+    if (drop_p > 0.f) v = (mix_hash(seed, salt, (uint64_t)i) >= thr) ? v * keep_scale : 0.f;
+    st_act<T>(A + r * lda + c, v);
+  }
+}
+
+template <typename T> struct BnBwdStatF {
+  const float* Z; int64_t ldz; const T* A; int64_t lda; const float* dA; int64_t ldda;
+  const float* mean; const float* invstd; int relu; float keep_scale;
+  __device__ __forceinline__ void operator()(int64_t r, int64_t c, double (&a)[2]) const {
+    float dy = dA[r * ldda + c];
+    if (relu) dy = ld_act<T>(A + r * lda + c) > 0.f ? dy * keep_scale : 0.f;
+    const float xh = (Z[r * ldz + c] - mean[c]) * invstd[c];
+    a[0] += (double)dy; a[1] += (double)dy * (double)xh;
+  }
+};
+
+// sums[0][c] = sum dy, sums[1][c] = sum dy*xhat  (fp32 copies kept in `sums` for the apply kernel)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, int64_t C, float* __restrict__ sums,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0, q = 0;
+  for (int k = 0; k < chunks; ++k) { s += partial[(int64_t)k * C + c]; q += partial[((int64_t)chunks + k) * C + c]; }
+  sums[c] = (float)s; sums[C + c] = (float)q;
+  if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
+  if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
+}
+
+template <typename T>
+__global__ void bn_bwd_apply_kernel(const float* __restrict__ Z, int64_t ldz, const T* __restrict__ A, int64_t lda,
+                                    const float* __restrict__ dA, int64_t ldda, float* __restrict__ dZ, int64_t lddz,
+                                    int64_t B, int64_t C, const float* __restrict__ gamma, const float* __restrict__ gamma2,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ sums, int relu, float keep_scale, int train) {
+  const int64_t total = B * C;
+  const float inv_n = 1.f / (float)B;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % C, r = i / C;
+    float dy = dA[r * ldda + c];
+    if (relu) dy = ld_act<T>(A + r * lda + c) > 0.f ? dy * keep_scale : 0.f;
+    float g = gamma[c];
+    if (gamma2) g *= gamma2[c];
+    float dz;
+    if (train) {
+      const float xh = (Z[r * ldz + c] - mean[c]) * invstd[c];
+      dz = g * invstd[c] * (dy - sums[c] * inv_n - xh * sums[C + c] * inv_n);
+    } else {
+      dz = dy * g * invstd[c];
+    }
+    dZ[r * lddz + c] = dz;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ sigmoid / select / BCE
+template <typename TT>
+__global__ void __launch_bounds__(256)
+sigmoid_select_bce_kernel(const float* __restrict__ logits, const float* __restrict__ lin, int64_t ld_lin, int64_t B, int T,
+                          int mode, const int64_t* __restrict__ sel, int col, const TT* __restrict__ target,
+                          float* __restrict__ pred, float* __restrict__ psel, double* __restrict__ partials,
+                          float* __restrict__ dlogits, float* __restrict__ dlin, int64_t ld_dlin, float inv_batch) {
+  double loss = 0.0;
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    const float l0 = lin ? lin[b * ld_lin] : 0.f;
+    int c = col;
+    if (mode == 0) c = (int)sel[b];
+    float ps = 0.f, ys = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float y = 1.f / (1.f + expf(-(logits[b * T + t] + l0)));
+      pred[b * T + t] = y;
+      if (mode == 2) ps += y;
+      else if (t == c) { ps = y; ys = y; }
+    }
+    if (mode == 2) ps = ps / (float)T;
+    if (psel) psel[b] = ps;
+    if (target) {
+      const float tg = (float)target[b];
+      const float lp = fmaxf(logf(ps), -100.f), l1p = fmaxf(log1pf(-ps), -100.f);
+      loss += (double)(-(tg * lp + (1.f - tg) * l1p));
+      if (dlogits) {
+        const float dps = (ps - tg) / fmaxf((1.f - ps) * ps, 1e-12f) * inv_batch;
+        float dsum = 0.f;
+        for (int t = 0; t < T; ++t) {
+          float dz;
+          if (mode == 2) { const float y = pred[b * T + t]; dz = dps / (float)T * y * (1.f - y); }
+          else dz = (t == c) ? dps * ys * (1.f - ys) : 0.f;
+          dlogits[b * T + t] = dz;
+          dsum += dz;
+        }
+        if (dlin) dlin[b * ld_dlin] = dsum;
+      }
+    }
+  }
+  if (partials) {
+    loss = block_sum_256(loss);
+    if (threadIdx.x == 0) partials[blockIdx.x] = loss;
+  }
+}
+
+__global__ void sigmoid_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ dpred, float* __restrict__ dl,
+                                   float* __restrict__ dlin, int64_t ld_dlin, int64_t B, int T) {
+  for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
+    float dsum = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float y = pred[b * T + t];
+      const float dz = dpred[b * T + t] * y * (1.f - y);
+      dl[b * T + t] = dz;
+      dsum += dz;
+    }
+    if (dlin) dlin[b * ld_dlin] = dsum;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ regulariser / Adam
+__global__ void __launch_bounds__(256)
+reg_l2_partial_kernel(const float* __restrict__ w, const float* __restrict__ coef, float coef_scalar, int64_t n,
+                      double* __restrict__ partials) {
+  double t = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float c = coef ? coef[i] : coef_scalar;
+    if (c != 0.f) t += (double)c * (double)w[i] * (double)w[i];
+  }
+  t = block_sum_256(t);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+__global__ void reg_l2_grad_kernel(const float* __restrict__ w, const float* __restrict__ coef, float coef_scalar, float scale,
+                                   float* __restrict__ grad, int accumulate, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = scale * 2.f * (coef ? coef[i] : coef_scalar) * w[i];
+    grad[i] = accumulate ? grad[i] + v : v;
+  }
+}
+__global__ void relu_mask_kernel(const float* __restrict__ dA, int64_t ldda, const float* __restrict__ A, int64_t lda, float* __restrict__ out,
+                                 int64_t ldo, int64_t rows, int64_t cols, float scale) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % cols, r = i / cols;
+    out[r * ldo + c] = A[r * lda + c] > 0.f ? dA[r * ldda + c] * scale : 0.f;
+  }
+}
+
+__global__ void adam_dense_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
+                                  const float* __restrict__ l2coef, const uint8_t* __restrict__ present, int64_t n,
+                                  const cdcmdr_step_state_t* __restrict__ st) {
+  const float lr_t = st->lr_t, b1 = st->beta1, b2 = st->beta2, eps = st->eps, wd = st->weight_decay, bc2 = st->bc2_sqrt;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    if (present && !present[i]) continue;
+    float p = w[i];
+    float g = grad[i];
+    if (l2coef) g = g + 2.f * l2coef[i] * p;
+    g = g + wd * p;
+    float mi = m[i], vi = v[i];
+    mi = mi + (1.f - b1) * (g - mi);
+    vi = b2 * vi + (1.f - b2) * g * g;
+    const float denom = sqrtf(vi) / bc2 + eps;
+    p = p - lr_t * (mi / denom);
+    w[i] = p; m[i] = mi; v[i] = vi;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ casts / elementwise
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, int64_t lds, uint16_t* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % cols, r = i / cols;
+    dst[r * ldd + c] = f32_to_bf16(src[r * lds + c]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const uint16_t* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, int accumulate) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % cols, r = i / cols;
+    const float v = bf16_to_f32(src[r * lds + c]);
+    dst[r * ldd + c] = accumulate ? dst[r * ldd + c] + v : v;
+  }
+}
+__global__ void ewise_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n, int op) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float v;
+    if (op == 0) v = a[i] * b[i];
+    else if (op == 1) v = a[i] + b[i];
+    else if (op == 2) v = out[i] + a[i] * b[i];
+    else v = out[i] + a[i];
+    out[i] = v;
+  }
+}
+__global__ void add2d_kernel(const float* __restrict__ a, int64_t lda, float* __restrict__ out, int64_t ldo, int64_t rows, int64_t cols, int accumulate) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % cols, r = i / cols;
+    const float v = a[r * lda + c];
+    out[r * ldo + c] = accumulate ? out[r * ldo + c] + v : v;
+  }
+}
+
+}  // namespace cdcmdr
+
+using namespace cdcmdr;
+
+// ============================================================================================ C-ABI
+static int check_mix(const cdcmdr_mix_desc_t* d) {
+  CDC_REQUIRE(d && d->n_gates >= 1 && d->n_gates <= 32 && d->max_sel >= 1 && d->max_sel <= 32 && d->n_experts >= 1 &&
+              d->n_experts <= 64 && d->h >= 1, "bad gate-mix descriptor");
+  return 0;
+}
+
+extern "C" int cdcmdr_gate_mix_fwd(const cdcmdr_mix_desc_t* d, const void* H, int64_t ldh, const float* logits, int64_t ldl,
+                                   void* out, int64_t ldo, float* probs, int64_t B, int is_bf16, cdcmdr_stream_t s) {
+  if (int rc = check_mix(d)) return rc;
+  if (B == 0) return 0;
+  MixK k{d->n_gates, d->n_experts, d->h, d->max_sel, d->gate_col, d->gate_n, d->gate_sel};
+  const size_t smem = (size_t)8 * d->n_gates * d->max_sel * sizeof(float);
+  CDC_REQUIRE(smem <= 32 * 1024, "gate-mix descriptor too large");
+  const int grid = grid_1d(B * 32, 256);
+  const bool vec = d->h % 4 == 0 && ldh % 4 == 0 && ldo % 4 == 0 &&
+                   ((uintptr_t)H % (is_bf16 ? 8 : 16) == 0) && ((uintptr_t)out % (is_bf16 ? 8 : 16) == 0);
+  cudaStream_t st = to_stream(s);
+  if (is_bf16) {
+    if (vec) gate_mix_fwd_kernel<uint16_t, 4><<<grid, 256, smem, st>>>(k, (const uint16_t*)H, ldh, logits, ldl, (uint16_t*)out, ldo, probs, B);
+    else gate_mix_fwd_kernel<uint16_t, 1><<<grid, 256, smem, st>>>(k, (const uint16_t*)H, ldh, logits, ldl, (uint16_t*)out, ldo, probs, B);
+  } else {
+    if (vec) gate_mix_fwd_kernel<float, 4><<<grid, 256, smem, st>>>(k, (const float*)H, ldh, logits, ldl, (float*)out, ldo, probs, B);
+    else gate_mix_fwd_kernel<float, 1><<<grid, 256, smem, st>>>(k, (const float*)H, ldh, logits, ldl, (float*)out, ldo, probs, B);
+  }
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_gate_mix_bwd(const cdcmdr_mix_desc_t* d, const void* H, int64_t ldh, const float* probs,
+                                   const void* dOut, int64_t ldo, void* dH, int64_t lddh, float relu_scale,
+                                   float* dlogits, int64_t lddl, int64_t B, int is_bf16, cdcmdr_stream_t s) {
+  if (int rc = check_mix(d)) return rc;
+  if (B == 0) return 0;
+  MixK k{d->n_gates, d->n_experts, d->h, d->max_sel, d->gate_col, d->gate_n, d->gate_sel};
+  const size_t smem = (size_t)16 * d->n_gates * d->max_sel * sizeof(float);
+  CDC_REQUIRE(smem <= 32 * 1024, "gate-mix descriptor too large");
+  const int grid = grid_1d(B * 32, 256);
+  const int al = is_bf16 ? 8 : 16;
+  const bool vec = d->h % 4 == 0 && ldh % 4 == 0 && ldo % 4 == 0 && lddh % 4 == 0 && ((uintptr_t)H % al == 0) &&
+                   ((uintptr_t)dOut % al == 0) && ((uintptr_t)dH % al == 0);
+  cudaStream_t st = to_stream(s);
+#define MIXB(T, V) gate_mix_bwd_kernel<T, V><<<grid, 256, smem, st>>>(k, (const T*)H, ldh, probs, (const T*)dOut, ldo, (T*)dH, lddh, relu_scale, dlogits, lddl, B)
+  if (is_bf16) { if (vec) MIXB(uint16_t, 4); else MIXB(uint16_t, 1); }
+  else { if (vec) MIXB(float, 4); else MIXB(float, 1); }
+#undef MIXB
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t cdcmdr_colsum_scratch_bytes(int64_t C) { return (size_t)kMaxChunks * (size_t)(C > 0 ? C : 1) * sizeof(double); }
+extern "C" size_t cdcmdr_bn_scratch_bytes(int64_t C) {
+  const size_t c = (size_t)(C > 0 ? C : 1);
+  return 2 * (size_t)kMaxChunks * c * sizeof(double) + 2 * c * sizeof(float) + 256;
+}
+extern "C" size_t cdcmdr_reduce_scratch_bytes(void) { return kReducePartials * sizeof(double); }
+
+extern "C" int cdcmdr_colsum(const void* X, int64_t ld, int is_bf16, int64_t B, int64_t C, float* out, int accumulate,
+                             void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(B >= 0 && C >= 0 && scratch, "bad colsum arguments");
+  if (C == 0) return 0;
+  cudaStream_t st = to_stream(s);
+  const int chunks = pick_chunks(B > 0 ? B : 1, C);
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+  double* partial = (double*)scratch;
+  if (is_bf16) col_partial_kernel<1><<<grid, 256, 0, st>>>(B, C, chunks, partial, ColSumF<uint16_t>{(const uint16_t*)X, ld});
+  else col_partial_kernel<1><<<grid, 256, 0, st>>>(B, C, chunks, partial, ColSumF<float>{(const float*)X, ld});
+  CDC_LAUNCHED();
+  colsum_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, chunks, C, out, accumulate);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_bn_fwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, void* A, int64_t lda_, int a_is_bf16,
+                             int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && p->gamma && p->beta && p->save_mean && p->save_invstd && scratch, "bad batch-norm arguments");
+  CDC_REQUIRE(p->train || (p->running_mean && p->running_var), "eval batch-norm needs running statistics");
+  CDC_REQUIRE(p->drop_p <= 0.f || (p->seed_dev && p->relu), "batch-norm dropout needs relu and a device seed");
+  CDC_REQUIRE((p->gamma2 == nullptr) == (p->beta2 == nullptr), "gamma2/beta2 must come together");
+  if (B == 0 || C == 0) return 0;
+  cudaStream_t st = to_stream(s);
+  const int chunks = pick_chunks(B, C);
+  double* partial = (double*)scratch;
+  if (p->train) {
+    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+    col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, BnStatF{Z, ldz});
+    CDC_LAUNCHED();
+  }
+  bn_fwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, chunks, B, C, p->train, p->running_mean, p->running_var,
+                                                                    p->save_mean, p->save_invstd);
+  CDC_LAUNCHED();
+  const int g = grid_1d(B * C, 256);
+  if (a_is_bf16)
+    bn_apply_kernel<uint16_t><<<g, 256, 0, st>>>(Z, ldz, (uint16_t*)A, lda_, B, C, p->gamma, p->beta, p->gamma2, p->beta2, p->save_mean,
+                                                 p->save_invstd, p->relu, p->drop_p, p->seed_dev, p->salt);
+  else
+    bn_apply_kernel<float><<<g, 256, 0, st>>>(Z, ldz, (float*)A, lda_, B, C, p->gamma, p->beta, p->gamma2, p->beta2, p->save_mean,
+                                              p->save_invstd, p->relu, p->drop_p, p->seed_dev, p->salt);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_bn_bwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
+                             const float* dA, int64_t ldda, float* dZ, int64_t lddz, float* dgamma, float* dbeta,
+                             int accumulate, int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && p->gamma && p->save_mean && p->save_invstd && scratch && dA && dZ, "bad batch-norm arguments");
+  CDC_REQUIRE(!p->relu || A, "relu backward needs the forward output");
+  if (B == 0 || C == 0) return 0;
+  cudaStream_t st = to_stream(s);
+  const int chunks = pick_chunks(B, C);
+  double* partial = (double*)scratch;
+  float* sums = (float*)((char*)scratch + 2 * (size_t)kMaxChunks * (size_t)C * sizeof(double));
+  const float keep_scale = p->drop_p > 0.f ? 1.f / (1.f - p->drop_p) : 1.f;
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+  if (a_is_bf16)
+    col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial,
+        BnBwdStatF<uint16_t>{Z, ldz, (const uint16_t*)A, lda_, dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale});
+  else
+    col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial,
+        BnBwdStatF<float>{Z, ldz, (const float*)A, lda_, dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale});
+  CDC_LAUNCHED();
+  bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, chunks, C, sums, dgamma, dbeta, accumulate);
+  CDC_LAUNCHED();
+  const int g = grid_1d(B * C, 256);
+  if (a_is_bf16)
+    bn_bwd_apply_kernel<uint16_t><<<g, 256, 0, st>>>(Z, ldz, (const uint16_t*)A, lda_, dA, ldda, dZ, lddz, B, C, p->gamma, p->gamma2,
+                                                     p->save_mean, p->save_invstd, sums, p->relu, keep_scale, p->train);
+  else
+    bn_bwd_apply_kernel<float><<<g, 256, 0, st>>>(Z, ldz, (const float*)A, lda_, dA, ldda, dZ, lddz, B, C, p->gamma, p->gamma2,
+                                                  p->save_mean, p->save_invstd, sums, p->relu, keep_scale, p->train);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_sigmoid_select_bce(const float* logits, const float* lin, int64_t ld_lin, int64_t B, int32_t T, int32_t mode,
+                                         const int64_t* sel, int32_t col, const void* target, int target_is_f32,
+                                         float* pred, float* psel, double* loss_sum, float* dlogits,
+                                         float* dlin, int64_t ld_dlin, float inv_batch, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(logits && pred && T >= 1 && mode >= 0 && mode <= 3, "bad sigmoid/BCE arguments");
+  CDC_REQUIRE(mode != 0 || sel, "mode 0 needs per-sample columns");
+  CDC_REQUIRE(mode != 1 || (col >= 0 && col < T), "mode 1 column out of range");
+  CDC_REQUIRE(mode != 3 || !target, "mode 3 is forward only");
+  CDC_REQUIRE(!target || (loss_sum && scratch), "loss needs an output and scratch");
+  CDC_REQUIRE(!dlin || dlogits, "dlin needs dlogits");
+  if (B == 0) return 0;
+  cudaStream_t st = to_stream(s);
+  int grid = grid_1d(B, 256);
+  if (grid > kReducePartials) grid = kReducePartials;
+  double* partials = target ? (double*)scratch : nullptr;
+  if (mode == 3) col = -1;
+  if (target_is_f32)
+    sigmoid_select_bce_kernel<float><<<grid, 256, 0, st>>>(logits, lin, ld_lin, B, T, mode, sel, col, (const float*)target, pred, psel,
+                                                           partials, dlogits, dlin, ld_dlin, inv_batch);
+  else
+    sigmoid_select_bce_kernel<int16_t><<<grid, 256, 0, st>>>(logits, lin, ld_lin, B, T, mode, sel, col, (const int16_t*)target, pred, psel,
+                                                             partials, dlogits, dlin, ld_dlin, inv_batch);
+  CDC_LAUNCHED();
+  if (target) {
+    reduce_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, loss_sum);
+    CDC_LAUNCHED();
+  }
+  return 0;
+}
+
+extern "C" int cdcmdr_sigmoid_bwd(const float* pred, const float* dpred, float* dlogits, float* dlin, int64_t ld_dlin,
+                                  int64_t B, int32_t T, cdcmdr_stream_t s) {
+  if (B <= 0 || T <= 0) return 0;
+  sigmoid_bwd_kernel<<<grid_1d(B, 256), 256, 0, to_stream(s)>>>(pred, dpred, dlogits, dlin, ld_dlin, B, T);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_reg_l2_sum(const float* w, const float* coef, float coef_scalar, int64_t n, double* out_sum, void* scratch,
+                                 cdcmdr_stream_t s) {
+  CDC_REQUIRE(w && out_sum && scratch && n >= 0, "bad reg_l2_sum arguments");
+  cudaStream_t st = to_stream(s);
+  int grid = grid_1d(n > 0 ? n : 1, 256);
+  if (grid > kReducePartials) grid = kReducePartials;
+  reg_l2_partial_kernel<<<grid, 256, 0, st>>>(w, coef, coef_scalar, n, (double*)scratch);
+  CDC_LAUNCHED();
+  reduce_finalize_kernel<<<1, 256, 0, st>>>((const double*)scratch, grid, out_sum);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_reg_l2_grad(const float* w, const float* coef, float coef_scalar, float scale, float* grad, int accumulate,
+                                  int64_t n, cdcmdr_stream_t s) {
+  if (n <= 0) return 0;
+  reg_l2_grad_kernel<<<grid_1d(n, 256), 256, 0, to_stream(s)>>>(w, coef, coef_scalar, scale, grad, accumulate, n);
+  CDC_LAUNCHED();
+  return 0;
+}
+extern "C" int cdcmdr_relu_mask_f32(const float* dA, int64_t ldda, const float* A, int64_t lda_, float* out, int64_t ldo, int64_t rows,
+                                    int64_t cols, float scale, cdcmdr_stream_t s) {
+  if (rows <= 0 || cols <= 0) return 0;
+  relu_mask_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(dA, ldda, A, lda_, out, ldo, rows, cols, scale);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_adam_dense(float* w, const float* grad, float* m, float* v, const float* l2coef, const uint8_t* present,
+                                 int64_t n, const cdcmdr_step_state_t* st, cdcmdr_stream_t s) {
+  CDC_REQUIRE(w && grad && m && v && st, "bad Adam arguments");
+  if (n <= 0) return 0;
+  adam_dense_kernel<<<grid_1d(n, 256), 256, 0, to_stream(s)>>>(w, grad, m, v, l2coef, present, n, st);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_cast_f32_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols, cdcmdr_stream_t s) {
+  if (rows <= 0 || cols <= 0) return 0;
+  cast_f32_bf16_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols);
+  CDC_LAUNCHED();
+  return 0;
+}
+extern "C" int cdcmdr_cast_bf16_f32(const uint16_t* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, int accumulate,
+                                    cdcmdr_stream_t s) {
+  if (rows <= 0 || cols <= 0) return 0;
+  cast_bf16_f32_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols, accumulate);
+  CDC_LAUNCHED();
+  return 0;
+}
+extern "C" int cdcmdr_ewise_f32(const float* a, const float* b, float* out, int64_t n, int op, cdcmdr_stream_t s) {
+  CDC_REQUIRE(op >= 0 && op <= 3, "bad elementwise op");
+  if (n <= 0) return 0;
+  ewise_kernel<<<grid_1d(n, 256), 256, 0, to_stream(s)>>>(a, b, out, n, op);
+  CDC_LAUNCHED();
+  return 0;
+}
+extern "C" int cdcmdr_add2d_f32(const float* a, int64_t lda, float* out, int64_t ldo, int64_t rows, int64_t cols, int accumulate,
+                                cdcmdr_stream_t s) {
+  if (rows <= 0 || cols <= 0) return 0;
+  add2d_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(a, lda, out, ldo, rows, cols, accumulate);
+  CDC_LAUNCHED();
+  return 0;
+}

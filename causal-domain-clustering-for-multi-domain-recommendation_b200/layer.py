@@ -1,0 +1,479 @@
+"""Host-side mirror of the reference's model/layer.py for the hot path: the same module tree (so `state_dict()`
+keys, shapes and - for equal torch seeds - initial values match), the same constructor / forward /
+get_regularization_loss surface, with every operation executed by libcdcmdr.so.
+
+The nn.Modules below only HOLD parameters (as views into the flat arena of runtime.py); none of them has a torch
+forward.  BaseModel drives the CUDA program of its subclass:
+  forward(x)                      drop-in for run.py:483 (autograd-compatible: loss.backward() runs our backward)
+  get_regularization_loss(device) drop-in for run.py:489 (layer.py:96-112)
+  train_step(...)                 the fused step: forward + tower selection + BCE + backward + regulariser + Adam
+                                  (run.py:483-492 / 635-640) with no host synchronisation - what bench.py times.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .core import Mat
+from .runtime import MlpGroup, Runtime
+
+
+# --------------------------------------------------------------------------------------------- parameter holders
+class FeaturesEmbedding(nn.Module):
+    """model/layer.py:129-157: one table over the concatenated vocabularies; offsets = exclusive cumsum."""
+
+    def __init__(self, field_dims, embed_dim):
+        super().__init__()
+        fd = np.asarray(list(field_dims), dtype=np.int64)
+        self.field_num = len(fd)
+        self.output_dim0 = self.field_num
+        self.embed_dim = embed_dim
+        self.embedding_dict = nn.Embedding(int(fd.sum()), embed_dim)
+        self.offsets = np.array((0, *np.cumsum(fd)[:-1]), dtype=np.int64)
+        self.register_buffer("offsets_dev", torch.from_numpy(self.offsets.copy()), persistent=False)
+
+
+class FeaturesLinear(nn.Module):
+    """model/layer.py:115-126."""
+
+    def __init__(self, field_dims, output_dim=1):
+        super().__init__()
+        self.fc = nn.Linear(field_dims, output_dim, bias=True)
+
+
+class MultiLayerPerceptron(nn.Module):
+    """model/layer.py:178-206 (parameter layout only: Linear at layers.{s*j}, BatchNorm1d at layers.{s*j+1},
+    s = 4 with bn else 3; optional Linear(., 1) last)."""
+
+    def __init__(self, input_dim, layer_dims, dropout, output_layer=True, bn=True):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        for d in layer_dims:
+            self.layers.append(nn.Linear(input_dim, d))
+            if bn:
+                self.layers.append(nn.BatchNorm1d(d))
+            self.layers.append(nn.ReLU())
+            self.layers.append(nn.Dropout(p=dropout))
+            input_dim = d
+        if output_layer:
+            self.layers.append(nn.Linear(input_dim, 1))
+        self.n_hidden, self.bn, self.has_out = len(layer_dims), bn, output_layer
+
+    def lin_name(self, j):
+        return f"layers.{(4 if self.bn else 3) * j}"
+
+    def bn_name(self, j):
+        return f"layers.{4 * j + 1}"
+
+    def out_name(self):
+        return f"layers.{(4 if self.bn else 3) * self.n_hidden}"
+
+
+def mlp_group_names(prefixes, mlp: MultiLayerPerceptron, tag):
+    """Arena block names + member parameter lists for a group of identically-shaped MLPs."""
+    blocks, bufs = [], []
+    names = {"W": [], "b": [], "gamma": [], "beta": [], "rmean": [], "rvar": []}
+    for j in range(mlp.n_hidden):
+        ln = mlp.lin_name(j)
+        names["W"].append(f"{tag}.W{j}"); names["b"].append(f"{tag}.b{j}")
+        blocks.append((f"{tag}.W{j}", [f"{p}.{ln}.weight" for p in prefixes]))
+        blocks.append((f"{tag}.b{j}", [f"{p}.{ln}.bias" for p in prefixes]))
+        if mlp.bn:
+            bn = mlp.bn_name(j)
+            names["gamma"].append(f"{tag}.gamma{j}"); names["beta"].append(f"{tag}.beta{j}")
+            names["rmean"].append(f"{tag}.rmean{j}"); names["rvar"].append(f"{tag}.rvar{j}")
+            blocks.append((f"{tag}.gamma{j}", [f"{p}.{bn}.weight" for p in prefixes]))
+            blocks.append((f"{tag}.beta{j}", [f"{p}.{bn}.bias" for p in prefixes]))
+            bufs.append((f"{tag}.rmean{j}", [f"{p}.{bn}.running_mean" for p in prefixes]))
+            bufs.append((f"{tag}.rvar{j}", [f"{p}.{bn}.running_var" for p in prefixes]))
+    if mlp.has_out:
+        on = mlp.out_name()
+        names["Wout"], names["bout"] = f"{tag}.Wout", f"{tag}.bout"
+        blocks.append((f"{tag}.Wout", [f"{p}.{on}.weight" for p in prefixes]))
+        blocks.append((f"{tag}.bout", [f"{p}.{on}.bias" for p in prefixes]))
+    return names, blocks, bufs
+
+
+# --------------------------------------------------------------------------------------------- autograd glue
+class _ForwardFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, x, kw, *params):
+        ctx.model = model
+        out = model._engine_forward(x, train=model.training, **kw)
+        ctx.token = model._fwd_token
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, dpred):
+        model = ctx.model
+        if ctx.token != model._fwd_token:
+            raise RuntimeError("cdcmdr: backward() must follow the forward() it differentiates (activations are kept "
+                               "in a per-batch-size workspace that the next forward overwrites)")
+        grads = model._engine_backward(dpred.contiguous())
+        return (None, None, None, *grads)
+
+
+class _RegFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, model, *params):
+        ctx.model = model
+        return model._reg_value().to(torch.float32).reshape(1)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return (None, *ctx.model._reg_grads(float(gout.reshape(-1)[0])))
+
+
+# --------------------------------------------------------------------------------------------- BaseModel
+class BaseModel(nn.Module):
+    """model/layer.py:10-112.  Subclasses define `_layout()` (arena blocks) and `_program_fwd/_program_bwd`."""
+
+    def __init__(self, feature_dims, embed_dim, l2_reg_embedding=1e-5, l2_reg_linear=1e-5):
+        super().__init__()
+        self.feature_dims = feature_dims
+        self.embedding = FeaturesEmbedding(feature_dims, embed_dim)
+        self.embed_output_dim = self.embedding.output_dim0 * embed_dim
+        self.embed_dim = embed_dim
+        self.field_num = self.embedding.field_num
+        self.linear = FeaturesLinear(self.embed_output_dim)
+        self.is_concat_linear_cn = None
+        self.regularization_weight = []            # [(parameter names, l1, l2)]
+        self.l2_reg_embedding = float(l2_reg_embedding)
+        self.add_regularization_weight(["embedding.embedding_dict.weight"], l2=l2_reg_embedding)
+        self.add_regularization_weight(self.reg_filter("linear"), l2=l2_reg_linear)
+        self._rt = None
+        self._fwd_token = 0
+        self._last = None
+        self._table_state = None                   # (m, v) of the fused embedding Adam
+        self.precision = "fp32"
+        self.n_out = 1
+        self.embedding_update = "dense_exact"      # or "sparse_lazy" (documented deviation)
+
+    # ---------------------------------------------------------------- regularisation bookkeeping (layer.py:86-112)
+    def reg_filter(self, prefix):
+        """Names under sub-module `prefix` that the reference's filter keeps: 'weight' in the RELATIVE name and 'bn'
+        not in it (so BatchNorm gammas inside MultiLayerPerceptron are regularised)."""
+        mod = self.get_submodule(prefix)
+        return [f"{prefix}.{n}" for n, _ in mod.named_parameters() if "weight" in n and "bn" not in n]
+
+    def add_regularization_weight(self, weight_list, l1=0.0, l2=0.0):
+        if l1:
+            raise NotImplementedError("l1 regularisation is never used by the reference's hot-path models")
+        self.regularization_weight.append((list(weight_list), l1, float(l2)))
+
+    # ---------------------------------------------------------------- arena construction
+    def _finalize(self, blocks, buffer_blocks, precision="fp32", dropout=0.0):
+        """blocks: [(block name, [parameter names])] in the order the GEMMs want them contiguous."""
+        self.precision = precision
+        self._blocks, self._buffer_blocks = list(blocks), list(buffer_blocks)
+        named = dict(self.named_parameters())
+        placed = {n for _, ns in self._blocks for n in ns}
+        for n in named:
+            if n not in placed and n != "embedding.embedding_dict.weight":
+                self._blocks.append((n, [n]))
+        self._dropout = float(dropout)
+        self._build_runtime()
+
+    def _build_runtime(self):
+        named = dict(self.named_parameters())
+        bufs = dict(self.named_buffers())
+        device = named["embedding.embedding_dict.weight"].device
+        rt = Runtime(device, self.precision)
+        rt.dropout = self._dropout
+        for bname, members in self._blocks:
+            off0 = rt.params.n
+            total = sum(named[m].numel() for m in members)
+            rt.params.add(bname, (total,))
+            o = off0
+            for m in members:
+                if m != bname:
+                    rt.params.off[m] = o
+                rt.params.shape[m] = tuple(named[m].shape)
+                o += named[m].numel()
+        for bname, members in self._buffer_blocks:
+            off0 = rt.buffers.n
+            total = sum(bufs[m].numel() for m in members)
+            rt.buffers.add(bname, (total,))
+            o = off0
+            for m in members:
+                if m != bname:
+                    rt.buffers.off[m] = o
+                rt.buffers.shape[m] = tuple(bufs[m].shape)
+                o += bufs[m].numel()
+        old = self._rt
+        rt.allocate()
+        with torch.no_grad():
+            for _, members in self._blocks:
+                for m in members:
+                    v = rt.view(m)
+                    v.copy_(named[m].data)
+                    named[m].data = v
+            for _, members in self._buffer_blocks:
+                for m in members:
+                    v = rt.buf_view(m)
+                    v.copy_(bufs[m].data)
+                    self._set_buffer(m, v)
+            for names, _, l2 in self.regularization_weight:
+                for m in names:
+                    if m == "embedding.embedding_dict.weight" or l2 <= 0:
+                        continue
+                    o = rt.params.off[m]
+                    rt.L2[o:o + named[m].numel()] += l2
+            for m in self._absent_grads():
+                o = rt.params.off[m]
+                rt.present[o:o + named[m].numel()] = 0
+        if old is not None and old.M is not None:
+            rt.M, rt.V = old.M.to(device), old.V.to(device)
+            rt.step_state = old.step_state.to(device) if old.step_state is not None else None
+        if self._table_state is not None:
+            self._table_state = tuple(t.to(device) for t in self._table_state)
+        self._rt = rt
+        self._last = None
+        self._on_runtime_built()
+
+    def _set_buffer(self, name, value):
+        mod_name, _, leaf = name.rpartition(".")
+        mod = self.get_submodule(mod_name) if mod_name else self
+        mod._buffers[leaf] = value
+
+    def _absent_grads(self):
+        """Parameters whose .grad stays None in the reference (never reached by forward)."""
+        return []
+
+    def _on_runtime_built(self):
+        pass
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse) if recurse is not True else super()._apply(fn)
+        if getattr(self, "_rt", None) is not None:
+            self._build_runtime()
+        return out
+
+    # ---------------------------------------------------------------- device checks
+    def _check_device(self, x):
+        rt = self._rt
+        if rt is None:
+            raise RuntimeError("cdcmdr: model was not finalised")
+        emu = getattr(rt.ops.lib, "is_host_emulator", False)
+        if rt.device.type != "cuda" and not emu:
+            raise RuntimeError("cdcmdr: this model runs only on a CUDA device (sm_100a); there is no CPU fallback. "
+                               "Move it with model.to('cuda').")
+        if x.device != rt.device and not (x.device.type == rt.device.type == "cuda" and rt.device.index is None):
+            raise RuntimeError(f"cdcmdr: input on {x.device}, model on {rt.device}")
+        if x.dtype != torch.int32:
+            raise TypeError("cdcmdr: sparse-field indices must be int32 (run.py:198-199)")
+        if x.dim() != 2 or x.shape[1] != self.field_num:
+            raise ValueError(f"cdcmdr: expected indices of shape [B, {self.field_num}]")
+
+    # ---------------------------------------------------------------- forward / backward drivers
+    def _gather(self, ws, x, B):
+        rt = self._rt
+        E, F = self.embed_dim, self.field_num
+        table = self.embedding.embedding_dict.weight
+        X = ws.mat("X", B, F * E)
+        rt.ops.embed_gather(x, self.embedding.offsets_dev, table, X, None, B, F, E, table.shape[0])
+        return X
+
+    def _engine_forward(self, x, train, **kw):
+        """Runs the CUDA forward; returns predictions (a workspace view)."""
+        self._check_device(x)
+        x = x.contiguous()
+        B = x.shape[0]
+        rt = self._rt
+        ws = rt.ws(B)
+        X = self._gather(ws, x, B)
+        logits, lin = self._program_fwd(ws, X, B, train, **kw)
+        T = self.n_out
+        pred = ws.get("pred", (B, T))
+        rt.ops.sigmoid_select_bce(logits.t, lin, B, T, 3, None, 0, None, pred, None, None, None, None, 0.0)
+        self._fwd_token += 1
+        self._last = dict(ws=ws, x=x, X=X, B=B, train=train, logits=logits, lin=lin, pred=pred, kw=kw)
+        if train:
+            self._bump_batches_tracked(B)
+        return self._shape_pred(pred[:B * T].view(B, T), **kw)
+
+    def _shape_pred(self, pred, **kw):
+        return pred
+
+    def _bump_batches_tracked(self, B):
+        if B == 1:
+            return
+        for name, buf in self.named_buffers():
+            if name.endswith("num_batches_tracked") and self._tracks(name):
+                buf += 1
+
+    def _tracks(self, name):
+        return True
+
+    def _engine_backward(self, dpred):
+        """dpred: gradient w.r.t. the (B, T) predictions.  Returns gradients for (dense parameters..., table)."""
+        last = self._last
+        rt, ws, B, T = self._rt, last["ws"], last["B"], self.n_out
+        dlogits = ws.get("dlogits", (B, T))
+        dlin = self._dlin_mat(ws, B)
+        rt.ops.sigmoid_bwd(last["pred"], self._unshape_dpred(dpred, B, T), dlogits, dlin, B, T)
+        dX = self._program_bwd(ws, last["X"], B, last["train"], Mat(dlogits, 0, T), **last["kw"])
+        table = self.embedding.embedding_dict.weight
+        V, E, F = table.shape[0], self.embed_dim, self.field_num
+        plan = rt.ops.embed_plan(last["x"], self.embedding.offsets_dev, B, F, V, E)
+        gtab = torch.empty_like(table)
+        rt.ops.embed_bwd_dense(dX, plan, B, F, E, V, gtab)
+        G = rt.G.clone()
+        grads = []
+        for name, p in self._autograd_params():
+            if name == "embedding.embedding_dict.weight":
+                grads.append(gtab)
+            elif name in self._absent_set:
+                grads.append(None)
+            else:
+                o = rt.params.off[name]
+                grads.append(G[o:o + p.numel()].view(p.shape))
+        return grads
+
+    def _unshape_dpred(self, dpred, B, T):
+        return dpred.reshape(B, T)
+
+    def _autograd_params(self):
+        return list(self.named_parameters())
+
+    @property
+    def _absent_set(self):
+        return set(self._absent_grads())
+
+    def _call(self, x, **kw):
+        if torch.is_grad_enabled():
+            params = [p for _, p in self._autograd_params()]
+            if any(p.requires_grad for p in params):
+                return _ForwardFn.apply(self, x, kw, *params)
+        return self._engine_forward(x, train=self.training, **kw).clone()
+
+    # ---------------------------------------------------------------- regulariser (layer.py:96-112)
+    def _reg_value(self):
+        rt = self._rt
+        table = self.embedding.embedding_dict.weight
+        out = torch.zeros(2, dtype=torch.float64, device=rt.device)
+        rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), out[0:1])
+        rt.ops.reg_l2_sum(table, None, self._l2_table(), table.numel(), out[1:2])
+        return out[0] + out[1]
+
+    def _l2_table(self):
+        return sum(l2 for names, _, l2 in self.regularization_weight if "embedding.embedding_dict.weight" in names)
+
+    def _reg_grads(self, scale):
+        rt = self._rt
+        table = self.embedding.embedding_dict.weight
+        g = torch.empty_like(rt.W)
+        rt.ops.reg_l2_grad(rt.W, rt.L2, 0.0, scale, g, False, rt.W.numel())
+        gt = torch.empty_like(table)
+        rt.ops.reg_l2_grad(table, None, self._l2_table(), scale, gt, False, table.numel())
+        out = []
+        for name, p in self._autograd_params():
+            if name == "embedding.embedding_dict.weight":
+                out.append(gt)
+            else:
+                o = rt.params.off[name]
+                out.append(g[o:o + p.numel()].view(p.shape))
+        return out
+
+    def get_regularization_loss(self, device=None):
+        self._check_device(torch.empty(0, self.field_num, dtype=torch.int32, device=self._rt.device))
+        params = [p for _, p in self._autograd_params()]
+        if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+            return _RegFn.apply(self, *params)
+        return self._reg_value().to(torch.float32).reshape(1)
+
+    # ---------------------------------------------------------------- fused training step
+    SEL_MODES = {"gather": 0, "col": 1, "mean": 2}
+
+    def train_step(self, x, y, optimizer, mode="gather", sel=None, col=0, **kw):
+        """One pass of run.py:483-492 entirely on the device, no host synchronisation:
+        gather -> model -> sigmoid -> tower selection -> BCE(mean) -> backward -> regulariser -> Adam (dense arena and
+        embedding table).  `optimizer` is a cdcmdr Adam (optim.py).  Returns a dict of device tensors:
+        loss (= bce + reg), bce, reg, pred (B, T)."""
+        self._check_device(x)
+        if not self.training:
+            raise RuntimeError("train_step() needs model.train()")
+        rt = self._rt
+        x = x.contiguous()
+        B, T = x.shape[0], self.n_out
+        ws = rt.ws(B)
+        optimizer.attach(self)
+        rt.ensure_opt_state()
+        optimizer.tick(rt)                                   # t += 1, dropout seed, Adam scalars
+        X = self._gather(ws, x, B)
+        logits, lin = self._program_fwd(ws, X, B, True, **kw)
+        pred = ws.get("pred", (B, T))
+        psel = ws.get("psel", (B,))
+        sums = ws.get("loss_sums", (4,), torch.float64)      # [bce_sum, reg_dense, table_sumsq, -]
+        dlogits = ws.get("dlogits", (B, T))
+        dlin = self._dlin_mat(ws, B)
+        y, sel = self._route_targets(ws, y, sel, B, **kw)
+        rt.ops.sigmoid_select_bce(logits.t, lin, B, T, self.SEL_MODES[mode], sel, col, y, pred, psel, sums[0:1], dlogits,
+                                  dlin, 1.0 / B)
+        self._fwd_token += 1
+        self._last = None
+        self._bump_batches_tracked(B)
+        dX = self._program_bwd(ws, X, B, True, Mat(dlogits, 0, T), **kw)
+        rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[1:2])
+        rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
+        table = self.embedding.embedding_dict.weight
+        V, E, F = table.shape[0], self.embed_dim, self.field_num
+        plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
+        if self._table_state is None:
+            self._table_state = (torch.zeros_like(table), torch.zeros_like(table))
+        m, v = self._table_state
+        l2t = self._l2_table()
+        lazy = self.embedding_update == "sparse_lazy"
+        if lazy:
+            rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[2:3])
+        rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[2:3], lazy=lazy)
+        return dict(sums=sums, pred=pred[:B * T].view(B, T), psel=psel[:B], B=B, l2_table=l2t)
+
+    @staticmethod
+    def step_losses(out):
+        """Host-side view of a train_step result (synchronises): (loss, bce, reg) as Python floats, computed like
+        run.py:484-489: float32 bce + float32 reg."""
+        s = out["sums"].tolist()
+        bce = np.float32(s[0] / out["B"])
+        reg = np.float32(s[1] + out["l2_table"] * s[2])
+        return float(np.float32(bce + reg)), float(bce), float(reg)
+
+    def _route_targets(self, ws, y, sel, B, **kw):
+        if y.dtype not in (torch.int16, torch.float32):
+            y = y.to(torch.float32)
+        y = y.reshape(-1).contiguous()
+        if sel is not None:
+            sel = sel.reshape(-1).contiguous()
+            if sel.dtype != torch.int64:
+                raise TypeError("tower selection indices must be int64 (run.py:229-230)")
+        return y, sel
+
+    # ---------------------------------------------------------------- subclass interface
+    def _dlin_mat(self, ws, B) -> Mat | None:
+        raise NotImplementedError
+
+    def _program_fwd(self, ws, X: Mat, B, train, **kw):
+        raise NotImplementedError
+
+    def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat, **kw) -> Mat:
+        raise NotImplementedError
+
+    def forward(self, x):
+        return self._call(x)
+
+    # ---------------------------------------------------------------- towers (layer.py:35-56)
+    def build_tower_output(self, n_tower, tower_input_dim, tower_dims, dropout):
+        towers = nn.ModuleList(MultiLayerPerceptron(tower_input_dim, tower_dims, dropout, output_layer=True)
+                               for _ in range(n_tower))
+        output_layers = nn.ModuleList([nn.Sigmoid() for _ in range(n_tower)])
+        return towers, None, output_layers
+
+    def _tower_group(self, rt, tower_in_dim, tower_dims) -> MlpGroup:
+        names, _, _ = mlp_group_names([f"towers.{t}" for t in range(self.n_tower)], self.towers[0], "towers")
+        return MlpGroup(rt, "towers", self.n_tower, tower_in_dim, tower_dims, names, bn=True, out_layer=True, in_groups=None)
+
+
+def precision_of(config, default="fp32"):
+    return getattr(config, "cdcmdr_precision", default) if config is not None else default

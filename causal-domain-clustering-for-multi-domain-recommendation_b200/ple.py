@@ -1,0 +1,171 @@
+"""PLE / CGC (reference model/ple.py:9-124) on libcdcmdr.so.
+
+Per level: all experts' first layers that read the same input run as ONE concatenated-N GEMM (level 0: every expert
+and every gate reads embed_x, ple.py:54), deeper expert layers as one grouped GEMM, gate softmax + expert mixing as one
+fused kernel (ple.py:106-123).  Parameter names / shapes are the reference's."""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from .core import Mat
+from .layer import BaseModel, MultiLayerPerceptron, mlp_group_names, precision_of
+from .runtime import MlpGroup
+
+
+class CGC(nn.Module):
+    """Parameter holder with the reference's layout (ple.py:73-94)."""
+
+    def __init__(self, cur_level, n_level, n_task, n_expert_specific, n_expert_shared, input_dims, expert_dims, dropout=0.2):
+        super().__init__()
+        self.cur_level, self.n_level, self.n_task = cur_level, n_level, n_task
+        self.n_expert_specific, self.n_expert_shared = n_expert_specific, n_expert_shared
+        self.n_expert_all = n_expert_specific * n_task + n_expert_shared
+        self.experts_specific = nn.ModuleList(
+            MultiLayerPerceptron(input_dims, expert_dims, dropout, output_layer=False, bn=False)
+            for _ in range(n_task * n_expert_specific))
+        self.experts_shared = nn.ModuleList(
+            MultiLayerPerceptron(input_dims, expert_dims, dropout, output_layer=False, bn=False)
+            for _ in range(n_expert_shared))
+        self.gates_specific = nn.ModuleList(
+            [nn.Sequential(nn.Linear(input_dims, n_expert_specific + n_expert_shared), nn.Softmax(dim=1))
+             for _ in range(n_task)])
+        if cur_level < n_level:
+            self.gate_shared = nn.Sequential(nn.Linear(input_dims, self.n_expert_all), nn.Softmax(dim=1))
+
+
+class _Level:
+    pass
+
+
+class PLE(BaseModel):
+    def __init__(self, feature_dims, embed_dim, n_tower, n_expert_specific, n_expert_shared, expert_dims, tower_dims,
+                 dropout=0.2, config=None, l2_reg_embedding=1e-5, l2_reg_linear=1e-5, l2_reg_dnn=1e-5, l2_reg_cross=1e-5,
+                 model_name='ple'):
+        super().__init__(feature_dims, embed_dim, l2_reg_embedding=l2_reg_embedding, l2_reg_linear=l2_reg_linear)
+        self.model_name = model_name
+        self.n_level = len(expert_dims)
+        self.n_tower = n_tower
+        self.n_out = n_tower
+        if getattr(config, 'use_dcn', False):
+            raise NotImplementedError("use_dcn=True is broken upstream (SURVEY G5) and not part of the hot path")
+        if getattr(config, 'use_atten', False):
+            raise NotImplementedError("use_atten=True (field self-attention) is a 'next' row (SURVEY §8f N3)")
+        self.n_expert_specific, self.n_expert_shared = n_expert_specific, n_expert_shared
+        self.expert_dims = tuple(tuple(d) for d in expert_dims)
+        self.tower_dims = tuple(tower_dims)
+        self.cgc_layers = nn.ModuleList(
+            CGC(i + 1, self.n_level, n_tower, n_expert_specific, n_expert_shared,
+                self.embed_output_dim if i == 0 else expert_dims[i - 1][-1], expert_dims[i], dropout)
+            for i in range(self.n_level))
+        self.towers, self.towers_linear, self.output_layers = self.build_tower_output(n_tower, expert_dims[-1][-1],
+                                                                                      tower_dims, dropout)
+        self.add_regularization_weight(self.reg_filter("cgc_layers"), l2=l2_reg_dnn)
+        self.add_regularization_weight(self.reg_filter("towers"), l2=l2_reg_dnn)
+
+        blocks, bufs = [], []
+        self._level_names = []
+        T, ns, nsh = n_tower, n_expert_specific, n_expert_shared
+        for l in range(self.n_level):
+            p = f"cgc_layers.{l}"
+            prefixes = [f"{p}.experts_specific.{i}" for i in range(T * ns)] + [f"{p}.experts_shared.{i}" for i in range(nsh)]
+            names, blk, _ = mlp_group_names(prefixes, self.cgc_layers[l].experts_specific[0], f"cgc{l}")
+            gw = [f"{p}.gates_specific.{t}.0.weight" for t in range(T)]
+            gb = [f"{p}.gates_specific.{t}.0.bias" for t in range(T)]
+            if l + 1 < self.n_level:
+                gw.append(f"{p}.gate_shared.0.weight"); gb.append(f"{p}.gate_shared.0.bias")
+            if l == 0:
+                gw.append("linear.fc.weight"); gb.append("linear.fc.bias")
+            # expert layer-0 weights, then the gates (and the wide linear) that read the same input: one Bt matrix
+            blocks += [blk[0], (f"cgc{l}.gW", gw), blk[1], (f"cgc{l}.gb", gb)] + blk[2:]
+            self._level_names.append(names)
+        tnames, tblk, tbufs = mlp_group_names([f"towers.{t}" for t in range(T)], self.towers[0], "towers")
+        self._tower_names = tnames
+        blocks += tblk
+        bufs += tbufs
+        self._finalize(blocks, bufs, precision=precision_of(config), dropout=dropout)
+
+    # ---------------------------------------------------------------- program construction
+    def _on_runtime_built(self):
+        rt = self._rt
+        T, ns, nsh = self.n_tower, self.n_expert_specific, self.n_expert_shared
+        nE = T * ns + nsh
+        self._levels = []
+        for l in range(self.n_level):
+            lv = _Level()
+            last = l + 1 == self.n_level
+            lv.K = self.embed_output_dim if l == 0 else self.expert_dims[l - 1][-1]
+            lv.h = self.expert_dims[l][-1]
+            lv.n_in = 1 if l == 0 else T + 1
+            in_groups = [(0, 0, nE)] if l == 0 else [(t, t * ns, (t + 1) * ns) for t in range(T)] + [(T, T * ns, nE)]
+            lv.experts = MlpGroup(rt, f"cgc{l}", nE, lv.K, self.expert_dims[l], self._level_names[l], bn=False,
+                                  out_layer=False, in_groups=in_groups)
+            lv.n_gates = T if last else T + 1
+            w = ns + nsh
+            n_gate_cols = T * w + (0 if last else nE)
+            lv.n_gcols = n_gate_cols + (1 if l == 0 else 0)
+            if l == 0:
+                lv.gate_groups = [(0, 0, lv.n_gcols)]
+            else:
+                lv.gate_groups = [(t, t * w, (t + 1) * w) for t in range(T)] + ([] if last else [(T, T * w, T * w + nE)])
+            lv.max_sel = w if last else nE
+            col = [t * w for t in range(T)] + ([] if last else [T * w])
+            n = [w] * T + ([] if last else [nE])
+            sel = []
+            for t in range(T):
+                s = list(range(t * ns, (t + 1) * ns)) + list(range(T * ns, nE))
+                sel += s + [0] * (lv.max_sel - len(s))
+            if not last:
+                sel += list(range(nE))
+            lv.desc_t = torch.tensor(col + n + sel, dtype=torch.int32, device=rt.device)
+            lv.desc = rt.ops.mix_desc(lv.n_gates, nE, lv.h, lv.max_sel, lv.desc_t)
+            self._levels.append(lv)
+        self._towers = MlpGroup(rt, "towers", T, self.expert_dims[-1][-1], self.tower_dims, self._tower_names, bn=True,
+                                out_layer=True, in_groups=None)
+
+    def _dlin_mat(self, ws, B):
+        n = self._levels[0].n_gcols
+        return ws.mat("cgc0.dlogits", B, n).cols(n - 1)
+
+    def _program_fwd(self, ws, X: Mat, B, train):
+        rt = self._rt
+        xin = X
+        for l, lv in enumerate(self._levels):
+            H = lv.experts.fwd(ws, xin, B, train)
+            Lg = ws.mat(f"cgc{l}.logits", B, lv.n_gcols)
+            for (blk, c0, c1) in lv.gate_groups:
+                rt.lin_fwd(xin.cols(blk * lv.K), lv.K, rt.w(f"cgc{l}.gW", c0 * lv.K), c1 - c0, rt.w(f"cgc{l}.gb", c0),
+                           Lg.cols(c0), B)
+            out = ws.mat(f"cgc{l}.out", B, lv.n_gates * lv.h)
+            probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
+            rt.ops.gate_mix_fwd(lv.desc, H, Lg, out, probs, B)
+            xin = out
+        logits = self._towers.fwd(ws, xin, B, train)
+        n0 = self._levels[0].n_gcols
+        return logits, ws.mat("cgc0.logits", B, n0).cols(n0 - 1)
+
+    def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat):
+        rt = self._rt
+        T = self.n_tower
+        keep = 1.0 / (1.0 - rt.dropout) if (train and rt.dropout > 0) else 1.0
+        last_lv = self._levels[-1]
+        dcur = ws.mat("towers.dX", B, T * last_lv.h)
+        self._towers.bwd(ws, ws.mat(f"cgc{self.n_level - 1}.out", B, last_lv.n_gates * last_lv.h), dlogits, B, train, dcur)
+        for l in reversed(range(self.n_level)):
+            lv = self._levels[l]
+            nE = lv.experts.G
+            H = lv.experts._act(ws, len(lv.experts.dims) - 1, B)
+            dH = ws.mat(f"cgc{l}.dH", B, nE * lv.h)
+            dLg = ws.mat(f"cgc{l}.dlogits", B, lv.n_gcols)
+            probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
+            rt.ops.gate_mix_bwd(lv.desc, H, probs, dcur, dH, keep, dLg, B)
+            xin = X if l == 0 else ws.mat(f"cgc{l - 1}.out", B, self._levels[l - 1].n_gates * self._levels[l - 1].h)
+            dxin = ws.mat(f"cgc{l}.dXin", B, lv.n_in * lv.K)
+            lv.experts.bwd(ws, xin, dH, B, train, dxin)
+            rt.ops.colsum(dLg, B, lv.n_gcols, rt.g(f"cgc{l}.gb"))
+            for (blk, c0, c1) in lv.gate_groups:
+                rt.lin_bwd_w(dLg.cols(c0), xin.cols(blk * lv.K), lv.K, rt.g(f"cgc{l}.gW", c0 * lv.K), c1 - c0, B)
+                rt.lin_bwd_x(dLg.cols(c0), lv.K, rt.w(f"cgc{l}.gW", c0 * lv.K), c1 - c0, dxin.cols(blk * lv.K), B,
+                             accumulate=True)
+            dcur = dxin
+        return dcur
