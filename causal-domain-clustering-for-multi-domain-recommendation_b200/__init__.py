@@ -9,5 +9,6 @@ from .optim import Adam  # noqa: F401
 from .ple import PLE, CGC  # noqa: F401
 from .mmoe import MMoE  # noqa: F401
 from .cdc import CDC  # noqa: F401
+from .graph import GraphedTrainStep  # noqa: F401
 
-__all__ = ["PLE", "CGC", "MMoE", "CDC", "Adam", "BaseModel"]
+__all__ = ["PLE", "CGC", "MMoE", "CDC", "Adam", "BaseModel", "GraphedTrainStep"]

@@ -98,14 +98,6 @@ __global__ void splitk_epilogue_kernel(const float* __restrict__ partial, int sp
   }
 }
 
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, int64_t stride, int splits, float* __restrict__ out, int64_t n, int accumulate) {
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    float v = 0.f;
-    for (int z = 0; z < splits; ++z) v += part[(int64_t)z * stride + i];
-    out[i] = accumulate ? out[i] + v : v;
-  }
-}
-
 }  // namespace cdcmdr
 using namespace cdcmdr;
 
@@ -128,14 +120,5 @@ extern "C" int cdcmdr_gemm_f32(const cdcmdr_gemm_f32_t* p, cdcmdr_stream_t s) {
     splitk_epilogue_kernel<<<grid2, 256, 0, to_stream(s)>>>(p->workspace, split, p->G, p->M, p->N, e);
     CDC_LAUNCHED();
   }
-  return 0;
-}
-
-extern "C" int cdcmdr_splitk_reduce(const float* part, int64_t stride, int32_t splits, float* out, int64_t n, int32_t accumulate,
-                                    cdcmdr_stream_t s) {
-  if (n <= 0) return 0;
-  int grid = (int)(ceil_div(n, 256) < 8 * kNumSMs ? ceil_div(n, 256) : 8 * kNumSMs);
-  splitk_reduce_kernel<<<grid, 256, 0, to_stream(s)>>>(part, stride, splits, out, n, accumulate);
-  CDC_LAUNCHED();
   return 0;
 }

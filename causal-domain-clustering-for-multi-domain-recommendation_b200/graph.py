@@ -1,0 +1,53 @@
+"""CUDA-graph capture of the fused training step: the whole step (about a hundred launches of libcdcmdr.so kernels,
+no host synchronisation, all state device-resident) is recorded once per batch size and replayed with one launch."""
+from __future__ import annotations
+
+import torch
+
+
+class GraphedTrainStep:
+    """Captures `model.train_step(x, y, optimizer, **kw)` over static input buffers.
+
+    usage:  step = GraphedTrainStep(model, optimizer, B, F, mode='split', domain_i=3)
+            step.x.copy_(batch_x, non_blocking=True); step.y.copy_(batch_y, non_blocking=True); out = step()
+    """
+
+    def __init__(self, model, optimizer, B, F, y_dtype=torch.int16, warmup=2, **kw):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("CUDA graphs need a CUDA device")
+        self.model, self.optimizer, self.kw = model, optimizer, kw
+        self.x = torch.zeros(B, F, dtype=torch.int32, device=dev)
+        self.y = torch.zeros(B, dtype=y_dtype, device=dev)
+        self.graph = None
+        self.out = None
+        self.warmup = warmup
+        self.launches_per_step = None
+
+    def capture(self):
+        """Call after x / y hold a valid batch (the warm-up steps are REAL optimizer steps on that batch)."""
+        lib = self.model_base()._rt.ops.lib
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(self.warmup):
+                self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
+        self.launches_per_step = int(lib.launch_count() - n0)
+        self.optimizer.steps -= 1          # capture records the step but does not execute it
+        return self
+
+    def model_base(self):
+        return getattr(self.model, "base_model_instance", self.model)
+
+    def __call__(self):
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        self.optimizer.steps += 1
+        return self.out

@@ -193,6 +193,16 @@ class MlpGroup:
             return L
         return prev
 
+    def fwd_layer0_only(self, ws: Workspace, X: Mat, B):
+        """The first (concatenated-N) layer alone, with the training epilogue: used by bench.py to time the dominant GEMM."""
+        rt, d = self.rt, self.dims[0]
+        fused_act = not self.bn
+        Y = self._act(ws, 0, B) if fused_act else ws.mat(f"{self.tag}.Z0", B, self.G * d)
+        for (blk, e0, e1) in (self.in_groups or [(0, 0, self.G)]):
+            rt.lin_fwd(X.cols(blk * self.in_dim), self.in_dim, rt.w(self.names["W"][0], e0 * d * self.in_dim), (e1 - e0) * d,
+                       rt.w(self.names["b"][0], e0 * d), Y.cols(e0 * d), B, relu=fused_act,
+                       drop=rt.dropout if fused_act else 0.0, salt=self.salts[0] + 7919 * e0)
+
     def bwd(self, ws: Workspace, X: Mat, dOut: Mat, B, train, dX: Mat | None, accumulate=False):
         """dOut: gradient w.r.t. the group's output: dlogits [B, G] (out_layer), else the gradient of the last
         post-activation [B, G*d_last] (bn) or of the last PRE-activation (no bn: the caller applied the ReLU mask)."""
