@@ -1,0 +1,444 @@
+// bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma with the
+// fp32 accumulator in TMEM -> tcgen05.ld epilogue (bias / ReLU / mask / dropout / bf16-or-fp32 split / split-K).
+// Replaces the nn.Linear / F.linear / autograd matmul call sites of the reference's expert, gate and tower layers
+// (layer.py:185,193; ple.py:83-94; mmoe.py:36-40) on the bf16 path.
+//
+// One persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).  Three mbarrier pipelines: smem full/empty
+// (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator stages so the epilogue of tile i overlaps the
+// MMAs of tile i+1).  Tile = 128 (M) x block_n (runtime, multiple of 16, <= 256) x 64 (K); UMMA 128 x block_n x 16.
+// Operands may be K-major (reduction index contiguous: activations / weights in the forward and input-gradient GEMMs)
+// or MN-major (reduction index is the row: weight-gradient GEMMs reduce over the batch) - both are read in place.
+#include "common.cuh"
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+namespace cdcmdr {
+
+constexpr int TC_BLOCK_M = 128;
+constexpr int TC_BLOCK_K = 64;                       // 64 bf16 = 128 bytes = one swizzle row
+constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_N = 256;
+constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;          // 16 KB
+constexpr int TC_B_BYTES = TC_MAX_N * TC_BLOCK_K * 2;            // 32 KB
+constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int TC_THREADS = 192;
+constexpr int TC_TMEM_COLS = 512;                    // 2 accumulator stages x 256 fp32 columns
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int32_t x, int32_t y) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+struct TcParams {
+  int64_t M, N, K;
+  int32_t G;
+  int32_t a_mn_major, b_mn_major;
+  int64_t a_gmn, a_gk, b_gmn, b_gk;          // per-group offsets (elements) along the MN / K index of each operand
+  int32_t block_n, n_tiles_n, n_tiles_m, split_k, kb_per_split, num_kb;
+  const float* bias; int64_t bias_gs;
+  int64_t n_main;
+  uint16_t* out_main; int64_t ld_main, main_gn;
+  float* out_aux; int64_t ld_aux, aux_gn, aux_split_stride;
+  int32_t act;
+  const uint16_t* mask; int64_t ld_mask, mask_gn; float mask_scale;
+  float drop_p; const uint64_t* seed_dev; uint32_t salt;
+  int32_t accumulate;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B needs 1024-byte alignment
+  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * TC_STAGES), tempty0 = smem_u32(bars + 2 * TC_STAGES + 2);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int64_t tiles_per_group = (int64_t)p.n_tiles_m * p.n_tiles_n * p.split_k;
+  const int64_t total_tiles = tiles_per_group * p.G;
+  const uint32_t stage_tx = (uint32_t)(TC_A_BYTES + (p.b_mn_major ? ((p.block_n + 63) / 64) * 64 : p.block_n) * TC_BLOCK_K * 2);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int g = (int)(tile / tiles_per_group);
+        int64_t r = tile % tiles_per_group;
+        const int z = (int)(r % p.split_k); r /= p.split_k;
+        const int nt = (int)(r % p.n_tiles_n), mt = (int)(r / p.n_tiles_n);
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        const int32_t a_mn = (int32_t)(g * p.a_gmn + (int64_t)mt * TC_BLOCK_M), b_mn = (int32_t)(g * p.b_gmn + (int64_t)nt * p.block_n);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
+          const uint32_t bar = full0 + 8 * stage;
+          mbar_expect_tx(bar, stage_tx);
+          const int32_t ak = (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), bk = (int32_t)(g * p.b_gk + (int64_t)kb * TC_BLOCK_K);
+          if (!p.a_mn_major) tma_load_2d(sa, &map_a, bar, ak, a_mn);                    // box [128 rows (m) x 64 (k)]
+          else { tma_load_2d(sa, &map_a, bar, a_mn, ak); tma_load_2d(sa + 8192, &map_a, bar, a_mn + 64, ak); }   // 2 x [64 (k) x 64 (m)]
+          if (!p.b_mn_major) tma_load_2d(sb, &map_b, bar, bk, b_mn);                    // box [block_n rows (n) x 64 (k)]
+          else for (int j = 0; j * 64 < p.block_n; ++j) tma_load_2d(sb + 8192 * j, &map_b, bar, b_mn + 64 * j, bk);
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+      // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn_major ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn_major ? 1 : 0) << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        int64_t r = tile % tiles_per_group;
+        const int z = (int)(r % p.split_k);
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+            // K-major: 16 bf16 = 32 bytes further inside the 128-byte swizzle row; MN-major: 16 k-rows = 2048 bytes further
+            const uint64_t ad = p.a_mn_major ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
+            const uint64_t bd = p.b_mn_major ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
+            tc_mma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(empty0 + 8 * stage);                 // frees the smem slot when these MMAs retire
+          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc_commit(tfull0 + 8 * acc);                     // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 2..5) ===============================
+    const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t thr = drop_threshold(p.drop_p);
+    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const uint64_t seed = p.drop_p > 0.f ? *p.seed_dev : 0;
+    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int g = (int)(tile / tiles_per_group);
+      int64_t r = tile % tiles_per_group;
+      const int z = (int)(r % p.split_k); r /= p.split_k;
+      const int nt = (int)(r % p.n_tiles_n), mt = (int)(r / p.n_tiles_n);
+      const int64_t m = (int64_t)mt * TC_BLOCK_M + q * 32 + lane;
+      const int64_t n0 = (int64_t)nt * p.block_n;
+      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
+      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
+        uint32_t v[32];
+        tc_ld32(trow + c0, v);
+        const int64_t nb = n0 + c0;
+        if (m < p.M && nb < p.N) {
+          const int ncols = (int)min((int64_t)32, min((int64_t)p.block_n - c0, p.N - nb));
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias && z == 0) {
+            const float* bp = p.bias + g * p.bias_gs + nb;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += __ldg(bp + j);
+          }
+          // columns [nb, nb+ncols): main part (bf16) below n_main, aux part (fp32) at/after n_main
+          const int n_mainc = (int)max((int64_t)0, min((int64_t)ncols, p.n_main - nb));
+          if (n_mainc > 0) {
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = fmaxf(f[j], 0.f);
+            }
+            uint16_t* op = p.out_main + m * p.ld_main + g * p.main_gn + nb;
+            if (p.mask) {
+              const uint16_t* mp = p.mask + m * p.ld_mask + g * p.mask_gn + nb;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = bf16_to_f32(mp[j]) > 0.f ? f[j] * p.mask_scale : 0.f;
+            }
+            if (p.drop_p > 0.f) {
+              const uint64_t base = (uint64_t)(m * p.ld_main + g * p.main_gn + nb);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = mix_hash(seed, p.salt, base + j) >= thr ? f[j] * keep_scale : 0.f;
+            }
+            if (p.accumulate) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] += bf16_to_f32(op[j]);
+            }
+            if (n_mainc == 32 && (((uintptr_t)op) & 15) == 0) {
+              uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) op[j] = f32_to_bf16(f[j]);
+            }
+          }
+          if (n_mainc < ncols) {
+            float* ap = p.out_aux + (int64_t)z * p.aux_split_stride + m * p.ld_aux + g * p.aux_gn + (nb - p.n_main);
+            if (p.accumulate && p.split_k == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) f[j] += ap[j];
+            }
+            if (n_mainc == 0 && ncols == 32 && (((uintptr_t)ap) & 15) == 0) {
+              float4* a4 = reinterpret_cast<float4*>(ap);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) a4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) ap[j] = f[j];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+  }
+}
+
+// sum split-K partials into the destination (fp32), fixed order
+__global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, int64_t stride, int splits, float* __restrict__ out, int64_t rows,
+                                        int64_t cols, int64_t ld_part, int64_t ld_out, int accumulate) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % cols, r = i / cols;
+    float v = 0.f;
+    for (int z = 0; z < splits; ++z) v += part[(int64_t)z * stride + r * ld_part + c];
+    float* o = out + r * ld_out + c;
+    *o = accumulate ? *o + v : v;
+  }
+}
+
+// tiled transpose of a bf16 matrix: dst[c, r] = src[r, c]
+__global__ void transpose_bf16_kernel(const uint16_t* __restrict__ src, int64_t lds, uint16_t* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
+  __shared__ uint16_t tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t r = r0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (r < rows && c < cols) ? src[r * lds + c] : (uint16_t)0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int64_t c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) dst[c * ldd + r] = tile[threadIdx.x][i];
+  }
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    fn = (PFN_cuTensorMapEncodeTiled_v12000)p;
+  }
+  return fn;
+}
+
+// row-major bf16 matrix [rows, cols] with leading dimension ld; box = [box_rows x 64 columns], 128-byte swizzle
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows) {
+  auto enc = get_encode();
+  if (!enc) return fail_msg("cdcmdr: cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cdcmdr: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%u ptr=%p", (int)r,
+             (long long)rows, (long long)cols, (long long)ld, box_rows, ptr);
+    return 3;
+  }
+  return 0;
+}
+
+}  // namespace cdcmdr
+
+using namespace cdcmdr;
+
+extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && p->G >= 1 && p->M >= 0 && p->N >= 0 && p->K >= 1, "bad gemm shape");
+  if (p->M == 0 || p->N == 0) return 0;
+  CDC_REQUIRE(p->A && p->Bt, "null operand");
+  CDC_REQUIRE(((uintptr_t)p->A % 16) == 0 && ((uintptr_t)p->Bt % 16) == 0 && p->lda % 8 == 0 && p->ldb % 8 == 0,
+              "TMA needs 16-byte aligned bf16 operands (pointer and leading dimension)");
+  CDC_REQUIRE(p->n_main >= 0 && p->n_main <= p->N, "n_main out of range");
+  CDC_REQUIRE(p->n_main == 0 || p->out_main, "main output missing");
+  CDC_REQUIRE(p->n_main == p->N || p->out_aux, "aux output missing");
+  CDC_REQUIRE(p->drop_p <= 0.f || p->seed_dev, "dropout needs a device seed");
+  const int split = p->split_k > 1 ? p->split_k : 1;
+  CDC_REQUIRE(split == 1 || p->n_main == 0, "split-K writes fp32 partials only");
+  CDC_REQUIRE(p->G == 1 || (p->a_gk == 0 && p->b_gk == 0) || p->K % TC_BLOCK_K == 0, "grouped K offsets need K to be a multiple of 64");
+
+  TcParams q{};
+  q.M = p->M; q.N = p->N; q.K = p->K; q.G = p->G;
+  q.a_mn_major = p->a_mn_major ? 1 : 0; q.b_mn_major = p->b_mn_major ? 1 : 0;
+  q.a_gmn = p->a_gm; q.a_gk = p->a_gk; q.b_gmn = p->b_gn; q.b_gk = p->b_gk;
+  int bn = p->block_n;
+  if (bn <= 0) {
+    const int64_t nt = ceil_div(p->N, TC_MAX_N);
+    bn = (int)(ceil_div(ceil_div(p->N, nt), 16) * 16);
+  }
+  if (q.b_mn_major) bn = (int)(ceil_div(bn, 64) * 64);            // whole 64-column boxes of the stored [K, N] matrix
+  CDC_REQUIRE(bn >= 16 && bn <= TC_MAX_N && bn % 16 == 0, "block_n must be a multiple of 16 in [16, 256]");
+  q.block_n = bn;
+  q.n_tiles_n = (int)ceil_div(p->N, bn);
+  q.n_tiles_m = (int)ceil_div(p->M, TC_BLOCK_M);
+  q.num_kb = (int)ceil_div(p->K, TC_BLOCK_K);
+  q.split_k = split > q.num_kb ? q.num_kb : split;
+  q.kb_per_split = (int)ceil_div(q.num_kb, q.split_k);
+  q.split_k = (int)ceil_div(q.num_kb, q.kb_per_split);            // no empty slices
+  q.bias = p->bias; q.bias_gs = p->bias_gs; q.n_main = p->n_main;
+  q.out_main = p->out_main; q.ld_main = p->ld_main; q.main_gn = p->main_gn;
+  q.out_aux = p->out_aux; q.ld_aux = p->ld_aux; q.aux_gn = p->aux_gn; q.aux_split_stride = p->aux_split_stride;
+  q.act = p->act; q.mask = p->mask; q.ld_mask = p->ld_mask; q.mask_gn = p->mask_gn; q.mask_scale = p->mask_scale;
+  q.drop_p = p->drop_p; q.seed_dev = p->seed_dev; q.salt = p->salt; q.accumulate = p->accumulate;
+  CDC_REQUIRE(split == 1 || q.split_k == 1 || p->aux_split_stride > 0, "split-K needs aux_split_stride");
+  if (q.split_k != split && split > 1) {
+    // the caller sized its partial buffer for `split` slices; unused slices must read as zero
+    CDC_REQUIRE(false, "split_k exceeds the number of non-empty K slices; use cdcmdr_gemm_bf16_tc_splits() to size it");
+  }
+
+  CUtensorMap ma, mb;
+  if (int rc = make_map(&ma, p->A, p->a_rows, p->a_cols, p->lda, q.a_mn_major ? 64u : (uint32_t)TC_BLOCK_M)) return rc;
+  if (int rc = make_map(&mb, p->Bt, p->b_rows, p->b_cols, p->ldb, q.b_mn_major ? 64u : (uint32_t)bn)) return rc;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    CDC_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
+  const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+  gemm_bf16_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, to_stream(s)>>>(ma, mb, q);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_gemm_bf16_tc_splits(int64_t M, int64_t N, int64_t K, int32_t G, int32_t want) {
+  // number of split-K slices the kernel will actually use for `want` requested slices
+  (void)M; (void)N; (void)G;
+  const int num_kb = (int)ceil_div(K, TC_BLOCK_K);
+  int s = want < 1 ? 1 : want;
+  if (s > num_kb) s = num_kb;
+  const int per = (int)ceil_div(num_kb, s);
+  return (int)ceil_div(num_kb, per);
+}
+
+extern "C" int cdcmdr_splitk_reduce(const float* part, int64_t stride, int32_t splits, float* out, int64_t rows, int64_t cols,
+                                    int64_t ld_part, int64_t ld_out, int32_t accumulate, cdcmdr_stream_t s) {
+  if (rows <= 0 || cols <= 0) return 0;
+  int64_t g = ceil_div(rows * cols, 256);
+  if (g > 8 * kNumSMs) g = 8 * kNumSMs;
+  tc_splitk_reduce_kernel<<<(int)g, 256, 0, to_stream(s)>>>(part, stride, splits, out, rows, cols, ld_part, ld_out, accumulate);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_transpose_bf16(const uint16_t* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols, cdcmdr_stream_t s) {
+  if (rows <= 0 || cols <= 0) return 0;
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+  CDC_REQUIRE(grid.y <= 65535, "transpose: too many rows");
+  transpose_bf16_kernel<<<grid, dim3(32, 8), 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols);
+  CDC_LAUNCHED();
+  return 0;
+}

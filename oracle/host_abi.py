@@ -27,7 +27,7 @@ def _arr(ptr, n, dtype):
     dtype = np.dtype(dtype)
     ct = {np.dtype(np.float32): C.c_float, np.dtype(np.float64): C.c_double, np.dtype(np.int32): C.c_int32,
           np.dtype(np.int64): C.c_int64, np.dtype(np.uint8): C.c_uint8, np.dtype(np.uint16): C.c_uint16,
-          np.dtype(np.int16): C.c_int16, np.dtype(np.uint64): C.c_uint64}[dtype]
+          np.dtype(np.int16): C.c_int16, np.dtype(np.uint64): C.c_uint64, np.dtype(np.uint32): C.c_uint32}[dtype]
     return np.ctypeslib.as_array(C.cast(C.c_void_p(int(ptr)), C.POINTER(ct)), shape=(max(int(n), 1),))
 
 

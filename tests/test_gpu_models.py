@@ -39,30 +39,56 @@ def _rand_ple(seed, B, F, E, T, vocab, dims, tower, device):
 
 
 @pytest.mark.parametrize("B,F,E,T", [(2048, 16, 16, 4), (1000, 23, 16, 3), (513, 5, 8, 2)])
-def test_ple_steps_match_oracle(B, F, E, T):
+def test_ple_gradients_and_steps_match_oracle(B, F, E, T):
+    """Seeded random PLE at larger sizes than the fixtures, against the CPU oracle:
+    (1) drop-in autograd path, step 0: predictions, loss and EVERY gradient (incl. the dense embedding gradient) within
+        1e-4 of each tensor's scale;
+    (2) fused path, 3 steps: step-0 predictions within 1e-4; later steps only statistically - Adam's first steps move
+        every entry by ~lr*sign(g), so the few entries whose gradient is at rounding-noise level flip by up to 2*lr per
+        step in a summation-order dependent way (in the reference as much as here)."""
     dims, tower = ((64, 32), (16,)), (16, 8)
     model, fd, x, y, g = _rand_ple(1, B, F, E, T, 500, dims, tower, "cuda")
     sd = {k: v.detach().cpu().numpy().copy() for k, v in model.state_dict().items()}
     om = O.PLE(fd, E, T, 2, 2, dims, tower, l2_reg_embedding=1e-5, l2_reg_linear=1e-5, l2_reg_dnn=1e-5)
-    oopt = O.Adam()
     model = model.to("cuda").train()
-    opt = cm.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
     xt, yt, gt = (torch.from_numpy(a).cuda() for a in (x, y, g))
+    # (1) gradients through loss.backward()
+    r = O.train_step(om, {k: v.copy() for k, v in sd.items()}, None, x, y, "gather", group=g)
+    pred = model(xt)
+    loss = torch.nn.BCELoss()(pred.gather(1, gt[:, None]).squeeze(1), yt.float()) + model.get_regularization_loss(device="cuda")
+    model.zero_grad()
+    loss.backward()
+    assert float(np.abs(pred.detach().cpu().numpy() - r["pred"]).max()) <= 1e-4
+    assert abs(float(loss) - float(r["loss"])) <= 1e-4 * abs(float(r["loss"]))
+    named = dict(model.named_parameters())
+    assert {k for k, p in named.items() if p.grad is not None} == set(r["grads"])
+    for k, go in r["grads"].items():
+        gm = named[k].grad.detach().cpu().numpy().reshape(go.shape)
+        scale = float(np.abs(go).max())
+        noise = 2e-6 if (k.startswith("towers") and k.endswith(".bias") and not k.endswith("layers.8.bias")) else 0.0
+        err = float(np.abs(gm - go).max())
+        assert err <= 1e-4 * scale + 1e-9 + noise, (k, err, scale)
+    # the regulariser state must not have been disturbed: fused steps start from the same weights
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
+    opt = cm.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+    oopt = O.Adam()
     for s in range(3):
         r = O.train_step(om, sd, oopt, x, y, "gather", group=g)
         out = model.train_step(xt, yt, opt, mode="gather", sel=gt)
         loss, bce, reg = model.step_losses(out)
-        np.testing.assert_allclose(out["pred"].cpu().numpy(), r["pred"], rtol=1e-4, atol=2e-6)
-        assert abs(bce - float(r["bce"])) <= 1e-4 * abs(float(r["bce"])) + 1e-6
+        perr = float(np.abs(out["pred"].cpu().numpy() - r["pred"]).max())
+        assert perr <= (1e-4 if s == 0 else 3e-2), (s, perr)
+        assert abs(bce - float(r["bce"])) <= (1e-4 if s == 0 else 5e-3) * abs(float(r["bce"])) + 1e-6
         assert abs(reg - float(r["reg"])) <= 1e-4 * abs(float(r["reg"])) + 1e-6
-    cur = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
-    for k, v in sd.items():
-        if k.endswith("num_batches_tracked"):
-            assert int(cur[k]) == int(v)
-            continue
-        tol = 6.5e-3 if (k.startswith("towers") and k.endswith(".bias") and not k.endswith("layers.8.bias")) else 2e-5
-        err = np.abs(cur[k] - v).max()
-        assert err <= tol + 1e-4 * np.abs(v).max(), (k, err)
+        cur = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                assert int(cur[k]) == int(v)
+                continue
+            d = np.abs(cur[k].astype(np.float64) - v)
+            assert d.max() <= 2.05e-3 * (s + 1) + 1e-5, (s, k, d.max())
+            if d.size >= 64 and not k.endswith(".bias"):
+                assert (d > 2e-5 * (s + 1)).mean() <= 0.03, (s, k, float((d > 2e-5 * (s + 1)).mean()))
 
 
 def test_eval_forward_is_bit_repeatable_and_matches_train_free_path():
