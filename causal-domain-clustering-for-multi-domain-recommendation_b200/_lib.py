@@ -36,10 +36,10 @@ class GemmF32(C.Structure):
 
 
 class GemmBf16(C.Structure):
-    _fields_ = [("A", P), ("lda", I64), ("a_rows", I64),
-                ("Bt", P), ("ldb", I64), ("b_rows", I64),
+    _fields_ = [("A", P), ("lda", I64), ("a_rows", I64), ("a_cols", I64),
+                ("Bt", P), ("ldb", I64), ("b_rows", I64), ("b_cols", I64),
                 ("M", I64), ("N", I64), ("K", I64),
-                ("G", I32), ("a_gk", I64), ("a_gm", I64), ("b_gn", I64), ("b_gk", I64),
+                ("G", I32), ("a_gm", I64), ("a_gk", I64), ("b_gn", I64), ("b_gk", I64),
                 ("a_mn_major", I32), ("b_mn_major", I32),
                 ("bias", P), ("bias_gs", I64),
                 ("n_main", I64),
@@ -48,6 +48,7 @@ class GemmBf16(C.Structure):
                 ("act", I32),
                 ("mask", P), ("ld_mask", I64), ("mask_gn", I64), ("mask_scale", F32),
                 ("drop_p", F32), ("seed_dev", P), ("salt", U32),
+                ("accumulate", I32),
                 ("split_k", I32), ("aux_split_stride", I64),
                 ("block_n", I32)]
 
@@ -83,11 +84,17 @@ SIGNATURES = {
     "cdcmdr_embed_bwd_adam_dense_exact": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P, P]),
     "cdcmdr_embed_bwd_adam_sparse_lazy": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P]),
     "cdcmdr_gemm_f32": (INT, [C.POINTER(GemmF32), P]),
+    "cdcmdr_gemm_bf16_tc": (INT, [C.POINTER(GemmBf16), P]),
+    "cdcmdr_gemm_bf16_tc_splits": (INT, [I64, I32]),
+    "cdcmdr_splitk_reduce": (INT, [P, I64, I32, P, I64, I64, I64, I64, I32, P]),
+    "cdcmdr_transpose_bf16": (INT, [P, I64, P, I64, I64, I64, P]),
     "cdcmdr_gate_mix_fwd": (INT, [C.POINTER(MixDesc), P, I64, P, I64, P, I64, P, I64, INT, P]),
     "cdcmdr_gate_mix_bwd": (INT, [C.POINTER(MixDesc), P, I64, P, P, I64, P, I64, F32, P, I64, I64, INT, P]),
     "cdcmdr_bn_scratch_bytes": (SZ, [I64]),
     "cdcmdr_bn_fwd": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, I64, I64, P, P]),
-    "cdcmdr_bn_bwd": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, P, I64, P, I64, P, P, INT, I64, I64, P, P]),
+    "cdcmdr_bn_bwd": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, P, I64, INT, P, I64, INT, P, P, INT, I64, I64, P, P]),
+    "cdcmdr_rowdot_fwd": (INT, [P, I64, INT, P, P, P, I64, I64, INT, INT, P]),
+    "cdcmdr_rowdot_bwd": (INT, [P, I64, INT, P, P, I64, P, I64, P, P, I64, INT, INT, P, P]),
     "cdcmdr_sigmoid_select_bce": (INT, [P, P, I64, I64, I32, I32, P, I32, P, INT, P, P, P, P, P, I64, F32, P, P]),
     "cdcmdr_sigmoid_bwd": (INT, [P, P, P, P, I64, I64, I32, P]),
     "cdcmdr_reg_l2_sum": (INT, [P, P, F32, I64, P, P, P]),
@@ -116,7 +123,7 @@ SIGNATURES = {
 }
 
 # entry points that return a status code (everything that launches work)
-_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is INT and k != "cdcmdr_version"}
+_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is INT and k not in ("cdcmdr_version", "cdcmdr_gemm_bf16_tc_splits")}
 
 
 class CdcmdrError(RuntimeError):

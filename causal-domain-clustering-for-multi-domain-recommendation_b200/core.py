@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import BnDesc, GemmF32, MixDesc
+from ._lib import BnDesc, GemmBf16, GemmF32, MixDesc
 
 
 def _addr(t: torch.Tensor, off: int = 0) -> int:
@@ -182,8 +182,63 @@ class Ops:
     def bn_bwd(self, d: BnDesc, Z: Mat, A: Mat | None, dA: Mat, dZ: Mat, dgamma, dbeta, accumulate, B, Cn):
         sc = self.scratch("bn", self.lib.bn_scratch_bytes(Cn))
         self.lib.bn_bwd(C.byref(d), Z.ptr, Z.ld, A.ptr if A is not None else None, A.ld if A is not None else 0,
-                        1 if (A is not None and A.is_bf16) else 0, dA.ptr, dA.ld, dZ.ptr, dZ.ld, dgamma, dbeta,
-                        1 if accumulate else 0, B, Cn, sc.data_ptr(), self.stream)
+                        1 if (A is not None and A.is_bf16) else 0, dA.ptr, dA.ld, 1 if dA.is_bf16 else 0, dZ.ptr, dZ.ld,
+                        1 if dZ.is_bf16 else 0, dgamma, dbeta, 1 if accumulate else 0, B, Cn, sc.data_ptr(), self.stream)
+
+    # ---------------------------------------------------------------- Linear(d, 1) heads
+    def rowdot_fwd(self, A: Mat, w_addr, b_addr, out: Mat, B, G, d):
+        self.lib.rowdot_fwd(A.ptr, A.ld, 1 if A.is_bf16 else 0, w_addr, b_addr, out.ptr, out.ld, B, G, d, self.stream)
+
+    def rowdot_bwd(self, A: Mat, w_addr, dlogit: Mat, dA: Mat | None, dW_addr, db_addr, B, G, d):
+        sc = self.scratch("colsum", self.lib.colsum_scratch_bytes(G * d))
+        self.lib.rowdot_bwd(A.ptr, A.ld, 1 if A.is_bf16 else 0, w_addr, dlogit.ptr, dlogit.ld, dA.ptr if dA is not None else None,
+                            dA.ld if dA is not None else 0, dW_addr, db_addr, B, G, d, sc.data_ptr(), self.stream)
+
+    def cast_f32_bf16(self, src: Mat, dst: Mat, rows, cols):
+        self.lib.cast_f32_bf16(src.ptr, src.ld, dst.ptr, dst.ld, rows, cols, self.stream)
+
+    # ---------------------------------------------------------------- bf16 tensor-core GEMM
+    def gemm_tc(self, *, A, lda, a_rows, a_cols, a_mn, Bt, ldb, b_rows, b_cols, b_mn, M, N, K, G=1, a_gm=0, a_gk=0, b_gn=0, b_gk=0,
+                bias=None, bias_gs=0, n_main=0, out_main=None, ld_main=0, main_gn=0, out_aux=None, ld_aux=0, aux_gn=0, act=0,
+                mask=None, ld_mask=0, mask_gn=0, mask_scale=1.0, drop_p=0.0, seed_ptr=None, salt=0, accumulate=0, split_k=1):
+        """A, Bt, outputs, bias, mask are raw addresses.  split_k='auto' (weight gradients, n_main == 0): enough K slices to
+        fill the machine, partials reduced into out_aux in a fixed order."""
+        if M <= 0 or N <= 0 or G <= 0:
+            return
+        if G > 1 and K % 64 != 0 and (a_gk or b_gk):
+            # a 64-wide K block would straddle two groups: one launch per group over that group's slice of the stored matrices
+            for g in range(G):
+                ao = (g * a_gk * lda if a_mn else g * a_gk) + (g * a_gm if a_mn else g * a_gm * lda)
+                bo = (g * b_gk * ldb if b_mn else g * b_gk) + (g * b_gn if b_mn else g * b_gn * ldb)
+                self.gemm_tc(A=A + 2 * ao, lda=lda, a_rows=K if a_mn else M, a_cols=M if a_mn else K, a_mn=a_mn,
+                             Bt=Bt + 2 * bo, ldb=ldb, b_rows=K if b_mn else N, b_cols=N if b_mn else K, b_mn=b_mn,
+                             M=M, N=N, K=K, G=1, bias=bias + 4 * g * bias_gs if bias else None, bias_gs=0, n_main=n_main,
+                             out_main=out_main + 2 * g * main_gn if out_main else None, ld_main=ld_main,
+                             out_aux=out_aux + 4 * g * aux_gn if out_aux else None, ld_aux=ld_aux, act=act,
+                             mask=mask + 2 * g * mask_gn if mask else None, ld_mask=ld_mask, mask_scale=mask_scale,
+                             drop_p=drop_p, seed_ptr=seed_ptr, salt=salt + 104729 * g, accumulate=accumulate, split_k=split_k)
+            return
+        split, part, stride = 1, None, 0
+        if split_k == "auto":
+            tiles = ((M + 127) // 128) * ((N + 255) // 256) * G
+            want = max(1, min(32, (2 * 148 + tiles - 1) // tiles))
+            split = self.lib.gemm_bf16_tc_splits(K, want)
+        elif split_k > 1:
+            split = self.lib.gemm_bf16_tc_splits(K, split_k)
+        dst = out_aux
+        if split > 1:
+            if n_main != 0 or aux_gn not in (0, M * N) or ld_aux != N:
+                raise ValueError("split-K needs a dense fp32 [G, M, N] destination")
+            stride = G * M * N
+            part = self.scratch("tc_splitk", 4 * split * stride).data_ptr()
+            dst = part
+        d = GemmBf16(A, lda, a_rows, a_cols, Bt, ldb, b_rows, b_cols, M, N, K, G, a_gm, a_gk, b_gn, b_gk, 1 if a_mn else 0,
+                     1 if b_mn else 0, bias, bias_gs, n_main, out_main, ld_main, main_gn, dst, ld_aux, aux_gn, act, mask, ld_mask,
+                     mask_gn, mask_scale, drop_p, seed_ptr if drop_p > 0 else None, salt, accumulate if split == 1 else 0,
+                     split, stride, 0)
+        self.lib.gemm_bf16_tc(C.byref(d), self.stream)
+        if split > 1:
+            self.lib.splitk_reduce(part, stride, split, out_aux, 1, stride, stride, stride, 1 if accumulate else 0, self.stream)
 
     # ---------------------------------------------------------------- loss
     def sigmoid_select_bce(self, logits, lin: Mat | None, B, T, mode, sel, col, target, pred, psel, loss_sum, dlogits,

@@ -414,9 +414,8 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   return 0;
 }
 
-extern "C" int cdcmdr_gemm_bf16_tc_splits(int64_t M, int64_t N, int64_t K, int32_t G, int32_t want) {
+extern "C" int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want) {
   // number of split-K slices the kernel will actually use for `want` requested slices
-  (void)M; (void)N; (void)G;
   const int num_kb = (int)ceil_div(K, TC_BLOCK_K);
   int s = want < 1 ? 1 : want;
   if (s > num_kb) s = num_kb;

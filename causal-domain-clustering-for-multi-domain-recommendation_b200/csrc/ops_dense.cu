@@ -293,11 +293,11 @@ __global__ void bn_apply_kernel(const float* __restrict__ Z, int64_t ldz, T* __r
   }
 }
 
-template <typename T> struct BnBwdStatF {
-  const float* Z; int64_t ldz; const T* A; int64_t lda; const float* dA; int64_t ldda;
+template <typename T, typename TD> struct BnBwdStatF {
+  const float* Z; int64_t ldz; const T* A; int64_t lda; const TD* dA; int64_t ldda;
   const float* mean; const float* invstd; int relu; float keep_scale;
   __device__ __forceinline__ void operator()(int64_t r, int64_t c, double (&a)[2]) const {
-    float dy = dA[r * ldda + c];
+    float dy = ld_act<TD>(dA + r * ldda + c);
     if (relu) dy = ld_act<T>(A + r * lda + c) > 0.f ? dy * keep_scale : 0.f;
     const float xh = (Z[r * ldz + c] - mean[c]) * invstd[c];
     a[0] += (double)dy; a[1] += (double)dy * (double)xh;
@@ -316,9 +316,9 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int c
   if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
 }
 
-template <typename T>
+template <typename T, typename TD, typename TZ>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ Z, int64_t ldz, const T* __restrict__ A, int64_t lda,
-                                    const float* __restrict__ dA, int64_t ldda, float* __restrict__ dZ, int64_t lddz,
+                                    const TD* __restrict__ dA, int64_t ldda, TZ* __restrict__ dZ, int64_t lddz,
                                     int64_t B, int64_t C, const float* __restrict__ gamma, const float* __restrict__ gamma2,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ sums, int relu, float keep_scale, int train) {
@@ -326,7 +326,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ Z, int64_t ldz, co
   const float inv_n = 1.f / (float)B;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = i % C, r = i / C;
-    float dy = dA[r * ldda + c];
+    float dy = ld_act<TD>(dA + r * ldda + c);
     if (relu) dy = ld_act<T>(A + r * lda + c) > 0.f ? dy * keep_scale : 0.f;
     float g = gamma[c];
     if (gamma2) g *= gamma2[c];
@@ -337,9 +337,44 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ Z, int64_t ldz, co
     } else {
       dz = dy * g * invstd[c];
     }
-    dZ[r * lddz + c] = dz;
+    st_act<TZ>(dZ + r * lddz + c, dz);
   }
 }
+
+// ------------------------------------------------------------------------------------------ row dot (Linear(d, 1) heads)
+// logit[b, g] = A[b, g*d : (g+1)*d] . w[g] + bias[g]     (tower output layers, layer.py:192-193)
+template <typename T>
+__global__ void __launch_bounds__(256)
+rowdot_fwd_kernel(const T* __restrict__ A, int64_t lda, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int64_t ldo, int64_t B, int G, int d) {
+  const int64_t total = B * G;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(i % G);
+    const int64_t b = i / G;
+    const T* a = A + b * lda + (int64_t)g * d;
+    const float* wg = w + (int64_t)g * d;
+    float acc = 0.f;
+    for (int k = 0; k < d; ++k) acc = fmaf(ld_act<T>(a + k), wg[k], acc);
+    out[b * ldo + g] = acc + (bias ? bias[g] : 0.f);
+  }
+}
+
+// dA[b, g*d + k] = dlogit[b, g] * w[g, k]
+__global__ void rowdot_bwd_x_kernel(const float* __restrict__ dl, int64_t ldl, const float* __restrict__ w, float* __restrict__ dA,
+                                    int64_t ldda, int64_t B, int G, int d) {
+  const int64_t C = (int64_t)G * d, total = B * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % C, b = i / C;
+    dA[b * ldda + c] = dl[b * ldl + c / d] * w[c];
+  }
+}
+
+template <typename T> struct RowdotWF {
+  const T* A; int64_t lda; const float* dl; int64_t ldl; int d;
+  __device__ __forceinline__ void operator()(int64_t r, int64_t c, double (&a)[1]) const {
+    a[0] += (double)(ld_act<T>(A + r * lda + c) * dl[r * ldl + c / d]);
+  }
+};
 
 // ------------------------------------------------------------------------------------------ sigmoid / select / BCE
 template <typename TT>
@@ -590,7 +625,7 @@ extern "C" int cdcmdr_bn_fwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, 
 }
 
 extern "C" int cdcmdr_bn_bwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
-                             const float* dA, int64_t ldda, float* dZ, int64_t lddz, float* dgamma, float* dbeta,
+                             const void* dA, int64_t ldda, int da_is_bf16, void* dZ, int64_t lddz, int dz_is_bf16, float* dgamma, float* dbeta,
                              int accumulate, int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s) {
   CDC_REQUIRE(p && p->gamma && p->save_mean && p->save_invstd && scratch && dA && dZ, "bad batch-norm arguments");
   CDC_REQUIRE(!p->relu || A, "relu backward needs the forward output");
@@ -601,23 +636,57 @@ extern "C" int cdcmdr_bn_bwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, 
   float* sums = (float*)((char*)scratch + 2 * (size_t)kMaxChunks * (size_t)C * sizeof(double));
   const float keep_scale = p->drop_p > 0.f ? 1.f / (1.f - p->drop_p) : 1.f;
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
-  if (a_is_bf16)
-    col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial,
-        BnBwdStatF<uint16_t>{Z, ldz, (const uint16_t*)A, lda_, dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale});
-  else
-    col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial,
-        BnBwdStatF<float>{Z, ldz, (const float*)A, lda_, dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale});
+  const int combo = (a_is_bf16 ? 4 : 0) | (da_is_bf16 ? 2 : 0) | (dz_is_bf16 ? 1 : 0);
+  CDC_REQUIRE(combo == 0 || combo == 5 || combo == 7, "batch-norm backward dtypes: (A, dA, dZ) must be fp32x3, (bf16, fp32, bf16) or bf16x3");
+#define BNS(TA, TD) col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, \
+      BnBwdStatF<TA, TD>{Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale})
+  if (combo == 0) BNS(float, float); else if (combo == 5) BNS(uint16_t, float); else BNS(uint16_t, uint16_t);
+#undef BNS
   CDC_LAUNCHED();
   bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, chunks, C, sums, dgamma, dbeta, accumulate);
   CDC_LAUNCHED();
   const int g = grid_1d(B * C, 256);
-  if (a_is_bf16)
-    bn_bwd_apply_kernel<uint16_t><<<g, 256, 0, st>>>(Z, ldz, (const uint16_t*)A, lda_, dA, ldda, dZ, lddz, B, C, p->gamma, p->gamma2,
-                                                     p->save_mean, p->save_invstd, sums, p->relu, keep_scale, p->train);
-  else
-    bn_bwd_apply_kernel<float><<<g, 256, 0, st>>>(Z, ldz, (const float*)A, lda_, dA, ldda, dZ, lddz, B, C, p->gamma, p->gamma2,
-                                                  p->save_mean, p->save_invstd, sums, p->relu, keep_scale, p->train);
+#define BNB(TA, TD, TZ) bn_bwd_apply_kernel<TA, TD, TZ><<<g, 256, 0, st>>>(Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, (TZ*)dZ, lddz, \
+      B, C, p->gamma, p->gamma2, p->save_mean, p->save_invstd, sums, p->relu, keep_scale, p->train)
+  if (combo == 0) BNB(float, float, float); else if (combo == 5) BNB(uint16_t, float, uint16_t); else BNB(uint16_t, uint16_t, uint16_t);
+#undef BNB
   CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_rowdot_fwd(const void* A, int64_t lda_, int a_is_bf16, const float* w, const float* bias, float* out, int64_t ldo,
+                                 int64_t B, int G, int d, cdcmdr_stream_t s) {
+  CDC_REQUIRE(A && w && out && G >= 1 && d >= 1, "bad rowdot arguments");
+  if (B <= 0) return 0;
+  const int g = grid_1d(B * G, 256);
+  if (a_is_bf16) rowdot_fwd_kernel<uint16_t><<<g, 256, 0, to_stream(s)>>>((const uint16_t*)A, lda_, w, bias, out, ldo, B, G, d);
+  else rowdot_fwd_kernel<float><<<g, 256, 0, to_stream(s)>>>((const float*)A, lda_, w, bias, out, ldo, B, G, d);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_rowdot_bwd(const void* A, int64_t lda_, int a_is_bf16, const float* w, const float* dlogit, int64_t ldl,
+                                 float* dA, int64_t ldda, float* dW, float* dbias, int64_t B, int G, int d, void* scratch,
+                                 cdcmdr_stream_t s) {
+  CDC_REQUIRE(A && w && dlogit && G >= 1 && d >= 1 && scratch, "bad rowdot arguments");
+  if (B <= 0) return 0;
+  cudaStream_t st = to_stream(s);
+  const int64_t C = (int64_t)G * d;
+  if (dA) {
+    rowdot_bwd_x_kernel<<<grid_1d(B * C, 256), 256, 0, st>>>(dlogit, ldl, w, dA, ldda, B, G, d);
+    CDC_LAUNCHED();
+  }
+  if (dW) {
+    const int chunks = pick_chunks(B, C);
+    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+    double* partial = (double*)scratch;
+    if (a_is_bf16) col_partial_kernel<1><<<grid, 256, 0, st>>>(B, C, chunks, partial, RowdotWF<uint16_t>{(const uint16_t*)A, lda_, dlogit, ldl, d});
+    else col_partial_kernel<1><<<grid, 256, 0, st>>>(B, C, chunks, partial, RowdotWF<float>{(const float*)A, lda_, dlogit, ldl, d});
+    CDC_LAUNCHED();
+    colsum_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, chunks, C, dW, 0);
+    CDC_LAUNCHED();
+  }
+  if (dbias) return cdcmdr_colsum(dlogit, ldl, 0, B, G, dbias, 0, scratch, s);
   return 0;
 }
 

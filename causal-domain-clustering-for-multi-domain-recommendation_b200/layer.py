@@ -272,8 +272,13 @@ class BaseModel(nn.Module):
         rt = self._rt
         E, F = self.embed_dim, self.field_num
         table = self.embedding.embedding_dict.weight
-        X = ws.mat("X", B, F * E)
-        rt.ops.embed_gather(x, self.embedding.offsets_dev, table, X, None, B, F, E, table.shape[0])
+        X = ws.mat("X", B, F * E, rt.act_dtype)
+        if rt.bf16:
+            if (F * E) % 8:
+                raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
+            rt.ops.embed_gather(x, self.embedding.offsets_dev, table, None, X, B, F, E, table.shape[0])
+        else:
+            rt.ops.embed_gather(x, self.embedding.offsets_dev, table, X, None, B, F, E, table.shape[0])
         return X
 
     def _engine_forward(self, x, train, **kw):
@@ -283,6 +288,7 @@ class BaseModel(nn.Module):
         B = x.shape[0]
         rt = self._rt
         ws = rt.ws(B)
+        rt.refresh_operands()
         X = self._gather(ws, x, B)
         logits, lin = self._program_fwd(ws, X, B, train, **kw)
         T = self.n_out
@@ -402,6 +408,7 @@ class BaseModel(nn.Module):
         optimizer.attach(self)
         rt.ensure_opt_state()
         optimizer.tick(rt)                                   # t += 1, dropout seed, Adam scalars
+        rt.refresh_operands()
         X = self._gather(ws, x, B)
         logits, lin = self._program_fwd(ws, X, B, True, **kw)
         pred = ws.get("pred", (B, T))

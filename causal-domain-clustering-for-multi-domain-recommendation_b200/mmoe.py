@@ -61,8 +61,8 @@ class MMoE(BaseModel):
         T, nE, D, h = self.n_tower, self.n_expert, self.embed_output_dim, self.expert_dims[-1]
         H = self._experts.fwd(ws, X, B, train)
         Lg = ws.mat("gates.logits", B, self._n_gcols)
-        rt.lin_fwd(X, D, rt.w("gates.W"), self._n_gcols, rt.w("gates.b"), Lg, B)
-        out = ws.mat("mix.out", B, T * h)
+        rt.lin_fwd(X, D, rt.o("gates.W"), self._n_gcols, rt.o("gates.b"), Lg, B)
+        out = ws.mat("mix.out", B, T * h, rt.act_dtype)
         probs = ws.get("mix.probs", (B, T * nE))
         rt.ops.gate_mix_fwd(self._desc, H, Lg, out, probs, B)
         logits = self._towers.fwd(ws, out, B, train)
@@ -71,11 +71,12 @@ class MMoE(BaseModel):
     def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat):
         rt = self._rt
         T, nE, D, h = self.n_tower, self.n_expert, self.embed_output_dim, self.expert_dims[-1]
-        out = ws.mat("mix.out", B, T * h)
-        dout = ws.mat("mix.dout", B, T * h)
+        act = rt.act_dtype
+        out = ws.mat("mix.out", B, T * h, act)
+        dout = ws.mat("mix.dout", B, T * h, act)
         self._towers.bwd(ws, out, dlogits, B, train, dout)
         H = self._experts._act(ws, len(self.expert_dims) - 1, B)
-        dH = ws.mat("mix.dH", B, nE * h)
+        dH = ws.mat("mix.dH", B, nE * h, act)
         dLg = ws.mat("gates.dlogits", B, self._n_gcols)
         probs = ws.get("mix.probs", (B, T * nE))
         if B == 1:      # BatchNorm skipped (layer.py:202-204): the ReLU/dropout mask is applied here instead
@@ -86,6 +87,7 @@ class MMoE(BaseModel):
         dX = ws.mat("dX", B, D)
         self._experts.bwd(ws, X, dH, B, train, dX)
         rt.ops.colsum(dLg, B, self._n_gcols, rt.g("gates.b"))
-        rt.lin_bwd_w(dLg, X, D, rt.g("gates.W"), self._n_gcols, B)
-        rt.lin_bwd_x(dLg, D, rt.w("gates.W"), self._n_gcols, dX, B, accumulate=True)
+        dLgi = rt.gemm_input(ws, "gates.dlogits_op", dLg, B, self._n_gcols)
+        rt.lin_bwd_w(dLgi, X, D, rt.o("gates.W"), self._n_gcols, B)
+        rt.lin_bwd_x(dLgi, D, rt.o("gates.W"), self._n_gcols, dX, B, accumulate=True)
         return dX

@@ -102,14 +102,20 @@ class PLE(BaseModel):
                                   out_layer=False, in_groups=in_groups)
             lv.n_gates = T if last else T + 1
             w = ns + nsh
-            n_gate_cols = T * w + (0 if last else nE)
-            lv.n_gcols = n_gate_cols + (1 if l == 0 else 0)
+            n_gate_rows = T * w + (0 if last else nE)
+            # gate_groups: (input block, first weight row, last weight row, first column in the logits buffer).  Level 0: every
+            # gate (and the wide linear, last row) reads embed_x -> one GEMM.  Deeper levels: one GEMM per input; each gate's
+            # logits start at a multiple of 8 columns so that bf16 operand views stay 16-byte aligned for TMA.
             if l == 0:
-                lv.gate_groups = [(0, 0, lv.n_gcols)]
+                lv.n_gcols = n_gate_rows + 1
+                lv.gate_groups = [(0, 0, lv.n_gcols, 0)]
+                col = [t * w for t in range(T)] + ([] if last else [T * w])
             else:
-                lv.gate_groups = [(t, t * w, (t + 1) * w) for t in range(T)] + ([] if last else [(T, T * w, T * w + nE)])
+                pw = (w + 7) // 8 * 8
+                lv.gate_groups = [(t, t * w, (t + 1) * w, t * pw) for t in range(T)] + ([] if last else [(T, T * w, T * w + nE, T * pw)])
+                lv.n_gcols = T * pw + (0 if last else (nE + 7) // 8 * 8)
+                col = [t * pw for t in range(T)] + ([] if last else [T * pw])
             lv.max_sel = w if last else nE
-            col = [t * w for t in range(T)] + ([] if last else [T * w])
             n = [w] * T + ([] if last else [nE])
             sel = []
             for t in range(T):
@@ -133,10 +139,10 @@ class PLE(BaseModel):
         for l, lv in enumerate(self._levels):
             H = lv.experts.fwd(ws, xin, B, train)
             Lg = ws.mat(f"cgc{l}.logits", B, lv.n_gcols)
-            for (blk, c0, c1) in lv.gate_groups:
-                rt.lin_fwd(xin.cols(blk * lv.K), lv.K, rt.w(f"cgc{l}.gW", c0 * lv.K), c1 - c0, rt.w(f"cgc{l}.gb", c0),
+            for (blk, r0, r1, c0) in lv.gate_groups:
+                rt.lin_fwd(xin.cols(blk * lv.K), lv.K, rt.o(f"cgc{l}.gW", r0 * lv.K), r1 - r0, rt.o(f"cgc{l}.gb", r0),
                            Lg.cols(c0), B)
-            out = ws.mat(f"cgc{l}.out", B, lv.n_gates * lv.h)
+            out = ws.mat(f"cgc{l}.out", B, lv.n_gates * lv.h, rt.act_dtype)
             probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
             rt.ops.gate_mix_fwd(lv.desc, H, Lg, out, probs, B)
             xin = out
@@ -149,23 +155,26 @@ class PLE(BaseModel):
         T = self.n_tower
         keep = 1.0 / (1.0 - rt.dropout) if (train and rt.dropout > 0) else 1.0
         last_lv = self._levels[-1]
-        dcur = ws.mat("towers.dX", B, T * last_lv.h)
-        self._towers.bwd(ws, ws.mat(f"cgc{self.n_level - 1}.out", B, last_lv.n_gates * last_lv.h), dlogits, B, train, dcur)
+        act = rt.act_dtype
+        dcur = ws.mat("towers.dX", B, T * last_lv.h, act)
+        self._towers.bwd(ws, ws.mat(f"cgc{self.n_level - 1}.out", B, last_lv.n_gates * last_lv.h, act), dlogits, B, train, dcur)
         for l in reversed(range(self.n_level)):
             lv = self._levels[l]
             nE = lv.experts.G
             H = lv.experts._act(ws, len(lv.experts.dims) - 1, B)
-            dH = ws.mat(f"cgc{l}.dH", B, nE * lv.h)
+            dH = ws.mat(f"cgc{l}.dH", B, nE * lv.h, act)
             dLg = ws.mat(f"cgc{l}.dlogits", B, lv.n_gcols)
             probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
             rt.ops.gate_mix_bwd(lv.desc, H, probs, dcur, dH, keep, dLg, B)
-            xin = X if l == 0 else ws.mat(f"cgc{l - 1}.out", B, self._levels[l - 1].n_gates * self._levels[l - 1].h)
-            dxin = ws.mat(f"cgc{l}.dXin", B, lv.n_in * lv.K)
+            xin = X if l == 0 else ws.mat(f"cgc{l - 1}.out", B, self._levels[l - 1].n_gates * self._levels[l - 1].h, act)
+            # the embedding backward consumes an fp32 gradient; deeper levels hand an activation-dtype gradient to gate_mix_bwd
+            dxin = ws.mat(f"cgc{l}.dXin", B, lv.n_in * lv.K, torch.float32 if l == 0 else act)
             lv.experts.bwd(ws, xin, dH, B, train, dxin)
-            rt.ops.colsum(dLg, B, lv.n_gcols, rt.g(f"cgc{l}.gb"))
-            for (blk, c0, c1) in lv.gate_groups:
-                rt.lin_bwd_w(dLg.cols(c0), xin.cols(blk * lv.K), lv.K, rt.g(f"cgc{l}.gW", c0 * lv.K), c1 - c0, B)
-                rt.lin_bwd_x(dLg.cols(c0), lv.K, rt.w(f"cgc{l}.gW", c0 * lv.K), c1 - c0, dxin.cols(blk * lv.K), B,
+            dLgi = rt.gemm_input(ws, f"cgc{l}.dlogits_op", dLg, B, lv.n_gcols)
+            for (blk, r0, r1, c0) in lv.gate_groups:
+                rt.ops.colsum(dLg.cols(c0), B, r1 - r0, rt.g(f"cgc{l}.gb", r0))
+                rt.lin_bwd_w(dLgi.cols(c0), xin.cols(blk * lv.K), lv.K, rt.o(f"cgc{l}.gW", r0 * lv.K), r1 - r0, B)
+                rt.lin_bwd_x(dLgi.cols(c0), lv.K, rt.o(f"cgc{l}.gW", r0 * lv.K), r1 - r0, dxin.cols(blk * lv.K), B,
                              accumulate=True)
             dcur = dxin
         return dcur

@@ -1,7 +1,13 @@
-"""Per-model runtime: the flat parameter arena (weights / gradients / Adam moments / per-element L2 coefficients),
-the BatchNorm buffer arena, workspaces, and the building blocks every model program is made of
-(grouped Linear forward / weight-gradient / input-gradient and the MLP groups of the reference,
-model/layer.py:178-206).  All arithmetic happens in libcdcmdr.so; this file only sequences launches.
+"""Per-model runtime: the flat parameter arena (weights / gradients / Adam moments / per-element L2 coefficients, plus
+the bf16 operand copy of the weights on the tensor-core path), the BatchNorm buffer arena, workspaces, and the building
+blocks every model program is made of (grouped Linear forward / weight-gradient / input-gradient and the MLP groups
+of the reference, model/layer.py:178-206).  All arithmetic happens in libcdcmdr.so; this file only sequences launches.
+
+Two precisions share the same programs:
+  fp32  every operand fp32, GEMMs on CUDA cores (cdcmdr_gemm_f32): the exact-parity path (<= 1e-4 vs the reference);
+  bf16  activations / activation gradients / weight operands bf16, GEMMs on tcgen05 tensor cores with fp32 TMEM
+        accumulation (cdcmdr_gemm_bf16_tc); master weights, gradients, Adam, BatchNorm statistics, gate logits, softmax,
+        loss stay fp32 (<= 2e-2 vs the reference).
 """
 from __future__ import annotations
 
@@ -29,7 +35,7 @@ class Arena:
         self.off[name] = self.n
         self.shape[name] = tuple(int(s) for s in shape)
         self.n += n
-        self.n = (self.n + 3) & ~3          # keep every entry 16-byte aligned for vector loads
+        self.n = (self.n + 7) & ~7          # every block 32-byte aligned in fp32 / 16-byte aligned in the bf16 copy (TMA)
 
     def numel(self, name):
         n = 1
@@ -47,25 +53,40 @@ class Runtime:
         self.ops = Ops(self.device)
         self.params = Arena()          # trainable dense parameters
         self.buffers = Arena()         # BatchNorm running statistics
-        self.W = self.G = self.M = self.V = self.L2 = self.present = self.Bf = None
+        self.W = self.G = self.M = self.V = self.L2 = self.present = self.Bf = self.Wb = None
         self._ws = {}
         self.step_state = None
         self.dropout = 0.0
         self.base_seed = 2000
         self._salt = 0
 
+    @property
+    def bf16(self) -> bool:
+        return self.precision == "bf16"
+
+    @property
+    def act_dtype(self):
+        return torch.bfloat16 if self.bf16 else torch.float32
+
     # ---------------------------------------------------------------- storage
     def allocate(self):
         dev = self.device
-        self.W = torch.zeros(max(self.params.n, 4), dtype=torch.float32, device=dev)
+        self.W = torch.zeros(max(self.params.n, 8), dtype=torch.float32, device=dev)
         self.G = torch.zeros_like(self.W)
         self.L2 = torch.zeros_like(self.W)
         self.present = torch.ones(self.W.numel(), dtype=torch.uint8, device=dev)
-        self.Bf = torch.zeros(max(self.buffers.n, 4), dtype=torch.float32, device=dev)
+        self.Bf = torch.zeros(max(self.buffers.n, 8), dtype=torch.float32, device=dev)
+        self.Wb = torch.zeros(self.W.numel(), dtype=torch.bfloat16, device=dev) if self.bf16 else None
         self.M = self.V = None
         self._ws = {}
         self.ops = Ops(dev)
         self.step_state = None
+
+    def refresh_operands(self):
+        """bf16 path: re-derive the bf16 GEMM operand copy of the (fp32 master) weights; one cast over the arena."""
+        if self.bf16:
+            n = self.W.numel()
+            self.ops.cast_f32_bf16(Mat(self.W, 0, n), Mat(self.Wb, 0, n), 1, n)
 
     def ensure_opt_state(self):
         if self.M is None:
@@ -78,13 +99,13 @@ class Runtime:
         o = self.params.off[name]
         return self.W[o:o + self.params.numel(name)].view(self.params.shape[name])
 
-    def grad_view(self, name) -> torch.Tensor:
-        o = self.params.off[name]
-        return self.G[o:o + self.params.numel(name)].view(self.params.shape[name])
-
     def buf_view(self, name) -> torch.Tensor:
         o = self.buffers.off[name]
         return self.Bf[o:o + self.buffers.numel(name)].view(self.buffers.shape[name])
+
+    def o(self, name, extra=0) -> int:
+        """element offset of a parameter (block) in the arena"""
+        return self.params.off[name] + extra
 
     def w(self, name, extra=0) -> int:
         return self.W.data_ptr() + 4 * (self.params.off[name] + extra)
@@ -112,28 +133,65 @@ class Runtime:
             self.step_state = self.ops.step_state_new()
         return Ops.seed_ptr(self.step_state)
 
-    # ---------------------------------------------------------------- grouped Linear building blocks (fp32 path)
-    def lin_fwd(self, X: Mat, K, w_addr, N, b_addr, Y: Mat, M, *, G=1, x_gs=0, w_gs=None, b_gs=None, y_gs=None,
-                relu=False, drop=0.0, salt=0):
-        """Y[g] = act(X[g] @ W[g]^T + b[g]);  W[g] is [N, K] row-major at w_addr + g*w_gs floats."""
-        self.ops.gemm_f32(A=X.ptr, a_rs=X.ld, a_cs=1, Bt=w_addr, b_rs=K, b_cs=1, Cm=Y.ptr, c_rs=Y.ld, M=M, N=N, K=K, G=G,
-                          a_gs=x_gs, b_gs=N * K if w_gs is None else w_gs, c_gs=N if y_gs is None else y_gs,
-                          bias=b_addr, bias_gs=N if b_gs is None else b_gs, act=1 if relu else 0,
-                          drop_p=drop, seed_ptr=self.seed_ptr if drop > 0 else None, salt=salt)
+    def gemm_input(self, ws: Workspace, name, m: Mat, rows, cols) -> Mat:
+        """A GEMM operand view of an fp32 matrix: itself on the fp32 path, a bf16 copy (ld padded to 8) on the bf16 path."""
+        if not self.bf16 or m.is_bf16:
+            return m
+        ld = (cols + 7) // 8 * 8
+        out = ws.mat(name, rows, ld, torch.bfloat16, zero=True)
+        self.ops.cast_f32_bf16(m, out, rows, cols)
+        return out
 
-    def lin_bwd_w(self, dY: Mat, X: Mat, K, gw_addr, N, M, *, G=1, dy_gs=None, x_gs=0, w_gs=None):
-        """dW[g][n, k] = sum_m dY[g][m, n] * X[g][m, k]  -> gradient arena."""
-        split = Ops.pick_split(N, K, G, M)
-        self.ops.gemm_f32(A=dY.ptr, a_rs=1, a_cs=dY.ld, Bt=X.ptr, b_rs=1, b_cs=X.ld, Cm=gw_addr, c_rs=K, M=N, N=K, K=M, G=G,
-                          a_gs=N if dy_gs is None else dy_gs, b_gs=x_gs, c_gs=N * K if w_gs is None else w_gs, split_k=split)
+    # ---------------------------------------------------------------- grouped Linear building blocks
+    # W[g] is [N, K] row-major at arena element offset w_off + g*N*K; bias [N] at b_off + g*N.
+    def lin_fwd(self, X: Mat, K, w_off, N, b_off, Y: Mat, M, *, G=1, x_gs=0, relu=False, drop=0.0, salt=0):
+        """Y[g] = act(X[g] @ W[g]^T + b[g])   (X[g] = columns g*x_gs.. of X, Y[g] = columns g*N.. of Y)"""
+        sp = self.seed_ptr if drop > 0 else None
+        if X.is_bf16:
+            ybf = Y.is_bf16
+            self.ops.gemm_tc(A=X.ptr, lda=X.ld, a_rows=M, a_cols=(G - 1) * x_gs + K, a_mn=0,
+                             Bt=self.Wb.data_ptr() + 2 * w_off, ldb=K, b_rows=G * N, b_cols=K, b_mn=0,
+                             M=M, N=N, K=K, G=G, a_gk=x_gs, b_gn=N, bias=self.W.data_ptr() + 4 * b_off, bias_gs=N,
+                             n_main=N if ybf else 0, out_main=Y.ptr if ybf else None, ld_main=Y.ld, main_gn=N,
+                             out_aux=None if ybf else Y.ptr, ld_aux=Y.ld, aux_gn=N, act=1 if relu else 0,
+                             drop_p=drop, seed_ptr=sp, salt=salt)
+        else:
+            self.ops.gemm_f32(A=X.ptr, a_rs=X.ld, a_cs=1, Bt=self.W.data_ptr() + 4 * w_off, b_rs=K, b_cs=1, Cm=Y.ptr, c_rs=Y.ld,
+                              M=M, N=N, K=K, G=G, a_gs=x_gs, b_gs=N * K, c_gs=N, bias=self.W.data_ptr() + 4 * b_off, bias_gs=N,
+                              act=1 if relu else 0, drop_p=drop, seed_ptr=sp, salt=salt)
 
-    def lin_bwd_x(self, dY: Mat, K, w_addr, N, dX: Mat, M, *, G=1, dy_gs=None, w_gs=None, dx_gs=0, mask: Mat | None = None,
-                  mask_gs=0, mask_scale=1.0, accumulate=False):
+    def lin_bwd_w(self, dY: Mat, X: Mat, K, w_off, N, M, *, G=1, x_gs=0):
+        """dW[g][n, k] = sum_m dY[g][m, n] * X[g][m, k]  -> gradient arena at w_off (+ g*N*K)."""
+        gaddr = self.G.data_ptr() + 4 * w_off
+        if X.is_bf16:
+            assert dY.is_bf16
+            self.ops.gemm_tc(A=dY.ptr, lda=dY.ld, a_rows=M, a_cols=G * N, a_mn=1,
+                             Bt=X.ptr, ldb=X.ld, b_rows=M, b_cols=(G - 1) * x_gs + K, b_mn=1,
+                             M=N, N=K, K=M, G=G, a_gm=N, b_gn=x_gs, n_main=0, out_aux=gaddr, ld_aux=K, aux_gn=N * K,
+                             split_k="auto")
+        else:
+            split = Ops.pick_split(N, K, G, M)
+            self.ops.gemm_f32(A=dY.ptr, a_rs=1, a_cs=dY.ld, Bt=X.ptr, b_rs=1, b_cs=X.ld, Cm=gaddr, c_rs=K, M=N, N=K, K=M, G=G,
+                              a_gs=N, b_gs=x_gs, c_gs=N * K, split_k=split)
+
+    def lin_bwd_x(self, dY: Mat, K, w_off, N, dX: Mat, M, *, G=1, dx_gs=0, mask: Mat | None = None, mask_gs=0,
+                  mask_scale=1.0, accumulate=False):
         """dX[g][m, k] (+)= sum_n dY[g][m, n] * W[g][n, k]; optional ReLU/dropout mask from the forward activation."""
-        self.ops.gemm_f32(A=dY.ptr, a_rs=dY.ld, a_cs=1, Bt=w_addr, b_rs=1, b_cs=K, Cm=dX.ptr, c_rs=dX.ld, M=M, N=K, K=N, G=G,
-                          a_gs=N if dy_gs is None else dy_gs, b_gs=N * K if w_gs is None else w_gs, c_gs=dx_gs,
-                          mask=mask.ptr if mask is not None else None, mask_rs=mask.ld if mask is not None else 0,
-                          mask_gs=mask_gs, mask_scale=mask_scale, accumulate=1 if accumulate else 0)
+        if dY.is_bf16:
+            xbf = dX.is_bf16
+            assert mask is None or xbf
+            self.ops.gemm_tc(A=dY.ptr, lda=dY.ld, a_rows=M, a_cols=G * N, a_mn=0,
+                             Bt=self.Wb.data_ptr() + 2 * w_off, ldb=K, b_rows=G * N, b_cols=K, b_mn=1,
+                             M=M, N=K, K=N, G=G, a_gk=N, b_gk=N, n_main=K if xbf else 0,
+                             out_main=dX.ptr if xbf else None, ld_main=dX.ld, main_gn=dx_gs,
+                             out_aux=None if xbf else dX.ptr, ld_aux=dX.ld, aux_gn=dx_gs,
+                             mask=mask.ptr if mask is not None else None, ld_mask=mask.ld if mask is not None else 0,
+                             mask_gn=mask_gs, mask_scale=mask_scale, accumulate=1 if accumulate else 0)
+        else:
+            self.ops.gemm_f32(A=dY.ptr, a_rs=dY.ld, a_cs=1, Bt=self.W.data_ptr() + 4 * w_off, b_rs=1, b_cs=K, Cm=dX.ptr, c_rs=dX.ld,
+                              M=M, N=K, K=N, G=G, a_gs=N, b_gs=N * K, c_gs=dx_gs,
+                              mask=mask.ptr if mask is not None else None, mask_rs=mask.ld if mask is not None else 0,
+                              mask_gs=mask_gs, mask_scale=mask_scale, accumulate=1 if accumulate else 0)
 
 
 class MlpGroup:
@@ -150,10 +208,27 @@ class MlpGroup:
         self.rt, self.tag, self.G, self.in_dim, self.dims = rt, tag, G, in_dim, tuple(dims)
         self.names, self.bn, self.out_layer, self.in_groups = names, bn, out_layer, in_groups
         self.salts = [rt.next_salt() for _ in dims]
+        if rt.bf16 and (in_dim % 8 or any(d % 8 for d in dims)):
+            raise ValueError("the bf16 tensor-core path needs every layer width to be a multiple of 8 (TMA alignment)")
 
-    # activation dtype of the fp32 path
     def _act(self, ws: Workspace, j, B) -> Mat:
-        return ws.mat(f"{self.tag}.A{j}", B, self.G * self.dims[j])
+        return ws.mat(f"{self.tag}.A{j}", B, self.G * self.dims[j], self.rt.act_dtype)
+
+    def _layer0(self, X: Mat, Y: Mat, B, fused_act, drop):
+        rt, d, K = self.rt, self.dims[0], self.in_dim
+        W0, b0 = self.names["W"][0], self.names["b"][0]
+        if self.in_groups is None:                               # MLP g reads input block g: one grouped launch
+            rt.lin_fwd(X, K, rt.o(W0), d, rt.o(b0), Y, B, G=self.G, x_gs=K, relu=fused_act, drop=drop, salt=self.salts[0])
+        else:
+            for (blk, e0, e1) in self.in_groups:
+                rt.lin_fwd(X.cols(blk * K), K, rt.o(W0, e0 * d * K), (e1 - e0) * d, rt.o(b0, e0 * d), Y.cols(e0 * d), B,
+                           relu=fused_act, drop=drop, salt=self.salts[0] + 7919 * e0)
+
+    def fwd_layer0_only(self, ws: Workspace, X: Mat, B):
+        """The first (concatenated-N) layer alone, with the training epilogue: used by bench.py to time the dominant GEMM."""
+        fused_act = not self.bn
+        Y = self._act(ws, 0, B) if fused_act else ws.mat(f"{self.tag}.Z0", B, self.G * self.dims[0])
+        self._layer0(X, Y, B, fused_act, self.rt.dropout if fused_act else 0.0)
 
     def fwd(self, ws: Workspace, X: Mat, B, train) -> Mat:
         rt, G = self.rt, self.G
@@ -163,16 +238,10 @@ class MlpGroup:
         for j, d in enumerate(self.dims):
             fused_act = not use_bn
             Y = self._act(ws, j, B) if fused_act else ws.mat(f"{self.tag}.Z{j}", B, G * d)
-            if j == 0 and self.in_groups is None:               # MLP g reads input block g: one grouped launch
-                rt.lin_fwd(prev, prev_d, rt.w(self.names["W"][0]), d, rt.w(self.names["b"][0]), Y, B, G=G, x_gs=prev_d,
-                           relu=fused_act, drop=drop if fused_act else 0.0, salt=self.salts[j])
-            elif j == 0:
-                for (blk, e0, e1) in self.in_groups:
-                    rt.lin_fwd(prev.cols(blk * prev_d), prev_d, rt.w(self.names["W"][0], e0 * d * prev_d), (e1 - e0) * d,
-                               rt.w(self.names["b"][0], e0 * d), Y.cols(e0 * d), B, relu=fused_act,
-                               drop=drop if fused_act else 0.0, salt=self.salts[j] + 7919 * e0)
+            if j == 0:
+                self._layer0(prev, Y, B, fused_act, drop if fused_act else 0.0)
             else:
-                rt.lin_fwd(prev, prev_d, rt.w(self.names["W"][j]), d, rt.w(self.names["b"][j]), Y, B, G=G, x_gs=prev_d,
+                rt.lin_fwd(prev, prev_d, rt.o(self.names["W"][j]), d, rt.o(self.names["b"][j]), Y, B, G=G, x_gs=prev_d,
                            relu=fused_act, drop=drop if fused_act else 0.0, salt=self.salts[j])
             if use_bn:
                 A = self._act(ws, j, B)
@@ -186,25 +255,12 @@ class MlpGroup:
             prev, prev_d = Y, d
         if self.out_layer:
             L = ws.mat(f"{self.tag}.logit", B, G)
-            # logit[b, g] = A_last[b, g*d:(g+1)*d] . Wout[g] + bout[g]
-            rt.ops.gemm_f32(A=prev.ptr, a_rs=prev.ld, a_cs=1, Bt=rt.w(self.names["Wout"]), b_rs=prev_d, b_cs=1, Cm=L.ptr,
-                            c_rs=G, M=B, N=1, K=prev_d, G=G, a_gs=prev_d, b_gs=prev_d, c_gs=1,
-                            bias=rt.w(self.names["bout"]), bias_gs=1)
+            rt.ops.rowdot_fwd(prev, rt.w(self.names["Wout"]), rt.w(self.names["bout"]), L, B, G, prev_d)
             return L
         return prev
 
-    def fwd_layer0_only(self, ws: Workspace, X: Mat, B):
-        """The first (concatenated-N) layer alone, with the training epilogue: used by bench.py to time the dominant GEMM."""
-        rt, d = self.rt, self.dims[0]
-        fused_act = not self.bn
-        Y = self._act(ws, 0, B) if fused_act else ws.mat(f"{self.tag}.Z0", B, self.G * d)
-        for (blk, e0, e1) in (self.in_groups or [(0, 0, self.G)]):
-            rt.lin_fwd(X.cols(blk * self.in_dim), self.in_dim, rt.w(self.names["W"][0], e0 * d * self.in_dim), (e1 - e0) * d,
-                       rt.w(self.names["b"][0], e0 * d), Y.cols(e0 * d), B, relu=fused_act,
-                       drop=rt.dropout if fused_act else 0.0, salt=self.salts[0] + 7919 * e0)
-
     def bwd(self, ws: Workspace, X: Mat, dOut: Mat, B, train, dX: Mat | None, accumulate=False):
-        """dOut: gradient w.r.t. the group's output: dlogits [B, G] (out_layer), else the gradient of the last
+        """dOut: gradient w.r.t. the group's output: dlogits [B, G] fp32 (out_layer), else the gradient of the last
         post-activation [B, G*d_last] (bn) or of the last PRE-activation (no bn: the caller applied the ReLU mask)."""
         rt, G, nl = self.rt, self.G, len(self.dims)
         use_bn = self.bn and B != 1
@@ -214,18 +270,13 @@ class MlpGroup:
         cur = dOut
         if self.out_layer:
             A_last = self._act(ws, nl - 1, B)
-            # dWout[g, k] = sum_b dlogit[b, g] * A_last[b, g*d + k]
-            split = rt.ops.pick_split(1, d_last, G, B)
-            rt.ops.gemm_f32(A=dOut.ptr, a_rs=0, a_cs=dOut.ld, Bt=A_last.ptr, b_rs=1, b_cs=A_last.ld, Cm=rt.g(self.names["Wout"]),
-                            c_rs=d_last, M=1, N=d_last, K=B, G=G, a_gs=1, b_gs=d_last, c_gs=d_last, split_k=split)
-            rt.ops.colsum(dOut, B, G, rt.g(self.names["bout"]))
-            dA = ws.mat(f"{self.tag}.dA{nl - 1}", B, G * d_last)
-            # dA_last[b, g*d + k] = dlogit[b, g] * Wout[g, k]    (ReLU mask applied below / by bn_bwd)
-            mask = None if use_bn else A_last
-            rt.ops.gemm_f32(A=dOut.ptr, a_rs=dOut.ld, a_cs=1, Bt=rt.w(self.names["Wout"]), b_rs=1, b_cs=1, Cm=dA.ptr,
-                            c_rs=dA.ld, M=B, N=d_last, K=1, G=G, a_gs=1, b_gs=d_last, c_gs=d_last,
-                            mask=mask.ptr if mask is not None else None, mask_rs=mask.ld if mask is not None else 0,
-                            mask_gs=d_last, mask_scale=keep)
+            dA = ws.mat(f"{self.tag}.dA{nl - 1}", B, G * d_last)          # fp32
+            rt.ops.rowdot_bwd(A_last, rt.w(self.names["Wout"]), dOut, dA, rt.g(self.names["Wout"]), rt.g(self.names["bout"]),
+                              B, G, d_last)
+            if not use_bn:
+                if rt.bf16:
+                    raise NotImplementedError("bf16 path: batch size 1 skips BatchNorm (layer.py:202-204); train it on the fp32 path")
+                rt.ops.relu_mask(dA, A_last, dA, B, G * d_last, keep)
             cur = dA
         for j in reversed(range(nl)):
             d = self.dims[j]
@@ -234,7 +285,7 @@ class MlpGroup:
                 Z = ws.mat(f"{self.tag}.Z{j}", B, G * d)
                 A = self._act(ws, j, B)
                 sm = ws.get(f"{self.tag}.bnsave{j}", (2, G * d))
-                dZ = ws.mat(f"{self.tag}.dZ{j}", B, G * d)
+                dZ = ws.mat(f"{self.tag}.dZ{j}", B, G * d, rt.act_dtype)
                 desc = rt.ops.bn_desc(rt.w(self.names["gamma"][j]), rt.w(self.names["beta"][j]), None, None,
                                       sm.data_ptr(), sm.data_ptr() + 4 * G * d, train, True, drop_p=drop,
                                       seed_ptr=rt.seed_ptr if drop > 0 else None)
@@ -242,26 +293,26 @@ class MlpGroup:
                 cur = dZ
             # cur is now dZ_j  [B, G*d]
             rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j]))
+            Wj = self.names["W"][j]
             if j == 0 and self.in_groups is None:
-                rt.lin_bwd_w(cur, X, prev_d, rt.g(self.names["W"][0]), d, B, G=G, x_gs=prev_d)
+                rt.lin_bwd_w(cur, X, prev_d, rt.o(Wj), d, B, G=G, x_gs=prev_d)
                 if dX is not None:
-                    rt.lin_bwd_x(cur, prev_d, rt.w(self.names["W"][0]), d, dX, B, G=G, dx_gs=prev_d, accumulate=accumulate)
+                    rt.lin_bwd_x(cur, prev_d, rt.o(Wj), d, dX, B, G=G, dx_gs=prev_d, accumulate=accumulate)
             elif j == 0:
                 for (blk, e0, e1) in self.in_groups:
-                    rt.lin_bwd_w(cur.cols(e0 * d), X.cols(blk * prev_d), prev_d, rt.g(self.names["W"][0], e0 * d * prev_d),
-                                 (e1 - e0) * d, B)
+                    rt.lin_bwd_w(cur.cols(e0 * d), X.cols(blk * prev_d), prev_d, rt.o(Wj, e0 * d * prev_d), (e1 - e0) * d, B)
                 if dX is not None:
                     seen = set()
                     for (blk, e0, e1) in self.in_groups:
                         acc = accumulate or (blk in seen)
                         seen.add(blk)
-                        rt.lin_bwd_x(cur.cols(e0 * d), prev_d, rt.w(self.names["W"][0], e0 * d * prev_d), (e1 - e0) * d,
-                                     dX.cols(blk * prev_d), B, accumulate=acc)
+                        rt.lin_bwd_x(cur.cols(e0 * d), prev_d, rt.o(Wj, e0 * d * prev_d), (e1 - e0) * d, dX.cols(blk * prev_d), B,
+                                     accumulate=acc)
             else:
                 A_prev = self._act(ws, j - 1, B)
-                rt.lin_bwd_w(cur, A_prev, prev_d, rt.g(self.names["W"][j]), d, B, G=G, x_gs=prev_d)
-                dA = ws.mat(f"{self.tag}.dA{j - 1}", B, G * prev_d)
+                rt.lin_bwd_w(cur, A_prev, prev_d, rt.o(Wj), d, B, G=G, x_gs=prev_d)
+                # next gradient: fp32 when BatchNorm consumes it (bn_bwd reads fp32 dA), activation dtype otherwise
+                dA = ws.mat(f"{self.tag}.dA{j - 1}", B, G * prev_d, torch.float32 if use_bn else rt.act_dtype)
                 mask = None if use_bn else A_prev
-                rt.lin_bwd_x(cur, prev_d, rt.w(self.names["W"][j]), d, dA, B, G=G, dx_gs=prev_d, mask=mask, mask_gs=prev_d,
-                             mask_scale=keep)
+                rt.lin_bwd_x(cur, prev_d, rt.o(Wj), d, dA, B, G=G, dx_gs=prev_d, mask=mask, mask_gs=prev_d, mask_scale=keep)
                 cur = dA

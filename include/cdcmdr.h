@@ -104,6 +104,47 @@ typedef struct {
 int cdcmdr_gemm_f32(const cdcmdr_gemm_f32_t* p, cdcmdr_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
+ * tcgen05 / TMEM / TMA bf16 GEMM (tensor-core path of the same call sites), fp32 accumulate in TMEM:
+ *   acc[g](m,n) = sum_k A[g](m,k) * Bt[g](n,k)
+ * Each operand is a STORED row-major bf16 matrix [rows, cols] with leading dimension ld (elements), read in place
+ * through a TMA tensor map (pointer and ld*2 must be 16-byte aligned; out-of-bounds reads are zero):
+ *   K-major  (x_mn_major == 0): stored [MN index, K index]   - activations / weights of forward and input-gradient GEMMs
+ *   MN-major (x_mn_major != 0): stored [K index, MN index]   - weight-gradient GEMMs reduce over the batch (the row index)
+ * Group g starts at (MN, K) offset (g*a_gm, g*a_gk) of A and (g*b_gn, g*b_gk) of Bt; with K offsets K % 64 must be 0.
+ * Columns n < n_main: main = epi(acc + bias) as bf16 at out_main[m*ld_main + g*main_gn + n]
+ *     epi: relu (act==1), * (mask>0)*mask_scale (mask bf16 at mask[m*ld_mask + g*mask_gn + n]), dropout, += if accumulate.
+ * Columns n >= n_main: aux = acc + bias as fp32 at out_aux[m*ld_aux + g*aux_gn + (n - n_main)] (+= if accumulate).
+ * split_k > 1 (requires n_main == 0): K slice z is written to out_aux + z*aux_split_stride; sum the slices with
+ * cdcmdr_splitk_reduce.  cdcmdr_gemm_bf16_tc_splits(K, want) = number of non-empty slices to pass as split_k.
+ * block_n: N tile (multiple of 16, <= 256); 0 = auto.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const uint16_t* A; int64_t lda; int64_t a_rows, a_cols;
+  const uint16_t* Bt; int64_t ldb; int64_t b_rows, b_cols;
+  int64_t M, N, K;
+  int32_t G; int64_t a_gm, a_gk, b_gn, b_gk;
+  int32_t a_mn_major, b_mn_major;
+  const float* bias; int64_t bias_gs;
+  int64_t n_main;
+  uint16_t* out_main; int64_t ld_main, main_gn;
+  float* out_aux; int64_t ld_aux, aux_gn;
+  int32_t act;
+  const uint16_t* mask; int64_t ld_mask, mask_gn; float mask_scale;
+  float drop_p; const uint64_t* seed_dev; uint32_t salt;
+  int32_t accumulate;
+  int32_t split_k; int64_t aux_split_stride;
+  int32_t block_n;
+} cdcmdr_gemm_bf16_t;
+int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t s);
+int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want);
+/* out[r*ld_out + c] (+)= sum_z part[z*stride + r*ld_part + c]   (deterministic order) */
+int cdcmdr_splitk_reduce(const float* part, int64_t stride, int32_t splits, float* out, int64_t rows, int64_t cols,
+                         int64_t ld_part, int64_t ld_out, int32_t accumulate, cdcmdr_stream_t s);
+/* dst[c*ldd + r] = src[r*lds + c] for a bf16 matrix */
+int cdcmdr_transpose_bf16(const uint16_t* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols,
+                          cdcmdr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
  * a5/a9  gate softmax + expert-weighted sum (CGC.forward, MMoE.forward)  ple.py:106-123, mmoe.py:56-60
  * H: expert outputs [B, ldh], expert e at columns [e*h, (e+1)*h).  logits: fp32 [B, ldl]; gate j reads
  * logits[:, gate_col[j] : gate_col[j]+gate_n[j]] and mixes experts gate_sel[j*max_sel + s].
@@ -143,11 +184,25 @@ size_t cdcmdr_bn_scratch_bytes(int64_t C);
 int cdcmdr_bn_fwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, void* A, int64_t lda_, int a_is_bf16,
                   int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s);
 /* backward through dropout/relu/BN: dZ from dA.  A is the forward output (its sign gives the relu/dropout mask).
+ * (A, dA, dZ) dtypes: all fp32, or (bf16, fp32, bf16), or all bf16.
  * dgamma/dbeta fp32 [C] (+= if accumulate).  With gamma2: dgamma is the gradient of the PRODUCT gamma*gamma2
  * and dbeta that of the SUM. */
 int cdcmdr_bn_bwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
-                  const float* dA, int64_t ldda, float* dZ, int64_t lddz, float* dgamma, float* dbeta,
+                  const void* dA, int64_t ldda, int da_is_bf16, void* dZ, int64_t lddz, int dz_is_bf16,
+                  float* dgamma, float* dbeta,
                   int accumulate, int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
+ * a4/a8  the Linear(d, 1) output layer of G towers                       layer.py:192-193
+ * fwd:  logit[b*ldo + g] = A[b, g*d:(g+1)*d] . w[g*d:(g+1)*d] + bias[g]      (A fp32 or bf16)
+ * bwd:  dA[b, g*d+k] = dlogit[b,g]*w[g,k] (fp32, may be NULL) ; dW[g,k] = sum_b dlogit[b,g]*A[b,g*d+k] ;
+ *       dbias[g] = sum_b dlogit[b,g]     (deterministic; scratch >= cdcmdr_colsum_scratch_bytes(G*d))
+ * ------------------------------------------------------------------------------------------- */
+int cdcmdr_rowdot_fwd(const void* A, int64_t lda_, int a_is_bf16, const float* w, const float* bias, float* out,
+                      int64_t ldo, int64_t B, int G, int d, cdcmdr_stream_t s);
+int cdcmdr_rowdot_bwd(const void* A, int64_t lda_, int a_is_bf16, const float* w, const float* dlogit, int64_t ldl,
+                      float* dA, int64_t ldda, float* dW, float* dbias, int64_t B, int G, int d, void* scratch,
+                      cdcmdr_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * a8/a15/a17  tower logit + FeaturesLinear + Sigmoid + tower selection + BCELoss(mean) and its backward

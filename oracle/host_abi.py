@@ -203,6 +203,71 @@ class HostABI:
             Cm[...] = (Cm + v) if p.accumulate else v
         return 0
 
+    # ------------------------------------------------------------------ bf16 tensor-core GEMM (same call sites, bf16 operands)
+    def gemm_bf16_tc_splits(self, K, want):
+        nkb = -(-int(K) // 64)
+        s_ = max(1, min(int(want), nkb))
+        per = -(-nkb // s_)
+        return -(-nkb // per)
+
+    def gemm_bf16_tc(self, ref, s):
+        p = _obj(ref)
+        if p.drop_p > 0:
+            raise NotImplementedError("the emulator does not reproduce the dropout hash; test with dropout=0")
+        A = _mat(p.A, p.a_rows, p.a_cols, p.lda, 1, np.uint16)
+        Bm = _mat(p.Bt, p.b_rows, p.b_cols, p.ldb, 1, np.uint16)
+        split = self.gemm_bf16_tc_splits(p.K, p.split_k) if p.split_k > 1 else 1
+        assert split == max(p.split_k, 1), "pass cdcmdr_gemm_bf16_tc_splits(K, want) as split_k"
+        nkb = -(-p.K // 64)
+        per = -(-nkb // split) * 64
+        for g in range(p.G):
+            am, ak, bn_, bk = g * p.a_gm, g * p.a_gk, g * p.b_gn, g * p.b_gk
+            if p.a_mn_major:
+                a = bf16_to_f32(A[ak:ak + p.K, am:am + p.M]).T
+            else:
+                a = bf16_to_f32(A[am:am + p.M, ak:ak + p.K])
+            if p.b_mn_major:
+                b = bf16_to_f32(Bm[bk:bk + p.K, bn_:bn_ + p.N]).T
+            else:
+                b = bf16_to_f32(Bm[bn_:bn_ + p.N, bk:bk + p.K])
+            # operands shorter than (M|N, K) because the stored matrix ends: TMA zero-fills
+            a = np.pad(a, ((0, p.M - a.shape[0]), (0, p.K - a.shape[1])))
+            b = np.pad(b, ((0, p.N - b.shape[0]), (0, p.K - b.shape[1])))
+            for z in range(split):
+                k0, k1 = z * per, min((z + 1) * per, p.K)
+                acc = (a[:, k0:k1].astype(np.float64) @ b[:, k0:k1].astype(np.float64).T).astype(np.float32)
+                if p.bias and z == 0:
+                    acc = acc + _arr(p.bias + 4 * g * p.bias_gs, p.N, np.float32)[None, :]
+                nm = int(p.n_main)
+                if nm > 0:
+                    v = acc[:, :nm]
+                    if p.act == 1:
+                        v = np.maximum(v, F32(0))
+                    if p.mask:
+                        mk = bf16_to_f32(_mat(p.mask + 2 * g * p.mask_gn, p.M, nm, p.ld_mask, 1, np.uint16))
+                        v = np.where(mk > 0, v * F32(p.mask_scale), F32(0))
+                    om = _mat(p.out_main + 2 * g * p.main_gn, p.M, nm, p.ld_main, 1, np.uint16)
+                    if p.accumulate:
+                        v = v + bf16_to_f32(om)
+                    om[...] = f32_to_bf16(v).reshape(p.M, nm)
+                if nm < p.N:
+                    oa = _mat(p.out_aux + 4 * (z * p.aux_split_stride + g * p.aux_gn), p.M, p.N - nm, p.ld_aux)
+                    v = acc[:, nm:]
+                    oa[...] = (oa + v) if (p.accumulate and split == 1) else v
+        return 0
+
+    def splitk_reduce(self, part, stride, splits, out, rows, cols, ld_part, ld_out, accumulate, s):
+        o = _mat(out, rows, cols, ld_out)
+        acc = np.zeros((rows, cols), dtype=np.float32)
+        for z in range(splits):
+            acc = acc + _mat(part + 4 * z * stride, rows, cols, ld_part)
+        o[...] = o + acc if accumulate else acc
+        return 0
+
+    def transpose_bf16(self, src, lds, dst, ldd, rows, cols, s):
+        _mat(dst, cols, rows, ldd, 1, np.uint16)[...] = _mat(src, rows, cols, lds, 1, np.uint16).T
+        return 0
+
     # ------------------------------------------------------------------ gate softmax + mix (ple.py:106-123, mmoe.py:56-60)
     def _mixdesc(self, ref):
         d = _obj(ref)
@@ -286,10 +351,10 @@ class HostABI:
         _wr(_act_mat(A, B, Cn, lda, a_is_bf16), v.astype(np.float32), a_is_bf16)
         return 0
 
-    def bn_bwd(self, ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, dZ, lddz, dgamma, dbeta, accumulate, B, Cn, scratch, s):
+    def bn_bwd(self, ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, da_is_bf16, dZ, lddz, dz_is_bf16, dgamma, dbeta, accumulate, B, Cn, scratch, s):
         p = _obj(ref)
         z = _mat(Z, B, Cn, ldz)
-        dy = _mat(dA, B, Cn, ldda).astype(np.float32)
+        dy = _rd(_act_mat(dA, B, Cn, ldda, da_is_bf16), da_is_bf16).astype(np.float32)
         if p.relu:
             a = _rd(_act_mat(A, B, Cn, lda, a_is_bf16), a_is_bf16)
             keep = F32(1.0 / (1.0 - p.drop_p)) if p.drop_p > 0 else F32(1)
@@ -312,7 +377,29 @@ class HostABI:
             dz = gam * si * (dy - s0 * inv_n - xh * s1 * inv_n)
         else:
             dz = dy * gam * si
-        _mat(dZ, B, Cn, lddz)[...] = dz
+        _wr(_act_mat(dZ, B, Cn, lddz, dz_is_bf16), dz.astype(np.float32), dz_is_bf16)
+        return 0
+
+    # ------------------------------------------------------------------ Linear(d, 1) heads (layer.py:192-193)
+    def rowdot_fwd(self, A, lda, a_is_bf16, w, bias, out, ldo, B, G, d, s):
+        a = _rd(_act_mat(A, B, G * d, lda, a_is_bf16), a_is_bf16).reshape(B, G, d)
+        ww = _arr(w, G * d, np.float32).reshape(G, d)
+        v = np.einsum("bgk,gk->bg", a.astype(np.float32), ww).astype(np.float32)
+        if bias:
+            v = v + _arr(bias, G, np.float32)[None, :]
+        _mat(out, B, G, ldo)[...] = v
+        return 0
+
+    def rowdot_bwd(self, A, lda, a_is_bf16, w, dlogit, ldl, dA, ldda, dW, dbias, B, G, d, scratch, s):
+        a = _rd(_act_mat(A, B, G * d, lda, a_is_bf16), a_is_bf16).reshape(B, G, d)
+        ww = _arr(w, G * d, np.float32).reshape(G, d)
+        dl = _mat(dlogit, B, G, ldl)
+        if dA:
+            _mat(dA, B, G * d, ldda)[...] = (dl[:, :, None] * ww[None]).reshape(B, G * d)
+        if dW:
+            _arr(dW, G * d, np.float32)[...] = np.einsum("bg,bgk->gk", dl.astype(np.float64), a.astype(np.float64)).reshape(-1)
+        if dbias:
+            _arr(dbias, G, np.float32)[...] = dl.astype(np.float64).sum(0)
         return 0
 
     # ------------------------------------------------------------------ sigmoid / selection / BCE (layer.py:48-56; cdc.py:99-111; run.py:723)

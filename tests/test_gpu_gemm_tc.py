@@ -1,0 +1,116 @@
+"""tcgen05/TMA bf16 GEMM (cdcmdr_gemm_bf16_tc) against the host restatement on identical bf16 inputs.  The fp32
+accumulation order differs (tensor core vs float64 dot), so fp32 outputs agree to ~1e-5 of the tensor scale and bf16
+outputs to one bf16 ulp (2^-8 relative) of the tensor scale."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+import cdcmdr_b200 as cm
+from oracle.host_abi import HostABI, f32_to_bf16
+from tests.test_gpu_ops import Env, check
+
+pytestmark = pytest.mark.gpu
+L = cm._lib
+
+# name: M, N, K, G, a_mn, b_mn, n_main(-1 = all main), extras
+CASES = {
+    "k_major_exact_tile": (128, 256, 64, 1, 0, 0, -1, {}),
+    "k_major_k_tail": (300, 240, 368, 1, 0, 0, -1, dict(bias=True, act=1)),
+    "k_major_multi_tile": (1000, 2587, 368, 1, 0, 0, 2560, dict(bias=True, act=1)),
+    "k_major_aux_only": (513, 27, 128, 1, 0, 0, 0, dict(bias=True)),
+    "grouped_k_offsets": (777, 128, 256, 5, 0, 0, -1, dict(bias=True, act=1, a_gk=256, b_gn=128, main_gn=128)),
+    "mask_accumulate": (260, 368, 2587, 1, 0, 0, -1, dict(mask=True, accumulate=True)),
+    "b_mn_major_dgrad": (640, 368, 2587, 1, 0, 1, -1, {}),
+    "grouped_b_mn_major": (400, 256, 128, 3, 0, 1, -1, dict(mask=True, a_gk=128, b_gk=128, main_gn=256)),
+    "wgrad_both_mn_major": (2587, 368, 4096, 1, 1, 1, 0, {}),
+    "wgrad_split_k": (200, 130, 8192, 1, 1, 1, 0, dict(split_k=6)),
+    "wgrad_grouped": (128, 256, 2048, 4, 1, 1, 0, dict(a_gm=128, b_gn=256, aux_gn=256 * 128, split_k=3, group_rows=True)),
+    "tiny": (5, 16, 8, 1, 0, 0, -1, {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gemm_bf16_tc(name):
+    M, N, K, G, a_mn, b_mn, n_main, ex = CASES[name]
+    n_main = N if n_main < 0 else n_main
+
+    def bf(e, r, c, pad=0, scale=1.0):
+        ld = (c + 7) // 8 * 8 + (8 if pad else 0)
+        v = (e.rng.standard_normal((r, ld)) * scale).astype(np.float32)
+        t = torch.from_numpy(f32_to_bf16(v).reshape(r, ld).view(np.int16)).to(e.dev)
+        e.keep.append(t)
+        return t, ld
+
+    def fn(lib, e):
+        a_gm, a_gk, b_gn, b_gk = ex.get("a_gm", 0), ex.get("a_gk", 0), ex.get("b_gn", 0), ex.get("b_gk", 0)
+        if a_mn:
+            A, lda = bf(e, K, max(M, a_gm * (G - 1) + M), pad=8)
+            a_rows, a_cols = K, max(M, a_gm * (G - 1) + M)
+        else:
+            A, lda = bf(e, M, max(K, a_gk * (G - 1) + K), pad=8)
+            a_rows, a_cols = M, max(K, a_gk * (G - 1) + K)
+        if b_mn:
+            Bt, ldb = bf(e, max(K, b_gk * (G - 1) + K), max(N, b_gn * (G - 1) + N), pad=0 if N % 8 == 0 else 8 - N % 8, scale=0.1)
+            b_rows, b_cols = max(K, b_gk * (G - 1) + K), max(N, b_gn * (G - 1) + N)
+        else:
+            Bt, ldb = bf(e, max(N, b_gn * (G - 1) + N), K, pad=0 if K % 8 == 0 else 8 - K % 8, scale=0.1)
+            b_rows, b_cols = max(N, b_gn * (G - 1) + N), K
+        main_gn = ex.get("main_gn", 0)
+        ld_main = max(n_main, main_gn * (G - 1) + n_main) + 8
+        out_main, _ = bf(e, M, ld_main - 8, pad=8)
+        n_aux = N - n_main
+        aux_gn = ex.get("aux_gn", 0)
+        want = ex.get("split_k", 1)
+        split = lib.gemm_bf16_tc_splits(K, want) if want > 1 else 1
+        if ex.get("group_rows"):                      # each group's [M, N] block stacked: aux_gn = M*N, ld = N
+            ld_aux = n_aux
+            aux_elems = G * M * n_aux
+        else:
+            ld_aux = max(n_aux, 1) + 4
+            aux_elems = M * ld_aux
+        out_aux = e.f32(max(split, 1) * aux_elems)
+        bias = e.f32(G, N) if ex.get("bias") else None
+        mask, ld_mask = (bf(e, M, ld_main - 8, pad=8)) if ex.get("mask") else (None, 0)
+        d = L.GemmBf16(A.data_ptr(), lda, a_rows, a_cols, Bt.data_ptr(), ldb, b_rows, b_cols, M, N, K, G, a_gm, a_gk, b_gn, b_gk,
+                       a_mn, b_mn, bias.data_ptr() if bias is not None else None, N, n_main,
+                       out_main.data_ptr() if n_main else None, ld_main, main_gn,
+                       out_aux.data_ptr() if n_aux else None, ld_aux, aux_gn, ex.get("act", 0),
+                       mask.data_ptr() if mask is not None else None, ld_mask, main_gn, 1.25, 0.0, None, 0,
+                       1 if ex.get("accumulate") else 0, split, aux_elems, 0)
+        lib.gemm_bf16_tc(C.byref(d), 0)
+        outs = []
+        if n_main:
+            outs.append(out_main)
+        if n_aux:
+            if split > 1:
+                red = e.zeros(aux_elems)
+                lib.splitk_reduce(out_aux.data_ptr(), aux_elems, split, red.data_ptr(), 1, aux_elems, aux_elems, aux_elems, 0, 0)
+                outs.append(red)
+            else:
+                outs.append(out_aux)
+        return outs
+
+    cpu, gpu = Env(11).run(fn)
+    i = 0
+    if n_main:
+        a = (cpu[i].view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+        b = (gpu[i].view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+        scale = max(float(np.abs(a).max()), 1e-30)
+        err = float(np.abs(a - b).max())
+        assert err <= 2 ** -7 * scale, f"{name} bf16 main: err {err:.3e} scale {scale:.3e}"
+        assert float((np.abs(a - b) > 2 ** -9 * scale).mean()) < 0.02, f"{name}: too many bf16 entries differ"
+        i += 1
+    if n_main < N:
+        check(cpu[i], gpu[i], tol=3e-5, what=f"{name} fp32 aux")
+
+
+def test_transpose_bf16():
+    def fn(lib, e):
+        src = e.ints(-30000, 30000, (300, 77), np.int16)
+        dst = e.zeros(77, 304, dtype=torch.int16)
+        lib.transpose_bf16(src.data_ptr(), 77, dst.data_ptr(), 304, 300, 77, 0)
+        return [dst]
+    cpu, gpu = Env().run(fn)
+    assert np.array_equal(cpu[0], gpu[0])

@@ -250,7 +250,7 @@ def test_batch_norm_fwd_bwd(B, Cn, train, relu, g2):
         dA = e.f32(B, Cn)
         dZ = e.zeros(B, Cn)
         dg, db = e.f32(Cn), e.f32(Cn)
-        lib.bn_bwd(C.byref(d), Z.data_ptr(), ldz, A.data_ptr(), Cn, 0, dA.data_ptr(), Cn, dZ.data_ptr(), Cn, dg.data_ptr(),
+        lib.bn_bwd(C.byref(d), Z.data_ptr(), ldz, A.data_ptr(), Cn, 0, dA.data_ptr(), Cn, 0, dZ.data_ptr(), Cn, 0, dg.data_ptr(),
                    db.data_ptr(), 1, B, Cn, sc.data_ptr(), 0)
         return [A, sm, si, rm, rv, dZ, dg, db]
     both(fn, tol=3e-5)
