@@ -1,0 +1,65 @@
+"""GPU probe: times cdcmdr_gemm_bf16_tc at the C4 shapes with epilogue variants (not a test, not the bench)."""
+import ctypes as C
+import json
+import sys
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import cdcmdr_b200 as cm
+
+L = cm._lib
+lib = L.load()
+dev = torch.device("cuda")
+st = torch.zeros(48, dtype=torch.uint8, device=dev)
+lib.step_state_init(st.data_ptr(), 1, 0)
+seed_ptr = st.data_ptr() + 8
+
+
+def run(name, M, N, K, a_mn=0, b_mn=0, out="bf16", act=0, drop=0.0, bias=True, mask=False, split=1, block_n=0, reps=10):
+    if a_mn:
+        A = torch.randn(K, M, device=dev).to(torch.bfloat16); lda, ar, ac = M, K, M
+    else:
+        A = torch.randn(M, K, device=dev).to(torch.bfloat16); lda, ar, ac = K, M, K
+    if b_mn:
+        B = torch.randn(K, N, device=dev).to(torch.bfloat16); ldb, br, bc = N, K, N
+    else:
+        B = torch.randn(N, K, device=dev).to(torch.bfloat16); ldb, br, bc = K, N, K
+    bias_t = torch.randn(N, device=dev) if bias else None
+    n_main = N if out == "bf16" else 0
+    om = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if n_main else None
+    s = lib.gemm_bf16_tc_splits(K, split) if split > 1 else 1
+    oa = torch.empty(max(s, 1) * M * N, device=dev) if not n_main else None
+    mk = torch.randn(M, N, device=dev).to(torch.bfloat16) if mask else None
+    d = L.GemmBf16(A.data_ptr(), lda, ar, ac, B.data_ptr(), ldb, br, bc, M, N, K, 1, 0, 0, 0, 0, a_mn, b_mn,
+                   bias_t.data_ptr() if bias else None, 0, n_main, om.data_ptr() if om is not None else None, N, 0,
+                   oa.data_ptr() if oa is not None else None, N, 0, act, mk.data_ptr() if mask else None, N, 0, 1.25,
+                   drop, seed_ptr if drop > 0 else None, 3, 0, s, M * N, block_n)
+    for _ in range(3):
+        lib.gemm_bf16_tc(C.byref(d), 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        lib.gemm_bf16_tc(C.byref(d), 0)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 1e3 / reps
+    tf = 2.0 * M * N * K / (us * 1e-6) / 1e12
+    by = (M * K + N * K) * 2 + M * N * (2 if n_main else 4 * s) + (M * N * 2 if mask else 0)
+    print(json.dumps(dict(name=name, M=M, N=N, K=K, us=round(us, 1), tflops=round(tf, 1), gbs=round(by / us / 1e3, 1))), flush=True)
+
+
+B = 65536
+run("l0_fwd_plain", B, 2560, 368, bias=False)
+run("l0_fwd_bias", B, 2560, 368)
+run("l0_fwd_bias_relu", B, 2560, 368, act=1)
+run("l0_fwd_bias_relu_drop", B, 2560, 368, act=1, drop=0.2)
+run("l0_fwd_bn128", B, 2560, 368, act=1, block_n=128)
+run("l0_fwd_f32out", B, 2560, 368, out="f32")
+run("l0b_fwd(256->128 x10 as one)", B, 128, 256, act=1, drop=0.2)
+run("l0_dgrad (N=368,K=2560,b_mn)", B, 368, 2560, b_mn=1, out="f32")
+run("l0_dgrad_bf16", B, 368, 2560, b_mn=1)
+run("l0_wgrad (M=2560,N=368,K=B)", 2560, 368, B, a_mn=1, b_mn=1, out="f32", split=6)
+run("l0_wgrad_nosplit", 2560, 368, B, a_mn=1, b_mn=1, out="f32", split=1)
+run("l1_mask_dgrad (N=256,K=128)", B, 256, 128, b_mn=1, mask=True)
+run("big_square", 8192, 8192, 8192, bias=False)
