@@ -44,8 +44,7 @@ inline cudaStream_t to_stream(cdcmdr_stream_t s) { return reinterpret_cast<cudaS
 
 __host__ __device__ static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-// Stateless dropout mask: keep iff hash(seed, salt, idx) >= p * 2^32.  Same bits in forward (epilogues /
-// BN kernels) and in tests/oracle; the backward never regenerates it (the stored activation is 0 where dropped).
+// 64-bit mixer (splitmix64 finaliser): derives the per-step dropout seed from (base seed, step) in cdcmdr_step_tick.
 __host__ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t salt, uint64_t idx) {
   uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1) + ((uint64_t)salt << 32 | salt);
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -53,9 +52,28 @@ __host__ __device__ __forceinline__ uint32_t mix_hash(uint64_t seed, uint32_t sa
   z = z ^ (z >> 31);
   return (uint32_t)(z >> 32);
 }
-__host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
-  double t = (double)p * 4294967296.0;
-  return t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t;
+
+// Stateless dropout mask (nn.Dropout, layer.py:189).  One 32-bit hash decides TWO neighbouring columns (16 bits each):
+// element (row, col) is kept iff the (col & 1)-th half of drop_hash_pair(s0, row, col >> 1) is >= p * 2^16.  32-bit
+// integer multiplies only, so the GEMM epilogues stay cheaper than the MMAs they overlap.  Every kernel that applies
+// dropout uses these helpers; the backward never regenerates the mask (the stored activation is 0 where dropped).
+__host__ __device__ __forceinline__ uint32_t drop_s0(uint64_t seed, uint32_t salt) {
+  return (uint32_t)seed ^ ((uint32_t)(seed >> 32) * 0xC2B2AE35u) ^ (salt * 0x27D4EB2Fu);
+}
+__host__ __device__ __forceinline__ uint32_t drop_mix32(uint32_t x) {           // "lowbias32" integer finaliser
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+constexpr uint32_t kDropRowMul = 0x9E3779B1u, kDropColMul = 0x85EBCA77u;
+__host__ __device__ __forceinline__ uint32_t drop_hash_pair(uint32_t s0, uint32_t row, uint32_t colpair) {
+  return drop_mix32(row * kDropRowMul + colpair * kDropColMul + s0);
+}
+__host__ __device__ __forceinline__ uint32_t drop_thr16(float p) {
+  const float t = p * 65536.f + 0.5f;
+  return t >= 65535.f ? 65535u : (t <= 0.f ? 0u : (uint32_t)t);
+}
+__host__ __device__ __forceinline__ bool drop_keep(uint32_t s0, uint32_t thr16, uint32_t row, uint32_t col) {
+  return ((drop_hash_pair(s0, row, col >> 1) >> ((col & 1u) * 16u)) & 0xFFFFu) >= thr16;
 }
 
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(((uint32_t)h) << 16); }

@@ -21,8 +21,8 @@ __device__ __forceinline__ void epilogue_store(const EpiF32& e, int g, int64_t m
   if (e.act == 1) v = fmaxf(v, 0.f);
   if (e.mask) v = (e.mask[g * e.mask_gs + m * e.mask_rs + n] > 0.f) ? v * e.mask_scale : 0.f;
   if (e.drop_p > 0.f) {
-    const uint64_t idx = (uint64_t)(g * e.c_gs + m * e.c_rs + n);
-    v = (mix_hash(*e.seed_dev, e.salt, idx) >= drop_threshold(e.drop_p)) ? v * (1.f / (1.f - e.drop_p)) : 0.f;
+    const bool keep = drop_keep(drop_s0(*e.seed_dev, e.salt), drop_thr16(e.drop_p), (uint32_t)m, (uint32_t)(g * e.c_gs + n));
+    v = keep ? v * (1.f / (1.f - e.drop_p)) : 0.f;
   }
   float* c = e.C + g * e.c_gs + m * e.c_rs + n;
   *c = e.accumulate ? (*c + v) : v;

@@ -1,14 +1,22 @@
 // bf16 tensor-core GEMM for sm_100a: TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma with the
-// fp32 accumulator in TMEM -> tcgen05.ld epilogue (bias / ReLU / mask / dropout / bf16-or-fp32 split / split-K).
+// fp32 accumulator in TMEM -> tcgen05.ld epilogue (bias / ReLU / mask / dropout / bf16-or-fp32 split / split-K) ->
+// swizzled shared-memory staging -> TMA store.
 // Replaces the nn.Linear / F.linear / autograd matmul call sites of the reference's expert, gate and tower layers
 // (layer.py:185,193; ple.py:83-94; mmoe.py:36-40) on the bf16 path.
 //
-// One persistent CTA per SM, 192 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..5 = epilogue (warp w owns TMEM lanes 32*(w%4)..+31).  Three mbarrier pipelines: smem full/empty
-// (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two accumulator stages so the epilogue of tile i overlaps the
-// MMAs of tile i+1).  Tile = 128 (M) x block_n (runtime, multiple of 16, <= 256) x 64 (K); UMMA 128 x block_n x 16.
+// One persistent CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..9 = epilogue (warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the tile's
+// 64-column chunks).  Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
+// accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1).  Tile = 128 (M) x block_n (runtime,
+// multiple of 16, <= 256) x 64 (K); UMMA 128 x block_n x 16.  The number of smem stages is whatever fits next to the
+// 32 KB of epilogue staging (4 at block_n = 256).
 // Operands may be K-major (reduction index contiguous: activations / weights in the forward and input-gradient GEMMs)
 // or MN-major (reduction index is the row: weight-gradient GEMMs reduce over the batch) - both are read in place.
+//
+// Why the epilogue looks the way it does (B200, probe of 2026-10-18, M=65536 N=2560 K=368): with K this short a tile's
+// MMAs take ~3k cycles, so the epilogue is on the critical path: per-thread row stores, 32 scalar bias loads per chunk
+// and a 64-bit dropout hash per element cost 190 / 430 / 1045 us against ~75 us of MMA time.  Hence: 8 epilogue warps,
+// bias staged in smem once per tile, a 32-bit hash per column PAIR, and 128-byte-row TMA stores from swizzled staging.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -17,13 +25,16 @@ namespace cdcmdr {
 
 constexpr int TC_BLOCK_M = 128;
 constexpr int TC_BLOCK_K = 64;                       // 64 bf16 = 128 bytes = one swizzle row
-constexpr int TC_STAGES = 4;
+constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_N = 256;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;          // 16 KB
-constexpr int TC_B_BYTES = TC_MAX_N * TC_BLOCK_K * 2;            // 32 KB
-constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
-constexpr int TC_SMEM_BYTES = TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;               // 320
+constexpr int TC_STAGING_WARP_BYTES = 32 * 128;                  // 32 rows x 64 bf16, 128B-swizzled
+constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * TC_STAGING_WARP_BYTES;
+constexpr int TC_BIAS_BYTES = 2 * TC_MAX_N * 4;                  // one bias tile per accumulator stage
+constexpr int TC_BAR_BYTES = 256;
+constexpr int TC_SMEM_LIMIT = 232448;                            // 227 KB opt-in maximum per CTA
 constexpr int TC_TMEM_COLS = 512;                    // 2 accumulator stages x 256 fp32 columns
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -53,6 +64,15 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int32_t x, int32_t y) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -66,7 +86,8 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+// 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (tile row), register j = column j.  No wait inside.
+__device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
       "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -76,8 +97,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
@@ -97,6 +118,7 @@ struct TcParams {
   int32_t a_mn_major, b_mn_major;
   int64_t a_gmn, a_gk, b_gmn, b_gk;          // per-group offsets (elements) along the MN / K index of each operand
   int32_t block_n, n_tiles_n, n_tiles_m, split_k, kb_per_split, num_kb;
+  int32_t stages, stage_bytes;
   const float* bias; int64_t bias_gs;
   int64_t n_main;
   uint16_t* out_main; int64_t ld_main, main_gn;
@@ -105,24 +127,74 @@ struct TcParams {
   const uint16_t* mask; int64_t ld_mask, mask_gn; float mask_scale;
   float drop_p; const uint64_t* seed_dev; uint32_t salt;
   int32_t accumulate;
+  int32_t tma_store;                         // out_main is written through map_c (alignment checked by the host)
 };
 
+// Epilogue math for 32 consecutive columns [col0, col0+32) of one row; f in/out.  Returns packed bf16 pairs in o[16].
+struct EpiCtx {
+  int act; float mask_scale; bool has_mask, has_drop; uint32_t s0, thr16; float keep_scale;
+};
+
+__device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], const float* bias_s /* smem, 32 floats, or null */,
+                                           const uint4* mask_row /* 4 x uint4 = 32 bf16, or null */, uint32_t row, uint32_t col0,
+                                           uint32_t (&o)[16]) {
+  if (bias_s) {
+    const float4* b4 = reinterpret_cast<const float4*>(bias_s);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { const float4 b = b4[j]; f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w; }
+  }
+  if (c.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (c.has_mask) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 mk = mask_row[j];
+      const uint32_t w[4] = {mk.x, mk.y, mk.z, mk.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        // bf16 > 0  <=>  sign bit clear and not zero
+        const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+        f[8 * j + 2 * k] = (lo != 0u && lo < 0x8000u) ? f[8 * j + 2 * k] * c.mask_scale : 0.f;
+        f[8 * j + 2 * k + 1] = (hi != 0u && hi < 0x8000u) ? f[8 * j + 2 * k + 1] * c.mask_scale : 0.f;
+      }
+    }
+  }
+  if (c.has_drop) {
+    uint32_t x = row * kDropRowMul + (col0 >> 1) * kDropColMul + c.s0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t h = drop_mix32(x);
+      x += kDropColMul;
+      f[2 * j] = (h & 0xFFFFu) >= c.thr16 ? f[2 * j] * c.keep_scale : 0.f;
+      f[2 * j + 1] = (h >> 16) >= c.thr16 ? f[2 * j + 1] * c.keep_scale : 0.f;
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);       // SWIZZLE_128B needs 1024-byte alignment
-  uint64_t* bars = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_STAGES);
-  const uint32_t tfull0 = smem_u32(bars + 2 * TC_STAGES), tempty0 = smem_u32(bars + 2 * TC_STAGES + 2);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_STAGES + 4);
+gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_c, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* staging = smem + p.stages * p.stage_bytes;
+  float* bias_s = (float*)(staging + TC_STAGING_BYTES);
+  uint64_t* bars = (uint64_t*)((uint8_t*)bias_s + TC_BIAS_BYTES);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_MAX_STAGES);
+  const uint32_t tfull0 = smem_u32(bars + 2 * TC_MAX_STAGES), tempty0 = smem_u32(bars + 2 * TC_MAX_STAGES + 2);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_MAX_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < TC_STAGES; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, 4); }
+    if (smem_u32(smem) & 1023u) __trap();                          // the swizzle atoms below assume it
+    for (int i = 0; i < p.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
@@ -151,7 +223,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int32_t a_mn = (int32_t)(g * p.a_gmn + (int64_t)mt * TC_BLOCK_M), b_mn = (int32_t)(g * p.b_gmn + (int64_t)nt * p.block_n);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
+          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
           const uint32_t bar = full0 + 8 * stage;
           mbar_expect_tx(bar, stage_tx);
           const int32_t ak = (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), bk = (int32_t)(g * p.b_gk + (int64_t)kb * TC_BLOCK_K);
@@ -159,7 +231,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           else { tma_load_2d(sa, &map_a, bar, a_mn, ak); tma_load_2d(sa + 8192, &map_a, bar, a_mn + 64, ak); }   // 2 x [64 (k) x 64 (m)]
           if (!p.b_mn_major) tma_load_2d(sb, &map_b, bar, bk, b_mn);                    // box [block_n rows (n) x 64 (k)]
           else for (int j = 0; j * 64 < p.block_n; ++j) tma_load_2d(sb + 8192 * j, &map_b, bar, b_mn + 64 * j, bk);
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -184,7 +256,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * TC_STAGE_BYTES), sb = sa + TC_A_BYTES;
+          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
 #pragma unroll
           for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
             // K-major: 16 bf16 = 32 bytes further inside the 128-byte swizzle row; MN-major: 16 k-rows = 2048 bytes further
@@ -193,19 +265,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             tc_mma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(empty0 + 8 * stage);                 // frees the smem slot when these MMAs retire
-          if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull0 + 8 * acc);                     // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // =============================== epilogue (warps 2..5) ===============================
+    // =============================== epilogue (warps 2..9) ===============================
+    const int ew = warp - 2;                             // 0..7
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
+    const int half = ew >> 2;                            // which of the two warps of the quarter
+    const int et = threadIdx.x - 64;                     // 0..255
+    uint8_t* my_stage = staging + ew * TC_STAGING_WARP_BYTES;
+    const uint32_t my_stage_u32 = smem_u32(my_stage);
     int acc = 0; uint32_t acc_phase = 0;
-    const uint32_t thr = drop_threshold(p.drop_p);
-    const float keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const uint64_t seed = p.drop_p > 0.f ? *p.seed_dev : 0;
+    EpiCtx ec;
+    ec.act = p.act; ec.mask_scale = p.mask_scale; ec.has_mask = p.mask != nullptr; ec.has_drop = p.drop_p > 0.f;
+    ec.thr16 = drop_thr16(p.drop_p);
+    ec.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    ec.s0 = p.drop_p > 0.f ? drop_s0(*p.seed_dev, p.salt) : 0u;
+    const int n_chunks = (p.block_n + 63) >> 6;
+    bool store_pending = false;
     for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int g = (int)(tile / tiles_per_group);
       int64_t r = tile % tiles_per_group;
@@ -213,69 +294,131 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int nt = (int)(r % p.n_tiles_n), mt = (int)(r / p.n_tiles_n);
       const int64_t m = (int64_t)mt * TC_BLOCK_M + q * 32 + lane;
       const int64_t n0 = (int64_t)nt * p.block_n;
+      float* bias_t = bias_s + acc * TC_MAX_N;
+      const bool use_bias = p.bias != nullptr && z == 0;
+      if (use_bias) {
+        if (et < p.block_n) bias_t[et] = (n0 + et < p.N) ? __ldg(p.bias + g * p.bias_gs + n0 + et) : 0.f;
+      }
+      epi_bar_sync();                                    // bias tile visible; also keeps the 8 warps within one tile of each other
       mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
-      for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-        uint32_t v[32];
-        tc_ld32(trow + c0, v);
-        const int64_t nb = n0 + c0;
-        if (m < p.M && nb < p.N) {
-          const int ncols = (int)min((int64_t)32, min((int64_t)p.block_n - c0, p.N - nb));
-          float f[32];
+      for (int ci = half; ci < n_chunks; ci += 2) {
+        const int c0 = ci * 64;
+        const int64_t nb = n0 + c0;                      // first global column of the chunk
+        if (nb >= p.N) break;
+        const int cw = (int)min((int64_t)64, min((int64_t)p.block_n - c0, p.N - nb));     // valid columns in this chunk
+        const bool full_main = nb + 64 <= p.n_main && cw == 64;
+        // a chunk cut short by the END OF THE MATRIX may still go through TMA: the store map clips columns >= N
+        const bool clip_ok = p.G == 1 && p.n_main == p.N && !p.mask && nb + cw == p.N;
+        if (p.tma_store && !p.accumulate && (full_main || clip_ok)) {
+          // ---------------- fast path: 64 bf16 columns per row -> swizzled staging -> TMA store ----------------
+          uint32_t v[64];
+          tc_ld32_nowait(trow + c0, v);
+          if (cw > 32) tc_ld32_nowait(trow + c0 + 32, v + 32);
+          uint4 mk[8];
+          if (ec.has_mask && m < p.M) {
+            const uint4* mp = reinterpret_cast<const uint4*>(p.mask + m * p.ld_mask + g * p.mask_gn + nb);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias && z == 0) {
-            const float* bp = p.bias + g * p.bias_gs + nb;
+            for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) if (j < ncols) f[j] += __ldg(bp + j);
+            for (int j = 0; j < 8; ++j) mk[j] = make_uint4(0, 0, 0, 0);
           }
-          // columns [nb, nb+ncols): main part (bf16) below n_main, aux part (fp32) at/after n_main
-          const int n_mainc = (int)max((int64_t)0, min((int64_t)ncols, p.n_main - nb));
-          if (n_mainc > 0) {
-            if (p.act == 1) {
+          if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
+          __syncwarp();
+          tc_ld_wait();
+          const uint32_t gcol = (uint32_t)(g * p.main_gn + nb);
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = fmaxf(f[j], 0.f);
-            }
-            uint16_t* op = p.out_main + m * p.ld_main + g * p.main_gn + nb;
-            if (p.mask) {
-              const uint16_t* mp = p.mask + m * p.ld_mask + g * p.mask_gn + nb;
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t o[16];
+            if (hh == 0 || cw > 32) {
+              float f[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = bf16_to_f32(mp[j]) > 0.f ? f[j] * p.mask_scale : 0.f;
-            }
-            if (p.drop_p > 0.f) {
-              const uint64_t base = (uint64_t)(m * p.ld_main + g * p.main_gn + nb);
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = mix_hash(seed, p.salt, base + j) >= thr ? f[j] * keep_scale : 0.f;
-            }
-            if (p.accumulate) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] += bf16_to_f32(op[j]);
-            }
-            if (n_mainc == 32 && (((uintptr_t)op) & 15) == 0) {
-              uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[32 * hh + j]);
+              epi_math32(ec, f, use_bias ? bias_t + c0 + 32 * hh : nullptr, mk + 4 * hh, (uint32_t)m, gcol + 32 * hh, o);
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < n_mainc) op[j] = f32_to_bf16(f[j]);
+              for (int j = 0; j < 16; ++j) o[j] = 0u;
+            }
+            // row `lane` of the warp's [32 x 128 B] staging tile; 16-byte chunk index XOR (row % 8) = SWIZZLE_128B
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = (4 * hh + j) ^ (lane & 7);
+              *reinterpret_cast<uint4*>(my_stage + lane * 128 + chunk * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             }
           }
-          if (n_mainc < ncols) {
-            float* ap = p.out_aux + (int64_t)z * p.aux_split_stride + m * p.ld_aux + g * p.aux_gn + (nb - p.n_main);
-            if (p.accumulate && p.split_k == 1) {
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&map_c, my_stage_u32, (int32_t)gcol, (int32_t)((int64_t)mt * TC_BLOCK_M + q * 32));
+            tma_store_commit();
+          }
+          store_pending = true;
+          continue;
+        }
+        // ---------------- general path: 32 columns at a time, direct global stores ----------------
+        for (int s0c = 0; s0c < cw; s0c += 32) {
+          uint32_t v[32];
+          tc_ld32_nowait(trow + c0 + s0c, v);
+          tc_ld_wait();
+          const int64_t nbb = nb + s0c;
+          if (m < p.M) {
+            const int ncols = min(32, cw - s0c);
+            float f[32];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) f[j] += ap[j];
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (use_bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] += bias_t[c0 + s0c + j];
             }
-            if (n_mainc == 0 && ncols == 32 && (((uintptr_t)ap) & 15) == 0) {
-              float4* a4 = reinterpret_cast<float4*>(ap);
+            // columns [nbb, nbb+ncols): main part (bf16) below n_main, aux part (fp32) at/after n_main
+            const int n_mainc = (int)max((int64_t)0, min((int64_t)ncols, p.n_main - nbb));
+            if (n_mainc > 0) {
+              if (p.act == 1) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) a4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-            } else {
+                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = fmaxf(f[j], 0.f);
+              }
+              uint16_t* op = p.out_main + m * p.ld_main + g * p.main_gn + nbb;
+              if (p.mask) {
+                const uint16_t* mp = p.mask + m * p.ld_mask + g * p.mask_gn + nbb;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) ap[j] = f[j];
+                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = bf16_to_f32(mp[j]) > 0.f ? f[j] * p.mask_scale : 0.f;
+              }
+              if (ec.has_drop) {
+                const uint32_t gcol = (uint32_t)(g * p.main_gn + nbb);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = drop_keep(ec.s0, ec.thr16, (uint32_t)m, gcol + j) ? f[j] * ec.keep_scale : 0.f;
+              }
+              if (p.accumulate) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] += bf16_to_f32(op[j]);
+              }
+              if (n_mainc == 32 && (((uintptr_t)op) & 15) == 0) {
+                uint4* o4 = reinterpret_cast<uint4*>(op);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j < n_mainc) op[j] = f32_to_bf16(f[j]);
+              }
+            }
+            if (n_mainc < ncols) {
+              float* ap = p.out_aux + (int64_t)z * p.aux_split_stride + m * p.ld_aux + g * p.aux_gn + (nbb - p.n_main);
+              if (p.accumulate && p.split_k == 1) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) f[j] += ap[j];
+              }
+              if (n_mainc == 0 && ncols == 32 && (((uintptr_t)ap) & 15) == 0) {
+                float4* a4 = reinterpret_cast<float4*>(ap);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) ap[j] = f[j];
+              }
             }
           }
         }
@@ -285,6 +428,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (store_pending && lane == 0) tma_store_wait_all();   // global writes complete before the kernel ends
   }
   tc_fence_before();
   __syncthreads();
@@ -398,18 +542,34 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
     CDC_REQUIRE(false, "split_k exceeds the number of non-empty K slices; use cdcmdr_gemm_bf16_tc_splits() to size it");
   }
 
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
   if (int rc = make_map(&ma, p->A, p->a_rows, p->a_cols, p->lda, q.a_mn_major ? 64u : (uint32_t)TC_BLOCK_M)) return rc;
   if (int rc = make_map(&mb, p->Bt, p->b_rows, p->b_cols, p->ldb, q.b_mn_major ? 64u : (uint32_t)bn)) return rc;
+  // bf16 output through TMA stores when its layout allows a tensor map (16-byte aligned base / pitch / group offsets)
+  q.tma_store = (p->n_main > 0 && ((uintptr_t)p->out_main % 16) == 0 && p->ld_main % 8 == 0 && p->main_gn % 8 == 0 &&
+                 (p->G - 1) * p->main_gn + p->n_main <= p->ld_main && p->M < (int64_t)1 << 31) ? 1 : 0;
+  if (q.tma_store) {
+    if (int rc = make_map(&mc, p->out_main, p->M, (p->G - 1) * p->main_gn + p->n_main, p->ld_main, 32u)) return rc;
+  } else {
+    mc = ma;
+  }
+  const int b_bytes = (q.b_mn_major ? (int)ceil_div(bn, 64) * 64 : bn) * TC_BLOCK_K * 2;
+  q.stage_bytes = TC_A_BYTES + b_bytes;
+  const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES;
+  int stages = (TC_SMEM_LIMIT - fixed) / q.stage_bytes;
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  CDC_REQUIRE(stages >= 2, "shared memory budget too small for a 2-stage pipeline");
+  q.stages = stages;
+  const int smem_bytes = stages * q.stage_bytes + fixed;
 
   static bool attr_set = false;
   if (!attr_set) {
-    CDC_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
+    CDC_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_set = true;
   }
   const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  gemm_bf16_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, to_stream(s)>>>(ma, mb, q);
+  gemm_bf16_tc_kernel<<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, q);
   CDC_LAUNCHED();
   return 0;
 }

@@ -230,6 +230,49 @@ template <typename T> struct ColSumF {
   __device__ __forceinline__ void operator()(int64_t r, int64_t c, double (&a)[1]) const { a[0] += (double)ld_act<T>(X + r * ld + c); }
 };
 
+// Bandwidth-shaped column sum (bias gradients of the big activation-gradient matrices): every thread owns VEC = 16 bytes
+// of consecutive columns and walks its chunk's rows with 128-bit loads (a warp reads 512 contiguous bytes per row), fp32
+// partial per thread over <= a few hundred rows, then double across the 8 row lanes and across chunks (fixed order).
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+colsum_vec_kernel(const T* __restrict__ X, int64_t ld, int64_t B, int64_t C, int chunks, double* __restrict__ partial) {
+  __shared__ float sm[8][32 * VEC + 1];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c0 = ((int64_t)blockIdx.x * 32 + tx) * VEC;
+  const int chunk = blockIdx.y;
+  const int64_t rpc = ceil_div(B, chunks);
+  const int64_t r0 = chunk * rpc, r1 = (r0 + rpc < B) ? r0 + rpc : B;
+  float acc[VEC];
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+  if (c0 < C) {
+    const T* p = X + c0;
+#pragma unroll 4
+    for (int64_t r = r0 + ty; r < r1; r += 8) {
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(p + r * ld));
+      if constexpr (VEC == 8) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { acc[2 * k] += __uint_as_float(w[k] << 16); acc[2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u); }
+      } else {
+        acc[0] += __uint_as_float(u.x); acc[1] += __uint_as_float(u.y); acc[2] += __uint_as_float(u.z); acc[3] += __uint_as_float(u.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < VEC; ++v) sm[ty][tx * VEC + v] = acc[v];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 32 * VEC; i += 256) {
+    const int64_t c = (int64_t)blockIdx.x * 32 * VEC + i;
+    if (c < C) {
+      double t = 0;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) t += (double)sm[y][i];
+      partial[(int64_t)chunk * C + c] = t;
+    }
+  }
+}
+
 __global__ void colsum_finalize_kernel(const double* __restrict__ partial, int chunks, int64_t C, float* __restrict__ out, int accumulate) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -279,8 +322,8 @@ __global__ void bn_apply_kernel(const float* __restrict__ Z, int64_t ldz, T* __r
                                 const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
                                 float drop_p, const uint64_t* __restrict__ seed_dev, uint32_t salt) {
   const int64_t total = B * C;
-  const uint64_t seed = drop_p > 0.f ? *seed_dev : 0;
-  const uint32_t thr = drop_threshold(drop_p);
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u;
+  const uint32_t thr = drop_thr16(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = i % C, r = i / C;
@@ -288,7 +331,7 @@ __global__ void bn_apply_kernel(const float* __restrict__ Z, int64_t ldz, T* __r
     if (gamma2) { g *= gamma2[c]; b += beta2[c]; }
     float v = (Z[r * ldz + c] - mean[c]) * invstd[c] * g + b;
     if (relu) v = fmaxf(v, 0.f);
-    if (drop_p > 0.f) v = (mix_hash(seed, salt, (uint64_t)i) >= thr) ? v * keep_scale : 0.f;
+    if (drop_p > 0.f) v = drop_keep(s0, thr, (uint32_t)r, (uint32_t)c) ? v * keep_scale : 0.f;
     st_act<T>(A + r * lda + c, v);
   }
 }
@@ -584,9 +627,24 @@ extern "C" int cdcmdr_colsum(const void* X, int64_t ld, int is_bf16, int64_t B, 
   CDC_REQUIRE(B >= 0 && C >= 0 && scratch, "bad colsum arguments");
   if (C == 0) return 0;
   cudaStream_t st = to_stream(s);
+  double* partial = (double*)scratch;
+  const int vec = is_bf16 ? 8 : 4;
+  if (B >= 1024 && C % vec == 0 && ld % vec == 0 && ((uintptr_t)X % 16) == 0) {
+    const int64_t col_blocks = ceil_div(C, 32 * vec);
+    int64_t ch = ceil_div(4 * kNumSMs, col_blocks);
+    if (ch > kMaxChunks) ch = kMaxChunks;
+    if (ch > B / 64) ch = B / 64;
+    if (ch < 1) ch = 1;
+    dim3 vgrid((unsigned)col_blocks, (unsigned)ch);
+    if (is_bf16) colsum_vec_kernel<uint16_t, 8><<<vgrid, 256, 0, st>>>((const uint16_t*)X, ld, B, C, (int)ch, partial);
+    else colsum_vec_kernel<float, 4><<<vgrid, 256, 0, st>>>((const float*)X, ld, B, C, (int)ch, partial);
+    CDC_LAUNCHED();
+    colsum_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, (int)ch, C, out, accumulate);
+    CDC_LAUNCHED();
+    return 0;
+  }
   const int chunks = pick_chunks(B > 0 ? B : 1, C);
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
-  double* partial = (double*)scratch;
   if (is_bf16) col_partial_kernel<1><<<grid, 256, 0, st>>>(B, C, chunks, partial, ColSumF<uint16_t>{(const uint16_t*)X, ld});
   else col_partial_kernel<1><<<grid, 256, 0, st>>>(B, C, chunks, partial, ColSumF<float>{(const float*)X, ld});
   CDC_LAUNCHED();

@@ -14,7 +14,10 @@ checks forward, loss, every gradient, BN running stats and post-Adam parameters 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
 this module.  The product package never does.
 
-All tensors are numpy arrays keyed by the reference's state_dict names.
+All tensors are numpy arrays keyed by the reference's state_dict names.  The arithmetic runs in the
+dtype of the state dict handed in: float32 reproduces the reference's precision (what the golden fixtures pin);
+float64 gives the exact value of the same algorithm, which the GPU parity tests use at sizes where float32 numpy
+itself is noisy (a BatchNorm unit that is constant over the batch: rounding-noise xhat, coin-flip ReLU mask).
 """
 from __future__ import annotations
 

@@ -27,6 +27,10 @@ def test_golden_autograd(name):
     run_golden_case(name, device="cuda", path="autograd")
 
 
+def _f64(sd):
+    return {k: (v.astype(np.float64) if v.dtype == np.float32 else v.copy()) for k, v in sd.items()}
+
+
 def _rand_ple(seed, B, F, E, T, vocab, dims, tower, device):
     torch.manual_seed(seed)
     rng = np.random.default_rng(seed)
@@ -53,7 +57,10 @@ def test_ple_gradients_and_steps_match_oracle(B, F, E, T):
     model = model.to("cuda").train()
     xt, yt, gt = (torch.from_numpy(a).cuda() for a in (x, y, g))
     # (1) gradients through loss.backward()
-    r = O.train_step(om, {k: v.copy() for k, v in sd.items()}, None, x, y, "gather", group=g)
+    # the oracle runs in float64 here: in float32 numpy a tower unit whose BatchNorm input is (nearly) constant over the
+    # batch gets a rounding-noise xhat and a coin-flip ReLU mask, which moves its gradients by percents; float64 pins the
+    # exact value of the same algorithm (the unmodified reference in fp32 AND in fp64 agrees with it to ~3e-6)
+    r = O.train_step(om, _f64(sd), None, x, y, "gather", group=g)
     pred = model(xt)
     loss = torch.nn.BCELoss()(pred.gather(1, gt[:, None]).squeeze(1), yt.float()) + model.get_regularization_loss(device="cuda")
     model.zero_grad()
@@ -67,14 +74,12 @@ def test_ple_gradients_and_steps_match_oracle(B, F, E, T):
         scale = float(np.abs(go).max())
         noise = 5e-5 if (k.startswith("towers") and k.endswith(".bias") and not k.endswith("layers.8.bias")) else 0.0
         err = float(np.abs(gm - go).max())
-        # tower weights sit behind train-mode BatchNorm: a unit whose batch variance is ~0 has invstd ~ 1/sqrt(eps) = 316 and
-        # its xhat is rounding noise in ANY implementation (the reference-generated fixtures pin towers to 1e-4 separately)
-        rel = 5e-2 if k.startswith("towers.") else 1e-4
-        assert err <= rel * scale + 1e-9 + noise, (k, err, scale)
+        assert err <= 1e-4 * scale + 1e-9 + noise, (k, err, scale)
     # the regulariser state must not have been disturbed: fused steps start from the same weights
     model.load_state_dict({k: torch.from_numpy(v) for k, v in sd.items()})
     opt = cm.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
     oopt = O.Adam()
+    sd = _f64(sd)
     for s in range(3):
         r = O.train_step(om, sd, oopt, x, y, "gather", group=g)
         out = model.train_step(xt, yt, opt, mode="gather", sel=gt)

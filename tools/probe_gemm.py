@@ -63,3 +63,29 @@ run("l0_wgrad (M=2560,N=368,K=B)", 2560, 368, B, a_mn=1, b_mn=1, out="f32", spli
 run("l0_wgrad_nosplit", 2560, 368, B, a_mn=1, b_mn=1, out="f32", split=1)
 run("l1_mask_dgrad (N=256,K=128)", B, 256, 128, b_mn=1, mask=True)
 run("big_square", 8192, 8192, 8192, bias=False)
+
+
+def colsum_probe(Bn, Cn, bf16=True):
+    X = torch.randn(Bn, Cn, device=dev)
+    if bf16:
+        X = X.to(torch.bfloat16)
+    out = torch.zeros(Cn, device=dev)
+    sc = torch.empty(lib.colsum_scratch_bytes(Cn), dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        lib.colsum(X.data_ptr(), Cn, 1 if bf16 else 0, Bn, Cn, out.data_ptr(), 0, sc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        lib.colsum(X.data_ptr(), Cn, 1 if bf16 else 0, Bn, Cn, out.data_ptr(), 0, sc.data_ptr(), 0)
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) * 100
+    ref = X.float().sum(0)
+    err = float((out - ref).abs().max() / ref.abs().max())
+    print(json.dumps(dict(name=f"colsum {Bn}x{Cn} {'bf16' if bf16 else 'f32'}", us=round(us, 1), gbs=round(X.numel() * X.element_size() / us / 1e3, 1), relerr=err)), flush=True)
+
+
+colsum_probe(B, 2560)
+colsum_probe(B, 1280)
+colsum_probe(B, 640, bf16=False)
