@@ -7,14 +7,16 @@
 namespace cdcmdr {
 
 constexpr int kShortSeg = 64;        // segments up to this many entries are summed inline, in order
-constexpr int kLongThreads = 256;    // one CTA per long segment
+constexpr int kLongThreads = 256;    // one CTA per PIECE of a long segment
+constexpr int kPiece = 512;          // long segments are cut into pieces of this many entries (a Zipf-hot id or the single
+                                     // domain id of a batch is a segment of up to B entries: one CTA per segment serialises)
 constexpr int kRegPartials = 2048;
 
 struct EmbedPlan {                   // lives at the start of the caller-provided workspace
   int64_t n, V, n_long_max;
   int E_max;
   size_t off_keys_in, off_vals_in, off_keys, off_vals, off_uniq, off_cnt, off_start, off_nuniq,
-      off_seg_of_row, off_long_slot, off_nlong, off_long_sum, off_long_seg, off_cub, off_reg;
+      off_seg_of_row, off_long_slot, off_nlong, off_long_sum, off_long_seg, off_long_off, off_cub, off_reg;
   size_t cub_bytes, total;
 };
 
@@ -35,7 +37,7 @@ static size_t cub_temp_bytes(int64_t n, int64_t V) {
 
 static EmbedPlan make_layout(int64_t n, int64_t V, int E_max) {
   EmbedPlan p{};
-  p.n = n; p.V = V; p.E_max = E_max; p.n_long_max = n / kShortSeg + 1;
+  p.n = n; p.V = V; p.E_max = E_max; p.n_long_max = n / kShortSeg + n / kPiece + 2;   // pieces <= n/kPiece + #long segments
   size_t o = align256(sizeof(EmbedPlan));
   auto take = [&](size_t bytes) { size_t r = o; o = align256(o + bytes); return r; };
   p.off_keys_in = take(n * 4); p.off_vals_in = take(n * 4);
@@ -45,6 +47,7 @@ static EmbedPlan make_layout(int64_t n, int64_t V, int E_max) {
   p.off_long_slot = take(n * 4); p.off_nlong = take(16);
   p.off_long_sum = take((size_t)p.n_long_max * E_max * 4);
   p.off_long_seg = take((size_t)p.n_long_max * 4);
+  p.off_long_off = take((size_t)p.n_long_max * 4);
   p.off_reg = take(kRegPartials * 8);
   p.cub_bytes = cub_temp_bytes(n, V);
   p.off_cub = take(p.cub_bytes);
@@ -108,30 +111,35 @@ __global__ void plan_keys_kernel(const int32_t* __restrict__ x, const int64_t* _
 __global__ void plan_segments_kernel(const uint32_t* __restrict__ uniq, const int32_t* __restrict__ cnt,
                                      const int32_t* __restrict__ nuniq, int64_t V, int32_t* __restrict__ seg_of_row,
                                      int32_t* __restrict__ long_slot, int32_t* __restrict__ nlong,
-                                     int32_t* __restrict__ long_seg) {
+                                     int32_t* __restrict__ long_seg, int32_t* __restrict__ long_off) {
   const int nu = *nuniq;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nu; i += gridDim.x * blockDim.x) {
     const uint32_t r = uniq[i];
     if ((int64_t)r < V) seg_of_row[r] = i;
     int slot = -1;
-    if (cnt[i] > kShortSeg && (int64_t)r < V) { slot = atomicAdd(nlong, 1); long_seg[slot] = i; }
+    if (cnt[i] > kShortSeg && (int64_t)r < V) {
+      // the slot NUMBER depends on atomic order, the sums stored there do not
+      const int np = (cnt[i] + kPiece - 1) / kPiece;
+      slot = atomicAdd(nlong, np);
+      for (int j = 0; j < np; ++j) { long_seg[slot + j] = i; long_off[slot + j] = j * kPiece; }
+    }
     long_slot[i] = slot;
   }
 }
 
-// one CTA per long segment: lane-group j sums entries j, j+G, j+2G, ... in order; fixed smem tree afterwards
+// one CTA per piece of a long segment: lane-group j sums entries j, j+G, j+2G, ... in order; fixed smem tree afterwards
 template <int VEC>
 __global__ void __launch_bounds__(kLongThreads)
 long_segment_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, const int32_t* __restrict__ vals,
                     const int32_t* __restrict__ start, const int32_t* __restrict__ cnt, const int32_t* __restrict__ long_seg,
-                    const int32_t* __restrict__ nlong, float* __restrict__ long_sum) {
+                    const int32_t* __restrict__ long_off, const int32_t* __restrict__ nlong, float* __restrict__ long_sum) {
   extern __shared__ float sm[];                    // [groups][E]
   const int lanes = E / VEC;
   const int groups = kLongThreads / lanes;
   const int g = threadIdx.x / lanes, q = threadIdx.x % lanes;
   for (int ls = blockIdx.x; ls < *nlong; ls += gridDim.x) {
-    const int seg = long_seg[ls];
-    const int s0 = start[seg], c = cnt[seg];
+    const int seg = long_seg[ls], off = long_off[ls];
+    const int s0 = start[seg] + off, c = min(kPiece, cnt[seg] - off);
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
@@ -170,10 +178,13 @@ __device__ __forceinline__ void segment_sum(float (&acc)[VEC], const float* __re
   for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
   if (seg < 0) return;
   const int c = cnt[seg];
-  if (c > kShortSeg) {
+  if (c > kShortSeg) {                                   // pieces of the segment, in order
     const float* src = long_sum + (int64_t)long_slot[seg] * E + q * VEC;
+    const int np = (c + kPiece - 1) / kPiece;
+    for (int i = 0; i < np; ++i, src += E) {
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) acc[j] = src[j];
+      for (int j = 0; j < VEC; ++j) acc[j] += src[j];
+    }
     return;
   }
   const int s0 = start[seg];
@@ -331,7 +342,8 @@ extern "C" int cdcmdr_embed_plan_build(const int32_t* x, const int64_t* offsets,
   CDC_CHECK(cudaMemsetAsync(seg_of_row, 0xFF, (size_t)V * 4, st));
   CDC_CHECK(cudaMemsetAsync(at<void>(plan, L.off_nlong), 0, 16, st));
   plan_segments_kernel<<<grid_for(n, 256), 256, 0, st>>>(uniq, cnt, nuniq, V, seg_of_row, at<int32_t>(plan, L.off_long_slot),
-                                                         at<int32_t>(plan, L.off_nlong), at<int32_t>(plan, L.off_long_seg));
+                                                         at<int32_t>(plan, L.off_nlong), at<int32_t>(plan, L.off_long_seg),
+                                                         at<int32_t>(plan, L.off_long_off));
   CDC_LAUNCHED();
   return 0;
 }
@@ -343,13 +355,15 @@ static int launch_long(const float* grad_out, int64_t ldg, const void* plan, con
   CDC_REQUIRE(lanes <= kLongThreads, "embed_dim too large for the long-segment kernel");
   const size_t smem = (size_t)(kLongThreads / lanes) * E * sizeof(float);
   CDC_REQUIRE(smem <= 48 * 1024, "embed_dim too large for the long-segment kernel");
-  const int grid = (int)(L.n_long_max < 4 * kNumSMs ? L.n_long_max : 4 * kNumSMs);
+  const int grid = (int)(L.n_long_max < 8 * kNumSMs ? L.n_long_max : 8 * kNumSMs);
   if (E % 4 == 0)
     long_segment_kernel<4><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
-        at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_nlong), at<float>(plan, L.off_long_sum));
+        at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_long_off), at<int32_t>(plan, L.off_nlong),
+        at<float>(plan, L.off_long_sum));
   else
     long_segment_kernel<1><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
-        at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_nlong), at<float>(plan, L.off_long_sum));
+        at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_long_off), at<int32_t>(plan, L.off_nlong),
+        at<float>(plan, L.off_long_sum));
   CDC_LAUNCHED();
   return 0;
 }

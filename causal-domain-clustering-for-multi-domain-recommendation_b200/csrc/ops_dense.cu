@@ -41,6 +41,8 @@ static int grid_1d(int64_t work, int threads, int max_per_sm = 8) {
   return g < 1 ? 1 : (int)g;
 }
 
+constexpr int kMixStageSmem = 96 * 1024;    // per-CTA cap for the row-staging gate-mix kernels (8 warps, one row each)
+constexpr int kMixSmemPerSM = 220 * 1024;
 constexpr int kReducePartials = 1024;       // fixed upper bound on stage-1 blocks of scalar reductions
 
 __device__ __forceinline__ double block_sum_256(double v) {   // deterministic: warp tree + ordered warp sum
@@ -64,11 +66,20 @@ __global__ void reduce_finalize_kernel(const double* __restrict__ partials, int 
 // ------------------------------------------------------------------------------------------ gate mix
 struct MixK { int n_gates, n_experts, h, max_sel; const int32_t* gate_col; const int32_t* gate_n; const int32_t* gate_sel; };
 
-template <typename T, int VEC>
+// STAGE: the warp first copies its row of H (and dOut in the backward) into shared memory with 128-bit loads - all of
+// them independent, so enough bytes are in flight to hide HBM latency - and the mixing loops then read shared memory.
+// Without it every (gate, expert) pair issues its own short global load behind runtime loop bounds.
+__device__ __forceinline__ void stage_row(void* dst, const void* src, int bytes, int lane) {
+  const uint4* s4 = reinterpret_cast<const uint4*>(src);
+  uint4* d4 = reinterpret_cast<uint4*>(dst);
+  for (int i = lane; i < bytes / 16; i += 32) d4[i] = __ldg(s4 + i);
+}
+
+template <typename T, int VEC, bool STAGE>
 __global__ void __launch_bounds__(256)
 gate_mix_fwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* __restrict__ logits, int64_t ldl,
-                    T* __restrict__ out, int64_t ldo, float* __restrict__ probs, int64_t B) {
-  extern __shared__ float dyn[];
+                    T* __restrict__ out, int64_t ldo, float* __restrict__ probs, int64_t B, int stage_off) {
+  extern __shared__ __align__(16) float dyn[];
   __shared__ int s_col[32], s_n[32], s_sel[1024];
   const int np = d.n_gates * d.max_sel;
   for (int i = threadIdx.x; i < d.n_gates; i += blockDim.x) { s_col[i] = d.gate_col[i]; s_n[i] = d.gate_n[i]; }
@@ -76,7 +87,11 @@ gate_mix_fwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sp = dyn + warp * np;
+  const int row_elems = d.n_experts * d.h;
+  T* Hs = reinterpret_cast<T*>(reinterpret_cast<char*>(dyn) + stage_off) + (size_t)warp * row_elems;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < B; row += (int64_t)gridDim.x * 8) {
+    if (STAGE) stage_row(Hs, H + row * ldh, row_elems * (int)sizeof(T), lane);
+    const T* Hrow = STAGE ? Hs : H + row * ldh;
     if (lane < d.n_gates) {
       const int n = s_n[lane];
       const float* lg = logits + row * ldl + s_col[lane];
@@ -99,7 +114,7 @@ gate_mix_fwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
         const int n = s_n[j];
         for (int s = 0; s < n; ++s) {
           float hv[VEC];
-          VecIO<T, VEC>::load(H + row * ldh + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
+          VecIO<T, VEC>::load(Hrow + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
           const float p = sp[j * d.max_sel + s];
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc[q] = fmaf(p, hv[q], acc[q]);
@@ -111,12 +126,12 @@ gate_mix_fwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
   }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool STAGE>
 __global__ void __launch_bounds__(256)
 gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* __restrict__ probs,
                     const T* __restrict__ dOut, int64_t ldo, T* __restrict__ dH, int64_t lddh, float relu_scale,
-                    float* __restrict__ dlogits, int64_t lddl, int64_t B) {
-  extern __shared__ float dyn[];
+                    float* __restrict__ dlogits, int64_t lddl, int64_t B, int stage_off) {
+  extern __shared__ __align__(16) float dyn[];
   __shared__ int s_col[32], s_n[32], s_sel[1024], s_inv_cnt[64], s_inv[64 * 32];
   const int np = d.n_gates * d.max_sel;
   for (int i = threadIdx.x; i < d.n_gates; i += blockDim.x) { s_col[i] = d.gate_col[i]; s_n[i] = d.gate_n[i]; }
@@ -133,7 +148,16 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sp = dyn + (warp * 2) * np;
   float* sd = sp + np;
+  const int h_elems = d.n_experts * d.h, o_elems = d.n_gates * d.h;
+  T* Hs = reinterpret_cast<T*>(reinterpret_cast<char*>(dyn) + stage_off) + (size_t)warp * (h_elems + o_elems);
+  T* Os = Hs + h_elems;
   for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < B; row += (int64_t)gridDim.x * 8) {
+    if (STAGE) {
+      stage_row(Hs, H + row * ldh, h_elems * (int)sizeof(T), lane);
+      stage_row(Os, dOut + row * ldo, o_elems * (int)sizeof(T), lane);
+    }
+    const T* Hrow = STAGE ? Hs : H + row * ldh;
+    const T* Orow = STAGE ? Os : dOut + row * ldo;
     for (int k = lane; k < np; k += 32) sp[k] = probs[row * np + k];
     __syncwarp();
     for (int j = 0; j < d.n_gates; ++j) {
@@ -142,8 +166,8 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
         float part = 0.f;
         for (int c = lane * VEC; c < d.h; c += 32 * VEC) {
           float dv[VEC], hv[VEC];
-          VecIO<T, VEC>::load(dOut + row * ldo + (int64_t)j * d.h + c, dv);
-          VecIO<T, VEC>::load(H + row * ldh + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
+          VecIO<T, VEC>::load(Orow + (int64_t)j * d.h + c, dv);
+          VecIO<T, VEC>::load(Hrow + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
 #pragma unroll
           for (int q = 0; q < VEC; ++q) part = fmaf(dv[q], hv[q], part);
         }
@@ -168,14 +192,14 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
         for (int i = 0; i < cnt; ++i) {
           const int k = s_inv[e * 32 + i];
           float dv[VEC];
-          VecIO<T, VEC>::load(dOut + row * ldo + (int64_t)(k / d.max_sel) * d.h + c, dv);
+          VecIO<T, VEC>::load(Orow + (int64_t)(k / d.max_sel) * d.h + c, dv);
           const float p = sp[k];
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc[q] = fmaf(p, dv[q], acc[q]);
         }
         if (relu_scale > 0.f) {
           float hv[VEC];
-          VecIO<T, VEC>::load(H + row * ldh + (int64_t)e * d.h + c, hv);
+          VecIO<T, VEC>::load(Hrow + (int64_t)e * d.h + c, hv);
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc[q] = hv[q] > 0.f ? acc[q] * relu_scale : 0.f;
         }
@@ -577,19 +601,23 @@ extern "C" int cdcmdr_gate_mix_fwd(const cdcmdr_mix_desc_t* d, const void* H, in
   if (int rc = check_mix(d)) return rc;
   if (B == 0) return 0;
   MixK k{d->n_gates, d->n_experts, d->h, d->max_sel, d->gate_col, d->gate_n, d->gate_sel};
-  const size_t smem = (size_t)8 * d->n_gates * d->max_sel * sizeof(float);
+  size_t smem = (size_t)8 * d->n_gates * d->max_sel * sizeof(float);
   CDC_REQUIRE(smem <= 32 * 1024, "gate-mix descriptor too large");
-  const int grid = grid_1d(B * 32, 256);
   const bool vec = d->h % 4 == 0 && ldh % 4 == 0 && ldo % 4 == 0 &&
                    ((uintptr_t)H % (is_bf16 ? 8 : 16) == 0) && ((uintptr_t)out % (is_bf16 ? 8 : 16) == 0);
+  const size_t elt = is_bf16 ? 2 : 4;
+  const size_t row_bytes = (size_t)d->n_experts * d->h * elt;
+  const int stage_off = (int)((smem + 15) & ~(size_t)15);
+  const bool stage = vec && B >= 64 && row_bytes % 16 == 0 && (ldh * elt) % 16 == 0 && ((uintptr_t)H % 16) == 0 &&
+                     stage_off + 8 * row_bytes <= kMixStageSmem;
+  if (stage) smem = stage_off + 8 * row_bytes;
+  const int grid = grid_1d(B * 32, 256, stage ? (int)(kMixSmemPerSM / smem > 8 ? 8 : (kMixSmemPerSM / smem < 1 ? 1 : kMixSmemPerSM / smem)) : 8);
   cudaStream_t st = to_stream(s);
-  if (is_bf16) {
-    if (vec) gate_mix_fwd_kernel<uint16_t, 4><<<grid, 256, smem, st>>>(k, (const uint16_t*)H, ldh, logits, ldl, (uint16_t*)out, ldo, probs, B);
-    else gate_mix_fwd_kernel<uint16_t, 1><<<grid, 256, smem, st>>>(k, (const uint16_t*)H, ldh, logits, ldl, (uint16_t*)out, ldo, probs, B);
-  } else {
-    if (vec) gate_mix_fwd_kernel<float, 4><<<grid, 256, smem, st>>>(k, (const float*)H, ldh, logits, ldl, (float*)out, ldo, probs, B);
-    else gate_mix_fwd_kernel<float, 1><<<grid, 256, smem, st>>>(k, (const float*)H, ldh, logits, ldl, (float*)out, ldo, probs, B);
-  }
+#define MIXF(T, V, S) do { if (S) CDC_CHECK(cudaFuncSetAttribute(gate_mix_fwd_kernel<T, V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixStageSmem)); \
+    gate_mix_fwd_kernel<T, V, S><<<grid, 256, smem, st>>>(k, (const T*)H, ldh, logits, ldl, (T*)out, ldo, probs, B, stage_off); } while (0)
+  if (is_bf16) { if (stage) MIXF(uint16_t, 4, true); else if (vec) MIXF(uint16_t, 4, false); else MIXF(uint16_t, 1, false); }
+  else { if (stage) MIXF(float, 4, true); else if (vec) MIXF(float, 4, false); else MIXF(float, 1, false); }
+#undef MIXF
   CDC_LAUNCHED();
   return 0;
 }
@@ -600,16 +628,23 @@ extern "C" int cdcmdr_gate_mix_bwd(const cdcmdr_mix_desc_t* d, const void* H, in
   if (int rc = check_mix(d)) return rc;
   if (B == 0) return 0;
   MixK k{d->n_gates, d->n_experts, d->h, d->max_sel, d->gate_col, d->gate_n, d->gate_sel};
-  const size_t smem = (size_t)16 * d->n_gates * d->max_sel * sizeof(float);
+  size_t smem = (size_t)16 * d->n_gates * d->max_sel * sizeof(float);
   CDC_REQUIRE(smem <= 32 * 1024, "gate-mix descriptor too large");
-  const int grid = grid_1d(B * 32, 256);
   const int al = is_bf16 ? 8 : 16;
   const bool vec = d->h % 4 == 0 && ldh % 4 == 0 && ldo % 4 == 0 && lddh % 4 == 0 && ((uintptr_t)H % al == 0) &&
                    ((uintptr_t)dOut % al == 0) && ((uintptr_t)dH % al == 0);
+  const size_t elt = is_bf16 ? 2 : 4;
+  const size_t h_bytes = (size_t)d->n_experts * d->h * elt, o_bytes = (size_t)d->n_gates * d->h * elt;
+  const int stage_off = (int)((smem + 15) & ~(size_t)15);
+  const bool stage = vec && B >= 64 && h_bytes % 16 == 0 && o_bytes % 16 == 0 && (ldh * elt) % 16 == 0 && (ldo * elt) % 16 == 0 &&
+                     ((uintptr_t)H % 16) == 0 && ((uintptr_t)dOut % 16) == 0 && stage_off + 8 * (h_bytes + o_bytes) <= kMixStageSmem;
+  if (stage) smem = stage_off + 8 * (h_bytes + o_bytes);
+  const int grid = grid_1d(B * 32, 256, stage ? (int)(kMixSmemPerSM / smem > 8 ? 8 : (kMixSmemPerSM / smem < 1 ? 1 : kMixSmemPerSM / smem)) : 8);
   cudaStream_t st = to_stream(s);
-#define MIXB(T, V) gate_mix_bwd_kernel<T, V><<<grid, 256, smem, st>>>(k, (const T*)H, ldh, probs, (const T*)dOut, ldo, (T*)dH, lddh, relu_scale, dlogits, lddl, B)
-  if (is_bf16) { if (vec) MIXB(uint16_t, 4); else MIXB(uint16_t, 1); }
-  else { if (vec) MIXB(float, 4); else MIXB(float, 1); }
+#define MIXB(T, V, S) do { if (S) CDC_CHECK(cudaFuncSetAttribute(gate_mix_bwd_kernel<T, V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixStageSmem)); \
+    gate_mix_bwd_kernel<T, V, S><<<grid, 256, smem, st>>>(k, (const T*)H, ldh, probs, (const T*)dOut, ldo, (T*)dH, lddh, relu_scale, dlogits, lddl, B, stage_off); } while (0)
+  if (is_bf16) { if (stage) MIXB(uint16_t, 4, true); else if (vec) MIXB(uint16_t, 4, false); else MIXB(uint16_t, 1, false); }
+  else { if (stage) MIXB(float, 4, true); else if (vec) MIXB(float, 4, false); else MIXB(float, 1, false); }
 #undef MIXB
   CDC_LAUNCHED();
   return 0;
