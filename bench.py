@@ -299,7 +299,7 @@ def ours_arm(args):
     barrier()
     ms_e2e = max(e0.elapsed_time(e1), 0.0)
     wall_e2e = (time.perf_counter() - t0) * 1e3
-    loss_last = base.step_losses(dict(sums=sums_host, B=B, l2_table=base._l2_table()))[0]
+    loss_last = base.step_losses(dict(sums=sums_host, B=B * world, l2_table=base._l2_table()))[0]
     if world > 1:
         t = torch.tensor([ms, max(ms_e2e, wall_e2e)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

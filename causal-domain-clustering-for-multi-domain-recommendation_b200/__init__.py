@@ -10,5 +10,6 @@ from .ple import PLE, CGC  # noqa: F401
 from .mmoe import MMoE  # noqa: F401
 from .cdc import CDC  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
+from . import parallel  # noqa: F401
 
 __all__ = ["PLE", "CGC", "MMoE", "CDC", "Adam", "BaseModel", "GraphedTrainStep"]

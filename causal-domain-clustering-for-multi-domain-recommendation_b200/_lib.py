@@ -93,6 +93,10 @@ SIGNATURES = {
     "cdcmdr_bn_scratch_bytes": (SZ, [I64]),
     "cdcmdr_bn_fwd": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, I64, I64, P, P]),
     "cdcmdr_bn_bwd": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, P, I64, INT, P, I64, INT, P, P, INT, I64, I64, P, P]),
+    "cdcmdr_bn_fwd_stats": (INT, [P, I64, I64, I64, P, P, P]),
+    "cdcmdr_bn_fwd_apply": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, I64, I64, I64, P, P]),
+    "cdcmdr_bn_bwd_stats": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, P, I64, INT, P, P, INT, I64, I64, P, P, P]),
+    "cdcmdr_bn_bwd_apply": (INT, [C.POINTER(BnDesc), P, I64, P, I64, INT, P, I64, INT, P, I64, INT, I64, I64, I64, P, P, P]),
     "cdcmdr_rowdot_fwd": (INT, [P, I64, INT, P, P, P, I64, I64, INT, INT, P]),
     "cdcmdr_rowdot_bwd": (INT, [P, I64, INT, P, P, I64, P, I64, P, P, I64, INT, INT, P, P]),
     "cdcmdr_sigmoid_select_bce": (INT, [P, P, I64, I64, I32, I32, P, I32, P, INT, P, P, P, P, P, I64, F32, P, P]),

@@ -185,6 +185,30 @@ class Ops:
                         1 if (A is not None and A.is_bf16) else 0, dA.ptr, dA.ld, 1 if dA.is_bf16 else 0, dZ.ptr, dZ.ld,
                         1 if dZ.is_bf16 else 0, dgamma, dbeta, 1 if accumulate else 0, B, Cn, sc.data_ptr(), self.stream)
 
+    def bn_fwd_sync(self, d: BnDesc, Z: Mat, A: Mat, B, Cn, n_total, all_reduce):
+        """Cross-replica BatchNorm forward: local sums -> all_reduce(sums) -> statistics over n_total rows -> normalise."""
+        sc = self.scratch("bn", self.lib.bn_scratch_bytes(Cn))
+        sums = self.scratch(f"bn_sums", 16 * Cn).view(torch.float64)[:2 * Cn]
+        if d.train:
+            self.lib.bn_fwd_stats(Z.ptr, Z.ld, B, Cn, sums.data_ptr(), sc.data_ptr(), self.stream)
+            all_reduce(sums)
+        self.lib.bn_fwd_apply(C.byref(d), Z.ptr, Z.ld, A.ptr, A.ld, 1 if A.is_bf16 else 0, B, n_total, Cn, sums.data_ptr(), self.stream)
+
+    def bn_bwd_sync(self, d: BnDesc, Z: Mat, A: Mat | None, dA: Mat, dZ: Mat, dgamma, dbeta, accumulate, B, Cn, n_total, all_reduce):
+        sc = self.scratch("bn", self.lib.bn_scratch_bytes(Cn))
+        sums = self.scratch(f"bn_sums", 16 * Cn).view(torch.float64)[:2 * Cn]
+        a_ptr, a_ld, a_bf = (A.ptr, A.ld, 1 if A.is_bf16 else 0) if A is not None else (None, 0, 0)
+        self.lib.bn_bwd_stats(C.byref(d), Z.ptr, Z.ld, a_ptr, a_ld, a_bf, dA.ptr, dA.ld, 1 if dA.is_bf16 else 0, dgamma, dbeta,
+                              1 if accumulate else 0, B, Cn, sums.data_ptr(), sc.data_ptr(), self.stream)
+        if d.train:
+            all_reduce(sums)
+        self.lib.bn_bwd_apply(C.byref(d), Z.ptr, Z.ld, a_ptr, a_ld, a_bf, dA.ptr, dA.ld, 1 if dA.is_bf16 else 0, dZ.ptr, dZ.ld,
+                              1 if dZ.is_bf16 else 0, B, n_total, Cn, sums.data_ptr(), sc.data_ptr(), self.stream)
+
+    def copy2d(self, src_addr, lds, dst_addr, ldd, rows, cols, elt_bytes):
+        """strided 2-D copy (cdcmdr_permute_rows with the identity permutation)"""
+        self.lib.permute_rows(src_addr, lds, None, rows, cols, elt_bytes, dst_addr, ldd, 0, self.stream)
+
     # ---------------------------------------------------------------- Linear(d, 1) heads
     def rowdot_fwd(self, A: Mat, w_addr, b_addr, out: Mat, B, G, d):
         self.lib.rowdot_fwd(A.ptr, A.ld, 1 if A.is_bf16 else 0, w_addr, b_addr, out.ptr, out.ld, B, G, d, self.stream)

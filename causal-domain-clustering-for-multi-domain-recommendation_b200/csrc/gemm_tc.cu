@@ -132,12 +132,13 @@ struct TcParams {
 
 // Epilogue math for 32 consecutive columns [col0, col0+32) of one row; f in/out.  Returns packed bf16 pairs in o[16].
 struct EpiCtx {
-  int act; float mask_scale; bool has_mask, has_drop; uint32_t s0, thr16; float keep_scale;
+  int act; float mask_scale; bool has_mask, has_drop, has_old; uint32_t s0, thr16; float keep_scale;
 };
 
 __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], const float* bias_s /* smem, 32 floats, or null */,
-                                           const uint4* mask_row /* 4 x uint4 = 32 bf16, or null */, uint32_t row, uint32_t col0,
-                                           uint32_t (&o)[16]) {
+                                           const uint4* mask_row /* 4 x uint4 = 32 bf16, or null */,
+                                           const uint4* old_row /* previous output values (accumulate), 32 bf16 */, uint32_t row,
+                                           uint32_t col0, uint32_t (&o)[16]) {
   if (bias_s) {
     const float4* b4 = reinterpret_cast<const float4*>(bias_s);
 #pragma unroll
@@ -169,6 +170,15 @@ __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], cons
       x += kDropColMul;
       f[2 * j] = (h & 0xFFFFu) >= c.thr16 ? f[2 * j] * c.keep_scale : 0.f;
       f[2 * j + 1] = (h >> 16) >= c.thr16 ? f[2 * j + 1] * c.keep_scale : 0.f;
+    }
+  }
+  if (c.has_old) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint4 ov = old_row[j];
+      const uint32_t w[4] = {ov.x, ov.y, ov.z, ov.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { f[8 * j + 2 * k] += __uint_as_float(w[k] << 16); f[8 * j + 2 * k + 1] += __uint_as_float(w[k] & 0xFFFF0000u); }
     }
   }
 #pragma unroll
@@ -282,6 +292,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     int acc = 0; uint32_t acc_phase = 0;
     EpiCtx ec;
     ec.act = p.act; ec.mask_scale = p.mask_scale; ec.has_mask = p.mask != nullptr; ec.has_drop = p.drop_p > 0.f;
+    ec.has_old = p.accumulate != 0;
     ec.thr16 = drop_thr16(p.drop_p);
     ec.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     ec.s0 = p.drop_p > 0.f ? drop_s0(*p.seed_dev, p.salt) : 0u;
@@ -310,8 +321,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int cw = (int)min((int64_t)64, min((int64_t)p.block_n - c0, p.N - nb));     // valid columns in this chunk
         const bool full_main = nb + 64 <= p.n_main && cw == 64;
         // a chunk cut short by the END OF THE MATRIX may still go through TMA: the store map clips columns >= N
-        const bool clip_ok = p.G == 1 && p.n_main == p.N && !p.mask && nb + cw == p.N;
-        if (p.tma_store && !p.accumulate && (full_main || clip_ok)) {
+        const bool clip_ok = p.G == 1 && p.n_main == p.N && !p.mask && !p.accumulate && nb + cw == p.N;
+        if (p.tma_store && (full_main || clip_ok)) {
           // ---------------- fast path: 64 bf16 columns per row -> swizzled staging -> TMA store ----------------
           uint32_t v[64];
           tc_ld32_nowait(trow + c0, v);
@@ -325,6 +336,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 8; ++j) mk[j] = make_uint4(0, 0, 0, 0);
           }
+          uint4 old[8];
+          if (ec.has_old && m < p.M) {
+            const uint4* op4 = reinterpret_cast<const uint4*>(p.out_main + m * p.ld_main + g * p.main_gn + nb);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) old[j] = op4[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) old[j] = make_uint4(0, 0, 0, 0);
+          }
           if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
           __syncwarp();
           tc_ld_wait();
@@ -336,7 +356,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               float f[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[32 * hh + j]);
-              epi_math32(ec, f, use_bias ? bias_t + c0 + 32 * hh : nullptr, mk + 4 * hh, (uint32_t)m, gcol + 32 * hh, o);
+              epi_math32(ec, f, use_bias ? bias_t + c0 + 32 * hh : nullptr, mk + 4 * hh, old + 4 * hh, (uint32_t)m, gcol + 32 * hh, o);
             } else {
 #pragma unroll
               for (int j = 0; j < 16; ++j) o[j] = 0u;

@@ -202,7 +202,7 @@ __global__ void permute_rows_kernel(const V* __restrict__ src, int64_t lds, cons
   const int64_t total = n * vec_cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = i % vec_cols, r = i / vec_cols;
-    const int64_t p = perm[r];
+    const int64_t p = perm ? (int64_t)perm[r] : r;          // perm == NULL: plain strided 2-D copy
     if (scatter) dst[p * ldd + c] = src[r * lds + c];
     else dst[r * ldd + c] = src[p * lds + c];
   }

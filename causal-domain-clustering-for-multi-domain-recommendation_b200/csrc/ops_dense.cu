@@ -371,6 +371,16 @@ template <typename T, typename TD> struct BnBwdStatF {
   }
 };
 
+// sums2[v*C + c] = sum_k partial[(v*chunks + k)*C + c], v in {0, 1}: the per-feature sums of one rank
+__global__ void chunks_to_sums_kernel(const double* __restrict__ partial, int chunks, int64_t C, double* __restrict__ sums2) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 2 * C) return;
+  const int64_t v = i / C, c = i % C;
+  double t = 0;
+  for (int k = 0; k < chunks; ++k) t += partial[((int64_t)v * chunks + k) * C + c];
+  sums2[i] = t;
+}
+
 // sums[0][c] = sum dy, sums[1][c] = sum dy*xhat  (fp32 copies kept in `sums` for the apply kernel)
 __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, int64_t C, float* __restrict__ sums,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta, int accumulate) {
@@ -386,11 +396,11 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int c
 template <typename T, typename TD, typename TZ>
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ Z, int64_t ldz, const T* __restrict__ A, int64_t lda,
                                     const TD* __restrict__ dA, int64_t ldda, TZ* __restrict__ dZ, int64_t lddz,
-                                    int64_t B, int64_t C, const float* __restrict__ gamma, const float* __restrict__ gamma2,
+                                    int64_t B, int64_t n_total, int64_t C, const float* __restrict__ gamma, const float* __restrict__ gamma2,
                                     const float* __restrict__ mean, const float* __restrict__ invstd,
                                     const float* __restrict__ sums, int relu, float keep_scale, int train) {
   const int64_t total = B * C;
-  const float inv_n = 1.f / (float)B;
+  const float inv_n = 1.f / (float)n_total;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t c = i % C, r = i / C;
     float dy = ld_act<TD>(dA + r * ldda + c);
@@ -653,7 +663,7 @@ extern "C" int cdcmdr_gate_mix_bwd(const cdcmdr_mix_desc_t* d, const void* H, in
 extern "C" size_t cdcmdr_colsum_scratch_bytes(int64_t C) { return (size_t)kMaxChunks * (size_t)(C > 0 ? C : 1) * sizeof(double); }
 extern "C" size_t cdcmdr_bn_scratch_bytes(int64_t C) {
   const size_t c = (size_t)(C > 0 ? C : 1);
-  return 2 * (size_t)kMaxChunks * c * sizeof(double) + 2 * c * sizeof(float) + 256;
+  return 2 * (size_t)kMaxChunks * c * sizeof(double) + 2 * c * sizeof(float) + 512 + 2 * c * sizeof(double);
 }
 extern "C" size_t cdcmdr_reduce_scratch_bytes(void) { return kReducePartials * sizeof(double); }
 
@@ -688,24 +698,42 @@ extern "C" int cdcmdr_colsum(const void* X, int64_t ld, int is_bf16, int64_t B, 
   return 0;
 }
 
-extern "C" int cdcmdr_bn_fwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, void* A, int64_t lda_, int a_is_bf16,
-                             int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s) {
-  CDC_REQUIRE(p && p->gamma && p->beta && p->save_mean && p->save_invstd && scratch, "bad batch-norm arguments");
-  CDC_REQUIRE(p->train || (p->running_mean && p->running_var), "eval batch-norm needs running statistics");
-  CDC_REQUIRE(p->drop_p <= 0.f || (p->seed_dev && p->relu), "batch-norm dropout needs relu and a device seed");
-  CDC_REQUIRE((p->gamma2 == nullptr) == (p->beta2 == nullptr), "gamma2/beta2 must come together");
-  if (B == 0 || C == 0) return 0;
+// ---- BatchNorm in two stages, so that data-parallel ranks can all-reduce the per-feature sums in between.
+// scratch layout: [2*kMaxChunks*C doubles: per-chunk partials][2*C floats: backward sums][pad to 8][2*C doubles: stage sums]
+static double* bn_stage_sums(void* scratch, int64_t C) {
+  size_t off = 2 * (size_t)kMaxChunks * (size_t)C * sizeof(double) + 2 * (size_t)C * sizeof(float);
+  off = (off + 255) & ~(size_t)255;
+  return (double*)((char*)scratch + off);
+}
+
+extern "C" int cdcmdr_bn_fwd_stats(const float* Z, int64_t ldz, int64_t B, int64_t C, double* sums, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(Z && sums && scratch, "bad batch-norm arguments");
+  if (C == 0) return 0;
   cudaStream_t st = to_stream(s);
+  if (B == 0) { CDC_CHECK(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st)); return 0; }
   const int chunks = pick_chunks(B, C);
   double* partial = (double*)scratch;
-  if (p->train) {
-    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
-    col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, BnStatF{Z, ldz});
-    CDC_LAUNCHED();
-  }
-  bn_fwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, chunks, B, C, p->train, p->running_mean, p->running_var,
+  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+  col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, BnStatF{Z, ldz});
+  CDC_LAUNCHED();
+  chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 256), 256, 0, st>>>(partial, chunks, C, sums);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_bn_fwd_apply(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, void* A, int64_t lda_, int a_is_bf16,
+                                   int64_t B, int64_t n_total, int64_t C, const double* sums, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && p->gamma && p->beta && p->save_mean && p->save_invstd, "bad batch-norm arguments");
+  CDC_REQUIRE(p->train || (p->running_mean && p->running_var), "eval batch-norm needs running statistics");
+  CDC_REQUIRE(!p->train || sums, "train batch-norm needs the stage-1 sums");
+  CDC_REQUIRE(p->drop_p <= 0.f || (p->seed_dev && p->relu), "batch-norm dropout needs relu and a device seed");
+  CDC_REQUIRE((p->gamma2 == nullptr) == (p->beta2 == nullptr), "gamma2/beta2 must come together");
+  if (C == 0) return 0;
+  cudaStream_t st = to_stream(s);
+  bn_fwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(sums, 1, n_total, C, p->train, p->running_mean, p->running_var,
                                                                     p->save_mean, p->save_invstd);
   CDC_LAUNCHED();
+  if (B == 0) return 0;
   const int g = grid_1d(B * C, 256);
   if (a_is_bf16)
     bn_apply_kernel<uint16_t><<<g, 256, 0, st>>>(Z, ldz, (uint16_t*)A, lda_, B, C, p->gamma, p->beta, p->gamma2, p->beta2, p->save_mean,
@@ -717,34 +745,84 @@ extern "C" int cdcmdr_bn_fwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, 
   return 0;
 }
 
-extern "C" int cdcmdr_bn_bwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
-                             const void* dA, int64_t ldda, int da_is_bf16, void* dZ, int64_t lddz, int dz_is_bf16, float* dgamma, float* dbeta,
-                             int accumulate, int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s) {
-  CDC_REQUIRE(p && p->gamma && p->save_mean && p->save_invstd && scratch && dA && dZ, "bad batch-norm arguments");
-  CDC_REQUIRE(!p->relu || A, "relu backward needs the forward output");
+extern "C" int cdcmdr_bn_fwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, void* A, int64_t lda_, int a_is_bf16,
+                             int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && scratch, "bad batch-norm arguments");
   if (B == 0 || C == 0) return 0;
+  double* sums = bn_stage_sums(scratch, C);
+  if (p->train) { if (int rc = cdcmdr_bn_fwd_stats(Z, ldz, B, C, sums, scratch, s)) return rc; }
+  return cdcmdr_bn_fwd_apply(p, Z, ldz, A, lda_, a_is_bf16, B, B, C, sums, s);
+}
+
+// stage 1 of the backward: LOCAL sums over the rows (sums[0..C) = sum dy, sums[C..2C) = sum dy*xhat) and the parameter
+// gradients they are (dgamma = sum dy*xhat, dbeta = sum dy; the data-parallel all-reduce of the gradient arena adds ranks)
+extern "C" int cdcmdr_bn_bwd_stats(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
+                                   const void* dA, int64_t ldda, int da_is_bf16, float* dgamma, float* dbeta, int accumulate,
+                                   int64_t B, int64_t C, double* sums, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && p->gamma && p->save_mean && p->save_invstd && scratch && sums, "bad batch-norm arguments");
+  CDC_REQUIRE(!p->relu || A, "relu backward needs the forward output");
+  if (C == 0) return 0;
   cudaStream_t st = to_stream(s);
+  if (B == 0) {
+    CDC_CHECK(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st));
+    if (!accumulate) {
+      if (dgamma) CDC_CHECK(cudaMemsetAsync(dgamma, 0, (size_t)C * sizeof(float), st));
+      if (dbeta) CDC_CHECK(cudaMemsetAsync(dbeta, 0, (size_t)C * sizeof(float), st));
+    }
+    return 0;
+  }
+  CDC_REQUIRE(dA, "bad batch-norm arguments");
   const int chunks = pick_chunks(B, C);
   double* partial = (double*)scratch;
-  float* sums = (float*)((char*)scratch + 2 * (size_t)kMaxChunks * (size_t)C * sizeof(double));
+  float* fsums = (float*)((char*)scratch + 2 * (size_t)kMaxChunks * (size_t)C * sizeof(double));
   const float keep_scale = p->drop_p > 0.f ? 1.f / (1.f - p->drop_p) : 1.f;
   dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
-  const int combo = (a_is_bf16 ? 4 : 0) | (da_is_bf16 ? 2 : 0) | (dz_is_bf16 ? 1 : 0);
-  CDC_REQUIRE(combo == 0 || combo == 5 || combo == 7, "batch-norm backward dtypes: (A, dA, dZ) must be fp32x3, (bf16, fp32, bf16) or bf16x3");
+  const int combo = (a_is_bf16 ? 2 : 0) | (da_is_bf16 ? 1 : 0);
+  CDC_REQUIRE(combo == 0 || combo == 2 || combo == 3, "batch-norm backward dtypes: (A, dA) must be (fp32, fp32), (bf16, fp32) or (bf16, bf16)");
 #define BNS(TA, TD) col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, \
       BnBwdStatF<TA, TD>{Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale})
-  if (combo == 0) BNS(float, float); else if (combo == 5) BNS(uint16_t, float); else BNS(uint16_t, uint16_t);
+  if (combo == 0) BNS(float, float); else if (combo == 2) BNS(uint16_t, float); else BNS(uint16_t, uint16_t);
 #undef BNS
   CDC_LAUNCHED();
-  bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, chunks, C, sums, dgamma, dbeta, accumulate);
+  chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 256), 256, 0, st>>>(partial, chunks, C, sums);
+  CDC_LAUNCHED();
+  bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(sums, 1, C, fsums, dgamma, dbeta, accumulate);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+// stage 2: dZ for the local rows from sums over ALL n_total rows
+extern "C" int cdcmdr_bn_bwd_apply(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
+                                   const void* dA, int64_t ldda, int da_is_bf16, void* dZ, int64_t lddz, int dz_is_bf16,
+                                   int64_t B, int64_t n_total, int64_t C, const double* sums, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && p->gamma && p->save_mean && p->save_invstd && scratch && sums, "bad batch-norm arguments");
+  CDC_REQUIRE(!p->relu || A, "relu backward needs the forward output");
+  if (B == 0 || C == 0) return 0;
+  CDC_REQUIRE(dA && dZ, "bad batch-norm arguments");
+  cudaStream_t st = to_stream(s);
+  float* fsums = (float*)((char*)scratch + 2 * (size_t)kMaxChunks * (size_t)C * sizeof(double));
+  const float keep_scale = p->drop_p > 0.f ? 1.f / (1.f - p->drop_p) : 1.f;
+  const int combo = (a_is_bf16 ? 4 : 0) | (da_is_bf16 ? 2 : 0) | (dz_is_bf16 ? 1 : 0);
+  CDC_REQUIRE(combo == 0 || combo == 5 || combo == 7, "batch-norm backward dtypes: (A, dA, dZ) must be fp32x3, (bf16, fp32, bf16) or bf16x3");
+  bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(sums, 1, C, fsums, nullptr, nullptr, 0);
   CDC_LAUNCHED();
   const int g = grid_1d(B * C, 256);
 #define BNB(TA, TD, TZ) bn_bwd_apply_kernel<TA, TD, TZ><<<g, 256, 0, st>>>(Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, (TZ*)dZ, lddz, \
-      B, C, p->gamma, p->gamma2, p->save_mean, p->save_invstd, sums, p->relu, keep_scale, p->train)
+      B, n_total, C, p->gamma, p->gamma2, p->save_mean, p->save_invstd, fsums, p->relu, keep_scale, p->train)
   if (combo == 0) BNB(float, float, float); else if (combo == 5) BNB(uint16_t, float, uint16_t); else BNB(uint16_t, uint16_t, uint16_t);
 #undef BNB
   CDC_LAUNCHED();
   return 0;
+}
+
+extern "C" int cdcmdr_bn_bwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
+                             const void* dA, int64_t ldda, int da_is_bf16, void* dZ, int64_t lddz, int dz_is_bf16, float* dgamma, float* dbeta,
+                             int accumulate, int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(p && scratch && dA && dZ, "bad batch-norm arguments");
+  if (B == 0 || C == 0) return 0;
+  double* sums = bn_stage_sums(scratch, C);
+  if (int rc = cdcmdr_bn_bwd_stats(p, Z, ldz, A, lda_, a_is_bf16, dA, ldda, da_is_bf16, dgamma, dbeta, accumulate, B, C, sums, scratch, s)) return rc;
+  return cdcmdr_bn_bwd_apply(p, Z, ldz, A, lda_, a_is_bf16, dA, ldda, da_is_bf16, dZ, lddz, dz_is_bf16, B, B, C, sums, scratch, s);
 }
 
 extern "C" int cdcmdr_rowdot_fwd(const void* A, int64_t lda_, int a_is_bf16, const float* w, const float* bias, float* out, int64_t ldo,

@@ -224,6 +224,8 @@ class BaseModel(nn.Module):
             for m in self._absent_grads():
                 o = rt.params.off[m]
                 rt.present[o:o + named[m].numel()] = 0
+        if old is not None:
+            rt.dp = old.dp
         if old is not None and old.M is not None:
             rt.M, rt.V = old.M.to(device), old.V.to(device)
             rt.step_state = old.step_state.to(device) if old.step_state is not None else None
@@ -273,9 +275,12 @@ class BaseModel(nn.Module):
         E, F = self.embed_dim, self.field_num
         table = self.embedding.embedding_dict.weight
         X = ws.mat("X", B, F * E, rt.act_dtype)
+        if rt.bf16 and (F * E) % 8:
+            raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
+        if rt.dp is not None and rt.dp.shard:
+            rt.dp.embed_forward(ws, x, B, X)          # row-sharded table: indices to the owners, rows back (parallel.py)
+            return X
         if rt.bf16:
-            if (F * E) % 8:
-                raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
             rt.ops.embed_gather(x, self.embedding.offsets_dev, table, None, X, B, F, E, table.shape[0])
         else:
             rt.ops.embed_gather(x, self.embedding.offsets_dev, table, X, None, B, F, E, table.shape[0])
@@ -317,6 +322,9 @@ class BaseModel(nn.Module):
         """dpred: gradient w.r.t. the (B, T) predictions.  Returns gradients for (dense parameters..., table)."""
         last = self._last
         rt, ws, B, T = self._rt, last["ws"], last["B"], self.n_out
+        if rt.dp is not None:
+            raise NotImplementedError("cdcmdr: the autograd path (loss.backward()) is single-device; data-parallel replicas "
+                                      "train through model.train_step()")
         dlogits = ws.get("dlogits", (B, T))
         dlin = self._dlin_mat(ws, B)
         rt.ops.sigmoid_bwd(last["pred"], self._unshape_dpred(dpred, B, T), dlogits, dlin, B, T)
@@ -413,30 +421,41 @@ class BaseModel(nn.Module):
         logits, lin = self._program_fwd(ws, X, B, True, **kw)
         pred = ws.get("pred", (B, T))
         psel = ws.get("psel", (B,))
-        sums = ws.get("loss_sums", (4,), torch.float64)      # [bce_sum, reg_dense, table_sumsq, -]
+        sums = ws.get("loss_sums", (4,), torch.float64)      # [bce_sum, table_sumsq, reg_dense, -]; [0:2] are per-rank partial sums
+        dp = rt.dp
+        n_global = dp.global_rows(B) if dp is not None else B
         dlogits = ws.get("dlogits", (B, T))
         dlin = self._dlin_mat(ws, B)
         y, sel = self._route_targets(ws, y, sel, B, **kw)
         rt.ops.sigmoid_select_bce(logits.t, lin, B, T, self.SEL_MODES[mode], sel, col, y, pred, psel, sums[0:1], dlogits,
-                                  dlin, 1.0 / B)
+                                  dlin, 1.0 / n_global)
         self._fwd_token += 1
         self._last = None
         self._bump_batches_tracked(B)
         dX = self._program_bwd(ws, X, B, True, Mat(dlogits, 0, T), **kw)
-        rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[1:2])
+        if dp is not None:
+            dp.all_reduce_sum(rt.G)                          # dense gradients: sum over replicas of d(global mean loss)
+        rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
         rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
         table = self.embedding.embedding_dict.weight
         V, E, F = table.shape[0], self.embed_dim, self.field_num
-        plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
-        if self._table_state is None:
-            self._table_state = (torch.zeros_like(table), torch.zeros_like(table))
-        m, v = self._table_state
         l2t = self._l2_table()
-        lazy = self.embedding_update == "sparse_lazy"
-        if lazy:
-            rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[2:3])
-        rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[2:3], lazy=lazy)
-        return dict(sums=sums, pred=pred[:B * T].view(B, T), psel=psel[:B], B=B, l2_table=l2t)
+        if dp is not None and dp.shard:
+            dp.embed_backward(ws, dX, B, l2t, sums[1:2])     # row gradients to the owners; owner-side segment sum + Adam
+        else:
+            if dp is not None:
+                raise NotImplementedError("cdcmdr: data-parallel replicas need the row-sharded table (shard_embedding=True)")
+            plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
+            if self._table_state is None:
+                self._table_state = (torch.zeros_like(table), torch.zeros_like(table))
+            m, v = self._table_state
+            lazy = self.embedding_update == "sparse_lazy"
+            if lazy:
+                rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[1:2])
+            rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[1:2], lazy=lazy)
+        if dp is not None:
+            dp.all_reduce_sum(sums[0:2])                     # BCE sum and table sum-of-squares are per-rank partials
+        return dict(sums=sums, pred=pred[:B * T].view(B, T), psel=psel[:B], B=n_global, l2_table=l2t)
 
     @staticmethod
     def step_losses(out):
@@ -444,7 +463,7 @@ class BaseModel(nn.Module):
         run.py:484-489: float32 bce + float32 reg."""
         s = out["sums"].tolist()
         bce = np.float32(s[0] / out["B"])
-        reg = np.float32(s[1] + out["l2_table"] * s[2])
+        reg = np.float32(s[2] + out["l2_table"] * s[1])
         return float(np.float32(bce + reg)), float(bce), float(reg)
 
     def _route_targets(self, ws, y, sel, B, **kw):

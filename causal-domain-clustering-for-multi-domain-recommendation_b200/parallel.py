@@ -1,0 +1,168 @@
+"""One process per GPU over `torch.distributed` (NCCL on B200 / NVLink, gloo for the CPU tests): the reference is a
+single-device program ("Parallelism"), so everything here is defined by what makes N ranks with B rows each
+produce exactly what the reference produces on the concatenated N*B-row batch:
+
+  * dense compute is data-parallel: every rank runs the model program on its B rows; the loss is the mean over the
+    GLOBAL batch (the BCE kernel is given 1/(N*B)), the dense gradient arena is all-reduced (sum) before the fused Adam,
+    so every replica applies the identical update;
+  * train-mode BatchNorm statistics are over the global batch: per-feature (sum, sum of squares) and the backward's
+    (sum dy, sum dy*xhat) are all-reduced between the two stages of the BatchNorm kernels (cdcmdr_bn_*_stats/_apply);
+  * the embedding table is ROW-SHARDED in contiguous ranges cut at field boundaries: rank r owns the rows of fields
+    [f0_r, f1_r) of the single concatenated table (layer.py:140) together with their Adam moments, and only the owner
+    ever reads or writes them.  Forward: all-to-all of the index columns to their owners -> owner-side gather kernel ->
+    all-to-all of the gathered rows back.  Backward: all-to-all of the row gradients to the owners -> owner-side
+    sorted-segment sum over all N*B samples fused with the reference-exact Adam sweep over the owner's rows only.
+    Cutting at field boundaries makes every message size a compile-time function of (B, fields) - no host
+    synchronisation, so the whole step still records into one CUDA graph.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .core import Mat
+
+
+def split_fields(n_fields: int, world: int):
+    """Contiguous field ranges [(f0, f1)] per rank, sizes differing by at most one."""
+    cuts = [(r * n_fields) // world for r in range(world + 1)]
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+class DataParallel:
+    def __init__(self, model, group=None, shard_embedding=True):
+        if not dist.is_initialized():
+            raise RuntimeError("cdcmdr.parallel: torch.distributed is not initialised")
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank = dist.get_rank(self.group)
+        self.world = dist.get_world_size(self.group)
+        self.model = model
+        self.shard = bool(shard_embedding) and self.world > 1
+        emb = model.embedding
+        self.F, self.E = emb.field_num, emb.embed_dim
+        off = np.asarray(emb.offsets, dtype=np.int64)
+        V = int(emb.embedding_dict.weight.shape[0])
+        self.ranges = split_fields(self.F, self.world)
+        self.nf = [f1 - f0 for f0, f1 in self.ranges]
+        bounds = np.concatenate([off, [V]])
+        self.row_range = [(int(bounds[f0]), int(bounds[f1])) for f0, f1 in self.ranges]
+        self.f0, self.f1 = self.ranges[self.rank]
+        self.row0, self.row1 = self.row_range[self.rank]
+        self._dev_state = None
+        self._moments = None
+        model._rt.dp = self
+        model._dp = self
+
+    # ---------------------------------------------------------------- collectives (plumbing only)
+    def global_rows(self, B):
+        return B * self.world
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _all_to_all(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits):
+        if out.device.type == "cuda":
+            dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
+            return
+        # gloo has no all_to_all on CPU tensors: the same exchange as pairwise sends
+        outs = list(out.split(out_splits))
+        ins = list(inp.split(in_splits))
+        outs[self.rank].copy_(ins[self.rank])
+        reqs = []
+        for r in range(self.world):
+            if r != self.rank:
+                reqs.append(dist.isend(ins[r].contiguous(), dist.get_global_rank(self.group, r), group=self.group))
+        for r in range(self.world):
+            if r != self.rank and outs[r].numel():
+                tmp = torch.empty_like(outs[r])
+                dist.recv(tmp, dist.get_global_rank(self.group, r), group=self.group)
+                outs[r].copy_(tmp)
+        for q in reqs:
+            q.wait()
+
+    # ---------------------------------------------------------------- sharded table
+    def _state(self, device):
+        if self._dev_state is None or self._dev_state["device"] != device:
+            emb = self.model.embedding
+            off = torch.as_tensor(np.asarray(emb.offsets[self.f0:self.f1], dtype=np.int64) - self.row0, device=device)
+            if off.numel() == 0:
+                off = torch.zeros(1, dtype=torch.int64, device=device)
+            self._dev_state = dict(device=device, offsets_local=off)
+        return self._dev_state
+
+    def shard_view(self):
+        """This rank's rows of the concatenated table (a view: the owner updates them in place)."""
+        return self.model.embedding.embedding_dict.weight.data[self.row0:self.row1]
+
+    def moments(self):
+        if self._moments is None:
+            sv = self.shard_view()
+            self._moments = (torch.zeros_like(sv), torch.zeros_like(sv))
+        return self._moments
+
+    def embed_forward(self, ws, x, B, X: Mat):
+        """x: this rank's [B, F] int32 indices -> X[B, F*E] (activation dtype) through the owners of each field."""
+        rt = self.model._rt
+        ops, N, E, F = rt.ops, self.world, self.E, self.F
+        nf_me = self.f1 - self.f0
+        st = self._state(x.device)
+        send_ids = ws.get("dp.send_ids", (B * F,), torch.int32)
+        for o, (f0, f1) in enumerate(self.ranges):
+            if f1 > f0:
+                ops.copy2d(x.data_ptr() + 4 * f0, F, send_ids.data_ptr() + 4 * B * f0, f1 - f0, B, f1 - f0, 4)
+        recv_ids = ws.get("dp.recv_ids", (N * B * max(nf_me, 1),), torch.int32)
+        self._all_to_all(recv_ids[:N * B * nf_me], send_ids[:B * F], [B * nf_me] * N, [B * n for n in self.nf])
+        esz = 2 if rt.bf16 else 4
+        rows_send = ws.get("dp.rows_send", (N * B * max(nf_me, 1) * E,), rt.act_dtype)
+        if nf_me:
+            shard = self.shard_view()
+            m = Mat(rows_send, 0, nf_me * E)
+            ops.embed_gather(recv_ids, st["offsets_local"], shard, None if rt.bf16 else m, m if rt.bf16 else None, N * B, nf_me, E,
+                             shard.shape[0])
+        rows_recv = ws.get("dp.rows_recv", (B * F * E,), rt.act_dtype)
+        self._all_to_all(rows_recv[:B * F * E], rows_send[:N * B * nf_me * E], [B * n * E for n in self.nf], [B * nf_me * E] * N)
+        for o, (f0, f1) in enumerate(self.ranges):
+            if f1 > f0:
+                ops.copy2d(rows_recv.data_ptr() + esz * B * f0 * E, (f1 - f0) * E, X.ptr + esz * f0 * E, X.ld, B, (f1 - f0) * E, esz)
+        return recv_ids
+
+    def embed_backward(self, ws, dX: Mat, B, l2, sumsq_out):
+        """dX: fp32 [B, F*E] gradient of this rank's gathered rows -> owner-side segment sum + Adam on the owner's rows.
+        sumsq_out (device double[1]): sum of squares of the owner's rows before the update (regulariser value)."""
+        rt = self.model._rt
+        ops, N, E, F = rt.ops, self.world, self.E, self.F
+        nf_me = self.f1 - self.f0
+        st = self._state(dX.t.device)
+        gsend = ws.get("dp.grad_send", (B * F * E,), torch.float32)
+        for o, (f0, f1) in enumerate(self.ranges):
+            if f1 > f0:
+                ops.copy2d(dX.ptr + 4 * f0 * E, dX.ld, gsend.data_ptr() + 4 * B * f0 * E, (f1 - f0) * E, B, (f1 - f0) * E, 4)
+        grecv = ws.get("dp.grad_recv", (N * B * max(nf_me, 1) * E,), torch.float32)
+        self._all_to_all(grecv[:N * B * nf_me * E], gsend[:B * F * E], [B * nf_me * E] * N, [B * n * E for n in self.nf])
+        if not nf_me:
+            sumsq_out.zero_()
+            return
+        shard = self.shard_view()
+        Vl = shard.shape[0]
+        recv_ids = ws.get("dp.recv_ids", (N * B * nf_me,), torch.int32)
+        plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+        m, v = self.moments()
+        lazy = self.model.embedding_update == "sparse_lazy"
+        if lazy:
+            ops.reg_l2_sum(shard, None, 1.0, shard.numel(), sumsq_out)
+        ops.embed_bwd_adam(Mat(grecv, 0, nf_me * E), plan, N * B, nf_me, E, Vl, shard, m, v, l2, rt.step_state,
+                           None if lazy else sumsq_out, lazy=lazy)
+
+    def gather_table(self):
+        """Make every rank's full table current (checkpointing / state_dict): broadcast each owner's rows."""
+        w = self.model.embedding.embedding_dict.weight.data
+        for r, (r0, r1) in enumerate(self.row_range):
+            if r1 > r0:
+                dist.broadcast(w[r0:r1], dist.get_global_rank(self.group, r), group=self.group)
+
+
+def attach_data_parallel(model, group=None, shard_embedding=True) -> DataParallel:
+    """Make `model` (a cdcmdr BaseModel, or a CDC wrapper) one replica of a data-parallel group."""
+    base = getattr(model, "base_model_instance", model)
+    return DataParallel(base, group, shard_embedding)

@@ -59,6 +59,7 @@ class Runtime:
         self.dropout = 0.0
         self.base_seed = 2000
         self._salt = 0
+        self.dp = None                 # parallel.DataParallel when the model is one replica of a data-parallel group
 
     @property
     def bf16(self) -> bool:
@@ -141,6 +142,19 @@ class Runtime:
         out = ws.mat(name, rows, ld, torch.bfloat16, zero=True)
         self.ops.cast_f32_bf16(m, out, rows, cols)
         return out
+
+    # ---------------------------------------------------------------- BatchNorm (cross-replica when data-parallel)
+    def bn_fwd(self, desc, Z: Mat, A: Mat, B, Cn):
+        if self.dp is not None and desc.train:
+            self.ops.bn_fwd_sync(desc, Z, A, B, Cn, self.dp.global_rows(B), self.dp.all_reduce_sum)
+        else:
+            self.ops.bn_fwd(desc, Z, A, B, Cn)
+
+    def bn_bwd(self, desc, Z: Mat, A, dA: Mat, dZ: Mat, dgamma, dbeta, accumulate, B, Cn):
+        if self.dp is not None and desc.train:
+            self.ops.bn_bwd_sync(desc, Z, A, dA, dZ, dgamma, dbeta, accumulate, B, Cn, self.dp.global_rows(B), self.dp.all_reduce_sum)
+        else:
+            self.ops.bn_bwd(desc, Z, A, dA, dZ, dgamma, dbeta, accumulate, B, Cn)
 
     # ---------------------------------------------------------------- grouped Linear building blocks
     # W[g] is [N, K] row-major at arena element offset w_off + g*N*K; bias [N] at b_off + g*N.
@@ -250,7 +264,7 @@ class MlpGroup:
                                       rt.b(self.names["rmean"][j]), rt.b(self.names["rvar"][j]),
                                       sm.data_ptr(), sm.data_ptr() + 4 * G * d, train, True,
                                       drop_p=drop, seed_ptr=rt.seed_ptr if drop > 0 else None, salt=self.salts[j])
-                rt.ops.bn_fwd(desc, Y, A, B, G * d)
+                rt.bn_fwd(desc, Y, A, B, G * d)
                 Y = A
             prev, prev_d = Y, d
         if self.out_layer:
@@ -289,7 +303,7 @@ class MlpGroup:
                 desc = rt.ops.bn_desc(rt.w(self.names["gamma"][j]), rt.w(self.names["beta"][j]), None, None,
                                       sm.data_ptr(), sm.data_ptr() + 4 * G * d, train, True, drop_p=drop,
                                       seed_ptr=rt.seed_ptr if drop > 0 else None)
-                rt.ops.bn_bwd(desc, Z, A, cur, dZ, rt.g(self.names["gamma"][j]), rt.g(self.names["beta"][j]), False, B, G * d)
+                rt.bn_bwd(desc, Z, A, cur, dZ, rt.g(self.names["gamma"][j]), rt.g(self.names["beta"][j]), False, B, G * d)
                 cur = dZ
             # cur is now dZ_j  [B, G*d]
             rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j]))

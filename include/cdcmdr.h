@@ -192,6 +192,24 @@ int cdcmdr_bn_bwd(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void*
                   float* dgamma, float* dbeta,
                   int accumulate, int64_t B, int64_t C, void* scratch, cdcmdr_stream_t s);
 
+/* The same two reductions split at the point where data-parallel ranks exchange per-feature sums (train-mode
+ * BatchNorm statistics are over the GLOBAL batch in the single-device reference).  `sums` is a device double[2*C]:
+ *   forward : sums[c] = sum_b z, sums[C+c] = sum_b z^2 over the local B rows; the caller all-reduces it over ranks and
+ *             passes n_total = total rows; cdcmdr_bn_fwd_apply derives mean / var / running statistics and normalises.
+ *   backward: cdcmdr_bn_bwd_stats writes sums[c] = sum_b dy, sums[C+c] = sum_b dy*xhat (local rows) and the LOCAL parameter
+ *             gradients dgamma / dbeta (the gradient all-reduce adds the ranks); after the all-reduce of `sums`,
+ *             cdcmdr_bn_bwd_apply computes dZ for the local rows.
+ * cdcmdr_bn_fwd / cdcmdr_bn_bwd are exactly stats + apply with n_total = B.  B may be 0 (a rank with no rows). */
+int cdcmdr_bn_fwd_stats(const float* Z, int64_t ldz, int64_t B, int64_t C, double* sums, void* scratch, cdcmdr_stream_t s);
+int cdcmdr_bn_fwd_apply(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, void* A, int64_t lda_, int a_is_bf16,
+                        int64_t B, int64_t n_total, int64_t C, const double* sums, cdcmdr_stream_t s);
+int cdcmdr_bn_bwd_stats(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
+                        const void* dA, int64_t ldda, int da_is_bf16, float* dgamma, float* dbeta, int accumulate,
+                        int64_t B, int64_t C, double* sums, void* scratch, cdcmdr_stream_t s);
+int cdcmdr_bn_bwd_apply(const cdcmdr_bn_t* p, const float* Z, int64_t ldz, const void* A, int64_t lda_, int a_is_bf16,
+                        const void* dA, int64_t ldda, int da_is_bf16, void* dZ, int64_t lddz, int dz_is_bf16,
+                        int64_t B, int64_t n_total, int64_t C, const double* sums, void* scratch, cdcmdr_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * a4/a8  the Linear(d, 1) output layer of G towers                       layer.py:192-193
  * fwd:  logit[b*ldo + g] = A[b, g*d:(g+1)*d] . w[g*d:(g+1)*d] + bias[g]      (A fp32 or bf16)
@@ -298,7 +316,8 @@ int cdcmdr_softmax_rows_bwd(const float* p, int64_t ldp, const float* dp, int64_
 size_t cdcmdr_route_scratch_bytes(int64_t B, int n_group);
 int cdcmdr_route_partition(const int64_t* group, int64_t B, int n_group, int32_t* perm, int32_t* counts,
                            int32_t* group_start, void* scratch, cdcmdr_stream_t s);
-/* gather: dst[i, :] = src[perm[i], :] ; scatter: dst[perm[i], :] = src[i, :]   (rows of cols*elt_bytes bytes) */
+/* gather: dst[i, :] = src[perm[i], :] ; scatter: dst[perm[i], :] = src[i, :]   (rows of cols*elt_bytes bytes).
+ * perm == NULL: identity, i.e. a strided 2-D copy (packing / unpacking the per-owner blocks of the embedding exchange) */
 int cdcmdr_permute_rows(const void* src, int64_t lds, const int32_t* perm, int64_t n, int64_t cols, int elt_bytes,
                         void* dst, int64_t ldd, int scatter, cdcmdr_stream_t s);
 /* a15  groups[b] = domain2group[x[b, domain_idx]]                       cdc.py:105 */

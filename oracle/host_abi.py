@@ -321,10 +321,27 @@ class HostABI:
         return 256
 
     def bn_fwd(self, ref, Z, ldz, A, lda, a_is_bf16, B, Cn, scratch, s):
+        if B == 0 or Cn == 0:
+            return 0
+        sums = np.zeros(2 * Cn, dtype=np.float64)
+        if _obj(ref).train:
+            self.bn_fwd_stats(Z, ldz, B, Cn, sums.ctypes.data, scratch, s)
+        return self.bn_fwd_apply(ref, Z, ldz, A, lda, a_is_bf16, B, B, Cn, sums.ctypes.data, s)
+
+    def bn_fwd_stats(self, Z, ldz, B, Cn, sums, scratch, s):
+        out = _arr(sums, 2 * Cn, np.float64)
+        if B == 0:
+            out[...] = 0
+            return 0
+        z64 = _mat(Z, B, Cn, ldz).astype(np.float64)
+        out[:Cn] = z64.sum(0)
+        out[Cn:] = (z64 * z64).sum(0)
+        return 0
+
+    def bn_fwd_apply(self, ref, Z, ldz, A, lda, a_is_bf16, B, n_total, Cn, sums, s):
         p = _obj(ref)
         if p.drop_p > 0:
             raise NotImplementedError("the emulator does not reproduce the dropout hash; test with dropout=0")
-        z = _mat(Z, B, Cn, ldz)
         gam = _arr(p.gamma, Cn, np.float32).copy()
         bet = _arr(p.beta, Cn, np.float32).copy()
         if p.gamma2:
@@ -332,53 +349,85 @@ class HostABI:
             bet = bet + _arr(p.beta2, Cn, np.float32)
         sm, si = _arr(p.save_mean, Cn, np.float32), _arr(p.save_invstd, Cn, np.float32)
         if p.train:
-            z64 = z.astype(np.float64)
-            mean = z64.mean(0)
-            var = np.maximum((z64 * z64).mean(0) - mean * mean, 0)
+            sums = _arr(sums, 2 * Cn, np.float64)
+            mean = sums[:Cn] / n_total
+            var = np.maximum(sums[Cn:] / n_total - mean * mean, 0)
             sm[...] = mean
             si[...] = 1.0 / np.sqrt(var + BN_EPS)
             if p.running_mean:
                 rm, rv = _arr(p.running_mean, Cn, np.float32), _arr(p.running_var, Cn, np.float32)
-                unb = var * (B / (B - 1)) if B > 1 else var
+                unb = var * (n_total / (n_total - 1)) if n_total > 1 else var
                 rm[...] = F32(1 - BN_MOM) * rm + F32(BN_MOM) * mean.astype(np.float32)
                 rv[...] = F32(1 - BN_MOM) * rv + F32(BN_MOM) * unb.astype(np.float32)
         else:
             sm[...] = _arr(p.running_mean, Cn, np.float32)
             si[...] = F32(1.0) / np.sqrt(_arr(p.running_var, Cn, np.float32) + F32(BN_EPS))
+        if B == 0:
+            return 0
+        z = _mat(Z, B, Cn, ldz)
         v = (z - sm) * si * gam + bet
         if p.relu:
             v = np.maximum(v, F32(0))
         _wr(_act_mat(A, B, Cn, lda, a_is_bf16), v.astype(np.float32), a_is_bf16)
         return 0
 
-    def bn_bwd(self, ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, da_is_bf16, dZ, lddz, dz_is_bf16, dgamma, dbeta, accumulate, B, Cn, scratch, s):
-        p = _obj(ref)
-        z = _mat(Z, B, Cn, ldz)
+    def _bn_dy(self, p, A, lda, a_is_bf16, dA, ldda, da_is_bf16, B, Cn):
         dy = _rd(_act_mat(dA, B, Cn, ldda, da_is_bf16), da_is_bf16).astype(np.float32)
         if p.relu:
             a = _rd(_act_mat(A, B, Cn, lda, a_is_bf16), a_is_bf16)
             keep = F32(1.0 / (1.0 - p.drop_p)) if p.drop_p > 0 else F32(1)
             dy = np.where(a > 0, dy * keep, F32(0))
-        gam = _arr(p.gamma, Cn, np.float32).copy()
-        if p.gamma2:
-            gam = gam * _arr(p.gamma2, Cn, np.float32)
-        sm, si = _arr(p.save_mean, Cn, np.float32), _arr(p.save_invstd, Cn, np.float32)
-        xh = (z - sm) * si
-        s0 = dy.astype(np.float64).sum(0).astype(np.float32)
-        s1 = (dy.astype(np.float64) * xh).sum(0).astype(np.float32)
+        return dy
+
+    def bn_bwd_stats(self, ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, da_is_bf16, dgamma, dbeta, accumulate, B, Cn, sums, scratch, s):
+        p = _obj(ref)
+        out = _arr(sums, 2 * Cn, np.float64)
+        if B == 0:
+            out[...] = 0
+            s0 = s1 = np.zeros(Cn, np.float32)
+        else:
+            z = _mat(Z, B, Cn, ldz)
+            dy = self._bn_dy(p, A, lda, a_is_bf16, dA, ldda, da_is_bf16, B, Cn)
+            sm, si = _arr(p.save_mean, Cn, np.float32), _arr(p.save_invstd, Cn, np.float32)
+            xh = (z - sm) * si
+            out[:Cn] = dy.astype(np.float64).sum(0)
+            out[Cn:] = (dy.astype(np.float64) * xh).sum(0)
+            s0, s1 = out[:Cn].astype(np.float32), out[Cn:].astype(np.float32)
         if dgamma:
             dg = _arr(dgamma, Cn, np.float32)
             dg[...] = dg + s1 if accumulate else s1
         if dbeta:
             db = _arr(dbeta, Cn, np.float32)
             db[...] = db + s0 if accumulate else s0
+        return 0
+
+    def bn_bwd_apply(self, ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, da_is_bf16, dZ, lddz, dz_is_bf16, B, n_total, Cn, sums, scratch, s):
+        p = _obj(ref)
+        if B == 0 or Cn == 0:
+            return 0
+        z = _mat(Z, B, Cn, ldz)
+        dy = self._bn_dy(p, A, lda, a_is_bf16, dA, ldda, da_is_bf16, B, Cn)
+        gam = _arr(p.gamma, Cn, np.float32).copy()
+        if p.gamma2:
+            gam = gam * _arr(p.gamma2, Cn, np.float32)
+        sm, si = _arr(p.save_mean, Cn, np.float32), _arr(p.save_invstd, Cn, np.float32)
+        sums = _arr(sums, 2 * Cn, np.float64)
+        s0, s1 = sums[:Cn].astype(np.float32), sums[Cn:].astype(np.float32)
         if p.train:
-            inv_n = F32(1.0 / B)
+            xh = (z - sm) * si
+            inv_n = F32(1.0 / n_total)
             dz = gam * si * (dy - s0 * inv_n - xh * s1 * inv_n)
         else:
             dz = dy * gam * si
         _wr(_act_mat(dZ, B, Cn, lddz, dz_is_bf16), dz.astype(np.float32), dz_is_bf16)
         return 0
+
+    def bn_bwd(self, ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, da_is_bf16, dZ, lddz, dz_is_bf16, dgamma, dbeta, accumulate, B, Cn, scratch, s):
+        if B == 0 or Cn == 0:
+            return 0
+        sums = np.zeros(2 * Cn, dtype=np.float64)
+        self.bn_bwd_stats(ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, da_is_bf16, dgamma, dbeta, accumulate, B, Cn, sums.ctypes.data, scratch, s)
+        return self.bn_bwd_apply(ref, Z, ldz, A, lda, a_is_bf16, dA, ldda, da_is_bf16, dZ, lddz, dz_is_bf16, B, B, Cn, sums.ctypes.data, scratch, s)
 
     # ------------------------------------------------------------------ Linear(d, 1) heads (layer.py:192-193)
     def rowdot_fwd(self, A, lda, a_is_bf16, w, bias, out, ldo, B, G, d, s):
@@ -610,7 +659,7 @@ class HostABI:
     def permute_rows(self, src, lds, perm, n, cols, elt_bytes, dst, ldd, scatter, s):
         dt = {2: np.uint16, 4: np.uint32, 8: np.uint64}[elt_bytes]
         S, Dm = _mat(src, 1, 1, lds, 1, dt), _mat(dst, 1, 1, ldd, 1, dt)
-        pm = _arr(perm, n, np.int32)[:n].astype(np.int64)
+        pm = _arr(perm, n, np.int32)[:n].astype(np.int64) if perm else np.arange(n, dtype=np.int64)
         sz = np.dtype(dt).itemsize
         rows_src = int(pm.max()) + 1 if (n and not scatter) else n
         rows_dst = int(pm.max()) + 1 if (n and scatter) else n

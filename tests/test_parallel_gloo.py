@@ -1,0 +1,133 @@
+"""Data-parallel replicas + row-sharded embedding table on CPU: world_size 2 over gloo, the CUDA library
+replaced by the host-memory emulator of its C-ABI.  Two ranks with B/2 rows each must reproduce what ONE process
+computes on the concatenated B-row batch - the reference is a single-device program, so that is the parity statement:
+global-batch BatchNorm statistics, global-mean loss, summed dense gradients, owner-side embedding update."""
+import os
+import socket
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cdcmdr_b200 as cm
+from oracle.host_abi import HostABI
+from tests.test_oracle_golden import bias_before_bn
+
+
+class Cfg:
+    use_atten = False; use_dcn = False; ple_n_expert_specific = 2; ple_n_expert_shared = 1; mmoe_n_expert = 3
+    cdcmdr_precision = "fp32"
+
+
+F, E, T, ND, DOM = 7, 4, 3, 6, 3
+FD = np.array([11, 7, 13, ND, 9, 5, 8], dtype=np.int64)
+L2 = dict(l2_reg_embedding=1e-3, l2_reg_linear=1e-3, l2_reg_dnn=1e-3)
+ADAM = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+
+
+def _build(kind, precision="fp32"):
+    torch.manual_seed(5)
+    cfg = Cfg(); cfg.cdcmdr_precision = precision
+    if kind == "ple":
+        return cm.PLE(FD, E, T, 2, 1, ((16, 8), (8,)), (8, 8), dropout=0.0, config=cfg, **L2)
+    if kind == "mmoe":
+        return cm.MMoE(FD, E, T, 3, (16, 8), (8, 8), dropout=0.0, config=cfg, **L2)
+    m = cm.CDC(FD, E, T, ND, "ple", ((16, 8), (8,)), (8, 8), DOM, dropout=0.0, config=cfg, **L2)
+    m.set_groups([d % T for d in range(ND)])
+    return m
+
+
+def _data(B):
+    rng = np.random.default_rng(3)
+    x = np.stack([rng.integers(0, d, size=B) for d in FD], axis=1).astype(np.int32)
+    y = (rng.random(B) < 0.3).astype(np.int16)
+    g = rng.integers(0, T, size=B).astype(np.int64)
+    return x, y, g
+
+
+def _steps(model, kind, x, y, g, n):
+    opt = cm.Adam(model.parameters(), **ADAM)
+    model.train()
+    outs = []
+    for _ in range(n):
+        xt, yt, gt = torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(g)
+        if kind == "cdc":
+            out = model.train_step(xt, yt, opt, mode="split", domain_i=None)
+        else:
+            out = model.train_step(xt, yt, opt, mode="gather", sel=gt)
+        outs.append((out["pred"].clone().numpy(), model.step_losses(out)))
+    return outs
+
+
+def _worker(rank, world, port, kind, B, n_steps, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cm._lib.install(HostABI())
+        model = _build(kind)
+        dp = cm.parallel.attach_data_parallel(model)
+        x, y, g = _data(B)
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        outs = _steps(model, kind, x[lo:hi], y[lo:hi], g[lo:hi], n_steps)
+        dp.gather_table()
+        sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        np.savez(os.path.join(path, f"rank{rank}.npz"), **sd,
+                 **{f"pred{i}": o[0] for i, o in enumerate(outs)}, **{f"loss{i}": np.array(o[1]) for i, o in enumerate(outs)})
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("kind", ["ple", "mmoe", "cdc"])
+def test_two_ranks_match_one_process(kind):
+    B, n_steps, world = 96, 3, 2
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker, args=(world, _free_port(), kind, B, n_steps, tmp), nprocs=world, join=True)
+        ranks = [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
+    old = cm._lib._LIB
+    cm._lib.install(HostABI())
+    try:
+        model = _build(kind)
+        x, y, g = _data(B)
+        ref = _steps(model, kind, x, y, g, n_steps)
+        sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    finally:
+        cm._lib.install(old)
+    for i in range(n_steps):
+        pred = np.concatenate([ranks[r][f"pred{i}"] for r in range(world)], axis=0)
+        assert np.abs(pred - ref[i][0]).max() <= 2e-6, (i, float(np.abs(pred - ref[i][0]).max()))
+        for r in range(world):
+            assert np.allclose(ranks[r][f"loss{i}"], np.array(ref[i][1]), rtol=1e-5, atol=1e-7), (i, r)
+    for k, v in sd.items():
+        for r in range(world):
+            got = ranks[r][k]
+            if k.endswith("num_batches_tracked"):
+                assert int(got) == int(v)
+                continue
+            # replicas are identical to each other bit for bit, and equal to the single process up to summation order
+            assert np.array_equal(got, ranks[0][k]), k
+            kk = k[len("base_model_instance."):] if k.startswith("base_model_instance.") else k
+            if bias_before_bn("mmoe" if kind == "mmoe" else "ple", kk) or kk.endswith("running_mean"):   # running_mean tracks that bias
+                # the true gradient of a Linear bias in front of train-mode BatchNorm is 0: Adam turns its rounding noise
+                # into +-lr steps whose sign depends on the summation order (in the reference as much as here)
+                assert np.abs(got - v).max() <= 2.1e-3 * n_steps, k
+                continue
+            assert np.abs(got - v).max() <= 2e-5 * max(1.0, float(np.abs(v).max())), (k, float(np.abs(got - v).max()))
+
+
+def test_field_split_covers_every_field_once():
+    for n_fields in (1, 5, 23, 26):
+        for world in (1, 2, 4, 8):
+            rg = cm.parallel.split_fields(n_fields, world)
+            assert len(rg) == world and rg[0][0] == 0 and rg[-1][1] == n_fields
+            assert all(rg[i][1] == rg[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in rg]
+            assert max(sizes) - min(sizes) <= 1
