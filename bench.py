@@ -41,10 +41,12 @@ def field_dims():
     return fd
 
 
-def make_batches(n_batches, B, seed):
+def make_batches(n_batches, B, seed, rank=0):
     """Ali-CCP-shaped: Zipf(1.05) ids per field, each batch holds ONE domain (run.py:499-526 per-domain loaders),
-    domains drawn from a power law, labels Bernoulli(0.05)."""
-    rng = np.random.default_rng(seed)
+    domains drawn from a power law, labels Bernoulli(0.05).  Data-parallel ranks hold different rows of the SAME step's
+    domain batch, so the domain sequence comes from the shared seed and everything else from (seed, rank)."""
+    drng = np.random.default_rng(seed)
+    rng = np.random.default_rng([seed, rank])
     fd = field_dims()
     pw = 1.0 / np.arange(1, N_DOMAIN + 1) ** 1.2
     pw /= pw.sum()
@@ -55,7 +57,7 @@ def make_batches(n_batches, B, seed):
             if f == DOMAIN_IDX:
                 continue
             x[:, f] = np.minimum(rng.zipf(1.05, size=B) - 1, fd[f] - 1).astype(np.int32)
-        d = int(rng.choice(N_DOMAIN, p=pw))
+        d = int(drng.choice(N_DOMAIN, p=pw))
         x[:, DOMAIN_IDX] = d
         y = (rng.random(B) < 0.05).astype(np.int16)
         out.append((x, y, d))
@@ -198,7 +200,7 @@ def reference_arm(args):
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
                              "sample": f"{args.steps} steps of batch {B_sample} of the same workload (numpy oracle port, dropout {DROPOUT})"},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, B):
@@ -218,8 +220,9 @@ def ours_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
+        import datetime
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     B = args.batch
@@ -235,7 +238,7 @@ def ours_arm(args):
         cm.parallel.attach_data_parallel(base, dist.group.WORLD)
     opt = cm.Adam(model.parameters(), **ADAM)
     nb = 8
-    batches = make_batches(nb, B, SEED + 1 + rank)
+    batches = make_batches(nb, B, SEED + 1, rank)
     dev_batches = [(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), d) for x, y, d in batches]
     pin_batches = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(), d) for x, y, d in batches]
     # one CUDA graph per cluster column (the selected tower is a kernel argument), sharing the static input buffers
@@ -308,8 +311,17 @@ def ours_arm(args):
         ms_e2e = max(ms_e2e, wall_e2e)
     roof = dominant_kernel_roofline(base, B, torch) if rank == 0 else None
     emb = embedding_bandwidth(base, dev_batches[0][0], B, torch) if rank == 0 else None
+    if world > 1:
+        # tear-down of a process group while CUDA graphs that recorded its collectives are alive hangs (seen on 2 x B200):
+        # drop the graphs, meet once more, and leave without the group destructor
+        steps_by_col.clear()
+        proto = g = None
+        import gc
+        gc.collect()
+        barrier()
     if rank != 0:
-        return
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     value = B * world * args.steps / (ms * 1e-3)
     cpu = None
@@ -330,9 +342,10 @@ def ours_arm(args):
             "roofline": roof, "embedding": emb, "cpu_baseline": cpu, "lib": lib.path}
     if roof is not None and peaks:
         roof["peak_source"] = "MEASURED_PEAKS.json (driver-measured on this pool)"
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 def dominant_kernel_roofline(base, B, torch):
@@ -366,31 +379,49 @@ def embedding_bandwidth(base, x, B, torch):
     """Gather kernel alone: algorithmic bytes F*(4 + E*4 + E*4) per sample."""
     rt = base._rt
     ws = rt.ws(B)
+    table = base.embedding.embedding_dict.weight
+    X = ws.mat("probe.X", B, F * E, rt.act_dtype)
+
+    def gather():                                     # the gather kernel alone (no exchange), on this rank's memory
+        rt.ops.embed_gather(x, base.embedding.offsets_dev, table, None if rt.bf16 else X, X if rt.bf16 else None, B, F, E, table.shape[0])
     for _ in range(3):
-        base._gather(ws, x, B)
+        gather()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n = 20
     e0.record()
     for _ in range(n):
-        base._gather(ws, x, B)
+        gather()
     e1.record()
     torch.cuda.synchronize()
     sec = e0.elapsed_time(e1) * 1e-3 / n
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
-    gbs = B * F * (4 + E * 4 + E * 4) / sec / 1e9
+    gbs = B * F * (4 + E * 4 + E * (2 if rt.bf16 else 4)) / sec / 1e9
     return {"kernel": "embed_gather_fwd", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
             "us_per_launch": sec * 1e6, "note": "Zipf ids: hot rows hit L2, so this can exceed the DRAM copy peak"}
 
 
+_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the ORIGINAL stdout; everything else any library prints to fd 1 (NCCL's version banner,
+    for one) has been redirected to stderr by main()."""
+    _OUT.write(json.dumps(line) + "\n")
+    _OUT.flush()
+
+
 def main():
+    global _OUT
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("CDCMDR_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("CDCMDR_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cpu-batch", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")

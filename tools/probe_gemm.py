@@ -50,6 +50,13 @@ def run(name, M, N, K, a_mn=0, b_mn=0, out="bf16", act=0, drop=0.0, bias=True, m
 
 
 B = 65536
+ONLY = sys.argv[1] if len(sys.argv) > 1 else None
+if ONLY:
+    _run = run
+
+    def run(name, *a, **k):            # noqa: F811
+        if name.startswith(ONLY):
+            _run(name, *a, **k)
 run("l0_fwd_plain", B, 2560, 368, bias=False)
 run("l0_fwd_bias", B, 2560, 368)
 run("l0_fwd_bias_relu", B, 2560, 368, act=1)
@@ -86,6 +93,7 @@ def colsum_probe(Bn, Cn, bf16=True):
     print(json.dumps(dict(name=f"colsum {Bn}x{Cn} {'bf16' if bf16 else 'f32'}", us=round(us, 1), gbs=round(X.numel() * X.element_size() / us / 1e3, 1), relerr=err)), flush=True)
 
 
-colsum_probe(B, 2560)
-colsum_probe(B, 1280)
-colsum_probe(B, 640, bf16=False)
+if not ONLY:
+    colsum_probe(B, 2560)
+    colsum_probe(B, 1280)
+    colsum_probe(B, 640, bf16=False)
