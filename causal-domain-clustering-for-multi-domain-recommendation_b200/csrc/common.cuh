@@ -75,6 +75,21 @@ __host__ __device__ __forceinline__ uint32_t drop_thr16(float p) {
 __host__ __device__ __forceinline__ bool drop_keep(uint32_t s0, uint32_t thr16, uint32_t row, uint32_t col) {
   return ((drop_hash_pair(s0, row, col >> 1) >> ((col & 1u) * 16u)) & 0xFFFFu) >= thr16;
 }
+// The tensor-core GEMM epilogue's generator (3 instructions per element): one mixed 32-bit seed per (row, 32-column block),
+// then a 32-bit LCG step per column; element kept iff state >= p * 2^32.
+constexpr uint32_t kLcgA = 1664525u, kLcgC = 1013904223u;
+__host__ __device__ __forceinline__ uint32_t drop_lcg_seed(uint32_t s0, uint32_t row, uint32_t colblock32) {
+  return drop_mix32(row * kDropRowMul + colblock32 * kDropColMul + s0);
+}
+__host__ __device__ __forceinline__ uint32_t drop_thr32(float p) {
+  const double t = (double)p * 4294967296.0;
+  return t >= 4294967295.0 ? 0xFFFFFFFFu : (t <= 0.0 ? 0u : (uint32_t)t);
+}
+__host__ __device__ __forceinline__ bool drop_keep_lcg(uint32_t s0, uint32_t thr32, uint32_t row, uint32_t col) {
+  uint32_t x = drop_lcg_seed(s0, row, col >> 5);
+  for (uint32_t j = 0; j <= (col & 31u); ++j) x = x * kLcgA + kLcgC;
+  return x >= thr32;
+}
 
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(((uint32_t)h) << 16); }
 __device__ __forceinline__ uint16_t f32_to_bf16(float f) {
@@ -82,7 +97,8 @@ __device__ __forceinline__ uint16_t f32_to_bf16(float f) {
   return *reinterpret_cast<uint16_t*>(&b);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  return (uint32_t)f32_to_bf16(lo) | ((uint32_t)f32_to_bf16(hi) << 16);
+  const __nv_bfloat162 b = __floats2bfloat162_rn(lo, hi);       // one cvt.rn.bf16x2.f32: .x (low half) = lo, .y = hi
+  return *reinterpret_cast<const uint32_t*>(&b);
 }
 
 template <typename T> __device__ __forceinline__ float ld_act(const T* p);

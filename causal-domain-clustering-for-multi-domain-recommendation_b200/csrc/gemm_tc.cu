@@ -132,17 +132,31 @@ struct TcParams {
 
 // Epilogue math for 32 consecutive columns [col0, col0+32) of one row; f in/out.  Returns packed bf16 pairs in o[16].
 struct EpiCtx {
-  int act; float mask_scale; bool has_mask, has_drop, has_old; uint32_t s0, thr16; float keep_scale;
+  int act; float mask_scale; bool has_mask, has_drop, has_old; uint32_t s0, thr32; float keep_scale;
 };
 
 __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], const float* bias_s /* smem, 32 floats, or null */,
                                            const uint4* mask_row /* 4 x uint4 = 32 bf16, or null */,
                                            const uint4* old_row /* previous output values (accumulate), 32 bf16 */, uint32_t row,
                                            uint32_t col0, uint32_t (&o)[16]) {
+  // with dropout the keep scale s = 1/(1-p) > 0 is folded into the accumulator: relu((acc + b)) * s == relu(acc*s + b*s);
+  // the bias tile in shared memory is pre-multiplied by s (see the tile prologue)
   if (bias_s) {
     const float4* b4 = reinterpret_cast<const float4*>(bias_s);
+    if (c.has_drop) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { const float4 b = b4[j]; f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w; }
+      for (int j = 0; j < 8; ++j) {
+        const float4 b = b4[j];
+        f[4 * j] = fmaf(f[4 * j], c.keep_scale, b.x); f[4 * j + 1] = fmaf(f[4 * j + 1], c.keep_scale, b.y);
+        f[4 * j + 2] = fmaf(f[4 * j + 2], c.keep_scale, b.z); f[4 * j + 3] = fmaf(f[4 * j + 3], c.keep_scale, b.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float4 b = b4[j]; f[4 * j] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w; }
+    }
+  } else if (c.has_drop) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] *= c.keep_scale;
   }
   if (c.act == 1) {
 #pragma unroll
@@ -163,13 +177,11 @@ __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], cons
     }
   }
   if (c.has_drop) {
-    uint32_t x = row * kDropRowMul + (col0 >> 1) * kDropColMul + c.s0;
+    uint32_t x = drop_lcg_seed(c.s0, row, col0 >> 5);
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t h = drop_mix32(x);
-      x += kDropColMul;
-      f[2 * j] = (h & 0xFFFFu) >= c.thr16 ? f[2 * j] * c.keep_scale : 0.f;
-      f[2 * j + 1] = (h >> 16) >= c.thr16 ? f[2 * j + 1] * c.keep_scale : 0.f;
+    for (int j = 0; j < 32; ++j) {
+      x = x * kLcgA + kLcgC;
+      f[j] = x >= c.thr32 ? f[j] : 0.f;
     }
   }
   if (c.has_old) {
@@ -293,7 +305,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     EpiCtx ec;
     ec.act = p.act; ec.mask_scale = p.mask_scale; ec.has_mask = p.mask != nullptr; ec.has_drop = p.drop_p > 0.f;
     ec.has_old = p.accumulate != 0;
-    ec.thr16 = drop_thr16(p.drop_p);
+    ec.thr32 = drop_thr32(p.drop_p);
     ec.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     ec.s0 = p.drop_p > 0.f ? drop_s0(*p.seed_dev, p.salt) : 0u;
     const int n_chunks = (p.block_n + 63) >> 6;
@@ -308,7 +320,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       float* bias_t = bias_s + acc * TC_MAX_N;
       const bool use_bias = p.bias != nullptr && z == 0;
       if (use_bias) {
-        if (et < p.block_n) bias_t[et] = (n0 + et < p.N) ? __ldg(p.bias + g * p.bias_gs + n0 + et) : 0.f;
+        // columns that take the dropout fold (bf16 main part) hold bias * keep_scale; aux columns (fp32, no dropout) the plain bias
+        if (et < p.block_n) {
+          float bv = (n0 + et < p.N) ? __ldg(p.bias + g * p.bias_gs + n0 + et) : 0.f;
+          if (ec.has_drop && n0 + et < p.n_main) bv *= ec.keep_scale;
+          bias_t[et] = bv;
+        }
       }
       epi_bar_sync();                                    // bias tile visible; also keeps the 8 warps within one tile of each other
       mbar_wait(tfull0 + 8 * acc, acc_phase);
@@ -388,12 +405,16 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            // columns [nbb, nbb+ncols): main part (bf16) below n_main, aux part (fp32) at/after n_main
+            const int n_mainc = (int)max((int64_t)0, min((int64_t)ncols, p.n_main - nbb));
+            if (ec.has_drop) {                           // same fold as the fast path: main columns carry the keep scale
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] *= ec.keep_scale;
+            }
             if (use_bias) {
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] += bias_t[c0 + s0c + j];
             }
-            // columns [nbb, nbb+ncols): main part (bf16) below n_main, aux part (fp32) at/after n_main
-            const int n_mainc = (int)max((int64_t)0, min((int64_t)ncols, p.n_main - nbb));
             if (n_mainc > 0) {
               if (p.act == 1) {
 #pragma unroll
@@ -408,7 +429,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               if (ec.has_drop) {
                 const uint32_t gcol = (uint32_t)(g * p.main_gn + nbb);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = drop_keep(ec.s0, ec.thr16, (uint32_t)m, gcol + j) ? f[j] * ec.keep_scale : 0.f;
+                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = drop_keep_lcg(ec.s0, ec.thr32, (uint32_t)m, gcol + j) ? f[j] : 0.f;
               }
               if (p.accumulate) {
 #pragma unroll

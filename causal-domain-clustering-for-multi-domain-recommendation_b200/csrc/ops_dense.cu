@@ -83,7 +83,7 @@ gate_mix_fwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
   __shared__ int s_col[32], s_n[32], s_sel[1024];
   const int np = d.n_gates * d.max_sel;
   for (int i = threadIdx.x; i < d.n_gates; i += blockDim.x) { s_col[i] = d.gate_col[i]; s_n[i] = d.gate_n[i]; }
-  for (int i = threadIdx.x; i < np; i += blockDim.x) s_sel[i] = d.gate_sel[i];
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s_sel[i] = d.gate_sel[i] * d.h;      // element offset of the expert's block
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sp = dyn + warp * np;
@@ -114,12 +114,12 @@ gate_mix_fwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
         const int n = s_n[j];
         for (int s = 0; s < n; ++s) {
           float hv[VEC];
-          VecIO<T, VEC>::load(Hrow + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
+          VecIO<T, VEC>::load(Hrow + s_sel[j * d.max_sel + s] + c, hv);
           const float p = sp[j * d.max_sel + s];
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc[q] = fmaf(p, hv[q], acc[q]);
         }
-        VecIO<T, VEC>::store(out + row * ldo + (int64_t)j * d.h + c, acc);
+        VecIO<T, VEC>::store(out + row * ldo + j * d.h + c, acc);
       }
     }
     __syncwarp();
@@ -132,7 +132,7 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
                     const T* __restrict__ dOut, int64_t ldo, T* __restrict__ dH, int64_t lddh, float relu_scale,
                     float* __restrict__ dlogits, int64_t lddl, int64_t B, int stage_off) {
   extern __shared__ __align__(16) float dyn[];
-  __shared__ int s_col[32], s_n[32], s_sel[1024], s_inv_cnt[64], s_inv[64 * 32];
+  __shared__ int s_col[32], s_n[32], s_sel[1024], s_inv_cnt[64], s_inv[64 * 32], s_inv_o[64 * 32];
   const int np = d.n_gates * d.max_sel;
   for (int i = threadIdx.x; i < d.n_gates; i += blockDim.x) { s_col[i] = d.gate_col[i]; s_n[i] = d.gate_n[i]; }
   for (int i = threadIdx.x; i < np; i += blockDim.x) s_sel[i] = d.gate_sel[i];
@@ -141,9 +141,11 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
     int cnt = 0;
     for (int j = 0; j < d.n_gates; ++j)
       for (int s = 0; s < s_n[j]; ++s)
-        if (s_sel[j * d.max_sel + s] == (int)threadIdx.x) s_inv[threadIdx.x * 32 + cnt++] = j * d.max_sel + s;
+        if (s_sel[j * d.max_sel + s] == (int)threadIdx.x) { s_inv[threadIdx.x * 32 + cnt] = j * d.max_sel + s; s_inv_o[threadIdx.x * 32 + cnt] = j * d.h; ++cnt; }
     s_inv_cnt[threadIdx.x] = cnt;
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < np; i += blockDim.x) s_sel[i] *= d.h;                     // element offset of the expert's block
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* sp = dyn + (warp * 2) * np;
@@ -166,8 +168,8 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
         float part = 0.f;
         for (int c = lane * VEC; c < d.h; c += 32 * VEC) {
           float dv[VEC], hv[VEC];
-          VecIO<T, VEC>::load(Orow + (int64_t)j * d.h + c, dv);
-          VecIO<T, VEC>::load(Hrow + (int64_t)s_sel[j * d.max_sel + s] * d.h + c, hv);
+          VecIO<T, VEC>::load(Orow + j * d.h + c, dv);
+          VecIO<T, VEC>::load(Hrow + s_sel[j * d.max_sel + s] + c, hv);
 #pragma unroll
           for (int q = 0; q < VEC; ++q) part = fmaf(dv[q], hv[q], part);
         }
@@ -192,18 +194,18 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
         for (int i = 0; i < cnt; ++i) {
           const int k = s_inv[e * 32 + i];
           float dv[VEC];
-          VecIO<T, VEC>::load(Orow + (int64_t)(k / d.max_sel) * d.h + c, dv);
+          VecIO<T, VEC>::load(Orow + s_inv_o[e * 32 + i] + c, dv);
           const float p = sp[k];
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc[q] = fmaf(p, dv[q], acc[q]);
         }
         if (relu_scale > 0.f) {
           float hv[VEC];
-          VecIO<T, VEC>::load(Hrow + (int64_t)e * d.h + c, hv);
+          VecIO<T, VEC>::load(Hrow + e * d.h + c, hv);
 #pragma unroll
           for (int q = 0; q < VEC; ++q) acc[q] = hv[q] > 0.f ? acc[q] * relu_scale : 0.f;
         }
-        VecIO<T, VEC>::store(dH + row * lddh + (int64_t)e * d.h + c, acc);
+        VecIO<T, VEC>::store(dH + row * lddh + e * d.h + c, acc);
       }
     }
     __syncwarp();

@@ -114,3 +114,42 @@ def test_transpose_bf16():
         return [dst]
     cpu, gpu = Env().run(fn)
     assert np.array_equal(cpu[0], gpu[0])
+
+
+@pytest.mark.parametrize("ld_pad", [0, 4])
+def test_gemm_bf16_tc_dropout_statistics(ld_pad):
+    """nn.Dropout(p) in the epilogue (layer.py:189): with A = 0 and bias = 1 the output is exactly keep/(1-p): the keep rate must be
+    1-p within sampling error, kept entries are scaled by 1/(1-p), the mask is a function of (seed, salt) only (bit-repeatable),
+    changes with the salt, and has no row/column structure.  ld_pad=4 forces the non-TMA store path (pitch not 16-byte aligned)."""
+    lib = cm._lib.load()
+    dev = torch.device("cuda")
+    M, N, K, p = 4096, 512, 64, 0.2
+    A = torch.zeros(M, K, dtype=torch.bfloat16, device=dev)
+    Bt = torch.zeros(N, K, dtype=torch.bfloat16, device=dev)
+    bias = torch.ones(N, device=dev)
+    st = torch.zeros(48, dtype=torch.uint8, device=dev)
+    lib.step_state_init(st.data_ptr(), 3, 0)
+    lib.step_tick(st.data_ptr(), 1e-3, 0.9, 0.99, 1e-8, 0.0, 2000, 0)
+    ld = N + ld_pad
+
+    def run(salt):
+        out = torch.full((M, ld), -7.0, dtype=torch.bfloat16, device=dev)
+        d = L.GemmBf16(A.data_ptr(), K, M, K, Bt.data_ptr(), K, N, K, M, N, K, 1, 0, 0, 0, 0, 0, 0, bias.data_ptr(), 0, N,
+                       out.data_ptr(), ld, 0, None, 0, 0, 1, None, 0, 0, 1.0, p, st.data_ptr() + 8, salt, 0, 1, 0, 0)
+        lib.gemm_bf16_tc(C.byref(d), 0)
+        torch.cuda.synchronize()
+        return out.float().cpu().numpy()
+    a, b, c = run(5), run(5), run(6)
+    assert np.array_equal(a, b)
+    if ld_pad:
+        assert (a[:, N:] == -7.0).all()                       # padding columns untouched
+    a, c = a[:, :N], c[:, :N]
+    assert set(np.unique(a).tolist()) == {0.0, 1.25}
+    keep = (a > 0)
+    assert abs(keep.mean() - (1 - p)) < 4e-3, keep.mean()
+    assert abs((c > 0).mean() - (1 - p)) < 4e-3
+    assert 0.25 < (keep != (c > 0)).mean() < 0.40              # independent masks differ on 2p(1-p) = 32% of the entries
+    assert np.abs(keep.mean(0) - (1 - p)).max() < 0.04 and np.abs(keep.mean(1) - (1 - p)).max() < 0.09
+    # neighbouring columns / rows are uncorrelated
+    k = keep.astype(np.float64) - keep.mean()
+    assert abs((k[:, 1:] * k[:, :-1]).mean()) < 2e-3 and abs((k[1:] * k[:-1]).mean()) < 2e-3
