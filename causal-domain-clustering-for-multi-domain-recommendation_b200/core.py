@@ -310,6 +310,36 @@ class Ops:
         sc = self.scratch("colsum", self.lib.colsum_scratch_bytes(Cn))
         self.lib.colsum(X.ptr, X.ld, 1 if X.is_bf16 else 0, B, Cn, out_addr, accumulate, sc.data_ptr(), self.stream)
 
+    # ---------------------------------------------------------------- cross networks / small elementwise stages (fp32)
+    def cross_fuse_fwd(self, x0: Mat, x: Mat, xw: Mat, xw_cols, b_addr, out: Mat, B, D):
+        """out = x0 * xw + b + x over dense [B, D] blocks (every Mat here has ld == D; xw has ld == xw_cols)"""
+        self.lib.cross_fuse_fwd(x0.ptr, x.ptr, xw.ptr, xw_cols, b_addr, out.ptr, B, D, self.stream)
+
+    def cross_fuse_bwd(self, x0: Mat, xw: Mat, xw_cols, dout: Mat, dx0_acc: Mat, dxw: Mat, B, D):
+        self.lib.cross_fuse_bwd(x0.ptr, xw.ptr, xw_cols, dout.ptr, dx0_acc.ptr, dxw.ptr, B, D, self.stream)
+
+    def crossmix_combine_fwd(self, x0: Mat, x: Mat, u, g, bias_addr, out: Mat, B, D, n_exp):
+        self.lib.crossmix_combine_fwd(x0.ptr, x.ptr, u.data_ptr(), g.data_ptr(), bias_addr, out.ptr, B, D, n_exp, self.stream)
+
+    def crossmix_combine_bwd(self, x0: Mat, u, g, bias_addr, dout: Mat, du, dgate, dx0_acc: Mat, B, D, n_exp):
+        self.lib.crossmix_combine_bwd(x0.ptr, u.data_ptr(), g.data_ptr(), bias_addr, dout.ptr, du.data_ptr(), dgate.data_ptr(),
+                                      dx0_acc.ptr, B, D, n_exp, self.stream)
+
+    def tanh_fwd(self, t, n):
+        self.lib.tanh_fwd(t.data_ptr(), n, self.stream)
+
+    def tanh_bwd(self, y, dy, n):
+        self.lib.tanh_bwd(y.data_ptr(), dy.data_ptr(), n, self.stream)
+
+    def softmax_rows_fwd(self, z, ldz, p, ldp, B, n):
+        self.lib.softmax_rows_fwd(z.data_ptr(), ldz, p.data_ptr(), ldp, B, n, self.stream)
+
+    def softmax_rows_bwd(self, p, ldp, dp, lddp, dz, lddz, B, n):
+        self.lib.softmax_rows_bwd(p.data_ptr(), ldp, dp.data_ptr(), lddp, dz.data_ptr(), lddz, B, n, self.stream)
+
+    def cast_bf16_f32(self, src: Mat, dst: Mat, rows, cols, accumulate=False):
+        self.lib.cast_bf16_f32(src.ptr, src.ld, dst.ptr, dst.ld, rows, cols, 1 if accumulate else 0, self.stream)
+
     def ewise(self, a, b, out, n, op):
         self.lib.ewise_f32(a, b, out, n, op, self.stream)
 

@@ -102,3 +102,42 @@ def test_bf16_path_host_logic(kind):
     out = model.train_step(xt, yt, opt, mode="gather", sel=gt)
     _, bce, reg = model.step_losses(out)
     assert abs(bce - float(r["bce"])) <= 2e-2 * float(r["bce"]) and abs(reg - float(r["reg"])) <= 1e-4 * float(r["reg"])
+
+
+@pytest.mark.parametrize("structure", ["parallel", "stacked"])
+def test_dcnv2_crossnet_v2_matches_oracle(structure):
+    """DCNv2 with CrossNetV2 (x0 * (W x) + b + x): upstream's constructor crashes for use_low_rank_mixture=False
+    (G9), so there is no model-level fixture; the oracle assembles it from the reference layers (pinned by layer_crossv2.npz)."""
+    from oracle import cdcmdr_oracle as O
+    torch.manual_seed(11)
+    rng = np.random.default_rng(11)
+    fd = np.array([9, 6, 12, 5], dtype=np.int64)
+    E_, B = 4, 200
+    l2 = dict(l2_reg_embedding=1e-3, l2_reg_linear=1e-3, l2_reg_dnn=1e-3, l2_reg_cross=1e-3)
+    model = cm.DCNv2(fd, E_, 3, (16, 8), dropout=0.0, model_structure=structure, use_low_rank_mixture=False, **l2)
+    with torch.no_grad():
+        for l in range(3):
+            model.crossnet.b[l].normal_(0, 0.1)
+    om = O.DCNv2(fd, E_, 3, (16, 8), model_structure=structure, use_low_rank_mixture=False, **l2)
+    sd = {k: v.detach().numpy().astype(np.float64) if v.dtype == torch.float32 else v.detach().numpy().copy()
+          for k, v in model.state_dict().items()}
+    x = np.stack([rng.integers(0, d, size=B) for d in fd], axis=1).astype(np.int32)
+    y = (rng.random(B) < 0.4).astype(np.int16)
+    model.train()
+    opt = cm.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+    oopt = O.Adam()
+    for s in range(2):
+        r = O.train_step(om, sd, oopt, x, y, "single")
+        out = model.train_step(torch.from_numpy(x), torch.from_numpy(y), opt, mode="col", col=0)
+        _, bce, reg = model.step_losses(out)
+        assert np.abs(out["pred"].numpy()[:, 0] - r["pred"]).max() <= 1e-5
+        assert abs(bce - float(r["bce"])) <= 1e-5 and abs(reg - float(r["reg"])) <= 1e-5 * float(r["reg"])
+        cur = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            # zero-true-gradient parameters (Adam turns rounding noise into +-lr steps): Linear biases in front of BatchNorm and,
+            # when stacked, the last cross bias (a constant shift of the MLP input is removed by its first BatchNorm)
+            noisy = bias_before_bn("dcnv2", k) or k.endswith("running_mean") or (structure == "stacked" and k == "crossnet.b.2")
+            tol = 2.1e-3 * (s + 1) if noisy else 2e-5
+            assert np.abs(cur[k] - v).max() <= tol, (s, k, float(np.abs(cur[k] - v).max()))
