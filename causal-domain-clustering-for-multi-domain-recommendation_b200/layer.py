@@ -192,6 +192,8 @@ class BaseModel(nn.Module):
                     rt.params.off[m] = o
                 rt.params.shape[m] = tuple(named[m].shape)
                 o += named[m].numel()
+        for bname, numel in getattr(self, "_extra_blocks", []):        # derived operands (e.g. STAR's W_d*W_s): arena space, not parameters
+            rt.params.add(bname, (numel,))
         for bname, members in self._buffer_blocks:
             off0 = rt.buffers.n
             total = sum(bufs[m].numel() for m in members)
@@ -224,6 +226,9 @@ class BaseModel(nn.Module):
             for m in self._absent_grads():
                 o = rt.params.off[m]
                 rt.present[o:o + named[m].numel()] = 0
+            for bname, numel in getattr(self, "_extra_blocks", []):
+                o = rt.params.off[bname]
+                rt.present[o:o + numel] = 0
         if old is not None:
             rt.dp = old.dp
         if old is not None and old.M is not None:
@@ -296,17 +301,22 @@ class BaseModel(nn.Module):
         rt.refresh_operands()
         X = self._gather(ws, x, B)
         logits, lin = self._program_fwd(ws, X, B, train, **kw)
-        T = self.n_out
-        pred = ws.get("pred", (B, T))
-        rt.ops.sigmoid_select_bce(logits.t, lin, B, T, 3, None, 0, None, pred, None, None, None, None, 0.0)
+        R, T = self._head_shape(B, **kw)
+        pred = ws.get("pred", (R, T))
+        rt.ops.sigmoid_select_bce(logits.t, lin, R, T, 3, None, 0, None, pred, None, None, None, None, 0.0)
         self._fwd_token += 1
-        self._last = dict(ws=ws, x=x, X=X, B=B, train=train, logits=logits, lin=lin, pred=pred, kw=kw)
+        self._last = dict(ws=ws, x=x, X=X, B=B, R=R, T=T, train=train, logits=logits, lin=lin, pred=pred, kw=kw)
         if train:
             self._bump_batches_tracked(B)
-        return self._shape_pred(pred[:B * T].view(B, T), **kw)
+        return self._shape_pred(pred[:R * T].view(R, T), **kw)
 
     def _shape_pred(self, pred, **kw):
         return pred
+
+    def _head_shape(self, B, **kw):
+        """(rows, columns) of the logits the program produced for a B-row batch.  Called after _program_fwd: STAR with row
+        routing produces one column and only the routed rows (star.py:112-114)."""
+        return B, self.n_out
 
     def _bump_batches_tracked(self, B):
         if B == 1:
@@ -321,13 +331,13 @@ class BaseModel(nn.Module):
     def _engine_backward(self, dpred):
         """dpred: gradient w.r.t. the (B, T) predictions.  Returns gradients for (dense parameters..., table)."""
         last = self._last
-        rt, ws, B, T = self._rt, last["ws"], last["B"], self.n_out
+        rt, ws, B, R, T = self._rt, last["ws"], last["B"], last["R"], last["T"]
         if rt.dp is not None:
             raise NotImplementedError("cdcmdr: the autograd path (loss.backward()) is single-device; data-parallel replicas "
                                       "train through model.train_step()")
-        dlogits = ws.get("dlogits", (B, T))
+        dlogits = ws.get("dlogits", (R, T))
         dlin = self._dlin_mat(ws, B)
-        rt.ops.sigmoid_bwd(last["pred"], self._unshape_dpred(dpred, B, T), dlogits, dlin, B, T)
+        rt.ops.sigmoid_bwd(last["pred"], self._unshape_dpred(dpred, R, T), dlogits, dlin, R, T)
         dX = self._program_bwd(ws, last["X"], B, last["train"], Mat(dlogits, 0, T), **last["kw"])
         table = self.embedding.embedding_dict.weight
         V, E, F = table.shape[0], self.embed_dim, self.field_num
@@ -383,9 +393,12 @@ class BaseModel(nn.Module):
         gt = torch.empty_like(table)
         rt.ops.reg_l2_grad(table, None, self._l2_table(), scale, gt, False, table.numel())
         out = []
+        regularised = {n for names, _, l2 in self.regularization_weight if l2 > 0 for n in names}
         for name, p in self._autograd_params():
             if name == "embedding.embedding_dict.weight":
                 out.append(gt)
+            elif name not in regularised:
+                out.append(None)                             # not part of the regulariser: contributes no gradient (layer.py:96-112)
             else:
                 o = rt.params.off[name]
                 out.append(g[o:o + p.numel()].view(p.shape))
@@ -411,7 +424,7 @@ class BaseModel(nn.Module):
             raise RuntimeError("train_step() needs model.train()")
         rt = self._rt
         x = x.contiguous()
-        B, T = x.shape[0], self.n_out
+        B = x.shape[0]
         ws = rt.ws(B)
         optimizer.attach(self)
         rt.ensure_opt_state()
@@ -419,16 +432,19 @@ class BaseModel(nn.Module):
         rt.refresh_operands()
         X = self._gather(ws, x, B)
         logits, lin = self._program_fwd(ws, X, B, True, **kw)
-        pred = ws.get("pred", (B, T))
+        R, T = self._head_shape(B, **kw)                     # R != B only when the program routed rows (STAR with x_group)
+        pred = ws.get("pred", (R, T))
         psel = ws.get("psel", (B,))
         sums = ws.get("loss_sums", (4,), torch.float64)      # [bce_sum, table_sumsq, reg_dense, -]; [0:2] are per-rank partial sums
         dp = rt.dp
-        n_global = dp.global_rows(B) if dp is not None else B
-        dlogits = ws.get("dlogits", (B, T))
+        if dp is not None and R != B:
+            raise NotImplementedError("cdcmdr: row routing is single-device")
+        n_global = dp.global_rows(B) if dp is not None else R
+        dlogits = ws.get("dlogits", (R, T))
         dlin = self._dlin_mat(ws, B)
         y, sel = self._route_targets(ws, y, sel, B, **kw)
-        rt.ops.sigmoid_select_bce(logits.t, lin, B, T, self.SEL_MODES[mode], sel, col, y, pred, psel, sums[0:1], dlogits,
-                                  dlin, 1.0 / n_global)
+        rt.ops.sigmoid_select_bce(logits.t, lin, R, T, self.SEL_MODES[mode], sel, col, y, pred, psel, sums[0:1], dlogits,
+                                  dlin, 1.0 / max(n_global, 1))
         self._fwd_token += 1
         self._last = None
         self._bump_batches_tracked(B)
@@ -455,7 +471,7 @@ class BaseModel(nn.Module):
             rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[1:2], lazy=lazy)
         if dp is not None:
             dp.all_reduce_sum(sums[0:2])                     # BCE sum and table sum-of-squares are per-rank partials
-        return dict(sums=sums, pred=pred[:B * T].view(B, T), psel=psel[:B], B=n_global, l2_table=l2t)
+        return dict(sums=sums, pred=pred[:R * T].view(R, T), psel=psel[:R], B=n_global, l2_table=l2t)
 
     @staticmethod
     def step_losses(out):

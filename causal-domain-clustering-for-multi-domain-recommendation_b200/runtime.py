@@ -218,24 +218,38 @@ class MlpGroup:
     [input_block*in_dim, (input_block+1)*in_dim) of X (one concatenated-N GEMM per entry); None: MLP g reads block g.
     """
 
-    def __init__(self, rt: Runtime, tag, G, in_dim, dims, names, *, bn, out_layer, in_groups):
+    def __init__(self, rt: Runtime, tag, G, in_dim, dims, names, *, bn, out_layer, in_groups, g0=0):
+        """g0: the arena blocks named by `names` hold MORE groups than this object runs; it runs groups g0 .. g0+G-1 of them
+        (STAR runs one tower at a time on that tower's rows, star.py:78-103)."""
         self.rt, self.tag, self.G, self.in_dim, self.dims = rt, tag, G, in_dim, tuple(dims)
-        self.names, self.bn, self.out_layer, self.in_groups = names, bn, out_layer, in_groups
+        self.names, self.bn, self.out_layer, self.in_groups, self.g0 = names, bn, out_layer, in_groups, g0
         self.salts = [rt.next_salt() for _ in dims]
         if rt.bf16 and (in_dim % 8 or any(d % 8 for d in dims)):
             raise ValueError("the bf16 tensor-core path needs every layer width to be a multiple of 8 (TMA alignment)")
+
+    # arena offsets of layer j's blocks, shifted to this object's first group
+    def _k(self, j):
+        return self.in_dim if j == 0 else self.dims[j - 1]
+
+    def _oW(self, j, extra=0):
+        return self.rt.o(self.names["W"][j], self.g0 * self.dims[j] * self._k(j) + extra)
+
+    def _ob(self, j, extra=0):
+        return self.rt.o(self.names["b"][j], self.g0 * self.dims[j] + extra)
+
+    def _vec(self, fn, key, j):
+        return fn(self.names[key][j], self.g0 * self.dims[j])
 
     def _act(self, ws: Workspace, j, B) -> Mat:
         return ws.mat(f"{self.tag}.A{j}", B, self.G * self.dims[j], self.rt.act_dtype)
 
     def _layer0(self, X: Mat, Y: Mat, B, fused_act, drop):
         rt, d, K = self.rt, self.dims[0], self.in_dim
-        W0, b0 = self.names["W"][0], self.names["b"][0]
         if self.in_groups is None:                               # MLP g reads input block g: one grouped launch
-            rt.lin_fwd(X, K, rt.o(W0), d, rt.o(b0), Y, B, G=self.G, x_gs=K, relu=fused_act, drop=drop, salt=self.salts[0])
+            rt.lin_fwd(X, K, self._oW(0), d, self._ob(0), Y, B, G=self.G, x_gs=K, relu=fused_act, drop=drop, salt=self.salts[0])
         else:
             for (blk, e0, e1) in self.in_groups:
-                rt.lin_fwd(X.cols(blk * K), K, rt.o(W0, e0 * d * K), (e1 - e0) * d, rt.o(b0, e0 * d), Y.cols(e0 * d), B,
+                rt.lin_fwd(X.cols(blk * K), K, self._oW(0, e0 * d * K), (e1 - e0) * d, self._ob(0, e0 * d), Y.cols(e0 * d), B,
                            relu=fused_act, drop=drop, salt=self.salts[0] + 7919 * e0)
 
     def fwd_layer0_only(self, ws: Workspace, X: Mat, B):
@@ -255,13 +269,13 @@ class MlpGroup:
             if j == 0:
                 self._layer0(prev, Y, B, fused_act, drop if fused_act else 0.0)
             else:
-                rt.lin_fwd(prev, prev_d, rt.o(self.names["W"][j]), d, rt.o(self.names["b"][j]), Y, B, G=G, x_gs=prev_d,
+                rt.lin_fwd(prev, prev_d, self._oW(j), d, self._ob(j), Y, B, G=G, x_gs=prev_d,
                            relu=fused_act, drop=drop if fused_act else 0.0, salt=self.salts[j])
             if use_bn:
                 A = self._act(ws, j, B)
                 sm = ws.get(f"{self.tag}.bnsave{j}", (2, G * d))
-                desc = rt.ops.bn_desc(rt.w(self.names["gamma"][j]), rt.w(self.names["beta"][j]),
-                                      rt.b(self.names["rmean"][j]), rt.b(self.names["rvar"][j]),
+                desc = rt.ops.bn_desc(self._vec(rt.w, "gamma", j), self._vec(rt.w, "beta", j),
+                                      self._vec(rt.b, "rmean", j), self._vec(rt.b, "rvar", j),
                                       sm.data_ptr(), sm.data_ptr() + 4 * G * d, train, True,
                                       drop_p=drop, seed_ptr=rt.seed_ptr if drop > 0 else None, salt=self.salts[j])
                 rt.bn_fwd(desc, Y, A, B, G * d)
@@ -269,7 +283,7 @@ class MlpGroup:
             prev, prev_d = Y, d
         if self.out_layer:
             L = ws.mat(f"{self.tag}.logit", B, G)
-            rt.ops.rowdot_fwd(prev, rt.w(self.names["Wout"]), rt.w(self.names["bout"]), L, B, G, prev_d)
+            rt.ops.rowdot_fwd(prev, rt.w(self.names["Wout"], self.g0 * prev_d), rt.w(self.names["bout"], self.g0), L, B, G, prev_d)
             return L
         return prev
 
@@ -285,8 +299,8 @@ class MlpGroup:
         if self.out_layer:
             A_last = self._act(ws, nl - 1, B)
             dA = ws.mat(f"{self.tag}.dA{nl - 1}", B, G * d_last)          # fp32
-            rt.ops.rowdot_bwd(A_last, rt.w(self.names["Wout"]), dOut, dA, rt.g(self.names["Wout"]), rt.g(self.names["bout"]),
-                              B, G, d_last)
+            rt.ops.rowdot_bwd(A_last, rt.w(self.names["Wout"], self.g0 * d_last), dOut, dA, rt.g(self.names["Wout"], self.g0 * d_last),
+                              rt.g(self.names["bout"], self.g0), B, G, d_last)
             if not use_bn:
                 if rt.bf16:
                     raise NotImplementedError("bf16 path: batch size 1 skips BatchNorm (layer.py:202-204); train it on the fp32 path")
@@ -300,33 +314,32 @@ class MlpGroup:
                 A = self._act(ws, j, B)
                 sm = ws.get(f"{self.tag}.bnsave{j}", (2, G * d))
                 dZ = ws.mat(f"{self.tag}.dZ{j}", B, G * d, rt.act_dtype)
-                desc = rt.ops.bn_desc(rt.w(self.names["gamma"][j]), rt.w(self.names["beta"][j]), None, None,
+                desc = rt.ops.bn_desc(self._vec(rt.w, "gamma", j), self._vec(rt.w, "beta", j), None, None,
                                       sm.data_ptr(), sm.data_ptr() + 4 * G * d, train, True, drop_p=drop,
                                       seed_ptr=rt.seed_ptr if drop > 0 else None)
-                rt.bn_bwd(desc, Z, A, cur, dZ, rt.g(self.names["gamma"][j]), rt.g(self.names["beta"][j]), False, B, G * d)
+                rt.bn_bwd(desc, Z, A, cur, dZ, self._vec(rt.g, "gamma", j), self._vec(rt.g, "beta", j), False, B, G * d)
                 cur = dZ
             # cur is now dZ_j  [B, G*d]
-            rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j]))
-            Wj = self.names["W"][j]
+            rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j], self.g0 * d))
             if j == 0 and self.in_groups is None:
-                rt.lin_bwd_w(cur, X, prev_d, rt.o(Wj), d, B, G=G, x_gs=prev_d)
+                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
                 if dX is not None:
-                    rt.lin_bwd_x(cur, prev_d, rt.o(Wj), d, dX, B, G=G, dx_gs=prev_d, accumulate=accumulate)
+                    rt.lin_bwd_x(cur, prev_d, self._oW(j), d, dX, B, G=G, dx_gs=prev_d, accumulate=accumulate)
             elif j == 0:
                 for (blk, e0, e1) in self.in_groups:
-                    rt.lin_bwd_w(cur.cols(e0 * d), X.cols(blk * prev_d), prev_d, rt.o(Wj, e0 * d * prev_d), (e1 - e0) * d, B)
+                    rt.lin_bwd_w(cur.cols(e0 * d), X.cols(blk * prev_d), prev_d, self._oW(j, e0 * d * prev_d), (e1 - e0) * d, B)
                 if dX is not None:
                     seen = set()
                     for (blk, e0, e1) in self.in_groups:
                         acc = accumulate or (blk in seen)
                         seen.add(blk)
-                        rt.lin_bwd_x(cur.cols(e0 * d), prev_d, rt.o(Wj, e0 * d * prev_d), (e1 - e0) * d, dX.cols(blk * prev_d), B,
+                        rt.lin_bwd_x(cur.cols(e0 * d), prev_d, self._oW(j, e0 * d * prev_d), (e1 - e0) * d, dX.cols(blk * prev_d), B,
                                      accumulate=acc)
             else:
                 A_prev = self._act(ws, j - 1, B)
-                rt.lin_bwd_w(cur, A_prev, prev_d, rt.o(Wj), d, B, G=G, x_gs=prev_d)
+                rt.lin_bwd_w(cur, A_prev, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
                 # next gradient: fp32 when BatchNorm consumes it (bn_bwd reads fp32 dA), activation dtype otherwise
                 dA = ws.mat(f"{self.tag}.dA{j - 1}", B, G * prev_d, torch.float32 if use_bn else rt.act_dtype)
                 mask = None if use_bn else A_prev
-                rt.lin_bwd_x(cur, prev_d, rt.o(Wj), d, dA, B, G=G, dx_gs=prev_d, mask=mask, mask_gs=prev_d, mask_scale=keep)
+                rt.lin_bwd_x(cur, prev_d, self._oW(j), d, dA, B, G=G, dx_gs=prev_d, mask=mask, mask_gs=prev_d, mask_scale=keep)
                 cur = dA
