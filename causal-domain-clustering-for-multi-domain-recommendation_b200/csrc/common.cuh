@@ -91,6 +91,17 @@ __host__ __device__ __forceinline__ bool drop_keep_lcg(uint32_t s0, uint32_t thr
   return x >= thr32;
 }
 
+// (row, col) of flat index i in a [*, C] row-major block.  64-bit div/mod costs ~100 instructions on the GPU; almost every
+// index here fits 32 bits, where it is ~20.
+__device__ __forceinline__ void split_idx(int64_t i, int64_t C, int64_t& r, int64_t& c) {
+  if (((uint64_t)i | (uint64_t)C) <= 0xFFFFFFFFull) {
+    const uint32_t q = (uint32_t)i / (uint32_t)C;
+    r = q; c = (uint32_t)i - q * (uint32_t)C;
+  } else {
+    r = i / C; c = i - r * C;
+  }
+}
+
 __device__ __forceinline__ float bf16_to_f32(uint16_t h) { return __uint_as_float(((uint32_t)h) << 16); }
 __device__ __forceinline__ uint16_t f32_to_bf16(float f) {
   __nv_bfloat16 b = __float2bfloat16_rn(f);

@@ -66,10 +66,10 @@ __global__ void embed_gather_kernel(const int32_t* __restrict__ x, const int64_t
   const int lanes = E / VEC;                       // lanes per (b,f) row
   const int64_t total = B * (int64_t)F * lanes;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % lanes);
-    const int64_t bf = i / lanes;
-    const int f = (int)(bf % F);
-    const int64_t b = bf / F;
+    int64_t bf, q64, b, f64;
+    split_idx(i, lanes, bf, q64);
+    split_idx(bf, F, b, f64);
+    const int q = (int)q64, f = (int)f64;
     const int64_t row = (int64_t)x[bf] + offsets[f];
     float v[VEC];
     if (row >= 0 && row < V) {
@@ -102,7 +102,9 @@ __global__ void embed_gather_kernel(const int32_t* __restrict__ x, const int64_t
 __global__ void plan_keys_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ offsets, int64_t n, int F,
                                  int64_t V, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t row = (int64_t)x[i] + offsets[i % F];
+    int64_t bi, fi;
+    split_idx(i, F, bi, fi);
+    int64_t row = (int64_t)x[i] + offsets[fi];
     keys[i] = (row >= 0 && row < V) ? (uint32_t)row : (uint32_t)V;   // out-of-range rows sort last and are ignored
     vals[i] = (int32_t)i;
   }
@@ -205,8 +207,9 @@ __global__ void embed_dense_grad_kernel(const float* __restrict__ grad_out, int6
   const int lanes = E / VEC;
   const int64_t total = V * lanes;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % lanes);
-    const int64_t r = i / lanes;
+    int64_t r, q64;
+    split_idx(i, lanes, r, q64);
+    const int q = (int)q64;
     float acc[VEC];
     segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg_of_row[r], vals, start, cnt, long_slot, long_sum);
     float* o = grad_table + r * E + q * VEC;
@@ -244,10 +247,11 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
   const int64_t total = rows * lanes;
   double sq = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int q = (int)(i % lanes);
-    int64_t r; int seg;
-    if (DENSE) { r = i / lanes; seg = seg_of_row[r]; }
-    else { seg = (int)(i / lanes); r = uniq[seg]; if (r >= V) continue; }
+    int64_t r, q64; int seg;
+    split_idx(i, lanes, r, q64);
+    const int q = (int)q64;
+    if (DENSE) { seg = seg_of_row[r]; }
+    else { seg = (int)r; r = uniq[seg]; if (r >= V) continue; }
     float acc[VEC];
     segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg, vals, start, cnt, long_slot, long_sum);
     const int64_t o = r * E + q * VEC;

@@ -484,7 +484,7 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, int64_t 
                                         int64_t cols, int64_t ld_part, int64_t ld_out, int accumulate) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % cols, r = i / cols;
+    int64_t r, c; split_idx(i, cols, r, c);
     float v = 0.f;
     for (int z = 0; z < splits; ++z) v += part[(int64_t)z * stride + r * ld_part + c];
     float* o = out + r * ld_out + c;

@@ -16,7 +16,7 @@ __global__ void cross_fuse_fwd_kernel(const float* __restrict__ x0, const float*
                                       const float* __restrict__ b, float* __restrict__ out, int64_t B, int64_t D) {
   const int64_t total = B * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t d = i % D, r = i / D;
+    int64_t r, d; split_idx(i, D, r, d);
     const float w = xw_cols == 1 ? xw[r] : xw[i];
     out[i] = x0[i] * w + b[d] + x[i];
   }
@@ -56,7 +56,7 @@ __global__ void crossmix_combine_fwd_kernel(const float* __restrict__ x0, const 
                                             int64_t B, int64_t D, int n_exp) {
   const int64_t total = B * D;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t d = i % D, r = i / D;
+    int64_t r, d; split_idx(i, D, r, d);
     const float bd = bias[d], x0v = x0[i];
     float acc = 0.f;
     for (int e = 0; e < n_exp; ++e) acc = fmaf(g[r * n_exp + e], x0v * (u[(int64_t)e * total + i] + bd), acc);
@@ -201,7 +201,7 @@ __global__ void permute_rows_kernel(const V* __restrict__ src, int64_t lds, cons
                                     V* __restrict__ dst, int64_t ldd, int scatter) {
   const int64_t total = n * vec_cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % vec_cols, r = i / vec_cols;
+    int64_t r, c; split_idx(i, vec_cols, r, c);
     const int64_t p = perm ? (int64_t)perm[r] : r;          // perm == NULL: plain strided 2-D copy
     if (scatter) dst[p * ldd + c] = src[r * lds + c];
     else dst[r * ldd + c] = src[p * lds + c];

@@ -352,13 +352,92 @@ __global__ void bn_apply_kernel(const float* __restrict__ Z, int64_t ldz, T* __r
   const uint32_t thr = drop_thr16(drop_p);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % C, r = i / C;
+    int64_t r, c; split_idx(i, C, r, c);
     float g = gamma[c], b = beta[c];
     if (gamma2) { g *= gamma2[c]; b += beta2[c]; }
     float v = (Z[r * ldz + c] - mean[c]) * invstd[c] * g + b;
     if (relu) v = fmaxf(v, 0.f);
     if (drop_p > 0.f) v = drop_keep(s0, thr, (uint32_t)r, (uint32_t)c) ? v * keep_scale : 0.f;
     st_act<T>(A + r * lda + c, v);
+  }
+}
+
+// 4 columns per thread, 128-bit accesses, 32-bit index arithmetic (one division per 4 elements): the towers' [B, 64..256]
+// activations are small enough that the scalar kernel's 64-bit div/mod per element dominated its run time.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bn_apply_vec4_kernel(const float* __restrict__ Z, int64_t ldz, T* __restrict__ A, int64_t lda, uint32_t total, uint32_t C4,
+                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* __restrict__ gamma2, const float* __restrict__ beta2,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, int relu,
+                     float drop_p, const uint64_t* __restrict__ seed_dev, uint32_t salt) {
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u;
+  const uint32_t thr = drop_thr16(drop_p);
+  const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / C4, c = (i - r * C4) * 4u;
+    float z[4], g[4], b[4], m[4], iv[4], v[4];
+    VecIO<float, 4>::load(Z + (int64_t)r * ldz + c, z);
+    VecIO<float, 4>::load(gamma + c, g); VecIO<float, 4>::load(beta + c, b);
+    VecIO<float, 4>::load(mean + c, m); VecIO<float, 4>::load(invstd + c, iv);
+    if (gamma2) {
+      float g2[4], b2[4];
+      VecIO<float, 4>::load(gamma2 + c, g2); VecIO<float, 4>::load(beta2 + c, b2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { g[q] *= g2[q]; b[q] += b2[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      v[q] = (z[q] - m[q]) * iv[q] * g[q] + b[q];
+      if (relu) v[q] = fmaxf(v[q], 0.f);
+    }
+    if (drop_p > 0.f) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) v[q] = drop_keep(s0, thr, r, c + q) ? v[q] * keep_scale : 0.f;
+    }
+    VecIO<T, 4>::store(A + (int64_t)r * lda + c, v);
+  }
+}
+
+template <typename T, typename TD, typename TZ>
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_vec4_kernel(const float* __restrict__ Z, int64_t ldz, const T* __restrict__ A, int64_t lda,
+                         const TD* __restrict__ dA, int64_t ldda, TZ* __restrict__ dZ, int64_t lddz,
+                         uint32_t total, uint32_t C4, int64_t C, int64_t n_total, const float* __restrict__ gamma,
+                         const float* __restrict__ gamma2, const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ sums, int relu, float keep_scale, int train) {
+  const float inv_n = 1.f / (float)n_total;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const uint32_t r = i / C4, c = (i - r * C4) * 4u;
+    float dy[4], g[4], iv[4], dz[4];
+    VecIO<TD, 4>::load(dA + (int64_t)r * ldda + c, dy);
+    if (relu) {
+      float a[4];
+      VecIO<T, 4>::load(A + (int64_t)r * lda + c, a);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dy[q] = a[q] > 0.f ? dy[q] * keep_scale : 0.f;
+    }
+    VecIO<float, 4>::load(gamma + c, g); VecIO<float, 4>::load(invstd + c, iv);
+    if (gamma2) {
+      float g2[4];
+      VecIO<float, 4>::load(gamma2 + c, g2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) g[q] *= g2[q];
+    }
+    if (train) {
+      float z[4], m[4], s1[4], s2[4];
+      VecIO<float, 4>::load(Z + (int64_t)r * ldz + c, z); VecIO<float, 4>::load(mean + c, m);
+      VecIO<float, 4>::load(sums + c, s1); VecIO<float, 4>::load(sums + C + c, s2);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float xh = (z[q] - m[q]) * iv[q];
+        dz[q] = g[q] * iv[q] * (dy[q] - s1[q] * inv_n - xh * s2[q] * inv_n);
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dz[q] = dy[q] * g[q] * iv[q];
+    }
+    VecIO<TZ, 4>::store(dZ + (int64_t)r * lddz + c, dz);
   }
 }
 
@@ -404,7 +483,7 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ Z, int64_t ldz, co
   const int64_t total = B * C;
   const float inv_n = 1.f / (float)n_total;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % C, r = i / C;
+    int64_t r, c; split_idx(i, C, r, c);
     float dy = ld_act<TD>(dA + r * ldda + c);
     if (relu) dy = ld_act<T>(A + r * lda + c) > 0.f ? dy * keep_scale : 0.f;
     float g = gamma[c];
@@ -428,8 +507,9 @@ rowdot_fwd_kernel(const T* __restrict__ A, int64_t lda, const float* __restrict_
                   float* __restrict__ out, int64_t ldo, int64_t B, int G, int d) {
   const int64_t total = B * G;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int g = (int)(i % G);
-    const int64_t b = i / G;
+    int64_t b, g64;
+    split_idx(i, G, b, g64);
+    const int g = (int)g64;
     const T* a = A + b * lda + (int64_t)g * d;
     const float* wg = w + (int64_t)g * d;
     float acc = 0.f;
@@ -443,8 +523,8 @@ __global__ void rowdot_bwd_x_kernel(const float* __restrict__ dl, int64_t ldl, c
                                     int64_t ldda, int64_t B, int G, int d) {
   const int64_t C = (int64_t)G * d, total = B * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % C, b = i / C;
-    dA[b * ldda + c] = dl[b * ldl + c / d] * w[c];
+    int64_t b, c; split_idx(i, C, b, c);
+    dA[b * ldda + c] = dl[b * ldl + (uint32_t)c / (uint32_t)d] * w[c];
   }
 }
 
@@ -538,7 +618,7 @@ __global__ void relu_mask_kernel(const float* __restrict__ dA, int64_t ldda, con
                                  int64_t ldo, int64_t rows, int64_t cols, float scale) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % cols, r = i / cols;
+    int64_t r, c; split_idx(i, cols, r, c);
     out[r * ldo + c] = A[r * lda + c] > 0.f ? dA[r * ldda + c] * scale : 0.f;
   }
 }
@@ -566,14 +646,14 @@ __global__ void adam_dense_kernel(float* __restrict__ w, const float* __restrict
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, int64_t lds, uint16_t* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % cols, r = i / cols;
+    int64_t r, c; split_idx(i, cols, r, c);
     dst[r * ldd + c] = f32_to_bf16(src[r * lds + c]);
   }
 }
 __global__ void cast_bf16_f32_kernel(const uint16_t* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, int accumulate) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % cols, r = i / cols;
+    int64_t r, c; split_idx(i, cols, r, c);
     const float v = bf16_to_f32(src[r * lds + c]);
     dst[r * ldd + c] = accumulate ? dst[r * ldd + c] + v : v;
   }
@@ -591,7 +671,7 @@ __global__ void ewise_kernel(const float* __restrict__ a, const float* __restric
 __global__ void add2d_kernel(const float* __restrict__ a, int64_t lda, float* __restrict__ out, int64_t ldo, int64_t rows, int64_t cols, int accumulate) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t c = i % cols, r = i / cols;
+    int64_t r, c; split_idx(i, cols, r, c);
     const float v = a[r * lda + c];
     out[r * ldo + c] = accumulate ? out[r * ldo + c] + v : v;
   }
@@ -737,6 +817,21 @@ extern "C" int cdcmdr_bn_fwd_apply(const cdcmdr_bn_t* p, const float* Z, int64_t
   CDC_LAUNCHED();
   if (B == 0) return 0;
   const int g = grid_1d(B * C, 256);
+  const int al = a_is_bf16 ? 8 : 16;
+  auto a16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+  if (C % 4 == 0 && ldz % 4 == 0 && lda_ % 4 == 0 && B * (C / 4) < ((int64_t)1 << 32) && a16(Z) && ((uintptr_t)A % al) == 0 && a16(p->gamma) &&
+      a16(p->beta) && a16(p->save_mean) && a16(p->save_invstd) && (!p->gamma2 || (a16(p->gamma2) && a16(p->beta2)))) {
+    const uint32_t total = (uint32_t)(B * (C / 4));
+    const int gv = grid_1d(total, 256);
+    if (a_is_bf16)
+      bn_apply_vec4_kernel<uint16_t><<<gv, 256, 0, st>>>(Z, ldz, (uint16_t*)A, lda_, total, (uint32_t)(C / 4), p->gamma, p->beta, p->gamma2,
+                                                         p->beta2, p->save_mean, p->save_invstd, p->relu, p->drop_p, p->seed_dev, p->salt);
+    else
+      bn_apply_vec4_kernel<float><<<gv, 256, 0, st>>>(Z, ldz, (float*)A, lda_, total, (uint32_t)(C / 4), p->gamma, p->beta, p->gamma2,
+                                                      p->beta2, p->save_mean, p->save_invstd, p->relu, p->drop_p, p->seed_dev, p->salt);
+    CDC_LAUNCHED();
+    return 0;
+  }
   if (a_is_bf16)
     bn_apply_kernel<uint16_t><<<g, 256, 0, st>>>(Z, ldz, (uint16_t*)A, lda_, B, C, p->gamma, p->beta, p->gamma2, p->beta2, p->save_mean,
                                                  p->save_invstd, p->relu, p->drop_p, p->seed_dev, p->salt);
@@ -809,6 +904,22 @@ extern "C" int cdcmdr_bn_bwd_apply(const cdcmdr_bn_t* p, const float* Z, int64_t
   bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(sums, 1, C, fsums, nullptr, nullptr, 0);
   CDC_LAUNCHED();
   const int g = grid_1d(B * C, 256);
+  {
+    auto al = [](const void* q, int is_bf16) { return ((uintptr_t)q % (is_bf16 ? 8 : 16)) == 0; };
+    auto a16 = [](const void* q) { return ((uintptr_t)q % 16) == 0; };
+    if (C % 4 == 0 && ldz % 4 == 0 && ldda % 4 == 0 && lddz % 4 == 0 && (!p->relu || lda_ % 4 == 0) && B * (C / 4) < ((int64_t)1 << 32) && a16(Z) &&
+        al(dA, da_is_bf16) && al(dZ, dz_is_bf16) && (!p->relu || al(A, a_is_bf16)) && a16(p->gamma) && a16(p->save_mean) && a16(p->save_invstd) &&
+        a16(fsums) && (!p->gamma2 || a16(p->gamma2))) {
+      const uint32_t total = (uint32_t)(B * (C / 4));
+      const int gv = grid_1d(total, 256);
+#define BNV(TA, TD, TZ) bn_bwd_apply_vec4_kernel<TA, TD, TZ><<<gv, 256, 0, st>>>(Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, (TZ*)dZ, lddz, \
+      total, (uint32_t)(C / 4), C, n_total, p->gamma, p->gamma2, p->save_mean, p->save_invstd, fsums, p->relu, keep_scale, p->train)
+      if (combo == 0) BNV(float, float, float); else if (combo == 5) BNV(uint16_t, float, uint16_t); else BNV(uint16_t, uint16_t, uint16_t);
+#undef BNV
+      CDC_LAUNCHED();
+      return 0;
+    }
+  }
 #define BNB(TA, TD, TZ) bn_bwd_apply_kernel<TA, TD, TZ><<<g, 256, 0, st>>>(Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, (TZ*)dZ, lddz, \
       B, n_total, C, p->gamma, p->gamma2, p->save_mean, p->save_invstd, fsums, p->relu, keep_scale, p->train)
   if (combo == 0) BNB(float, float, float); else if (combo == 5) BNB(uint16_t, float, uint16_t); else BNB(uint16_t, uint16_t, uint16_t);
