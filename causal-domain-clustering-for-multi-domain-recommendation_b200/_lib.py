@@ -55,7 +55,7 @@ class GemmBf16(C.Structure):
 
 class MixDesc(C.Structure):
     _fields_ = [("n_gates", I32), ("n_experts", I32), ("h", I32), ("max_sel", I32),
-                ("gate_col", P), ("gate_n", P), ("gate_sel", P)]
+                ("gate_col", P), ("gate_n", P), ("gate_sel", P), ("n_pairs", I32)]
 
 
 class BnDesc(C.Structure):

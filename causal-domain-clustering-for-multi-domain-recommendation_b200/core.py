@@ -156,10 +156,11 @@ class Ops:
         return max(1, int(s))
 
     # ---------------------------------------------------------------- gate mix
-    def mix_desc(self, n_gates, n_experts, h, max_sel, desc_t: torch.Tensor) -> MixDesc:
-        """desc_t: int32 device tensor laid out [gate_col(n_gates) | gate_n(n_gates) | gate_sel(n_gates*max_sel)]."""
+    def mix_desc(self, n_gates, n_experts, h, max_sel, desc_t: torch.Tensor, n_pairs=0) -> MixDesc:
+        """desc_t: int32 device tensor laid out [gate_col(n_gates) | gate_n(n_gates) | gate_sel(n_gates*max_sel)];
+        n_pairs = sum(gate_n), known to the caller on the host."""
         base = desc_t.data_ptr()
-        return MixDesc(n_gates, n_experts, h, max_sel, base, base + 4 * n_gates, base + 8 * n_gates)
+        return MixDesc(n_gates, n_experts, h, max_sel, base, base + 4 * n_gates, base + 8 * n_gates, int(n_pairs))
 
     def gate_mix_fwd(self, d: MixDesc, H: Mat, logits: Mat, out: Mat, probs: torch.Tensor, B):
         self.lib.gate_mix_fwd(C.byref(d), H.ptr, H.ld, logits.ptr, logits.ld, out.ptr, out.ld, probs.data_ptr(), B,

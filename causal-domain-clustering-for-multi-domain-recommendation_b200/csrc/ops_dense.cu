@@ -212,6 +212,117 @@ gate_mix_bwd_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* _
   }
 }
 
+// Row-per-warp backward for the common shape h == 32*VEC (every lane owns VEC columns of each expert block, no inner
+// column loop) and at most 32 (gate, expert) pairs.  The generic kernel above spends ~70 instructions per pair (unrolled
+// column-loop prologues, 64-bit index math, a 10-instruction warp reduction per pair; ncu: 3.5 k instructions per row,
+// issue-bound).  Here: offsets precomputed per pair, one partial per lane per pair into shared memory, and ONE transposed
+// reduction (lane p sums the 32 partials of pair p) instead of 26 butterfly reductions.
+template <int VEC> struct VecS;
+template <> struct VecS<4> {
+  static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[4]) { VecIO<uint16_t, 4>::load(p, v); }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[4]) { VecIO<float, 4>::load(p, v); }
+  static __device__ __forceinline__ void store(uint16_t* p, const float (&v)[4]) { VecIO<uint16_t, 4>::store(p, v); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[4]) { VecIO<float, 4>::store(p, v); }
+};
+template <> struct VecS<2> {
+  static __device__ __forceinline__ void load(const uint16_t* p, float (&v)[2]) {
+    const uint32_t t = *reinterpret_cast<const uint32_t*>(p); v[0] = __uint_as_float(t << 16); v[1] = __uint_as_float(t & 0xffff0000u);
+  }
+  static __device__ __forceinline__ void load(const float* p, float (&v)[2]) { const float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y; }
+  static __device__ __forceinline__ void store(uint16_t* p, const float (&v)[2]) { *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]); }
+  static __device__ __forceinline__ void store(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+};
+
+constexpr int kMixFastPairs = 32;
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+gate_mix_bwd_row_kernel(MixK d, const T* __restrict__ H, int64_t ldh, const float* __restrict__ probs,
+                        const T* __restrict__ dOut, int64_t ldo, T* __restrict__ dH, int64_t lddh, float relu_scale,
+                        float* __restrict__ dlogits, int64_t lddl, int64_t B, int stage_off) {
+  extern __shared__ __align__(16) float dyn[];
+  __shared__ int s_col[32], s_n[32], s_first[32], p_h[kMixFastPairs], p_o[kMixFastPairs], p_slot[kMixFastPairs];
+  __shared__ int s_inv_cnt[64], s_inv_slot[64 * 8], s_inv_o[64 * 8], s_npairs;
+  const int np = d.n_gates * d.max_sel, h = d.h;
+  if (threadIdx.x == 0) {                                // compact list of valid (gate, slot) pairs, gate-major
+    int n = 0;
+    for (int j = 0; j < d.n_gates; ++j) {
+      s_col[j] = d.gate_col[j]; s_n[j] = d.gate_n[j]; s_first[j] = n;
+      for (int s2 = 0; s2 < d.gate_n[j]; ++s2, ++n) { p_h[n] = d.gate_sel[j * d.max_sel + s2] * h; p_o[n] = j * h; p_slot[n] = j * d.max_sel + s2; }
+    }
+    s_npairs = n;
+  }
+  __syncthreads();
+  if (threadIdx.x < d.n_experts) {                       // inverse map expert -> pairs that mix it (at most 8 per expert here)
+    int cnt = 0;
+    for (int p = 0; p < s_npairs; ++p)
+      if (p_h[p] == (int)threadIdx.x * h) { s_inv_slot[threadIdx.x * 8 + cnt] = p_slot[p]; s_inv_o[threadIdx.x * 8 + cnt] = p_o[p]; ++cnt; }
+    s_inv_cnt[threadIdx.x] = cnt;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = s_npairs;
+  // per warp: probabilities [np] | pair dots by slot [np] | partials [32 pairs][33]
+  float* sp = dyn + warp * (2 * np + kMixFastPairs * 33);
+  float* sd = sp + np;
+  float* part = sd + np;
+  const int h_elems = d.n_experts * h, o_elems = d.n_gates * h;
+  T* Hs = reinterpret_cast<T*>(reinterpret_cast<char*>(dyn) + stage_off) + (size_t)warp * (h_elems + o_elems);
+  T* Os = Hs + h_elems;
+  const int lc = lane * VEC;
+  for (int64_t row = (int64_t)blockIdx.x * 8 + warp; row < B; row += (int64_t)gridDim.x * 8) {
+    stage_row(Hs, H + row * ldh, h_elems * (int)sizeof(T), lane);
+    stage_row(Os, dOut + row * ldo, o_elems * (int)sizeof(T), lane);
+    for (int k = lane; k < np; k += 32) sp[k] = probs[row * np + k];
+    __syncwarp();
+    for (int p = 0; p < n_pairs; ++p) {                  // partial <dOut_j, H_e> over this lane's VEC columns
+      float dv[VEC], hv[VEC];
+      VecS<VEC>::load(Os + p_o[p] + lc, dv);
+      VecS<VEC>::load(Hs + p_h[p] + lc, hv);
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) t = fmaf(dv[q], hv[q], t);
+      part[p * 33 + lane] = t;
+    }
+    __syncwarp();
+    if (lane < n_pairs) {                                // fixed-order sum of the 32 partials of pair `lane`
+      float t = 0.f;
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) t += part[lane * 33 + l];
+      sd[p_slot[lane]] = t;
+    }
+    __syncwarp();
+    if (lane < d.n_gates) {                              // softmax backward: dz = p * (dp - <p, dp>)
+      const int n = s_n[lane], base = lane * d.max_sel;
+      float dot = 0.f;
+      for (int s2 = 0; s2 < n; ++s2) dot = fmaf(sp[base + s2], sd[base + s2], dot);
+      float* dz = dlogits + row * lddl + s_col[lane];
+      for (int s2 = 0; s2 < n; ++s2) dz[s2] = sp[base + s2] * (sd[base + s2] - dot);
+    }
+    for (int e = 0; e < d.n_experts; ++e) {              // dH_e = (sum_{pairs mixing e} p * dOut_gate) * relu'(H_e)
+      float acc[VEC];
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) acc[q] = 0.f;
+      const int cnt = s_inv_cnt[e];
+      for (int i = 0; i < cnt; ++i) {
+        float dv[VEC];
+        VecS<VEC>::load(Os + s_inv_o[e * 8 + i] + lc, dv);
+        const float pr = sp[s_inv_slot[e * 8 + i]];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = fmaf(pr, dv[q], acc[q]);
+      }
+      if (relu_scale > 0.f) {
+        float hv[VEC];
+        VecS<VEC>::load(Hs + e * h + lc, hv);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) acc[q] = hv[q] > 0.f ? acc[q] * relu_scale : 0.f;
+      }
+      VecS<VEC>::store(dH + row * lddh + e * h + lc, acc);
+    }
+    __syncwarp();
+  }
+}
+
 // ------------------------------------------------------------------------------------------ column reductions
 constexpr int kMaxChunks = 64;
 
@@ -733,6 +844,25 @@ extern "C" int cdcmdr_gate_mix_bwd(const cdcmdr_mix_desc_t* d, const void* H, in
   if (stage) smem = stage_off + 8 * (h_bytes + o_bytes);
   const int grid = grid_1d(B * 32, 256, stage ? (int)(kMixSmemPerSM / smem > 8 ? 8 : (kMixSmemPerSM / smem < 1 ? 1 : kMixSmemPerSM / smem)) : 8);
   cudaStream_t st = to_stream(s);
+  {
+    // fast row kernel: every lane owns VEC columns of each expert block (h == 32*VEC) and <= 32 (gate, expert) pairs, each expert
+    // mixed by <= 8 gates.  Pair counts come from the descriptor's host mirror: the caller's n_gates*max_sel bound is enough.
+    const int vecw = d->h == 128 ? 4 : (d->h == 64 ? 2 : 0);
+    const size_t per_warp = (size_t)(2 * d->n_gates * d->max_sel + kMixFastPairs * 33) * sizeof(float);
+    const int soff = (int)((8 * per_warp + 15) & ~(size_t)15);
+    const size_t fsmem = soff + 8 * (h_bytes + o_bytes);
+    if (stage && vecw && d->n_gates * d->max_sel <= 64 && d->n_gates <= 8 && fsmem <= kMixStageSmem && d->n_pairs > 0 && d->n_pairs <= kMixFastPairs) {
+      const int per_sm = (int)(kMixSmemPerSM / fsmem);
+      const int fgrid = grid_1d(B * 32, 256, per_sm > 8 ? 8 : (per_sm < 1 ? 1 : per_sm));
+#define MIXR(T, V) do { CDC_CHECK(cudaFuncSetAttribute(gate_mix_bwd_row_kernel<T, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixStageSmem)); \
+      gate_mix_bwd_row_kernel<T, V><<<fgrid, 256, fsmem, st>>>(k, (const T*)H, ldh, probs, (const T*)dOut, ldo, (T*)dH, lddh, relu_scale, dlogits, lddl, B, soff); } while (0)
+      if (is_bf16) { if (vecw == 4) MIXR(uint16_t, 4); else MIXR(uint16_t, 2); }
+      else { if (vecw == 4) MIXR(float, 4); else MIXR(float, 2); }
+#undef MIXR
+      CDC_LAUNCHED();
+      return 0;
+    }
+  }
 #define MIXB(T, V, S) do { if (S) CDC_CHECK(cudaFuncSetAttribute(gate_mix_bwd_kernel<T, V, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMixStageSmem)); \
     gate_mix_bwd_kernel<T, V, S><<<grid, 256, smem, st>>>(k, (const T*)H, ldh, probs, (const T*)dOut, ldo, (T*)dH, lddh, relu_scale, dlogits, lddl, B, stage_off); } while (0)
   if (is_bf16) { if (stage) MIXB(uint16_t, 4, true); else if (vec) MIXB(uint16_t, 4, false); else MIXB(uint16_t, 1, false); }

@@ -51,7 +51,7 @@ class MMoE(BaseModel):
         self._n_gcols = T * nE + 1
         col = [t * nE for t in range(T)]
         self._desc_t = torch.tensor(col + [nE] * T + list(range(nE)) * T, dtype=torch.int32, device=rt.device)
-        self._desc = rt.ops.mix_desc(T, nE, self.expert_dims[-1], nE, self._desc_t)
+        self._desc = rt.ops.mix_desc(T, nE, self.expert_dims[-1], nE, self._desc_t, n_pairs=T * nE)
 
     def _dlin_mat(self, ws, B):
         return ws.mat("gates.dlogits", B, self._n_gcols).cols(self._n_gcols - 1)

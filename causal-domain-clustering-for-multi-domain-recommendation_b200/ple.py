@@ -124,7 +124,7 @@ class PLE(BaseModel):
             if not last:
                 sel += list(range(nE))
             lv.desc_t = torch.tensor(col + n + sel, dtype=torch.int32, device=rt.device)
-            lv.desc = rt.ops.mix_desc(lv.n_gates, nE, lv.h, lv.max_sel, lv.desc_t)
+            lv.desc = rt.ops.mix_desc(lv.n_gates, nE, lv.h, lv.max_sel, lv.desc_t, n_pairs=sum(n))
             self._levels.append(lv)
         self._towers = MlpGroup(rt, "towers", T, self.expert_dims[-1][-1], self.tower_dims, self._tower_names, bn=True,
                                 out_layer=True, in_groups=None)

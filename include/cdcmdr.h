@@ -150,11 +150,13 @@ int cdcmdr_transpose_bf16(const uint16_t* src, int64_t lds, uint16_t* dst, int64
  * logits[:, gate_col[j] : gate_col[j]+gate_n[j]] and mixes experts gate_sel[j*max_sel + s].
  * out gate j -> out[:, j*h : (j+1)*h].  probs (fp32 [B, n_gates*max_sel]) saved for backward.
  * is_bf16: H/out (and dOut/dH) are bf16, else fp32.  Descriptor arrays live in DEVICE memory.
- * Limits: n_gates <= 32, max_sel <= 32, n_experts <= 64.
+ * Limits: n_gates <= 32, max_sel <= 32, n_experts <= 64.  With h in {64, 128}, n_pairs <= 32 and n_gates <= 8 the backward runs
+ * as one warp per row with every lane owning h/32 columns of each expert block (same results, fixed summation order).
  * ------------------------------------------------------------------------------------------- */
 typedef struct {
   int32_t n_gates, n_experts, h, max_sel;
   const int32_t* gate_col; const int32_t* gate_n; const int32_t* gate_sel;   /* device */
+  int32_t n_pairs;   /* sum of gate_n (the host's copy; 0 = not given): lets the launcher pick the row-per-warp backward kernel */
 } cdcmdr_mix_desc_t;
 int cdcmdr_gate_mix_fwd(const cdcmdr_mix_desc_t* d, const void* H, int64_t ldh, const float* logits, int64_t ldl,
                         void* out, int64_t ldo, float* probs, int64_t B, int is_bf16, cdcmdr_stream_t s);

@@ -188,8 +188,11 @@ def test_gemm_f32(M, N, K, G, layout, extra):
 
 
 # ------------------------------------------------------------------------------------------------ gate mix
-@pytest.mark.parametrize("B,h,cfg", [(130, 128, "ple"), (77, 64, "ple_last"), (64, 8, "mmoe"), (5, 6, "odd")])
-def test_gate_mix_fwd_bwd(B, h, cfg):
+@pytest.mark.parametrize("fast", [False, True])
+@pytest.mark.parametrize("B,h,cfg", [(130, 128, "ple"), (77, 64, "ple_last"), (300, 64, "mmoe"), (64, 8, "mmoe"), (5, 6, "odd")])
+def test_gate_mix_fwd_bwd(B, h, cfg, fast):
+    """fast=True hands the launcher the pair count, which selects the row-per-warp backward kernel where the shape allows it
+    (h in {64, 128}, <= 32 pairs); both kernels must agree with the emulator."""
     T, ns, nsh = 4, 2, 2
     nE = T * ns + nsh
     if cfg == "ple":
@@ -212,7 +215,7 @@ def test_gate_mix_fwd_bwd(B, h, cfg):
 
     def fn(lib, e):
         desc = e.put(np.array(col + n + sel, dtype=np.int32))
-        d = L.MixDesc(ng, nE, h, ms, desc.data_ptr(), desc.data_ptr() + 4 * ng, desc.data_ptr() + 8 * ng)
+        d = L.MixDesc(ng, nE, h, ms, desc.data_ptr(), desc.data_ptr() + 4 * ng, desc.data_ptr() + 8 * ng, sum(n) if fast else 0)
         H = torch.relu(e.f32(B, nE * h))
         logits = e.f32(B, ncol)
         out = e.zeros(B, ng * h)
