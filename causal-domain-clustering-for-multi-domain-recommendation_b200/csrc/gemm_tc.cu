@@ -128,6 +128,7 @@ struct TcParams {
   float drop_p; const uint64_t* seed_dev; uint32_t salt;
   int32_t accumulate;
   int32_t tma_store;                         // out_main is written through map_c (alignment checked by the host)
+  int32_t tma_aux;                           // out_aux (fp32) is written through map_d
 };
 
 // Epilogue math for 32 consecutive columns [col0, col0+32) of one row; f in/out.  Returns packed bf16 pairs in o[16].
@@ -199,7 +200,7 @@ __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], cons
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_c, const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* staging = smem + p.stages * p.stage_bytes;
   float* bias_s = (float*)(staging + TC_STAGING_BYTES);
@@ -217,6 +218,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
+    if (p.tma_aux) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
@@ -394,6 +396,44 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           store_pending = true;
           continue;
         }
+        // ---------------- fast fp32 path: 32 fp32 columns (128 B) per row -> swizzled staging -> TMA store ----------------
+        if (p.tma_aux && nb >= p.n_main && ((cw & 31) == 0 || (p.G == 1 && nb + cw == p.N && !p.accumulate))) {
+          for (int s0c = 0; s0c < cw; s0c += 32) {
+            uint32_t v[32];
+            tc_ld32_nowait(trow + c0 + s0c, v);
+            const int64_t nbb = nb + s0c;
+            float4 old[8];
+            if (p.accumulate && m < p.M) {
+              const float4* op4 = reinterpret_cast<const float4*>(p.out_aux + m * p.ld_aux + g * p.aux_gn + (nbb - p.n_main));
+#pragma unroll
+              for (int j = 0; j < 8; ++j) old[j] = op4[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) old[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
+            __syncwarp();
+            tc_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+              if (use_bias) {
+                const float4 b = *reinterpret_cast<const float4*>(bias_t + c0 + s0c + 4 * j);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w;
+              *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) * 16)) = o;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&map_d, my_stage_u32, (int32_t)(g * p.aux_gn + (nbb - p.n_main)), (int32_t)((int64_t)mt * TC_BLOCK_M + q * 32));
+              tma_store_commit();
+            }
+            store_pending = true;
+          }
+          continue;
+        }
         // ---------------- general path: 32 columns at a time, direct global stores ----------------
         for (int s0c = 0; s0c < cw; s0c += 32) {
           uint32_t v[32];
@@ -519,14 +559,15 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // row-major bf16 matrix [rows, cols] with leading dimension ld; box = [box_rows x 64 columns], 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows) {
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows, bool f32 = false) {
   auto enc = get_encode();
   if (!enc) return fail_msg("cdcmdr: cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {64, box_rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
+  cuuint32_t box[2] = {f32 ? 32u : 64u, box_rows};          // 128 bytes per box row either way
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cdcmdr: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%u ptr=%p", (int)r,
@@ -594,6 +635,13 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   } else {
     mc = ma;
   }
+  CUtensorMap md = ma;
+  const int64_t n_aux = p->N - p->n_main;
+  q.tma_aux = (n_aux > 0 && q.split_k == 1 && ((uintptr_t)p->out_aux % 16) == 0 && p->ld_aux % 4 == 0 && p->aux_gn % 4 == 0 &&
+               p->n_main % 32 == 0 && (p->G - 1) * p->aux_gn + n_aux <= p->ld_aux && p->M < (int64_t)1 << 31) ? 1 : 0;
+  if (q.tma_aux) {
+    if (int rc = make_map(&md, p->out_aux, p->M, (p->G - 1) * p->aux_gn + n_aux, p->ld_aux, 32u, true)) return rc;
+  }
   const int b_bytes = (q.b_mn_major ? (int)ceil_div(bn, 64) * 64 : bn) * TC_BLOCK_K * 2;
   q.stage_bytes = TC_A_BYTES + b_bytes;
   const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES;
@@ -610,7 +658,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   }
   const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
   const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  gemm_bf16_tc_kernel<<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, q);
+  gemm_bf16_tc_kernel<<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, q);
   CDC_LAUNCHED();
   return 0;
 }
