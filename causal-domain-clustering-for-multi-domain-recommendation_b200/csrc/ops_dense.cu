@@ -473,6 +473,80 @@ __global__ void bn_apply_kernel(const float* __restrict__ Z, int64_t ldz, T* __r
   }
 }
 
+// Two per-column sums at once, 4 columns per thread with 128-bit loads.  Block = 8 column quads (32 columns) x 32 row lanes, so
+// that narrow matrices (the towers' 64..256 columns) still spread over several hundred blocks; fp32 partial per thread over its
+// rows, double across row lanes and chunks (fixed order).
+template <typename F>
+__global__ void __launch_bounds__(256)
+col_partial2_vec4_kernel(int64_t B, int64_t C, int chunks, double* __restrict__ partial, F f) {
+  __shared__ float sm[2][32][33];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int64_t c0 = ((int64_t)blockIdx.x * 8 + tx) * 4;
+  const int chunk = blockIdx.y;
+  const int64_t rpc = ceil_div(B, chunks);
+  const int64_t r0 = chunk * rpc, r1 = (r0 + rpc < B) ? r0 + rpc : B;
+  float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f};
+  if (c0 < C) {
+    typename F::Cols cols(f, c0);
+#pragma unroll 2
+    for (int64_t r = r0 + ty; r < r1; r += 32) f.add4(cols, r, c0, a, b);
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { sm[0][ty][tx * 4 + q] = a[q]; sm[1][ty][tx * 4 + q] = b[q]; }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int v = threadIdx.x >> 5, i = threadIdx.x & 31;        // 2 statistics x 32 columns
+    const int64_t c = (int64_t)blockIdx.x * 32 + i;
+    if (c < C) {
+      double t = 0;
+#pragma unroll 8
+      for (int y = 0; y < 32; ++y) t += (double)sm[v][y][i];
+      partial[((int64_t)v * chunks + chunk) * C + c] = t;
+    }
+  }
+}
+
+struct BnStatV4 {
+  const float* Z; int64_t ldz;
+  struct Cols { __device__ Cols(const BnStatV4&, int64_t) {} };
+  __device__ __forceinline__ void add4(const Cols&, int64_t r, int64_t c, float (&a)[4], float (&b)[4]) const {
+    float z[4];
+    VecIO<float, 4>::load(Z + r * ldz + c, z);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { a[q] += z[q]; b[q] = fmaf(z[q], z[q], b[q]); }
+  }
+};
+
+template <typename T, typename TD> struct BnBwdStatV4 {
+  const float* Z; int64_t ldz; const T* A; int64_t lda; const TD* dA; int64_t ldda;
+  const float* mean; const float* invstd; int relu; float keep_scale;
+  struct Cols {
+    float m[4], iv[4];
+    __device__ Cols(const BnBwdStatV4& f, int64_t c) { VecIO<float, 4>::load(f.mean + c, m); VecIO<float, 4>::load(f.invstd + c, iv); }
+  };
+  __device__ __forceinline__ void add4(const Cols& k, int64_t r, int64_t c, float (&a)[4], float (&b)[4]) const {
+    float dy[4], z[4];
+    VecIO<TD, 4>::load(dA + r * ldda + c, dy);
+    if (relu) {
+      float av[4];
+      VecIO<T, 4>::load(A + r * lda + c, av);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dy[q] = av[q] > 0.f ? dy[q] * keep_scale : 0.f;
+    }
+    VecIO<float, 4>::load(Z + r * ldz + c, z);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { a[q] += dy[q]; b[q] = fmaf(dy[q], (z[q] - k.m[q]) * k.iv[q], b[q]); }
+  }
+};
+
+static int pick_chunks_vec4(int64_t B, int64_t C) {
+  const int64_t col_blocks = ceil_div(C, 32);
+  int64_t ch = ceil_div(4 * kNumSMs, col_blocks);
+  if (ch > kMaxChunks) ch = kMaxChunks;
+  if (ch > B / 128) ch = B / 128;
+  return ch < 1 ? 1 : (int)ch;
+}
+
 // 4 columns per thread, 128-bit accesses, 32-bit index arithmetic (one division per 4 elements): the towers' [B, 64..256]
 // activations are small enough that the scalar kernel's 64-bit div/mod per element dominated its run time.
 template <typename T>
@@ -886,7 +960,16 @@ extern "C" int cdcmdr_colsum(const void* X, int64_t ld, int is_bf16, int64_t B, 
   cudaStream_t st = to_stream(s);
   double* partial = (double*)scratch;
   const int vec = is_bf16 ? 8 : 4;
-  if (B >= 1024 && C % vec == 0 && ld % vec == 0 && ((uintptr_t)X % 16) == 0) {
+  const int64_t c_pad = ceil_div(C, vec) * vec;
+  if (B >= 1024 && C % vec != 0 && C > 4 * vec && ld % vec == 0 && ld < c_pad && ((uintptr_t)X % 16) == 0) {
+    // whole vectors through the bandwidth-shaped kernel, the few tail columns through the generic one
+    const int64_t Cm = C - C % vec;
+    if (int rc = cdcmdr_colsum(X, ld, is_bf16, B, Cm, out, accumulate, scratch, s)) return rc;
+    const void* Xt = is_bf16 ? (const void*)((const uint16_t*)X + Cm) : (const void*)((const float*)X + Cm);
+    return cdcmdr_colsum(Xt, ld, is_bf16, B, C - Cm, out + Cm, accumulate, scratch, s);
+  }
+  // a last vector that hangs over C reads the row's padding columns (ld >= c_pad); their sums are never written
+  if (B >= 1024 && ld >= c_pad && ld % vec == 0 && ((uintptr_t)X % 16) == 0) {
     const int64_t col_blocks = ceil_div(C, 32 * vec);
     int64_t ch = ceil_div(4 * kNumSMs, col_blocks);
     if (ch > kMaxChunks) ch = kMaxChunks;
@@ -923,10 +1006,16 @@ extern "C" int cdcmdr_bn_fwd_stats(const float* Z, int64_t ldz, int64_t B, int64
   if (C == 0) return 0;
   cudaStream_t st = to_stream(s);
   if (B == 0) { CDC_CHECK(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st)); return 0; }
-  const int chunks = pick_chunks(B, C);
+  int chunks = pick_chunks(B, C);
   double* partial = (double*)scratch;
-  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
-  col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, BnStatF{Z, ldz});
+  if (B >= 256 && C % 4 == 0 && ldz % 4 == 0 && ((uintptr_t)Z % 16) == 0) {
+    chunks = pick_chunks_vec4(B, C);
+    dim3 vgrid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+    col_partial2_vec4_kernel<<<vgrid, 256, 0, st>>>(B, C, chunks, partial, BnStatV4{Z, ldz});
+  } else {
+    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+    col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, BnStatF{Z, ldz});
+  }
   CDC_LAUNCHED();
   chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 256), 256, 0, st>>>(partial, chunks, C, sums);
   CDC_LAUNCHED();
@@ -999,17 +1088,28 @@ extern "C" int cdcmdr_bn_bwd_stats(const cdcmdr_bn_t* p, const float* Z, int64_t
     return 0;
   }
   CDC_REQUIRE(dA, "bad batch-norm arguments");
-  const int chunks = pick_chunks(B, C);
+  int chunks = pick_chunks(B, C);
   double* partial = (double*)scratch;
   float* fsums = (float*)((char*)scratch + 2 * (size_t)kMaxChunks * (size_t)C * sizeof(double));
   const float keep_scale = p->drop_p > 0.f ? 1.f / (1.f - p->drop_p) : 1.f;
-  dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
   const int combo = (a_is_bf16 ? 2 : 0) | (da_is_bf16 ? 1 : 0);
   CDC_REQUIRE(combo == 0 || combo == 2 || combo == 3, "batch-norm backward dtypes: (A, dA) must be (fp32, fp32), (bf16, fp32) or (bf16, bf16)");
+  auto al = [](const void* q, int is_bf16) { return ((uintptr_t)q % (is_bf16 ? 8 : 16)) == 0; };
+  if (B >= 256 && C % 4 == 0 && ldz % 4 == 0 && ldda % 4 == 0 && (!p->relu || lda_ % 4 == 0) && al(Z, 0) && al(dA, da_is_bf16) &&
+      (!p->relu || al(A, a_is_bf16)) && al(p->save_mean, 0) && al(p->save_invstd, 0)) {
+    chunks = pick_chunks_vec4(B, C);
+    dim3 vgrid((unsigned)ceil_div(C, 32), (unsigned)chunks);
+#define BNSV(TA, TD) col_partial2_vec4_kernel<<<vgrid, 256, 0, st>>>(B, C, chunks, partial, \
+      BnBwdStatV4<TA, TD>{Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale})
+    if (combo == 0) BNSV(float, float); else if (combo == 2) BNSV(uint16_t, float); else BNSV(uint16_t, uint16_t);
+#undef BNSV
+  } else {
+    dim3 grid((unsigned)ceil_div(C, 32), (unsigned)chunks);
 #define BNS(TA, TD) col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, \
       BnBwdStatF<TA, TD>{Z, ldz, (const TA*)A, lda_, (const TD*)dA, ldda, p->save_mean, p->save_invstd, p->relu, keep_scale})
-  if (combo == 0) BNS(float, float); else if (combo == 2) BNS(uint16_t, float); else BNS(uint16_t, uint16_t);
+    if (combo == 0) BNS(float, float); else if (combo == 2) BNS(uint16_t, float); else BNS(uint16_t, uint16_t);
 #undef BNS
+  }
   CDC_LAUNCHED();
   chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 256), 256, 0, st>>>(partial, chunks, C, sums);
   CDC_LAUNCHED();

@@ -125,6 +125,14 @@ class PLE(BaseModel):
                 sel += list(range(nE))
             lv.desc_t = torch.tensor(col + n + sel, dtype=torch.int32, device=rt.device)
             lv.desc = rt.ops.mix_desc(lv.n_gates, nE, lv.h, lv.max_sel, lv.desc_t, n_pairs=sum(n))
+            # level 0: gates and wide linear read the same input as the experts and their weights / biases follow the experts' in
+            # the arena -> their backward rides on the experts' layer-0 GEMMs as extra columns
+            d0 = self.expert_dims[l][0]
+            lv.fused_bwd = (l == 0 and lv.experts.can_fuse_tail() and
+                            rt.o(f"cgc{l}.gW") == rt.o(self._level_names[l]["W"][0]) + nE * d0 * lv.K and
+                            rt.o(f"cgc{l}.gb") == rt.o(self._level_names[l]["b"][0]) + nE * d0)
+            if lv.fused_bwd:
+                lv.experts.tail0 = lv.n_gcols
             self._levels.append(lv)
         self._towers = MlpGroup(rt, "towers", T, self.expert_dims[-1][-1], self.tower_dims, self._tower_names, bn=True,
                                 out_layer=True, in_groups=None)
@@ -169,6 +177,15 @@ class PLE(BaseModel):
             xin = X if l == 0 else ws.mat(f"cgc{l - 1}.out", B, self._levels[l - 1].n_gates * self._levels[l - 1].h, act)
             # the embedding backward consumes an fp32 gradient; deeper levels hand an activation-dtype gradient to gate_mix_bwd
             dxin = ws.mat(f"cgc{l}.dXin", B, lv.n_in * lv.K, torch.float32 if l == 0 else act)
+            if lv.fused_bwd:
+                tail = lv.experts.dA0(ws, B).cols(nE * lv.experts.dims[0])
+                if rt.bf16:
+                    rt.ops.cast_f32_bf16(dLg, tail, B, lv.n_gcols)
+                else:
+                    rt.ops.add2d(dLg, tail, B, lv.n_gcols, False)
+                lv.experts.bwd(ws, xin, dH, B, train, dxin)
+                dcur = dxin
+                continue
             lv.experts.bwd(ws, xin, dH, B, train, dxin)
             dLgi = rt.gemm_input(ws, f"cgc{l}.dlogits_op", dLg, B, lv.n_gcols)
             for (blk, r0, r1, c0) in lv.gate_groups:

@@ -224,6 +224,10 @@ class MlpGroup:
         self.rt, self.tag, self.G, self.in_dim, self.dims = rt, tag, G, in_dim, tuple(dims)
         self.names, self.bn, self.out_layer, self.in_groups, self.g0 = names, bn, out_layer, in_groups, g0
         self.salts = [rt.next_salt() for _ in dims]
+        # tail0 > 0: the layer-0 pre-activation gradient buffer carries `tail0` extra columns that the caller fills (PLE level 0:
+        # the gate / wide-linear logit gradients, whose weights sit right after the experts' in the arena), so that ONE weight-
+        # gradient GEMM, ONE input-gradient GEMM and ONE column sum serve experts and gates together
+        self.tail0 = 0
         if rt.bf16 and (in_dim % 8 or any(d % 8 for d in dims)):
             raise ValueError("the bf16 tensor-core path needs every layer width to be a multiple of 8 (TMA alignment)")
 
@@ -239,6 +243,16 @@ class MlpGroup:
 
     def _vec(self, fn, key, j):
         return fn(self.names[key][j], self.g0 * self.dims[j])
+
+    def can_fuse_tail(self):
+        return (not self.bn) and len(self.dims) >= 2 and self.in_groups is not None and len(self.in_groups) == 1 and self.g0 == 0
+
+    def dA0(self, ws: Workspace, B) -> Mat:
+        """layer-0 pre-activation gradient [B, G*d0 (+ tail0 columns, pitch padded to 8)]"""
+        n = self.G * self.dims[0]
+        ld = n + ((self.tail0 + 7) // 8 * 8 if self.tail0 else 0)
+        use_bn = self.bn and B != 1
+        return ws.mat(f"{self.tag}.dA0", B, ld, torch.float32 if use_bn else self.rt.act_dtype)
 
     def _act(self, ws: Workspace, j, B) -> Mat:
         return ws.mat(f"{self.tag}.A{j}", B, self.G * self.dims[j], self.rt.act_dtype)
@@ -320,6 +334,13 @@ class MlpGroup:
                 rt.bn_bwd(desc, Z, A, cur, dZ, self._vec(rt.g, "gamma", j), self._vec(rt.g, "beta", j), False, B, G * d)
                 cur = dZ
             # cur is now dZ_j  [B, G*d]
+            if j == 0 and self.tail0 and nl >= 2:                # experts + the caller's tail columns in one go
+                n_tot = G * d + self.tail0
+                rt.ops.colsum(cur, B, n_tot, rt.g(self.names["b"][j]))
+                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), n_tot, B)
+                if dX is not None:
+                    rt.lin_bwd_x(cur, prev_d, self._oW(j), n_tot, dX, B, accumulate=accumulate)
+                continue
             rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j], self.g0 * d))
             if j == 0 and self.in_groups is None:
                 rt.lin_bwd_w(cur, X, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
@@ -339,7 +360,7 @@ class MlpGroup:
                 A_prev = self._act(ws, j - 1, B)
                 rt.lin_bwd_w(cur, A_prev, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
                 # next gradient: fp32 when BatchNorm consumes it (bn_bwd reads fp32 dA), activation dtype otherwise
-                dA = ws.mat(f"{self.tag}.dA{j - 1}", B, G * prev_d, torch.float32 if use_bn else rt.act_dtype)
+                dA = self.dA0(ws, B) if j == 1 else ws.mat(f"{self.tag}.dA{j - 1}", B, G * prev_d, torch.float32 if use_bn else rt.act_dtype)
                 mask = None if use_bn else A_prev
                 rt.lin_bwd_x(cur, prev_d, self._oW(j), d, dA, B, G=G, dx_gs=prev_d, mask=mask, mask_gs=prev_d, mask_scale=keep)
                 cur = dA
