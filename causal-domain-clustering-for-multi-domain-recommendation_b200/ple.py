@@ -83,6 +83,16 @@ class PLE(BaseModel):
         self._tower_names = tnames
         blocks += tblk
         bufs += tbufs
+        # Levels >= 1: every gate reads a different input and is only 4..10 outputs wide - five launch-bound GEMMs per pass.
+        # Their weights are packed once per step into ONE block-diagonal operand [n_gates*16, (T+1)*K] (gate j: rows j*16.., columns
+        # of its input block) living in the arena as a derived block (not a parameter), so forward, weight-gradient and
+        # input-gradient of all gates of a level are one plain GEMM each over the concatenated inputs.
+        self._gpad = 16
+        self._extra_blocks = []
+        for l in range(1, self.n_level):
+            n_gates = T if l + 1 == self.n_level else T + 1
+            Kl = expert_dims[l - 1][-1]
+            self._extra_blocks += [(f"cgc{l}.Wbd", n_gates * self._gpad * (T + 1) * Kl), (f"cgc{l}.bbd", n_gates * self._gpad)]
         self._finalize(blocks, bufs, precision=precision_of(config), dropout=dropout)
 
     # ---------------------------------------------------------------- program construction
@@ -111,10 +121,12 @@ class PLE(BaseModel):
                 lv.gate_groups = [(0, 0, lv.n_gcols, 0)]
                 col = [t * w for t in range(T)] + ([] if last else [T * w])
             else:
-                pw = (w + 7) // 8 * 8
+                pw = self._gpad
+                if max(w, nE) > pw:
+                    raise NotImplementedError("more than 16 experts per gate at a deeper CGC level")
                 lv.gate_groups = [(t, t * w, (t + 1) * w, t * pw) for t in range(T)] + ([] if last else [(T, T * w, T * w + nE, T * pw)])
-                lv.n_gcols = T * pw + (0 if last else (nE + 7) // 8 * 8)
-                col = [t * pw for t in range(T)] + ([] if last else [T * pw])
+                lv.n_gcols = lv.n_gates * pw
+                col = [j * pw for j in range(lv.n_gates)]
             lv.max_sel = w if last else nE
             n = [w] * T + ([] if last else [nE])
             sel = []
@@ -137,9 +149,36 @@ class PLE(BaseModel):
         self._towers = MlpGroup(rt, "towers", T, self.expert_dims[-1][-1], self.tower_dims, self._tower_names, bn=True,
                                 out_layer=True, in_groups=None)
 
+    # ---------------------------------------------------------------- packed gates of the deeper levels
+    def _gate_blocks(self, lv):
+        """(first weight row in cgc.gW, rows, packed row, input block) per gate"""
+        return [(r0, r1 - r0, c0, blk) for (blk, r0, r1, c0) in lv.gate_groups]
+
+    def _pack_gates(self, l, lv):
+        rt, K = self._rt, lv.K
+        ops, ldw = rt.ops, lv.n_in * lv.K
+        for (r0, n, c0, blk) in self._gate_blocks(lv):
+            ops.copy2d(rt.w(f"cgc{l}.gW", r0 * K), K, rt.w(f"cgc{l}.Wbd", c0 * ldw + blk * K), ldw, n, K, 4)
+            ops.copy2d(rt.w(f"cgc{l}.gb", r0), n, rt.w(f"cgc{l}.bbd", c0), n, 1, n, 4)
+        if rt.bf16:                                              # bf16 operand copy of the packed block (the arena cast ran earlier)
+            lo, n_el = rt.o(f"cgc{l}.Wbd"), lv.n_gcols * ldw
+            ops.cast_f32_bf16(Mat(rt.W, lo, n_el), Mat(rt.Wb, lo, n_el), 1, n_el)
+
+    def _gates_bwd_packed(self, ws, l, lv, xin, dLg, dxin, B):
+        rt, K = self._rt, lv.K
+        ops, ldw = rt.ops, lv.n_in * lv.K
+        tmpb = ws.get(f"cgc{l}.dbbd", (lv.n_gcols,))
+        ops.colsum(dLg, B, lv.n_gcols, tmpb.data_ptr())
+        dLgi = rt.gemm_input(ws, f"cgc{l}.dlogits_op", dLg, B, lv.n_gcols)
+        rt.lin_bwd_w(dLgi, xin, ldw, rt.o(f"cgc{l}.Wbd"), lv.n_gcols, B)          # dWbd (diagonal blocks are the gates' gradients)
+        rt.lin_bwd_x(dLgi, ldw, rt.o(f"cgc{l}.Wbd"), lv.n_gcols, dxin, B, accumulate=True)
+        for (r0, n, c0, blk) in self._gate_blocks(lv):
+            ops.copy2d(rt.g(f"cgc{l}.Wbd", c0 * ldw + blk * K), ldw, rt.g(f"cgc{l}.gW", r0 * K), K, n, K, 4)
+            ops.copy2d(tmpb.data_ptr() + 4 * c0, n, rt.g(f"cgc{l}.gb", r0), n, 1, n, 4)
+
     def _dlin_mat(self, ws, B):
         n = self._levels[0].n_gcols
-        return ws.mat("cgc0.dlogits", B, n).cols(n - 1)
+        return ws.mat("cgc0.dlogits", B, n, zero=True).cols(n - 1)
 
     def _program_fwd(self, ws, X: Mat, B, train):
         rt = self._rt
@@ -147,9 +186,13 @@ class PLE(BaseModel):
         for l, lv in enumerate(self._levels):
             H = lv.experts.fwd(ws, xin, B, train)
             Lg = ws.mat(f"cgc{l}.logits", B, lv.n_gcols)
-            for (blk, r0, r1, c0) in lv.gate_groups:
-                rt.lin_fwd(xin.cols(blk * lv.K), lv.K, rt.o(f"cgc{l}.gW", r0 * lv.K), r1 - r0, rt.o(f"cgc{l}.gb", r0),
-                           Lg.cols(c0), B)
+            if l > 0:
+                self._pack_gates(l, lv)
+                rt.lin_fwd(xin, lv.n_in * lv.K, rt.o(f"cgc{l}.Wbd"), lv.n_gcols, rt.o(f"cgc{l}.bbd"), Lg, B)
+            else:
+                for (blk, r0, r1, c0) in lv.gate_groups:
+                    rt.lin_fwd(xin.cols(blk * lv.K), lv.K, rt.o(f"cgc{l}.gW", r0 * lv.K), r1 - r0, rt.o(f"cgc{l}.gb", r0),
+                               Lg.cols(c0), B)
             out = ws.mat(f"cgc{l}.out", B, lv.n_gates * lv.h, rt.act_dtype)
             probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
             rt.ops.gate_mix_fwd(lv.desc, H, Lg, out, probs, B)
@@ -171,7 +214,8 @@ class PLE(BaseModel):
             nE = lv.experts.G
             H = lv.experts._act(ws, len(lv.experts.dims) - 1, B)
             dH = ws.mat(f"cgc{l}.dH", B, nE * lv.h, act)
-            dLg = ws.mat(f"cgc{l}.dlogits", B, lv.n_gcols)
+            # zero-initialised once: the padding columns between gates are never written and must not feed NaNs into the GEMMs
+            dLg = ws.mat(f"cgc{l}.dlogits", B, lv.n_gcols, zero=True)
             probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
             rt.ops.gate_mix_bwd(lv.desc, H, probs, dcur, dH, keep, dLg, B)
             xin = X if l == 0 else ws.mat(f"cgc{l - 1}.out", B, self._levels[l - 1].n_gates * self._levels[l - 1].h, act)
@@ -187,6 +231,10 @@ class PLE(BaseModel):
                 dcur = dxin
                 continue
             lv.experts.bwd(ws, xin, dH, B, train, dxin)
+            if l > 0:
+                self._gates_bwd_packed(ws, l, lv, xin, dLg, dxin, B)
+                dcur = dxin
+                continue
             dLgi = rt.gemm_input(ws, f"cgc{l}.dlogits_op", dLg, B, lv.n_gcols)
             for (blk, r0, r1, c0) in lv.gate_groups:
                 rt.ops.colsum(dLg.cols(c0), B, r1 - r0, rt.g(f"cgc{l}.gb", r0))
