@@ -228,6 +228,10 @@ class MlpGroup:
         # the gate / wide-linear logit gradients, whose weights sit right after the experts' in the arena), so that ONE weight-
         # gradient GEMM, ONE input-gradient GEMM and ONE column sum serve experts and gates together
         self.tail0 = 0
+        # in_groups that are uniform (group i = input block i feeding experts [i*c, (i+1)*c)) run as ONE grouped launch
+        ig = in_groups
+        self.uniform = (ig is not None and len(ig) > 1 and all(b == i and e1 - e0 == ig[0][2] - ig[0][1] and e0 == i * (ig[0][2] - ig[0][1])
+                                                                for i, (b, e0, e1) in enumerate(ig)))
         if rt.bf16 and (in_dim % 8 or any(d % 8 for d in dims)):
             raise ValueError("the bf16 tensor-core path needs every layer width to be a multiple of 8 (TMA alignment)")
 
@@ -261,6 +265,10 @@ class MlpGroup:
         rt, d, K = self.rt, self.dims[0], self.in_dim
         if self.in_groups is None:                               # MLP g reads input block g: one grouped launch
             rt.lin_fwd(X, K, self._oW(0), d, self._ob(0), Y, B, G=self.G, x_gs=K, relu=fused_act, drop=drop, salt=self.salts[0])
+        elif self.uniform:                                       # c MLPs per input block: grouped over the blocks
+            c = self.in_groups[0][2] - self.in_groups[0][1]
+            rt.lin_fwd(X, K, self._oW(0), c * d, self._ob(0), Y, B, G=len(self.in_groups), x_gs=K, relu=fused_act, drop=drop,
+                       salt=self.salts[0])
         else:
             for (blk, e0, e1) in self.in_groups:
                 rt.lin_fwd(X.cols(blk * K), K, self._oW(0, e0 * d * K), (e1 - e0) * d, self._ob(0, e0 * d), Y.cols(e0 * d), B,
@@ -346,6 +354,11 @@ class MlpGroup:
                 rt.lin_bwd_w(cur, X, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
                 if dX is not None:
                     rt.lin_bwd_x(cur, prev_d, self._oW(j), d, dX, B, G=G, dx_gs=prev_d, accumulate=accumulate)
+            elif j == 0 and self.uniform:
+                c, ng = self.in_groups[0][2] - self.in_groups[0][1], len(self.in_groups)
+                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), c * d, B, G=ng, x_gs=prev_d)
+                if dX is not None:
+                    rt.lin_bwd_x(cur, prev_d, self._oW(j), c * d, dX, B, G=ng, dx_gs=prev_d, accumulate=accumulate)
             elif j == 0:
                 for (blk, e0, e1) in self.in_groups:
                     rt.lin_bwd_w(cur.cols(e0 * d), X.cols(blk * prev_d), prev_d, self._oW(j, e0 * d * prev_d), (e1 - e0) * d, B)

@@ -161,3 +161,37 @@ def test_dcnv2_crossnet_v2_matches_oracle(structure):
             noisy = bias_before_bn("dcnv2", k) or k.endswith("running_mean") or (structure == "stacked" and k == "crossnet.b.2")
             tol = 2.1e-3 * (s + 1) if noisy else 2e-5
             assert np.abs(cur[k] - v).max() <= tol, (s, k, float(np.abs(cur[k] - v).max()))
+
+
+@pytest.mark.parametrize("ns,nsh,levels", [(2, 2, ((16, 8), (8,))), (1, 1, ((8,), (8, 8), (4,))), (3, 2, ((16, 8), (8,)))])
+def test_ple_launch_shapes_match_oracle(ns, nsh, levels):
+    """PLE expert / gate launch shapes that the reference fixtures (2 specific + 1 shared, two levels) do not reach: equal specific
+    and shared counts (deeper levels run as ONE grouped launch over the input blocks), single-layer level 0 (no fused gate
+    backward), three levels (two packed block-diagonal gate operands)."""
+    from oracle import cdcmdr_oracle as O
+    torch.manual_seed(21)
+    rng = np.random.default_rng(21)
+    fd = np.array([9, 6, 12, 5, 7], dtype=np.int64)
+    E_, T, B = 4, 3, 96
+    l2 = dict(l2_reg_embedding=1e-3, l2_reg_linear=1e-3, l2_reg_dnn=1e-3)
+    model = cm.PLE(fd, E_, T, ns, nsh, levels, (8, 4), dropout=0.0, **l2)
+    om = O.PLE(fd, E_, T, ns, nsh, levels, (8, 4), **l2)
+    sd = {k: (v.detach().numpy().astype(np.float64) if v.dtype == torch.float32 else v.detach().numpy().copy())
+          for k, v in model.state_dict().items()}
+    x = np.stack([rng.integers(0, d, size=B) for d in fd], axis=1).astype(np.int32)
+    y = (rng.random(B) < 0.4).astype(np.int16)
+    g = rng.integers(0, T, size=B).astype(np.int64)
+    model.train()
+    opt, oopt = cm.Adam(model.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8), O.Adam()
+    for s in range(2):
+        r = O.train_step(om, sd, oopt, x, y, "gather", group=g)
+        out = model.train_step(torch.from_numpy(x), torch.from_numpy(y), opt, mode="gather", sel=torch.from_numpy(g))
+        _, bce, reg = model.step_losses(out)
+        assert np.abs(out["pred"].numpy() - r["pred"]).max() <= 1e-5
+        assert abs(bce - float(r["bce"])) <= 1e-5 and abs(reg - float(r["reg"])) <= 1e-5 * float(r["reg"])
+        cur = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+        for k, v in sd.items():
+            if k.endswith("num_batches_tracked"):
+                continue
+            tol = 2.1e-3 * (s + 1) if bias_before_bn("ple", k) or k.endswith("running_mean") else 2e-5
+            assert np.abs(cur[k] - v).max() <= tol, (s, k, float(np.abs(cur[k] - v).max()))
