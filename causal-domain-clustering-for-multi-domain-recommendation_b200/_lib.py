@@ -86,6 +86,7 @@ SIGNATURES = {
     "cdcmdr_gemm_f32": (INT, [C.POINTER(GemmF32), P]),
     "cdcmdr_gemm_bf16_tc": (INT, [C.POINTER(GemmBf16), P]),
     "cdcmdr_gemm_bf16_tc_splits": (INT, [I64, I32]),
+    "cdcmdr_gemm_bf16_tc_mode": (INT, [INT]),
     "cdcmdr_splitk_reduce": (INT, [P, I64, I32, P, I64, I64, I64, I64, I32, P]),
     "cdcmdr_transpose_bf16": (INT, [P, I64, P, I64, I64, I64, P]),
     "cdcmdr_gate_mix_fwd": (INT, [C.POINTER(MixDesc), P, I64, P, I64, P, I64, P, I64, INT, P]),
@@ -127,7 +128,7 @@ SIGNATURES = {
 }
 
 # entry points that return a status code (everything that launches work)
-_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is INT and k not in ("cdcmdr_version", "cdcmdr_gemm_bf16_tc_splits")}
+_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is INT and k not in ("cdcmdr_version", "cdcmdr_gemm_bf16_tc_splits", "cdcmdr_gemm_bf16_tc_mode")}
 
 
 class CdcmdrError(RuntimeError):

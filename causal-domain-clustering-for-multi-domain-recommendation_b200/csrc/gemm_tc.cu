@@ -86,6 +86,41 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// ---- 2-CTA (cta_group::2) helpers: the CTA pair of a cluster works on one 256 x block_n tile; rank 0 issues the MMAs
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank)); return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {       // acquire at cluster scope
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE_C;\n"
+      "bra WAIT_LOOP_C;\n"
+      "WAIT_DONE_C:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tc_commit2_mc(uint32_t bar) {                             // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
 // 32 lanes x 32 consecutive fp32 columns: thread = TMEM lane (tile row), register j = column j.  No wait inside.
 __device__ __forceinline__ void tc_ld32_nowait(uint32_t taddr, uint32_t* r) {
   asm volatile(
@@ -198,6 +233,13 @@ __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], cons
   for (int j = 0; j < 16; ++j) o[j] = pack_bf16x2(f[2 * j], f[2 * j + 1]);
 }
 
+// CTA2 = true: launched as clusters of two CTAs (one SM pair).  The pair owns a 256 x block_n tile: each CTA loads its own 128
+// rows of A and HALF of the B tile (block_n/2 rows of N), rank 0 issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs'
+// shared memory and writes each CTA's 128 accumulator rows into that CTA's TMEM; both CTAs run their own epilogue.  Per CTA and
+// k-block that is 16 + 16 KB of operands instead of 16 + 32 KB - the level-0 GEMMs are bound by exactly that L2 -> SM traffic.
+// Cross-CTA signalling: rank 1 relays "my stage is full" to rank 0 (remote mbarrier arrive), rank 0's tcgen05.commit multicasts
+// "stage free" / "accumulator ready" to both CTAs, both epilogues arrive on rank 0's "accumulator drained" barrier.
+template <bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d, const TcParams p) {
@@ -207,13 +249,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint64_t* bars = (uint64_t*)((uint8_t*)bias_s + TC_BIAS_BYTES);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_MAX_STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * TC_MAX_STAGES), tempty0 = smem_u32(bars + 2 * TC_MAX_STAGES + 2);
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * TC_MAX_STAGES + 4);
+  const uint32_t pfull0 = smem_u32(bars + 2 * TC_MAX_STAGES + 4);            // rank 0 only: "rank 1's stage is full"
+  uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_MAX_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int64_t tile0 = CTA2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t tile_step = CTA2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();                          // the swizzle atoms below assume it
-    for (int i = 0; i < p.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, TC_EPI_WARPS); }
+    for (int i = 0; i < p.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); mbar_init(pfull0 + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -226,59 +272,81 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();                        // both CTAs' barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (CTA2 && tmem_base != 0u && threadIdx.x == 0) __trap();       // the pair's MMA addresses both CTAs' TMEM with one address
 
+  // p.n_tiles_m counts 128-row tiles (CTA2: 256-row pair tiles; this CTA's rows are tile (2*mt + rank))
   const int64_t tiles_per_group = (int64_t)p.n_tiles_m * p.n_tiles_n * p.split_k;
   const int64_t total_tiles = tiles_per_group * p.G;
-  const uint32_t stage_tx = (uint32_t)(TC_A_BYTES + (p.b_mn_major ? ((p.block_n + 63) / 64) * 64 : p.block_n) * TC_BLOCK_K * 2);
+  const int b_cols = CTA2 ? (p.block_n >> 1) : p.block_n;          // N columns of the B tile held by this CTA
+  const uint32_t stage_tx = (uint32_t)(TC_A_BYTES + (p.b_mn_major ? ((b_cols + 63) / 64) * 64 : b_cols) * TC_BLOCK_K * 2);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
         const int g = (int)(tile / tiles_per_group);
         int64_t r = tile % tiles_per_group;
         const int z = (int)(r % p.split_k); r /= p.split_k;
-        const int nt = (int)(r % p.n_tiles_n), mt = (int)(r / p.n_tiles_n);
+        const int nt = (int)(r % p.n_tiles_n);
+        const int64_t mt = CTA2 ? 2 * (r / p.n_tiles_n) + rank : r / p.n_tiles_n;
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-        const int32_t a_mn = (int32_t)(g * p.a_gmn + (int64_t)mt * TC_BLOCK_M), b_mn = (int32_t)(g * p.b_gmn + (int64_t)nt * p.block_n);
+        const int32_t a_mn = (int32_t)(g * p.a_gmn + mt * TC_BLOCK_M);
+        const int32_t b_mn = (int32_t)(g * p.b_gmn + (int64_t)nt * p.block_n + (CTA2 ? (int64_t)rank * b_cols : 0));
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          if (CTA2) mbar_wait_cluster(empty0 + 8 * stage, phase ^ 1); else mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
           const uint32_t bar = full0 + 8 * stage;
           mbar_expect_tx(bar, stage_tx);
           const int32_t ak = (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), bk = (int32_t)(g * p.b_gk + (int64_t)kb * TC_BLOCK_K);
           if (!p.a_mn_major) tma_load_2d(sa, &map_a, bar, ak, a_mn);                    // box [128 rows (m) x 64 (k)]
           else { tma_load_2d(sa, &map_a, bar, a_mn, ak); tma_load_2d(sa + 8192, &map_a, bar, a_mn + 64, ak); }   // 2 x [64 (k) x 64 (m)]
-          if (!p.b_mn_major) tma_load_2d(sb, &map_b, bar, bk, b_mn);                    // box [block_n rows (n) x 64 (k)]
-          else for (int j = 0; j * 64 < p.block_n; ++j) tma_load_2d(sb + 8192 * j, &map_b, bar, b_mn + 64 * j, bk);
+          if (!p.b_mn_major) tma_load_2d(sb, &map_b, bar, bk, b_mn);                    // box [b_cols rows (n) x 64 (k)]
+          else for (int j = 0; j * 64 < b_cols; ++j) tma_load_2d(sb + 8192 * j, &map_b, bar, b_mn + 64 * j, bk);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
-      // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn_major ? 1 : 0) << 15) |
-                             ((uint32_t)(p.b_mn_major ? 1 : 0) << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
-                             ((uint32_t)(TC_BLOCK_M >> 4) << 24);
+    if (lane == 0 && CTA2 && rank == 1) {
+      // rank 1 issues no MMAs: it tells rank 0 when its own operands of a stage have landed
+      const uint32_t remote_pfull0 = mapa_u32(pfull0, 0);
       int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
         int64_t r = tile % tiles_per_group;
         const int z = (int)(r % p.split_k);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full0 + 8 * stage, phase);
+          mbar_arrive_cluster(remote_pfull0 + 8 * stage);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
+      // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn_major ? 1 : 0) << 15) |
+                             ((uint32_t)(p.b_mn_major ? 1 : 0) << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
+                             ((uint32_t)((CTA2 ? 2 * TC_BLOCK_M : TC_BLOCK_M) >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
+        int64_t r = tile % tiles_per_group;
+        const int z = (int)(r % p.split_k);
+        const int kb0 = z * p.kb_per_split;
+        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        if (CTA2) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1); else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full0 + 8 * stage, phase);
+          if (CTA2) mbar_wait_cluster(pfull0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
 #pragma unroll
@@ -286,12 +354,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             // K-major: 16 bf16 = 32 bytes further inside the 128-byte swizzle row; MN-major: 16 k-rows = 2048 bytes further
             const uint64_t ad = p.a_mn_major ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
             const uint64_t bd = p.b_mn_major ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            tc_mma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (CTA2) tc_mma2_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else tc_mma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          tc_commit(empty0 + 8 * stage);                 // frees the smem slot when these MMAs retire
+          if (CTA2) tc_commit2_mc(empty0 + 8 * stage); else tc_commit(empty0 + 8 * stage);   // frees the smem slot(s) when these MMAs retire
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        tc_commit(tfull0 + 8 * acc);                     // accumulator complete -> epilogue
+        if (CTA2) tc_commit2_mc(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc);         // accumulator complete -> epilogue(s)
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -312,12 +381,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     ec.s0 = p.drop_p > 0.f ? drop_s0(*p.seed_dev, p.salt) : 0u;
     const int n_chunks = (p.block_n + 63) >> 6;
     bool store_pending = false;
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const uint32_t tempty_target0 = (CTA2 && rank == 1) ? mapa_u32(tempty0, 0) : tempty0;
+    for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
       const int g = (int)(tile / tiles_per_group);
       int64_t r = tile % tiles_per_group;
       const int z = (int)(r % p.split_k); r /= p.split_k;
-      const int nt = (int)(r % p.n_tiles_n), mt = (int)(r / p.n_tiles_n);
-      const int64_t m = (int64_t)mt * TC_BLOCK_M + q * 32 + lane;
+      const int nt = (int)(r % p.n_tiles_n);
+      const int64_t mt = CTA2 ? 2 * (r / p.n_tiles_n) + rank : r / p.n_tiles_n;
+      const int64_t m = mt * TC_BLOCK_M + q * 32 + lane;
       const int64_t n0 = (int64_t)nt * p.block_n;
       float* bias_t = bias_s + acc * TC_MAX_N;
       const bool use_bias = p.bias != nullptr && z == 0;
@@ -330,7 +401,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
       }
       epi_bar_sync();                                    // bias tile visible; also keeps the 8 warps within one tile of each other
-      mbar_wait(tfull0 + 8 * acc, acc_phase);
+      if (CTA2) mbar_wait_cluster(tfull0 + 8 * acc, acc_phase); else mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
       for (int ci = half; ci < n_chunks; ci += 2) {
@@ -506,13 +577,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (lane == 0) { if (CTA2) mbar_arrive_cluster(tempty_target0 + 8 * acc); else mbar_arrive(tempty0 + 8 * acc); }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (store_pending && lane == 0) tma_store_wait_all();   // global writes complete before the kernel ends
   }
   tc_fence_before();
   __syncthreads();
+  if (CTA2) cluster_sync_all();                        // neither CTA leaves while its partner may still signal it or read its smem
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -546,6 +618,9 @@ __global__ void transpose_bf16_kernel(const uint16_t* __restrict__ src, int64_t 
     if (c < cols && r < rows) dst[c * ldd + r] = tile[threadIdx.x][i];
   }
 }
+
+// 0 = CTA pairs (cta_group::2) wherever the tile shape allows, 1 = single-CTA tiles only
+static std::atomic<int> g_tc_mode{0};
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -624,9 +699,15 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
     CDC_REQUIRE(false, "split_k exceeds the number of non-empty K slices; use cdcmdr_gemm_bf16_tc_splits() to size it");
   }
 
+  // CTA pairs (cta_group::2) when the tile shape allows halving B between the two CTAs and there are at least two row tiles
+  const int mode = g_tc_mode.load(std::memory_order_relaxed);
+  const bool pair_ok = p->M > TC_BLOCK_M && (q.b_mn_major ? bn % 128 == 0 : bn % 32 == 0);
+  const bool cta2 = mode == 1 ? false : pair_ok;
+  if (cta2) q.n_tiles_m = (int)ceil_div(p->M, 2 * TC_BLOCK_M);
+  const int b_cols = cta2 ? bn / 2 : bn;
   CUtensorMap ma, mb, mc;
   if (int rc = make_map(&ma, p->A, p->a_rows, p->a_cols, p->lda, q.a_mn_major ? 64u : (uint32_t)TC_BLOCK_M)) return rc;
-  if (int rc = make_map(&mb, p->Bt, p->b_rows, p->b_cols, p->ldb, q.b_mn_major ? 64u : (uint32_t)bn)) return rc;
+  if (int rc = make_map(&mb, p->Bt, p->b_rows, p->b_cols, p->ldb, q.b_mn_major ? 64u : (uint32_t)b_cols)) return rc;
   // bf16 output through TMA stores when its layout allows a tensor map (16-byte aligned base / pitch / group offsets)
   q.tma_store = (p->n_main > 0 && ((uintptr_t)p->out_main % 16) == 0 && p->ld_main % 8 == 0 && p->main_gn % 8 == 0 &&
                  (p->G - 1) * p->main_gn + p->n_main <= p->ld_main && p->M < (int64_t)1 << 31) ? 1 : 0;
@@ -642,7 +723,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   if (q.tma_aux) {
     if (int rc = make_map(&md, p->out_aux, p->M, (p->G - 1) * p->aux_gn + n_aux, p->ld_aux, 32u, true)) return rc;
   }
-  const int b_bytes = (q.b_mn_major ? (int)ceil_div(bn, 64) * 64 : bn) * TC_BLOCK_K * 2;
+  const int b_bytes = (q.b_mn_major ? (int)ceil_div(b_cols, 64) * 64 : b_cols) * TC_BLOCK_K * 2;
   q.stage_bytes = TC_A_BYTES + b_bytes;
   const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES;
   int stages = (TC_SMEM_LIMIT - fixed) / q.stage_bytes;
@@ -653,14 +734,36 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
 
   static bool attr_set = false;
   if (!attr_set) {
-    CDC_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    CDC_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
+    CDC_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_set = true;
   }
   const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
-  const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-  gemm_bf16_tc_kernel<<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, q);
+  if (!cta2) {
+    const int grid = (int)(total < kNumSMs ? total : kNumSMs);
+    gemm_bf16_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, q);
+    CDC_LAUNCHED();
+    return 0;
+  }
+  const int64_t clusters = total < kNumSMs / 2 ? total : kNumSMs / 2;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * clusters), 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = to_stream(s);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  CDC_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<true>, ma, mb, mc, md, q));
   CDC_LAUNCHED();
   return 0;
+}
+
+extern "C" int cdcmdr_gemm_bf16_tc_mode(int mode) {
+  const int old = g_tc_mode.load(std::memory_order_relaxed);
+  if (mode >= 0) g_tc_mode.store(mode == 1 ? 1 : 0, std::memory_order_relaxed);
+  return old;
 }
 
 extern "C" int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want) {

@@ -137,6 +137,10 @@ typedef struct {
 } cdcmdr_gemm_bf16_t;
 int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t s);
 int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want);
+/* Tile mode of cdcmdr_gemm_bf16_tc: 0 (default) = CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles, B operand split between
+ * the two SMs of a pair) wherever the shape allows, 1 = single-CTA 128 x block_n tiles only; mode < 0 only queries.
+ * Returns the previous mode.  Both modes compute the same values (same K order per output element). */
+int cdcmdr_gemm_bf16_tc_mode(int mode);
 /* out[r*ld_out + c] (+)= sum_z part[z*stride + r*ld_part + c]   (deterministic order) */
 int cdcmdr_splitk_reduce(const float* part, int64_t stride, int32_t splits, float* out, int64_t rows, int64_t cols,
                          int64_t ld_part, int64_t ld_out, int32_t accumulate, cdcmdr_stream_t s);

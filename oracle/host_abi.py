@@ -204,6 +204,9 @@ class HostABI:
         return 0
 
     # ------------------------------------------------------------------ bf16 tensor-core GEMM (same call sites, bf16 operands)
+    def gemm_bf16_tc_mode(self, mode):
+        return 0
+
     def gemm_bf16_tc_splits(self, K, want):
         nkb = -(-int(K) // 64)
         s_ = max(1, min(int(want), nkb))

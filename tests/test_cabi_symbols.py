@@ -43,5 +43,5 @@ def test_library_loads_and_reports_version():
 def test_struct_sizes_match_header():
     import ctypes as C
     assert cm._lib.STEP_STATE_BYTES == 48
-    assert C.sizeof(cm._lib.MixDesc) == 16 + 3 * 8
+    assert C.sizeof(cm._lib.MixDesc) == 16 + 3 * 8 + 8          # + n_pairs (int32) padded to the pointer alignment
     assert C.sizeof(cm._lib.BnDesc) == 8 * 8 + 8 + 4 + 4 + 8 + 8

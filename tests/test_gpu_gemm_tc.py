@@ -28,11 +28,23 @@ CASES = {
     "wgrad_split_k": (200, 130, 8192, 1, 1, 1, 0, dict(split_k=6)),
     "wgrad_grouped": (128, 256, 2048, 4, 1, 1, 0, dict(a_gm=128, b_gn=256, aux_gn=256 * 128, split_k=3, group_rows=True)),
     "tiny": (5, 16, 8, 1, 0, 0, -1, {}),
+    "pair_odd_row_tiles": (128 * 5 + 17, 256, 200, 1, 0, 0, -1, dict(bias=True, act=1)),
+    "pair_aux_f32": (1024, 320, 96, 1, 0, 0, 0, dict(bias=True)),
+    "pair_many_tiles": (128 * 40, 512, 64, 1, 0, 0, -1, {}),
 }
 
 
+@pytest.fixture(params=[0, 1], ids=["cta_pairs", "single_cta"])
+def tc_mode(request):
+    """cdcmdr_gemm_bf16_tc tile mode: CTA pairs (cta_group::2) where the shape allows / single-CTA tiles only."""
+    lib = cm._lib.load()
+    old = lib.gemm_bf16_tc_mode(request.param)
+    yield request.param
+    lib.gemm_bf16_tc_mode(old)
+
+
 @pytest.mark.parametrize("name", sorted(CASES))
-def test_gemm_bf16_tc(name):
+def test_gemm_bf16_tc(name, tc_mode):
     M, N, K, G, a_mn, b_mn, n_main, ex = CASES[name]
     n_main = N if n_main < 0 else n_main
 
