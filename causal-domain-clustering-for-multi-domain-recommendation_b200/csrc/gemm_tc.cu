@@ -64,6 +64,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                ::"r"(dst), "l"(map), "r"(bar), "r"(x), "r"(y) : "memory");
 }
+// cta_group::2 form: the data lands in THIS CTA's shared memory, the completion bytes are counted on a barrier that may live in
+// the partner CTA (address in the shared::cluster window) - rank 1's loads signal rank 0's "stage full" barrier directly
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_cluster, int32_t x, int32_t y) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(x), "r"(y) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int32_t x, int32_t y) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(x), "r"(y) : "memory");
@@ -237,8 +243,9 @@ __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], cons
 // rows of A and HALF of the B tile (block_n/2 rows of N), rank 0 issues tcgen05.mma.cta_group::2 (M = 256) which reads both CTAs'
 // shared memory and writes each CTA's 128 accumulator rows into that CTA's TMEM; both CTAs run their own epilogue.  Per CTA and
 // k-block that is 16 + 16 KB of operands instead of 16 + 32 KB - the level-0 GEMMs are bound by exactly that L2 -> SM traffic.
-// Cross-CTA signalling: rank 1 relays "my stage is full" to rank 0 (remote mbarrier arrive), rank 0's tcgen05.commit multicasts
-// "stage free" / "accumulator ready" to both CTAs, both epilogues arrive on rank 0's "accumulator drained" barrier.
+// Cross-CTA signalling: both CTAs' TMA loads count their bytes on rank 0's "stage full" barrier (cp.async.bulk.tensor
+// .cta_group::2), rank 0's tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs, both epilogues arrive on
+// rank 0's "accumulator drained" barrier.
 template <bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
@@ -287,6 +294,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const uint32_t full_pair0 = CTA2 ? mapa_u32(full0, 0) : full0;               // rank 0's "stage full" barriers
       for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
         const int g = (int)(tile / tiles_per_group);
         int64_t r = tile % tiles_per_group;
@@ -300,9 +308,20 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int kb = kb0; kb < kb1; ++kb) {
           if (CTA2) mbar_wait_cluster(empty0 + 8 * stage, phase ^ 1); else mbar_wait(empty0 + 8 * stage, phase ^ 1);
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
+          const int32_t ak = (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), bk = (int32_t)(g * p.b_gk + (int64_t)kb * TC_BLOCK_K);
+          if (CTA2) {
+            // both CTAs' bytes are counted on rank 0's barrier of this stage; rank 0 announces the total
+            const uint32_t bar = full_pair0 + 8 * stage;
+            if (rank == 0) mbar_expect_tx(full0 + 8 * stage, 2 * stage_tx);
+            if (!p.a_mn_major) tma_load_2d_pair(sa, &map_a, bar, ak, a_mn);
+            else { tma_load_2d_pair(sa, &map_a, bar, a_mn, ak); tma_load_2d_pair(sa + 8192, &map_a, bar, a_mn + 64, ak); }
+            if (!p.b_mn_major) tma_load_2d_pair(sb, &map_b, bar, bk, b_mn);
+            else for (int j = 0; j * 64 < b_cols; ++j) tma_load_2d_pair(sb + 8192 * j, &map_b, bar, b_mn + 64 * j, bk);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const uint32_t bar = full0 + 8 * stage;
           mbar_expect_tx(bar, stage_tx);
-          const int32_t ak = (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), bk = (int32_t)(g * p.b_gk + (int64_t)kb * TC_BLOCK_K);
           if (!p.a_mn_major) tma_load_2d(sa, &map_a, bar, ak, a_mn);                    // box [128 rows (m) x 64 (k)]
           else { tma_load_2d(sa, &map_a, bar, a_mn, ak); tma_load_2d(sa + 8192, &map_a, bar, a_mn + 64, ak); }   // 2 x [64 (k) x 64 (m)]
           if (!p.b_mn_major) tma_load_2d(sb, &map_b, bar, bk, b_mn);                    // box [b_cols rows (n) x 64 (k)]
@@ -313,21 +332,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0 && CTA2 && rank == 1) {
-      // rank 1 issues no MMAs: it tells rank 0 when its own operands of a stage have landed
-      const uint32_t remote_pfull0 = mapa_u32(pfull0, 0);
-      int stage = 0; uint32_t phase = 0;
-      for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
-        int64_t r = tile % tiles_per_group;
-        const int z = (int)(r % p.split_k);
-        const int kb0 = z * p.kb_per_split;
-        const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full0 + 8 * stage, phase);
-          mbar_arrive_cluster(remote_pfull0 + 8 * stage);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
-        }
-      }
+    if (CTA2 && rank == 1) {
+      // rank 1 issues no MMAs; its operand loads are counted on rank 0's barriers by the TMA unit itself
     } else if (lane == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
       // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
@@ -345,8 +351,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
         for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(full0 + 8 * stage, phase);
-          if (CTA2) mbar_wait_cluster(pfull0 + 8 * stage, phase);
+          if (CTA2) mbar_wait_cluster(full0 + 8 * stage, phase); else mbar_wait(full0 + 8 * stage, phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
 #pragma unroll
@@ -619,7 +624,7 @@ __global__ void transpose_bf16_kernel(const uint16_t* __restrict__ src, int64_t 
   }
 }
 
-// 0 = CTA pairs (cta_group::2) wherever the tile shape allows, 1 = single-CTA tiles only
+// bit 0: single-CTA tiles only; bit 2: CTA pairs whenever legal (default 0: pairs only for long K loops)
 static std::atomic<int> g_tc_mode{0};
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
@@ -702,7 +707,8 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   // CTA pairs (cta_group::2) when the tile shape allows halving B between the two CTAs and there are at least two row tiles
   const int mode = g_tc_mode.load(std::memory_order_relaxed);
   const bool pair_ok = p->M > TC_BLOCK_M && (q.b_mn_major ? bn % 128 == 0 : bn % 32 == 0);
-  const bool cta2 = mode == 1 ? false : pair_ok;
+  // auto: pairs pay off once a tile's K loop is long enough to hide the cross-CTA hand-offs (probe: +8 % at 128 k-blocks, -20 % at 6)
+  const bool cta2 = (mode & 1) ? false : ((mode & 4) ? pair_ok : (pair_ok && q.kb_per_split >= 32));
   if (cta2) q.n_tiles_m = (int)ceil_div(p->M, 2 * TC_BLOCK_M);
   const int b_cols = cta2 ? bn / 2 : bn;
   CUtensorMap ma, mb, mc;
@@ -762,7 +768,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
 
 extern "C" int cdcmdr_gemm_bf16_tc_mode(int mode) {
   const int old = g_tc_mode.load(std::memory_order_relaxed);
-  if (mode >= 0) g_tc_mode.store(mode == 1 ? 1 : 0, std::memory_order_relaxed);
+  if (mode >= 0) g_tc_mode.store(mode & 7, std::memory_order_relaxed);
   return old;
 }
 

@@ -137,9 +137,13 @@ typedef struct {
 } cdcmdr_gemm_bf16_t;
 int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t s);
 int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want);
-/* Tile mode of cdcmdr_gemm_bf16_tc: 0 (default) = CTA pairs (tcgen05 cta_group::2, 256 x block_n tiles, B operand split between
- * the two SMs of a pair) wherever the shape allows, 1 = single-CTA 128 x block_n tiles only; mode < 0 only queries.
- * Returns the previous mode.  Both modes compute the same values (same K order per output element). */
+/* Tuning switches of cdcmdr_gemm_bf16_tc (bit mask; mode < 0 only queries; returns the previous mask).  Every combination computes
+ * the same values (same K order per output element):
+ *   bit 0  single-CTA 128 x block_n tiles only
+ *   bit 2  CTA pairs (tcgen05 cta_group::2: 256 x block_n tiles, B operand split between the two SMs of a pair) whenever the tile
+ *          shape allows; default (neither bit): pairs only when a tile's K loop has >= 32 k-blocks
+ * (Measured on B200: pairs +8 % at 128 k-blocks per tile, -20 % at 6; reading staged tiles back for coalesced st.global instead of
+ * TMA stores was 15-25 % slower and was removed.) */
 int cdcmdr_gemm_bf16_tc_mode(int mode);
 /* out[r*ld_out + c] (+)= sum_z part[z*stride + r*ld_part + c]   (deterministic order) */
 int cdcmdr_splitk_reduce(const float* part, int64_t stride, int32_t splits, float* out, int64_t rows, int64_t cols,

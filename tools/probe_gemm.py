@@ -15,15 +15,20 @@ lib.step_state_init(st.data_ptr(), 1, 0)
 seed_ptr = st.data_ptr() + 8
 
 
-def run(name, M, N, K, a_mn=0, b_mn=0, out="bf16", act=0, drop=0.0, bias=True, mask=False, split=1, block_n=0, reps=10):
+def run(name, M, N, K, a_mn=0, b_mn=0, out="bf16", act=0, drop=0.0, bias=True, mask=False, split=1, block_n=0, reps=10, pad=0, mode=None):
+    """pad: round the operands' row pitch up to a multiple of `pad` elements (logical shape unchanged)"""
+    def pitch(n):
+        return (n + pad - 1) // pad * pad if pad else n
+    if mode is not None:
+        lib.gemm_bf16_tc_mode(mode)
     if a_mn:
-        A = torch.randn(K, M, device=dev).to(torch.bfloat16); lda, ar, ac = M, K, M
+        A = torch.randn(K, pitch(M), device=dev).to(torch.bfloat16); lda, ar, ac = pitch(M), K, M
     else:
-        A = torch.randn(M, K, device=dev).to(torch.bfloat16); lda, ar, ac = K, M, K
+        A = torch.randn(M, pitch(K), device=dev).to(torch.bfloat16); lda, ar, ac = pitch(K), M, K
     if b_mn:
-        B = torch.randn(K, N, device=dev).to(torch.bfloat16); ldb, br, bc = N, K, N
+        B = torch.randn(K, pitch(N), device=dev).to(torch.bfloat16); ldb, br, bc = pitch(N), K, N
     else:
-        B = torch.randn(N, K, device=dev).to(torch.bfloat16); ldb, br, bc = K, N, K
+        B = torch.randn(N, pitch(K), device=dev).to(torch.bfloat16); ldb, br, bc = pitch(K), N, K
     bias_t = torch.randn(N, device=dev) if bias else None
     n_main = N if out == "bf16" else 0
     om = torch.empty(M, N, device=dev, dtype=torch.bfloat16) if n_main else None
@@ -46,7 +51,9 @@ def run(name, M, N, K, a_mn=0, b_mn=0, out="bf16", act=0, drop=0.0, bias=True, m
     us = e0.elapsed_time(e1) * 1e3 / reps
     tf = 2.0 * M * N * K / (us * 1e-6) / 1e12
     by = (M * K + N * K) * 2 + M * N * (2 if n_main else 4 * s) + (M * N * 2 if mask else 0)
-    print(json.dumps(dict(name=name, M=M, N=N, K=K, us=round(us, 1), tflops=round(tf, 1), gbs=round(by / us / 1e3, 1))), flush=True)
+    print(json.dumps(dict(name=name, M=M, N=N, K=K, us=round(us, 1), tflops=round(tf, 1), gbs=round(by / us / 1e3, 1), pad=pad, mode=mode)), flush=True)
+    if mode is not None:
+        lib.gemm_bf16_tc_mode(0)
 
 
 B = 65536
@@ -57,6 +64,12 @@ if ONLY:
     def run(name, *a, **k):            # noqa: F811
         if name.startswith(ONLY):
             _run(name, *a, **k)
+for md in (1, 4):
+    for pd in (0, 64):
+        run("align_l0_fwd_plain", B, 2560, 368, bias=False, pad=pd, mode=md)
+        run("align_l0_fwd_full", B, 2560, 368, act=1, drop=0.2, pad=pd, mode=md)
+        run("align_l0_dgrad", B, 368, 2560, b_mn=1, out="f32", pad=pd, mode=md)
+        run("align_l0_wgrad", 2560, 368, B, a_mn=1, b_mn=1, out="f32", split=6, pad=pd, mode=md)
 run("l0_fwd_plain", B, 2560, 368, bias=False)
 run("l0_fwd_bias", B, 2560, 368)
 run("l0_fwd_bias_relu", B, 2560, 368, act=1)
