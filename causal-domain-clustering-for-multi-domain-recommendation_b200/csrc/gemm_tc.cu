@@ -374,8 +374,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int ew = warp - 2;                             // 0..7
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int half = ew >> 2;                            // which of the two warps of the quarter
-    const int et = threadIdx.x - 64;                     // 0..255
     uint8_t* my_stage = staging + ew * TC_STAGING_WARP_BYTES;
+    float* bias_t = bias_s + ew * 64;                    // this warp's bias slice: the 64 columns of the chunk in flight
     const uint32_t my_stage_u32 = smem_u32(my_stage);
     int acc = 0; uint32_t acc_phase = 0;
     EpiCtx ec;
@@ -395,17 +395,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int64_t mt = CTA2 ? 2 * (r / p.n_tiles_n) + rank : r / p.n_tiles_n;
       const int64_t m = mt * TC_BLOCK_M + q * 32 + lane;
       const int64_t n0 = (int64_t)nt * p.block_n;
-      float* bias_t = bias_s + acc * TC_MAX_N;
       const bool use_bias = p.bias != nullptr && z == 0;
-      if (use_bias) {
-        // columns that take the dropout fold (bf16 main part) hold bias * keep_scale; aux columns (fp32, no dropout) the plain bias
-        if (et < p.block_n) {
-          float bv = (n0 + et < p.N) ? __ldg(p.bias + g * p.bias_gs + n0 + et) : 0.f;
-          if (ec.has_drop && n0 + et < p.n_main) bv *= ec.keep_scale;
-          bias_t[et] = bv;
-        }
-      }
-      epi_bar_sync();                                    // bias tile visible; also keeps the 8 warps within one tile of each other
       if (CTA2) mbar_wait_cluster(tfull0 + 8 * acc, acc_phase); else mbar_wait(tfull0 + 8 * acc, acc_phase);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
@@ -414,6 +404,19 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int64_t nb = n0 + c0;                      // first global column of the chunk
         if (nb >= p.N) break;
         const int cw = (int)min((int64_t)64, min((int64_t)p.block_n - c0, p.N - nb));     // valid columns in this chunk
+        if (use_bias) {
+          // this warp's 64 bias values of the chunk, in its private slice (no CTA-wide barrier per tile).  Columns that take the
+          // dropout fold (bf16 main part) hold bias * keep_scale; aux columns (fp32, no dropout) the plain bias.
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int64_t col = nb + 2 * lane + j;
+            float bv = col < p.N ? __ldg(p.bias + g * p.bias_gs + col) : 0.f;
+            if (ec.has_drop && col < p.n_main) bv *= ec.keep_scale;
+            bias_t[2 * lane + j] = bv;
+          }
+          __syncwarp();
+        }
         const bool full_main = nb + 64 <= p.n_main && cw == 64;
         // a chunk cut short by the END OF THE MATRIX may still go through TMA: the store map clips columns >= N
         const bool clip_ok = p.G == 1 && p.n_main == p.N && !p.mask && !p.accumulate && nb + cw == p.N;
@@ -440,27 +443,32 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 8; ++j) old[j] = make_uint4(0, 0, 0, 0);
           }
-          if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
-          __syncwarp();
           tc_ld_wait();
           const uint32_t gcol = (uint32_t)(g * p.main_gn + nb);
+          uint32_t o[2][16];
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            uint32_t o[16];
             if (hh == 0 || cw > 32) {
               float f[32];
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[32 * hh + j]);
-              epi_math32(ec, f, use_bias ? bias_t + c0 + 32 * hh : nullptr, mk + 4 * hh, old + 4 * hh, (uint32_t)m, gcol + 32 * hh, o);
+              epi_math32(ec, f, use_bias ? bias_t + 32 * hh : nullptr, mk + 4 * hh, old + 4 * hh, (uint32_t)m, gcol + 32 * hh, o[hh]);
             } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = 0u;
+              for (int j = 0; j < 16; ++j) o[hh][j] = 0u;
             }
-            // row `lane` of the warp's [32 x 128 B] staging tile; 16-byte chunk index XOR (row % 8) = SWIZZLE_128B
+          }
+          // the epilogue math above overlapped the bulk engine still reading the previous chunk out of the staging buffer
+          if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
+          __syncwarp();
+          // row `lane` of the warp's [32 x 128 B] staging tile; 16-byte chunk index XOR (row % 8) = SWIZZLE_128B
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int chunk = (4 * hh + j) ^ (lane & 7);
-              *reinterpret_cast<uint4*>(my_stage + lane * 128 + chunk * 16) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              *reinterpret_cast<uint4*>(my_stage + lane * 128 + chunk * 16) =
+                  make_uint4(o[hh][4 * j], o[hh][4 * j + 1], o[hh][4 * j + 2], o[hh][4 * j + 3]);
             }
           }
           fence_async_smem();
@@ -494,7 +502,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int j = 0; j < 8; ++j) {
               float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
               if (use_bias) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_t + c0 + s0c + 4 * j);
+                const float4 b = *reinterpret_cast<const float4*>(bias_t + s0c + 4 * j);
                 o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
               }
               o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w;
@@ -529,7 +537,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             if (use_bias) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += bias_t[c0 + s0c + j];
+              for (int j = 0; j < 32; ++j) f[j] += bias_t[s0c + j];
             }
             if (n_mainc > 0) {
               if (p.act == 1) {
