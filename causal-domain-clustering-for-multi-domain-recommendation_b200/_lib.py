@@ -87,6 +87,7 @@ SIGNATURES = {
     "cdcmdr_gemm_bf16_tc": (INT, [C.POINTER(GemmBf16), P]),
     "cdcmdr_gemm_bf16_tc_splits": (INT, [I64, I32]),
     "cdcmdr_gemm_bf16_tc_mode": (INT, [INT]),
+    "cdcmdr_gemm_bf16_tc_profile": (INT, [P]),
     "cdcmdr_splitk_reduce": (INT, [P, I64, I32, P, I64, I64, I64, I64, I32, P]),
     "cdcmdr_transpose_bf16": (INT, [P, I64, P, I64, I64, I64, P]),
     "cdcmdr_gate_mix_fwd": (INT, [C.POINTER(MixDesc), P, I64, P, I64, P, I64, P, I64, INT, P]),

@@ -170,9 +170,16 @@ struct TcParams {
   int32_t accumulate;
   int32_t tma_store;                         // out_main is written through map_c (alignment checked by the host)
   int32_t tma_aux;                           // out_aux (fp32) is written through map_d
+  unsigned long long* prof;                  // diagnostics: cycles spent in each pipeline wait, summed over CTAs (NULL = off)
 };
 
 // Epilogue math for 32 consecutive columns [col0, col0+32) of one row; f in/out.  Returns packed bf16 pairs in o[16].
+// cycle counters of cdcmdr_gemm_bf16_tc_profile: [0] producer waits for a free stage, [1] MMA waits for a drained accumulator,
+// [2] MMA waits for operands, [3] epilogue warp 0 waits for an accumulator, [4] epilogue warp 0 waits for the staging buffer,
+// [5] epilogue warp 0 busy (total loop time), [6] CTA lifetime, [7] number of CTAs
+#define TC_PROF_T0() const long long prof_t0 = p.prof ? clock64() : 0
+#define TC_PROF_ADD(i) do { if (p.prof) atomicAdd(p.prof + (i), (unsigned long long)(clock64() - prof_t0)); } while (0)
+
 struct EpiCtx {
   int act; float mask_scale; bool has_mask, has_drop, has_old; uint32_t s0, thr32; float keep_scale;
 };
@@ -260,6 +267,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_MAX_STAGES + 4);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const long long prof_cta0 = p.prof ? clock64() : 0;
   const int64_t tile0 = CTA2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
   const int64_t tile_step = CTA2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
@@ -306,7 +314,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int32_t a_mn = (int32_t)(g * p.a_gmn + mt * TC_BLOCK_M);
         const int32_t b_mn = (int32_t)(g * p.b_gmn + (int64_t)nt * p.block_n + (CTA2 ? (int64_t)rank * b_cols : 0));
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (CTA2) mbar_wait_cluster(empty0 + 8 * stage, phase ^ 1); else mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          { TC_PROF_T0();
+            if (CTA2) mbar_wait_cluster(empty0 + 8 * stage, phase ^ 1); else mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            TC_PROF_ADD(0); }
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
           const int32_t ak = (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), bk = (int32_t)(g * p.b_gk + (int64_t)kb * TC_BLOCK_K);
           if (CTA2) {
@@ -347,11 +357,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int z = (int)(r % p.split_k);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
-        if (CTA2) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1); else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+        { TC_PROF_T0();
+          if (CTA2) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1); else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
+          TC_PROF_ADD(1); }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (CTA2) mbar_wait_cluster(full0 + 8 * stage, phase); else mbar_wait(full0 + 8 * stage, phase);
+          { TC_PROF_T0();
+            if (CTA2) mbar_wait_cluster(full0 + 8 * stage, phase); else mbar_wait(full0 + 8 * stage, phase);
+            TC_PROF_ADD(2); }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
 #pragma unroll
@@ -387,6 +401,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const int n_chunks = (p.block_n + 63) >> 6;
     bool store_pending = false;
     const uint32_t tempty_target0 = (CTA2 && rank == 1) ? mapa_u32(tempty0, 0) : tempty0;
+    const long long prof_epi0 = p.prof ? clock64() : 0;
     for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
       const int g = (int)(tile / tiles_per_group);
       int64_t r = tile % tiles_per_group;
@@ -396,7 +411,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int64_t m = mt * TC_BLOCK_M + q * 32 + lane;
       const int64_t n0 = (int64_t)nt * p.block_n;
       const bool use_bias = p.bias != nullptr && z == 0;
-      if (CTA2) mbar_wait_cluster(tfull0 + 8 * acc, acc_phase); else mbar_wait(tfull0 + 8 * acc, acc_phase);
+      { TC_PROF_T0();
+        if (CTA2) mbar_wait_cluster(tfull0 + 8 * acc, acc_phase); else mbar_wait(tfull0 + 8 * acc, acc_phase);
+        if (ew == 0 && lane == 0) TC_PROF_ADD(3); }
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
       for (int ci = half; ci < n_chunks; ci += 2) {
@@ -404,6 +421,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int64_t nb = n0 + c0;                      // first global column of the chunk
         if (nb >= p.N) break;
         const int cw = (int)min((int64_t)64, min((int64_t)p.block_n - c0, p.N - nb));     // valid columns in this chunk
+        const long long prof_b0 = p.prof ? clock64() : 0;
         if (use_bias) {
           // this warp's 64 bias values of the chunk, in its private slice (no CTA-wide barrier per tile).  Columns that take the
           // dropout fold (bf16 main part) hold bias * keep_scale; aux columns (fp32, no dropout) the plain bias.
@@ -416,6 +434,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             bias_t[2 * lane + j] = bv;
           }
           __syncwarp();
+          if (p.prof && ew == 0 && lane == 0) atomicAdd(p.prof + 11, (unsigned long long)(clock64() - prof_b0));
         }
         const bool full_main = nb + 64 <= p.n_main && cw == 64;
         // a chunk cut short by the END OF THE MATRIX may still go through TMA: the store map clips columns >= N
@@ -443,7 +462,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 8; ++j) old[j] = make_uint4(0, 0, 0, 0);
           }
-          tc_ld_wait();
+          { TC_PROF_T0(); tc_ld_wait(); if (ew == 0 && lane == 0) TC_PROF_ADD(8); }
+          const long long prof_m0 = p.prof ? clock64() : 0;
           const uint32_t gcol = (uint32_t)(g * p.main_gn + nb);
           uint32_t o[2][16];
 #pragma unroll
@@ -458,9 +478,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               for (int j = 0; j < 16; ++j) o[hh][j] = 0u;
             }
           }
+          if (p.prof && ew == 0 && lane == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - prof_m0));
           // the epilogue math above overlapped the bulk engine still reading the previous chunk out of the staging buffer
-          if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
+          if (store_pending) {
+            if (lane == 0) { TC_PROF_T0(); tma_store_wait_read0(); if (ew == 0) TC_PROF_ADD(4); }
+            store_pending = false;
+          }
           __syncwarp();
+          const long long prof_s0 = p.prof ? clock64() : 0;
           // row `lane` of the warp's [32 x 128 B] staging tile; 16-byte chunk index XOR (row % 8) = SWIZZLE_128B
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
@@ -476,6 +501,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (lane == 0) {
             tma_store_2d(&map_c, my_stage_u32, (int32_t)gcol, (int32_t)((int64_t)mt * TC_BLOCK_M + q * 32));
             tma_store_commit();
+            if (p.prof && ew == 0) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - prof_s0));
           }
           store_pending = true;
           continue;
@@ -594,10 +620,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (store_pending && lane == 0) tma_store_wait_all();   // global writes complete before the kernel ends
+    if (p.prof && ew == 0 && lane == 0) atomicAdd(p.prof + 5, (unsigned long long)(clock64() - prof_epi0));
   }
   tc_fence_before();
   __syncthreads();
   if (CTA2) cluster_sync_all();                        // neither CTA leaves while its partner may still signal it or read its smem
+  if (p.prof && threadIdx.x == 0) { atomicAdd(p.prof + 6, (unsigned long long)(clock64() - prof_cta0)); atomicAdd(p.prof + 7, 1ull); }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
@@ -634,6 +662,7 @@ __global__ void transpose_bf16_kernel(const uint16_t* __restrict__ src, int64_t 
 
 // bit 0: single-CTA tiles only; bit 2: CTA pairs whenever legal (default 0: pairs only for long K loops)
 static std::atomic<int> g_tc_mode{0};
+static std::atomic<unsigned long long*> g_tc_prof{nullptr};
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -713,6 +742,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   }
 
   // CTA pairs (cta_group::2) when the tile shape allows halving B between the two CTAs and there are at least two row tiles
+  q.prof = g_tc_prof.load(std::memory_order_relaxed);
   const int mode = g_tc_mode.load(std::memory_order_relaxed);
   const bool pair_ok = p->M > TC_BLOCK_M && (q.b_mn_major ? bn % 128 == 0 : bn % 32 == 0);
   // auto: pairs pay off once a tile's K loop is long enough to hide the cross-CTA hand-offs (probe: +8 % at 128 k-blocks, -20 % at 6)
@@ -771,6 +801,11 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   cfg.attrs = attr; cfg.numAttrs = 1;
   CDC_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<true>, ma, mb, mc, md, q));
   CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_gemm_bf16_tc_profile(uint64_t* counters8) {
+  g_tc_prof.store(reinterpret_cast<unsigned long long*>(counters8), std::memory_order_relaxed);
   return 0;
 }
 

@@ -145,6 +145,12 @@ int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want);
  * (Measured on B200: pairs +8 % at 128 k-blocks per tile, -20 % at 6; reading staged tiles back for coalesced st.global instead of
  * TMA stores was 15-25 % slower and was removed.) */
 int cdcmdr_gemm_bf16_tc_mode(int mode);
+/* Diagnostics: while `counters8` (device, 16 x uint64 - the first 8 documented here, [8..11] = epilogue warp 0 inside the bf16 store
+ * path: accumulator load, math, staging + store issue, bias slice - zeroed by the caller) is installed, every cdcmdr_gemm_bf16_tc launch adds
+ * the SM cycles its warps spent in each pipeline wait, summed over CTAs: [0] TMA producer waiting for a free stage, [1] MMA issuer
+ * waiting for a drained accumulator, [2] MMA issuer waiting for operands, [3] epilogue warp 0 waiting for an accumulator,
+ * [4] epilogue warp 0 waiting for its staging buffer, [5] epilogue warp 0 lifetime, [6] CTA lifetime, [7] CTAs.  NULL switches it off. */
+int cdcmdr_gemm_bf16_tc_profile(uint64_t* counters8);
 /* out[r*ld_out + c] (+)= sum_z part[z*stride + r*ld_part + c]   (deterministic order) */
 int cdcmdr_splitk_reduce(const float* part, int64_t stride, int32_t splits, float* out, int64_t rows, int64_t cols,
                          int64_t ld_part, int64_t ld_out, int32_t accumulate, cdcmdr_stream_t s);

@@ -207,6 +207,9 @@ class HostABI:
     def gemm_bf16_tc_mode(self, mode):
         return 0
 
+    def gemm_bf16_tc_profile(self, counters):
+        return 0
+
     def gemm_bf16_tc_splits(self, K, want):
         nkb = -(-int(K) // 64)
         s_ = max(1, min(int(want), nkb))

@@ -49,9 +49,22 @@ def run(name, M, N, K, a_mn=0, b_mn=0, out="bf16", act=0, drop=0.0, bias=True, m
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 1e3 / reps
+    prof = None
+    if os.environ.get("PROBE_PROF"):
+        cnt = torch.zeros(16, dtype=torch.int64, device=dev)
+        lib.gemm_bf16_tc_profile(cnt.data_ptr())
+        lib.gemm_bf16_tc(C.byref(d), 0)
+        torch.cuda.synchronize()
+        lib.gemm_bf16_tc_profile(None)
+        c = cnt.tolist()
+        n = max(c[7], 1)
+        prof = dict(cta_kcyc=round(c[6] / n / 1e3, 1), prod_wait_empty=round(c[0] / c[6], 3), mma_wait_tempty=round(c[1] / c[6], 3),
+                    mma_wait_full=round(c[2] / c[6], 3), epi_wait_tfull=round(c[3] / c[6], 3), epi_wait_stage=round(c[4] / c[6], 3),
+                    epi_life=round(c[5] / c[6], 3), epi_tmem_ld=round(c[8] / c[6], 3), epi_math=round(c[9] / c[6], 3),
+                    epi_stage_store=round(c[10] / c[6], 3), epi_bias=round(c[11] / c[6], 3))
     tf = 2.0 * M * N * K / (us * 1e-6) / 1e12
     by = (M * K + N * K) * 2 + M * N * (2 if n_main else 4 * s) + (M * N * 2 if mask else 0)
-    print(json.dumps(dict(name=name, M=M, N=N, K=K, us=round(us, 1), tflops=round(tf, 1), gbs=round(by / us / 1e3, 1), pad=pad, mode=mode)), flush=True)
+    print(json.dumps(dict(name=name, M=M, N=N, K=K, us=round(us, 1), tflops=round(tf, 1), gbs=round(by / us / 1e3, 1), pad=pad, mode=mode, prof=prof)), flush=True)
     if mode is not None:
         lib.gemm_bf16_tc_mode(0)
 
