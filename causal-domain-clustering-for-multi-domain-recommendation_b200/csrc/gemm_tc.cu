@@ -4,19 +4,22 @@
 // Replaces the nn.Linear / F.linear / autograd matmul call sites of the reference's expert, gate and tower layers
 // (layer.py:185,193; ple.py:83-94; mmoe.py:36-40) on the bf16 path.
 //
-// One persistent CTA per SM, 320 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
-// warps 2..9 = epilogue (warp w may touch TMEM lanes 32*(w%4)..+31; the two warps of a lane quarter split the tile's
-// 64-column chunks).  Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
+// One persistent CTA per SM, 576 threads: warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2..17 = epilogue (warp w may touch TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter take the tile's
+// 32-column chunks in turn).  Three mbarrier pipelines: smem full/empty (TMA <-> MMA), TMEM full/empty (MMA <-> epilogue, two
 // accumulator stages so the epilogue of tile i overlaps the MMAs of tile i+1).  Tile = 128 (M) x block_n (runtime,
 // multiple of 16, <= 256) x 64 (K); UMMA 128 x block_n x 16.  The number of smem stages is whatever fits next to the
-// 32 KB of epilogue staging (4 at block_n = 256).
+// 32 KB of epilogue staging (4 at block_n = 256).  CTA pairs (cta_group::2, 256 x block_n tiles) for long K loops.
 // Operands may be K-major (reduction index contiguous: activations / weights in the forward and input-gradient GEMMs)
 // or MN-major (reduction index is the row: weight-gradient GEMMs reduce over the batch) - both are read in place.
 //
-// Why the epilogue looks the way it does (B200, probe of 2026-10-18, M=65536 N=2560 K=368): with K this short a tile's
-// MMAs take ~3k cycles, so the epilogue is on the critical path: per-thread row stores, 32 scalar bias loads per chunk
-// and a 64-bit dropout hash per element cost 190 / 430 / 1045 us against ~75 us of MMA time.  Hence: 8 epilogue warps,
-// bias staged in smem once per tile, a 32-bit hash per column PAIR, and 128-byte-row TMA stores from swizzled staging.
+// Why the epilogue looks the way it does (B200 probes of 2026-10-18, M=65536 N=2560 K=368): with K this short a tile's MMAs
+// take ~3k cycles, so the epilogue is on the critical path.  Per-thread row stores, 32 scalar bias loads per chunk and a 64-bit
+// dropout hash per element cost 190 / 430 / 1045 us; 8 epilogue warps with 64-column chunks were still busy ~7k cycles per tile
+// (cdcmdr_gemm_bf16_tc_profile: the MMA issuer waited 25 % of the kernel for a drained accumulator).  Hence: 16 epilogue warps,
+// a per-warp bias slice, an LCG step per column for dropout, 64-byte-row TMA stores from swizzled staging: 167 us, the MMA
+// issuer now waits < 3 % for the epilogue and the tile is bound by the tensor pipe's operand reads competing with the TMA fills
+// and the staging traffic for shared-memory bandwidth.
 #include "common.cuh"
 #include <cuda.h>
 #include <cudaTypedefs.h>
@@ -28,9 +31,9 @@ constexpr int TC_BLOCK_K = 64;                       // 64 bf16 = 128 bytes = on
 constexpr int TC_MAX_STAGES = 8;
 constexpr int TC_MAX_N = 256;
 constexpr int TC_A_BYTES = TC_BLOCK_M * TC_BLOCK_K * 2;          // 16 KB
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;               // 320
-constexpr int TC_STAGING_WARP_BYTES = 32 * 128;                  // 32 rows x 64 bf16, 128B-swizzled
+constexpr int TC_EPI_WARPS = 16;
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;               // 576
+constexpr int TC_STAGING_WARP_BYTES = 32 * 64;                   // 32 rows x 32 bf16 (or 16 fp32), 64B-swizzled
 constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * TC_STAGING_WARP_BYTES;
 constexpr int TC_BIAS_BYTES = 2 * TC_MAX_N * 4;                  // one bias tile per accumulator stage
 constexpr int TC_BAR_BYTES = 256;
@@ -384,12 +387,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
     }
   } else {
-    // =============================== epilogue (warps 2..9) ===============================
-    const int ew = warp - 2;                             // 0..7
+    // =============================== epilogue (warps 2..17) ===============================
+    // 16 warps: warp w may touch TMEM lanes 32*(w%4)..+31; the four warps of a lane quarter take the tile's 32-column chunks in
+    // turn.  The epilogue is SIMT work at one CTA per SM: it is bound by how many warps can hide each other's latencies (8 warps
+    // with 64-column chunks spent ~7 k cycles per tile against 3 k cycles of MMAs), hence many narrow chunks rather than few wide ones.
+    const int ew = warp - 2;                             // 0..15
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
-    const int half = ew >> 2;                            // which of the two warps of the quarter
-    uint8_t* my_stage = staging + ew * TC_STAGING_WARP_BYTES;
-    float* bias_t = bias_s + ew * 64;                    // this warp's bias slice: the 64 columns of the chunk in flight
+    const int sub = ew >> 2;                             // which of the four warps of the quarter
+    uint8_t* my_stage = staging + ew * TC_STAGING_WARP_BYTES;       // 32 rows x 64 B, 64B-swizzled
+    float* bias_t = bias_s + ew * 32;                    // this warp's bias slice: the 32 columns of the chunk in flight
     const uint32_t my_stage_u32 = smem_u32(my_stage);
     int acc = 0; uint32_t acc_phase = 0;
     EpiCtx ec;
@@ -398,7 +404,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     ec.thr32 = drop_thr32(p.drop_p);
     ec.keep_scale = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
     ec.s0 = p.drop_p > 0.f ? drop_s0(*p.seed_dev, p.salt) : 0u;
-    const int n_chunks = (p.block_n + 63) >> 6;
+    const int n_chunks = (p.block_n + 31) >> 5;
+    const int swz = (lane >> 1) & 3;                     // SWIZZLE_64B: 16-byte chunk index XOR ((row / 2) % 4)
     bool store_pending = false;
     const uint32_t tempty_target0 = (CTA2 && rank == 1) ? mapa_u32(tempty0, 0) : tempty0;
     const long long prof_epi0 = p.prof ? clock64() : 0;
@@ -416,200 +423,171 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (ew == 0 && lane == 0) TC_PROF_ADD(3); }
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
-      for (int ci = half; ci < n_chunks; ci += 2) {
-        const int c0 = ci * 64;
+      for (int ci = sub; ci < n_chunks; ci += 4) {
+        const int c0 = ci * 32;
         const int64_t nb = n0 + c0;                      // first global column of the chunk
         if (nb >= p.N) break;
-        const int cw = (int)min((int64_t)64, min((int64_t)p.block_n - c0, p.N - nb));     // valid columns in this chunk
-        const long long prof_b0 = p.prof ? clock64() : 0;
+        const int cw = (int)min((int64_t)32, min((int64_t)p.block_n - c0, p.N - nb));     // valid columns in this chunk
+        uint32_t v[32];
+        tc_ld32_nowait(trow + c0, v);                    // in flight while the bias slice / mask / old values are fetched
         if (use_bias) {
-          // this warp's 64 bias values of the chunk, in its private slice (no CTA-wide barrier per tile).  Columns that take the
-          // dropout fold (bf16 main part) hold bias * keep_scale; aux columns (fp32, no dropout) the plain bias.
+          // this warp's 32 bias values of the chunk, in its private slice.  Columns that take the dropout fold (bf16 main part)
+          // hold bias * keep_scale; aux columns (fp32, no dropout) the plain bias.
           __syncwarp();
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const int64_t col = nb + 2 * lane + j;
-            float bv = col < p.N ? __ldg(p.bias + g * p.bias_gs + col) : 0.f;
-            if (ec.has_drop && col < p.n_main) bv *= ec.keep_scale;
-            bias_t[2 * lane + j] = bv;
-          }
+          const int64_t col = nb + lane;
+          float bv = col < p.N ? __ldg(p.bias + g * p.bias_gs + col) : 0.f;
+          if (ec.has_drop && col < p.n_main) bv *= ec.keep_scale;
+          bias_t[lane] = bv;
           __syncwarp();
-          if (p.prof && ew == 0 && lane == 0) atomicAdd(p.prof + 11, (unsigned long long)(clock64() - prof_b0));
         }
-        const bool full_main = nb + 64 <= p.n_main && cw == 64;
+        const bool full_main = nb + 32 <= p.n_main && cw == 32;
         // a chunk cut short by the END OF THE MATRIX may still go through TMA: the store map clips columns >= N
         const bool clip_ok = p.G == 1 && p.n_main == p.N && !p.mask && !p.accumulate && nb + cw == p.N;
         if (p.tma_store && (full_main || clip_ok)) {
-          // ---------------- fast path: 64 bf16 columns per row -> swizzled staging -> TMA store ----------------
-          uint32_t v[64];
-          tc_ld32_nowait(trow + c0, v);
-          if (cw > 32) tc_ld32_nowait(trow + c0 + 32, v + 32);
-          uint4 mk[8];
+          // ---------------- fast path: 32 bf16 columns per row -> swizzled staging -> TMA store ----------------
+          uint4 mk[4], old[4];
           if (ec.has_mask && m < p.M) {
             const uint4* mp = reinterpret_cast<const uint4*>(p.mask + m * p.ld_mask + g * p.mask_gn + nb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mk[j] = __ldg(mp + j);
+            for (int j = 0; j < 4; ++j) mk[j] = __ldg(mp + j);
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) mk[j] = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 4; ++j) mk[j] = make_uint4(0, 0, 0, 0);
           }
-          uint4 old[8];
           if (ec.has_old && m < p.M) {
             const uint4* op4 = reinterpret_cast<const uint4*>(p.out_main + m * p.ld_main + g * p.main_gn + nb);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) old[j] = op4[j];
+            for (int j = 0; j < 4; ++j) old[j] = op4[j];
           } else {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) old[j] = make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < 4; ++j) old[j] = make_uint4(0, 0, 0, 0);
           }
-          { TC_PROF_T0(); tc_ld_wait(); if (ew == 0 && lane == 0) TC_PROF_ADD(8); }
-          const long long prof_m0 = p.prof ? clock64() : 0;
+          tc_ld_wait();
           const uint32_t gcol = (uint32_t)(g * p.main_gn + nb);
-          uint32_t o[2][16];
+          float f[32];
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-            if (hh == 0 || cw > 32) {
-              float f[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[32 * hh + j]);
-              epi_math32(ec, f, use_bias ? bias_t + 32 * hh : nullptr, mk + 4 * hh, old + 4 * hh, (uint32_t)m, gcol + 32 * hh, o[hh]);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[hh][j] = 0u;
-            }
-          }
-          if (p.prof && ew == 0 && lane == 0) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - prof_m0));
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          uint32_t o[16];
+          epi_math32(ec, f, use_bias ? bias_t : nullptr, mk, old, (uint32_t)m, gcol, o);
           // the epilogue math above overlapped the bulk engine still reading the previous chunk out of the staging buffer
           if (store_pending) {
             if (lane == 0) { TC_PROF_T0(); tma_store_wait_read0(); if (ew == 0) TC_PROF_ADD(4); }
             store_pending = false;
           }
           __syncwarp();
-          const long long prof_s0 = p.prof ? clock64() : 0;
-          // row `lane` of the warp's [32 x 128 B] staging tile; 16-byte chunk index XOR (row % 8) = SWIZZLE_128B
+          // row `lane` of the warp's [32 x 64 B] staging tile
 #pragma unroll
-          for (int hh = 0; hh < 2; ++hh) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int chunk = (4 * hh + j) ^ (lane & 7);
-              *reinterpret_cast<uint4*>(my_stage + lane * 128 + chunk * 16) =
-                  make_uint4(o[hh][4 * j], o[hh][4 * j + 1], o[hh][4 * j + 2], o[hh][4 * j + 3]);
-            }
-          }
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ swz) * 16)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&map_c, my_stage_u32, (int32_t)gcol, (int32_t)((int64_t)mt * TC_BLOCK_M + q * 32));
+            tma_store_2d(&map_c, my_stage_u32, (int32_t)gcol, (int32_t)(mt * TC_BLOCK_M + q * 32));
             tma_store_commit();
-            if (p.prof && ew == 0) atomicAdd(p.prof + 10, (unsigned long long)(clock64() - prof_s0));
           }
           store_pending = true;
           continue;
         }
-        // ---------------- fast fp32 path: 32 fp32 columns (128 B) per row -> swizzled staging -> TMA store ----------------
-        if (p.tma_aux && nb >= p.n_main && ((cw & 31) == 0 || (p.G == 1 && nb + cw == p.N && !p.accumulate))) {
-          for (int s0c = 0; s0c < cw; s0c += 32) {
-            uint32_t v[32];
-            tc_ld32_nowait(trow + c0 + s0c, v);
-            const int64_t nbb = nb + s0c;
-            float4 old[8];
+        // ---------------- fast fp32 path: 2 x (16 fp32 columns = 64 B per row) -> swizzled staging -> TMA store ----------------
+        if (p.tma_aux && nb >= p.n_main && ((cw & 15) == 0 || (p.G == 1 && nb + cw == p.N && !p.accumulate))) {
+          tc_ld_wait();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            if (16 * hh >= cw) break;
+            const int64_t nbb = nb + 16 * hh;
+            float4 old[4];
             if (p.accumulate && m < p.M) {
               const float4* op4 = reinterpret_cast<const float4*>(p.out_aux + m * p.ld_aux + g * p.aux_gn + (nbb - p.n_main));
 #pragma unroll
-              for (int j = 0; j < 8; ++j) old[j] = op4[j];
+              for (int j = 0; j < 4; ++j) old[j] = op4[j];
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) old[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int j = 0; j < 4; ++j) old[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
             __syncwarp();
-            tc_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            for (int j = 0; j < 4; ++j) {
+              const int e = 16 * hh + 4 * j;
+              float4 o = make_float4(__uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
               if (use_bias) {
-                const float4 b = *reinterpret_cast<const float4*>(bias_t + s0c + 4 * j);
+                const float4 b = *reinterpret_cast<const float4*>(bias_t + e);
                 o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
               }
               o.x += old[j].x; o.y += old[j].y; o.z += old[j].z; o.w += old[j].w;
-              *reinterpret_cast<float4*>(my_stage + lane * 128 + ((j ^ (lane & 7)) * 16)) = o;
+              *reinterpret_cast<float4*>(my_stage + lane * 64 + ((j ^ swz) * 16)) = o;
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_2d(&map_d, my_stage_u32, (int32_t)(g * p.aux_gn + (nbb - p.n_main)), (int32_t)((int64_t)mt * TC_BLOCK_M + q * 32));
+              tma_store_2d(&map_d, my_stage_u32, (int32_t)(g * p.aux_gn + (nbb - p.n_main)), (int32_t)(mt * TC_BLOCK_M + q * 32));
               tma_store_commit();
             }
             store_pending = true;
           }
           continue;
         }
-        // ---------------- general path: 32 columns at a time, direct global stores ----------------
-        for (int s0c = 0; s0c < cw; s0c += 32) {
-          uint32_t v[32];
-          tc_ld32_nowait(trow + c0 + s0c, v);
-          tc_ld_wait();
-          const int64_t nbb = nb + s0c;
-          if (m < p.M) {
-            const int ncols = min(32, cw - s0c);
-            float f[32];
+        // ---------------- general path: direct global stores ----------------
+        tc_ld_wait();
+        if (m < p.M) {
+          const int ncols = cw;
+          float f[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            // columns [nbb, nbb+ncols): main part (bf16) below n_main, aux part (fp32) at/after n_main
-            const int n_mainc = (int)max((int64_t)0, min((int64_t)ncols, p.n_main - nbb));
-            if (ec.has_drop) {                           // same fold as the fast path: main columns carry the keep scale
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          // columns [nb, nb+ncols): main part (bf16) below n_main, aux part (fp32) at/after n_main
+          const int n_mainc = (int)max((int64_t)0, min((int64_t)ncols, p.n_main - nb));
+          if (ec.has_drop) {                             // same fold as the fast path: main columns carry the keep scale
 #pragma unroll
-              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] *= ec.keep_scale;
+            for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] *= ec.keep_scale;
+          }
+          if (use_bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] += bias_t[j];
+          }
+          if (n_mainc > 0) {
+            if (p.act == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = fmaxf(f[j], 0.f);
             }
-            if (use_bias) {
+            uint16_t* op = p.out_main + m * p.ld_main + g * p.main_gn + nb;
+            if (p.mask) {
+              const uint16_t* mp = p.mask + m * p.ld_mask + g * p.mask_gn + nb;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] += bias_t[s0c + j];
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = bf16_to_f32(mp[j]) > 0.f ? f[j] * p.mask_scale : 0.f;
             }
-            if (n_mainc > 0) {
-              if (p.act == 1) {
+            if (ec.has_drop) {
+              const uint32_t gcol = (uint32_t)(g * p.main_gn + nb);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = fmaxf(f[j], 0.f);
-              }
-              uint16_t* op = p.out_main + m * p.ld_main + g * p.main_gn + nbb;
-              if (p.mask) {
-                const uint16_t* mp = p.mask + m * p.ld_mask + g * p.mask_gn + nbb;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = bf16_to_f32(mp[j]) > 0.f ? f[j] * p.mask_scale : 0.f;
-              }
-              if (ec.has_drop) {
-                const uint32_t gcol = (uint32_t)(g * p.main_gn + nbb);
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = drop_keep_lcg(ec.s0, ec.thr32, (uint32_t)m, gcol + j) ? f[j] : 0.f;
-              }
-              if (p.accumulate) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] += bf16_to_f32(op[j]);
-              }
-              if (n_mainc == 32 && (((uintptr_t)op) & 15) == 0) {
-                uint4* o4 = reinterpret_cast<uint4*>(op);
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                  o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                                     pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) if (j < n_mainc) op[j] = f32_to_bf16(f[j]);
-              }
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] = drop_keep_lcg(ec.s0, ec.thr32, (uint32_t)m, gcol + j) ? f[j] : 0.f;
             }
-            if (n_mainc < ncols) {
-              float* ap = p.out_aux + (int64_t)z * p.aux_split_stride + m * p.ld_aux + g * p.aux_gn + (nbb - p.n_main);
-              if (p.accumulate && p.split_k == 1) {
+            if (p.accumulate) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) f[j] += ap[j];
-              }
-              if (n_mainc == 0 && ncols == 32 && (((uintptr_t)ap) & 15) == 0) {
-                float4* a4 = reinterpret_cast<float4*>(ap);
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) f[j] += bf16_to_f32(op[j]);
+            }
+            if (n_mainc == 32 && (((uintptr_t)op) & 15) == 0) {
+              uint4* o4 = reinterpret_cast<uint4*>(op);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) a4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-              } else {
+              for (int j = 0; j < 4; ++j)
+                o4[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                                   pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+            } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) ap[j] = f[j];
-              }
+              for (int j = 0; j < 32; ++j) if (j < n_mainc) op[j] = f32_to_bf16(f[j]);
+            }
+          }
+          if (n_mainc < ncols) {
+            float* ap = p.out_aux + (int64_t)z * p.aux_split_stride + m * p.ld_aux + g * p.aux_gn + (nb - p.n_main);
+            if (p.accumulate && p.split_k == 1) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) f[j] += ap[j];
+            }
+            if (n_mainc == 0 && ncols == 32 && (((uintptr_t)ap) & 15) == 0) {
+              float4* a4 = reinterpret_cast<float4*>(ap);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) a4[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (j >= n_mainc && j < ncols) ap[j] = f[j];
             }
           }
         }
@@ -676,16 +654,19 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // row-major bf16 matrix [rows, cols] with leading dimension ld; box = [box_rows x 64 columns], 128-byte swizzle
-static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows, bool f32 = false) {
+// store_box: the epilogue's output boxes are 64 bytes wide (32 bf16 / 16 fp32 per row, 64B swizzle); operand boxes 128 bytes
+static int make_map(CUtensorMap* map, const void* ptr, int64_t rows, int64_t cols, int64_t ld, uint32_t box_rows, bool f32 = false,
+                    bool store_box = false) {
   auto enc = get_encode();
   if (!enc) return fail_msg("cdcmdr: cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * (f32 ? 4 : 2)};
-  cuuint32_t box[2] = {f32 ? 32u : 64u, box_rows};          // 128 bytes per box row either way
+  const uint32_t row_bytes = store_box ? 64u : 128u;
+  cuuint32_t box[2] = {row_bytes / (f32 ? 4u : 2u), box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   store_box ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cdcmdr: cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld box_rows=%u ptr=%p", (int)r,
              (long long)rows, (long long)cols, (long long)ld, box_rows, ptr);
@@ -756,16 +737,16 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   q.tma_store = (p->n_main > 0 && ((uintptr_t)p->out_main % 16) == 0 && p->ld_main % 8 == 0 && p->main_gn % 8 == 0 &&
                  (p->G - 1) * p->main_gn + p->n_main <= p->ld_main && p->M < (int64_t)1 << 31) ? 1 : 0;
   if (q.tma_store) {
-    if (int rc = make_map(&mc, p->out_main, p->M, (p->G - 1) * p->main_gn + p->n_main, p->ld_main, 32u)) return rc;
+    if (int rc = make_map(&mc, p->out_main, p->M, (p->G - 1) * p->main_gn + p->n_main, p->ld_main, 32u, false, true)) return rc;
   } else {
     mc = ma;
   }
   CUtensorMap md = ma;
   const int64_t n_aux = p->N - p->n_main;
   q.tma_aux = (n_aux > 0 && q.split_k == 1 && ((uintptr_t)p->out_aux % 16) == 0 && p->ld_aux % 4 == 0 && p->aux_gn % 4 == 0 &&
-               p->n_main % 32 == 0 && (p->G - 1) * p->aux_gn + n_aux <= p->ld_aux && p->M < (int64_t)1 << 31) ? 1 : 0;
+               p->n_main % 16 == 0 && (p->G - 1) * p->aux_gn + n_aux <= p->ld_aux && p->M < (int64_t)1 << 31) ? 1 : 0;
   if (q.tma_aux) {
-    if (int rc = make_map(&md, p->out_aux, p->M, (p->G - 1) * p->aux_gn + n_aux, p->ld_aux, 32u, true)) return rc;
+    if (int rc = make_map(&md, p->out_aux, p->M, (p->G - 1) * p->aux_gn + n_aux, p->ld_aux, 32u, true, true)) return rc;
   }
   const int b_bytes = (q.b_mn_major ? (int)ceil_div(b_cols, 64) * 64 : b_cols) * TC_BLOCK_K * 2;
   q.stage_bytes = TC_A_BYTES + b_bytes;
