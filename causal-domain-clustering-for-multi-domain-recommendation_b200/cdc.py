@@ -7,8 +7,8 @@ plus the domain -> cluster routing of its towers.
   train_step(...)                           the same three modes fused into the sigmoid+BCE kernel (run.py:635-640)
 
 The clustering itself (update_group: affinity matrices -> causal kernel -> k-means / regrouping, cdc.py:121-341) is
-host-side float64 NumPy in the reference, runs once per `update_interval` steps and is a "next" row (SURVEY §8f N4);
-it is not part of this package yet - `update_group` raises."""
+host-side NumPy / SciPy / scikit-learn in the reference and runs once per `update_interval` steps; it is
+restated on the host in cdc_group.py so that run.py::train_cdc works unchanged."""
 from __future__ import annotations
 
 import copy
@@ -16,6 +16,7 @@ import re
 
 import torch
 
+from .cdc_group import Grouping
 from .layer import BaseModel
 from .mmoe import MMoE
 from .ple import PLE
@@ -61,6 +62,7 @@ class CDC(BaseModel):
         self.matrix_causal = torch.zeros((n_causal_mask, n_domain), dtype=torch.float32, device=device)
         self.use_metric = use_metric
         self.model_state = None
+        self._grouping = Grouping(n_domain, self.n_cluster, dcw, config, use_metric)
 
     # ---------------------------------------------------------------- grouping state
     def set_groups(self, domain2group_list):
@@ -70,6 +72,7 @@ class CDC(BaseModel):
             raise ValueError("domain2group must map every domain to a cluster in [0, n_cluster)")
         self.domain2group_list = d2g
         self.domain2group = torch.tensor(d2g, dtype=torch.int64, device=self.domain2group.device)
+        self._grouping.domain2group_list = list(d2g)
 
     def _apply(self, fn, recurse=True):
         out = torch.nn.Module._apply(self, fn)
@@ -133,5 +136,26 @@ class CDC(BaseModel):
         self.load_state_dict(self.model_state, strict=False)
 
     def update_group(self, mode='iterative'):
-        raise NotImplementedError("CDC.update_group (host-side clustering, cdc.py:121-341) is a 'next' row (SURVEY §8f N4); "
-                                  "install assignments with set_groups()")
+        """cdc.py:121-238: turn the probed affinity matrices (matrix_A / matrix_B / matrix_mask, filled row by row by
+        run.py::update_matrix_cdc) into a new domain -> cluster assignment.  Host-side (cdc_group.py)."""
+        g = self._grouping
+        dev = self.domain2group.device
+        out = g.update(self.matrix_A.detach().cpu().numpy(), self.matrix_B.detach().cpu().numpy(),
+                       self.matrix_mask.detach().cpu().numpy(), mode=mode)
+        self.matrix_A = torch.from_numpy(out["A"]).to(dev)
+        self.matrix_B = torch.from_numpy(out["B"]).to(dev)
+        self.matrix_mask = torch.from_numpy(out["mask"]).to(dev)
+        self.matrix_causal = torch.from_numpy(out["causal"]).to(dev)
+        self.domain2group_list = list(g.domain2group_list)
+        self.domain2group = torch.tensor(self.domain2group_list, dtype=torch.int64, device=dev)
+        self.s_group2domain_list = [list(v) for v in g.s_group2domain_list]
+        self.t_group2domain_list = [list(v) for v in g.t_group2domain_list]
+        return self.domain2group_list
+
+    @property
+    def call_update_group(self):
+        return self._grouping.call_update_group
+
+    @property
+    def p_weight(self):
+        return self._grouping.p_weight

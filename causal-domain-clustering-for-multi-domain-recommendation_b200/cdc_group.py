@@ -1,0 +1,237 @@
+"""Host side of CDC's causal domain clustering (reference model/cdc.py:121-341, 359-393).
+
+This is small float32 / float64 matrix logic over n_domain x n_domain affinities (30..50 domains) that the reference runs once
+per `update_interval` training steps on the host; it stays on the host here too (NumPy / SciPy / scikit-learn, as upstream).
+It is restated - not accelerated - so that `CDC.update_group()` works and `run.py::train_cdc` runs unchanged against this
+package.  The xlsx / png dumps of the matrices (cdc.py:395-426) are an I/O side effect outside the hot path and are not produced.
+
+Pinned against the unmodified reference in tests/test_cdc_group.py (same matrices, same NumPy seed for the unseeded KMeans).
+"""
+from __future__ import annotations
+
+import copy
+
+import numpy as np
+
+F32 = np.float32
+
+
+def calc_causal_matrix(X, alpha=None):
+    """Distance-covariance dependence kernel between the columns of X (cdc.py:364-393): per feature j the doubly-centred,
+    mean-normalised |x_i - x_k| matrix Z_j; gamma = (F^T F)^2 - 2 <Z, Z>_thresh + |thresh|; cosine-normalised, clipped at 1."""
+    from scipy.spatial.distance import pdist, squareform
+    X = np.asarray(X)
+    n, nf = X.shape
+    thresh = np.eye(nf)
+    if alpha is not None:
+        from scipy.stats import chi2
+        thresh[thresh == 0] = chi2(1).ppf(1 - alpha) / n
+        thresh[thresh == 1] = 0
+    Z = np.zeros((nf, n, n))
+    for j in range(nf):
+        D = squareform(pdist(X[:, j].reshape(-1, 1), "cityblock"))
+        Z[j] = ((D - D.mean(0) - D.mean(1).reshape(-1, 1)) / D.mean()) + 1
+    Fm = Z.reshape(nf * n, n)
+    left = np.tensordot(Z, thresh, axes=([0], [0]))
+    left_right = np.tensordot(left, Z, axes=([2, 1], [0, 1]))
+    gamma = (Fm.T @ Fm) ** 2 - 2 * left_right + np.linalg.norm(thresh)
+    diag = np.diag(gamma)
+    kappa = gamma / np.sqrt(np.outer(diag, diag))
+    kappa[kappa > 1] = 1
+    return kappa
+
+
+class Grouping:
+    """The mutable clustering state of one CDC model (the attributes cdc.py keeps on the module) and its update rule."""
+
+    def __init__(self, n_domain, n_cluster, domain_cnt_weight, config, use_metric="loss"):
+        self.n_domain, self.n_cluster = n_domain, n_cluster
+        self.w = np.asarray(domain_cnt_weight, dtype=F32)
+        self.affinity_func = getattr(config, "affinity_func", "minus")
+        self.p_weight0 = getattr(config, "p_weight", 0.1)
+        self.p_weight = self.p_weight0
+        self.p_weight_method = getattr(config, "p_weight_method", "linear_decay")
+        self.p_weight_exp_decay = getattr(config, "p_weight_exp_decay", 0.9)
+        self.old_matrix_weight = getattr(config, "old_matrix_weight", 0.0)
+        self.domain2group_list = [0] * n_domain
+        self.s_group2domain_list = [list(range(n_domain))]
+        self.t_group2domain_list = [list(range(n_domain))]
+        self.initial_s_group2domain_list = None
+        self.call_update_group = 0
+        self.old_A = self.old_B = self.old_mask = None
+        if (use_metric == "loss") ^ (self.affinity_func == "divide"):          # cdc.py:88-93
+            self.default_metric_value, self.max_better = F32(1e6), False
+        else:
+            self.default_metric_value, self.max_better = F32(-1e6), True
+        self.A = self.B = self.causal = None
+
+    # ---------------------------------------------------------------- cdc.py:296-306
+    def _update_p_weight(self):
+        if self.p_weight > 1e-10:
+            if self.p_weight_method == "linear_decay":
+                self.p_weight = self.p_weight0 / self.call_update_group
+            elif self.p_weight_method == "quadratic_decay":
+                self.p_weight = self.p_weight0 / (self.call_update_group ** 2)
+            elif self.p_weight_method == "exponential_decay":
+                self.p_weight = self.p_weight * self.p_weight_exp_decay
+
+    # ---------------------------------------------------------------- cdc.py:321-341
+    def _lambda(self, group, domain=None):
+        """lambda_d = clamp(0.5 (|G|-1) sum_{g in G} dist[g, d] / (sum_{GxG} dist - sum_{g in G} dist[g, d]), 0, 1)"""
+        g = list(group)
+        dom = list(range(self.n_domain)) if domain is None else list(domain)
+        total = self.causal[np.ix_(g, g)].sum(dtype=F32)
+        related = self.causal[np.ix_(g, dom)].sum(axis=0, dtype=F32)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            vals = F32(len(g) - 1) * related / (total - related) * F32(0.5)
+        return np.clip(vals, F32(0), F32(1)).astype(F32)           # NaN (0/0) stays NaN, as torch.clamp leaves it
+
+    # ---------------------------------------------------------------- cdc.py:314-319
+    def _centers(self, group, center_num=1):
+        k = min(center_num, len(group))
+        dist = self._lambda(group, group)
+        order = _topk_smallest(dist, k)
+        return [group[i] for i in order]
+
+    # ---------------------------------------------------------------- cdc.py:308-312
+    def _metric_in_source_group(self, target, s_group):
+        lam = self._lambda(s_group, [target])
+        a, b = self.A[s_group, target], self.B[s_group, target]
+        return ((F32(1) - lam) * a + lam * b).sum(dtype=F32)
+
+    # ---------------------------------------------------------------- cdc.py:240-294
+    def _source_domains(self, t_group, group_idx):
+        nd = self.n_domain
+        s_group = self._centers(t_group, center_num=2)
+        useful = True
+        while useful and len(s_group) < nd:
+            lam = np.zeros((nd, len(t_group)), dtype=F32)
+            for d in range(nd):
+                if d not in s_group:
+                    lam[d] = self._lambda(s_group + [d], t_group)
+            wt = self.w[t_group]
+            sw = wt.sum(dtype=F32)
+            if sw != 0:
+                wt = wt / sw
+            J = (((F32(1) - lam) * self.A[:nd][:, t_group] + lam * self.B[:nd][:, t_group]) * wt).sum(axis=1, dtype=F32)
+            if self.initial_s_group2domain_list is None:
+                result = J
+            else:
+                P = (F32(1) - F32(2) * self._lambda(self.initial_s_group2domain_list[group_idx])) * np.power(self.w, F32(0.5))
+                result = J + F32(self.p_weight) * P if self.max_better else J - F32(self.p_weight) * P
+            result = result.astype(F32)
+            result[s_group] = self.default_metric_value
+            if self.max_better:
+                best = int(_argmax(result)); useful = bool(result[best] > 0)
+            else:
+                best = int(_argmin(result)); useful = bool(result[best] < 0)
+            if useful:
+                s_group.append(best)
+        return s_group
+
+    # ---------------------------------------------------------------- cdc.py:121-238
+    def update(self, matrix_A, matrix_B, matrix_mask, mode="iterative"):
+        """matrix_A (n_domain+1, n_domain), matrix_B (n_domain+n_cluster, n_domain), matrix_mask (n_mask, n_domain): float32.
+        Returns dict(A, B, mask, causal) - the transformed matrices the reference leaves on the module - and updates the lists."""
+        nd, nc = self.n_domain, self.n_cluster
+        self.call_update_group += 1
+        self._update_p_weight()
+        A, B, M = (np.array(t, dtype=F32, copy=True) for t in (matrix_A, matrix_B, matrix_mask))
+        if self.old_matrix_weight > 0 and self.old_A is not None:
+            ow = F32(self.old_matrix_weight)
+            A = self.old_A * ow + A * (F32(1) - ow)
+            B = self.old_B * ow + B * (F32(1) - ow)
+        self.old_A, self.old_B, self.old_mask = A.copy(), B.copy(), M.copy()
+        d2g = np.asarray(self.domain2group_list, dtype=np.int64)
+        if self.affinity_func == "minus":
+            A[:-1] -= A[-1]
+            B[:nd] = B[d2g + nd] - B[:nd]
+            M = M - A[-1]
+        elif self.affinity_func == "divide":
+            A[:-1] = F32(1) - A[:-1] / A[-1]
+            B[:nd] = F32(1) - B[d2g + nd] / B[:nd]
+            M = F32(1) - M / A[-1]
+        else:
+            raise ValueError("Unknown affinity_func: " + str(self.affinity_func))
+        self.A, self.B = A, B
+        self.causal = np.arccos(calc_causal_matrix(M.T)).astype(F32)
+
+        if max(self.domain2group_list) == 0:
+            # first call: k-means on the rows of the causal distance matrix (unseeded upstream: NumPy's global RNG)
+            from sklearn.cluster import KMeans
+            labels = KMeans(n_clusters=nc).fit(self.causal).labels_
+            t_groups = [[] for _ in range(nc)]
+            for i, gidx in enumerate(labels):
+                t_groups[int(gidx)].append(i)
+            self.domain2group_list = [int(v) for v in labels]
+            self.t_group2domain_list = t_groups
+            self.s_group2domain_list = [self._source_domains(t_groups[c], c) for c in range(nc)]
+            self.initial_s_group2domain_list = copy.deepcopy(self.s_group2domain_list)
+        else:
+            t_old = self.t_group2domain_list
+            queue = list(range(nd))
+            t_group, s_group = [[] for _ in range(nc)], [[] for _ in range(nc)]
+            metric = np.empty((nd, nc), dtype=F32)
+            metric[...] = 0
+            centers = [self._centers(t_old[c])[0] for c in range(nc)]
+            for c in range(nc):
+                t_group[c].append(centers[c])
+                queue.remove(centers[c])
+                metric[centers[c], :] = self.default_metric_value
+            pick = _argmax if self.max_better else _argmin
+            if mode == "iterative":
+                progressed = True
+                while queue and progressed:
+                    progressed = False
+                    for c in range(nc):
+                        s_group[c] = self._source_domains(t_group[c], c)
+                    for d in queue:
+                        for c in range(nc):
+                            metric[d, c] = self._metric_in_source_group(d, s_group[c])
+                    best = [int(pick(metric[:, c])) for c in range(nc)]
+                    for c in range(nc):
+                        if int(pick(metric[best[c], :])) == c:
+                            progressed = True
+                            t_group[c].append(best[c])
+                            queue.remove(best[c])
+                            metric[best[c], :] = self.default_metric_value
+                if queue:
+                    raise ValueError("target domain_queue is not empty")
+            elif mode == "greedy":
+                for c in range(nc):
+                    s_group[c] = self._source_domains(t_group[c], c)
+                for d in queue:
+                    for c in range(nc):
+                        metric[d, c] = self._metric_in_source_group(d, s_group[c])
+                for d in queue:
+                    t_group[int(pick(metric[d, :]))].append(d)
+            else:
+                raise ValueError(f"unknown update_group mode {mode!r}")
+            self.t_group2domain_list = t_group
+            d2g_new = np.zeros(nd, dtype=np.int64)
+            for c in range(nc):
+                self.s_group2domain_list[c] = self._source_domains(t_group[c], c)
+                d2g_new[t_group[c]] = c
+            self.domain2group_list = d2g_new.tolist()
+        return dict(A=A, B=B, mask=M, causal=self.causal)
+
+
+# torch.argmax / argmin / topk return the FIRST extreme element on ties and treat NaN as the largest value
+def _argmax(v):
+    v = np.asarray(v)
+    nan = np.isnan(v)
+    return int(np.flatnonzero(nan)[0]) if nan.any() else int(np.argmax(v))
+
+
+def _argmin(v):
+    v = np.asarray(v)
+    nan = np.isnan(v)
+    if nan.all():
+        return 0
+    return int(np.argmin(np.where(nan, np.inf, v)))
+
+
+def _topk_smallest(v, k):
+    v = np.asarray(v, dtype=np.float64)
+    key = np.where(np.isnan(v), np.inf, v)
+    return [int(i) for i in np.argsort(key, kind="stable")[:k]]
