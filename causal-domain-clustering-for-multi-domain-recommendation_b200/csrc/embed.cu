@@ -256,7 +256,7 @@ __device__ __forceinline__ void adam_elem(float& w, float& m, float& v, float g,
 }
 
 template <int VEC, bool DENSE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, int64_t V,
                   const int32_t* __restrict__ seg_of_row, const uint32_t* __restrict__ uniq, const int32_t* __restrict__ nuniq,
                   const int32_t* __restrict__ vals, const int32_t* __restrict__ start, const int32_t* __restrict__ cnt,
@@ -267,23 +267,54 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
   const int lanes = E / VEC;
   const int64_t rows = DENSE ? V : (int64_t)(*nuniq);
   const int64_t total = rows * lanes;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   double sq = 0.0;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    int64_t r, q64; int seg;
-    split_idx(i, lanes, r, q64);
-    const int q = (int)q64;
-    if (DENSE) { seg = seg_of_row[r]; }
-    else { seg = (int)r; r = uniq[seg]; if (r >= V) continue; }
-    float acc[VEC];
-    segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg, vals, start, cnt, long_slot, long_sum);
-    const int64_t o = r * E + q * VEC;
-    if (VEC == 4) {
-      float4 w = *reinterpret_cast<float4*>(table + o), m = *reinterpret_cast<float4*>(mom + o), v = *reinterpret_cast<float4*>(var + o);
-      sq += (double)w.x * w.x + (double)w.y * w.y + (double)w.z * w.z + (double)w.w * w.w;
-      adam_elem(w.x, m.x, v.x, acc[0], k); adam_elem(w.y, m.y, v.y, acc[1 % VEC], k);
-      adam_elem(w.z, m.z, v.z, acc[2 % VEC], k); adam_elem(w.w, m.w, v.w, acc[3 % VEC], k);
-      *reinterpret_cast<float4*>(table + o) = w; *reinterpret_cast<float4*>(mom + o) = m; *reinterpret_cast<float4*>(var + o) = v;
-    } else {
+  if (VEC == 4) {
+    // The sweep is bound by memory latency (ncu: long-scoreboard stalls, 29 % of DRAM bandwidth at one row per thread in flight):
+    // every thread keeps TWO independent rows in flight - all six 128-bit loads are issued before either row is touched.
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += 2 * stride) {
+      int64_t r[2], o[2]; int q[2], seg[2]; bool ok[2];
+      float4 w[2], m[2], v[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int64_t i = i0 + u * stride;
+        ok[u] = i < total;
+        int64_t q64 = 0; r[u] = 0;
+        if (ok[u]) split_idx(i, lanes, r[u], q64);
+        q[u] = (int)q64;
+        seg[u] = -1;
+        if (ok[u]) {
+          if (DENSE) seg[u] = seg_of_row[r[u]];
+          else { seg[u] = (int)r[u]; r[u] = uniq[seg[u]]; ok[u] = r[u] < V; }
+        }
+        o[u] = r[u] * E + q[u] * VEC;
+        if (ok[u]) {
+          w[u] = *reinterpret_cast<const float4*>(table + o[u]); m[u] = *reinterpret_cast<const float4*>(mom + o[u]);
+          v[u] = *reinterpret_cast<const float4*>(var + o[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (!ok[u]) continue;
+        float acc[VEC];
+        segment_sum<VEC>(acc, grad_out, ldg, F, E, q[u], seg[u], vals, start, cnt, long_slot, long_sum);
+        sq += (double)w[u].x * w[u].x + (double)w[u].y * w[u].y + (double)w[u].z * w[u].z + (double)w[u].w * w[u].w;
+        adam_elem(w[u].x, m[u].x, v[u].x, acc[0], k); adam_elem(w[u].y, m[u].y, v[u].y, acc[1 % VEC], k);
+        adam_elem(w[u].z, m[u].z, v[u].z, acc[2 % VEC], k); adam_elem(w[u].w, m[u].w, v[u].w, acc[3 % VEC], k);
+        *reinterpret_cast<float4*>(table + o[u]) = w[u]; *reinterpret_cast<float4*>(mom + o[u]) = m[u];
+        *reinterpret_cast<float4*>(var + o[u]) = v[u];
+      }
+    }
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+      int64_t r, q64; int seg;
+      split_idx(i, lanes, r, q64);
+      const int q = (int)q64;
+      if (DENSE) { seg = seg_of_row[r]; }
+      else { seg = (int)r; r = uniq[seg]; if (r >= V) continue; }
+      float acc[VEC];
+      segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg, vals, start, cnt, long_slot, long_sum);
+      const int64_t o = r * E + q * VEC;
       float w = table[o], m = mom[o], v = var[o];
       sq += (double)w * w;
       adam_elem(w, m, v, acc[0], k);

@@ -174,6 +174,8 @@ struct TcParams {
   int32_t tma_store;                         // out_main is written through map_c (alignment checked by the host)
   int32_t tma_aux;                           // out_aux (fp32) is written through map_d
   unsigned long long* prof;                  // diagnostics: cycles spent in each pipeline wait, summed over CTAs (NULL = off)
+  int32_t debug;                             // probe only (cdcmdr_gemm_bf16_tc_mode bits 4..6): 16 = epilogue drains nothing, 64 = tcgen05.ld only,
+                                             // 32 = everything but the TMA store.  Results are garbage; never set by the product path.
 };
 
 // Epilogue math for 32 consecutive columns [col0, col0+32) of one row; f in/out.  Returns packed bf16 pairs in o[16].
@@ -424,6 +426,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
       for (int ci = sub; ci < n_chunks; ci += 4) {
+        if (p.debug & 16) break;
         const int c0 = ci * 32;
         const int64_t nb = n0 + c0;                      // first global column of the chunk
         if (nb >= p.N) break;
@@ -463,6 +466,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int j = 0; j < 4; ++j) old[j] = make_uint4(0, 0, 0, 0);
           }
           tc_ld_wait();
+          if (p.debug & 64) continue;
           const uint32_t gcol = (uint32_t)(g * p.main_gn + nb);
           float f[32];
 #pragma unroll
@@ -481,6 +485,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ swz) * 16)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
           fence_async_smem();
           __syncwarp();
+          if (p.debug & 32) continue;
           if (lane == 0) {
             tma_store_2d(&map_c, my_stage_u32, (int32_t)gcol, (int32_t)(mt * TC_BLOCK_M + q * 32));
             tma_store_commit();
@@ -725,6 +730,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   // CTA pairs (cta_group::2) when the tile shape allows halving B between the two CTAs and there are at least two row tiles
   q.prof = g_tc_prof.load(std::memory_order_relaxed);
   const int mode = g_tc_mode.load(std::memory_order_relaxed);
+  q.debug = mode & 0x70;
   const bool pair_ok = p->M > TC_BLOCK_M && (q.b_mn_major ? bn % 128 == 0 : bn % 32 == 0);
   // auto: pairs pay off once a tile's K loop is long enough to hide the cross-CTA hand-offs (probe: +8 % at 128 k-blocks, -20 % at 6)
   const bool cta2 = (mode & 1) ? false : ((mode & 4) ? pair_ok : (pair_ok && q.kb_per_split >= 32));
@@ -792,7 +798,7 @@ extern "C" int cdcmdr_gemm_bf16_tc_profile(uint64_t* counters8) {
 
 extern "C" int cdcmdr_gemm_bf16_tc_mode(int mode) {
   const int old = g_tc_mode.load(std::memory_order_relaxed);
-  if (mode >= 0) g_tc_mode.store(mode & 7, std::memory_order_relaxed);
+  if (mode >= 0) g_tc_mode.store(mode & 0x77, std::memory_order_relaxed);
   return old;
 }
 

@@ -867,6 +867,19 @@ __global__ void add2d_kernel(const float* __restrict__ a, int64_t lda, float* __
 using namespace cdcmdr;
 
 // ============================================================================================ C-ABI
+namespace cdcmdr {
+// gate_mix_mma.cu: bf16 rows on mma.sync; -1 = shape / layout not covered
+int gate_mix_fwd_mma(const cdcmdr_mix_desc_t* d, const void* H, int64_t ldh, const float* logits, int64_t ldl, void* out, int64_t ldo,
+                     float* probs, int64_t B, int is_bf16, cudaStream_t st);
+int gate_mix_bwd_mma(const cdcmdr_mix_desc_t* d, const void* H, int64_t ldh, const float* probs, const void* dOut, int64_t ldo, void* dH,
+                     int64_t lddh, float relu_scale, float* dlogits, int64_t lddl, int64_t B, int is_bf16, cudaStream_t st);
+}
+// CDCMDR_MIX_SIMT=1 keeps the SIMT gate-mix kernels for bf16 rows too (A/B measurements)
+static bool mix_simt_only() {
+  static const bool v = [] { const char* e = getenv("CDCMDR_MIX_SIMT"); return e && e[0] == '1'; }();
+  return v;
+}
+
 static int check_mix(const cdcmdr_mix_desc_t* d) {
   CDC_REQUIRE(d && d->n_gates >= 1 && d->n_gates <= 32 && d->max_sel >= 1 && d->max_sel <= 32 && d->n_experts >= 1 &&
               d->n_experts <= 64 && d->h >= 1, "bad gate-mix descriptor");
@@ -877,6 +890,10 @@ extern "C" int cdcmdr_gate_mix_fwd(const cdcmdr_mix_desc_t* d, const void* H, in
                                    void* out, int64_t ldo, float* probs, int64_t B, int is_bf16, cdcmdr_stream_t s) {
   if (int rc = check_mix(d)) return rc;
   if (B == 0) return 0;
+  if (!mix_simt_only()) {
+    const int rc = gate_mix_fwd_mma(d, H, ldh, logits, ldl, out, ldo, probs, B, is_bf16, to_stream(s));
+    if (rc >= 0) return rc;
+  }
   MixK k{d->n_gates, d->n_experts, d->h, d->max_sel, d->gate_col, d->gate_n, d->gate_sel};
   size_t smem = (size_t)8 * d->n_gates * d->max_sel * sizeof(float);
   CDC_REQUIRE(smem <= 32 * 1024, "gate-mix descriptor too large");
@@ -904,6 +921,10 @@ extern "C" int cdcmdr_gate_mix_bwd(const cdcmdr_mix_desc_t* d, const void* H, in
                                    float* dlogits, int64_t lddl, int64_t B, int is_bf16, cdcmdr_stream_t s) {
   if (int rc = check_mix(d)) return rc;
   if (B == 0) return 0;
+  if (!mix_simt_only()) {
+    const int rc = gate_mix_bwd_mma(d, H, ldh, probs, dOut, ldo, dH, lddh, relu_scale, dlogits, lddl, B, is_bf16, to_stream(s));
+    if (rc >= 0) return rc;
+  }
   MixK k{d->n_gates, d->n_experts, d->h, d->max_sel, d->gate_col, d->gate_n, d->gate_sel};
   size_t smem = (size_t)16 * d->n_gates * d->max_sel * sizeof(float);
   CDC_REQUIRE(smem <= 32 * 1024, "gate-mix descriptor too large");

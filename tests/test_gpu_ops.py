@@ -234,6 +234,79 @@ def test_gate_mix_fwd_bwd(B, h, cfg, fast):
     both(fn, tol=1e-5)
 
 
+def _mix_cfg(cfg):
+    T, ns, nsh = 4, 2, 2
+    nE = T * ns + nsh
+    if cfg == "ple":
+        ng, ms = T + 1, nE
+        col = [t * 4 for t in range(T)] + [16]
+        n = [4] * T + [nE]
+        sel = sum(([*range(t * ns, (t + 1) * ns), *range(T * ns, nE)] + [0] * (ms - 4) for t in range(T)), []) + list(range(nE))
+        ncol = 16 + nE + 1
+    elif cfg == "ple_last":
+        ng, ms = T, 4
+        col = [t * 4 for t in range(T)]; n = [4] * T
+        sel = sum(([*range(t * ns, (t + 1) * ns), *range(T * ns, nE)] for t in range(T)), [])
+        ncol = 16
+    elif cfg == "mmoe":
+        nE, ng, ms = 8, 3, 8
+        col = [0, 8, 16]; n = [8] * 3; sel = list(range(8)) * 3; ncol = 25
+    elif cfg == "wide":                                 # 16 experts, 2 gates of 16: every fragment slot in use
+        nE, ng, ms = 16, 2, 16
+        col = [0, 16]; n = [16, 16]; sel = list(range(16)) + list(range(15, -1, -1)); ncol = 32
+    else:
+        nE, ng, ms = 3, 2, 3
+        col = [1, 4]; n = [2, 3]; sel = [2, 0, 0, 0, 1, 2]; ncol = 7
+    return nE, ng, ms, col, n, sel, ncol
+
+
+@pytest.mark.parametrize("B,h,cfg", [(130, 128, "ple"), (77, 64, "ple_last"), (300, 64, "mmoe"), (1000, 128, "mmoe"), (513, 128, "wide"),
+                                     (9, 64, "odd"), (4100, 128, "ple"), (64, 32, "mmoe")])
+def test_gate_mix_bf16(B, h, cfg):
+    """bf16 rows: h in {64, 128} with <= 8 gates / 16 experts / 32 pairs run on the mma.sync kernels (gate_mix_mma.cu), the rest
+    on the SIMT kernels; both against the emulator (fp32 math on the bf16-rounded inputs, rounded once on output)."""
+    from oracle.host_abi import f32_to_bf16
+    nE, ng, ms, col, n, sel, ncol = _mix_cfg(cfg)
+
+    def bf(e, r, c, relu=False):
+        v = e.rng.standard_normal((r, c)).astype(np.float32)
+        if relu:
+            v = np.maximum(v, 0)
+        t = torch.from_numpy(f32_to_bf16(v).reshape(r, c).view(np.int16)).to(e.dev)
+        e.keep.append(t)
+        return t
+
+    def fn(lib, e):
+        desc = e.put(np.array(col + n + sel, dtype=np.int32))
+        d = L.MixDesc(ng, nE, h, ms, desc.data_ptr(), desc.data_ptr() + 4 * ng, desc.data_ptr() + 8 * ng, sum(n))
+        H = bf(e, B, nE * h, relu=True)
+        logits = e.f32(B, ncol, scale=2.0)
+        out = e.zeros(B, ng * h, dtype=torch.int16)
+        probs = e.zeros(B, ng * ms)
+        lib.gate_mix_fwd(C.byref(d), H.data_ptr(), nE * h, logits.data_ptr(), ncol, out.data_ptr(), ng * h, probs.data_ptr(), B, 1, 0)
+        dOut = bf(e, B, ng * h)
+        dH = e.zeros(B, nE * h, dtype=torch.int16)
+        dl = e.zeros(B, ncol)
+        lib.gate_mix_bwd(C.byref(d), H.data_ptr(), nE * h, probs.data_ptr(), dOut.data_ptr(), ng * h, dH.data_ptr(), nE * h, 1.25,
+                         dl.data_ptr(), ncol, B, 1, 0)
+        dH2 = e.zeros(B, nE * h, dtype=torch.int16)
+        dl2 = e.zeros(B, ncol)
+        lib.gate_mix_bwd(C.byref(d), H.data_ptr(), nE * h, probs.data_ptr(), dOut.data_ptr(), ng * h, dH2.data_ptr(), nE * h, 0.0,
+                         dl2.data_ptr(), ncol, B, 1, 0)
+        return [out, probs, dH, dl, dH2, dl2]
+
+    cpu, gpu = Env(3).run(fn)
+    for i, (a, b) in enumerate(zip(cpu, gpu)):
+        if a.dtype == np.int16:                          # bf16 payload: within one bf16 ulp of the tensor scale, almost all equal
+            af = (a.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+            bfv = (b.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+            err = np.abs(af - bfv)
+            assert float((err > 2 ** -7 * np.maximum(np.abs(af), 1e-3)).mean()) == 0.0, f"output {i}: more than one bf16 ulp off"
+            assert float((a != b).mean()) < 0.01, f"output {i}: {(a != b).mean():.4f} of the bf16 entries differ"
+        else:
+            check(a, b, tol=2e-5, what=f"output {i}")
+
+
 # ------------------------------------------------------------------------------------------------ batch norm
 @pytest.mark.parametrize("B,Cn,train,relu,g2", [(257, 70, 1, 1, 0), (4096, 256, 1, 1, 0), (100, 33, 0, 1, 0), (64, 16, 1, 0, 1),
                                                   (2, 5, 1, 1, 0)])

@@ -77,6 +77,11 @@ if ONLY:
     def run(name, *a, **k):            # noqa: F811
         if name.startswith(ONLY):
             _run(name, *a, **k)
+# epilogue knock-out probes (mode bits 16 / 64 / 32: no drain / tcgen05.ld only / everything but the TMA store)
+for dbg in (0, 16, 64, 32):
+    run(f"dbg{dbg}_l0_fwd_full", B, 2560, 368, act=1, drop=0.2, mode=1 | dbg)
+    run(f"dbg{dbg}_l0_fwd_full_pad", B, 2560, 368, act=1, drop=0.2, pad=64, mode=1 | dbg)
+    run(f"dbg{dbg}_l0_fwd_pair", B, 2560, 368, act=1, drop=0.2, mode=4 | dbg)
 for md in (1, 4):
     for pd in (0, 64):
         run("align_l0_fwd_plain", B, 2560, 368, bias=False, pad=pd, mode=md)
