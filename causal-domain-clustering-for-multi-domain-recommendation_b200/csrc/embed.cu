@@ -16,7 +16,7 @@ struct EmbedPlan {                   // lives at the start of the caller-provide
   int64_t n, V, n_long_max;
   int E_max;
   size_t off_keys_in, off_vals_in, off_keys, off_vals, off_uniq, off_cnt, off_start, off_nuniq,
-      off_seg_of_row, off_long_slot, off_nlong, off_long_sum, off_long_seg, off_long_off, off_cub, off_reg;
+      off_seg_of_row, off_long_slot, off_nlong, off_long_sum, off_long_seg, off_long_off, off_cub, off_reg, off_gsum;
   size_t cub_bytes, total;
 };
 
@@ -49,6 +49,7 @@ static EmbedPlan make_layout(int64_t n, int64_t V, int E_max) {
   p.off_long_seg = take((size_t)p.n_long_max * 4);
   p.off_long_off = take((size_t)p.n_long_max * 4);
   p.off_reg = take(kRegPartials * 8);
+  p.off_gsum = take((size_t)n * E_max * 4);          // per-segment gradient sums of the dense-exact update (<= n segments)
   p.cub_bytes = cub_temp_bytes(n, V);
   p.off_cub = take(p.cub_bytes);
   p.total = o;
@@ -330,6 +331,63 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
   }
 }
 
+// Dense-exact update in two passes.  Pass 1 (this kernel): one thread per (touched row, 4 columns) sums the row's segment into a
+// compact [n_unique, E] buffer - every thread has work, the dependent vals -> grad_out loads of different segments overlap.
+// Pass 2 (embed_adam_dense4_kernel) is then a pure stream over table / m / v: the only dependent load is seg_of_row -> gsum row,
+// and consecutive touched rows read consecutive gsum rows.  The fused single pass interleaved the segment walks with the sweep:
+// ncu showed long-scoreboard stalls at 29 % of DRAM bandwidth (every warp waited for its slowest segment).
+template <int VEC>
+__global__ void __launch_bounds__(256)
+embed_segsum_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, const int32_t* __restrict__ nuniq,
+                    const int32_t* __restrict__ vals, const int32_t* __restrict__ start, const int32_t* __restrict__ cnt,
+                    const int32_t* __restrict__ long_slot, const float* __restrict__ long_sum, float* __restrict__ gsum) {
+  const int lanes = E / VEC;
+  const int64_t total = (int64_t)(*nuniq) * lanes;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t seg, q64;
+    split_idx(i, lanes, seg, q64);
+    const int q = (int)q64;
+    float acc[VEC];
+    segment_sum<VEC>(acc, grad_out, ldg, F, E, q, (int)seg, vals, start, cnt, long_slot, long_sum);
+    float* o = gsum + seg * E + q * VEC;
+    if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    else o[0] = acc[0];
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+embed_adam_dense4_kernel(int E, int64_t V, const int32_t* __restrict__ seg_of_row, const float* __restrict__ gsum,
+                         float* __restrict__ table, float* __restrict__ mom, float* __restrict__ var,
+                         const cdcmdr_step_state_t* __restrict__ st, float l2, double* __restrict__ reg_partials) {
+  const AdamK k = load_adam(st, l2);
+  const int lanes = E / 4;
+  const int64_t total = V * lanes;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  double sq = 0.0;
+#pragma unroll 2
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += stride) {
+    int64_t r, q64;
+    split_idx(i, lanes, r, q64);
+    const int64_t o = r * E + q64 * 4;
+    const int seg = __ldg(seg_of_row + r);
+    float4 w = *reinterpret_cast<const float4*>(table + o), m = *reinterpret_cast<const float4*>(mom + o);
+    float4 v = *reinterpret_cast<const float4*>(var + o);
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (seg >= 0) g = __ldg(reinterpret_cast<const float4*>(gsum + (int64_t)seg * E + q64 * 4));
+    sq += (double)w.x * w.x + (double)w.y * w.y + (double)w.z * w.z + (double)w.w * w.w;
+    adam_elem(w.x, m.x, v.x, g.x, k); adam_elem(w.y, m.y, v.y, g.y, k);
+    adam_elem(w.z, m.z, v.z, g.z, k); adam_elem(w.w, m.w, v.w, g.w, k);
+    *reinterpret_cast<float4*>(table + o) = w; *reinterpret_cast<float4*>(mom + o) = m; *reinterpret_cast<float4*>(var + o) = v;
+  }
+  if (reg_partials) {                              // deterministic: fixed grid, fixed in-block tree
+    __shared__ double red[8];
+    sq = warp_sum(sq);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w]; reg_partials[blockIdx.x] = t; }
+  }
+}
+
 __global__ void reg_finalize_kernel(const double* __restrict__ partials, int n, double* __restrict__ out) {
   __shared__ double red[32];
   double t = 0;
@@ -459,9 +517,15 @@ static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const
 #define ARGS grad_out, ldg, F, E, V, at<int32_t>(plan, L.off_seg_of_row), at<uint32_t>(plan, L.off_uniq), at<int32_t>(plan, L.off_nuniq), \
              at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start), at<int32_t>(plan, L.off_cnt),                                  \
              at<int32_t>(plan, L.off_long_slot), at<float>(plan, L.off_long_sum), table, m, v, h, l2, partials
-  if (dense) {
-    if (E % 4 == 0) embed_adam_kernel<4, true><<<grid, 256, 0, st>>>(ARGS);
-    else embed_adam_kernel<1, true><<<grid, 256, 0, st>>>(ARGS);
+  if (dense && E % 4 == 0) {
+    float* gsum = at<float>(plan, L.off_gsum);
+    embed_segsum_kernel<4><<<grid_for(B * F * lanes, 256), 256, 0, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_nuniq),
+        at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start), at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_slot),
+        at<float>(plan, L.off_long_sum), gsum);
+    CDC_LAUNCHED();
+    embed_adam_dense4_kernel<<<grid, 256, 0, st>>>(E, V, at<int32_t>(plan, L.off_seg_of_row), gsum, table, m, v, h, l2, partials);
+  } else if (dense) {
+    embed_adam_kernel<1, true><<<grid, 256, 0, st>>>(ARGS);
   } else {
     if (E % 4 == 0) embed_adam_kernel<4, false><<<grid, 256, 0, st>>>(ARGS);
     else embed_adam_kernel<1, false><<<grid, 256, 0, st>>>(ARGS);

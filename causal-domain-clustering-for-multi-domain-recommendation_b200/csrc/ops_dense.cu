@@ -418,6 +418,25 @@ __global__ void colsum_finalize_kernel(const double* __restrict__ partial, int c
   out[c] = accumulate ? out[c] + (float)t : (float)t;
 }
 
+// Same sum for many chunks (narrow matrices are cut into up to kColsumMaxChunks row chunks so that the partial kernel fills the
+// machine): block = 32 columns x 8 chunk lanes, lane y adds chunks y, y+8, ... and the 8 lane sums are added in lane order.
+__global__ void __launch_bounds__(256)
+colsum_finalize_wide_kernel(const double* __restrict__ partial, int chunks, int64_t C, float* __restrict__ out, int accumulate) {
+  __shared__ double sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + tx;
+  double t = 0;
+  if (c < C) for (int k = ty; k < chunks; k += 8) t += partial[(int64_t)k * C + c];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    double u = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) u += sm[y][tx];
+    out[c] = accumulate ? out[c] + (float)u : (float)u;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ batch norm
 struct BnStatF {
   const float* Z; int64_t ldz;
@@ -967,7 +986,21 @@ extern "C" int cdcmdr_gate_mix_bwd(const cdcmdr_mix_desc_t* d, const void* H, in
   return 0;
 }
 
-extern "C" size_t cdcmdr_colsum_scratch_bytes(int64_t C) { return (size_t)kMaxChunks * (size_t)(C > 0 ? C : 1) * sizeof(double); }
+// row chunks of the bandwidth-shaped column sum: enough blocks to fill the machine even when the matrix is one column block wide
+constexpr int kColsumMaxChunks = 1024;
+static int colsum_chunks(int64_t B, int64_t col_blocks) {
+  int64_t ch = ceil_div(4 * kNumSMs, col_blocks);
+  if (ch > kColsumMaxChunks) ch = kColsumMaxChunks;
+  if (ch > B / 64) ch = B / 64;
+  return ch < 1 ? 1 : (int)ch;
+}
+extern "C" size_t cdcmdr_colsum_scratch_bytes(int64_t C) {
+  const int64_t c = C > 0 ? C : 1;
+  // the widest vector (8 bf16) gives the fewest column blocks; a ragged C is summed as its whole vectors (>= C-7 columns) + a tail
+  int64_t ch = colsum_chunks((int64_t)1 << 40, ceil_div(c > 8 ? c - 7 : 1, 256));
+  if (ch < kMaxChunks) ch = kMaxChunks;
+  return (size_t)ch * (size_t)(c + 8) * sizeof(double);
+}
 extern "C" size_t cdcmdr_bn_scratch_bytes(int64_t C) {
   const size_t c = (size_t)(C > 0 ? C : 1);
   return 2 * (size_t)kMaxChunks * c * sizeof(double) + 2 * c * sizeof(float) + 512 + 2 * c * sizeof(double);
@@ -992,15 +1025,13 @@ extern "C" int cdcmdr_colsum(const void* X, int64_t ld, int is_bf16, int64_t B, 
   // a last vector that hangs over C reads the row's padding columns (ld >= c_pad); their sums are never written
   if (B >= 1024 && ld >= c_pad && ld % vec == 0 && ((uintptr_t)X % 16) == 0) {
     const int64_t col_blocks = ceil_div(C, 32 * vec);
-    int64_t ch = ceil_div(4 * kNumSMs, col_blocks);
-    if (ch > kMaxChunks) ch = kMaxChunks;
-    if (ch > B / 64) ch = B / 64;
-    if (ch < 1) ch = 1;
+    const int ch = colsum_chunks(B, col_blocks);
     dim3 vgrid((unsigned)col_blocks, (unsigned)ch);
-    if (is_bf16) colsum_vec_kernel<uint16_t, 8><<<vgrid, 256, 0, st>>>((const uint16_t*)X, ld, B, C, (int)ch, partial);
-    else colsum_vec_kernel<float, 4><<<vgrid, 256, 0, st>>>((const float*)X, ld, B, C, (int)ch, partial);
+    if (is_bf16) colsum_vec_kernel<uint16_t, 8><<<vgrid, 256, 0, st>>>((const uint16_t*)X, ld, B, C, ch, partial);
+    else colsum_vec_kernel<float, 4><<<vgrid, 256, 0, st>>>((const float*)X, ld, B, C, ch, partial);
     CDC_LAUNCHED();
-    colsum_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, (int)ch, C, out, accumulate);
+    if (ch > 32) colsum_finalize_wide_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(partial, ch, C, out, accumulate);
+    else colsum_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, ch, C, out, accumulate);
     CDC_LAUNCHED();
     return 0;
   }
