@@ -213,11 +213,32 @@ __device__ __forceinline__ void segment_sum(float (&acc)[VEC], const float* __re
     return;
   }
   const int s0 = start[seg];
+  if (VEC == 4) {
+    // four entries per round: the four index loads, then the four row loads, are independent of each other - a segment of <= 4
+    // entries (most of them) costs three dependent round trips instead of two per entry.  The adds keep the entry order.
+    for (int i = 0; i < c; i += 4) {
+      int pos[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pos[u] = (i + u < c) ? __ldg(vals + s0 + i + u) : -1;
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pos[u] >= 0) {
+          const uint32_t b = (uint32_t)pos[u] / (uint32_t)F, f = (uint32_t)pos[u] - b * (uint32_t)F;
+          t[u] = __ldg(reinterpret_cast<const float4*>(grad_out + (int64_t)b * ldg + (int64_t)f * E + q * VEC));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (pos[u] >= 0) { acc[0] += t[u].x; acc[1 % VEC] += t[u].y; acc[2 % VEC] += t[u].z; acc[3 % VEC] += t[u].w; }
+    }
+    return;
+  }
   for (int i = 0; i < c; ++i) {
     const int pos = vals[s0 + i];
     const float* src = grad_out + (int64_t)(pos / F) * ldg + (int64_t)(pos % F) * E + q * VEC;
-    if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(src); acc[0] += t.x; acc[1 % VEC] += t.y; acc[2 % VEC] += t.z; acc[3 % VEC] += t.w; }
-    else acc[0] += src[0];
+    acc[0] += src[0];
   }
 }
 

@@ -36,7 +36,8 @@ constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;               // 576
 constexpr int TC_STAGING_WARP_BYTES = 32 * 64;                   // 32 rows x 32 bf16 (or 16 fp32), 64B-swizzled
 constexpr int TC_STAGING_BYTES = TC_EPI_WARPS * TC_STAGING_WARP_BYTES;
 constexpr int TC_BIAS_BYTES = 2 * TC_MAX_N * 4;                  // one bias tile per accumulator stage
-constexpr int TC_BAR_BYTES = 256;
+constexpr int TC_BAR_BYTES = 512;
+constexpr int TC_MASK_BYTES = TC_EPI_WARPS * TC_STAGING_WARP_BYTES;  // ReLU-mask tiles (one 32 x 32 bf16 box per epilogue warp), only with p.tma_mask
 constexpr int TC_SMEM_LIMIT = 232448;                            // 227 KB opt-in maximum per CTA
 constexpr int TC_TMEM_COLS = 512;                    // 2 accumulator stages x 256 fp32 columns
 
@@ -173,6 +174,7 @@ struct TcParams {
   int32_t accumulate;
   int32_t tma_store;                         // out_main is written through map_c (alignment checked by the host)
   int32_t tma_aux;                           // out_aux (fp32) is written through map_d
+  int32_t tma_mask;                          // the ReLU mask (forward activation) is read through map_m into shared memory
   unsigned long long* prof;                  // diagnostics: cycles spent in each pipeline wait, summed over CTAs (NULL = off)
   int32_t debug;                             // probe only (cdcmdr_gemm_bf16_tc_mode bits 4..6): 16 = epilogue drains nothing, 64 = tcgen05.ld only,
                                              // 32 = everything but the TMA store.  Results are garbage; never set by the product path.
@@ -261,7 +263,8 @@ __device__ __forceinline__ void epi_math32(const EpiCtx& c, float (&f)[32], cons
 template <bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d, const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d,
+                    const __grid_constant__ CUtensorMap map_m, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* staging = smem + p.stages * p.stage_bytes;
   float* bias_s = (float*)(staging + TC_STAGING_BYTES);
@@ -270,6 +273,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t tfull0 = smem_u32(bars + 2 * TC_MAX_STAGES), tempty0 = smem_u32(bars + 2 * TC_MAX_STAGES + 2);
   const uint32_t pfull0 = smem_u32(bars + 2 * TC_MAX_STAGES + 4);            // rank 0 only: "rank 1's stage is full"
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_MAX_STAGES + 4);
+  const uint32_t mbar0 = smem_u32(bars + 32);                                 // one "mask tile landed" barrier per epilogue warp
+  uint8_t* mask_s = (uint8_t*)bars + TC_BAR_BYTES;                             // [TC_EPI_WARPS][32 rows x 64 B], 64B-swizzled
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const long long prof_cta0 = p.prof ? clock64() : 0;
@@ -280,11 +285,13 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (smem_u32(smem) & 1023u) __trap();                          // the swizzle atoms below assume it
     for (int i = 0; i < p.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); mbar_init(pfull0 + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
+    for (int i = 0; i < TC_EPI_WARPS; ++i) mbar_init(mbar0 + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     if (p.tma_aux) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
+    if (p.tma_mask) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_m) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
@@ -394,11 +401,28 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // turn.  The epilogue is SIMT work at one CTA per SM: it is bound by how many warps can hide each other's latencies (8 warps
     // with 64-column chunks spent ~7 k cycles per tile against 3 k cycles of MMAs), hence many narrow chunks rather than few wide ones.
     const int ew = warp - 2;                             // 0..15
+    const int n_chunks_c = (p.block_n + 31) >> 5;
     const int q = warp & 3;                              // TMEM lane quarter this warp may access
     const int sub = ew >> 2;                             // which of the four warps of the quarter
     uint8_t* my_stage = staging + ew * TC_STAGING_WARP_BYTES;       // 32 rows x 64 B, 64B-swizzled
     float* bias_t = bias_s + ew * 32;                    // this warp's bias slice: the 32 columns of the chunk in flight
     const uint32_t my_stage_u32 = smem_u32(my_stage);
+    // ReLU mask through TMA: the warp's next 32 x 32 mask box streams into its private buffer while the previous chunk is still in
+    // the math / store phase (per-lane 64-byte global reads of 32 different rows cost ~5 k cycles per tile in the masked dgrad)
+    const uint8_t* my_mask = mask_s + ew * TC_STAGING_WARP_BYTES;
+    const uint32_t my_mask_u32 = smem_u32(my_mask), my_mbar = mbar0 + 8 * ew;
+    uint32_t mask_phase = 0;
+    // chunk (n0 + 32*ci) of this tile takes the TMA-store fast path AND carries a mask
+    auto mask_by_tma = [&](int64_t n0_, int ci_) -> bool {
+      const int64_t nb_ = n0_ + 32 * ci_;
+      return p.tma_mask && ci_ < n_chunks_c && 32 * ci_ + 32 <= p.block_n && nb_ + 32 <= p.n_main;
+    };
+    auto issue_mask = [&](int g_, int64_t mt_, int64_t nb_) {
+      if (lane == 0) {
+        mbar_expect_tx(my_mbar, TC_STAGING_WARP_BYTES);
+        tma_load_2d(my_mask_u32, &map_m, my_mbar, (int32_t)(g_ * p.mask_gn + nb_), (int32_t)(mt_ * TC_BLOCK_M + q * 32));
+      }
+    };
     int acc = 0; uint32_t acc_phase = 0;
     EpiCtx ec;
     ec.act = p.act; ec.mask_scale = p.mask_scale; ec.has_mask = p.mask != nullptr; ec.has_drop = p.drop_p > 0.f;
@@ -420,6 +444,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int64_t m = mt * TC_BLOCK_M + q * 32 + lane;
       const int64_t n0 = (int64_t)nt * p.block_n;
       const bool use_bias = p.bias != nullptr && z == 0;
+      if (mask_by_tma(n0, sub)) issue_mask(g, mt, n0 + 32 * sub);
       { TC_PROF_T0();
         if (CTA2) mbar_wait_cluster(tfull0 + 8 * acc, acc_phase); else mbar_wait(tfull0 + 8 * acc, acc_phase);
         if (ew == 0 && lane == 0) TC_PROF_ADD(3); }
@@ -449,7 +474,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (p.tma_store && (full_main || clip_ok)) {
           // ---------------- fast path: 32 bf16 columns per row -> swizzled staging -> TMA store ----------------
           uint4 mk[4], old[4];
-          if (ec.has_mask && m < p.M) {
+          if (p.tma_mask) {
+            // full_main holds here (clip_ok excludes masks), i.e. mask_by_tma(n0, ci) was true when this box was requested
+            mbar_wait(my_mbar, mask_phase);
+            mask_phase ^= 1;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mk[j] = *reinterpret_cast<const uint4*>(my_mask + lane * 64 + ((j ^ swz) * 16));
+            __syncwarp();                                // every lane has its row: the buffer may take the next box
+            if (mask_by_tma(n0, ci + 4)) issue_mask(g, mt, n0 + 32 * (ci + 4));
+          } else if (ec.has_mask && m < p.M) {
             const uint4* mp = reinterpret_cast<const uint4*>(p.mask + m * p.ld_mask + g * p.mask_gn + nb);
 #pragma unroll
             for (int j = 0; j < 4; ++j) mk[j] = __ldg(mp + j);
@@ -747,16 +780,22 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   } else {
     mc = ma;
   }
-  CUtensorMap md = ma;
+  CUtensorMap md = ma, mm = ma;
   const int64_t n_aux = p->N - p->n_main;
   q.tma_aux = (n_aux > 0 && q.split_k == 1 && ((uintptr_t)p->out_aux % 16) == 0 && p->ld_aux % 4 == 0 && p->aux_gn % 4 == 0 &&
                p->n_main % 16 == 0 && (p->G - 1) * p->aux_gn + n_aux <= p->ld_aux && p->M < (int64_t)1 << 31) ? 1 : 0;
   if (q.tma_aux) {
     if (int rc = make_map(&md, p->out_aux, p->M, (p->G - 1) * p->aux_gn + n_aux, p->ld_aux, 32u, true, true)) return rc;
   }
+  // ReLU mask through TMA when every chunk that carries it is a whole 32-column TMA-store chunk of a TMA-able matrix
+  q.tma_mask = (p->mask && q.tma_store && p->n_main == p->N && p->N % 32 == 0 && bn % 32 == 0 && ((uintptr_t)p->mask % 16) == 0 &&
+                p->ld_mask % 8 == 0 && p->mask_gn % 8 == 0 && (p->G - 1) * p->mask_gn + p->n_main <= p->ld_mask && !p->accumulate) ? 1 : 0;
+  if (q.tma_mask) {
+    if (int rc = make_map(&mm, p->mask, p->M, (p->G - 1) * p->mask_gn + p->n_main, p->ld_mask, 32u, false, true)) return rc;
+  }
   const int b_bytes = (q.b_mn_major ? (int)ceil_div(b_cols, 64) * 64 : b_cols) * TC_BLOCK_K * 2;
   q.stage_bytes = TC_A_BYTES + b_bytes;
-  const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES;
+  const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + (q.tma_mask ? TC_MASK_BYTES : 0);
   int stages = (TC_SMEM_LIMIT - fixed) / q.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CDC_REQUIRE(stages >= 2, "shared memory budget too small for a 2-stage pipeline");
@@ -772,7 +811,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
   if (!cta2) {
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-    gemm_bf16_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, q);
+    gemm_bf16_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, mm, q);
     CDC_LAUNCHED();
     return 0;
   }
@@ -786,7 +825,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CDC_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<true>, ma, mb, mc, md, q));
+  CDC_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<true>, ma, mb, mc, md, mm, q));
   CDC_LAUNCHED();
   return 0;
 }

@@ -419,20 +419,23 @@ __global__ void colsum_finalize_kernel(const double* __restrict__ partial, int c
 }
 
 // Same sum for many chunks (narrow matrices are cut into up to kColsumMaxChunks row chunks so that the partial kernel fills the
-// machine): block = 32 columns x 8 chunk lanes, lane y adds chunks y, y+8, ... and the 8 lane sums are added in lane order.
-__global__ void __launch_bounds__(256)
+// machine): block = 32 columns x 32 chunk lanes, lane y adds chunks y, y+32, ... and the 32 lane sums are added in lane order.
+__global__ void __launch_bounds__(1024)
 colsum_finalize_wide_kernel(const double* __restrict__ partial, int chunks, int64_t C, float* __restrict__ out, int accumulate) {
-  __shared__ double sm[8][33];
+  __shared__ double sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int64_t c = (int64_t)blockIdx.x * 32 + tx;
   double t = 0;
-  if (c < C) for (int k = ty; k < chunks; k += 8) t += partial[(int64_t)k * C + c];
+  if (c < C) {
+#pragma unroll 4
+    for (int k = ty; k < chunks; k += 32) t += partial[(int64_t)k * C + c];
+  }
   sm[ty][tx] = t;
   __syncthreads();
   if (ty == 0 && c < C) {
     double u = 0;
 #pragma unroll
-    for (int y = 0; y < 8; ++y) u += sm[y][tx];
+    for (int y = 0; y < 32; ++y) u += sm[y][tx];
     out[c] = accumulate ? out[c] + (float)u : (float)u;
   }
 }
@@ -1030,7 +1033,7 @@ extern "C" int cdcmdr_colsum(const void* X, int64_t ld, int is_bf16, int64_t B, 
     if (is_bf16) colsum_vec_kernel<uint16_t, 8><<<vgrid, 256, 0, st>>>((const uint16_t*)X, ld, B, C, ch, partial);
     else colsum_vec_kernel<float, 4><<<vgrid, 256, 0, st>>>((const float*)X, ld, B, C, ch, partial);
     CDC_LAUNCHED();
-    if (ch > 32) colsum_finalize_wide_kernel<<<(unsigned)ceil_div(C, 32), 256, 0, st>>>(partial, ch, C, out, accumulate);
+    if (ch > 32) colsum_finalize_wide_kernel<<<(unsigned)ceil_div(C, 32), 1024, 0, st>>>(partial, ch, C, out, accumulate);
     else colsum_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(partial, ch, C, out, accumulate);
     CDC_LAUNCHED();
     return 0;
