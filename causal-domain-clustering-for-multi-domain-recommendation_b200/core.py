@@ -245,8 +245,16 @@ class Ops:
             return
         split, part, stride = 1, None, 0
         if split_k == "auto":
+            # one persistent CTA per SM walks tiles*split work items: pick the slice count whose (waves x k-blocks per slice) is
+            # smallest - e.g. 40 tiles: 8 slices are 3 waves of 128 k-blocks, 11 slices 3 waves of 94
             tiles = ((M + 127) // 128) * ((N + 255) // 256) * G
-            want = max(1, min(32, (2 * 148 + tiles - 1) // tiles))
+            num_kb = (K + 63) // 64
+            best, want = None, 1
+            for cand in range(1, min(48, num_kb) + 1):
+                per = (num_kb + cand - 1) // cand
+                cost = ((tiles * cand + 147) // 148) * (per + 2)          # + epilogue / pipeline fill per work item
+                if best is None or cost < best:
+                    best, want = cost, cand
             split = self.lib.gemm_bf16_tc_splits(K, want)
         elif split_k > 1:
             split = self.lib.gemm_bf16_tc_splits(K, split_k)

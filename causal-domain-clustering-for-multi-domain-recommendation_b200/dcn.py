@@ -219,19 +219,36 @@ class DCNv2(_CrossModel):
                              in_groups=None)
 
     # ---------------------------------------------------------------- CrossNetV2: x <- x0 * (x W^T) + b + x
-    def _v2_fwd(self, ws, x0: Mat, B) -> Mat:
+    def _v2_tc(self) -> bool:
+        """bf16 path: the D x D contractions of CrossNetV2 run on the tcgen05 GEMM (bf16 operands, fp32 accumulate and fp32 results);
+        the Hadamard / bias / residual stages stay fp32.  TMA needs 16-byte aligned operand pitches."""
+        return self._rt.bf16 and self.embed_output_dim % 8 == 0
+
+    def _v2_operand(self, ws, l, cur: Mat, X: Mat | None, B) -> Mat:
+        """bf16 GEMM operand of the layer-l input: the gathered bf16 embeddings themselves for l = 0, else a bf16 copy of x_l"""
+        if l == 0 and X is not None and X.is_bf16:
+            return X
+        return self._rt.gemm_input(ws, f"cv2.xop{l}", cur, B, self.embed_output_dim)
+
+    def _v2_fwd(self, ws, x0: Mat, B, X: Mat | None = None) -> Mat:
         rt, D = self._rt, self.embed_output_dim
         cur = x0
         for l in range(self.n_cross_layers):
             xw = ws.mat(f"cv2.xw{l}", B, D)
-            rt.ops.gemm_f32(A=cur.ptr, a_rs=cur.ld, a_cs=1, Bt=rt.w(f"crossnet.w.{l}.weight"), b_rs=D, b_cs=1, Cm=xw.ptr, c_rs=D,
-                            M=B, N=D, K=D)
+            wname = f"crossnet.w.{l}.weight"
+            if self._v2_tc():
+                cop = self._v2_operand(ws, l, cur, X, B)
+                rt.ops.gemm_tc(A=cop.ptr, lda=cop.ld, a_rows=B, a_cols=D, a_mn=0, Bt=rt.Wb.data_ptr() + 2 * rt.o(wname), ldb=D,
+                               b_rows=D, b_cols=D, b_mn=0, M=B, N=D, K=D, n_main=0, out_aux=xw.ptr, ld_aux=xw.ld)
+            else:
+                rt.ops.gemm_f32(A=cur.ptr, a_rs=cur.ld, a_cs=1, Bt=rt.w(wname), b_rs=D, b_cs=1, Cm=xw.ptr, c_rs=D,
+                                M=B, N=D, K=D)
             nxt = ws.mat(f"cv2.x{l + 1}", B, D)
             rt.ops.cross_fuse_fwd(x0, cur, xw, D, rt.w(f"crossnet.b.{l}"), nxt, B, D)
             cur = nxt
         return cur
 
-    def _v2_bwd(self, ws, x0: Mat, dout: Mat, B) -> Mat:
+    def _v2_bwd(self, ws, x0: Mat, dout: Mat, B, X: Mat | None = None) -> Mat:
         """dout: fp32 [B, D] gradient of the cross output (consumed: updated in place) -> gradient w.r.t. x0."""
         rt, D, L = self._rt, self.embed_output_dim, self.n_cross_layers
         xs = [x0] + [ws.mat(f"cv2.x{l + 1}", B, D) for l in range(L)]
@@ -239,13 +256,24 @@ class DCNv2(_CrossModel):
         dx0.t[:B * D].zero_()
         dx = dout
         for l in reversed(range(L)):
-            W = rt.w(f"crossnet.w.{l}.weight")
+            wname = f"crossnet.w.{l}.weight"
+            W = rt.w(wname)
             xw = ws.mat(f"cv2.xw{l}", B, D)
             rt.ops.colsum(dx, B, D, rt.g(f"crossnet.b.{l}"))
             dxw = ws.mat("cv2.dxw", B, D)
             rt.ops.cross_fuse_bwd(x0, xw, D, dx, dx0, dxw, B, D)           # dx0 += dx*xw ; dxw = dx*x0
+            if self._v2_tc():
+                dop = rt.gemm_input(ws, "cv2.dxw_op", dxw, B, D)
+                xop = self._v2_operand(ws, l, xs[l], X, B) if l == 0 else ws.mat(f"cv2.xop{l}", B, (D + 7) // 8 * 8, torch.bfloat16)
+                # dW[n, k] = sum_b dxw[b, n] * x_l[b, k]: both operands are read as stored ([B, D], the batch is the reduction index)
+                rt.ops.gemm_tc(A=dop.ptr, lda=dop.ld, a_rows=B, a_cols=D, a_mn=1, Bt=xop.ptr, ldb=xop.ld, b_rows=B, b_cols=D, b_mn=1,
+                               M=D, N=D, K=B, n_main=0, out_aux=rt.g(wname), ld_aux=D, split_k="auto")
+                # dx <- dx + dxw W   (W is [n, k]: the reduction index n is its row)
+                rt.ops.gemm_tc(A=dop.ptr, lda=dop.ld, a_rows=B, a_cols=D, a_mn=0, Bt=rt.Wb.data_ptr() + 2 * rt.o(wname), ldb=D,
+                               b_rows=D, b_cols=D, b_mn=1, M=B, N=D, K=D, n_main=0, out_aux=dx.ptr, ld_aux=dx.ld, accumulate=1)
+                continue
             # dW[n, k] = sum_b dxw[b, n] * x_l[b, k]
-            rt.ops.gemm_f32(A=dxw.ptr, a_rs=1, a_cs=D, Bt=xs[l].ptr, b_rs=1, b_cs=xs[l].ld, Cm=rt.g(f"crossnet.w.{l}.weight"), c_rs=D,
+            rt.ops.gemm_f32(A=dxw.ptr, a_rs=1, a_cs=D, Bt=xs[l].ptr, b_rs=1, b_cs=xs[l].ld, Cm=rt.g(wname), c_rs=D,
                             M=D, N=D, K=B, split_k=rt.ops.pick_split(D, D, 1, B))
             # dx <- dx + dxw W
             rt.ops.gemm_f32(A=dxw.ptr, a_rs=D, a_cs=1, Bt=W, b_rs=1, b_cs=D, Cm=dx.ptr, c_rs=dx.ld, M=B, N=D, K=D, accumulate=1)
@@ -340,7 +368,7 @@ class DCNv2(_CrossModel):
     def _program_fwd(self, ws, X: Mat, B, train):
         rt, D = self._rt, self.embed_output_dim
         x0 = self._x32(ws, X, B)
-        cross = self._mix_fwd(ws, x0, B) if self.use_low_rank_mixture else self._v2_fwd(ws, x0, B)
+        cross = self._mix_fwd(ws, x0, B) if self.use_low_rank_mixture else self._v2_fwd(ws, x0, B, X)
         if self.model_structure == "parallel":
             mlp_out = self._mlp.fwd(ws, X, B, train)
             logit = self._head_fwd(ws, "dnn_linear.weight", cross, mlp_out, B)
@@ -359,7 +387,7 @@ class DCNv2(_CrossModel):
         x0 = ws.mat("X32", B, D) if X.is_bf16 else X
         cross = self._cross_out(ws, B)
         mlp_out = self._mlp._act(ws, len(self.mlp_dims) - 1, B)
-        cross_bwd = self._mix_bwd if self.use_low_rank_mixture else self._v2_bwd
+        cross_bwd = self._mix_bwd if self.use_low_rank_mixture else (lambda w, a, d, n: self._v2_bwd(w, a, d, n, X))
         dX = ws.mat("dX", B, D)
         if self.model_structure == "parallel":
             dcross, dmlp = self._head_bwd(ws, "dnn_linear.weight", cross, mlp_out, dlogits, B)
