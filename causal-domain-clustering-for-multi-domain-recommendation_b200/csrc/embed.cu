@@ -121,6 +121,45 @@ embed_gather_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ o
   }
 }
 
+// One thread per (sample, field) row: the index is read once per row, then the row's EV 128-bit loads are issued back to back
+// (EV x 16 bytes in flight per thread - the lane-per-quad kernel above has 16 and runs out of resident threads: 2048 x 148
+// threads x 16 B = 4.8 MB in flight bound it to ~4 TB/s on random 64-byte rows).  Same bytes, same order: bit-exact.
+template <int EV>
+__global__ void __launch_bounds__(256)
+embed_gather_rows_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ offsets, const float* __restrict__ table,
+                         float* __restrict__ out_f32, uint16_t* __restrict__ out_bf16, int64_t ld_bf16, int64_t B, int F,
+                         int64_t V, int* __restrict__ oob) {
+  constexpr int E = 4 * EV;
+  const int64_t total = B * (int64_t)F;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b, f;
+    split_idx(i, F, b, f);
+    const int64_t row = (int64_t)__ldg(x + i) + __ldg(offsets + f);
+    const bool ok = row >= 0 && row < V;
+    float4 t[EV];
+    const float4* src = reinterpret_cast<const float4*>(table + (ok ? row : 0) * E);
+#pragma unroll
+    for (int k = 0; k < EV; ++k) t[k] = __ldg(src + k);
+    if (!ok) {
+      if (oob) *oob = 1;
+#pragma unroll
+      for (int k = 0; k < EV; ++k) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (out_f32) {
+      float4* o = reinterpret_cast<float4*>(out_f32 + i * E);
+#pragma unroll
+      for (int k = 0; k < EV; ++k) o[k] = t[k];
+    }
+    if (out_bf16) {
+      uint4* o = reinterpret_cast<uint4*>(out_bf16 + b * ld_bf16 + f * E);
+#pragma unroll
+      for (int k = 0; k < EV / 2; ++k)
+        o[k] = make_uint4(pack_bf16x2(t[2 * k].x, t[2 * k].y), pack_bf16x2(t[2 * k].z, t[2 * k].w),
+                          pack_bf16x2(t[2 * k + 1].x, t[2 * k + 1].y), pack_bf16x2(t[2 * k + 1].z, t[2 * k + 1].w));
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ plan
 __global__ void plan_keys_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ offsets, int64_t n, int F,
                                  int64_t V, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
@@ -436,7 +475,14 @@ extern "C" int cdcmdr_embed_gather_fwd(const int32_t* x, const int64_t* offsets,
   CDC_REQUIRE(B >= 0 && F > 0 && E > 0 && V > 0, "bad gather shape");
   if (B == 0) return 0;
   CDC_REQUIRE(out_f32 || out_bf16, "gather needs an output");
-  if (E % 4 == 0 && (!out_bf16 || ld_bf16 % 4 == 0)) {
+  const bool rows_ok = (E == 16 || E == 32 || E == 64) && ((uintptr_t)table % 16) == 0 && (!out_f32 || ((uintptr_t)out_f32 % 16) == 0) &&
+                       (!out_bf16 || (ld_bf16 % 8 == 0 && ((uintptr_t)out_bf16 % 16) == 0));
+  if (rows_ok) {
+    const int grid = grid_for(B * F, 256);
+    if (E == 16) embed_gather_rows_kernel<4><<<grid, 256, 0, to_stream(s)>>>(x, offsets, table, out_f32, out_bf16, ld_bf16, B, F, V, oob_flag);
+    else if (E == 32) embed_gather_rows_kernel<8><<<grid, 256, 0, to_stream(s)>>>(x, offsets, table, out_f32, out_bf16, ld_bf16, B, F, V, oob_flag);
+    else embed_gather_rows_kernel<16><<<grid, 256, 0, to_stream(s)>>>(x, offsets, table, out_f32, out_bf16, ld_bf16, B, F, V, oob_flag);
+  } else if (E % 4 == 0 && (!out_bf16 || ld_bf16 % 4 == 0)) {
     const int64_t work = B * F * (E / 4);
     embed_gather_kernel<4, 1><<<grid_for(work, 256), 256, 0, to_stream(s)>>>(x, offsets, table, out_f32, out_bf16, ld_bf16, B, F, E, V, oob_flag);
   } else {

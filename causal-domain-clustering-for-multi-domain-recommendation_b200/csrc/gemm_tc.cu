@@ -96,6 +96,41 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// descriptor given as its low word; the high word (SBO 1024 B >> 4 at [32,46), version 1 at [46,48), SWIZZLE_128B = 2 at [61,64)) is constant
+constexpr uint32_t kDescHi = 64u | (1u << 14) | (2u << 29);
+__device__ __forceinline__ void tc_mma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+__device__ __forceinline__ void tc_mma2_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "mov.b64 da, {%1, %5};\n"
+      "mov.b64 db, {%2, %5};\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc), "r"(accumulate), "r"(kDescHi) : "memory");
+}
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n" : "=r"(pred));
+  return pred != 0;
+}
 // ---- 2-CTA (cta_group::2) helpers: the CTA pair of a cluster works on one 256 x block_n tile; rank 0 issues the MMAs
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -356,12 +391,24 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // =============================== MMA issuer ===============================
     if (CTA2 && rank == 1) {
       // rank 1 issues no MMAs; its operand loads are counted on rank 0's barriers by the TMA unit itself
-    } else if (lane == 0) {
+    } else {
+      // The whole warp walks the loop converged (every lane polls the barriers) and ONE elected lane issues: everything the
+      // tcgen05 instructions take is warp-uniform, so it lives in uniform registers - a `lane == 0` branch made the compiler
+      // rebuild both 64-bit descriptors and broadcast five registers per MMA (~150 instructions per k-block on a scheduler
+      // the issuer shares with four busy epilogue warps).  Descriptors are a constant high word + a low word that advances by
+      // a constant per k-step and per stage.
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 [4,6)=1, A=BF16 [7,10)=1, B=BF16 [10,13)=1,
       // a_major bit 15, b_major bit 16, N>>3 [17,23), M>>4 [24,29)
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.a_mn_major ? 1 : 0) << 15) |
                              ((uint32_t)(p.b_mn_major ? 1 : 0) << 16) | ((uint32_t)(p.block_n >> 3) << 17) |
                              ((uint32_t)((CTA2 ? 2 * TC_BLOCK_M : TC_BLOCK_M) >> 4) << 24);
+      // shared-memory descriptor low word: start >> 4 [0,14) | LBO >> 4 [16,30).  K-major: LBO 16 B, a k-step of 16 bf16 is 32 bytes
+      // further inside the 128-byte swizzle row; MN-major: LBO 8192 B, 16 k-rows are 2048 bytes further.  High word (SBO 1024 B,
+      // version 1, SWIZZLE_128B) is the constant kDescHi inside the wrappers.
+      const uint32_t a_flag = p.a_mn_major ? (512u << 16) : (1u << 16), b_flag = p.b_mn_major ? (512u << 16) : (1u << 16);
+      const uint32_t a_kstep = p.a_mn_major ? 128u : 2u, b_kstep = p.b_mn_major ? 128u : 2u;
+      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | a_flag, b_lo0 = ((smem_u32(smem) + TC_A_BYTES) >> 4) | b_flag;
+      const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
@@ -371,27 +418,31 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         { TC_PROF_T0();
           if (CTA2) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1); else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
-          TC_PROF_ADD(1); }
+          if (lane == 0) TC_PROF_ADD(1); }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
         for (int kb = kb0; kb < kb1; ++kb) {
           { TC_PROF_T0();
             if (CTA2) mbar_wait_cluster(full0 + 8 * stage, phase); else mbar_wait(full0 + 8 * stage, phase);
-            TC_PROF_ADD(2); }
+            if (lane == 0) TC_PROF_ADD(2); }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
+          __syncwarp();
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
-            // K-major: 16 bf16 = 32 bytes further inside the 128-byte swizzle row; MN-major: 16 k-rows = 2048 bytes further
-            const uint64_t ad = p.a_mn_major ? make_smem_desc(sa + k * 2048, 8192, 1024) : make_smem_desc(sa + k * 32, 16, 1024);
-            const uint64_t bd = p.b_mn_major ? make_smem_desc(sb + k * 2048, 8192, 1024) : make_smem_desc(sb + k * 32, 16, 1024);
-            if (CTA2) tc_mma2_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            else tc_mma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < TC_BLOCK_K / 16; ++k) {
+              if (CTA2) tc_mma2_bf16_lo(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+              else tc_mma_bf16_lo(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+            if (CTA2) tc_commit2_mc(empty0 + 8 * stage); else tc_commit(empty0 + 8 * stage);   // frees the smem slot(s) when these MMAs retire
           }
-          if (CTA2) tc_commit2_mc(empty0 + 8 * stage); else tc_commit(empty0 + 8 * stage);   // frees the smem slot(s) when these MMAs retire
+          __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        if (CTA2) tc_commit2_mc(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc);         // accumulator complete -> epilogue(s)
+        if (elect_one()) {
+          if (CTA2) tc_commit2_mc(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc);         // accumulator complete -> epilogue(s)
+        }
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }

@@ -321,9 +321,9 @@ class BaseModel(nn.Module):
     def _bump_batches_tracked(self, B):
         if B == 1:
             return
-        for name, buf in self.named_buffers():
-            if name.endswith("num_batches_tracked") and self._tracks(name):
-                buf += 1
+        bufs = [buf for name, buf in self.named_buffers() if name.endswith("num_batches_tracked") and self._tracks(name)]
+        if bufs:
+            torch._foreach_add_(bufs, 1)                     # one multi-tensor launch instead of one per BatchNorm module
 
     def _tracks(self, name):
         return True
