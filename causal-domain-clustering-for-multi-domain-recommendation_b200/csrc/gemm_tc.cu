@@ -210,6 +210,8 @@ struct TcParams {
   int32_t tma_store;                         // out_main is written through map_c (alignment checked by the host)
   int32_t tma_aux;                           // out_aux (fp32) is written through map_d
   int32_t tma_mask;                          // the ReLU mask (forward activation) is read through map_m into shared memory
+  int32_t a_res;                             // A-resident sweep: see the kernel comment
+  int64_t tiles_lo; int32_t tiles_rem;       // a_res: CTA c owns tiles [c*lo + min(c, rem), +lo + (c < rem))
   unsigned long long* prof;                  // diagnostics: cycles spent in each pipeline wait, summed over CTAs (NULL = off)
   int32_t debug;                             // probe only (cdcmdr_gemm_bf16_tc_mode bits 4..6): 16 = epilogue drains nothing, 64 = tcgen05.ld only,
                                              // 32 = everything but the TMA store.  Results are garbage; never set by the product path.
@@ -301,26 +303,36 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d,
                     const __grid_constant__ CUtensorMap map_m, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B tiles need 1024-byte alignment
-  uint8_t* staging = smem + p.stages * p.stage_bytes;
+  // A-resident sweep (p.a_res; short K loops with several column tiles): a CTA owns a CONTIGUOUS range of tiles, column tile
+  // fastest, so consecutive tiles share their 128 rows of A.  All k-blocks of that A panel sit in dedicated slots, loaded once per
+  // row tile; only B streams through the ring.  At M=65536 N=2560 K=368 the operand fill drops from 288 KB to ~200 KB per tile
+  // (1.45 GB -> 1.0 GB per launch): the probes showed the main loop waiting for operands half of its time at the L2 -> SM rate.
+  const uint32_t a_region = p.a_res ? (uint32_t)p.num_kb * TC_A_BYTES : 0u;      // [num_kb][128 x 64] resident A panel
+  const uint32_t b_in_stage = p.a_res ? 0u : (uint32_t)TC_A_BYTES;              // B's offset inside a ring stage
+  uint8_t* ring = smem + a_region;
+  uint8_t* staging = ring + p.stages * p.stage_bytes;
   float* bias_s = (float*)(staging + TC_STAGING_BYTES);
   uint64_t* bars = (uint64_t*)((uint8_t*)bias_s + TC_BIAS_BYTES);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_MAX_STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * TC_MAX_STAGES), tempty0 = smem_u32(bars + 2 * TC_MAX_STAGES + 2);
   const uint32_t pfull0 = smem_u32(bars + 2 * TC_MAX_STAGES + 4);            // rank 0 only: "rank 1's stage is full"
   uint32_t* tmem_slot = (uint32_t*)(bars + 3 * TC_MAX_STAGES + 4);
+  const uint32_t afull0 = smem_u32(bars + 48), aempty0 = smem_u32(bars + 56);   // a_res: per k-block "A slot full / free"
   const uint32_t mbar0 = smem_u32(bars + 32);                                 // one "mask tile landed" barrier per epilogue warp
   uint8_t* mask_s = (uint8_t*)bars + TC_BAR_BYTES;                             // [TC_EPI_WARPS][32 rows x 64 B], 64B-swizzled
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
   const long long prof_cta0 = p.prof ? clock64() : 0;
-  const int64_t tile0 = CTA2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
-  const int64_t tile_step = CTA2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
+  const int64_t cta_id = CTA2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t tile0 = p.a_res ? cta_id * p.tiles_lo + min(cta_id, (int64_t)p.tiles_rem) : cta_id;
+  const int64_t tile_step = p.a_res ? 1 : (CTA2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x);
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();                          // the swizzle atoms below assume it
     for (int i = 0; i < p.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); mbar_init(pfull0 + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
     for (int i = 0; i < TC_EPI_WARPS; ++i) mbar_init(mbar0 + 8 * i, 1);
+    for (int i = 0; i < 8; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -341,14 +353,15 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   // p.n_tiles_m counts 128-row tiles (CTA2: 256-row pair tiles; this CTA's rows are tile (2*mt + rank))
   const int64_t tiles_per_group = (int64_t)p.n_tiles_m * p.n_tiles_n * p.split_k;
-  const int64_t total_tiles = tiles_per_group * p.G;
+  const int64_t all_tiles = tiles_per_group * p.G;
+  const int64_t total_tiles = p.a_res ? min(all_tiles, tile0 + p.tiles_lo + (cta_id < p.tiles_rem ? 1 : 0)) : all_tiles;   // end of this CTA's tiles
   const int b_cols = CTA2 ? (p.block_n >> 1) : p.block_n;          // N columns of the B tile held by this CTA
-  const uint32_t stage_tx = (uint32_t)(TC_A_BYTES + (p.b_mn_major ? ((b_cols + 63) / 64) * 64 : b_cols) * TC_BLOCK_K * 2);
+  const uint32_t stage_tx = (uint32_t)((p.a_res ? 0 : TC_A_BYTES) + (p.b_mn_major ? ((b_cols + 63) / 64) * 64 : b_cols) * TC_BLOCK_K * 2);
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0, a_phase = 0;
       const uint32_t full_pair0 = CTA2 ? mapa_u32(full0, 0) : full0;               // rank 0's "stage full" barriers
       for (int64_t tile = tile0; tile < total_tiles; tile += tile_step) {
         const int g = (int)(tile / tiles_per_group);
@@ -360,11 +373,17 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
         const int32_t a_mn = (int32_t)(g * p.a_gmn + mt * TC_BLOCK_M);
         const int32_t b_mn = (int32_t)(g * p.b_gmn + (int64_t)nt * p.block_n + (CTA2 ? (int64_t)rank * b_cols : 0));
+        const bool new_run = p.a_res && (tile == tile0 || nt == 0);          // first tile of a row tile in this CTA's range
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (new_run) {                                                     // this k-block of the new A panel, once per row tile
+            mbar_wait(aempty0 + 8 * kb, a_phase ^ 1);
+            mbar_expect_tx(afull0 + 8 * kb, TC_A_BYTES);
+            tma_load_2d(smem_u32(smem + kb * TC_A_BYTES), &map_a, afull0 + 8 * kb, (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), a_mn);
+          }
           { TC_PROF_T0();
             if (CTA2) mbar_wait_cluster(empty0 + 8 * stage, phase ^ 1); else mbar_wait(empty0 + 8 * stage, phase ^ 1);
             TC_PROF_ADD(0); }
-          const uint32_t sa = smem_u32(smem + stage * p.stage_bytes), sb = sa + TC_A_BYTES;
+          const uint32_t sa = smem_u32(ring + stage * p.stage_bytes), sb = sa + b_in_stage;
           const int32_t ak = (int32_t)(g * p.a_gk + (int64_t)kb * TC_BLOCK_K), bk = (int32_t)(g * p.b_gk + (int64_t)kb * TC_BLOCK_K);
           if (CTA2) {
             // both CTAs' bytes are counted on rank 0's barrier of this stage; rank 0 announces the total
@@ -379,12 +398,14 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           }
           const uint32_t bar = full0 + 8 * stage;
           mbar_expect_tx(bar, stage_tx);
-          if (!p.a_mn_major) tma_load_2d(sa, &map_a, bar, ak, a_mn);                    // box [128 rows (m) x 64 (k)]
+          if (p.a_res) {}                                                               // A panel is resident
+          else if (!p.a_mn_major) tma_load_2d(sa, &map_a, bar, ak, a_mn);              // box [128 rows (m) x 64 (k)]
           else { tma_load_2d(sa, &map_a, bar, a_mn, ak); tma_load_2d(sa + 8192, &map_a, bar, a_mn + 64, ak); }   // 2 x [64 (k) x 64 (m)]
           if (!p.b_mn_major) tma_load_2d(sb, &map_b, bar, bk, b_mn);                    // box [b_cols rows (n) x 64 (k)]
           else for (int j = 0; j * 64 < b_cols; ++j) tma_load_2d(sb + 8192 * j, &map_b, bar, b_mn + 64 * j, bk);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        if (new_run) a_phase ^= 1;
       }
     }
   } else if (warp == 1) {
@@ -407,7 +428,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       // version 1, SWIZZLE_128B) is the constant kDescHi inside the wrappers.
       const uint32_t a_flag = p.a_mn_major ? (512u << 16) : (1u << 16), b_flag = p.b_mn_major ? (512u << 16) : (1u << 16);
       const uint32_t a_kstep = p.a_mn_major ? 128u : 2u, b_kstep = p.b_mn_major ? 128u : 2u;
-      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | a_flag, b_lo0 = ((smem_u32(smem) + TC_A_BYTES) >> 4) | b_flag;
+      // a_res: A k-block kb sits in slot kb of the resident panel (16 KB apart); otherwise at the head of ring stage `stage`
+      const uint32_t a_lo0 = (smem_u32(smem) >> 4) | a_flag, b_lo0 = ((smem_u32(ring) + b_in_stage) >> 4) | b_flag;
+      uint32_t a_phase = 0;
       const uint32_t stage_step = (uint32_t)p.stage_bytes >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
@@ -416,6 +439,9 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int z = (int)(r % p.split_k);
         const int kb0 = z * p.kb_per_split;
         const int kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+        const int nt_i = (int)((r / p.split_k) % p.n_tiles_n);
+        const bool new_run = p.a_res && (tile == tile0 || nt_i == 0);
+        const bool end_run = p.a_res && (tile + 1 == total_tiles || nt_i == p.n_tiles_n - 1);
         { TC_PROF_T0();
           if (CTA2) mbar_wait_cluster(tempty0 + 8 * acc, acc_phase ^ 1); else mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1);
           if (lane == 0) TC_PROF_ADD(1); }
@@ -423,10 +449,12 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * TC_MAX_N);
         for (int kb = kb0; kb < kb1; ++kb) {
           { TC_PROF_T0();
+            if (new_run) mbar_wait(afull0 + 8 * kb, a_phase);
             if (CTA2) mbar_wait_cluster(full0 + 8 * stage, phase); else mbar_wait(full0 + 8 * stage, phase);
             if (lane == 0) TC_PROF_ADD(2); }
           tc_fence_after();
-          const uint32_t a_lo = a_lo0 + (uint32_t)stage * stage_step, b_lo = b_lo0 + (uint32_t)stage * stage_step;
+          const uint32_t a_lo = a_lo0 + (p.a_res ? (uint32_t)kb * (TC_A_BYTES >> 4) : (uint32_t)stage * stage_step);
+          const uint32_t b_lo = b_lo0 + (uint32_t)stage * stage_step;
           __syncwarp();
           if (elect_one()) {
 #pragma unroll
@@ -435,6 +463,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               else tc_mma_bf16_lo(tmem_d, a_lo + k * a_kstep, b_lo + k * b_kstep, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
             if (CTA2) tc_commit2_mc(empty0 + 8 * stage); else tc_commit(empty0 + 8 * stage);   // frees the smem slot(s) when these MMAs retire
+            if (end_run) tc_commit(aempty0 + 8 * kb);       // last column tile of this row tile: the A slot may take the next panel
           }
           __syncwarp();
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -443,6 +472,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           if (CTA2) tc_commit2_mc(tfull0 + 8 * acc); else tc_commit(tfull0 + 8 * acc);         // accumulator complete -> epilogue(s)
         }
         __syncwarp();
+        if (new_run) a_phase ^= 1;
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -727,7 +757,7 @@ __global__ void transpose_bf16_kernel(const uint16_t* __restrict__ src, int64_t 
   }
 }
 
-// bit 0: single-CTA tiles only; bit 2: CTA pairs whenever legal (default 0: pairs only for long K loops)
+// bit 0: single-CTA tiles only; bit 1: no A-resident sweep; bit 2: CTA pairs whenever legal (default 0: pairs only for long K loops)
 static std::atomic<int> g_tc_mode{0};
 static std::atomic<unsigned long long*> g_tc_prof{nullptr};
 
@@ -845,13 +875,23 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
     if (int rc = make_map(&mm, p->mask, p->M, (p->G - 1) * p->mask_gn + p->n_main, p->ld_mask, 32u, false, true)) return rc;
   }
   const int b_bytes = (q.b_mn_major ? (int)ceil_div(b_cols, 64) * 64 : b_cols) * TC_BLOCK_K * 2;
-  q.stage_bytes = TC_A_BYTES + b_bytes;
   const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + (q.tma_mask ? TC_MASK_BYTES : 0);
-  int stages = (TC_SMEM_LIMIT - fixed) / q.stage_bytes;
+  // A-resident sweep: K-major A, no split, a short K loop whose whole A panel fits next to >= 3 ring stages of B, and at least
+  // two column tiles to sweep.  Mode bit 1 switches it off.
+  const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
+  q.a_res = (!cta2 && !(mode & 2) && !q.a_mn_major && q.split_k == 1 && q.n_tiles_n >= 2 && q.num_kb <= 8 &&
+             q.num_kb * TC_A_BYTES + 3 * b_bytes + fixed <= TC_SMEM_LIMIT) ? 1 : 0;
+  const int a_region = q.a_res ? q.num_kb * TC_A_BYTES : 0;
+  q.stage_bytes = (q.a_res ? 0 : TC_A_BYTES) + b_bytes;
+  int stages = (TC_SMEM_LIMIT - fixed - a_region) / q.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CDC_REQUIRE(stages >= 2, "shared memory budget too small for a 2-stage pipeline");
   q.stages = stages;
-  const int smem_bytes = stages * q.stage_bytes + fixed;
+  const int smem_bytes = a_region + stages * q.stage_bytes + fixed;
+  {
+    const int64_t ctas = total < kNumSMs ? total : kNumSMs;
+    q.tiles_lo = total / ctas; q.tiles_rem = (int32_t)(total % ctas);
+  }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -859,7 +899,6 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
     CDC_CHECK(cudaFuncSetAttribute(gemm_bf16_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_LIMIT));
     attr_set = true;
   }
-  const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
   if (!cta2) {
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
     gemm_bf16_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, mm, q);

@@ -34,7 +34,7 @@ CASES = {
 }
 
 
-@pytest.fixture(params=[4, 1, 0], ids=["cta_pairs", "single_cta", "auto"])
+@pytest.fixture(params=[4, 1, 3, 0], ids=["cta_pairs", "single_cta", "single_cta_streamed_a", "auto"])
 def tc_mode(request):
     """cdcmdr_gemm_bf16_tc tile mode: CTA pairs (cta_group::2) where the shape allows / single-CTA tiles only."""
     lib = cm._lib.load()
