@@ -431,6 +431,20 @@ class BaseModel(nn.Module):
         optimizer.tick(rt)                                   # t += 1, dropout seed, Adam scalars
         rt.refresh_operands()
         X = self._gather(ws, x, B)
+        # The backward plan of the embedding (sort of the step's indices into segments) only needs x: it runs on a side stream
+        # next to the model program (a parallel branch of the CUDA graph) and is joined before the segment sums.
+        table = self.embedding.embedding_dict.weight
+        V, E, F = table.shape[0], self.embed_dim, self.field_num
+        sharded = rt.dp is not None and rt.dp.shard
+        plan, side = None, rt.side_stream()
+        if not sharded:
+            if side is not None:
+                main = torch.cuda.current_stream(rt.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
+            else:
+                plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
         logits, lin = self._program_fwd(ws, X, B, True, **kw)
         R, T = self._head_shape(B, **kw)                     # R != B only when the program routed rows (STAR with x_group)
         pred = ws.get("pred", (R, T))
@@ -451,17 +465,23 @@ class BaseModel(nn.Module):
         dX = self._program_bwd(ws, X, B, True, Mat(dlogits, 0, T), **kw)
         if dp is not None:
             dp.all_reduce_sum(rt.G)                          # dense gradients: sum over replicas of d(global mean loss)
-        rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
-        rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
-        table = self.embedding.embedding_dict.weight
-        V, E, F = table.shape[0], self.embed_dim, self.field_num
+        # the dense arena's regulariser + Adam do not touch the table: second branch, next to the embedding backward
+        if side is not None:
+            main = torch.cuda.current_stream(rt.device)
+            main.wait_stream(side)                           # joins the plan branch
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
+                rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
+        else:
+            rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
+            rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
         l2t = self._l2_table()
         if dp is not None and dp.shard:
             dp.embed_backward(ws, dX, B, l2t, sums[1:2])     # row gradients to the owners; owner-side segment sum + Adam
         else:
             if dp is not None:
                 raise NotImplementedError("cdcmdr: data-parallel replicas need the row-sharded table (shard_embedding=True)")
-            plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
             if self._table_state is None:
                 self._table_state = (torch.zeros_like(table), torch.zeros_like(table))
             m, v = self._table_state
@@ -469,6 +489,8 @@ class BaseModel(nn.Module):
             if lazy:
                 rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[1:2])
             rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[1:2], lazy=lazy)
+        if side is not None:
+            torch.cuda.current_stream(rt.device).wait_stream(side)      # joins the dense-optimizer branch
         if dp is not None:
             dp.all_reduce_sum(sums[0:2])                     # BCE sum and table sum-of-squares are per-rank partials
         return dict(sums=sums, pred=pred[:R * T].view(R, T), psel=psel[:R], B=n_global, l2_table=l2t)

@@ -117,6 +117,14 @@ class Runtime:
     def b(self, name, extra=0) -> int:
         return self.Bf.data_ptr() + 4 * (self.buffers.off[name] + extra)
 
+    def side_stream(self):
+        """Second CUDA stream for the step's independent branches (None on a non-CUDA device, i.e. under the host emulator)."""
+        if self.device.type != "cuda":
+            return None
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(self.device)
+        return self._side
+
     def ws(self, B) -> Workspace:
         w = self._ws.get(B)
         if w is None:
