@@ -275,7 +275,7 @@ class BaseModel(nn.Module):
             raise ValueError(f"cdcmdr: expected indices of shape [B, {self.field_num}]")
 
     # ---------------------------------------------------------------- forward / backward drivers
-    def _gather(self, ws, x, B):
+    def _gather(self, ws, x, B, plan_ahead=False):
         rt = self._rt
         E, F = self.embed_dim, self.field_num
         table = self.embedding.embedding_dict.weight
@@ -283,7 +283,7 @@ class BaseModel(nn.Module):
         if rt.bf16 and (F * E) % 8:
             raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
         if rt.dp is not None and rt.dp.shard:
-            rt.dp.embed_forward(ws, x, B, X)          # row-sharded table: indices to the owners, rows back (parallel.py)
+            rt.dp.embed_forward(ws, x, B, X, plan_ahead)   # row-sharded table: indices to the owners, rows back (parallel.py)
             return X
         if rt.bf16:
             rt.ops.embed_gather(x, self.embedding.offsets_dev, table, None, X, B, F, E, table.shape[0])
@@ -430,7 +430,7 @@ class BaseModel(nn.Module):
         rt.ensure_opt_state()
         optimizer.tick(rt)                                   # t += 1, dropout seed, Adam scalars
         rt.refresh_operands()
-        X = self._gather(ws, x, B)
+        X = self._gather(ws, x, B, plan_ahead=True)
         # The backward plan of the embedding (sort of the step's indices into segments) only needs x: it runs on a side stream
         # next to the model program (a parallel branch of the CUDA graph) and is joined before the segment sums.
         table = self.embedding.embedding_dict.weight
@@ -468,7 +468,8 @@ class BaseModel(nn.Module):
         # the dense arena's regulariser + Adam do not touch the table: second branch, next to the embedding backward
         if side is not None:
             main = torch.cuda.current_stream(rt.device)
-            main.wait_stream(side)                           # joins the plan branch
+            if not sharded:
+                main.wait_stream(side)                       # joins the plan branch (the sharded path waits for its plan in dp.embed_backward)
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])

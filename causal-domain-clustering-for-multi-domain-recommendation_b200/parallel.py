@@ -101,8 +101,10 @@ class DataParallel:
             self._moments = (torch.zeros_like(sv), torch.zeros_like(sv))
         return self._moments
 
-    def embed_forward(self, ws, x, B, X: Mat):
-        """x: this rank's [B, F] int32 indices -> X[B, F*E] (activation dtype) through the owners of each field."""
+    def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False):
+        """x: this rank's [B, F] int32 indices -> X[B, F*E] (activation dtype) through the owners of each field.
+        plan_ahead (training step): the owner-side backward plan over the received indices starts on the side stream as soon as
+        they have arrived and runs next to the model program."""
         rt = self.model._rt
         ops, N, E, F = rt.ops, self.world, self.E, self.F
         nf_me = self.f1 - self.f0
@@ -113,6 +115,17 @@ class DataParallel:
                 ops.copy2d(x.data_ptr() + 4 * f0, F, send_ids.data_ptr() + 4 * B * f0, f1 - f0, B, f1 - f0, 4)
         recv_ids = ws.get("dp.recv_ids", (N * B * max(nf_me, 1),), torch.int32)
         self._all_to_all(recv_ids[:N * B * nf_me], send_ids[:B * F], [B * nf_me] * N, [B * n for n in self.nf])
+        self._plan, self._plan_event = None, None
+        side = rt.side_stream() if plan_ahead else None
+        if nf_me and plan_ahead:
+            Vl = self.shard_view().shape[0]
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(rt.device))
+                with torch.cuda.stream(side):
+                    self._plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+                    self._plan_event = side.record_event()
+            else:
+                self._plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
         esz = 2 if rt.bf16 else 4
         rows_send = ws.get("dp.rows_send", (N * B * max(nf_me, 1) * E,), rt.act_dtype)
         if nf_me:
@@ -146,7 +159,12 @@ class DataParallel:
         shard = self.shard_view()
         Vl = shard.shape[0]
         recv_ids = ws.get("dp.recv_ids", (N * B * nf_me,), torch.int32)
-        plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+        plan = getattr(self, "_plan", None)
+        if plan is None:
+            plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+        elif self._plan_event is not None:
+            torch.cuda.current_stream(rt.device).wait_event(self._plan_event)
+        self._plan, self._plan_event = None, None
         m, v = self.moments()
         lazy = self.model.embedding_update == "sparse_lazy"
         if lazy:
