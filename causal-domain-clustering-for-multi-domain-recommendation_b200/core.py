@@ -210,6 +210,10 @@ class Ops:
         """strided 2-D copy (cdcmdr_permute_rows with the identity permutation)"""
         self.lib.permute_rows(src_addr, lds, None, rows, cols, elt_bytes, dst_addr, ldd, 0, self.stream)
 
+    def copy2d_batched(self, src_addr, src_bs, lds, dst_addr, dst_bs, ldd, batches, rows, cols, elt_bytes):
+        """`batches` strided 2-D copies in one launch (element strides)"""
+        self.lib.copy2d_batched(src_addr, src_bs, lds, dst_addr, dst_bs, ldd, batches, rows, cols, elt_bytes, self.stream)
+
     # ---------------------------------------------------------------- Linear(d, 1) heads
     def rowdot_fwd(self, A: Mat, w_addr, b_addr, out: Mat, B, G, d):
         self.lib.rowdot_fwd(A.ptr, A.ld, 1 if A.is_bf16 else 0, w_addr, b_addr, out.ptr, out.ld, B, G, d, self.stream)

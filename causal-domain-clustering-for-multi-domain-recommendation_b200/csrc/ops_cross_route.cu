@@ -208,6 +208,18 @@ __global__ void permute_rows_kernel(const V* __restrict__ src, int64_t lds, cons
   }
 }
 
+template <typename V>
+__global__ void copy2d_batched_kernel(const V* __restrict__ src, int64_t src_bs, int64_t lds, V* __restrict__ dst, int64_t dst_bs, int64_t ldd,
+                                      int64_t batches, int64_t rows, int64_t cols) {
+  const int64_t per = rows * cols, total = batches * per;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t b, rc, r, c;
+    split_idx(i, per, b, rc);
+    split_idx(rc, cols, r, c);
+    dst[b * dst_bs + r * ldd + c] = src[b * src_bs + r * lds + c];
+  }
+}
+
 __global__ void domain_to_group_kernel(const int32_t* __restrict__ x, int64_t B, int F, int domain_idx,
                                        const int64_t* __restrict__ d2g, int n_domain, int64_t* __restrict__ groups) {
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
@@ -323,6 +335,20 @@ extern "C" int cdcmdr_permute_rows(const void* src, int64_t lds, const int32_t* 
   } else {
     permute_rows_kernel<uint64_t><<<grid_1d(n * cols, 256), 256, 0, st>>>((const uint64_t*)src, lds, perm, n, cols, (uint64_t*)dst, ldd, scatter);
   }
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_copy2d_batched(const void* src, int64_t src_bs, int64_t lds, void* dst, int64_t dst_bs, int64_t ldd, int64_t batches,
+                                     int64_t rows, int64_t cols, int elt_bytes, cdcmdr_stream_t s) {
+  CDC_REQUIRE(elt_bytes == 2 || elt_bytes == 4, "element size must be 2 or 4 bytes");
+  if (batches <= 0 || rows <= 0 || cols <= 0) return 0;
+  CDC_REQUIRE(src && dst, "null copy operand");
+  const int grid = grid_1d(batches * rows * cols, 256);
+  if (elt_bytes == 4)
+    copy2d_batched_kernel<uint32_t><<<grid, 256, 0, to_stream(s)>>>((const uint32_t*)src, src_bs, lds, (uint32_t*)dst, dst_bs, ldd, batches, rows, cols);
+  else
+    copy2d_batched_kernel<uint16_t><<<grid, 256, 0, to_stream(s)>>>((const uint16_t*)src, src_bs, lds, (uint16_t*)dst, dst_bs, ldd, batches, rows, cols);
   CDC_LAUNCHED();
   return 0;
 }

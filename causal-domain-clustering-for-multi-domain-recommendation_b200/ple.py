@@ -154,12 +154,29 @@ class PLE(BaseModel):
         """(first weight row in cgc.gW, rows, packed row, input block) per gate"""
         return [(r0, r1 - r0, c0, blk) for (blk, r0, r1, c0) in lv.gate_groups]
 
+    def _gate_runs(self, lv):
+        """The gate blocks grouped into arithmetic runs: (r0, rows, c0, blk, n_blocks, d_r0, d_c0, d_blk) - every block of a run has
+        `rows` rows and starts d_r0 weight rows / d_c0 packed rows / d_blk input blocks after the previous one (the T task gates
+        of a level are one run; the shared gate of a non-last level is a run of its own)."""
+        runs = []
+        for (r0, n, c0, blk) in self._gate_blocks(lv):
+            if runs:
+                pr0, pn, pc0, pblk, nb, dr, dc, db = runs[-1]
+                lr0, lc0, lblk = pr0 + (nb - 1) * dr, pc0 + (nb - 1) * dc, pblk + (nb - 1) * db
+                step = (r0 - lr0, c0 - lc0, blk - lblk)
+                if n == pn and (nb == 1 or step == (dr, dc, db)):
+                    runs[-1] = (pr0, pn, pc0, pblk, nb + 1, *step)
+                    continue
+            runs.append((r0, n, c0, blk, 1, 0, 0, 0))
+        return runs
+
     def _pack_gates(self, l, lv):
         rt, K = self._rt, lv.K
         ops, ldw = rt.ops, lv.n_in * lv.K
-        for (r0, n, c0, blk) in self._gate_blocks(lv):
-            ops.copy2d(rt.w(f"cgc{l}.gW", r0 * K), K, rt.w(f"cgc{l}.Wbd", c0 * ldw + blk * K), ldw, n, K, 4)
-            ops.copy2d(rt.w(f"cgc{l}.gb", r0), n, rt.w(f"cgc{l}.bbd", c0), n, 1, n, 4)
+        for (r0, n, c0, blk, nb, dr, dc, db) in self._gate_runs(lv):       # runs of equally spaced, equally sized gate blocks
+            ops.copy2d_batched(rt.w(f"cgc{l}.gW", r0 * K), dr * K, K, rt.w(f"cgc{l}.Wbd", c0 * ldw + blk * K), dc * ldw + db * K, ldw,
+                               nb, n, K, 4)
+            ops.copy2d_batched(rt.w(f"cgc{l}.gb", r0), dr, n, rt.w(f"cgc{l}.bbd", c0), dc, n, nb, 1, n, 4)
         if rt.bf16:                                              # bf16 operand copy of the packed block (the arena cast ran earlier)
             lo, n_el = rt.o(f"cgc{l}.Wbd"), lv.n_gcols * ldw
             ops.cast_f32_bf16(Mat(rt.W, lo, n_el), Mat(rt.Wb, lo, n_el), 1, n_el)
@@ -172,9 +189,10 @@ class PLE(BaseModel):
         dLgi = rt.gemm_input(ws, f"cgc{l}.dlogits_op", dLg, B, lv.n_gcols)
         rt.lin_bwd_w(dLgi, xin, ldw, rt.o(f"cgc{l}.Wbd"), lv.n_gcols, B)          # dWbd (diagonal blocks are the gates' gradients)
         rt.lin_bwd_x(dLgi, ldw, rt.o(f"cgc{l}.Wbd"), lv.n_gcols, dxin, B, accumulate=True)
-        for (r0, n, c0, blk) in self._gate_blocks(lv):
-            ops.copy2d(rt.g(f"cgc{l}.Wbd", c0 * ldw + blk * K), ldw, rt.g(f"cgc{l}.gW", r0 * K), K, n, K, 4)
-            ops.copy2d(tmpb.data_ptr() + 4 * c0, n, rt.g(f"cgc{l}.gb", r0), n, 1, n, 4)
+        for (r0, n, c0, blk, nb, dr, dc, db) in self._gate_runs(lv):
+            ops.copy2d_batched(rt.g(f"cgc{l}.Wbd", c0 * ldw + blk * K), dc * ldw + db * K, ldw, rt.g(f"cgc{l}.gW", r0 * K), dr * K, K,
+                               nb, n, K, 4)
+            ops.copy2d_batched(tmpb.data_ptr() + 4 * c0, dc, n, rt.g(f"cgc{l}.gb", r0), dr, n, nb, 1, n, 4)
 
     def _dlin_mat(self, ws, B):
         n = self._levels[0].n_gcols

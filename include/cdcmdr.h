@@ -336,6 +336,11 @@ int cdcmdr_route_partition(const int64_t* group, int64_t B, int n_group, int32_t
  * perm == NULL: identity, i.e. a strided 2-D copy (packing / unpacking the per-owner blocks of the embedding exchange) */
 int cdcmdr_permute_rows(const void* src, int64_t lds, const int32_t* perm, int64_t n, int64_t cols, int elt_bytes,
                         void* dst, int64_t ldd, int scatter, cdcmdr_stream_t s);
+/* strided batch of 2-D copies: dst[b*dst_bs + r*ldd + c] = src[b*src_bs + r*lds + c] for b < batches, r < rows, c < cols
+ * (element offsets).  Packs the per-task gate weights of a CGC level (ple.py:89-94) into the block-diagonal operand of one
+ * GEMM, and unpacks that operand's gradient, in one launch instead of one per gate. */
+int cdcmdr_copy2d_batched(const void* src, int64_t src_bs, int64_t lds, void* dst, int64_t dst_bs, int64_t ldd, int64_t batches,
+                          int64_t rows, int64_t cols, int elt_bytes, cdcmdr_stream_t s);
 /* a15  groups[b] = domain2group[x[b, domain_idx]]                       cdc.py:105 */
 int cdcmdr_domain_to_group(const int32_t* x, int64_t B, int F, int domain_idx, const int64_t* domain2group,
                            int n_domain, int64_t* groups, cdcmdr_stream_t s);

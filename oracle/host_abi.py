@@ -662,6 +662,16 @@ class HostABI:
         gs[n_group] = off
         return 0
 
+    def copy2d_batched(self, src, src_bs, lds, dst, dst_bs, ldd, batches, rows, cols, elt_bytes, s):
+        dt = {2: np.uint16, 4: np.uint32}[elt_bytes]
+        sz = np.dtype(dt).itemsize
+        if batches <= 0 or rows <= 0 or cols <= 0:
+            return 0
+        S = as_strided(_mat(src, 1, 1, lds, 1, dt), (batches, rows, cols), (src_bs * sz, lds * sz, sz))
+        Dm = as_strided(_mat(dst, 1, 1, ldd, 1, dt), (batches, rows, cols), (dst_bs * sz, ldd * sz, sz), writeable=True)
+        Dm[...] = S
+        return 0
+
     def permute_rows(self, src, lds, perm, n, cols, elt_bytes, dst, ldd, scatter, s):
         dt = {2: np.uint16, 4: np.uint32, 8: np.uint64}[elt_bytes]
         S, Dm = _mat(src, 1, 1, lds, 1, dt), _mat(dst, 1, 1, ldd, 1, dt)

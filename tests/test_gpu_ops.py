@@ -512,3 +512,19 @@ def test_domain_to_group_bit_exact():
         lib.domain_to_group(x.data_ptr(), B, F, 10, d2g.data_ptr(), nd, out.data_ptr(), 0)
         return [out]
     both(fn, exact=True)
+
+
+@pytest.mark.parametrize("batches,rows,cols,elt", [(4, 4, 128, 4), (3, 1, 5, 4), (5, 7, 33, 2), (1, 16, 64, 4)])
+def test_copy2d_batched_bit_exact(batches, rows, cols, elt):
+    """strided batch of 2-D copies (gate blocks -> block-diagonal operand and back)"""
+    def fn(lib, e):
+        lds, ldd = cols + 3, 2 * cols + 5
+        src_bs, dst_bs = rows * lds + 7, rows * ldd + cols
+        dt = torch.int32 if elt == 4 else torch.int16
+        src = e.put(e.rng.integers(-1000, 1000, size=batches * src_bs + 16).astype(np.int32 if elt == 4 else np.int16))
+        dst = e.zeros(batches * dst_bs + rows * ldd + 16, dtype=dt)
+        lib.copy2d_batched(src.data_ptr(), src_bs, lds, dst.data_ptr(), dst_bs, ldd, batches, rows, cols, elt, 0)
+        back = e.zeros(batches * src_bs + 16, dtype=dt)
+        lib.copy2d_batched(dst.data_ptr(), dst_bs, ldd, back.data_ptr(), src_bs, lds, batches, rows, cols, elt, 0)
+        return [dst, back]
+    both(fn, exact=True)
