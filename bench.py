@@ -372,8 +372,9 @@ def dominant_kernel_roofline(base, B, torch):
     peak = json.load(open(peaks_path))["bf16_tflops"] if os.path.exists(peaks_path) else 1590.0
     ach = 2.0 * B * D * N / sec / 1e12
     # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed ncu --set full capture
-    # (profiles/r1_ncu_gemm_l0_fwd.md: 50.2 MB + 276.3 MB; the algorithmic bytes are 385.7 MB, part of the output is still in L2)
-    traffic = 326.5e6 if (B, D, N) == (65536, 368, 2560) else None
+    # (profiles/r1_ncu_gemm_l0_fwd.md, third capture: 59.2 MB + 286.0 MB; the algorithmic bytes are 385.7 MB, the tail of the
+    # output is still dirty in L2 when the kernel ends)
+    traffic = 345.3e6 if (B, D, N) == (65536, 368, 2560) else None
     return {"kernel": "level-0 expert GEMM fwd (concat-N, bias+ReLU+dropout epilogue)", "bound": "tensor", "achieved": ach,
             "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "us_per_launch": sec * 1e6,
             "algorithmic_flops": 2.0 * B * D * N}

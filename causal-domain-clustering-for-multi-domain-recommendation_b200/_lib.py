@@ -126,6 +126,8 @@ SIGNATURES = {
     "cdcmdr_route_partition": (INT, [P, I64, INT, P, P, P, P, P]),
     "cdcmdr_permute_rows": (INT, [P, I64, P, I64, I64, INT, P, I64, INT, P]),
     "cdcmdr_copy2d_batched": (INT, [P, I64, I64, P, I64, I64, I64, I64, I64, INT, P]),
+    "cdcmdr_bce_segments_scratch_bytes": (SZ, [INT]),
+    "cdcmdr_bce_segments": (INT, [P, I64, P, INT, P, INT, P, P, P]),
     "cdcmdr_domain_to_group": (INT, [P, I64, INT, INT, P, INT, P, P]),
 }
 

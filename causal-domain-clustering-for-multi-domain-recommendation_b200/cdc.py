@@ -127,6 +127,41 @@ class CDC(BaseModel):
             raise NotImplementedError("use_metric='auc' runs sklearn on the host in the reference (cdc.py:116-119)")
         return torch.nn.functional.binary_cross_entropy(preds, targets).detach()
 
+    def probe_all_domains(self, batches):
+        """One row of the affinity matrices (run.py:551-560 `cdc_test_all_domain`): the BCE of every domain's batch under the current
+        weights.  The reference runs n_domain forwards of `model(X_d, mode='split', domain_i=d)`, each followed by
+        `get_matrix_metric`; here the batches are concatenated, evaluated in ONE pass with the tower of every row's domain
+        (`domain2group[x[:, domain_idx]]` - the same tower `domain_i=d` selects for rows of domain d) and reduced per domain on the
+        device (cdcmdr_bce_segments).  batches: sequence of (X_d int32 [B_d, F], y_d [B_d]) for d = 0..n_domain-1.
+        Returns a float32 tensor [len(batches)] on the model's device; the caller assigns it to matrix_mask / matrix_A / matrix_B."""
+        if self.use_metric != 'loss':
+            raise NotImplementedError("use_metric='auc' runs sklearn on the host in the reference (cdc.py:116-119)")
+        base = self.base_model_instance
+        rt = base._rt
+        xs = [b[0] for b in batches]
+        ys = [b[1].reshape(-1) for b in batches]
+        x = torch.cat(xs, dim=0).contiguous()
+        y = torch.cat(ys, dim=0)
+        y = (y if y.dtype in (torch.int16, torch.float32) else y.to(torch.float32)).contiguous()
+        bounds = [0]
+        for xb in xs:
+            bounds.append(bounds[-1] + int(xb.shape[0]))
+        seg = torch.tensor(bounds, dtype=torch.int64, device=x.device)
+        was_training = self.training
+        self.eval()
+        try:
+            with torch.no_grad():
+                pred = self.forward(x, mode='split').reshape(-1).contiguous()        # (sum B_d,) fp32 probabilities
+        finally:
+            self.train(was_training)
+        n_seg = len(xs)
+        out = torch.empty(n_seg, dtype=torch.float32, device=x.device)
+        lib = rt.ops.lib
+        sc = rt.ops.scratch("bce_segments", lib.bce_segments_scratch_bytes(n_seg))
+        lib.bce_segments(pred.data_ptr(), 1, y.data_ptr(), 1 if y.dtype == torch.float32 else 0, seg.data_ptr(), n_seg,
+                         out.data_ptr(), sc.data_ptr(), rt.ops.stream)
+        return out
+
     # ---------------------------------------------------------------- snapshot / restore (cdc.py:343-354)
     def save_model_state(self):
         pattern = re.compile('^(base_model_instance)')

@@ -220,6 +220,42 @@ __global__ void copy2d_batched_kernel(const V* __restrict__ src, int64_t src_bs,
   }
 }
 
+// per-segment BCE means: block (seg, chunk) sums its rows in double, a second kernel adds the chunks of a segment in order
+constexpr int kBceChunks = 64;
+__global__ void __launch_bounds__(256)
+bce_segments_partial_kernel(const float* __restrict__ pred, int64_t ld_pred, const void* __restrict__ target, int target_is_f32,
+                            const int64_t* __restrict__ seg_start, double* __restrict__ partial) {
+  const int seg = blockIdx.x, chunk = blockIdx.y;
+  const int64_t r0 = seg_start[seg], r1 = seg_start[seg + 1];
+  const int64_t per = ceil_div(r1 - r0 > 0 ? r1 - r0 : 1, (int64_t)kBceChunks);
+  const int64_t c0 = r0 + chunk * per, c1 = (c0 + per < r1) ? c0 + per : r1;
+  double acc = 0.0;
+  for (int64_t i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+    const float p = pred[i * ld_pred];
+    const float t = target_is_f32 ? static_cast<const float*>(target)[i] : (float)static_cast<const int16_t*>(target)[i];
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(log1pf(-p), -100.f);
+    acc += (double)(-(t * lp + (1.f - t) * l1p));
+  }
+  __shared__ double red[8];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tsum = 0;
+    for (int w = 0; w < 8; ++w) tsum += red[w];
+    partial[(int64_t)seg * kBceChunks + chunk] = tsum;
+  }
+}
+__global__ void bce_segments_finalize_kernel(const double* __restrict__ partial, const int64_t* __restrict__ seg_start, int n_seg,
+                                             float* __restrict__ out_mean) {
+  const int seg = blockIdx.x * blockDim.x + threadIdx.x;
+  if (seg >= n_seg) return;
+  double t = 0;
+  for (int c = 0; c < kBceChunks; ++c) t += partial[(int64_t)seg * kBceChunks + c];
+  const int64_t n = seg_start[seg + 1] - seg_start[seg];
+  out_mean[seg] = n > 0 ? (float)(t / (double)n) : __int_as_float(0x7fc00000);
+}
+
 __global__ void domain_to_group_kernel(const int32_t* __restrict__ x, int64_t B, int F, int domain_idx,
                                        const int64_t* __restrict__ d2g, int n_domain, int64_t* __restrict__ groups) {
   for (int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
@@ -335,6 +371,22 @@ extern "C" int cdcmdr_permute_rows(const void* src, int64_t lds, const int32_t* 
   } else {
     permute_rows_kernel<uint64_t><<<grid_1d(n * cols, 256), 256, 0, st>>>((const uint64_t*)src, lds, perm, n, cols, (uint64_t*)dst, ldd, scatter);
   }
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t cdcmdr_bce_segments_scratch_bytes(int n_seg) { return (size_t)(n_seg > 0 ? n_seg : 1) * kBceChunks * sizeof(double); }
+
+extern "C" int cdcmdr_bce_segments(const float* pred, int64_t ld_pred, const void* target, int target_is_f32, const int64_t* seg_start,
+                                   int n_seg, float* out_mean, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(n_seg >= 0 && n_seg <= 65535, "bad segment count");
+  if (n_seg == 0) return 0;
+  CDC_REQUIRE(pred && target && seg_start && out_mean && scratch && ld_pred >= 1, "bad bce_segments arguments");
+  cudaStream_t st = to_stream(s);
+  bce_segments_partial_kernel<<<dim3((unsigned)n_seg, kBceChunks), 256, 0, st>>>(pred, ld_pred, target, target_is_f32, seg_start,
+                                                                                 (double*)scratch);
+  CDC_LAUNCHED();
+  bce_segments_finalize_kernel<<<(n_seg + 255) / 256, 256, 0, st>>>((const double*)scratch, seg_start, n_seg, out_mean);
   CDC_LAUNCHED();
   return 0;
 }

@@ -286,35 +286,58 @@ class DCNv2(_CrossModel):
         return dict(g=ws.get(f"cmix.g{l}", (B, ne)), v1=ws.get(f"cmix.v1_{l}", (ne, B, r)), v2=ws.get(f"cmix.v2_{l}", (ne, B, r)),
                     u=ws.get(f"cmix.u{l}", (ne, B, D)))
 
-    def _mix_fwd(self, ws, x0: Mat, B) -> Mat:
+    def _mix_tc(self) -> bool:
+        """bf16 path: the contractions of CrossNetMix that involve the feature dimension D (x V_e, v U_e^T and their gradients) run on
+        the tcgen05 GEMM with fp32 results; the r x r and gating products, tanh, softmax and the Hadamard stages stay fp32."""
+        return self._rt.bf16 and self.embed_output_dim % 8 == 0 and self.low_rank % 8 == 0
+
+    def _mix_fwd(self, ws, x0: Mat, B, X: Mat | None = None) -> Mat:
         rt, D, ne, r = self._rt, self.embed_output_dim, self.num_experts, self.low_rank
         ops = rt.ops
+        tc = self._mix_tc()
         cur = x0
         for l in range(self.n_cross_layers):
             b = self._mix_bufs(ws, l, B)
             U, V, Cw = rt.w(f"crossnet.u_list.{l}"), rt.w(f"crossnet.v_list.{l}"), rt.w(f"crossnet.c_list.{l}")
+            if tc:
+                Ub = rt.Wb.data_ptr() + 2 * rt.o(f"crossnet.u_list.{l}")
+                Vb = rt.Wb.data_ptr() + 2 * rt.o(f"crossnet.v_list.{l}")
             z = ws.get("cmix.z", (B, ne))
             ops.gemm_f32(A=cur.ptr, a_rs=cur.ld, a_cs=1, Bt=rt.w("crossnet.G"), b_rs=D, b_cs=1, Cm=z.data_ptr(), c_rs=ne, M=B, N=ne, K=D)
             ops.softmax_rows_fwd(z, ne, b["g"], ne, B, ne)
             # v1[e] = tanh(x V_e)            V_e stored [D, r]: Bt(n, k) = V_e[k, n]
-            ops.gemm_f32(A=cur.ptr, a_rs=cur.ld, a_cs=1, Bt=V, b_rs=1, b_cs=r, Cm=b["v1"].data_ptr(), c_rs=r, M=B, N=r, K=D,
-                         G=ne, a_gs=0, b_gs=D * r, c_gs=B * r)
+            if tc:
+                xop = self._v2_operand(ws, l, cur, X, B) if l == 0 else rt.gemm_input(ws, f"cmix.xop{l}", cur, B, D)
+                for e in range(ne):
+                    ops.gemm_tc(A=xop.ptr, lda=xop.ld, a_rows=B, a_cols=D, a_mn=0, Bt=Vb + 2 * e * D * r, ldb=r, b_rows=D, b_cols=r,
+                                b_mn=1, M=B, N=r, K=D, n_main=0, out_aux=b["v1"].data_ptr() + 4 * e * B * r, ld_aux=r)
+            else:
+                ops.gemm_f32(A=cur.ptr, a_rs=cur.ld, a_cs=1, Bt=V, b_rs=1, b_cs=r, Cm=b["v1"].data_ptr(), c_rs=r, M=B, N=r, K=D,
+                             G=ne, a_gs=0, b_gs=D * r, c_gs=B * r)
             ops.tanh_fwd(b["v1"], ne * B * r)
             # v2[e] = tanh(v1[e] C_e^T)      C_e stored [r, r]: Bt(n, k) = C_e[n, k]
             ops.gemm_f32(A=b["v1"].data_ptr(), a_rs=r, a_cs=1, Bt=Cw, b_rs=r, b_cs=1, Cm=b["v2"].data_ptr(), c_rs=r, M=B, N=r, K=r,
                          G=ne, a_gs=B * r, b_gs=r * r, c_gs=B * r)
             ops.tanh_fwd(b["v2"], ne * B * r)
             # u[e] = v2[e] U_e^T             U_e stored [D, r]: Bt(n, k) = U_e[n, k]
-            ops.gemm_f32(A=b["v2"].data_ptr(), a_rs=r, a_cs=1, Bt=U, b_rs=r, b_cs=1, Cm=b["u"].data_ptr(), c_rs=D, M=B, N=D, K=r,
-                         G=ne, a_gs=B * r, b_gs=D * r, c_gs=B * D)
+            if tc:
+                v2op = rt.gemm_input(ws, f"cmix.v2op{l}", Mat(b["v2"], 0, r), ne * B, r)
+                for e in range(ne):
+                    ops.gemm_tc(A=v2op.ptr + 2 * e * B * v2op.ld, lda=v2op.ld, a_rows=B, a_cols=r, a_mn=0, Bt=Ub + 2 * e * D * r, ldb=r,
+                                b_rows=D, b_cols=r, b_mn=0, M=B, N=D, K=r, n_main=0, out_aux=b["u"].data_ptr() + 4 * e * B * D, ld_aux=D)
+            else:
+                ops.gemm_f32(A=b["v2"].data_ptr(), a_rs=r, a_cs=1, Bt=U, b_rs=r, b_cs=1, Cm=b["u"].data_ptr(), c_rs=D, M=B, N=D, K=r,
+                             G=ne, a_gs=B * r, b_gs=D * r, c_gs=B * D)
             nxt = ws.mat(f"cmix.x{l + 1}", B, D)
             ops.crossmix_combine_fwd(x0, cur, b["u"], b["g"], rt.w(f"crossnet.bias.{l}"), nxt, B, D, ne)
             cur = nxt
         return cur
 
-    def _mix_bwd(self, ws, x0: Mat, dout: Mat, B) -> Mat:
+    def _mix_bwd(self, ws, x0: Mat, dout: Mat, B, X: Mat | None = None) -> Mat:
         rt, D, ne, r, L = self._rt, self.embed_output_dim, self.num_experts, self.low_rank, self.n_cross_layers
         ops = rt.ops
+        tc = self._mix_tc()
+        ldp = (D + 7) // 8 * 8
         xs = [x0] + [ws.mat(f"cmix.x{l + 1}", B, D) for l in range(L)]
         dx0 = ws.mat("cmix.dx0", B, D)
         dx0.t[:B * D].zero_()
@@ -333,12 +356,26 @@ class DCNv2(_CrossModel):
             ops.crossmix_combine_bwd(x0, b["u"], b["g"], rt.w(f"crossnet.bias.{l}"), dx, du, dgate, dx0, B, D, ne)
             ops.colsum(Mat(du, 0, D), ne * B, D, rt.g(f"crossnet.bias.{l}"))
             sp = ops.pick_split(D, r, ne, B)
-            # dU_e[d, j] = sum_b du[e][b, d] * v2[e][b, j]
-            ops.gemm_f32(A=du.data_ptr(), a_rs=1, a_cs=D, Bt=b["v2"].data_ptr(), b_rs=1, b_cs=r, Cm=gU, c_rs=r, M=D, N=r, K=B,
-                         G=ne, a_gs=B * D, b_gs=B * r, c_gs=D * r, split_k=sp)
-            # dv2[e] = (du[e] U_e) * (1 - v2^2)      Bt(n=j, k=d) = U_e[d, j]
-            ops.gemm_f32(A=du.data_ptr(), a_rs=D, a_cs=1, Bt=U, b_rs=1, b_cs=r, Cm=dv2.data_ptr(), c_rs=r, M=B, N=r, K=D,
-                         G=ne, a_gs=B * D, b_gs=D * r, c_gs=B * r)
+            if tc:
+                Ub = rt.Wb.data_ptr() + 2 * rt.o(f"crossnet.u_list.{l}")
+                Vb = rt.Wb.data_ptr() + 2 * rt.o(f"crossnet.v_list.{l}")
+                duop = rt.gemm_input(ws, "cmix.duop", Mat(du, 0, D), ne * B, D)
+                v2op = ws.mat(f"cmix.v2op{l}", ne * B, r, torch.bfloat16)          # made by the forward
+                for e in range(ne):
+                    du_e = duop.ptr + 2 * e * B * duop.ld
+                    # dU_e[d, j] = sum_b du[e][b, d] * v2[e][b, j]     (both read as stored: the batch is the reduction index)
+                    ops.gemm_tc(A=du_e, lda=duop.ld, a_rows=B, a_cols=D, a_mn=1, Bt=v2op.ptr + 2 * e * B * r, ldb=r, b_rows=B, b_cols=r,
+                                b_mn=1, M=D, N=r, K=B, n_main=0, out_aux=gU + 4 * e * D * r, ld_aux=r, split_k="auto")
+                    # dv2[e] = du[e] U_e                               Bt(n=j, k=d) = U_e[d, j]
+                    ops.gemm_tc(A=du_e, lda=duop.ld, a_rows=B, a_cols=D, a_mn=0, Bt=Ub + 2 * e * D * r, ldb=r, b_rows=D, b_cols=r,
+                                b_mn=1, M=B, N=r, K=D, n_main=0, out_aux=dv2.data_ptr() + 4 * e * B * r, ld_aux=r)
+            else:
+                # dU_e[d, j] = sum_b du[e][b, d] * v2[e][b, j]
+                ops.gemm_f32(A=du.data_ptr(), a_rs=1, a_cs=D, Bt=b["v2"].data_ptr(), b_rs=1, b_cs=r, Cm=gU, c_rs=r, M=D, N=r, K=B,
+                             G=ne, a_gs=B * D, b_gs=B * r, c_gs=D * r, split_k=sp)
+                # dv2[e] = (du[e] U_e) * (1 - v2^2)      Bt(n=j, k=d) = U_e[d, j]
+                ops.gemm_f32(A=du.data_ptr(), a_rs=D, a_cs=1, Bt=U, b_rs=1, b_cs=r, Cm=dv2.data_ptr(), c_rs=r, M=B, N=r, K=D,
+                             G=ne, a_gs=B * D, b_gs=D * r, c_gs=B * r)
             ops.tanh_bwd(b["v2"], dv2, ne * B * r)
             # dC_e[i, j] = sum_b dv2[e][b, i] * v1[e][b, j]
             ops.gemm_f32(A=dv2.data_ptr(), a_rs=1, a_cs=r, Bt=b["v1"].data_ptr(), b_rs=1, b_cs=r, Cm=gC, c_rs=r, M=r, N=r, K=B,
@@ -348,15 +385,26 @@ class DCNv2(_CrossModel):
                          G=ne, a_gs=B * r, b_gs=r * r, c_gs=B * r)
             ops.tanh_bwd(b["v1"], dv1, ne * B * r)
             # dV_e[d, j] = sum_b x[b, d] * dv1[e][b, j]
-            ops.gemm_f32(A=x.ptr, a_rs=1, a_cs=x.ld, Bt=dv1.data_ptr(), b_rs=1, b_cs=r, Cm=gV, c_rs=r, M=D, N=r, K=B,
-                         G=ne, a_gs=0, b_gs=B * r, c_gs=D * r, split_k=sp)
+            if tc:
+                xop = self._v2_operand(ws, l, x, X, B) if l == 0 else ws.mat(f"cmix.xop{l}", B, ldp, torch.bfloat16)
+                dv1op = rt.gemm_input(ws, "cmix.dv1op", Mat(dv1, 0, r), ne * B, r)
+                for e in range(ne):
+                    ops.gemm_tc(A=xop.ptr, lda=xop.ld, a_rows=B, a_cols=D, a_mn=1, Bt=dv1op.ptr + 2 * e * B * r, ldb=r, b_rows=B,
+                                b_cols=r, b_mn=1, M=D, N=r, K=B, n_main=0, out_aux=gV + 4 * e * D * r, ld_aux=r, split_k="auto")
+            else:
+                ops.gemm_f32(A=x.ptr, a_rs=1, a_cs=x.ld, Bt=dv1.data_ptr(), b_rs=1, b_cs=r, Cm=gV, c_rs=r, M=D, N=r, K=B,
+                             G=ne, a_gs=0, b_gs=B * r, c_gs=D * r, split_k=sp)
             ops.softmax_rows_bwd(b["g"], ne, dgate, ne, dz, ne, B, ne)
             # dG[e, d] (+)= sum_b dz[b, e] * x[b, d]   (the gating vectors are shared by every layer)
             ops.gemm_f32(A=dz.data_ptr(), a_rs=1, a_cs=ne, Bt=x.ptr, b_rs=1, b_cs=x.ld, Cm=rt.g("crossnet.G"), c_rs=D, M=ne, N=D, K=B,
-                         accumulate=0 if first else 1, split_k=1)
+                         accumulate=0 if first else 1, split_k=ops.pick_split(ne, D, 1, B))     # 4 x D outputs: the batch must be split
             first = False
             # dx <- dx + sum_e dv1[e] V_e^T + dz G
             for e in range(ne):
+                if tc:
+                    ops.gemm_tc(A=dv1op.ptr + 2 * e * B * r, lda=r, a_rows=B, a_cols=r, a_mn=0, Bt=Vb + 2 * e * D * r, ldb=r, b_rows=D,
+                                b_cols=r, b_mn=0, M=B, N=D, K=r, n_main=0, out_aux=dx.ptr, ld_aux=dx.ld, accumulate=1)
+                    continue
                 ops.gemm_f32(A=dv1.data_ptr() + 4 * e * B * r, a_rs=r, a_cs=1, Bt=V + 4 * e * D * r, b_rs=r, b_cs=1, Cm=dx.ptr, c_rs=dx.ld,
                              M=B, N=D, K=r, accumulate=1)
             ops.gemm_f32(A=dz.data_ptr(), a_rs=ne, a_cs=1, Bt=rt.w("crossnet.G"), b_rs=1, b_cs=D, Cm=dx.ptr, c_rs=dx.ld, M=B, N=D, K=ne,
@@ -368,7 +416,7 @@ class DCNv2(_CrossModel):
     def _program_fwd(self, ws, X: Mat, B, train):
         rt, D = self._rt, self.embed_output_dim
         x0 = self._x32(ws, X, B)
-        cross = self._mix_fwd(ws, x0, B) if self.use_low_rank_mixture else self._v2_fwd(ws, x0, B, X)
+        cross = self._mix_fwd(ws, x0, B, X) if self.use_low_rank_mixture else self._v2_fwd(ws, x0, B, X)
         if self.model_structure == "parallel":
             mlp_out = self._mlp.fwd(ws, X, B, train)
             logit = self._head_fwd(ws, "dnn_linear.weight", cross, mlp_out, B)
@@ -387,7 +435,7 @@ class DCNv2(_CrossModel):
         x0 = ws.mat("X32", B, D) if X.is_bf16 else X
         cross = self._cross_out(ws, B)
         mlp_out = self._mlp._act(ws, len(self.mlp_dims) - 1, B)
-        cross_bwd = self._mix_bwd if self.use_low_rank_mixture else (lambda w, a, d, n: self._v2_bwd(w, a, d, n, X))
+        cross_bwd = (lambda w, a, d, n: (self._mix_bwd if self.use_low_rank_mixture else self._v2_bwd)(w, a, d, n, X))
         dX = ws.mat("dX", B, D)
         if self.model_structure == "parallel":
             dcross, dmlp = self._head_bwd(ws, "dnn_linear.weight", cross, mlp_out, dlogits, B)

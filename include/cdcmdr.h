@@ -336,6 +336,16 @@ int cdcmdr_route_partition(const int64_t* group, int64_t B, int n_group, int32_t
  * perm == NULL: identity, i.e. a strided 2-D copy (packing / unpacking the per-owner blocks of the embedding exchange) */
 int cdcmdr_permute_rows(const void* src, int64_t lds, const int32_t* perm, int64_t n, int64_t cols, int elt_bytes,
                         void* dst, int64_t ldd, int scatter, cdcmdr_stream_t s);
+/* N1  affinity probe of CDC: per-domain BCE means of one batched evaluation      run.py:551-560, cdc.py:116-119
+ * The reference evaluates the model once per domain (`cdc_test_all_domain`: n_domain forwards, each followed by a host BCE);
+ * here the domains' batches are concatenated, evaluated in one pass, and this entry point reduces the selected predictions
+ * per contiguous row segment: out_mean[s] = mean over rows [seg_start[s], seg_start[s+1]) of the clamped BCE term (torch
+ * BCELoss: log terms clamped at -100).  pred fp32 with row stride ld_pred; target int16 or float per `target_is_f32`;
+ * seg_start int64 [n_seg + 1] in device memory; empty segments give NaN like torch's mean of an empty tensor.
+ * scratch >= cdcmdr_bce_segments_scratch_bytes(n_seg).  Deterministic (fixed chunking, fixed summation order). */
+size_t cdcmdr_bce_segments_scratch_bytes(int n_seg);
+int cdcmdr_bce_segments(const float* pred, int64_t ld_pred, const void* target, int target_is_f32, const int64_t* seg_start,
+                        int n_seg, float* out_mean, void* scratch, cdcmdr_stream_t s);
 /* strided batch of 2-D copies: dst[b*dst_bs + r*ldd + c] = src[b*src_bs + r*lds + c] for b < batches, r < rows, c < cols
  * (element offsets).  Packs the per-task gate weights of a CGC level (ple.py:89-94) into the block-diagonal operand of one
  * GEMM, and unpacks that operand's gradient, in one launch instead of one per gate. */

@@ -662,6 +662,24 @@ class HostABI:
         gs[n_group] = off
         return 0
 
+    def bce_segments_scratch_bytes(self, n_seg):
+        return 256
+
+    def bce_segments(self, pred, ld_pred, target, target_is_f32, seg_start, n_seg, out_mean, scratch, s):
+        st = _arr(seg_start, n_seg + 1, np.int64)
+        n = int(st[n_seg])
+        p = _mat(pred, n, 1, ld_pred)[:, 0].astype(np.float32) if n else np.zeros(0, np.float32)
+        tg = _arr(target, n, np.float32 if target_is_f32 else np.int16).astype(np.float32) if n else np.zeros(0, np.float32)
+        out = _arr(out_mean, n_seg, np.float32)
+        with np.errstate(divide="ignore"):
+            lp = np.maximum(np.log(p), F32(-100))
+            l1p = np.maximum(np.log1p(-p), F32(-100))
+        term = (-(tg * lp + (F32(1) - tg) * l1p)).astype(np.float64)
+        for k in range(n_seg):
+            a, b = int(st[k]), int(st[k + 1])
+            out[k] = np.float32(term[a:b].sum() / (b - a)) if b > a else np.float32(np.nan)
+        return 0
+
     def copy2d_batched(self, src, src_bs, lds, dst, dst_bs, ldd, batches, rows, cols, elt_bytes, s):
         dt = {2: np.uint16, 4: np.uint32}[elt_bytes]
         sz = np.dtype(dt).itemsize

@@ -31,6 +31,9 @@ CASES = {
     "pair_odd_row_tiles": (128 * 5 + 17, 256, 200, 1, 0, 0, -1, dict(bias=True, act=1)),
     "pair_aux_f32": (1024, 320, 96, 1, 0, 0, 0, dict(bias=True)),
     "pair_many_tiles": (128 * 40, 512, 64, 1, 0, 0, -1, {}),
+    # A-resident column sweep: short K, several column tiles - ungrouped with an odd tile count per CTA range, and grouped
+    "sweep_ragged_ranges": (128 * 37 + 5, 3 * 256 + 40, 368, 1, 0, 0, -1, dict(bias=True, act=1)),
+    "sweep_grouped": (500, 304, 128, 3, 0, 0, -1, dict(bias=True, act=1, a_gk=128, b_gn=304, main_gn=304)),
 }
 
 
