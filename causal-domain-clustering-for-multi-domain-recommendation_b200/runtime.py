@@ -263,8 +263,7 @@ class MlpGroup:
         """layer-0 pre-activation gradient [B, G*d0 (+ tail0 columns, pitch padded to 8)]"""
         n = self.G * self.dims[0]
         ld = n + ((self.tail0 + 7) // 8 * 8 if self.tail0 else 0)
-        use_bn = self.bn and B != 1
-        return ws.mat(f"{self.tag}.dA0", B, ld, torch.float32 if use_bn else self.rt.act_dtype)
+        return ws.mat(f"{self.tag}.dA0", B, ld, self.rt.act_dtype)
 
     def _act(self, ws: Workspace, j, B) -> Mat:
         return ws.mat(f"{self.tag}.A{j}", B, self.G * self.dims[j], self.rt.act_dtype)
@@ -380,8 +379,9 @@ class MlpGroup:
             else:
                 A_prev = self._act(ws, j - 1, B)
                 rt.lin_bwd_w(cur, A_prev, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
-                # next gradient: fp32 when BatchNorm consumes it (bn_bwd reads fp32 dA), activation dtype otherwise
-                dA = self.dA0(ws, B) if j == 1 else ws.mat(f"{self.tag}.dA{j - 1}", B, G * prev_d, torch.float32 if use_bn else rt.act_dtype)
+                # next gradient in the activation dtype (bf16 on the tensor-core path: the BatchNorm backward reads either type and
+                # keeps its sums in double) - an fp32 gradient here doubled the two HBM passes of every BatchNorm layer
+                dA = self.dA0(ws, B) if j == 1 else ws.mat(f"{self.tag}.dA{j - 1}", B, G * prev_d, rt.act_dtype)
                 mask = None if use_bn else A_prev
                 rt.lin_bwd_x(cur, prev_d, self._oW(j), d, dA, B, G=G, dx_gs=prev_d, mask=mask, mask_gs=prev_d, mask_scale=keep)
                 cur = dA
