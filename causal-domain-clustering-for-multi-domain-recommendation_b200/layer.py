@@ -462,27 +462,19 @@ class BaseModel(nn.Module):
         self._fwd_token += 1
         self._last = None
         self._bump_batches_tracked(B)
+        rt.arm_input_grad(side is not None and not sharded)
         dX = self._program_bwd(ws, X, B, True, Mat(dlogits, 0, T), **kw)
+        dx_event = getattr(rt, "_dx_event", None)
+        rt.arm_input_grad(False)
         if dp is not None:
             dp.all_reduce_sum(rt.G)                          # dense gradients: sum over replicas of d(global mean loss)
-        # the dense arena's regulariser + Adam do not touch the table: second branch, next to the embedding backward
-        if side is not None:
-            main = torch.cuda.current_stream(rt.device)
-            if not sharded:
-                main.wait_stream(side)                       # joins the plan branch (the sharded path waits for its plan in dp.embed_backward)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
-                rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
-        else:
+        l2t = self._l2_table()
+
+        def dense_update():
             rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
             rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
-        l2t = self._l2_table()
-        if dp is not None and dp.shard:
-            dp.embed_backward(ws, dX, B, l2t, sums[1:2])     # row gradients to the owners; owner-side segment sum + Adam
-        else:
-            if dp is not None:
-                raise NotImplementedError("cdcmdr: data-parallel replicas need the row-sharded table (shard_embedding=True)")
+
+        def table_update():
             if self._table_state is None:
                 self._table_state = (torch.zeros_like(table), torch.zeros_like(table))
             m, v = self._table_state
@@ -490,6 +482,36 @@ class BaseModel(nn.Module):
             if lazy:
                 rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[1:2])
             rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[1:2], lazy=lazy)
+
+        if sharded:
+            # row gradients to the owners; owner-side segment sum + Adam (collectives stay on the main stream); the dense arena's
+            # regulariser + Adam do not touch the table: side branch
+            if side is not None:
+                main = torch.cuda.current_stream(rt.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    dense_update()
+            else:
+                dense_update()
+            dp.embed_backward(ws, dX, B, l2t, sums[1:2])
+        else:
+            if dp is not None:
+                raise NotImplementedError("cdcmdr: data-parallel replicas need the row-sharded table (shard_embedding=True)")
+            if side is not None:
+                # The embedding backward (segment sums + the HBM-bound sweep over table / m / v) goes to the side stream behind
+                # the plan.  When the program marked its input gradient as final (PLE level 0 computes it before that layer's bias
+                # / weight gradients) it starts there, under the remaining tensor-bound GEMMs; otherwise after the whole backward.
+                main = torch.cuda.current_stream(rt.device)
+                if dx_event is not None:
+                    side.wait_event(dx_event)
+                else:
+                    side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    table_update()
+                dense_update()
+            else:
+                dense_update()
+                table_update()
         if side is not None:
             torch.cuda.current_stream(rt.device).wait_stream(side)      # joins the dense-optimizer branch
         if dp is not None:

@@ -245,7 +245,7 @@ class PLE(BaseModel):
                     rt.ops.cast_f32_bf16(dLg, tail, B, lv.n_gcols)
                 else:
                     rt.ops.add2d(dLg, tail, B, lv.n_gcols, False)
-                lv.experts.bwd(ws, xin, dH, B, train, dxin)
+                lv.experts.bwd(ws, xin, dH, B, train, dxin, final_dx=(l == 0))      # level 0: dxin is the embeddings' gradient
                 dcur = dxin
                 continue
             lv.experts.bwd(ws, xin, dH, B, train, dxin)

@@ -125,6 +125,17 @@ class Runtime:
             self._side = torch.cuda.Stream(self.device)
         return self._side
 
+    def mark_input_grad(self):
+        """Called by a model program when a gradient w.r.t. the gathered embeddings has just been enqueued.  While a fused step
+        is armed (`arm_input_grad`) this records an event: the program promises that the gradient is FINAL at this point, so the
+        embedding backward may start on the side stream at that event, next to the rest of the dense backward."""
+        if getattr(self, "_dx_armed", False) and self.device.type == "cuda":
+            self._dx_event = torch.cuda.Event()
+            self._dx_event.record(torch.cuda.current_stream(self.device))
+
+    def arm_input_grad(self, on: bool):
+        self._dx_armed, self._dx_event = bool(on), None
+
     def ws(self, B) -> Workspace:
         w = self._ws.get(B)
         if w is None:
@@ -316,7 +327,7 @@ class MlpGroup:
             return L
         return prev
 
-    def bwd(self, ws: Workspace, X: Mat, dOut: Mat, B, train, dX: Mat | None, accumulate=False):
+    def bwd(self, ws: Workspace, X: Mat, dOut: Mat, B, train, dX: Mat | None, accumulate=False, final_dx=False):
         """dOut: gradient w.r.t. the group's output: dlogits [B, G] fp32 (out_layer), else the gradient of the last
         post-activation [B, G*d_last] (bn) or of the last PRE-activation (no bn: the caller applied the ReLU mask)."""
         rt, G, nl = self.rt, self.G, len(self.dims)
@@ -349,19 +360,27 @@ class MlpGroup:
                 rt.bn_bwd(desc, Z, A, cur, dZ, self._vec(rt.g, "gamma", j), self._vec(rt.g, "beta", j), False, B, G * d)
                 cur = dZ
             # cur is now dZ_j  [B, G*d]
+            # Layer 0: the input gradient FIRST - it is what the embedding backward waits for (rt.mark_input_grad), and the bias /
+            # weight gradients of this layer can then run next to it.
             if j == 0 and self.tail0 and nl >= 2:                # experts + the caller's tail columns in one go
                 n_tot = G * d + self.tail0
-                rt.ops.colsum(cur, B, n_tot, rt.g(self.names["b"][j]))
-                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), n_tot, B)
                 if dX is not None:
                     rt.lin_bwd_x(cur, prev_d, self._oW(j), n_tot, dX, B, accumulate=accumulate)
+                    if final_dx:                                 # the caller adds nothing to dX after this call
+                        rt.mark_input_grad()
+                rt.ops.colsum(cur, B, n_tot, rt.g(self.names["b"][j]))
+                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), n_tot, B)
                 continue
-            rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j], self.g0 * d))
             if j == 0 and self.in_groups is None:
-                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
                 if dX is not None:
                     rt.lin_bwd_x(cur, prev_d, self._oW(j), d, dX, B, G=G, dx_gs=prev_d, accumulate=accumulate)
-            elif j == 0 and self.uniform:
+                    if final_dx:
+                        rt.mark_input_grad()
+                rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j], self.g0 * d))
+                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), d, B, G=G, x_gs=prev_d)
+                continue
+            rt.ops.colsum(cur, B, G * d, rt.g(self.names["b"][j], self.g0 * d))
+            if j == 0 and self.uniform:
                 c, ng = self.in_groups[0][2] - self.in_groups[0][1], len(self.in_groups)
                 rt.lin_bwd_w(cur, X, prev_d, self._oW(j), c * d, B, G=ng, x_gs=prev_d)
                 if dX is not None:
