@@ -376,7 +376,7 @@ def dominant_kernel_roofline(base, B, torch):
     ws = rt.ws(B)
     lv = base._levels[0]
     D, N = base.embed_output_dim, lv.experts.G * lv.experts.dims[0]
-    X = ws.mat("X", B, D, rt.act_dtype)
+    X = base._x_mat(ws, B)                                        # the step's own gathered-embedding buffer (same pitch)
     fn = lambda: lv.experts.fwd_layer0_only(ws, X, B)            # noqa: E731
     for _ in range(3):
         fn()

@@ -277,6 +277,29 @@ class Ops:
         if split > 1:
             self.lib.splitk_reduce(part, stride, split, out_aux, 1, stride, stride, stride, 1 if accumulate else 0, self.stream)
 
+    def wgrad_with_bias_tc(self, dY: Mat, X: Mat, K, M, B, gW_addr, gb_addr):
+        """dW[m, k] = sum_b dY[b, m] * X[b, k] (-> gW_addr, [M, K] fp32) and db[m] = sum_b dY[b, m] (-> gb_addr) from ONE product:
+        X carries a column of ones at index K (layer.py::_x_mat), so dY^T [X | 1] is [M, K+1] and its last column is the bias
+        gradient - the separate column-sum pass over dY (a full HBM read of the largest activation gradient) disappears.
+        Split-K partials [split, M, K+1] are reduced straight into the two destinations (fixed order)."""
+        N = K + 1
+        tiles = ((M + 127) // 128) * ((N + 255) // 256)
+        num_kb = (B + 63) // 64
+        best, want = None, 1
+        for cand in range(1, min(48, num_kb) + 1):
+            per = (num_kb + cand - 1) // cand
+            cost = ((tiles * cand + 147) // 148) * (per + 2)
+            if best is None or cost < best:
+                best, want = cost, cand
+        split = self.lib.gemm_bf16_tc_splits(B, want)
+        stride = M * N
+        part = self.scratch("tc_splitk", 4 * max(split, 1) * stride).data_ptr()
+        d = GemmBf16(dY.ptr, dY.ld, B, M, X.ptr, X.ld, B, N, M, N, B, 1, 0, 0, 0, 0, 1, 1, None, 0, 0, None, 0, 0, part, N, 0, 0,
+                     None, 0, 0, 1.0, 0.0, None, 0, 0, split, stride, 0)
+        self.lib.gemm_bf16_tc(C.byref(d), self.stream)
+        self.lib.splitk_reduce(part, stride, split, gW_addr, M, K, N, K, 0, self.stream)
+        self.lib.splitk_reduce(part + 4 * K, stride, split, gb_addr, M, 1, N, 1, 0, self.stream)
+
     # ---------------------------------------------------------------- loss
     def sigmoid_select_bce(self, logits, lin: Mat | None, B, T, mode, sel, col, target, pred, psel, loss_sum, dlogits,
                            dlin: Mat | None, inv_batch):

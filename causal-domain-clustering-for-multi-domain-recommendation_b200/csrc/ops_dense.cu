@@ -660,13 +660,27 @@ template <typename T, typename TD> struct BnBwdStatF {
 };
 
 // sums2[v*C + c] = sum_k partial[(v*chunks + k)*C + c], v in {0, 1}: the per-feature sums of one rank
-__global__ void chunks_to_sums_kernel(const double* __restrict__ partial, int chunks, int64_t C, double* __restrict__ sums2) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 2 * C) return;
-  const int64_t v = i / C, c = i % C;
+// block = 32 (v, c) entries x 8 chunk lanes: lane y adds chunks y, y+8, ..., the 8 lane sums are added in lane order (fixed order;
+// a single thread per entry walked the <= 64 chunks serially: 12 us for a few KB)
+__global__ void __launch_bounds__(256)
+chunks_to_sums_kernel(const double* __restrict__ partial, int chunks, int64_t C, double* __restrict__ sums2) {
+  __shared__ double sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + tx;
   double t = 0;
-  for (int k = 0; k < chunks; ++k) t += partial[((int64_t)v * chunks + k) * C + c];
-  sums2[i] = t;
+  if (i < 2 * C) {
+    const int64_t v = i / C, c = i % C;
+#pragma unroll 4
+    for (int k = ty; k < chunks; k += 8) t += partial[((int64_t)v * chunks + k) * C + c];
+  }
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && i < 2 * C) {
+    double u = 0;
+#pragma unroll
+    for (int y = 0; y < 8; ++y) u += sm[y][tx];
+    sums2[i] = u;
+  }
 }
 
 // sums[0][c] = sum dy, sums[1][c] = sum dy*xhat  (fp32 copies kept in `sums` for the apply kernel)
@@ -1072,7 +1086,7 @@ extern "C" int cdcmdr_bn_fwd_stats(const float* Z, int64_t ldz, int64_t B, int64
     col_partial_kernel<2><<<grid, 256, 0, st>>>(B, C, chunks, partial, BnStatF{Z, ldz});
   }
   CDC_LAUNCHED();
-  chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 256), 256, 0, st>>>(partial, chunks, C, sums);
+  chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 32), 256, 0, st>>>(partial, chunks, C, sums);
   CDC_LAUNCHED();
   return 0;
 }
@@ -1166,7 +1180,7 @@ extern "C" int cdcmdr_bn_bwd_stats(const cdcmdr_bn_t* p, const float* Z, int64_t
 #undef BNS
   }
   CDC_LAUNCHED();
-  chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 256), 256, 0, st>>>(partial, chunks, C, sums);
+  chunks_to_sums_kernel<<<(unsigned)ceil_div(2 * C, 32), 256, 0, st>>>(partial, chunks, C, sums);
   CDC_LAUNCHED();
   bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 256), 256, 0, st>>>(sums, 1, C, fsums, dgamma, dbeta, accumulate);
   CDC_LAUNCHED();

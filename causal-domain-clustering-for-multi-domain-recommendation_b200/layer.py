@@ -275,13 +275,28 @@ class BaseModel(nn.Module):
             raise ValueError(f"cdcmdr: expected indices of shape [B, {self.field_num}]")
 
     # ---------------------------------------------------------------- forward / backward drivers
+    def _x_mat(self, ws, B) -> Mat:
+        """The gathered embeddings [B, F*E].  Models whose first layer takes its bias gradient from the weight-gradient GEMM
+        (`_x_ones_col`, bf16 path) get 8 extra columns per row: column F*E holds 1.0, the rest 0 - written once, the gather
+        never touches them - so that dY^T [X | 1] yields dW and db in one product."""
+        rt = self._rt
+        D = self.field_num * self.embed_dim
+        if not (rt.bf16 and getattr(self, "_x_ones_col", False)):
+            return ws.mat("X", B, D, rt.act_dtype)
+        ld = D + 8
+        fresh = "X" not in ws.bufs or ws.bufs["X"].numel() < B * ld
+        X = ws.mat("X", B, ld, rt.act_dtype, zero=True)
+        if fresh:
+            X.t[:B * ld].view(B, ld)[:, D] = 1.0
+        return X
+
     def _gather(self, ws, x, B, plan_ahead=False):
         rt = self._rt
         E, F = self.embed_dim, self.field_num
         table = self.embedding.embedding_dict.weight
-        X = ws.mat("X", B, F * E, rt.act_dtype)
         if rt.bf16 and (F * E) % 8:
             raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
+        X = self._x_mat(ws, B)
         if rt.dp is not None and rt.dp.shard:
             rt.dp.embed_forward(ws, x, B, X, plan_ahead)   # row-sharded table: indices to the owners, rows back (parallel.py)
             return X

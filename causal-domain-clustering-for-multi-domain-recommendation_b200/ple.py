@@ -145,6 +145,10 @@ class PLE(BaseModel):
                             rt.o(f"cgc{l}.gb") == rt.o(self._level_names[l]["b"][0]) + nE * d0)
             if lv.fused_bwd:
                 lv.experts.tail0 = lv.n_gcols
+                if rt.bf16 and rt.dp is None:
+                    # the gathered embeddings carry a column of ones: layer 0's bias gradient comes out of its weight-gradient GEMM
+                    self._x_ones_col = True
+                    lv.experts.x_has_ones = True
             self._levels.append(lv)
         self._towers = MlpGroup(rt, "towers", T, self.expert_dims[-1][-1], self.tower_dims, self._tower_names, bn=True,
                                 out_layer=True, in_groups=None)

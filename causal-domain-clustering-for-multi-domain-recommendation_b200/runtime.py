@@ -368,8 +368,12 @@ class MlpGroup:
                     rt.lin_bwd_x(cur, prev_d, self._oW(j), n_tot, dX, B, accumulate=accumulate)
                     if final_dx:                                 # the caller adds nothing to dX after this call
                         rt.mark_input_grad()
-                rt.ops.colsum(cur, B, n_tot, rt.g(self.names["b"][j]))
-                rt.lin_bwd_w(cur, X, prev_d, self._oW(j), n_tot, B)
+                if X.is_bf16 and cur.is_bf16 and X.ld >= prev_d + 8 and getattr(self, "x_has_ones", False):
+                    # X[:, prev_d] == 1: weight and bias gradient from one GEMM
+                    rt.ops.wgrad_with_bias_tc(cur, X, prev_d, n_tot, B, rt.G.data_ptr() + 4 * self._oW(j), rt.g(self.names["b"][j]))
+                else:
+                    rt.ops.colsum(cur, B, n_tot, rt.g(self.names["b"][j]))
+                    rt.lin_bwd_w(cur, X, prev_d, self._oW(j), n_tot, B)
                 continue
             if j == 0 and self.in_groups is None:
                 if dX is not None:
