@@ -396,6 +396,16 @@ extern "C" int cdcmdr_copy2d_batched(const void* src, int64_t src_bs, int64_t ld
   CDC_REQUIRE(elt_bytes == 2 || elt_bytes == 4, "element size must be 2 or 4 bytes");
   if (batches <= 0 || rows <= 0 || cols <= 0) return 0;
   CDC_REQUIRE(src && dst, "null copy operand");
+  // 128-bit path when every byte stride, the row length and both bases are multiples of 16 (the exchange blocks of the sharded table)
+  const int64_t eb = elt_bytes;
+  if ((cols * eb) % 16 == 0 && (lds * eb) % 16 == 0 && (ldd * eb) % 16 == 0 && (src_bs * eb) % 16 == 0 && (dst_bs * eb) % 16 == 0 &&
+      (uintptr_t)src % 16 == 0 && (uintptr_t)dst % 16 == 0) {
+    const int64_t vc = cols * eb / 16;
+    copy2d_batched_kernel<uint4><<<grid_1d(batches * rows * vc, 256), 256, 0, to_stream(s)>>>(
+        (const uint4*)src, src_bs * eb / 16, lds * eb / 16, (uint4*)dst, dst_bs * eb / 16, ldd * eb / 16, batches, rows, vc);
+    CDC_LAUNCHED();
+    return 0;
+  }
   const int grid = grid_1d(batches * rows * cols, 256);
   if (elt_bytes == 4)
     copy2d_batched_kernel<uint32_t><<<grid, 256, 0, to_stream(s)>>>((const uint32_t*)src, src_bs, lds, (uint32_t*)dst, dst_bs, ldd, batches, rows, cols);

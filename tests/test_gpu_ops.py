@@ -528,3 +528,19 @@ def test_copy2d_batched_bit_exact(batches, rows, cols, elt):
         lib.copy2d_batched(dst.data_ptr(), dst_bs, ldd, back.data_ptr(), src_bs, lds, batches, rows, cols, elt, 0)
         return [dst, back]
     both(fn, exact=True)
+
+
+@pytest.mark.parametrize("elt", [2, 4])
+def test_copy2d_batched_aligned_blocks(elt):
+    """the exchange blocks of the sharded table: every stride a multiple of 16 bytes (128-bit path), 3 owners x [B, n*E]"""
+    B, nE, F_E = 257, 48, 368
+    def fn(lib, e):
+        dt = torch.int32 if elt == 4 else torch.int16
+        npdt = np.int32 if elt == 4 else np.int16
+        X = e.put(e.rng.integers(-1000, 1000, size=B * F_E).astype(npdt))
+        packed = e.zeros(3 * B * nE, dtype=dt)
+        lib.copy2d_batched(X.data_ptr() + elt * 16, nE, F_E, packed.data_ptr(), B * nE, nE, 3, B, nE, elt, 0)
+        back = e.zeros(B * F_E, dtype=dt)
+        lib.copy2d_batched(packed.data_ptr(), B * nE, nE, back.data_ptr() + elt * 16, nE, F_E, 3, B, nE, elt, 0)
+        return [packed, back]
+    both(fn, exact=True)

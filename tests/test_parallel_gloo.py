@@ -131,3 +131,27 @@ def test_field_split_covers_every_field_once():
             assert all(rg[i][1] == rg[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in rg]
             assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("n_fields,world", [(23, 8), (23, 4), (26, 8), (5, 8), (7, 2)])
+def test_field_runs_pack_like_per_owner_copies(n_fields, world):
+    """the exchange buffers of the sharded table are packed one RUN of equally sized owners per strided-batch copy
+    (parallel.field_runs); the result must be the per-owner layout [owner][B, fields of owner * E] the all-to-all expects"""
+    B, E = 9, 4
+    rg = cm.parallel.split_fields(n_fields, world)
+    runs = cm.parallel.field_runs(rg)
+    assert sum(n * cnt for _, n, cnt in runs) == n_fields
+    assert all(n > 0 and cnt > 0 for _, n, cnt in runs)
+    abi = HostABI()
+    X = np.arange(B * n_fields * E, dtype=np.uint32).reshape(B, n_fields * E)
+    want = np.concatenate([X[:, f0 * E:f1 * E].reshape(-1) for f0, f1 in rg])
+    packed = np.zeros(B * n_fields * E, dtype=np.uint32)
+    for f0, n, cnt in runs:
+        abi.copy2d_batched(X.ctypes.data + 4 * f0 * E, n * E, n_fields * E, packed.ctypes.data + 4 * B * f0 * E, B * n * E, n * E, cnt, B,
+                           n * E, 4, 0)
+    assert np.array_equal(packed, want)
+    back = np.zeros_like(X)
+    for f0, n, cnt in runs:
+        abi.copy2d_batched(packed.ctypes.data + 4 * B * f0 * E, B * n * E, n * E, back.ctypes.data + 4 * f0 * E, n * E, n_fields * E, cnt, B,
+                           n * E, 4, 0)
+    assert np.array_equal(back, X)
