@@ -14,6 +14,7 @@ from __future__ import annotations
 import copy
 import re
 
+import numpy as np
 import torch
 
 from .cdc_group import Grouping
@@ -51,6 +52,7 @@ class CDC(BaseModel):
         self.n_domain = n_domain
         self.domain_idx = domain_idx
         dcw = domain_cnt_weight if domain_cnt_weight is not None else [1.0 / n_domain] * n_domain
+        self._dcw = [float(v) for v in dcw]            # the runner's own float64 weights: np.random.choice checks sum(p) == 1 in double
         self.domain_cnt_weight = torch.tensor(dcw, dtype=torch.float32, device=device)
         self.domain2group = torch.zeros(n_domain, dtype=torch.int64, device=device)
         self.domain2group_list = [0] * n_domain
@@ -106,8 +108,6 @@ class CDC(BaseModel):
     def train_step(self, x, y, optimizer, mode='split', domain_i=None):
         """run.py:616-622 (warmup) / 635-640 (split), fused."""
         base = self.base_model_instance
-        if not self.training:
-            raise RuntimeError("train_step() needs model.train()")
         if mode == 'warmup':
             return base.train_step(x, y, optimizer, mode="mean")
         if mode != 'split':
@@ -161,6 +161,62 @@ class CDC(BaseModel):
         lib.bce_segments(pred.data_ptr(), 1, y.data_ptr(), 1 if y.dtype == torch.float32 else 0, seg.data_ptr(), n_seg,
                          out.data_ptr(), sc.data_ptr(), rt.ops.stream)
         return out
+
+    # ---------------------------------------------------------------- the affinity-matrix probing loop (run.py:528-594)
+    def update_matrix_cdc(self, get_domain_data, optimizer, update_matrix_step, rng=None):
+        """`Run.update_matrix_cdc` (run.py:528-594) as one call: snapshot -> for every probe {k fused training steps on a domain
+        (multi)set -> one batched evaluation of all domains -> restore} -> update_group().  Returns the new domain2group_list
+        (the caller stores it: `self.domain2group_list = model.update_matrix_cdc(self.get_domain_data, optimizer, k)`).
+
+        get_domain_data(d) is the runner's own batch provider (run.py:499-526): an int yields that domain's next (X, y), a list
+        yields the concatenation over the (shuffled in place) list.  Draws, shuffles and fetches happen in the reference's order
+        from NumPy's global RNG (or `rng`, a RandomState), so a seeded run probes the same multisets on the same batches.
+        Faithful to two upstream quirks, because they change the numbers: (1) cdc_test_all_domain leaves the model in eval mode
+        and only the matrix-A loop switches back, so the mask probes after the first one and every matrix-B probe TRAIN in eval
+        mode (BatchNorm on running statistics, dropout off), and the model is still in eval mode on return; (2) for the rows of
+        matrix B past n_domain the training "set" is `domain2group_list[d_i - n_domain]` - an int, i.e. the single domain whose
+        index equals that group id (run.py:587-588)."""
+        rs = rng if rng is not None else np.random
+        n_domain, n_cluster = self.n_domain, self.n_cluster
+        p = self._dcw
+
+        def train_with(domains, k):                                  # cdc_train_update_with_domain (run.py:529-548), mode 'split'
+            if isinstance(domains, (int, np.integer)):
+                seq = [domains] * k
+            else:
+                tmp = list(domains) * k
+                seq = [tmp[i:i + 7] for i in range(0, len(tmp), 7)]
+            for one in seq:
+                X, y = get_domain_data(one)
+                self.train_step(X, y, optimizer, mode='split', domain_i=one if isinstance(one, (int, np.integer)) else None)
+
+        def probe():                                                 # cdc_test_all_domain (run.py:550-558)
+            self.eval()
+            return self.probe_all_domains([get_domain_data(d) for d in range(n_domain)])
+
+        self.save_model_state()
+        for line_i in range(self.n_causal_mask):                     # treatment rows (run.py:563-569)
+            size = rs.randint(5, n_domain)
+            domains = rs.choice(range(n_domain), p=p, size=size)
+            train_with(domains, update_matrix_step)
+            self.matrix_mask[line_i] = probe()
+            self.load_model_state()
+        self.matrix_A[n_domain] = probe()                            # matrix A (run.py:572-577)
+        for d_i in range(n_domain):
+            self.train()
+            train_with(d_i, update_matrix_step)
+            self.matrix_A[d_i] = probe()
+            self.load_model_state()
+        n_rows = n_domain + n_cluster if max(self.domain2group_list) > 0 else n_domain + 1      # matrix B (run.py:580-592)
+        for d_i in range(n_rows):
+            if d_i >= n_domain:
+                domains = self.domain2group_list[d_i - n_domain]
+            else:
+                domains = [d for d in self.s_group2domain_list[self.domain2group_list[d_i]] if d != d_i]
+            train_with(domains, update_matrix_step)
+            self.matrix_B[d_i] = probe()
+            self.load_model_state()
+        return self.update_group()
 
     # ---------------------------------------------------------------- snapshot / restore (cdc.py:343-354)
     def save_model_state(self):

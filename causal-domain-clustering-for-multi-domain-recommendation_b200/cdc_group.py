@@ -216,7 +216,8 @@ class Grouping:
         return dict(A=A, B=B, mask=M, causal=self.causal)
 
 
-# torch.argmax / argmin / topk return the FIRST extreme element on ties and treat NaN as the largest value
+# torch.argmax / argmin / max / min return the FIRST extreme element on ties and PROPAGATE NaN (a NaN is both the largest and the
+# smallest value: the index of the first NaN comes back); topk(largest=False) ranks NaN last
 def _argmax(v):
     v = np.asarray(v)
     nan = np.isnan(v)
@@ -226,9 +227,7 @@ def _argmax(v):
 def _argmin(v):
     v = np.asarray(v)
     nan = np.isnan(v)
-    if nan.all():
-        return 0
-    return int(np.argmin(np.where(nan, np.inf, v)))
+    return int(np.flatnonzero(nan)[0]) if nan.any() else int(np.argmin(v))
 
 
 def _topk_smallest(v, k):

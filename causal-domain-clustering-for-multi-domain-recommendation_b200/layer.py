@@ -435,8 +435,10 @@ class BaseModel(nn.Module):
         embedding table).  `optimizer` is a cdcmdr Adam (optim.py).  Returns a dict of device tensors:
         loss (= bce + reg), bce, reg, pred (B, T)."""
         self._check_device(x)
-        if not self.training:
-            raise RuntimeError("train_step() needs model.train()")
+        # model.eval() + a training step is legal in the reference and HAPPENS there: cdc_test_all_domain (run.py:551) leaves the
+        # model in eval mode, so most probe steps of update_matrix_cdc - and the rest of that epoch - run BatchNorm on its running
+        # statistics (gradients flow through the fixed affine map) with dropout off.
+        train = bool(self.training)
         rt = self._rt
         x = x.contiguous()
         B = x.shape[0]
@@ -460,7 +462,7 @@ class BaseModel(nn.Module):
                     plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
             else:
                 plan = rt.ops.embed_plan(x, self.embedding.offsets_dev, B, F, V, E)
-        logits, lin = self._program_fwd(ws, X, B, True, **kw)
+        logits, lin = self._program_fwd(ws, X, B, train, **kw)
         R, T = self._head_shape(B, **kw)                     # R != B only when the program routed rows (STAR with x_group)
         pred = ws.get("pred", (R, T))
         psel = ws.get("psel", (B,))
@@ -476,9 +478,10 @@ class BaseModel(nn.Module):
                                   dlin, 1.0 / max(n_global, 1))
         self._fwd_token += 1
         self._last = None
-        self._bump_batches_tracked(B)
+        if train:
+            self._bump_batches_tracked(B)
         rt.arm_input_grad(side is not None and not sharded)
-        dX = self._program_bwd(ws, X, B, True, Mat(dlogits, 0, T), **kw)
+        dX = self._program_bwd(ws, X, B, train, Mat(dlogits, 0, T), **kw)
         dx_event = getattr(rt, "_dx_event", None)
         rt.arm_input_grad(False)
         if dp is not None:
