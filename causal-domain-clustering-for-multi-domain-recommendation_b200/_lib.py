@@ -129,6 +129,11 @@ SIGNATURES = {
     "cdcmdr_bce_segments_scratch_bytes": (SZ, [INT]),
     "cdcmdr_bce_segments": (INT, [P, I64, P, INT, P, INT, P, P, P]),
     "cdcmdr_domain_to_group": (INT, [P, I64, INT, INT, P, INT, P, P]),
+    "cdcmdr_attn_fwd": (INT, [P, I64, P, I64, P, I64, INT, INT, INT, F32, F32, P, U32, P]),
+    "cdcmdr_attn_bwd": (INT, [P, I64, P, P, I64, P, I64, I64, INT, INT, INT, F32, F32, P, U32, P]),
+    "cdcmdr_attn_pool_fwd": (INT, [P, P, P, I64, INT, I64, I64, P]),
+    "cdcmdr_attn_pool_scratch_bytes": (C.c_size_t, [I64, I64]),
+    "cdcmdr_attn_pool_bwd": (INT, [P, P, P, I64, P, P, I64, I64, P, P]),
 }
 
 # entry points that return a status code (everything that launches work)

@@ -1,0 +1,275 @@
+// N3: the field self-attention block of BaseModel.atten_forward (reference model/layer.py:58-84): the attention
+// core of nn.MultiheadAttention over the L = field_num tokens of one sample, and the ReLU + Linear(F*A -> 1) head that turns the
+// block's output into the scalar added to every tower logit.  The projections around the core (atten_embedding, in_proj,
+// out_proj, V_res_embedding) are plain Linear layers over the [B*L, A] token matrix and run on the GEMM entry points.
+//
+// L <= 32 tokens, so one (sample, head) pair is a warp-sized problem: a warp stages Q, K, V [L, dh] (and dO in the backward) in
+// its own shared-memory slice (row stride dh+1: the score loop reads one row per lane), lane j owns score column j, the softmax
+// reductions are warp shuffles, and the products against V / K / Q put lanes on the head dimension.  fp32 throughout.
+#include "common.cuh"
+
+namespace cdcmdr {
+
+constexpr int kAttnWarps = 4;
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// dropout on the attention weights (nn.MultiheadAttention(dropout=p), train mode): element (pair, i, j) -> hash row pair*L+i, col j
+__device__ __forceinline__ float attn_keep_scale(float drop_p, uint32_t s0, uint32_t thr, uint32_t row, uint32_t col) {
+  if (drop_p <= 0.f) return 1.f;
+  return drop_keep(s0, thr, row, col) ? 1.f / (1.f - drop_p) : 0.f;
+}
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_fwd_kernel(const float* __restrict__ qkv, int64_t ld, float* __restrict__ out, int64_t ldo, float* __restrict__ probs,
+                int64_t B, int L, int H, int dh, float scale, float drop_p, const uint64_t* __restrict__ seed_dev, uint32_t salt) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ds = dh + 1, A = H * dh;
+  float* Q = smem + (size_t)warp * (3 * L * ds + L * L);
+  float* K = Q + L * ds;
+  float* V = K + L * ds;
+  float* P = V + L * ds;
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u, thr = drop_thr16(drop_p);
+  const int64_t pairs = B * H;
+  for (int64_t pr = (int64_t)blockIdx.x * kAttnWarps + warp; pr < pairs; pr += (int64_t)gridDim.x * kAttnWarps) {
+    const int64_t b = pr / H;
+    const int h = (int)(pr - b * H);
+    const float* base = qkv + b * L * ld + h * dh;
+    for (int e = lane; e < L * dh; e += 32) {
+      const int l = e / dh, d = e - l * dh;
+      const float* row = base + (int64_t)l * ld + d;
+      Q[l * ds + d] = row[0];
+      K[l * ds + d] = row[A];
+      V[l * ds + d] = row[2 * A];
+    }
+    __syncwarp();
+    for (int i = 0; i < L; ++i) {                              // lane j: score (i, j)
+      float s = -INFINITY;
+      if (lane < L) {
+        float acc = 0.f;
+        for (int d = 0; d < dh; ++d) acc = fmaf(Q[i * ds + d], K[lane * ds + d], acc);
+        s = acc * scale;
+      }
+      const float mx = warp_max(s);
+      const float ex = lane < L ? expf(s - mx) : 0.f;
+      const float sum = warp_sum(ex);
+      if (lane < L) {
+        const float p = ex / sum;
+        if (probs) probs[(pr * L + i) * L + lane] = p;
+        P[i * L + lane] = p * attn_keep_scale(drop_p, s0, thr, (uint32_t)(pr * L + i), (uint32_t)lane);
+      }
+    }
+    __syncwarp();
+    float* obase = out + b * L * ldo + h * dh;
+    for (int d = lane; d < dh; d += 32) {                      // lane d: O[i, d] = sum_j P[i, j] V[j, d]
+      for (int i = 0; i < L; ++i) {
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) acc = fmaf(P[i * L + j], V[j * ds + d], acc);
+        obase[(int64_t)i * ldo + d] = acc;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_bwd_kernel(const float* __restrict__ qkv, int64_t ld, const float* __restrict__ probs, const float* __restrict__ dout, int64_t lddo,
+                float* __restrict__ dqkv, int64_t lddq, int64_t B, int L, int H, int dh, float scale, float drop_p,
+                const uint64_t* __restrict__ seed_dev, uint32_t salt) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ds = dh + 1, A = H * dh;
+  float* Q = smem + (size_t)warp * (4 * L * ds + 2 * L * L);
+  float* K = Q + L * ds;
+  float* V = K + L * ds;
+  float* dO = V + L * ds;
+  float* Pd = dO + L * ds;                                     // dropped + rescaled probabilities (what multiplied V)
+  float* dS = Pd + L * L;
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u, thr = drop_thr16(drop_p);
+  const int64_t pairs = B * H;
+  for (int64_t pr = (int64_t)blockIdx.x * kAttnWarps + warp; pr < pairs; pr += (int64_t)gridDim.x * kAttnWarps) {
+    const int64_t b = pr / H;
+    const int h = (int)(pr - b * H);
+    const float* base = qkv + b * L * ld + h * dh;
+    const float* dobase = dout + b * L * lddo + h * dh;
+    for (int e = lane; e < L * dh; e += 32) {
+      const int l = e / dh, d = e - l * dh;
+      const float* row = base + (int64_t)l * ld + d;
+      Q[l * ds + d] = row[0];
+      K[l * ds + d] = row[A];
+      V[l * ds + d] = row[2 * A];
+      dO[l * ds + d] = dobase[(int64_t)l * lddo + d];
+    }
+    __syncwarp();
+    for (int i = 0; i < L; ++i) {                              // lane j: dP(i, j) = dO[i] . V[j]; softmax backward along j
+      float p = 0.f, dp = 0.f, ks = 1.f;
+      if (lane < L) {
+        p = probs[(pr * L + i) * L + lane];
+        ks = attn_keep_scale(drop_p, s0, thr, (uint32_t)(pr * L + i), (uint32_t)lane);
+        float acc = 0.f;
+        for (int d = 0; d < dh; ++d) acc = fmaf(dO[i * ds + d], V[lane * ds + d], acc);
+        dp = acc * ks;                                         // gradient w.r.t. the softmax output
+      }
+      const float dot = warp_sum(p * dp);
+      if (lane < L) {
+        Pd[i * L + lane] = p * ks;
+        dS[i * L + lane] = p * (dp - dot) * scale;             // gradient w.r.t. q.k (the 1/sqrt(dh) folded in)
+      }
+    }
+    __syncwarp();
+    float* dbase = dqkv + b * L * lddq + h * dh;
+    for (int d = lane; d < dh; d += 32) {
+      for (int i = 0; i < L; ++i) {                            // dQ[i, d] = sum_j dS[i, j] K[j, d]
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) acc = fmaf(dS[i * L + j], K[j * ds + d], acc);
+        dbase[(int64_t)i * lddq + d] = acc;
+      }
+      for (int j = 0; j < L; ++j) {                            // dK[j, d] = sum_i dS[i, j] Q[i, d] ; dV[j, d] = sum_i Pd[i, j] dO[i, d]
+        float ak = 0.f, av = 0.f;
+        for (int i = 0; i < L; ++i) {
+          ak = fmaf(dS[i * L + j], Q[i * ds + d], ak);
+          av = fmaf(Pd[i * L + j], dO[i * ds + d], av);
+        }
+        dbase[(int64_t)j * lddq + A + d] = ak;
+        dbase[(int64_t)j * lddq + 2 * A + d] = av;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// head: lin[b] (+)= sum_j relu(z[b, j]) * w[j]            (F.relu -> view(B, F*A) -> atten_linear, layer.py:82-83)
+__global__ void __launch_bounds__(256)
+attn_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ w, float* __restrict__ lin, int64_t ld_lin, int accumulate,
+                     int64_t B, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const float* zr = z + row * n;
+  float acc = 0.f;
+  for (int64_t j = lane; j < n; j += 32) acc = fmaf(fmaxf(zr[j], 0.f), w[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) lin[row * ld_lin] = accumulate ? lin[row * ld_lin] + acc : acc;
+}
+
+// backward of the head: dz[b, j] = dlin[b] * w[j] * [z > 0] ; partial[chunk, j] = sum over the chunk's rows of dlin[b] * relu(z[b, j])
+constexpr int kPoolRowsPerBlock = 8;
+__global__ void __launch_bounds__(32 * kPoolRowsPerBlock)
+attn_pool_bwd_kernel(const float* __restrict__ z, const float* __restrict__ w, const float* __restrict__ dlin, int64_t ld_dlin,
+                     float* __restrict__ dz, double* __restrict__ partial, int64_t B, int64_t n, int64_t rows_per_chunk) {
+  __shared__ double red[kPoolRowsPerBlock][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = (r0 + rows_per_chunk < B) ? r0 + rows_per_chunk : B;
+  double acc = 0.0;
+  if (j < n) {
+    const float wj = w[j];
+    for (int64_t r = r0 + ty; r < r1; r += kPoolRowsPerBlock) {
+      const float zv = z[r * n + j], g = dlin[r * ld_dlin];
+      dz[r * n + j] = zv > 0.f ? g * wj : 0.f;
+      acc += (double)(g * fmaxf(zv, 0.f));
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPoolRowsPerBlock; ++k) s += red[k][tx];
+    partial[(int64_t)blockIdx.y * n + j] = s;
+  }
+}
+
+__global__ void attn_pool_bwd_finalize_kernel(const double* __restrict__ partial, int chunks, int64_t n, float* __restrict__ dw) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partial[(int64_t)c * n + j];
+  dw[j] = (float)s;
+}
+
+static inline int pool_chunks(int64_t B) {
+  const int64_t c = ceil_div(B, 64);
+  return (int)(c < 1 ? 1 : (c > 256 ? 256 : c));
+}
+
+static inline int attn_grid(int64_t pairs) {
+  const int64_t blocks = ceil_div(pairs, kAttnWarps);
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(blocks < cap ? blocks : cap);
+}
+
+}  // namespace cdcmdr
+
+using namespace cdcmdr;
+
+extern "C" int cdcmdr_attn_fwd(const float* qkv, int64_t ld, float* out, int64_t ldo, float* probs, int64_t B, int L, int H, int dh,
+                               float scale, float drop_p, const uint64_t* seed_dev, uint32_t salt, cdcmdr_stream_t s) {
+  CDC_REQUIRE(L >= 1 && L <= 32, "attention runs over at most 32 field tokens");
+  CDC_REQUIRE(H >= 1 && dh >= 1 && dh <= 256, "bad head geometry");
+  CDC_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed_dev), "bad attention dropout");
+  if (B <= 0) return 0;
+  CDC_REQUIRE(qkv && out && ld >= 3 * (int64_t)H * dh && ldo >= (int64_t)H * dh, "bad attention operands");
+  const size_t smem = (size_t)kAttnWarps * (3 * (size_t)L * (dh + 1) + (size_t)L * L) * sizeof(float);
+  CDC_REQUIRE(smem <= 200 * 1024, "attention tile does not fit shared memory");
+  CDC_CHECK(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_fwd_kernel<<<attn_grid(B * H), kAttnWarps * 32, smem, to_stream(s)>>>(qkv, ld, out, ldo, probs, B, L, H, dh, scale, drop_p, seed_dev,
+                                                                            salt);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_attn_bwd(const float* qkv, int64_t ld, const float* probs, const float* dout, int64_t lddo, float* dqkv,
+                               int64_t lddq, int64_t B, int L, int H, int dh, float scale, float drop_p, const uint64_t* seed_dev,
+                               uint32_t salt, cdcmdr_stream_t s) {
+  CDC_REQUIRE(L >= 1 && L <= 32, "attention runs over at most 32 field tokens");
+  CDC_REQUIRE(H >= 1 && dh >= 1 && dh <= 256, "bad head geometry");
+  CDC_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed_dev), "bad attention dropout");
+  if (B <= 0) return 0;
+  CDC_REQUIRE(qkv && probs && dout && dqkv && ld >= 3 * (int64_t)H * dh && lddq >= 3 * (int64_t)H * dh && lddo >= (int64_t)H * dh,
+              "bad attention operands");
+  const size_t smem = (size_t)kAttnWarps * (4 * (size_t)L * (dh + 1) + 2 * (size_t)L * L) * sizeof(float);
+  CDC_REQUIRE(smem <= 200 * 1024, "attention tile does not fit shared memory");
+  CDC_CHECK(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_bwd_kernel<<<attn_grid(B * H), kAttnWarps * 32, smem, to_stream(s)>>>(qkv, ld, probs, dout, lddo, dqkv, lddq, B, L, H, dh, scale,
+                                                                            drop_p, seed_dev, salt);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_attn_pool_fwd(const float* z, const float* w, float* lin, int64_t ld_lin, int accumulate, int64_t B, int64_t n,
+                                    cdcmdr_stream_t s) {
+  if (B <= 0) return 0;
+  CDC_REQUIRE(z && w && lin && n >= 1 && ld_lin >= 1, "bad attention head operands");
+  attn_pool_fwd_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, to_stream(s)>>>(z, w, lin, ld_lin, accumulate, B, n);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" size_t cdcmdr_attn_pool_scratch_bytes(int64_t B, int64_t n) {
+  return (size_t)pool_chunks(B) * (size_t)(n > 0 ? n : 1) * sizeof(double);
+}
+
+extern "C" int cdcmdr_attn_pool_bwd(const float* z, const float* w, const float* dlin, int64_t ld_dlin, float* dz, float* dw, int64_t B,
+                                    int64_t n, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(n >= 1, "bad attention head width");
+  CDC_REQUIRE(dw && scratch, "bad attention head operands");
+  if (B <= 0) {
+    CDC_CHECK(cudaMemsetAsync(dw, 0, (size_t)n * sizeof(float), to_stream(s)));
+    return 0;
+  }
+  CDC_REQUIRE(z && w && dlin && dz && ld_dlin >= 1, "bad attention head operands");
+  const int chunks = pool_chunks(B);
+  const int64_t rows_per_chunk = ceil_div(B, chunks);
+  attn_pool_bwd_kernel<<<dim3((unsigned)ceil_div(n, 32), (unsigned)chunks), 32 * kPoolRowsPerBlock, 0, to_stream(s)>>>(
+      z, w, dlin, ld_dlin, dz, (double*)scratch, B, n, rows_per_chunk);
+  CDC_LAUNCHED();
+  attn_pool_bwd_finalize_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, to_stream(s)>>>((const double*)scratch, chunks, n, dw);
+  CDC_LAUNCHED();
+  return 0;
+}

@@ -150,6 +150,14 @@ class BaseModel(nn.Module):
         self.precision = "fp32"
         self.n_out = 1
         self.embedding_update = "dense_exact"      # or "sparse_lazy" (documented deviation)
+        self.use_atten = False
+        self._att = None
+
+    def build_atten(self, config, dropout):
+        """layer.py:58-69 (config.use_atten): parameter holders of the field self-attention block; computed by atten.AttnBlock."""
+        from .atten import build_atten
+        build_atten(self, config, dropout)
+        self.use_atten = True
 
     # ---------------------------------------------------------------- regularisation bookkeeping (layer.py:86-112)
     def reg_filter(self, prefix):
@@ -238,6 +246,9 @@ class BaseModel(nn.Module):
             self._table_state = tuple(t.to(device) for t in self._table_state)
         self._rt = rt
         self._last = None
+        if getattr(self, "use_atten", False):
+            from .atten import AttnBlock
+            self._att = AttnBlock(self, rt)
         self._on_runtime_built()
 
     def _set_buffer(self, name, value):
@@ -298,13 +309,22 @@ class BaseModel(nn.Module):
             raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
         X = self._x_mat(ws, B)
         if rt.dp is not None and rt.dp.shard:
+            if self._att is not None:
+                raise NotImplementedError("cdcmdr: use_atten with the row-sharded table is not wired (the attention block needs the "
+                                          "fp32 embeddings next to the bf16 operand)")
             rt.dp.embed_forward(ws, x, B, X, plan_ahead)   # row-sharded table: indices to the owners, rows back (parallel.py)
             return X
         if rt.bf16:
-            rt.ops.embed_gather(x, self.embedding.offsets_dev, table, None, X, B, F, E, table.shape[0])
+            # the attention block (fp32 this round) reads the embeddings in fp32: the gather writes both copies in one pass
+            x32 = ws.mat("X32", B, F * E) if self._att is not None else None
+            rt.ops.embed_gather(x, self.embedding.offsets_dev, table, x32, X, B, F, E, table.shape[0])
         else:
             rt.ops.embed_gather(x, self.embedding.offsets_dev, table, X, None, B, F, E, table.shape[0])
         return X
+
+    def _x32(self, ws, X: Mat, B) -> Mat:
+        """The fp32 embeddings [B, F*E] (the gathered matrix itself on the fp32 path)."""
+        return ws.mat("X32", B, self.field_num * self.embed_dim) if X.is_bf16 else X
 
     def _engine_forward(self, x, train, **kw):
         """Runs the CUDA forward; returns predictions (a workspace view)."""

@@ -22,7 +22,7 @@ class MMoE(BaseModel):
         if getattr(config, 'use_dcn', False):
             raise NotImplementedError("use_dcn=True is broken upstream (SURVEY G5) and not part of the hot path")
         if getattr(config, 'use_atten', False):
-            raise NotImplementedError("use_atten=True (field self-attention) is a 'next' row (SURVEY §8f N3)")
+            self.build_atten(config, dropout)                  # mmoe.py: build_atten before the experts, like upstream
         self.expert_dims, self.tower_dims = tuple(expert_dims), tuple(tower_dims)
         self.experts = nn.ModuleList(MultiLayerPerceptron(self.embed_output_dim, expert_dims, dropout, output_layer=False)
                                      for _ in range(n_expert))
@@ -66,7 +66,10 @@ class MMoE(BaseModel):
         probs = ws.get("mix.probs", (B, T * nE))
         rt.ops.gate_mix_fwd(self._desc, H, Lg, out, probs, B)
         logits = self._towers.fwd(ws, out, B, train)
-        return logits, Lg.cols(self._n_gcols - 1)
+        lin = Lg.cols(self._n_gcols - 1)
+        if self._att is not None:
+            self._att.fwd(ws, self._x32(ws, X, B), B, lin, train)
+        return logits, lin
 
     def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat):
         rt = self._rt
@@ -90,4 +93,6 @@ class MMoE(BaseModel):
         dLgi = rt.gemm_input(ws, "gates.dlogits_op", dLg, B, self._n_gcols)
         rt.lin_bwd_w(dLgi, X, D, rt.o("gates.W"), self._n_gcols, B)
         rt.lin_bwd_x(dLgi, D, rt.o("gates.W"), self._n_gcols, dX, B, accumulate=True)
+        if self._att is not None:
+            self._att.bwd(ws, self._x32(ws, X, B), B, self._dlin_mat(ws, B), dX, train)
         return dX

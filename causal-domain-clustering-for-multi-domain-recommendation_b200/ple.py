@@ -50,7 +50,7 @@ class PLE(BaseModel):
         if getattr(config, 'use_dcn', False):
             raise NotImplementedError("use_dcn=True is broken upstream (SURVEY G5) and not part of the hot path")
         if getattr(config, 'use_atten', False):
-            raise NotImplementedError("use_atten=True (field self-attention) is a 'next' row (SURVEY §8f N3)")
+            self.build_atten(config, dropout)                  # ple.py:31-32 (before the CGC levels, like upstream)
         self.n_expert_specific, self.n_expert_shared = n_expert_specific, n_expert_shared
         self.expert_dims = tuple(tuple(d) for d in expert_dims)
         self.tower_dims = tuple(tower_dims)
@@ -221,7 +221,10 @@ class PLE(BaseModel):
             xin = out
         logits = self._towers.fwd(ws, xin, B, train)
         n0 = self._levels[0].n_gcols
-        return logits, ws.mat("cgc0.logits", B, n0).cols(n0 - 1)
+        lin = ws.mat("cgc0.logits", B, n0).cols(n0 - 1)
+        if self._att is not None:                              # ple.py:65-67: one more `other_out` on every tower logit
+            self._att.fwd(ws, self._x32(ws, X, B), B, lin, train)
+        return logits, lin
 
     def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat):
         rt = self._rt
@@ -249,7 +252,7 @@ class PLE(BaseModel):
                     rt.ops.cast_f32_bf16(dLg, tail, B, lv.n_gcols)
                 else:
                     rt.ops.add2d(dLg, tail, B, lv.n_gcols, False)
-                lv.experts.bwd(ws, xin, dH, B, train, dxin, final_dx=(l == 0))      # level 0: dxin is the embeddings' gradient
+                lv.experts.bwd(ws, xin, dH, B, train, dxin, final_dx=(l == 0 and self._att is None))      # level 0: dxin is the embeddings' gradient
                 dcur = dxin
                 continue
             lv.experts.bwd(ws, xin, dH, B, train, dxin)
@@ -264,4 +267,6 @@ class PLE(BaseModel):
                 rt.lin_bwd_x(dLgi.cols(c0), lv.K, rt.o(f"cgc{l}.gW", r0 * lv.K), r1 - r0, dxin.cols(blk * lv.K), B,
                              accumulate=True)
             dcur = dxin
+        if self._att is not None:
+            self._att.bwd(ws, self._x32(ws, X, B), B, self._dlin_mat(ws, B), dcur, train)
         return dcur

@@ -355,6 +355,35 @@ int cdcmdr_copy2d_batched(const void* src, int64_t src_bs, int64_t lds, void* ds
 int cdcmdr_domain_to_group(const int32_t* x, int64_t B, int F, int domain_idx, const int64_t* domain2group,
                            int n_domain, int64_t* groups, cdcmdr_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------
+ * N3  field self-attention block   BaseModel.build_atten / atten_forward, model/layer.py:58-84
+ * (config.use_atten, on in the stock config.py:24-28: PLE / MMoE add its scalar output to every tower logit)
+ *
+ * The Linear layers of the block (atten_embedding, nn.MultiheadAttention in_proj / out_proj, V_res_embedding) act on the
+ * token matrix [B*L, .] (row b*L + l = field l of sample b) and run on cdcmdr_gemm_f32.  These entry points are the rest:
+ *
+ * cdcmdr_attn_fwd: the core of torch.nn.MultiheadAttention (batch_first=False semantics, no masks) for every sample and head:
+ *   qkv fp32 [B*L, ld] with columns [Q | K | V], A = H*dh each, head h in columns h*dh.. of its third;
+ *   P = softmax_j(scale * Q_h K_h^T) over the L tokens of the sample (scale = 1/sqrt(dh)), dropout on P in train mode
+ *   (drop_p > 0: the library's stateless hash, seed *seed_dev, salt), out[b*L + i, h*dh + d] = sum_j P[i, j] V[j, d].
+ *   probs (may be NULL for inference) receives the pre-dropout softmax [B, H, L, L] for the backward.  L <= 32.
+ * cdcmdr_attn_bwd: dqkv [B*L, lddq] (same column layout) from dout [B*L, lddo], qkv and probs; same drop_p / seed / salt.
+ * cdcmdr_attn_pool_fwd: the head  F.relu(z).view(B, L*A) -> atten_linear (no bias):  lin[b*ld_lin] (+)= sum_j relu(z[b, j]) w[j],
+ *   z fp32 [B, n] contiguous (n = L*A); accumulate != 0 adds onto the FeaturesLinear logit already in lin (layer.py:52-54).
+ * cdcmdr_attn_pool_bwd: dz[b, j] = dlin[b*ld_dlin] * w[j] * [z[b, j] > 0] ; dw[j] = sum_b dlin[b] * relu(z[b, j])
+ *   (deterministic two-stage column sum in double; scratch >= cdcmdr_attn_pool_scratch_bytes(B, n)).
+ * ------------------------------------------------------------------------------------------- */
+int cdcmdr_attn_fwd(const float* qkv, int64_t ld, float* out, int64_t ldo, float* probs, int64_t B, int L, int H, int dh,
+                    float scale, float drop_p, const uint64_t* seed_dev, uint32_t salt, cdcmdr_stream_t s);
+int cdcmdr_attn_bwd(const float* qkv, int64_t ld, const float* probs, const float* dout, int64_t lddo, float* dqkv, int64_t lddq,
+                    int64_t B, int L, int H, int dh, float scale, float drop_p, const uint64_t* seed_dev, uint32_t salt,
+                    cdcmdr_stream_t s);
+int cdcmdr_attn_pool_fwd(const float* z, const float* w, float* lin, int64_t ld_lin, int accumulate, int64_t B, int64_t n,
+                         cdcmdr_stream_t s);
+size_t cdcmdr_attn_pool_scratch_bytes(int64_t B, int64_t n);
+int cdcmdr_attn_pool_bwd(const float* z, const float* w, const float* dlin, int64_t ld_dlin, float* dz, float* dw, int64_t B,
+                         int64_t n, void* scratch, cdcmdr_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -711,3 +711,69 @@ class HostABI:
         m = _arr(d2g, n_domain, np.int64)
         _arr(groups, B, np.int64)[:B] = np.where((d >= 0) & (d < n_domain), m[np.clip(d, 0, n_domain - 1)], -1)
         return 0
+
+    # ------------------------------------------------------------------ N3: field self-attention (model/layer.py:58-84)
+    # The core of torch.nn.MultiheadAttention as F.multi_head_attention_forward computes it (no masks, need_weights irrelevant):
+    # q, k, v split per head, softmax(q k^T / sqrt(dh)) over the L tokens of one sample, weighted sum of v.
+    def _attn_views(self, ptr, ld, B, L, H, dh):
+        A = H * dh
+        m = _mat(ptr, B * L, 3 * A, ld).reshape(B, L, 3, H, dh)
+        return m[:, :, 0].transpose(0, 2, 1, 3), m[:, :, 1].transpose(0, 2, 1, 3), m[:, :, 2].transpose(0, 2, 1, 3)     # [B, H, L, dh]
+
+    def attn_fwd(self, qkv, ld, out, ldo, probs, B, L, H, dh, scale, drop_p, seed_dev, salt, s):
+        if drop_p > 0:
+            raise NotImplementedError("the emulator does not reproduce the dropout hash; test with dropout=0")
+        if B <= 0:
+            return 0
+        q, k, v = self._attn_views(qkv, ld, B, L, H, dh)
+        sc = np.einsum("bhid,bhjd->bhij", q, k).astype(np.float32) * F32(scale)
+        sc = sc - sc.max(axis=-1, keepdims=True)
+        e = np.exp(sc).astype(np.float32)
+        p = (e / e.sum(axis=-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+        if probs:
+            _arr(probs, B * H * L * L, np.float32)[:B * H * L * L] = p.reshape(-1)
+        o = np.einsum("bhij,bhjd->bhid", p, v).astype(np.float32)                       # [B, H, L, dh]
+        _mat(out, B * L, H * dh, ldo)[...] = o.transpose(0, 2, 1, 3).reshape(B * L, H * dh)
+        return 0
+
+    def attn_bwd(self, qkv, ld, probs, dout, lddo, dqkv, lddq, B, L, H, dh, scale, drop_p, seed_dev, salt, s):
+        if drop_p > 0:
+            raise NotImplementedError("the emulator does not reproduce the dropout hash; test with dropout=0")
+        if B <= 0:
+            return 0
+        A = H * dh
+        q, k, v = self._attn_views(qkv, ld, B, L, H, dh)
+        p = _arr(probs, B * H * L * L, np.float32)[:B * H * L * L].reshape(B, H, L, L)
+        do = _mat(dout, B * L, A, lddo).reshape(B, L, H, dh).transpose(0, 2, 1, 3)      # [B, H, L, dh]
+        dv = np.einsum("bhij,bhid->bhjd", p, do)
+        dp = np.einsum("bhid,bhjd->bhij", do, v)
+        ds = (p * (dp - (p * dp).sum(axis=-1, keepdims=True)) * F32(scale)).astype(np.float32)
+        dq = np.einsum("bhij,bhjd->bhid", ds, k)
+        dk = np.einsum("bhij,bhid->bhjd", ds, q)
+        g = _mat(dqkv, B * L, 3 * A, lddq)
+        for idx, t in enumerate((dq, dk, dv)):
+            g[:, idx * A:(idx + 1) * A] = t.astype(np.float32).transpose(0, 2, 1, 3).reshape(B * L, A)
+        return 0
+
+    def attn_pool_fwd(self, z, w, lin, ld_lin, accumulate, B, n, s):
+        if B <= 0:
+            return 0
+        zz = _mat(z, B, n, n)
+        v = (np.maximum(zz, 0) @ _arr(w, n, np.float32)[:n]).astype(np.float32)
+        o = _mat(lin, B, 1, ld_lin)
+        o[:, 0] = (o[:, 0] + v) if accumulate else v
+        return 0
+
+    def attn_pool_scratch_bytes(self, B, n):
+        return 256
+
+    def attn_pool_bwd(self, z, w, dlin, ld_dlin, dz, dw, B, n, scratch, s):
+        if B <= 0:
+            _arr(dw, n, np.float32)[:n] = 0
+            return 0
+        zz = _mat(z, B, n, n)
+        ww = _arr(w, n, np.float32)[:n]
+        g = _mat(dlin, B, 1, ld_dlin)[:, 0]
+        _mat(dz, B, n, n)[...] = np.where(zz > 0, g[:, None] * ww[None, :], F32(0)).astype(np.float32)
+        _arr(dw, n, np.float32)[:n] = (g.astype(np.float64)[:, None] * np.maximum(zz, 0).astype(np.float64)).sum(axis=0).astype(np.float32)
+        return 0

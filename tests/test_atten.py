@@ -1,0 +1,159 @@
+"""The field self-attention block (config.use_atten - ON in the reference's stock config.py:24-28; model/layer.py:58-84; SURVEY
+§8f N3) against fixtures produced by the unmodified reference with the block switched on (tests/golden/make_golden_atten.py):
+PLE with 2 attention layers + the V_res residual, MMoE with 3 layers without it; predictions, losses, every gradient, the
+state_dict after each of three Adam steps, eval forward - through the fused step and through loss.backward()."""
+import numpy as np
+import pytest
+import torch
+
+import cdcmdr_b200 as cm
+from oracle.host_abi import HostABI
+from tests.golden_cases import ATTEN, load, state
+from tests.util import build_model, run_golden_case
+
+
+@pytest.fixture
+def emulator():
+    old = cm._lib._LIB
+    cm._lib.install(HostABI())
+    yield
+    cm._lib.install(old)
+
+
+@pytest.mark.parametrize("path", ["fused", "autograd"])
+@pytest.mark.parametrize("name", sorted(ATTEN))
+def test_attention_block_host_logic(name, path, emulator):
+    run_golden_case(name, "cpu", path=path)
+
+
+@pytest.mark.parametrize("name", sorted(ATTEN))
+def test_attention_state_dict_keys_match_reference(name, emulator):
+    m = build_model(name)
+    ref = state(load(name), 0)
+    mine = {k: tuple(v.shape) for k, v in m.state_dict().items()}
+    assert set(mine) == set(ref)
+    for k, v in ref.items():
+        assert mine[k] == tuple(v.shape), k
+    assert any(k.startswith("self_attns.0.in_proj_weight") for k in mine) and "atten_linear.weight" in mine
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["fused", "autograd"])
+@pytest.mark.parametrize("name", sorted(ATTEN))
+def test_attention_block_gpu(name, path):
+    run_golden_case(name, "cuda", path=path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(ATTEN))
+def test_attention_block_gpu_bf16_path(name):
+    """bf16 tensor-core path for the experts / gates / towers with the attention block in fp32 on the fp32 copy of the embeddings
+    (one gather writes both): predictions and the first step's loss against the fp32 path on the same weights"""
+    gold = load(name)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        m = build_model(name, precision=prec)
+        m.load_state_dict({k: torch.from_numpy(v) for k, v in state(gold, 0).items()}, strict=True)
+        m = m.to("cuda").eval()
+        x, y, g = (torch.from_numpy(gold[f"in0.{k}"]).cuda() for k in ("x", "y", "g"))
+        with torch.no_grad():
+            pred = m(x).cpu().numpy()
+        m.train()
+        opt = cm.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+        out = m.train_step(x, y, opt, mode="gather", sel=g)
+        loss, bce, _ = m.step_losses(out)
+        w = m.state_dict()["atten_linear.weight"].cpu().numpy()
+        res[prec] = (pred, bce, w)
+    logit = lambda p: np.log(p) - np.log1p(-p)   # noqa: E731
+    assert np.abs(logit(res["bf16"][0]) - logit(res["fp32"][0])).max() <= 2e-2 * max(1.0, float(np.abs(logit(res["fp32"][0])).max()))
+    assert abs(res["bf16"][1] - res["fp32"][1]) <= 2e-2 * abs(res["fp32"][1])
+    assert np.abs(res["fp32"][2] - gold["sd0.atten_linear.weight"]).max() > 1e-4           # the block's weights did train
+    assert np.abs(res["bf16"][2] - gold["sd0.atten_linear.weight"]).max() > 1e-4
+
+
+def _attn_case(B, L, H, dh, seed):
+    rng = np.random.default_rng(seed)
+    A = H * dh
+    qkv = rng.standard_normal((B * L, 3 * A)).astype(np.float32)
+    dout = rng.standard_normal((B * L, A)).astype(np.float32)
+    z = rng.standard_normal((B, L * A)).astype(np.float32)
+    w = rng.standard_normal(L * A).astype(np.float32)
+    dlin = rng.standard_normal((B, 3)).astype(np.float32)
+    lin0 = rng.standard_normal((B, 3)).astype(np.float32)
+    return qkv, dout, z, w, dlin, lin0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,H,dh", [(5, 6, 2, 4), (300, 23, 2, 32), (64, 32, 4, 16), (1000, 26, 1, 64), (3, 1, 2, 8), (130, 16, 2, 40)])
+def test_attention_entry_points_gpu(B, L, H, dh):
+    """cdcmdr_attn_fwd / _bwd / _pool_fwd / _pool_bwd on the GPU against the numpy restatement (and, for the core, torch's own
+    nn.functional.scaled_dot_product_attention math in float64)"""
+    lib, emu = cm._lib.load(), HostABI()
+    A = H * dh
+    qkv, dout, z, w, dlin, lin0 = _attn_case(B, L, H, dh, B + L)
+    scale = 1.0 / np.sqrt(dh)
+    # --- emulator (host)
+    h_out, h_p, h_dqkv = np.zeros((B * L, A), np.float32), np.zeros(B * H * L * L, np.float32), np.zeros((B * L, 3 * A), np.float32)
+    emu.attn_fwd(qkv.ctypes.data, 3 * A, h_out.ctypes.data, A, h_p.ctypes.data, B, L, H, dh, scale, 0.0, None, 0, 0)
+    emu.attn_bwd(qkv.ctypes.data, 3 * A, h_p.ctypes.data, dout.ctypes.data, A, h_dqkv.ctypes.data, 3 * A, B, L, H, dh, scale, 0.0, None, 0, 0)
+    # --- float64 cross-check of the emulator itself with torch autograd
+    t = torch.from_numpy(qkv).double().requires_grad_(True)
+    q, k, v = (t[:, i * A:(i + 1) * A].reshape(B, L, H, dh).transpose(1, 2) for i in range(3))
+    o = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1) @ v
+    o = o.transpose(1, 2).reshape(B * L, A)
+    o.backward(torch.from_numpy(dout).double())
+    assert np.abs(h_out - o.detach().numpy()).max() <= 1e-4
+    assert np.abs(h_dqkv - t.grad.numpy()).max() <= 1e-4
+    # --- GPU
+    d = lambda a: torch.from_numpy(a).cuda()   # noqa: E731
+    g_qkv, g_dout = d(qkv), d(dout)
+    g_out, g_p, g_dqkv = torch.zeros(B * L, A, device="cuda"), torch.zeros(B * H * L * L, device="cuda"), torch.zeros(B * L, 3 * A, device="cuda")
+    lib.attn_fwd(g_qkv.data_ptr(), 3 * A, g_out.data_ptr(), A, g_p.data_ptr(), B, L, H, dh, scale, 0.0, None, 0, 0)
+    lib.attn_bwd(g_qkv.data_ptr(), 3 * A, g_p.data_ptr(), g_dout.data_ptr(), A, g_dqkv.data_ptr(), 3 * A, B, L, H, dh, scale, 0.0, None, 0, 0)
+    torch.cuda.synchronize()
+    assert np.abs(g_out.cpu().numpy() - h_out).max() <= 1e-4
+    assert np.abs(g_p.cpu().numpy() - h_p).max() <= 5e-6
+    assert np.abs(g_dqkv.cpu().numpy() - h_dqkv).max() <= 1e-4
+    # --- head
+    n = L * A
+    h_lin, h_dz, h_dw = lin0.copy(), np.zeros((B, n), np.float32), np.zeros(n, np.float32)
+    emu.attn_pool_fwd(z.ctypes.data, w.ctypes.data, h_lin.ctypes.data + 4, 3, 1, B, n, 0)
+    emu.attn_pool_bwd(z.ctypes.data, w.ctypes.data, dlin.ctypes.data + 8, 3, h_dz.ctypes.data, h_dw.ctypes.data, B, n, None, 0)
+    g_z, g_w, g_lin, g_dlin = d(z), d(w), d(lin0.copy()), d(dlin)
+    g_dz, g_dw = torch.zeros(B, n, device="cuda"), torch.zeros(n, device="cuda")
+    sc = torch.empty(lib.attn_pool_scratch_bytes(B, n), dtype=torch.uint8, device="cuda")
+    lib.attn_pool_fwd(g_z.data_ptr(), g_w.data_ptr(), g_lin.data_ptr() + 4, 3, 1, B, n, 0)
+    lib.attn_pool_bwd(g_z.data_ptr(), g_w.data_ptr(), g_dlin.data_ptr() + 8, 3, g_dz.data_ptr(), g_dw.data_ptr(), B, n, sc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    ref_scale = max(1.0, float(np.abs(h_lin).max()))
+    assert np.abs(g_lin.cpu().numpy() - h_lin).max() <= 1e-5 * ref_scale * np.sqrt(n)
+    assert np.array_equal(g_lin.cpu().numpy()[:, [0, 2]], lin0[:, [0, 2]])            # neighbours of the strided column untouched
+    assert np.array_equal(g_dz.cpu().numpy(), h_dz)
+    assert np.abs(g_dw.cpu().numpy() - h_dw).max() <= 1e-5 * max(1.0, float(np.abs(h_dw).max()))
+
+
+@pytest.mark.gpu
+def test_attention_dropout_statistics_gpu():
+    """attention-weight dropout (nn.MultiheadAttention(dropout=p), train mode): kept fraction, 1/(1-p) rescale, the backward uses the
+    same mask (dV of a dropped weight is zero), repeatable for the same seed"""
+    lib = cm._lib.load()
+    B, L, H, dh, p = 400, 23, 2, 32, 0.25
+    A = H * dh
+    scale = 1.0 / np.sqrt(dh)
+    qkv = torch.zeros(B * L, 3 * A, device="cuda")                                    # q = k = 0 -> uniform softmax 1/L
+    qkv[:, 2 * A:] = 1.0                                                              # v = 1 -> out = sum of kept, rescaled weights
+    seed = torch.tensor([12345], dtype=torch.int64, device="cuda")
+    outs = []
+    for _ in range(2):
+        out, pr = torch.zeros(B * L, A, device="cuda"), torch.zeros(B * H * L * L, device="cuda")
+        lib.attn_fwd(qkv.data_ptr(), 3 * A, out.data_ptr(), A, pr.data_ptr(), B, L, H, dh, scale, p, seed.data_ptr(), 7, 0)
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    o = outs[0].reshape(B, L, H, dh)
+    assert np.abs(o - o[..., :1]).max() == 0                                          # the mask is per (pair, i, j), not per d
+    kept = o[..., 0] * (1 - p) * L                                                    # number of kept weights in the row
+    assert np.abs(kept - np.round(kept)).max() < 1e-3
+    frac = kept.sum() / (B * L * H * L)
+    assert abs(frac - (1 - p)) < 0.01, frac
+    assert np.allclose(pr.cpu().numpy(), 1.0 / L, atol=1e-6)                          # probs are saved before the dropout

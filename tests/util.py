@@ -5,7 +5,7 @@ import numpy as np
 import torch
 
 import cdcmdr_b200 as cm
-from tests.golden_cases import CASES, FIELD_DIMS, E, L2, load, state
+from tests.golden_cases import ALL_CASES as CASES, ATTEN, FIELD_DIMS, E, L2, load, state
 from tests.test_oracle_golden import bias_before_bn, close
 
 
@@ -33,6 +33,10 @@ def build_model(name, probe=False, precision="fp32"):
         return True
     cfg = Cfg()
     cfg.cdcmdr_precision = precision
+    if name in ATTEN:
+        cfg.use_atten = True
+        for k, v in ATTEN[name].items():
+            setattr(cfg, k, v)
     if is_cdc:
         gold = load(name)
         n_domain = len(gold["d2g"])
@@ -141,6 +145,15 @@ def run_golden_case(name, device, path="fused", rtol=1e-4, atol=2e-6, precision=
         assert set(ref) == set(cur), set(ref) ^ set(cur)
         for k, v in ref.items():
             a = (2.1e-3 * (s + 1) if bias_before_bn(kind, k) else (3e-4 * (s + 1) if k.endswith("running_mean") else 1e-6))
+            if k.endswith("in_proj_bias"):
+                # the KEY bias of an attention layer shifts every score of a row by the same q.b_k: softmax cancels it, its gradient
+                # is rounding noise, and Adam turns the noise's sign into +-lr steps (in the reference as much as here) - the same
+                # allowance as for a bias in front of a batch-statistics BatchNorm; the query / value thirds are checked tightly
+                n3 = v.shape[0] // 3
+                c = cur[k].reshape(v.shape)
+                close(c[n3:2 * n3], v[n3:2 * n3], f"{name} step{s + 1} {k} (key third)", rtol * loose, 2.1e-3 * (s + 1) * loose)
+                close(np.delete(c, np.s_[n3:2 * n3]), np.delete(v, np.s_[n3:2 * n3]), f"{name} step{s + 1} {k}", rtol * loose, a * loose)
+                continue
             close(cur[k].reshape(v.shape), v, f"{name} step{s + 1} {k}", rtol * loose, a * loose)
     # eval-mode forward with the reference's final weights
     model.load_state_dict({prefix + k: torch.from_numpy(v) for k, v in state(gold, steps).items()}, strict=True)
