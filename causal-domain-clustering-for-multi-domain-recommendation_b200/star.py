@@ -52,7 +52,7 @@ class STAR(BaseModel):
         if getattr(config, 'use_dcn', False):
             raise NotImplementedError("use_dcn=True is broken upstream (SURVEY G5) and not part of the hot path")
         if getattr(config, 'use_atten', False):
-            raise NotImplementedError("use_atten=True (field self-attention) is a 'next' row (SURVEY §8f N3)")
+            self.build_atten(config, dropout)                  # star.py:35-36
         D, T = self.embed_output_dim, n_tower
         self.tower_dims = tuple(tower_dims)
         self.shared_bn_weight = nn.Parameter(torch.ones(D))
@@ -239,6 +239,10 @@ class STAR(BaseModel):
         x32 = self._x32(ws, Xs, n_rows)
         lin = ws.mat("lin", max(n_rows, 1), 1)
         ops.rowdot_fwd(Xs, rt.w("linear.fc.weight"), rt.w("linear.fc.bias"), lin, n_rows, 1, D)
+        if self._att is not None and n_rows > 0:
+            # star.py:70-72, 103-107: atten_forward(embed_x) is per-row, `other[mask]` picks the tower's rows - the same as running
+            # the block on the routed rows
+            self._att.fwd(ws, x32, n_rows, lin, train)
         for t, (r0, n) in enumerate(slices):
             if n == 0:
                 continue
@@ -295,6 +299,8 @@ class STAR(BaseModel):
         tmp = ws.mat("dX.lin", max(n_rows, 1), D)
         ops.rowdot_bwd(Xs, rt.w("linear.fc.weight"), dlin, tmp, rt.g("linear.fc.weight"), rt.g("linear.fc.bias"), n_rows, 1, D)
         ops.add2d(tmp, dXs, n_rows, D, True)
+        if self._att is not None and n_rows > 0:
+            self._att.bwd(ws, x32, n_rows, dlin, dXs, train)
         if not routed:
             return dXs
         dX = ws.mat("dX", B, D)

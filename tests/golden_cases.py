@@ -25,8 +25,11 @@ for _base, _kw in (("ple", CASES["ple"][1]), ("mmoe", CASES["mmoe"][1]), ("star"
 # the field self-attention block (config.use_atten; tests/golden/make_golden_atten.py): the same models with the
 # block switched on - not part of the numpy model oracle, pinned through the host logic and on the GPU
 ATTEN = {"ple_atten": dict(atten_embed_dim=8, att_layer_num=2, att_head_num=2, att_res=True),
-         "mmoe_atten": dict(atten_embed_dim=8, att_layer_num=3, att_head_num=2, att_res=False)}
-ATTEN_CASES = {"ple_atten": CASES["ple"], "mmoe_atten": CASES["mmoe"]}
+         "mmoe_atten": dict(atten_embed_dim=8, att_layer_num=3, att_head_num=2, att_res=False),
+         "star_atten": dict(atten_embed_dim=8, att_layer_num=2, att_head_num=2, att_res=True),
+         "star_grouped_atten": dict(atten_embed_dim=8, att_layer_num=2, att_head_num=2, att_res=True)}
+ATTEN_CASES = {"ple_atten": CASES["ple"], "mmoe_atten": CASES["mmoe"], "star_atten": CASES["star"],
+               "star_grouped_atten": CASES["star_grouped"]}
 ALL_CASES = {**CASES, **ATTEN_CASES}
 
 
