@@ -152,7 +152,10 @@ class Ops:
         ctas = ((M + 63) // 64) * ((N + 63) // 64) * G
         if ctas >= target_ctas or K < 2 * min_k:
             return 1
-        s = min((target_ctas + ctas - 1) // ctas, K // min_k, 64)
+        # up to 64 slices; a reduction over the B*F token rows of the attention block (K >= 2^18) feeds tiles as small as 64 x 16,
+        # where 64 CTAs leave most of the 148 SMs idle: up to 512 slices there
+        cap = 512 if K >= (1 << 18) else 64
+        s = min((target_ctas + ctas - 1) // ctas, K // min_k, cap)
         return max(1, int(s))
 
     # ---------------------------------------------------------------- gate mix
