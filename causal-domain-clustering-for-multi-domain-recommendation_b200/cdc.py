@@ -127,17 +127,37 @@ class CDC(BaseModel):
             raise NotImplementedError("use_metric='auc' runs sklearn on the host in the reference (cdc.py:116-119)")
         return torch.nn.functional.binary_cross_entropy(preds, targets).detach()
 
-    def probe_all_domains(self, batches):
+    def probe_all_domains(self, batches, max_rows=None):
         """One row of the affinity matrices (run.py:551-560 `cdc_test_all_domain`): the BCE of every domain's batch under the current
         weights.  The reference runs n_domain forwards of `model(X_d, mode='split', domain_i=d)`, each followed by
         `get_matrix_metric`; here the batches are concatenated, evaluated in ONE pass with the tower of every row's domain
         (`domain2group[x[:, domain_idx]]` - the same tower `domain_i=d` selects for rows of domain d) and reduced per domain on the
         device (cdcmdr_bce_segments).  batches: sequence of (X_d int32 [B_d, F], y_d [B_d]) for d = 0..n_domain-1.
+        max_rows caps the rows of one evaluation (consecutive domains are grouped up to that many rows; the workspace of the
+        probe is proportional to it - 30 x 65 536 rows hold ~25 GB of activations at the C4 shape); results are identical.
         Returns a float32 tensor [len(batches)] on the model's device; the caller assigns it to matrix_mask / matrix_A / matrix_B."""
         if self.use_metric != 'loss':
             raise NotImplementedError("use_metric='auc' runs sklearn on the host in the reference (cdc.py:116-119)")
-        base = self.base_model_instance
-        rt = base._rt
+        n_seg = len(batches)
+        dev = batches[0][0].device
+        out = torch.empty(n_seg, dtype=torch.float32, device=dev)
+        was_training = self.training
+        self.eval()
+        try:
+            first = 0
+            while first < n_seg:
+                last, rows = first, 0
+                while last < n_seg and (last == first or max_rows is None or rows + int(batches[last][0].shape[0]) <= max_rows):
+                    rows += int(batches[last][0].shape[0])
+                    last += 1
+                self._probe_chunk(batches[first:last], out[first:last])
+                first = last
+        finally:
+            self.train(was_training)
+        return out
+
+    def _probe_chunk(self, batches, out):
+        rt = self.base_model_instance._rt
         xs = [b[0] for b in batches]
         ys = [b[1].reshape(-1) for b in batches]
         x = torch.cat(xs, dim=0).contiguous()
@@ -147,23 +167,16 @@ class CDC(BaseModel):
         for xb in xs:
             bounds.append(bounds[-1] + int(xb.shape[0]))
         seg = torch.tensor(bounds, dtype=torch.int64, device=x.device)
-        was_training = self.training
-        self.eval()
-        try:
-            with torch.no_grad():
-                pred = self.forward(x, mode='split').reshape(-1).contiguous()        # (sum B_d,) fp32 probabilities
-        finally:
-            self.train(was_training)
+        with torch.no_grad():
+            pred = self.forward(x, mode='split').reshape(-1).contiguous()            # (sum B_d,) fp32 probabilities
         n_seg = len(xs)
-        out = torch.empty(n_seg, dtype=torch.float32, device=x.device)
         lib = rt.ops.lib
         sc = rt.ops.scratch("bce_segments", lib.bce_segments_scratch_bytes(n_seg))
         lib.bce_segments(pred.data_ptr(), 1, y.data_ptr(), 1 if y.dtype == torch.float32 else 0, seg.data_ptr(), n_seg,
                          out.data_ptr(), sc.data_ptr(), rt.ops.stream)
-        return out
 
     # ---------------------------------------------------------------- the affinity-matrix probing loop (run.py:528-594)
-    def update_matrix_cdc(self, get_domain_data, optimizer, update_matrix_step, rng=None):
+    def update_matrix_cdc(self, get_domain_data, optimizer, update_matrix_step, rng=None, probe_rows=None):
         """`Run.update_matrix_cdc` (run.py:528-594) as one call: snapshot -> for every probe {k fused training steps on a domain
         (multi)set -> one batched evaluation of all domains -> restore} -> update_group().  Returns the new domain2group_list
         (the caller stores it: `self.domain2group_list = model.update_matrix_cdc(self.get_domain_data, optimizer, k)`).
@@ -171,6 +184,7 @@ class CDC(BaseModel):
         get_domain_data(d) is the runner's own batch provider (run.py:499-526): an int yields that domain's next (X, y), a list
         yields the concatenation over the (shuffled in place) list.  Draws, shuffles and fetches happen in the reference's order
         from NumPy's global RNG (or `rng`, a RandomState), so a seeded run probes the same multisets on the same batches.
+        probe_rows caps the rows of one batched evaluation (probe_all_domains(max_rows=...)).
         Faithful to two upstream quirks, because they change the numbers: (1) cdc_test_all_domain leaves the model in eval mode
         and only the matrix-A loop switches back, so the mask probes after the first one and every matrix-B probe TRAIN in eval
         mode (BatchNorm on running statistics, dropout off), and the model is still in eval mode on return; (2) for the rows of
@@ -192,7 +206,7 @@ class CDC(BaseModel):
 
         def probe():                                                 # cdc_test_all_domain (run.py:550-558)
             self.eval()
-            return self.probe_all_domains([get_domain_data(d) for d in range(n_domain)])
+            return self.probe_all_domains([get_domain_data(d) for d in range(n_domain)], max_rows=probe_rows)
 
         self.save_model_state()
         for line_i in range(self.n_causal_mask):                     # treatment rows (run.py:563-569)

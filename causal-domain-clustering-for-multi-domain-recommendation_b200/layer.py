@@ -309,10 +309,10 @@ class BaseModel(nn.Module):
             raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
         X = self._x_mat(ws, B)
         if rt.dp is not None and rt.dp.shard:
-            if self._att is not None:
-                raise NotImplementedError("cdcmdr: use_atten with the row-sharded table is not wired (the attention block needs the "
-                                          "fp32 embeddings next to the bf16 operand)")
             rt.dp.embed_forward(ws, x, B, X, plan_ahead)   # row-sharded table: indices to the owners, rows back (parallel.py)
+            if self._att is not None and rt.bf16:
+                # the rows travel in bf16 on this path: the attention block (fp32 this round) reads them widened back
+                rt.ops.cast_bf16_f32(X, ws.mat("X32", B, F * E), B, F * E)
             return X
         if rt.bf16:
             # the attention block (fp32 this round) reads the embeddings in fp32: the gather writes both copies in one pass

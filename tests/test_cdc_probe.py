@@ -40,6 +40,10 @@ def _run(base, device, sizes):
             m.train_step(batches[d][0], batches[d][1], opt, mode="split", domain_i=d)
     got = m.probe_all_domains(batches)
     assert m.training                                           # the probe restores the mode it found
+    # capped evaluations (consecutive domains grouped up to max_rows rows; a single batch may exceed the cap): same numbers
+    for cap in (1, sum(sizes), 3 * max(sizes)):
+        chunked = m.probe_all_domains(batches, max_rows=cap)
+        assert torch.allclose(torch.nan_to_num(chunked, nan=-1.0), torch.nan_to_num(got, nan=-1.0), rtol=0, atol=1e-6), cap
     m.eval()
     want = []
     with torch.no_grad():

@@ -31,6 +31,9 @@ ADAM = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
 def _build(kind, precision="fp32"):
     torch.manual_seed(5)
     cfg = Cfg(); cfg.cdcmdr_precision = precision
+    if kind == "ple_atten":                                   # the stock config's field self-attention block on replicas
+        cfg.use_atten, cfg.atten_embed_dim, cfg.att_layer_num, cfg.att_head_num, cfg.att_res = True, 8, 2, 2, True
+        return cm.PLE(FD, E, T, 2, 1, ((16, 8), (8,)), (8, 8), dropout=0.0, config=cfg, **L2)
     if kind == "ple":
         return cm.PLE(FD, E, T, 2, 1, ((16, 8), (8,)), (8, 8), dropout=0.0, config=cfg, **L2)
     if kind == "mmoe":
@@ -86,7 +89,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("kind", ["ple", "mmoe", "cdc"])
+@pytest.mark.parametrize("kind", ["ple", "mmoe", "cdc", "ple_atten"])
 def test_two_ranks_match_one_process(kind):
     B, n_steps, world = 96, 3, 2
     with tempfile.TemporaryDirectory() as tmp:
