@@ -147,3 +147,61 @@ def test_reference_loops_drive_this_package(monkeypatch):
     assert a["training"] == b["training"] is False                        # upstream leaves the model in eval mode
     for k in ("total_auc", "total_loss", "mean_auc", "mean_loss"):
         assert abs(a["result"][k] - b["result"][k]) <= 1e-3, (k, a["result"][k], b["result"][k])       # observed 3e-6
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# the generic loops: Run.train (run.py:470-497) + Run.test over one DataLoader of (X, y[, group])
+def _generic(ref_run, kind, model, optimizer, loader_cls, train, valid, weight, group_of):
+    torch.manual_seed(77)
+    np.random.seed(77)
+    me = types.SimpleNamespace(config=Cfg(), n_domain=ND, domain_cnt_weight=weight, device="cpu", model=kind, domain_idx=DOMAIN_IDX,
+                               is_multi_tower=kind in ("ple", "mmoe", "star"), is_concat_group=kind == "star")
+    for name in ("train", "test", "evaluate_multi_domain"):
+        setattr(me, name, types.MethodType(getattr(ref_run.Run, name), me))
+
+    def loader(parts):
+        X, y = torch.cat([p[0] for p in parts]), torch.cat([p[1] for p in parts])
+        tensors = (X, y, group_of(X)) if me.is_multi_tower else (X, y)
+        return loader_cls(TensorDataset(*tensors), BS, shuffle=True)
+    crit = Recorder()
+    for epoch in range(2):
+        me.train(loader(train), model, crit, optimizer, epoch)
+    n_train = len(crit.values)
+    return dict(losses=np.array(crit.values[:n_train]), result=me.test(loader(valid), model, mode="valid"))
+
+
+@pytest.mark.parametrize("kind", ["ple", "star", "dcn"])
+def test_reference_generic_loops_drive_this_package(kind, monkeypatch):
+    G, ref_run = _reference()
+    monkeypatch.setattr(ref_run.wandb, "log", lambda *a, **k: None)
+    train, valid = _data(3)[:4], _data(4)[:4]
+    weight = np.full(ND, 1.0 / ND)
+    group_of = lambda X: (X[:, DOMAIN_IDX] % T).to(torch.int64).view(-1, 1)   # noqa: E731  (run.py:228-230: domain -> group map)
+
+    def build(mod):
+        cfg = Cfg()
+        if kind == "ple":
+            return mod.PLE(FIELD_DIMS, E, T, 2, 1, ((16, 8), (8,)), (8, 4), dropout=0.0, config=cfg, **L2)
+        if kind == "star":
+            return mod.STAR(FIELD_DIMS, E, T, (16, 8), domain_idx=DOMAIN_IDX, dropout=0.0, config=cfg, device="cpu", **L2)
+        return mod.DCN(FIELD_DIMS, E, 3, (16, 8), dropout=0.0, **L2)
+    torch.manual_seed(10)
+    ref = build(G)
+    sd0 = {k: v.clone() for k, v in ref.state_dict().items()}
+    opt = torch.optim.Adam(ref.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+    a = _generic(ref_run, kind, ref, opt, DataLoader, train, valid, weight, group_of)
+    old = cm._lib._LIB
+    cm._lib.install(HostABI())
+    try:
+        mine = build(cm)
+        mine.load_state_dict(sd0, strict=True)
+        opt = cm.Adam(mine.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+        opt.attach(mine)
+        b = _generic(ref_run, kind, mine, opt, cm.DeviceLoader, train, valid, weight, group_of)
+    finally:
+        cm._lib.install(old)
+    assert len(a["losses"]) == len(b["losses"]) >= 10
+    err = np.abs(a["losses"] - b["losses"])
+    assert err[:3].max() <= 1e-5 and err.max() <= 5e-4, err
+    for k in ("total_auc", "total_loss", "mean_auc", "mean_loss"):
+        assert abs(a["result"][k] - b["result"][k]) <= 1e-3, (k, a["result"][k], b["result"][k])
