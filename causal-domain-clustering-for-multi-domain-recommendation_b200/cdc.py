@@ -160,6 +160,9 @@ class CDC(BaseModel):
         rt = self.base_model_instance._rt
         xs = [b[0] for b in batches]
         ys = [b[1].reshape(-1) for b in batches]
+        if sum(int(xb.shape[0]) for xb in xs) == 0:
+            out.fill_(float("nan"))                                                  # torch's mean of an empty tensor (cdc.py:116-119)
+            return
         x = torch.cat(xs, dim=0).contiguous()
         y = torch.cat(ys, dim=0)
         y = (y if y.dtype in (torch.int16, torch.float32) else y.to(torch.float32)).contiguous()

@@ -208,6 +208,77 @@ class Base:
         self.V = int(self.field_dims.sum())
         self.l2_emb, self.l2_lin = l2_reg_embedding, l2_reg_linear
         self.drop = None
+        self.atten = None          # enable_atten(): the field self-attention block of BaseModel.build_atten (layer.py:58-69)
+        self._att_cache = None
+
+    # ---------------------------------------------------------------- field self-attention (model/layer.py:58-84)
+    def enable_atten(self, atten_embed_dim, att_layer_num, att_head_num, att_res=True):
+        """config.use_atten with config.atten_embed_dim / att_layer_num / att_head_num / att_res (config.py:24-28).  The block is
+        not regularised (none of the models registers its parameters, ple.py:42-48)."""
+        self.atten = dict(A=int(atten_embed_dim), n_layer=int(att_layer_num), H=int(att_head_num), res=bool(att_res))
+        return self
+
+    def atten_fwd(self, sd, e):
+        """atten_forward (layer.py:71-84): tokens = embed_x.view(B, F, E); atten_embedding; att_layer_num x nn.MultiheadAttention
+        (in_proj -> per-head softmax(q k^T / sqrt(dh)) v -> out_proj; no residual, no norm between layers; attention dropout is
+        inactive at dropout = 0 / eval, the only settings the oracle is used at); + V_res_embedding(tokens) if att_res; ReLU;
+        view(B, F*A); atten_linear (no bias) -> (B, 1)."""
+        a = self.atten
+        B, F, E, A, H = e.shape[0], self.F, self.E, a["A"], a["H"]
+        dh = A // H
+        tok = e.reshape(B * F, E)
+        cur = linear_fwd(tok, sd["atten_embedding.weight"], sd["atten_embedding.bias"])
+        layers = []
+        for i in range(a["n_layer"]):
+            pre = f"self_attns.{i}."
+            qkv = linear_fwd(cur, sd[pre + "in_proj_weight"], sd[pre + "in_proj_bias"])
+            q, k, v = (qkv[:, j * A:(j + 1) * A].reshape(B, F, H, dh).transpose(0, 2, 1, 3) for j in range(3))     # [B, H, F, dh]
+            sc = np.einsum("bhid,bhjd->bhij", q, k).astype(F32) * F32(1.0 / np.sqrt(dh))
+            sc = sc - sc.max(axis=-1, keepdims=True)
+            p = np.exp(sc).astype(F32)
+            p = (p / p.sum(axis=-1, keepdims=True, dtype=F32)).astype(F32)
+            o = np.einsum("bhij,bhjd->bhid", p, v).astype(F32).transpose(0, 2, 1, 3).reshape(B * F, A)
+            layers.append(dict(x=cur, q=q, k=k, v=v, p=p, o=o))
+            cur = linear_fwd(o, sd[pre + "out_proj.weight"], sd[pre + "out_proj.bias"])
+        if a["res"]:
+            cur = cur + linear_fwd(tok, sd["V_res_embedding.weight"], sd["V_res_embedding.bias"])
+        r = np.maximum(cur, 0).reshape(B, F * A)
+        out = linear_fwd(r, sd["atten_linear.weight"])
+        return out, dict(tok=tok, layers=layers, z=cur, r=r)
+
+    def atten_bwd(self, sd, c, dout, grads):
+        """gradient of atten_fwd's (B, 1) output: parameter gradients into `grads`, returns d(embed_x) [B, F*E]."""
+        a = self.atten
+        A, H = a["A"], a["H"]
+        dh = A // H
+        tok = c["tok"]
+        M = tok.shape[0]
+        B = M // self.F
+        dr, dW, _ = linear_bwd(c["r"], sd["atten_linear.weight"], dout, has_bias=False)
+        _acc(grads, "atten_linear.weight", dW)
+        dy = (dr.reshape(M, A) * (c["z"] > 0)).astype(F32)
+        dtok = np.zeros_like(tok)
+        if a["res"]:
+            dx, dW, db = linear_bwd(tok, sd["V_res_embedding.weight"], dy)
+            _acc(grads, "V_res_embedding.weight", dW); _acc(grads, "V_res_embedding.bias", db)
+            dtok += dx
+        for i in reversed(range(a["n_layer"])):
+            pre, L = f"self_attns.{i}.", c["layers"][i]
+            do, dW, db = linear_bwd(L["o"], sd[pre + "out_proj.weight"], dy)
+            _acc(grads, pre + "out_proj.weight", dW); _acc(grads, pre + "out_proj.bias", db)
+            do = do.reshape(B, self.F, H, dh).transpose(0, 2, 1, 3)
+            dv = np.einsum("bhij,bhid->bhjd", L["p"], do)
+            dp = np.einsum("bhid,bhjd->bhij", do, L["v"])
+            ds = (L["p"] * (dp - (L["p"] * dp).sum(axis=-1, keepdims=True)) * F32(1.0 / np.sqrt(dh))).astype(F32)
+            dq = np.einsum("bhij,bhjd->bhid", ds, L["k"])
+            dk = np.einsum("bhij,bhid->bhjd", ds, L["q"])
+            dqkv = np.concatenate([t.astype(F32).transpose(0, 2, 1, 3).reshape(M, A) for t in (dq, dk, dv)], axis=1)
+            dy, dW, db = linear_bwd(L["x"], sd[pre + "in_proj_weight"], dqkv)
+            _acc(grads, pre + "in_proj_weight", dW); _acc(grads, pre + "in_proj_bias", db)
+        dx, dW, db = linear_bwd(tok, sd["atten_embedding.weight"], dy)
+        _acc(grads, "atten_embedding.weight", dW); _acc(grads, "atten_embedding.bias", db)
+        dtok += dx
+        return dtok.reshape(B, self.F * self.E)
 
     # model/layer.py:31-33, 86-112 and the per-model add_regularization_weight calls
     def reg_items(self, sd):
@@ -237,7 +308,14 @@ class Base:
         return embed_gather(x, self.offsets, sd["embedding.embedding_dict.weight"])
 
     def lin_fwd(self, sd, e):
-        return linear_fwd(e, sd["linear.fc.weight"], sd["linear.fc.bias"])
+        """The `other_outs` every tower logit receives (layer.py:52-54): FeaturesLinear, plus the field self-attention scalar when
+        the model was built with config.use_atten (ple.py:65-67, mmoe.py:68-70, star.py:70-72)."""
+        lin = linear_fwd(e, sd["linear.fc.weight"], sd["linear.fc.bias"])
+        self._att_cache = None
+        if self.atten is not None:
+            a, self._att_cache = self.atten_fwd(sd, e)
+            lin = lin + a
+        return lin
 
     def embed_bwd(self, sd, idx, e, dembed, dlin, grads):
         """FeaturesLinear backward (layer.py:122-126) + embedding scatter (layer.py:153)."""
@@ -245,6 +323,8 @@ class Base:
             dx, dW, db = linear_bwd(e, sd["linear.fc.weight"], dlin)
             _acc(grads, "linear.fc.weight", dW); _acc(grads, "linear.fc.bias", db)
             dembed = dembed + dx
+            if self._att_cache is not None:
+                dembed = dembed + self.atten_bwd(sd, self._att_cache, dlin, grads)
         _acc(grads, "embedding.embedding_dict.weight", embed_scatter_grad(idx, dembed, self.V, self.E))
 
     def towers_fwd(self, sd, tower_in, lin, train, bufs):

@@ -69,9 +69,10 @@ def emulator():
     cm._lib.install(old)
 
 
+@pytest.mark.parametrize("sizes", [(37, 5, 64), (30, 0, 17)])
 @pytest.mark.parametrize("base", sorted(BASES))
-def test_probe_all_domains_host_logic(base, emulator):
-    _run(base, "cpu", sizes=(37, 5, 64))
+def test_probe_all_domains_host_logic(base, sizes, emulator):
+    _run(base, "cpu", sizes=sizes)
 
 
 @pytest.mark.gpu

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import cdcmdr_oracle as O
-from tests.golden_cases import CASES, FIELD_DIMS, E, L2, load, state, strip
+from tests.golden_cases import ALL_CASES as CASES, ATTEN, FIELD_DIMS, E, L2, load, state, strip
 
 KINDS = {"ple": O.PLE, "mmoe": O.MMoE, "dcn": O.DCN, "dcnv2": O.DCNv2, "star": O.STAR}
 RTOL, ATOL = 1e-4, 2e-6      # north_star: fp32 logits and gradients within 1e-4 relative
@@ -44,6 +44,8 @@ def test_train_steps_match_reference(name):
     kind, kw, mode, steps = CASES[name]
     gold = load(name)
     model = KINDS[kind](FIELD_DIMS, E, **kw, **L2)
+    if name in ATTEN:                                        # config.use_atten (tests/golden/make_golden_atten.py)
+        model.enable_atten(**ATTEN[name])
     sd = state(gold, 0)
     opt = O.Adam()
     sel = {}
@@ -75,6 +77,13 @@ def test_train_steps_match_reference(name):
         for k, v in ref.items():
             # a Linear bias that feeds BatchNorm has an exactly-zero true gradient; what Adam sees is
             # fp32 rounding noise normalised to +-lr per step, in the reference as much as here.
+            if k.endswith("in_proj_bias"):
+                # the key bias of an attention layer has a mathematically zero gradient (softmax cancels a shift common to a row's
+                # scores): rounding noise -> +-lr steps under Adam, like a bias in front of a batch-statistics BatchNorm
+                n3 = v.shape[0] // 3
+                close(sd[k][n3:2 * n3], v[n3:2 * n3], f"{name} step{s + 1} {k} (key third)", atol=2.1e-3 * (s + 1))
+                close(np.delete(sd[k], np.s_[n3:2 * n3]), np.delete(v, np.s_[n3:2 * n3]), f"{name} step{s + 1} {k}", atol=1e-6)
+                continue
             close(sd[k].reshape(v.shape), v, f"{name} step{s + 1} {k}",
                   atol=2.1e-3 * (s + 1) if bias_before_bn(kind, k) else (3e-4 * (s + 1) if k.endswith("running_mean") else 1e-6))
     # eval-mode forward with the reference's final weights (eval BN does not cancel the noise-driven biases)
