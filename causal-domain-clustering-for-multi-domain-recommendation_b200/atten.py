@@ -1,5 +1,5 @@
 """The field self-attention block of BaseModel (reference model/layer.py:58-84): with `config.use_atten`
-(on in the stock config.py:24-28) PLE / MMoE add one more scalar to every tower logit,
+(on in the stock config.py:24-28) PLE / MMoE / STAR add one more scalar to every tower logit,
 
     atten_x = atten_embedding(embed_x.view(B, F, E))                     Linear(E -> A) per field token
     for attn in self_attns:  x = MultiheadAttention(A, heads)(x, x, x)    in_proj -> softmax(q k^T / sqrt(dh)) v -> out_proj
@@ -14,7 +14,6 @@ from __future__ import annotations
 
 import math
 
-import torch
 from torch import nn
 
 from .core import Mat
@@ -61,11 +60,8 @@ class AttnBlock:
         p = rt.dropout if train else 0.0
         return p, (rt.seed_ptr if p > 0 else None)
 
-    def _attn_core(self, fn, *args):
-        fn(*args, self.rt.ops.stream)
-
     # ---------------------------------------------------------------- forward: lin[b] += atten_forward(embed_x)[b]
-    def fwd(self, ws, X32: Mat, B, lin: Mat, train, save=True):
+    def fwd(self, ws, X32: Mat, B, lin: Mat, train):
         rt, ops = self.rt, self.rt.ops
         F, E, A, H, dh = self.F, self.E, self.A, self.H, self.dh
         M = B * F

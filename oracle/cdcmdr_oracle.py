@@ -21,7 +21,6 @@ itself is noisy (a BatchNorm unit that is constant over the batch: rounding-nois
 """
 from __future__ import annotations
 
-import re
 import numpy as np
 
 F32 = np.float32

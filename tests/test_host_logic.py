@@ -8,8 +8,8 @@ import torch
 
 import cdcmdr_b200 as cm
 from oracle.host_abi import HostABI
-from tests.golden_cases import CASES, FIELD_DIMS, E, L2, load, state
-from tests.test_oracle_golden import bias_before_bn, close
+from tests.golden_cases import CASES, FIELD_DIMS, load
+from tests.test_oracle_golden import bias_before_bn
 from tests.util import build_model, run_golden_case
 
 
