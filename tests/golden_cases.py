@@ -23,7 +23,7 @@ for _base, _kw in (("ple", CASES["ple"][1]), ("mmoe", CASES["mmoe"][1]), ("star"
         CASES[f"cdc_{_base}_{_mode}"] = (_base, _kw, _sel, 2)
 
 # the field self-attention block (config.use_atten; tests/golden/make_golden_atten.py): the same models with the
-# block switched on - not part of the numpy model oracle, pinned through the host logic and on the GPU
+# block switched on; the numpy model oracle is pinned on them too (Base.enable_atten, tests/test_oracle_golden.py)
 ATTEN = {"ple_atten": dict(atten_embed_dim=8, att_layer_num=2, att_head_num=2, att_res=True),
          "mmoe_atten": dict(atten_embed_dim=8, att_layer_num=3, att_head_num=2, att_res=False),
          "star_atten": dict(atten_embed_dim=8, att_layer_num=2, att_head_num=2, att_res=True),
