@@ -12,6 +12,7 @@ from __future__ import annotations
 import copy
 
 import numpy as np
+import torch
 
 F32 = np.float32
 
@@ -47,6 +48,7 @@ class Grouping:
     def __init__(self, n_domain, n_cluster, domain_cnt_weight, config, use_metric="loss"):
         self.n_domain, self.n_cluster = n_domain, n_cluster
         self.w = np.asarray(domain_cnt_weight, dtype=F32)
+        self.w_t = torch.tensor([float(v) for v in domain_cnt_weight], dtype=torch.float32)      # cdc.py:62
         self.affinity_func = getattr(config, "affinity_func", "minus")
         self.p_weight0 = getattr(config, "p_weight", 0.1)
         self.p_weight = self.p_weight0
@@ -64,6 +66,7 @@ class Grouping:
         else:
             self.default_metric_value, self.max_better = F32(-1e6), True
         self.A = self.B = self.causal = None
+        self.A_t = self.B_t = self.causal_t = None
 
     # ---------------------------------------------------------------- cdc.py:296-306
     def _update_p_weight(self):
@@ -75,29 +78,30 @@ class Grouping:
             elif self.p_weight_method == "exponential_decay":
                 self.p_weight = self.p_weight * self.p_weight_exp_decay
 
+    # The affinity arithmetic below runs on torch CPU float32 tensors, operation for operation in upstream's order: the regrouping
+    # compares sums over the SAME domains taken in different orders (two source groups that both grew to contain every domain),
+    # so its decisions hang on the last bit of a float32 reduction - only torch's own reduction order reproduces them (found by
+    # differential fuzzing against the reference: 3 of 480 calls disagreed with NumPy sums, 0 with these).
     # ---------------------------------------------------------------- cdc.py:321-341
     def _lambda(self, group, domain=None):
         """lambda_d = clamp(0.5 (|G|-1) sum_{g in G} dist[g, d] / (sum_{GxG} dist - sum_{g in G} dist[g, d]), 0, 1)"""
         g = list(group)
         dom = list(range(self.n_domain)) if domain is None else list(domain)
-        total = self.causal[np.ix_(g, g)].sum(dtype=F32)
-        related = self.causal[np.ix_(g, dom)].sum(axis=0, dtype=F32)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            vals = F32(len(g) - 1) * related / (total - related) * F32(0.5)
-        return np.clip(vals, F32(0), F32(1)).astype(F32)           # NaN (0/0) stays NaN, as torch.clamp leaves it
+        total = torch.sum(self.causal_t[np.ix_(g, g)])
+        related = torch.sum(self.causal_t[np.ix_(g, dom)], dim=0)
+        vals = (len(g) - 1) * related / (total - related) * 0.5
+        return torch.clamp(vals, min=0, max=1)                  # NaN (0/0) stays NaN
 
     # ---------------------------------------------------------------- cdc.py:314-319
     def _centers(self, group, center_num=1):
         k = min(center_num, len(group))
-        dist = self._lambda(group, group)
-        order = _topk_smallest(dist, k)
-        return [group[i] for i in order]
+        order = torch.topk(self._lambda(group, group), k=k, largest=False)[1]
+        return [group[int(i)] for i in order]
 
     # ---------------------------------------------------------------- cdc.py:308-312
     def _metric_in_source_group(self, target, s_group):
         lam = self._lambda(s_group, [target])
-        a, b = self.A[s_group, target], self.B[s_group, target]
-        return ((F32(1) - lam) * a + lam * b).sum(dtype=F32)
+        return torch.sum((1 - lam) * self.A_t[s_group, target] + lam * self.B_t[s_group, target])
 
     # ---------------------------------------------------------------- cdc.py:240-294
     def _source_domains(self, t_group, group_idx):
@@ -105,28 +109,25 @@ class Grouping:
         s_group = self._centers(t_group, center_num=2)
         useful = True
         while useful and len(s_group) < nd:
-            lam = np.zeros((nd, len(t_group)), dtype=F32)
+            rows = []
             for d in range(nd):
-                if d not in s_group:
-                    lam[d] = self._lambda(s_group + [d], t_group)
-            wt = self.w[t_group]
-            sw = wt.sum(dtype=F32)
+                rows.append(torch.zeros(len(t_group), dtype=torch.float32) if d in s_group else self._lambda(s_group + [d], t_group))
+            lam = torch.stack(rows, dim=0)
+            wt = self.w_t[t_group]
+            sw = wt.sum()
             if sw != 0:
                 wt = wt / sw
-            J = (((F32(1) - lam) * self.A[:nd][:, t_group] + lam * self.B[:nd][:, t_group]) * wt).sum(axis=1, dtype=F32)
+            J = (((1 - lam) * self.A_t[:nd, t_group] + lam * self.B_t[:nd, t_group]) * wt).sum(dim=1)
             if self.initial_s_group2domain_list is None:
                 result = J
             else:
-                P = (F32(1) - F32(2) * self._lambda(self.initial_s_group2domain_list[group_idx])) * np.power(self.w, F32(0.5))
-                result = J + F32(self.p_weight) * P if self.max_better else J - F32(self.p_weight) * P
-            result = result.astype(F32)
-            result[s_group] = self.default_metric_value
-            if self.max_better:
-                best = int(_argmax(result)); useful = bool(result[best] > 0)
-            else:
-                best = int(_argmin(result)); useful = bool(result[best] < 0)
+                P = (1 - 2 * self._lambda(self.initial_s_group2domain_list[group_idx])) * torch.pow(self.w_t, 0.5)
+                result = J + self.p_weight * P if self.max_better else J - self.p_weight * P
+            result[s_group] = float(self.default_metric_value)
+            best_value, best = torch.max(result, 0) if self.max_better else torch.min(result, 0)
+            useful = bool(best_value > 0) if self.max_better else bool(best_value < 0)
             if useful:
-                s_group.append(best)
+                s_group.append(int(best))
         return s_group
 
     # ---------------------------------------------------------------- cdc.py:121-238
@@ -155,6 +156,7 @@ class Grouping:
             raise ValueError("Unknown affinity_func: " + str(self.affinity_func))
         self.A, self.B = A, B
         self.causal = np.arccos(calc_causal_matrix(M.T)).astype(F32)
+        self.A_t, self.B_t, self.causal_t = torch.from_numpy(A), torch.from_numpy(B), torch.from_numpy(self.causal)
 
         if max(self.domain2group_list) == 0:
             # first call: k-means on the rows of the causal distance matrix (unseeded upstream: NumPy's global RNG)
@@ -171,14 +173,13 @@ class Grouping:
             t_old = self.t_group2domain_list
             queue = list(range(nd))
             t_group, s_group = [[] for _ in range(nc)], [[] for _ in range(nc)]
-            metric = np.empty((nd, nc), dtype=F32)
-            metric[...] = 0
+            metric = torch.zeros(nd, nc, dtype=torch.float32)       # upstream: torch.empty, every entry is written before it is read
             centers = [self._centers(t_old[c])[0] for c in range(nc)]
             for c in range(nc):
                 t_group[c].append(centers[c])
                 queue.remove(centers[c])
-                metric[centers[c], :] = self.default_metric_value
-            pick = _argmax if self.max_better else _argmin
+                metric[centers[c], :] = float(self.default_metric_value)
+            pick = (lambda v: int(torch.argmax(v))) if self.max_better else (lambda v: int(torch.argmin(v)))
             if mode == "iterative":
                 progressed = True
                 while queue and progressed:
@@ -188,13 +189,13 @@ class Grouping:
                     for d in queue:
                         for c in range(nc):
                             metric[d, c] = self._metric_in_source_group(d, s_group[c])
-                    best = [int(pick(metric[:, c])) for c in range(nc)]
+                    best = [int(v) for v in (torch.argmax(metric, dim=0) if self.max_better else torch.argmin(metric, dim=0))]
                     for c in range(nc):
                         if int(pick(metric[best[c], :])) == c:
                             progressed = True
                             t_group[c].append(best[c])
                             queue.remove(best[c])
-                            metric[best[c], :] = self.default_metric_value
+                            metric[best[c], :] = float(self.default_metric_value)
                 if queue:
                     raise ValueError("target domain_queue is not empty")
             elif mode == "greedy":
@@ -214,23 +215,3 @@ class Grouping:
                 d2g_new[t_group[c]] = c
             self.domain2group_list = d2g_new.tolist()
         return dict(A=A, B=B, mask=M, causal=self.causal)
-
-
-# torch.argmax / argmin / max / min return the FIRST extreme element on ties and PROPAGATE NaN (a NaN is both the largest and the
-# smallest value: the index of the first NaN comes back); topk(largest=False) ranks NaN last
-def _argmax(v):
-    v = np.asarray(v)
-    nan = np.isnan(v)
-    return int(np.flatnonzero(nan)[0]) if nan.any() else int(np.argmax(v))
-
-
-def _argmin(v):
-    v = np.asarray(v)
-    nan = np.isnan(v)
-    return int(np.flatnonzero(nan)[0]) if nan.any() else int(np.argmin(v))
-
-
-def _topk_smallest(v, k):
-    v = np.asarray(v, dtype=np.float64)
-    key = np.where(np.isnan(v), np.inf, v)
-    return [int(i) for i in np.argsort(key, kind="stable")[:k]]

@@ -60,16 +60,3 @@ def test_causal_kernel_matches_oracle():
     rng = np.random.default_rng(0)
     X = rng.standard_normal((9, 14))
     np.testing.assert_allclose(calc_causal_matrix(X), O.calc_causal_matrix(X), rtol=1e-12)
-
-
-def test_extreme_element_picks_follow_torch_nan_rules():
-    """update_group picks domains with torch.argmax / argmin / min / max (cdc.py:186-201, 282-287), which PROPAGATE NaN: the index
-    of the first NaN comes back for both (a single-domain group has lambda 0/0 = NaN against itself, so NaNs do reach these picks;
-    found by the probing-loop fixtures, tests/test_cdc_update_matrix.py).  Checked against torch itself."""
-    g = cm.cdc_group
-    nan = float("nan")
-    for v in ([1.0, nan, 0.0], [nan, nan, 3.0], [2.0, 1.0, 1.0], [5.0, 7.0, 7.0], [0.5, 2.0, nan, nan]):
-        t = torch.tensor(v)
-        assert g._argmin(np.array(v, dtype=np.float32)) == int(torch.argmin(t)), v
-        assert g._argmax(np.array(v, dtype=np.float32)) == int(torch.argmax(t)), v
-        assert g._argmin(np.array(v, dtype=np.float32)) == int(torch.min(t, 0)[1]), v
