@@ -164,7 +164,7 @@ class DCN(_CrossModel):
         mlp_out = self._mlp._act(ws, len(self.mlp_dims) - 1, B)
         dcross, dmlp = self._head_bwd(ws, "mlp_linear.weight", xs[L], mlp_out, dlogits, B)
         dX = ws.mat("dX", B, D)
-        self._mlp.bwd(ws, X, dmlp, B, train, dX)
+        self._mlp.bwd(ws, X, dmlp, B, train, dX, post_act_grad=True)
         dx0 = ws.mat("cn.dx0", B, D, zero=True)
         dx0.t[:B * D].zero_()
         dx = dcross
@@ -439,14 +439,14 @@ class DCNv2(_CrossModel):
         dX = ws.mat("dX", B, D)
         if self.model_structure == "parallel":
             dcross, dmlp = self._head_bwd(ws, "dnn_linear.weight", cross, mlp_out, dlogits, B)
-            self._mlp.bwd(ws, X, dmlp, B, train, dX)
+            self._mlp.bwd(ws, X, dmlp, B, train, dX, post_act_grad=True)
             dx = cross_bwd(ws, x0, dcross, B)
             rt.ops.add2d(dx, dX, B, D, True)
         else:
             _, dmlp = self._head_bwd(ws, "dnn_linear.weight", None, mlp_out, dlogits, B)
             mlp_in = rt.gemm_input(ws, "dnn.in_op", cross, B, D) if rt.bf16 else cross
             dcross = ws.mat("dnn.dX", B, D)
-            self._mlp.bwd(ws, mlp_in, dmlp, B, train, dcross)
+            self._mlp.bwd(ws, mlp_in, dmlp, B, train, dcross, post_act_grad=True)
             dx = cross_bwd(ws, x0, dcross, B)
             rt.ops.add2d(dx, dX, B, D, False)
         self._lin_bwd(ws, X, B, dX)

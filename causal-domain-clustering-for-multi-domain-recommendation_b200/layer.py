@@ -237,6 +237,10 @@ class BaseModel(nn.Module):
             for bname, numel in getattr(self, "_extra_blocks", []):
                 o = rt.params.off[bname]
                 rt.present[o:o + numel] = 0
+            rt.present_b1 = rt.present.clone()
+            for m in self._single_row_absent():
+                o = rt.params.off[m]
+                rt.present_b1[o:o + named[m].numel()] = 0
         if old is not None:
             rt.dp = old.dp
         if old is not None and old.M is not None:
@@ -259,6 +263,18 @@ class BaseModel(nn.Module):
     def _absent_grads(self):
         """Parameters whose .grad stays None in the reference (never reached by forward)."""
         return []
+
+    def _single_row_absent(self):
+        """Parameters the reference does not reach on a ONE-row batch: every BatchNorm is skipped there (MultiLayerPerceptron
+        layer.py:202-204, STAR's partitioned norm and DNN star.py:134-135 / layer.py:290-292), so its affine parameters keep
+        `.grad is None` and torch.optim.Adam leaves them and their moments alone (a last batch of size 1 happens whenever the
+        dataset size is 1 modulo the batch size)."""
+        names = []
+        for mname, mod in self.named_modules():
+            if isinstance(mod, nn.modules.batchnorm._NormBase):
+                names += [f"{mname}.{leaf}" for leaf, _ in mod.named_parameters(recurse=False)]
+        names += [n for n in ("shared_bn_weight", "shared_bn_bias") if hasattr(self, n)]
+        return names
 
     def _on_runtime_built(self):
         pass
@@ -381,10 +397,11 @@ class BaseModel(nn.Module):
         rt.ops.embed_bwd_dense(dX, plan, B, F, E, V, gtab)
         G = rt.G.clone()
         grads = []
+        single_row = set(self._single_row_absent()) if B == 1 else ()
         for name, p in self._autograd_params():
             if name == "embedding.embedding_dict.weight":
                 grads.append(gtab)
-            elif name in self._absent_set:
+            elif name in self._absent_set or (B == 1 and name in single_row):
                 grads.append(None)
             else:
                 o = rt.params.off[name]
@@ -510,7 +527,7 @@ class BaseModel(nn.Module):
 
         def dense_update():
             rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
-            rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present, rt.W.numel(), rt.step_state)
+            rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present_b1 if B == 1 else rt.present, rt.W.numel(), rt.step_state)
 
         def table_update():
             if self._table_state is None:

@@ -327,15 +327,22 @@ class MlpGroup:
             return L
         return prev
 
-    def bwd(self, ws: Workspace, X: Mat, dOut: Mat, B, train, dX: Mat | None, accumulate=False, final_dx=False):
+    def bwd(self, ws: Workspace, X: Mat, dOut: Mat, B, train, dX: Mat | None, accumulate=False, final_dx=False, post_act_grad=False):
         """dOut: gradient w.r.t. the group's output: dlogits [B, G] fp32 (out_layer), else the gradient of the last
-        post-activation [B, G*d_last] (bn) or of the last PRE-activation (no bn: the caller applied the ReLU mask)."""
+        post-activation [B, G*d_last] (bn) or of the last PRE-activation (no bn: the caller applied the ReLU mask).
+        post_act_grad: the caller always hands the post-activation gradient (DCN / DCNv2 heads); a BatchNorm group that skips its
+        BatchNorm on a single row (layer.py:202-204) then applies the ReLU / dropout mask itself."""
         rt, G, nl = self.rt, self.G, len(self.dims)
         use_bn = self.bn and B != 1
         drop = rt.dropout if train else 0.0
         keep = 1.0 / (1.0 - drop) if drop > 0 else 1.0
         d_last = self.dims[-1]
         cur = dOut
+        if post_act_grad and self.bn and not use_bn and not self.out_layer:
+            if rt.bf16:
+                raise NotImplementedError("bf16 path: batch size 1 skips BatchNorm (layer.py:202-204); train it on the fp32 path")
+            cur = ws.mat(f"{self.tag}.dA{nl - 1}", B, G * d_last)
+            rt.ops.relu_mask(dOut, self._act(ws, nl - 1, B), cur, B, G * d_last, keep)
         if self.out_layer:
             A_last = self._act(ws, nl - 1, B)
             dA = ws.mat(f"{self.tag}.dA{nl - 1}", B, G * d_last)          # fp32
