@@ -9,6 +9,7 @@ batch of an epoch whenever the dataset size is 1 modulo the batch size: DCN / DC
 MLP backward, and BatchNorm parameters must be ABSENT from that step (the reference never reaches them: `.grad is None`, Adam
 leaves them and their moments alone) instead of taking a stale or zero gradient."""
 import contextlib
+import copy
 import io
 import os
 import sys
@@ -75,6 +76,17 @@ def _noise_gradient(ref, kind, k):
     return isinstance(nxt, torch.nn.BatchNorm1d)
 
 
+def _grads64(model, mode, x, y, g):
+    """first-step gradients of the float64 copy of the reference module"""
+    model.train()
+    p = model(x)
+    sel = p.reshape(-1) if mode == "single" else p.gather(1, g).squeeze(1)
+    loss = torch.nn.BCELoss()(sel, y.reshape(-1).double()) + model.get_regularization_loss(device="cpu")
+    model.zero_grad()
+    loss.backward()
+    return {k: v.grad.detach().numpy().copy() for k, v in model.named_parameters() if v.grad is not None}
+
+
 def _two_steps(model, mode, x, y, g, opt):
     crit = torch.nn.BCELoss()
     model.train()
@@ -138,6 +150,7 @@ def test_models_match_live_reference(block, monkeypatch):
                     for b_ in ref.crossnet.bias:
                         b_.normal_(0, 0.1)
             mine.load_state_dict(ref.state_dict(), strict=True)
+            ref64, truth = copy.deepcopy(ref).double(), None
             xt, yt, gt = torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(g)
             adam = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
             a, ae = _two_steps(ref, mode, xt, yt, gt, torch.optim.Adam(ref.parameters(), **adam))
@@ -162,7 +175,17 @@ def test_models_match_live_reference(block, monkeypatch):
                                 assert np.abs(v[n3:2 * n3] - w[n3:2 * n3]).max() <= 1e-3, (what, k)
                                 v, w = np.delete(v, np.s_[n3:2 * n3]), np.delete(w, np.s_[n3:2 * n3])
                             err = float(np.abs(v - w).max())
-                            assert err <= 2e-4 * float(np.abs(v).max()) + 3e-5, (what, k, err)
+                            if err > 2e-4 * float(np.abs(v).max()) + 3e-5:
+                                # the reference's own fp32 run is fragile where a pre-activation sits within an ulp of zero (which
+                                # side of the ReLU it lands on depends on the BLAS kernel torch picks): the float64 run of the same
+                                # module decides
+                                if truth is None:
+                                    truth = _grads64(ref64, mode, xt, yt, gt)
+                                t = truth[k]
+                                if k.endswith("in_proj_bias"):
+                                    t = np.delete(t, np.s_[n3:2 * n3])
+                                err = float(np.abs(t - w).max())
+                                assert err <= 2e-4 * float(np.abs(t).max()) + 3e-5, (what, k, err, "against the float64 reference")
             assert ae.shape == be.shape and np.abs(ae - be).max() <= 3e-3, (what, "eval")
     finally:
         cm._lib.install(old)
