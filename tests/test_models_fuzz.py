@@ -150,6 +150,9 @@ def test_models_match_live_reference(block, monkeypatch):
                     for b_ in ref.crossnet.bias:
                         b_.normal_(0, 0.1)
             mine.load_state_dict(ref.state_dict(), strict=True)
+            with contextlib.redirect_stdout(io.StringIO()):
+                fused, _ = _build(cm, kind, fd, E, T, cfg, seed)
+            fused.load_state_dict(ref.state_dict(), strict=True)
             ref64, truth = copy.deepcopy(ref).double(), None
             xt, yt, gt = torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(g)
             adam = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
@@ -187,5 +190,23 @@ def test_models_match_live_reference(block, monkeypatch):
                                 err = float(np.abs(t - w).max())
                                 assert err <= 2e-4 * float(np.abs(t).max()) + 3e-5, (what, k, err, "against the float64 reference")
             assert ae.shape == be.shape and np.abs(ae - be).max() <= 3e-3, (what, "eval")
+            # the fused step (what bench.py times) against the loss.backward() path of this package on the same weights: same kernels,
+            # different wiring (selection fused into the BCE kernel, regulariser and Adam inside the step)
+            opt_f = cm.Adam(fused.parameters(), **adam)
+            fused.train()
+            for s in range(2):
+                if mode == "star" and s == 1:
+                    out = fused.train_step(xt, yt, opt_f, mode="col", col=0, x_group=gt)
+                elif mode == "single":
+                    out = fused.train_step(xt, yt, opt_f, mode="col", col=0)
+                else:
+                    out = fused.train_step(xt, yt, opt_f, mode="gather", sel=gt)
+                loss_f, _, _ = fused.step_losses(out)
+                pf = out["pred"].detach().numpy().reshape(-1)
+                assert pf.shape == b[s][0].shape and np.abs(pf - b[s][0]).max() <= 1e-6 + (2e-3 if s else 0), (what, s, "fused pred")
+                assert abs(loss_f - b[s][1]) <= (1e-5 + (2e-3 if s else 0)) * max(1.0, abs(loss_f)), (what, s, "fused loss", loss_f, b[s][1])
+            sd_a = {k: v.detach().numpy() for k, v in mine.state_dict().items()}
+            for k, v in fused.state_dict().items():
+                assert np.abs(v.detach().numpy() - sd_a[k]).max() <= 2.1e-3 * 2, (what, k, "fused state")   # at most the +-lr noise moves
     finally:
         cm._lib.install(old)
