@@ -91,7 +91,7 @@ class DataParallel:
         outs[self.rank].copy_(ins[self.rank])
         reqs = []
         for r in range(self.world):
-            if r != self.rank:
+            if r != self.rank and ins[r].numel():            # empty blocks (an owner without fields) are skipped on both sides
                 reqs.append(dist.isend(ins[r].contiguous(), dist.get_global_rank(self.group, r), group=self.group))
         for r in range(self.world):
             if r != self.rank and outs[r].numel():

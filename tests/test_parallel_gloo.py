@@ -28,7 +28,7 @@ L2 = dict(l2_reg_embedding=1e-3, l2_reg_linear=1e-3, l2_reg_dnn=1e-3)
 ADAM = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
 
 
-def _build(kind, precision="fp32"):
+def _build(kind, precision="fp32", FD=FD):
     torch.manual_seed(5)
     cfg = Cfg(); cfg.cdcmdr_precision = precision
     if kind == "ple_atten":                                   # the stock config's field self-attention block on replicas
@@ -43,7 +43,7 @@ def _build(kind, precision="fp32"):
     return m
 
 
-def _data(B):
+def _data(B, FD=FD):
     rng = np.random.default_rng(3)
     x = np.stack([rng.integers(0, d, size=B) for d in FD], axis=1).astype(np.int32)
     y = (rng.random(B) < 0.3).astype(np.int16)
@@ -65,14 +65,15 @@ def _steps(model, kind, x, y, g, n):
     return outs
 
 
-def _worker(rank, world, port, kind, B, n_steps, path):
+def _worker(rank, world, port, kind, B, n_steps, path, fd=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         cm._lib.install(HostABI())
-        model = _build(kind)
+        fd = FD if fd is None else np.asarray(fd, dtype=np.int64)
+        model = _build(kind, FD=fd)
         dp = cm.parallel.attach_data_parallel(model)
-        x, y, g = _data(B)
+        x, y, g = _data(B, FD=fd)
         lo, hi = rank * B // world, (rank + 1) * B // world
         outs = _steps(model, kind, x[lo:hi], y[lo:hi], g[lo:hi], n_steps)
         dp.gather_table()
@@ -91,15 +92,27 @@ def _free_port():
 
 @pytest.mark.parametrize("kind", ["ple", "mmoe", "cdc", "ple_atten"])
 def test_two_ranks_match_one_process(kind):
-    B, n_steps, world = 96, 3, 2
+    _ranks_match_one_process(kind, 2, FD)
+
+
+@pytest.mark.parametrize("kind,world,fields", [("mmoe", 3, [11, 7, 13, ND, 9, 5, 8]), ("cdc", 4, [11, 7, 13, ND, 9, 5, 8]),
+                                               ("ple", 4, [11, 7, 13, ND]), ("ple", 4, [11, 7, 13])])
+def test_more_ranks_and_uneven_field_splits(kind, world, fields):
+    """3 and 4 ranks over 7 fields (owners of 2 / 2 / 3 and 1 / 2 / 2 / 2 fields: runs of equal owners are packed per strided-batch
+    copy) and 4 ranks over 4 fields (one field each) and over 3 fields (rank 0 owns no rows of the table at all); the batch splits unevenly too (96 rows over 3 ranks is even, 4 ranks 24 each)"""
+    _ranks_match_one_process(kind, world, np.asarray(fields, dtype=np.int64))
+
+
+def _ranks_match_one_process(kind, world, fd):
+    B, n_steps = 96, 3
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_worker, args=(world, _free_port(), kind, B, n_steps, tmp), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, _free_port(), kind, B, n_steps, tmp, [int(v) for v in fd]), nprocs=world, join=True)
         ranks = [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
     old = cm._lib._LIB
     cm._lib.install(HostABI())
     try:
-        model = _build(kind)
-        x, y, g = _data(B)
+        model = _build(kind, FD=fd)
+        x, y, g = _data(B, FD=fd)
         ref = _steps(model, kind, x, y, g, n_steps)
         sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
     finally:
