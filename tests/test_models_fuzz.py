@@ -210,3 +210,63 @@ def test_models_match_live_reference(block, monkeypatch):
                 assert np.abs(v.detach().numpy() - sd_a[k]).max() <= 2.1e-3 * 2, (what, k, "fused state")   # at most the +-lr noise moves
     finally:
         cm._lib.install(old)
+
+
+def test_cdc_modes_match_live_reference(monkeypatch):
+    """CDC over PLE / MMoE / STAR (with and without the attention block) on random geometries and a random domain -> cluster map: the
+    three forward modes in sequence (warm-up mean, fixed domain, per-sample gather; cdc.py:95-111), each followed by a step - the
+    reference against this package's loss.backward() path, and that against the fused train_step.  (150 seeds swept offline.)"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as G
+    monkeypatch.chdir(tempfile.mkdtemp())
+    old = cm._lib._LIB
+    cm._lib.install(HostABI())
+    try:
+        for seed in range(24):
+            rng = np.random.default_rng(seed)
+            base, nd, T, E, F = ["ple", "mmoe", "star"][seed % 3], int(rng.integers(3, 9)), int(rng.integers(1, 5)), int(rng.choice([2, 4, 8])), \
+                int(rng.integers(3, 7))
+            fd = rng.integers(3, 12, size=F).astype(np.int64)
+            dom = int(rng.integers(0, F))
+            fd[dom] = nd
+            B, atten = int(rng.choice([1, 17, 40])), bool(rng.integers(0, 2))
+            cfg = _config(rng, atten)
+            cfg.p_weight, cfg.p_weight_method, cfg.p_weight_exp_decay, cfg.old_matrix_weight, cfg.affinity_func = 0.1, "linear_decay", 0.9, 0.0, "minus"
+            ed, td = {"ple": (((8, 6), (4,)), (6,)), "mmoe": ((8, 4), (6, 4)), "star": (None, (8, 4))}[base]
+            w = (np.ones(nd) / nd).tolist()
+            x = torch.from_numpy(np.stack([rng.integers(0, d, size=B) for d in fd], axis=1).astype(np.int32))
+            y = torch.from_numpy((rng.random((B, 1)) < 0.4).astype(np.int16))
+            d2g = [int(v) for v in rng.integers(0, T, size=nd)]
+            what = dict(seed=seed, base=base, nd=nd, T=T, E=E, F=F, B=B, atten=atten)
+            torch.manual_seed(seed)
+            with contextlib.redirect_stdout(io.StringIO()):
+                ref = G.CDC(fd, E, T, nd, base, ed, td, dom, domain_cnt_weight=w, n_causal_mask=3, device="cpu", dropout=0.0, config=cfg, **L2)
+                mine, fused = (cm.CDC(fd, E, T, nd, base, ed, td, dom, domain_cnt_weight=w, n_causal_mask=3, dropout=0.0, config=cfg, **L2)
+                               for _ in range(2))
+            ref.domain2group_list, ref.domain2group = list(d2g), torch.tensor(d2g, dtype=torch.int64)
+            for m in (mine, fused):
+                m.load_state_dict(ref.state_dict(), strict=True)
+                m.set_groups(d2g)
+            adam = dict(lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+            opt_r, opt_m, opt_f = torch.optim.Adam(ref.parameters(), **adam), cm.Adam(mine.parameters(), **adam), cm.Adam(fused.parameters(), **adam)
+            opt_m.attach(mine.base_model_instance)
+            for step, (mode, di) in enumerate([("warmup", None), ("split", int(rng.integers(0, nd))), ("split", None)]):
+                res = []
+                for m, o in ((ref, opt_r), (mine, opt_m)):
+                    m.train()
+                    p = m(x, mode=mode, domain_i=di)
+                    loss = torch.nn.BCELoss()(p.reshape(-1), y.reshape(-1).float()) + m.get_regularization_loss(device="cpu")
+                    m.zero_grad()
+                    loss.backward()
+                    o.step()
+                    res.append((p.detach().numpy().reshape(-1).copy(), float(loss.detach())))
+                fused.train()
+                out = fused.train_step(x, y, opt_f, mode=mode, domain_i=di)
+                loss_f, _, _ = fused.step_losses(out)
+                tol = 1e-4 + 3e-3 * step                    # later steps see Adam's +-lr moves of the noise-gradient biases
+                assert np.abs(res[0][0] - res[1][0]).max() <= tol, (what, step, mode, "pred")
+                assert abs(res[0][1] - res[1][1]) <= tol * max(1.0, abs(res[0][1])), (what, step, mode, "loss")
+                assert np.abs(out["psel"].numpy().reshape(-1) - res[1][0]).max() <= 1e-6 + 2e-3 * step, (what, step, mode, "fused pred")
+                assert abs(loss_f - res[1][1]) <= (1e-5 + 2e-3 * step) * max(1.0, abs(loss_f)), (what, step, mode, "fused loss")
+    finally:
+        cm._lib.install(old)
