@@ -123,9 +123,13 @@ class CDC(BaseModel):
         return self.base_model_instance.get_regularization_loss(device)
 
     def get_matrix_metric(self, preds, targets):
-        if self.use_metric != 'loss':
-            raise NotImplementedError("use_metric='auc' runs sklearn on the host in the reference (cdc.py:116-119)")
-        return torch.nn.functional.binary_cross_entropy(preds, targets).detach()
+        """cdc.py:113-119.  'auc' is scikit-learn on the host upstream and stays there (one affinity entry per call)."""
+        if self.use_metric == 'loss':
+            return torch.nn.functional.binary_cross_entropy(preds, targets).detach()
+        if self.use_metric == 'auc':
+            from sklearn.metrics import roc_auc_score
+            return roc_auc_score(targets.detach().cpu().numpy(), preds.detach().cpu().numpy())
+        raise ValueError(f"unknown use_metric {self.use_metric!r}")
 
     def probe_all_domains(self, batches, max_rows=None):
         """One row of the affinity matrices (run.py:551-560 `cdc_test_all_domain`): the BCE of every domain's batch under the current
@@ -137,7 +141,7 @@ class CDC(BaseModel):
         probe is proportional to it - 30 x 65 536 rows hold ~25 GB of activations at the C4 shape); results are identical.
         Returns a float32 tensor [len(batches)] on the model's device; the caller assigns it to matrix_mask / matrix_A / matrix_B."""
         if self.use_metric != 'loss':
-            raise NotImplementedError("use_metric='auc' runs sklearn on the host in the reference (cdc.py:116-119)")
+            return self._probe_per_domain(batches)                # 'auc': scikit-learn on the host per domain, as upstream
         n_seg = len(batches)
         dev = batches[0][0].device
         out = torch.empty(n_seg, dtype=torch.float32, device=dev)
@@ -155,6 +159,20 @@ class CDC(BaseModel):
         finally:
             self.train(was_training)
         return out
+
+    def _probe_per_domain(self, batches):
+        """run.py:550-558 as written: one evaluation per domain with `domain_i=d`, each followed by get_matrix_metric."""
+        was_training = self.training
+        self.eval()
+        try:
+            row = []
+            with torch.no_grad():
+                for d, (x, y) in enumerate(batches):
+                    pred = self.forward(x, mode='split', domain_i=d)
+                    row.append(float(self.get_matrix_metric(pred.reshape(-1), y.reshape(-1).float())))
+        finally:
+            self.train(was_training)
+        return torch.tensor(row, dtype=torch.float32, device=batches[0][0].device)
 
     def _probe_chunk(self, batches, out):
         rt = self.base_model_instance._rt

@@ -80,3 +80,23 @@ def test_probe_all_domains_host_logic(base, sizes, emulator):
 @pytest.mark.parametrize("base", sorted(BASES))
 def test_probe_all_domains_gpu(base, sizes):
     _run(base, "cuda", sizes)
+
+
+def test_probe_with_auc_metric_runs_per_domain_on_the_host(emulator):
+    """use_metric='auc' (cdc.py:116-119): scikit-learn per domain on the host, as upstream - no batched device reduction"""
+    from sklearn.metrics import roc_auc_score
+    m = cm.CDC(FIELD_DIMS, E, 3, 4, "ple", ((16, 8), (8,)), (8, 4), DOMAIN_IDX, use_metric="auc", dropout=0.0, config=Cfg(), **L2)
+    m.set_groups([0, 1, 2, 1])
+    rng = np.random.default_rng(0)
+    batches = []
+    for d in range(4):
+        x = np.stack([rng.integers(0, c, size=30) for c in FIELD_DIMS], axis=1).astype(np.int32)
+        x[:, DOMAIN_IDX] = d
+        batches.append((torch.from_numpy(x), torch.from_numpy((rng.random(30) < 0.4).astype(np.int16))))
+    m.train()
+    row = m.probe_all_domains(batches).numpy()
+    assert m.training
+    m.eval()
+    with torch.no_grad():
+        want = [roc_auc_score(y.numpy(), m(x, mode="split", domain_i=d).numpy().reshape(-1)) for d, (x, y) in enumerate(batches)]
+    assert np.allclose(row, want, atol=1e-6)
