@@ -8,7 +8,8 @@ One JSON line on stdout (rank 0).  Workload = BASELINE.json configs[3] ("C4"): C
 GPU, steady-state step `model(X, mode='split', domain_i=d)` + BCE + L2 + Adam (reference run.py:635-640).
 `value` times K steps with inputs resident in HBM; `e2e` times the same step through the public API from pinned HOST
 buffers (H2D of the batch and D2H of the loss inside the timed region, one synchronisation per step like the reference's
-loss.item()).  `--impl reference` times the CPU restatement of the reference path (oracle/, numpy) on the host cores.
+loss.item()).  `--impl reference` times the reference's OWN torch modules (oracle/_ref, installed verbatim by oracle/make_ref.py) on the host
+cores at the same batch size; the numpy oracle port is reported beside it (and is the fallback when oracle/_ref is absent).
 """
 from __future__ import annotations
 
@@ -186,19 +187,89 @@ def init_state_numpy(fd, rng):
     return sd
 
 
+def run_cpu_reference(steps, warmup, B, budget_s=None):
+    """The UNMODIFIED reference (its own torch modules, installed verbatim into oracle/_ref/ by oracle/make_ref.py) through its own
+    public API on the host cores: CDC(base='ple') with the nested expert dims, loop body exactly run.py:635-640
+    (`model(X, mode='split', domain_i=d)`, BCELoss + get_regularization_loss, zero_grad / backward / torch.optim.Adam.step,
+    loss.item()), fp32, dropout 0.2, all host threads.  Batches are pre-collated tensors (DataLoader excluded, as SURVEY §8d).
+    budget_s: stop timing after this many seconds of timed steps (at least one) - the bounded sample of the cpu_baseline leg.
+    Returns (samples/s, seconds per step, timed steps, threads)."""
+    import tempfile
+    import torch
+    from oracle import make_ref
+    ref = make_ref.load_reference()
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+
+    class RefCfg:
+        use_atten = False; use_dcn = False; dataset_name = "synthetic"
+        ple_n_expert_specific = NS; ple_n_expert_shared = NSH; mmoe_n_expert = 8
+        p_weight = 0.1; p_weight_method = "linear_decay"; p_weight_exp_decay = 0.9; old_matrix_weight = 0.0
+        affinity_func = "minus"
+    fd = field_dims()
+    torch.manual_seed(SEED)
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)                                    # CDC.__init__ creates result/<dataset>/ (model/cdc.py:60-62)
+        try:
+            model = ref["CDC"](fd, E, T, N_DOMAIN, "ple", EXPERT_DIMS, TOWER_DIMS, DOMAIN_IDX,
+                               domain_cnt_weight=[1.0 / N_DOMAIN] * N_DOMAIN, dropout=DROPOUT, config=RefCfg(), **L2)
+        finally:
+            os.chdir(cwd)
+    d2g = [d % T for d in range(N_DOMAIN)]
+    model.domain2group_list = d2g
+    model.domain2group = torch.tensor(d2g, dtype=torch.int64)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=ADAM["lr"], betas=ADAM["betas"], eps=ADAM["eps"], weight_decay=ADAM["weight_decay"])
+    crit = torch.nn.BCELoss()
+    batches = [(torch.from_numpy(x), torch.from_numpy(y), d) for x, y, d in make_batches(max(1, min(4, steps + warmup)), B, SEED + 1)]
+    t_steps = []
+    for i in range(warmup + steps):
+        x, y, d = batches[i % len(batches)]
+        t0 = time.perf_counter()
+        pred = model(x, mode="split", domain_i=d)
+        loss = crit(pred, y.float())
+        loss = loss + model.get_regularization_loss(device="cpu")
+        model.zero_grad()
+        loss.backward()
+        opt.step()
+        loss.item()
+        if i >= warmup:
+            t_steps.append(time.perf_counter() - t0)
+            if budget_s is not None and sum(t_steps) >= budget_s:
+                break
+    sec = float(np.sum(t_steps))
+    return B * len(t_steps) / sec, sec / len(t_steps), len(t_steps), threads
+
+
 def reference_arm(args):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores, same config (batch included)
+    as the GPU arm.  Falls back to the numpy port only when oracle/_ref is absent (kind says which)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    B_sample = args.cpu_batch
-    v, sec = run_cpu_port(args.steps, args.warmup, B_sample)
-    cores = os.cpu_count()
+    os.environ.pop("OMP_NUM_THREADS", None)               # torchrun pins it to 1; too late for this process' OpenMP pool, hence set_num_threads below
+    from oracle import make_ref
+    B = args.batch
+    if make_ref.available():
+        # a 65 536-row reference step takes 5-15 s of host time: one warm-up step is enough for a CPU loop, and the timed steps stop
+        # early once they have used args.ref_budget seconds (the line then reports the steps actually timed)
+        warm = min(args.warmup, 1)
+        v, sec, done, cores = run_cpu_reference(args.steps, warm, B, budget_s=args.ref_budget)
+        kind = "reference"
+        sample = (f"{done} of {args.steps} requested steps (after {warm} warm-up; time budget {args.ref_budget:.0f} s) of batch {B}: the "
+                  f"reference's own torch modules (oracle/_ref, unmodified) on {cores} threads, fp32, dropout {DROPOUT}, loop body run.py:635-640")
+        args.steps, args.warmup = done, warm
+    else:
+        B = args.cpu_batch
+        v, sec = run_cpu_port(args.steps, args.warmup, B)
+        kind, cores = "port", os.cpu_count()
+        sample = f"{args.steps} steps of batch {B} of the same workload (numpy oracle port, dropout {DROPOUT}); oracle/_ref absent"
     line = {"impl": "reference", "metric": "train samples/sec (fwd+bwd+opt) CDC-PLE", "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args, B_sample),
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} steps of batch {B_sample} of the same workload (numpy oracle port, dropout {DROPOUT})"},
+            "config": workload_config(args, B),
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -347,10 +418,20 @@ def ours_arm(args):
     value = B * world * args.steps / (ms * 1e-3)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        v, sec = run_cpu_port(2, 1, args.cpu_batch)
-        cpu = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
-               "sample": f"2 steps (after 1 warm-up) of batch {args.cpu_batch} of the same workload, numpy oracle port, "
-                         f"dropout {DROPOUT}; {sec * 1e3:.0f} ms/step"}
+        from oracle import make_ref
+        if make_ref.available():
+            # bounded sample: one warm-up + up to 3 timed steps (about 10-30 s) of the SAME batch size on the reference's own modules
+            v, sec, done, cores = run_cpu_reference(3, 1, B, budget_s=20.0)
+            cpu = {"value": v, "unit": "samples/s", "cores": cores, "kind": "reference",
+                   "sample": f"{done} steps (after 1 warm-up) of batch {B} of the same workload on the reference's own torch modules "
+                             f"(oracle/_ref, unmodified), fp32, dropout {DROPOUT}; {sec * 1e3:.0f} ms/step"}
+            pv, psec = run_cpu_port(1, 1, args.cpu_batch)
+            cpu["port"] = {"value": pv, "unit": "samples/s", "sample": f"numpy oracle port, 1 step of batch {args.cpu_batch}"}
+        else:
+            v, sec = run_cpu_port(2, 1, args.cpu_batch)
+            cpu = {"value": v, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
+                   "sample": f"2 steps (after 1 warm-up) of batch {args.cpu_batch} of the same workload, numpy oracle port, "
+                             f"dropout {DROPOUT}; {sec * 1e3:.0f} ms/step (oracle/_ref absent)"}
     flops_step = 3 * fwd_flops_per_sample() * B
     line = {"metric": "train samples/sec (fwd+bwd+opt) CDC-PLE", "value": value, "unit": "samples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -451,6 +532,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cpu-batch", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: stop timing after this many seconds")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

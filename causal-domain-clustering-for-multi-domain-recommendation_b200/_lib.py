@@ -107,6 +107,7 @@ SIGNATURES = {
     "cdcmdr_reduce_scratch_bytes": (SZ, []),
     "cdcmdr_reg_l2_grad": (INT, [P, P, F32, F32, P, INT, I64, P]),
     "cdcmdr_relu_mask_f32": (INT, [P, I64, P, I64, P, I64, I64, I64, F32, P]),
+    "cdcmdr_relu_mask": (INT, [P, I64, INT, P, I64, INT, P, I64, INT, I64, I64, F32, P]),
     "cdcmdr_adam_dense": (INT, [P, P, P, P, P, P, I64, P, P]),
     "cdcmdr_colsum": (INT, [P, I64, INT, I64, I64, P, INT, P, P]),
     "cdcmdr_colsum_scratch_bytes": (SZ, [I64]),

@@ -73,8 +73,14 @@ class CDC(BaseModel):
         if len(d2g) != self.n_domain or min(d2g) < 0 or max(d2g) >= self.n_cluster:
             raise ValueError("domain2group must map every domain to a cluster in [0, n_cluster)")
         self.domain2group_list = d2g
-        self.domain2group = torch.tensor(d2g, dtype=torch.int64, device=self.domain2group.device)
+        self._install_domain2group(d2g)
         self._grouping.domain2group_list = list(d2g)
+
+    def _install_domain2group(self, d2g):
+        """In place: a captured CUDA graph (mode 'gather') addresses this tensor; the generation counter tells GraphedTrainStep
+        that a baked tower column (mode 'col') is stale."""
+        self.domain2group.copy_(torch.tensor(d2g, dtype=torch.int64))
+        self._group_gen = getattr(self, "_group_gen", 0) + 1
 
     def _apply(self, fn, recurse=True):
         out = torch.nn.Module._apply(self, fn)
@@ -273,7 +279,7 @@ class CDC(BaseModel):
         self.matrix_mask = torch.from_numpy(out["mask"]).to(dev)
         self.matrix_causal = torch.from_numpy(out["causal"]).to(dev)
         self.domain2group_list = list(g.domain2group_list)
-        self.domain2group = torch.tensor(self.domain2group_list, dtype=torch.int64, device=dev)
+        self._install_domain2group(self.domain2group_list)
         self.s_group2domain_list = [list(v) for v in g.s_group2domain_list]
         self.t_group2domain_list = [list(v) for v in g.t_group2domain_list]
         return self.domain2group_list

@@ -74,6 +74,8 @@ class Ops:
         self.lib = _lib.load()
         self.device = torch.device(device)
         self._scratch = {}
+        self._retired = []
+        self.graph_pinned = False                        # set once a CUDA graph holds scratch addresses (Runtime.pin_ws)
         self.launches = 0
 
     # ---------------------------------------------------------------- plumbing
@@ -86,6 +88,8 @@ class Ops:
     def scratch(self, name, nbytes) -> torch.Tensor:
         t = self._scratch.get(name)
         if t is None or t.numel() < nbytes:
+            if t is not None and self.graph_pinned:
+                self._retired.append(t)                      # a captured graph may still address the smaller buffer
             t = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
             self._scratch[name] = t
         return t
@@ -116,7 +120,7 @@ class Ops:
 
     def embed_plan(self, x, offsets, B, F, V, E) -> torch.Tensor:
         nbytes = self.lib.embed_plan_bytes(B * F, V, E)
-        plan = self.scratch(f"embed_plan_{B}", nbytes)
+        plan = self.scratch("embed_plan", nbytes)            # one buffer for every batch size (grows to the largest seen)
         self.lib.embed_plan_build(x.data_ptr(), offsets.data_ptr(), B, F, V, E, plan.data_ptr(), plan.numel(), self.stream)
         return plan
 
@@ -328,8 +332,10 @@ class Ops:
                              dlin.ld if dlin is not None else 0, B, T, self.stream)
 
     # ---------------------------------------------------------------- regulariser / optimiser / reductions
-    def reg_l2_sum(self, w, coef, coef_scalar, n, out):
-        sc = self.scratch("reduce", self.lib.reduce_scratch_bytes())
+    def reg_l2_sum(self, w, coef, coef_scalar, n, out, scratch="reduce"):
+        """scratch: name of the partials buffer - a reduction issued on the side stream must not share it with one that may run
+        concurrently on the main stream (the fused step's table and dense regulariser sums)."""
+        sc = self.scratch(scratch, self.lib.reduce_scratch_bytes())
         self.lib.reg_l2_sum(w.data_ptr(), coef.data_ptr() if coef is not None else None, coef_scalar, n, out.data_ptr(),
                             sc.data_ptr(), self.stream)
 
@@ -338,6 +344,10 @@ class Ops:
                              1 if accumulate else 0, n, self.stream)
 
     def relu_mask(self, dA: Mat, A: Mat, out: Mat, rows, cols, scale):
+        if dA.is_bf16 or A.is_bf16 or out.is_bf16:
+            self.lib.relu_mask(dA.ptr, dA.ld, 1 if dA.is_bf16 else 0, A.ptr, A.ld, 1 if A.is_bf16 else 0, out.ptr, out.ld,
+                               1 if out.is_bf16 else 0, rows, cols, scale, self.stream)
+            return
         self.lib.relu_mask_f32(dA.ptr, dA.ld, A.ptr, A.ld, out.ptr, out.ld, rows, cols, scale, self.stream)
 
     def adam_dense(self, w, grad, m, v, l2coef, present, n, st):

@@ -844,6 +844,19 @@ __global__ void relu_mask_kernel(const float* __restrict__ dA, int64_t ldda, con
   }
 }
 
+// mixed-dtype variant (bf16 path on a one-row batch): each operand is fp32 or bf16 by flag
+__global__ void relu_mask_any_kernel(const void* __restrict__ dA, int64_t ldda, int da_bf16, const void* __restrict__ A, int64_t lda, int a_bf16,
+                                     void* __restrict__ out, int64_t ldo, int out_bf16, int64_t rows, int64_t cols, float scale) {
+  const int64_t total = rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r, c; split_idx(i, cols, r, c);
+    const float a = a_bf16 ? bf16_to_f32(((const uint16_t*)A)[r * lda + c]) : ((const float*)A)[r * lda + c];
+    const float d = da_bf16 ? bf16_to_f32(((const uint16_t*)dA)[r * ldda + c]) : ((const float*)dA)[r * ldda + c];
+    const float v = a > 0.f ? d * scale : 0.f;
+    if (out_bf16) ((uint16_t*)out)[r * ldo + c] = f32_to_bf16(v); else ((float*)out)[r * ldo + c] = v;
+  }
+}
+
 __global__ void adam_dense_kernel(float* __restrict__ w, const float* __restrict__ grad, float* __restrict__ m, float* __restrict__ v,
                                   const float* __restrict__ l2coef, const uint8_t* __restrict__ present, int64_t n,
                                   const cdcmdr_step_state_t* __restrict__ st) {
@@ -1335,6 +1348,15 @@ extern "C" int cdcmdr_relu_mask_f32(const float* dA, int64_t ldda, const float* 
                                     int64_t cols, float scale, cdcmdr_stream_t s) {
   if (rows <= 0 || cols <= 0) return 0;
   relu_mask_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(dA, ldda, A, lda_, out, ldo, rows, cols, scale);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_relu_mask(const void* dA, int64_t ldda, int da_bf16, const void* A, int64_t lda_, int a_bf16, void* out, int64_t ldo,
+                                int out_bf16, int64_t rows, int64_t cols, float scale, cdcmdr_stream_t s) {
+  if (rows <= 0 || cols <= 0) return 0;
+  CDC_REQUIRE(dA && A && out, "relu_mask: null operand");
+  relu_mask_any_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(dA, ldda, da_bf16, A, lda_, a_bf16, out, ldo, out_bf16, rows, cols, scale);
   CDC_LAUNCHED();
   return 0;
 }

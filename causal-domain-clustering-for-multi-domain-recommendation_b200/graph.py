@@ -23,16 +23,25 @@ class GraphedTrainStep:
         self.out = None
         self.warmup = warmup
         self.launches_per_step = None
+        self._gen = None
+
+    def _routing_generation(self):
+        """CDC bakes its routing into the recorded step (mode 'col': the tower column of `domain_i` is a kernel argument); every
+        regrouping (CDC.update_group / set_groups, run.py:594 - once per update_interval steps) bumps this counter."""
+        return getattr(self.model, "_group_gen", 0)
 
     def capture(self):
         """Call after x / y hold a valid batch (the warm-up steps are REAL optimizer steps on that batch)."""
-        lib = self.model_base()._rt.ops.lib
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(self.warmup):
-                self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
-        torch.cuda.current_stream().wait_stream(side)
+        rt = self.model_base()._rt
+        lib = rt.ops.lib
+        rt.pin_ws(self.x.shape[0])                      # the graph holds this workspace's addresses: never evicted
+        if self.graph is None:                          # a re-capture (routing changed) must not take extra optimizer steps
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(self.warmup):
+                    self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
+            torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = lib.launch_count()
@@ -40,14 +49,15 @@ class GraphedTrainStep:
             self.out = self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
         self.launches_per_step = int(lib.launch_count() - n0)
         self.optimizer.steps -= 1          # capture records the step but does not execute it
+        self._gen = self._routing_generation()
         return self
 
     def model_base(self):
         return getattr(self.model, "base_model_instance", self.model)
 
     def __call__(self):
-        if self.graph is None:
-            self.capture()
+        if self.graph is None or self._gen != self._routing_generation():
+            self.capture()                 # first use, or CDC regrouped since the capture: the recorded tower column is stale
         self.graph.replay()
         self.optimizer.steps += 1
         return self.out

@@ -535,7 +535,7 @@ class BaseModel(nn.Module):
             m, v = self._table_state
             lazy = self.embedding_update == "sparse_lazy"
             if lazy:
-                rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[1:2])
+                rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[1:2], scratch="reduce_table")
             rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[1:2], lazy=lazy)
 
         if sharded:

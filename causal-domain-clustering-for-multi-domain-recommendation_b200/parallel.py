@@ -186,7 +186,7 @@ class DataParallel:
         m, v = self.moments()
         lazy = self.model.embedding_update == "sparse_lazy"
         if lazy:
-            ops.reg_l2_sum(shard, None, 1.0, shard.numel(), sumsq_out)
+            ops.reg_l2_sum(shard, None, 1.0, shard.numel(), sumsq_out, scratch="reduce_table")
         ops.embed_bwd_adam(Mat(grecv, 0, nf_me * E), plan, N * B, nf_me, E, Vl, shard, m, v, l2, rt.step_state,
                            None if lazy else sumsq_out, lazy=lazy)
 

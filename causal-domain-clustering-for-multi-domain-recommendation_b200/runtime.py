@@ -136,12 +136,38 @@ class Runtime:
     def arm_input_grad(self, on: bool):
         self._dx_armed, self._dx_event = bool(on), None
 
+    # Workspaces are keyed by the exact batch size (a captured CUDA graph holds their addresses), but only the most recently used
+    # ones are kept: the CDC probing loop (run.py:528-594) concatenates 1..7 per-domain batches whose row total changes whenever a
+    # loader yields its short last batch, and every distinct total would otherwise pin a full activation workspace for good.
+    WS_MAX_ENTRIES = 12
+    WS_MAX_BYTES = 32 << 30
+
     def ws(self, B) -> Workspace:
-        w = self._ws.get(B)
+        w = self._ws.pop(B, None)
         if w is None:
             w = Workspace(self.device)
-            self._ws[B] = w
+        self._ws[B] = w                                  # most recently used last
+        self._evict_workspaces(keep=B)
         return w
+
+    def pin_ws(self, B):
+        """A CUDA graph was captured over the workspace of batch size B: it must never be evicted."""
+        self._ws_pinned = getattr(self, "_ws_pinned", set()) | {B}
+        self.ops.graph_pinned = True                     # scratch buffers that grow later keep their old storage alive
+
+    def _evict_workspaces(self, keep):
+        pinned = getattr(self, "_ws_pinned", ())
+        def total():
+            return sum(w.nbytes() for w in self._ws.values())
+        for key in list(self._ws):
+            if len(self._ws) <= self.WS_MAX_ENTRIES and total() <= self.WS_MAX_BYTES:
+                break
+            if key == keep or key in pinned:
+                continue
+            del self._ws[key]                            # back to torch's caching allocator (stream-ordered reuse)
+
+    def ws_bytes(self) -> int:
+        return sum(w.nbytes() for w in self._ws.values())
 
     def next_salt(self) -> int:
         self._salt += 1
@@ -339,20 +365,19 @@ class MlpGroup:
         d_last = self.dims[-1]
         cur = dOut
         if post_act_grad and self.bn and not use_bn and not self.out_layer:
-            if rt.bf16:
-                raise NotImplementedError("bf16 path: batch size 1 skips BatchNorm (layer.py:202-204); train it on the fp32 path")
-            cur = ws.mat(f"{self.tag}.dA{nl - 1}", B, G * d_last)
+            # one-row batch: BatchNorm is skipped (layer.py:202-204), the ReLU / dropout mask is applied here; the result feeds the
+            # GEMMs below, so it is in the activation dtype (bf16 on the tensor-core path)
+            cur = ws.mat(f"{self.tag}.dZ1row", B, G * d_last, rt.act_dtype)
             rt.ops.relu_mask(dOut, self._act(ws, nl - 1, B), cur, B, G * d_last, keep)
         if self.out_layer:
             A_last = self._act(ws, nl - 1, B)
             dA = ws.mat(f"{self.tag}.dA{nl - 1}", B, G * d_last)          # fp32
             rt.ops.rowdot_bwd(A_last, rt.w(self.names["Wout"], self.g0 * d_last), dOut, dA, rt.g(self.names["Wout"], self.g0 * d_last),
                               rt.g(self.names["bout"], self.g0), B, G, d_last)
-            if not use_bn:
-                if rt.bf16:
-                    raise NotImplementedError("bf16 path: batch size 1 skips BatchNorm (layer.py:202-204); train it on the fp32 path")
-                rt.ops.relu_mask(dA, A_last, dA, B, G * d_last, keep)
             cur = dA
+            if not use_bn:                                       # one-row batch (layer.py:202-204): no BatchNorm backward to apply the mask
+                cur = ws.mat(f"{self.tag}.dZ1row", B, G * d_last, rt.act_dtype) if rt.bf16 else dA
+                rt.ops.relu_mask(dA, A_last, cur, B, G * d_last, keep)
         for j in reversed(range(nl)):
             d = self.dims[j]
             prev_d = self.in_dim if j == 0 else self.dims[j - 1]

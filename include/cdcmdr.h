@@ -272,6 +272,10 @@ int cdcmdr_reg_l2_grad(const float* w, const float* coef, float coef_scalar, flo
  * of MultiLayerPerceptron, where BatchNorm is skipped)                               layer.py:202-204 */
 int cdcmdr_relu_mask_f32(const float* dA, int64_t ldda, const float* A, int64_t lda_, float* out, int64_t ldo,
                          int64_t rows, int64_t cols, float scale, cdcmdr_stream_t s);
+/* the same with each operand fp32 (flag 0) or bf16 (flag 1): the tensor-core path on a one-row batch, where
+ * activations are bf16 and the tower gradient fp32                                    layer.py:202-204 */
+int cdcmdr_relu_mask(const void* dA, int64_t ldda, int da_bf16, const void* A, int64_t lda_, int a_bf16, void* out,
+                     int64_t ldo, int out_bf16, int64_t rows, int64_t cols, float scale, cdcmdr_stream_t s);
 
 /* a17  torch.optim.Adam over a flat arena, fused with the L2-regulariser gradient  run.py:720-721
  *   g = grad[i] + 2*l2coef[i]*w[i] + wd*w[i] ; m,v,w update.  present[i]==0 (uint8, may be NULL)

@@ -527,6 +527,12 @@ class HostABI:
         _mat(out, rows, cols, ldo)[...] = np.where(_mat(A, rows, cols, lda) > 0, _mat(dA, rows, cols, ldda) * F32(scale), F32(0))
         return 0
 
+    def relu_mask(self, dA, ldda, da_bf16, A, lda, a_bf16, out, ldo, out_bf16, rows, cols, scale, s):
+        a = _rd(_act_mat(A, rows, cols, lda, a_bf16), a_bf16)
+        d = _rd(_act_mat(dA, rows, cols, ldda, da_bf16), da_bf16)
+        _wr(_act_mat(out, rows, cols, ldo, out_bf16), np.where(a > 0, d * F32(scale), F32(0)).astype(np.float32), out_bf16)
+        return 0
+
     def adam_dense(self, w, grad, m, v, l2coef, present, n, st, s):
         ww, g, mm, vv = (_arr(p, n, np.float32) for p in (w, grad, m, v))
         coef = F32(2) * _arr(l2coef, n, np.float32) if l2coef else F32(0)

@@ -63,7 +63,7 @@ def test_bf16_path_wiring_agrees_with_fp32_path(block, emulator):
         E, F, T = int(rng.choice([8, 16])), int(rng.integers(2, 6)), int(rng.integers(1, 5))
         fd = rng.integers(3, 12, size=F).astype(np.int64)
         fd[1] = max(T, 3)
-        B = int(rng.choice([17, 40, 130]))
+        B = int(rng.choice([1, 17, 40, 130]))
         atten = kind in ("ple", "mmoe", "star") and bool(rng.integers(0, 2))
         x = torch.from_numpy(np.stack([rng.integers(0, d, size=B) for d in fd], axis=1).astype(np.int32))
         y = torch.from_numpy((rng.random((B, 1)) < 0.4).astype(np.int16))

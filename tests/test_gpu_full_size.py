@@ -1,7 +1,8 @@
-"""BASELINE.json configs at their full shapes on the B200, checked through size-independent properties (the CPU oracle does
-not finish in seconds there): bit-repeatability of the whole fused step (every reduction has a fixed order), CUDA-graph replay ==
-eager, bf16 tensor-core path vs fp32 path on identical weights (2e-2 on the logit scale, north_star), row routing == all-rows
-computation + selection (bit-exact order), and the C1 case - which the oracle does finish - against the oracle itself."""
+"""BASELINE.json configs at their full shapes on the B200.  Against the CPU oracle itself (one full-size oracle step takes 5-15 s
+of numpy): C1 (fp32), C2 DCNv2 with CrossNetMix and CrossNetV2, C3 PLE / MMoE and C4 CDC-PLE - fp32 path at 1e-4, bf16 tensor-core
+path at 2e-2 on the logit scale (north_star) - `test_*_matches_oracle`.  And through size-independent properties: bit-repeatability
+of the whole fused step (every reduction has a fixed order), CUDA-graph replay == eager, row routing == all-rows computation +
+selection (bit-exact order)."""
 import numpy as np
 import pytest
 import torch
@@ -183,3 +184,91 @@ def test_c5_star_routing_equals_selection():
         cf = c.base_model_instance(xt).cpu().numpy()
         cs = c(xt, mode="split").cpu().numpy()[:, 0]
     assert np.array_equal(cs, cf[np.arange(B), np.array(c.domain2group_list)[x[:, 10]]])
+
+
+# ------------------------------------------------------------------------------------------------ full shapes against the oracle
+def _sd64(model):
+    return {k: (v.detach().cpu().numpy().astype(np.float64) if v.dtype == torch.float32 else v.detach().cpu().numpy().copy())
+            for k, v in model.state_dict().items()}
+
+
+def _check_step_vs_oracle(build, om, x, y, step_kw, oracle_kw, strip=""):
+    """One fused training step of the fp32 path and of the bf16 path against ONE oracle step (float64 numpy, reference
+    arithmetic) on identical weights and inputs: predictions, BCE, regulariser."""
+    m32 = build("fp32")
+    sd = {k[len(strip):]: v for k, v in _sd64(m32).items()}
+    r = O.train_step(om, sd, O.Adam(), x, y, **oracle_kw)
+    ref_p = np.asarray(r["pred"], dtype=np.float64)
+    lr_ = logit(ref_p)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    for prec, model in (("fp32", m32), ("bf16", None)):
+        if model is None:
+            model = build(prec)
+        model = model.to("cuda").train()
+        opt = cm.Adam(model.parameters(), **ADAM)
+        out = model.train_step(xt, yt, opt, **step_kw(model))
+        loss, bce, reg = model.step_losses(out)
+        p = out["pred"].cpu().numpy().astype(np.float64).reshape(ref_p.shape)
+        if prec == "fp32":
+            assert np.abs(p - ref_p).max() <= 1e-4, (prec, float(np.abs(p - ref_p).max()))
+            assert abs(bce - float(r["bce"])) <= 1e-4 * float(r["bce"]), (prec, bce, float(r["bce"]))
+        else:
+            err = float(np.abs(logit(p) - lr_).max())
+            assert err <= 2e-2 * max(1.0, float(np.abs(lr_).max())), (prec, err, float(np.abs(lr_).max()))
+            assert abs(bce - float(r["bce"])) <= 2e-2 * float(r["bce"]), (prec, bce, float(r["bce"]))
+        assert abs(reg - float(r["reg"])) <= 1e-4 * float(r["reg"]), (prec, reg, float(r["reg"]))
+        del model, opt, out
+        torch.cuda.empty_cache()
+
+
+def test_c4_cdc_ple_full_batch_matches_oracle():
+    """configs[3] at its full shape (30 domains -> 4 clusters, 23 fields x 16, vocab 1M, batch 65536), mode='split' with the
+    per-sample tower gather, dropout 0: fp32 path and bf16 path against the oracle."""
+    F, E, T, nd, B = 23, 16, 4, 30, 65536
+    fd = np.full(F, 45_000, dtype=np.int64); fd[10] = nd
+    x, y, rng = data(fd, B, 14)
+    x[:, 10] = rng.integers(0, nd, size=B)
+    d2g = [d % T for d in range(nd)]
+
+    def build(precision):
+        torch.manual_seed(2000)
+        m = cm.CDC(fd, E, T, nd, "ple", ((256, 128), (64,)), (64, 32), 10, dropout=0.0, config=cfg(precision), **L2)
+        m.set_groups(d2g)
+        return m
+    om = O.PLE(fd, E, T, 2, 2, ((256, 128), (64,)), (64, 32), **L2)
+    _check_step_vs_oracle(build, om, x, y, lambda m: dict(mode="split", domain_i=None),
+                          dict(mode="split_gather", domain2group=np.array(d2g), domain_idx=10), strip="base_model_instance.")
+
+
+@pytest.mark.parametrize("kind", ["ple", "mmoe"])
+def test_c3_eight_experts_full_batch_matches_oracle(kind):
+    """configs[2] at its full shape (8 experts, 3 tasks, batch 65536): fp32 and bf16 paths against the oracle."""
+    F, E, T, B = 23, 16, 3, 65536
+    fd = np.full(F, 45_000, dtype=np.int64); fd[10] = 10
+    x, y, rng = data(fd, B, 13)
+    g = (x[:, 10] % T).astype(np.int64)
+    gt = torch.from_numpy(g).cuda()
+
+    def build(precision):
+        torch.manual_seed(9)
+        if kind == "ple":
+            return cm.PLE(fd, E, T, 2, 2, ((256, 128), (64,)), (64, 32), dropout=0.0, config=cfg(precision), **L2)
+        return cm.MMoE(fd, E, T, 8, (256, 128, 64), (64, 32), dropout=0.0, config=cfg(precision), **L2)
+    om = (O.PLE(fd, E, T, 2, 2, ((256, 128), (64,)), (64, 32), **L2) if kind == "ple"
+          else O.MMoE(fd, E, T, 8, (256, 128, 64), (64, 32), **L2))
+    _check_step_vs_oracle(build, om, x, y, lambda m: dict(mode="gather", sel=gt), dict(mode="gather", group=g))
+
+
+@pytest.mark.parametrize("mix", [True, False])
+def test_c2_dcnv2_full_shape_matches_oracle(mix):
+    """configs[1] at its full shape (26 fields x 32, 3 cross layers, MLP 512-256-128, batch 16384): CrossNetMix (stock) and
+    CrossNetV2 (the north_star formula), fp32 and bf16 paths against the oracle."""
+    F, E, B = 26, 32, 16384
+    fd = np.full(F, 40_000, dtype=np.int64)
+    x, y, rng = data(fd, B, 12)
+
+    def build(precision):
+        torch.manual_seed(7)
+        return cm.DCNv2(fd, E, 3, (512, 256, 128), dropout=0.0, use_low_rank_mixture=mix, config=cfg(precision), **L2)
+    om = O.DCNv2(fd, E, 3, (512, 256, 128), use_low_rank_mixture=mix, **L2)
+    _check_step_vs_oracle(build, om, x, y, lambda m: dict(mode="col", col=0), dict(mode="single"))

@@ -200,12 +200,14 @@ def test_bf16_tensor_core_path_matches_fp32_oracle(kind):
 
 
 def test_bf16_auc_tracks_fp32_after_training():
-    """north_star: bf16 tensor-core runs agree with fp32 to 1e-3 absolute AUC after a fixed number of steps."""
-    def run(precision):
+    """north_star: bf16 tensor-core runs agree with fp32 to 1e-3 absolute AUC after a fixed number of steps (150).  The bar is the
+    stated 1e-3, checked per seed on a 131 072-row evaluation set (a 16 384-row set adds ~2e-3 of sampling noise to the DIFFERENCE
+    of two slightly different rankings, which is what the first round's widened bar had absorbed) and on the mean over seeds."""
+    def run(precision, seed):
         class Cfg:
             use_atten = False; use_dcn = False; cdcmdr_precision = precision
-        torch.manual_seed(5)
-        rng = np.random.default_rng(5)
+        torch.manual_seed(seed)
+        rng = np.random.default_rng(seed)
         F, E, T, B = 16, 16, 4, 16384
         fd = np.full(F, 200, dtype=np.int64)
         m = cm.PLE(fd, E, T, 2, 2, ((128, 64), (32,)), (32, 16), dropout=0.0, config=Cfg(), l2_reg_embedding=1e-7,
@@ -213,20 +215,26 @@ def test_bf16_auc_tracks_fp32_after_training():
         opt = cm.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
         wtrue = rng.standard_normal((F, 200)) * 1.5
 
-        def batch():
-            x = rng.integers(0, 200, size=(B, F)).astype(np.int32)
+        def batch(n=B):
+            x = rng.integers(0, 200, size=(n, F)).astype(np.int32)
             s = wtrue[np.arange(F)[None, :], x].sum(1) / np.sqrt(F) - 1.0
-            y = (rng.random(B) < 1 / (1 + np.exp(-2 * s))).astype(np.int16)
-            g = rng.integers(0, T, size=B).astype(np.int64)
+            y = (rng.random(n) < 1 / (1 + np.exp(-2 * s))).astype(np.int16)
+            g = rng.integers(0, T, size=n).astype(np.int64)
             return x, y, g
         for _ in range(150):
             x, y, g = batch()
             m.train_step(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), opt, mode="gather", sel=torch.from_numpy(g).cuda())
         m.eval()
-        x, y, g = batch()
-        with torch.no_grad():
-            p = m(torch.from_numpy(x).cuda()).cpu().numpy()[np.arange(B), g]
-        return _auc(p, y)
-    a32, a16 = run("fp32"), run("bf16")
-    assert a32 > 0.6, a32                                   # the model learned something
-    assert abs(a32 - a16) <= 1e-3 + 2e-3, (a32, a16)         # 1e-3 target + run-to-run Adam sign-noise margin
+        ps, ys = [], []
+        for _ in range(8):
+            x, y, g = batch()
+            with torch.no_grad():
+                ps.append(m(torch.from_numpy(x).cuda()).cpu().numpy()[np.arange(B), g])
+            ys.append(y)
+        return _auc(np.concatenate(ps), np.concatenate(ys))
+    diffs = []
+    for seed in (5, 6, 7):
+        a32, a16 = run("fp32", seed), run("bf16", seed)
+        assert a32 > 0.6, a32                               # the model learned something
+        diffs.append(a16 - a32)
+    assert max(abs(d) for d in diffs) <= 1e-3, diffs
