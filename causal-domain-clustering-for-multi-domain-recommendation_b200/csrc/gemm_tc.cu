@@ -213,6 +213,7 @@ struct TcParams {
   int32_t a_res;                             // A-resident sweep: see the kernel comment
   int64_t tiles_lo; int32_t tiles_rem;       // a_res: CTA c owns tiles [c*lo + min(c, rem), +lo + (c < rem))
   unsigned long long* prof;                  // diagnostics: cycles spent in each pipeline wait, summed over CTAs (NULL = off)
+  const float* cross_x0; const float* cross_x; float* cross_xw; int64_t ld_cross;   // CrossNetV2 epilogue (see cdcmdr.h)
   int32_t debug;                             // probe only (cdcmdr_gemm_bf16_tc_mode bits 4..6): 16 = epilogue drains nothing, 64 = tcgen05.ld only,
                                              // 32 = everything but the TMA store.  Results are garbage; never set by the product path.
 };
@@ -549,6 +550,52 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           bias_t[lane] = bv;
           __syncwarp();
         }
+        if (p.cross_x0) {
+          // ---------------- CrossNetV2 layer: y = x0 * acc + b + x -> fp32 layer output, bf16 operand of the next layer, fp32 acc ----------------
+          // (layer.py:339-343).  Every stream is read / written by the row's own lane: 128 contiguous bytes per lane per fp32 stream.
+          tc_ld_wait();
+          if (m < p.M) {
+            const float* x0p = p.cross_x0 + m * p.ld_cross + nb;
+            const float* xp = p.cross_x + m * p.ld_cross + nb;
+            float* yp = p.out_aux + m * p.ld_aux + nb;
+            float* wp = p.cross_xw ? p.cross_xw + m * p.ld_cross + nb : nullptr;
+            uint16_t* bp = p.out_main ? p.out_main + m * p.ld_main + nb : nullptr;
+            const bool vec = cw == 32 && ((((uintptr_t)x0p) | ((uintptr_t)xp) | ((uintptr_t)yp) | ((uintptr_t)wp) | ((uintptr_t)bp)) & 15) == 0;
+            if (vec) {
+              float4 a[8], b[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { a[j] = __ldg(reinterpret_cast<const float4*>(x0p) + j); b[j] = __ldg(reinterpret_cast<const float4*>(xp) + j); }
+              uint32_t o[16];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bs = *reinterpret_cast<const float4*>(bias_t + 4 * j);
+                const float4 acc = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                float4 y;
+                y.x = fmaf(a[j].x, acc.x, bs.x) + b[j].x; y.y = fmaf(a[j].y, acc.y, bs.y) + b[j].y;
+                y.z = fmaf(a[j].z, acc.z, bs.z) + b[j].z; y.w = fmaf(a[j].w, acc.w, bs.w) + b[j].w;
+                reinterpret_cast<float4*>(yp)[j] = y;
+                if (wp) reinterpret_cast<float4*>(wp)[j] = acc;
+                o[2 * j] = pack_bf16x2(y.x, y.y); o[2 * j + 1] = pack_bf16x2(y.z, y.w);
+              }
+              if (bp) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(bp)[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                if (j < cw) {
+                  const float acc = __uint_as_float(v[j]);
+                  const float y = fmaf(x0p[j], acc, bias_t[j]) + xp[j];
+                  yp[j] = y;
+                  if (wp) wp[j] = acc;
+                  if (bp) bp[j] = f32_to_bf16(y);
+                }
+              }
+            }
+          }
+          continue;
+        }
         const bool full_main = nb + 32 <= p.n_main && cw == 32;
         // a chunk cut short by the END OF THE MATRIX may still go through TMA: the store map clips columns >= N
         const bool clip_ok = p.G == 1 && p.n_main == p.N && !p.mask && !p.accumulate && nb + cw == p.N;
@@ -835,6 +882,12 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   q.out_aux = p->out_aux; q.ld_aux = p->ld_aux; q.aux_gn = p->aux_gn; q.aux_split_stride = p->aux_split_stride;
   q.act = p->act; q.mask = p->mask; q.ld_mask = p->ld_mask; q.mask_gn = p->mask_gn; q.mask_scale = p->mask_scale;
   q.drop_p = p->drop_p; q.seed_dev = p->seed_dev; q.salt = p->salt; q.accumulate = p->accumulate;
+  q.cross_x0 = p->cross_x0; q.cross_x = p->cross_x; q.cross_xw = p->cross_xw; q.ld_cross = p->ld_cross;
+  if (p->cross_x0) {
+    CDC_REQUIRE(p->cross_x && p->out_aux && p->bias && p->G == 1 && split == 1 && !p->mask && p->drop_p <= 0.f && !p->accumulate && p->act == 0,
+                "cross epilogue: needs x, a fp32 output and a bias; no groups / split-K / mask / dropout / accumulate / activation");
+    q.n_main = 0;                                                   // both outputs cover every column; the generic main / aux split is unused
+  }
   CDC_REQUIRE(split == 1 || q.split_k == 1 || p->aux_split_stride > 0, "split-K needs aux_split_stride");
   if (q.split_k != split && split > 1) {
     // the caller sized its partial buffer for `split` slices; unused slices must read as zero
@@ -854,7 +907,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   if (int rc = make_map(&ma, p->A, p->a_rows, p->a_cols, p->lda, q.a_mn_major ? 64u : (uint32_t)TC_BLOCK_M)) return rc;
   if (int rc = make_map(&mb, p->Bt, p->b_rows, p->b_cols, p->ldb, q.b_mn_major ? 64u : (uint32_t)b_cols)) return rc;
   // bf16 output through TMA stores when its layout allows a tensor map (16-byte aligned base / pitch / group offsets)
-  q.tma_store = (p->n_main > 0 && ((uintptr_t)p->out_main % 16) == 0 && p->ld_main % 8 == 0 && p->main_gn % 8 == 0 &&
+  q.tma_store = (!p->cross_x0 && p->n_main > 0 && ((uintptr_t)p->out_main % 16) == 0 && p->ld_main % 8 == 0 && p->main_gn % 8 == 0 &&
                  (p->G - 1) * p->main_gn + p->n_main <= p->ld_main && p->M < (int64_t)1 << 31) ? 1 : 0;
   if (q.tma_store) {
     if (int rc = make_map(&mc, p->out_main, p->M, (p->G - 1) * p->main_gn + p->n_main, p->ld_main, 32u, false, true)) return rc;
@@ -863,7 +916,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   }
   CUtensorMap md = ma, mm = ma;
   const int64_t n_aux = p->N - p->n_main;
-  q.tma_aux = (n_aux > 0 && q.split_k == 1 && ((uintptr_t)p->out_aux % 16) == 0 && p->ld_aux % 4 == 0 && p->aux_gn % 4 == 0 &&
+  q.tma_aux = (!p->cross_x0 && n_aux > 0 && q.split_k == 1 && ((uintptr_t)p->out_aux % 16) == 0 && p->ld_aux % 4 == 0 && p->aux_gn % 4 == 0 &&
                p->n_main % 16 == 0 && (p->G - 1) * p->aux_gn + n_aux <= p->ld_aux && p->M < (int64_t)1 << 31) ? 1 : 0;
   if (q.tma_aux) {
     if (int rc = make_map(&md, p->out_aux, p->M, (p->G - 1) * p->aux_gn + n_aux, p->ld_aux, 32u, true, true)) return rc;

@@ -134,6 +134,12 @@ typedef struct {
   int32_t accumulate;
   int32_t split_k; int64_t aux_split_stride;
   int32_t block_n;
+  /* a11 CrossNetV2 layer fused into the epilogue (layer.py:339-343: x_{l+1} = x0 * (x_l W^T) + b + x_l), cross_x0 != NULL:
+   *   acc = A Bt^T (this GEMM, A = bf16 x_l, Bt = bf16 W_l) ; y = cross_x0[m, n] * acc + bias[n] + cross_x[m, n]
+   *   out_aux[m*ld_aux + n] = y (fp32, the layer output) ; out_main[m*ld_main + n] = bf16(y) (next layer's GEMM operand, may be NULL)
+   *   cross_xw[m*ld_cross + n] = acc (fp32, kept for the backward; may be NULL).
+   * Requires G == 1, bias, no mask / dropout / accumulate / split-K; n_main is ignored (both outputs cover all N columns). */
+  const float* cross_x0; const float* cross_x; float* cross_xw; int64_t ld_cross;
 } cdcmdr_gemm_bf16_t;
 int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t s);
 int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want);
