@@ -262,7 +262,9 @@ class Ops:
             tiles = ((M + 127) // 128) * ((N + 255) // 256) * G
             num_kb = (K + 63) // 64
             best, want = None, 1
-            for cand in range(1, min(48, num_kb) + 1):
+            # reductions over the B*F token rows of the attention block (>= 2^18 rows) feed one or two output tiles: up to one
+            # slice per SM there, 48 otherwise
+            for cand in range(1, min(148 if num_kb >= 4096 else 48, num_kb) + 1):
                 per = (num_kb + cand - 1) // cand
                 cost = ((tiles * cand + 147) // 148) * (per + 2)          # + epilogue / pipeline fill per work item
                 if best is None or cost < best:

@@ -193,6 +193,174 @@ __global__ void attn_pool_bwd_finalize_kernel(const double* __restrict__ partial
   dw[j] = (float)s;
 }
 
+// ------------------------------------------------------------------------------------------ bf16 token path
+// The tensor-core path keeps the whole block's token matrices in bf16 (the projections run on the tcgen05 GEMM): the core reads
+// bf16 q / k / v, keeps its arithmetic in fp32, writes bf16, and stores NO probabilities - the backward recomputes the L x L
+// softmax from q and k (34 kFLOP per (sample, head), against a 4*L*L-byte round trip through HBM per layer).
+__device__ __forceinline__ void attn_stage_bf16(const uint16_t* __restrict__ base, int64_t ld, int col0, float* __restrict__ dst, int L, int dh,
+                                                int ds, int lane) {
+  const int hp = dh >> 1;                                      // bf16 pairs per row (dh is even on this path)
+  for (int e = lane; e < L * hp; e += 32) {
+    const int l = e / hp, d2 = e - l * hp;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(base + (int64_t)l * ld + col0 + 2 * d2);
+    dst[l * ds + 2 * d2] = __uint_as_float(w << 16);
+    dst[l * ds + 2 * d2 + 1] = __uint_as_float(w & 0xFFFF0000u);
+  }
+}
+
+// softmax row i of the (sample, head) pair `pr` from staged Q / K: returns this lane's probability p(i, lane) (0 for lane >= L)
+__device__ __forceinline__ float attn_prob_row(const float* __restrict__ Q, const float* __restrict__ K, int i, int L, int dh, int ds, float scale,
+                                               int lane) {
+  float s = -INFINITY;
+  if (lane < L) {
+    float acc = 0.f;
+    for (int d = 0; d < dh; ++d) acc = fmaf(Q[i * ds + d], K[lane * ds + d], acc);
+    s = acc * scale;
+  }
+  const float mx = warp_max(s);
+  const float ex = lane < L ? expf(s - mx) : 0.f;
+  const float sum = warp_sum(ex);
+  return lane < L ? ex / sum : 0.f;
+}
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_fwd_bf16_kernel(const uint16_t* __restrict__ qkv, int64_t ld, uint16_t* __restrict__ out, int64_t ldo, int64_t B, int L, int H, int dh,
+                     float scale, float drop_p, const uint64_t* __restrict__ seed_dev, uint32_t salt) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ds = dh + 1, A = H * dh;
+  float* Q = smem + (size_t)warp * (3 * L * ds + L * L);
+  float* K = Q + L * ds;
+  float* V = K + L * ds;
+  float* P = V + L * ds;
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u, thr = drop_thr16(drop_p);
+  const int64_t pairs = B * H;
+  for (int64_t pr = (int64_t)blockIdx.x * kAttnWarps + warp; pr < pairs; pr += (int64_t)gridDim.x * kAttnWarps) {
+    const int64_t b = pr / H;
+    const int h = (int)(pr - b * H);
+    const uint16_t* base = qkv + b * L * ld;
+    attn_stage_bf16(base, ld, h * dh, Q, L, dh, ds, lane);
+    attn_stage_bf16(base, ld, A + h * dh, K, L, dh, ds, lane);
+    attn_stage_bf16(base, ld, 2 * A + h * dh, V, L, dh, ds, lane);
+    __syncwarp();
+    for (int i = 0; i < L; ++i) {
+      const float p = attn_prob_row(Q, K, i, L, dh, ds, scale, lane);
+      if (lane < L) P[i * L + lane] = p * attn_keep_scale(drop_p, s0, thr, (uint32_t)(pr * L + i), (uint32_t)lane);
+    }
+    __syncwarp();
+    uint16_t* obase = out + b * L * ldo + h * dh;
+    for (int d = lane; d < dh; d += 32) {
+      for (int i = 0; i < L; ++i) {
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) acc = fmaf(P[i * L + j], V[j * ds + d], acc);
+        obase[(int64_t)i * ldo + d] = f32_to_bf16(acc);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(kAttnWarps * 32)
+attn_bwd_bf16_kernel(const uint16_t* __restrict__ qkv, int64_t ld, const uint16_t* __restrict__ dout, int64_t lddo, uint16_t* __restrict__ dqkv,
+                     int64_t lddq, int64_t B, int L, int H, int dh, float scale, float drop_p, const uint64_t* __restrict__ seed_dev,
+                     uint32_t salt) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ds = dh + 1, A = H * dh;
+  float* Q = smem + (size_t)warp * (4 * L * ds + 2 * L * L);
+  float* K = Q + L * ds;
+  float* V = K + L * ds;
+  float* dO = V + L * ds;
+  float* Pd = dO + L * ds;
+  float* dS = Pd + L * L;
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u, thr = drop_thr16(drop_p);
+  const int64_t pairs = B * H;
+  for (int64_t pr = (int64_t)blockIdx.x * kAttnWarps + warp; pr < pairs; pr += (int64_t)gridDim.x * kAttnWarps) {
+    const int64_t b = pr / H;
+    const int h = (int)(pr - b * H);
+    const uint16_t* base = qkv + b * L * ld;
+    attn_stage_bf16(base, ld, h * dh, Q, L, dh, ds, lane);
+    attn_stage_bf16(base, ld, A + h * dh, K, L, dh, ds, lane);
+    attn_stage_bf16(base, ld, 2 * A + h * dh, V, L, dh, ds, lane);
+    attn_stage_bf16(dout + b * L * lddo, lddo, h * dh, dO, L, dh, ds, lane);
+    __syncwarp();
+    for (int i = 0; i < L; ++i) {
+      const float p = attn_prob_row(Q, K, i, L, dh, ds, scale, lane);     // recomputed, not stored by the forward
+      float dp = 0.f, ks = 1.f;
+      if (lane < L) {
+        ks = attn_keep_scale(drop_p, s0, thr, (uint32_t)(pr * L + i), (uint32_t)lane);
+        float acc = 0.f;
+        for (int d = 0; d < dh; ++d) acc = fmaf(dO[i * ds + d], V[lane * ds + d], acc);
+        dp = acc * ks;
+      }
+      const float dot = warp_sum(p * dp);
+      if (lane < L) {
+        Pd[i * L + lane] = p * ks;
+        dS[i * L + lane] = p * (dp - dot) * scale;
+      }
+    }
+    __syncwarp();
+    uint16_t* dbase = dqkv + b * L * lddq + h * dh;
+    for (int d = lane; d < dh; d += 32) {
+      for (int i = 0; i < L; ++i) {
+        float acc = 0.f;
+        for (int j = 0; j < L; ++j) acc = fmaf(dS[i * L + j], K[j * ds + d], acc);
+        dbase[(int64_t)i * lddq + d] = f32_to_bf16(acc);
+      }
+      for (int j = 0; j < L; ++j) {
+        float ak = 0.f, av = 0.f;
+        for (int i = 0; i < L; ++i) {
+          ak = fmaf(dS[i * L + j], Q[i * ds + d], ak);
+          av = fmaf(Pd[i * L + j], dO[i * ds + d], av);
+        }
+        dbase[(int64_t)j * lddq + A + d] = f32_to_bf16(ak);
+        dbase[(int64_t)j * lddq + 2 * A + d] = f32_to_bf16(av);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// head on bf16 tokens: one warp per sample, 8 bf16 per 128-bit load
+__global__ void __launch_bounds__(256)
+attn_pool_fwd_bf16_kernel(const uint16_t* __restrict__ z, const float* __restrict__ w, float* __restrict__ lin, int64_t ld_lin, int accumulate,
+                          int64_t B, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= B) return;
+  const uint16_t* zr = z + row * n;
+  float acc = 0.f;
+  for (int64_t j = lane; j < n; j += 32) acc = fmaf(fmaxf(bf16_to_f32(zr[j]), 0.f), w[j], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) lin[row * ld_lin] = accumulate ? lin[row * ld_lin] + acc : acc;
+}
+
+__global__ void __launch_bounds__(32 * kPoolRowsPerBlock)
+attn_pool_bwd_bf16_kernel(const uint16_t* __restrict__ z, const float* __restrict__ w, const float* __restrict__ dlin, int64_t ld_dlin,
+                          uint16_t* __restrict__ dz, double* __restrict__ partial, int64_t B, int64_t n, int64_t rows_per_chunk) {
+  __shared__ double red[kPoolRowsPerBlock][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = (r0 + rows_per_chunk < B) ? r0 + rows_per_chunk : B;
+  double acc = 0.0;
+  if (j < n) {
+    const float wj = w[j];
+    for (int64_t r = r0 + ty; r < r1; r += kPoolRowsPerBlock) {
+      const float zv = bf16_to_f32(z[r * n + j]), g = dlin[r * ld_dlin];
+      dz[r * n + j] = f32_to_bf16(zv > 0.f ? g * wj : 0.f);
+      acc += (double)(g * fmaxf(zv, 0.f));
+    }
+  }
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < n) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kPoolRowsPerBlock; ++k) s += red[k][tx];
+    partial[(int64_t)blockIdx.y * n + j] = s;
+  }
+}
+
 static inline int pool_chunks(int64_t B) {
   const int64_t c = ceil_div(B, 64);
   return (int)(c < 1 ? 1 : (c > 256 ? 256 : c));
@@ -267,6 +435,69 @@ extern "C" int cdcmdr_attn_pool_bwd(const float* z, const float* w, const float*
   const int chunks = pool_chunks(B);
   const int64_t rows_per_chunk = ceil_div(B, chunks);
   attn_pool_bwd_kernel<<<dim3((unsigned)ceil_div(n, 32), (unsigned)chunks), 32 * kPoolRowsPerBlock, 0, to_stream(s)>>>(
+      z, w, dlin, ld_dlin, dz, (double*)scratch, B, n, rows_per_chunk);
+  CDC_LAUNCHED();
+  attn_pool_bwd_finalize_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, to_stream(s)>>>((const double*)scratch, chunks, n, dw);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ bf16 token path entry points
+extern "C" int cdcmdr_attn_fwd_bf16(const uint16_t* qkv, int64_t ld, uint16_t* out, int64_t ldo, int64_t B, int L, int H, int dh, float scale,
+                                    float drop_p, const uint64_t* seed_dev, uint32_t salt, cdcmdr_stream_t s) {
+  CDC_REQUIRE(L >= 1 && L <= 32, "attention runs over at most 32 field tokens");
+  CDC_REQUIRE(H >= 1 && dh >= 2 && dh <= 256 && dh % 2 == 0, "bf16 attention needs an even head width");
+  CDC_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed_dev), "bad attention dropout");
+  if (B <= 0) return 0;
+  CDC_REQUIRE(qkv && out && ld >= 3 * (int64_t)H * dh && ldo >= (int64_t)H * dh && ld % 2 == 0 && ((uintptr_t)qkv & 3) == 0,
+              "bad attention operands");
+  const size_t smem = (size_t)kAttnWarps * (3 * (size_t)L * (dh + 1) + (size_t)L * L) * sizeof(float);
+  CDC_REQUIRE(smem <= 200 * 1024, "attention tile does not fit shared memory");
+  CDC_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_fwd_bf16_kernel<<<attn_grid(B * H), kAttnWarps * 32, smem, to_stream(s)>>>(qkv, ld, out, ldo, B, L, H, dh, scale, drop_p, seed_dev, salt);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_attn_bwd_bf16(const uint16_t* qkv, int64_t ld, const uint16_t* dout, int64_t lddo, uint16_t* dqkv, int64_t lddq, int64_t B,
+                                    int L, int H, int dh, float scale, float drop_p, const uint64_t* seed_dev, uint32_t salt,
+                                    cdcmdr_stream_t s) {
+  CDC_REQUIRE(L >= 1 && L <= 32, "attention runs over at most 32 field tokens");
+  CDC_REQUIRE(H >= 1 && dh >= 2 && dh <= 256 && dh % 2 == 0, "bf16 attention needs an even head width");
+  CDC_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (drop_p == 0.f || seed_dev), "bad attention dropout");
+  if (B <= 0) return 0;
+  CDC_REQUIRE(qkv && dout && dqkv && ld >= 3 * (int64_t)H * dh && lddq >= 3 * (int64_t)H * dh && lddo >= (int64_t)H * dh && ld % 2 == 0 &&
+              lddo % 2 == 0 && ((uintptr_t)qkv & 3) == 0 && ((uintptr_t)dout & 3) == 0, "bad attention operands");
+  const size_t smem = (size_t)kAttnWarps * (4 * (size_t)L * (dh + 1) + 2 * (size_t)L * L) * sizeof(float);
+  CDC_REQUIRE(smem <= 200 * 1024, "attention tile does not fit shared memory");
+  CDC_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_bwd_bf16_kernel<<<attn_grid(B * H), kAttnWarps * 32, smem, to_stream(s)>>>(qkv, ld, dout, lddo, dqkv, lddq, B, L, H, dh, scale, drop_p,
+                                                                                 seed_dev, salt);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_attn_pool_fwd_bf16(const uint16_t* z, const float* w, float* lin, int64_t ld_lin, int accumulate, int64_t B, int64_t n,
+                                         cdcmdr_stream_t s) {
+  if (B <= 0) return 0;
+  CDC_REQUIRE(z && w && lin && n >= 1 && ld_lin >= 1, "bad attention head operands");
+  attn_pool_fwd_bf16_kernel<<<(unsigned)ceil_div(B, 8), 256, 0, to_stream(s)>>>(z, w, lin, ld_lin, accumulate, B, n);
+  CDC_LAUNCHED();
+  return 0;
+}
+
+extern "C" int cdcmdr_attn_pool_bwd_bf16(const uint16_t* z, const float* w, const float* dlin, int64_t ld_dlin, uint16_t* dz, float* dw,
+                                         int64_t B, int64_t n, void* scratch, cdcmdr_stream_t s) {
+  CDC_REQUIRE(n >= 1, "bad attention head width");
+  CDC_REQUIRE(dw && scratch, "bad attention head operands");
+  if (B <= 0) {
+    CDC_CHECK(cudaMemsetAsync(dw, 0, (size_t)n * sizeof(float), to_stream(s)));
+    return 0;
+  }
+  CDC_REQUIRE(z && w && dlin && dz && ld_dlin >= 1, "bad attention head operands");
+  const int chunks = pool_chunks(B);
+  const int64_t rows_per_chunk = ceil_div(B, chunks);
+  attn_pool_bwd_bf16_kernel<<<dim3((unsigned)ceil_div(n, 32), (unsigned)chunks), 32 * kPoolRowsPerBlock, 0, to_stream(s)>>>(
       z, w, dlin, ld_dlin, dz, (double*)scratch, B, n, rows_per_chunk);
   CDC_LAUNCHED();
   attn_pool_bwd_finalize_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, to_stream(s)>>>((const double*)scratch, chunks, n, dw);

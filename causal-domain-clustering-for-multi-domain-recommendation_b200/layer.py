@@ -326,13 +326,13 @@ class BaseModel(nn.Module):
         X = self._x_mat(ws, B)
         if rt.dp is not None and rt.dp.shard:
             rt.dp.embed_forward(ws, x, B, X, plan_ahead)   # row-sharded table: indices to the owners, rows back (parallel.py)
-            if self._att is not None and rt.bf16:
-                # the rows travel in bf16 on this path: the attention block (fp32 this round) reads them widened back
+            if rt.bf16 and self._att_needs_x32():
+                # the rows travel in bf16 on this path: a block that computes in fp32 reads them widened back
                 rt.ops.cast_bf16_f32(X, ws.mat("X32", B, F * E), B, F * E)
             return X
         if rt.bf16:
-            # the attention block (fp32 this round) reads the embeddings in fp32: the gather writes both copies in one pass
-            x32 = ws.mat("X32", B, F * E) if self._att is not None else None
+            # an attention block that computes in fp32 reads the embeddings in fp32: the gather writes both copies in one pass
+            x32 = ws.mat("X32", B, F * E) if self._att_needs_x32() else None
             rt.ops.embed_gather(x, self.embedding.offsets_dev, table, x32, X, B, F, E, table.shape[0])
         else:
             rt.ops.embed_gather(x, self.embedding.offsets_dev, table, X, None, B, F, E, table.shape[0])
@@ -341,6 +341,16 @@ class BaseModel(nn.Module):
     def _x32(self, ws, X: Mat, B) -> Mat:
         """The fp32 embeddings [B, F*E] (the gathered matrix itself on the fp32 path)."""
         return ws.mat("X32", B, self.field_num * self.embed_dim) if X.is_bf16 else X
+
+    def _att_x(self, ws, X: Mat, B) -> Mat:
+        """What the attention block reads: on the tensor-core path the gathered bf16 embeddings themselves (their [B, F*E] rows are the
+        [B*F, E] token matrix - which is why models with the block do not pad X with a ones column), else the fp32 embeddings."""
+        if X.is_bf16 and self._att.can_bf16 and X.ld == self.field_num * self.embed_dim:
+            return X
+        return self._x32(ws, X, B)
+
+    def _att_needs_x32(self) -> bool:
+        return self._att is not None and not (self._rt.bf16 and self._att.can_bf16 and not getattr(self, "_x_ones_col", False))
 
     def _engine_forward(self, x, train, **kw):
         """Runs the CUDA forward; returns predictions (a workspace view)."""

@@ -68,7 +68,7 @@ class MMoE(BaseModel):
         logits = self._towers.fwd(ws, out, B, train)
         lin = Lg.cols(self._n_gcols - 1)
         if self._att is not None:
-            self._att.fwd(ws, self._x32(ws, X, B), B, lin, train)
+            self._att.fwd(ws, self._att_x(ws, X, B), B, lin, train)
         return logits, lin
 
     def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat):
@@ -94,5 +94,5 @@ class MMoE(BaseModel):
         rt.lin_bwd_w(dLgi, X, D, rt.o("gates.W"), self._n_gcols, B)
         rt.lin_bwd_x(dLgi, D, rt.o("gates.W"), self._n_gcols, dX, B, accumulate=True)
         if self._att is not None:
-            self._att.bwd(ws, self._x32(ws, X, B), B, self._dlin_mat(ws, B), dX, train)
+            self._att.bwd(ws, self._att_x(ws, X, B), B, self._dlin_mat(ws, B), dX, train)
         return dX

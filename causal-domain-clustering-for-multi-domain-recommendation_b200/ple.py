@@ -145,7 +145,7 @@ class PLE(BaseModel):
                             rt.o(f"cgc{l}.gb") == rt.o(self._level_names[l]["b"][0]) + nE * d0)
             if lv.fused_bwd:
                 lv.experts.tail0 = lv.n_gcols
-                if rt.bf16 and rt.dp is None:
+                if rt.bf16 and rt.dp is None and self._att is None:
                     # the gathered embeddings carry a column of ones: layer 0's bias gradient comes out of its weight-gradient GEMM
                     self._x_ones_col = True
                     lv.experts.x_has_ones = True
@@ -223,7 +223,7 @@ class PLE(BaseModel):
         n0 = self._levels[0].n_gcols
         lin = ws.mat("cgc0.logits", B, n0).cols(n0 - 1)
         if self._att is not None:                              # ple.py:65-67: one more `other_out` on every tower logit
-            self._att.fwd(ws, self._x32(ws, X, B), B, lin, train)
+            self._att.fwd(ws, self._att_x(ws, X, B), B, lin, train)
         return logits, lin
 
     def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat):
@@ -268,5 +268,5 @@ class PLE(BaseModel):
                              accumulate=True)
             dcur = dxin
         if self._att is not None:
-            self._att.bwd(ws, self._x32(ws, X, B), B, self._dlin_mat(ws, B), dcur, train)
+            self._att.bwd(ws, self._att_x(ws, X, B), B, self._dlin_mat(ws, B), dcur, train)
         return dcur

@@ -393,6 +393,18 @@ int cdcmdr_attn_pool_fwd(const float* z, const float* w, float* lin, int64_t ld_
 size_t cdcmdr_attn_pool_scratch_bytes(int64_t B, int64_t n);
 int cdcmdr_attn_pool_bwd(const float* z, const float* w, const float* dlin, int64_t ld_dlin, float* dz, float* dw, int64_t B,
                          int64_t n, void* scratch, cdcmdr_stream_t s);
+/* The same four stages on bf16 token matrices (the tensor-core path: the block's projections run on cdcmdr_gemm_bf16_tc, so qkv,
+ * the core's output, dout and dqkv are bf16; arithmetic inside stays fp32).  The forward stores NO probabilities: the backward
+ * recomputes the L x L softmax of every (sample, head) from q and k (same dropout hash).  dh must be even.  w, lin, dlin, dw fp32. */
+int cdcmdr_attn_fwd_bf16(const uint16_t* qkv, int64_t ld, uint16_t* out, int64_t ldo, int64_t B, int L, int H, int dh, float scale,
+                         float drop_p, const uint64_t* seed_dev, uint32_t salt, cdcmdr_stream_t s);
+int cdcmdr_attn_bwd_bf16(const uint16_t* qkv, int64_t ld, const uint16_t* dout, int64_t lddo, uint16_t* dqkv, int64_t lddq,
+                         int64_t B, int L, int H, int dh, float scale, float drop_p, const uint64_t* seed_dev, uint32_t salt,
+                         cdcmdr_stream_t s);
+int cdcmdr_attn_pool_fwd_bf16(const uint16_t* z, const float* w, float* lin, int64_t ld_lin, int accumulate, int64_t B, int64_t n,
+                              cdcmdr_stream_t s);
+int cdcmdr_attn_pool_bwd_bf16(const uint16_t* z, const float* w, const float* dlin, int64_t ld_dlin, uint16_t* dz, float* dw,
+                              int64_t B, int64_t n, void* scratch, cdcmdr_stream_t s);
 
 #ifdef __cplusplus
 }

@@ -795,3 +795,67 @@ class HostABI:
         _mat(dz, B, n, n)[...] = np.where(zz > 0, g[:, None] * ww[None, :], F32(0)).astype(np.float32)
         _arr(dw, n, np.float32)[:n] = (g.astype(np.float64)[:, None] * np.maximum(zz, 0).astype(np.float64)).sum(axis=0).astype(np.float32)
         return 0
+
+    # ---- the same stages on bf16 token matrices (cdcmdr_attn_*_bf16): fp32 arithmetic on bf16-rounded inputs, bf16 outputs, no
+    # stored probabilities (the backward recomputes the softmax)
+    def _attn_views_bf16(self, ptr, ld, B, L, H, dh):
+        A = H * dh
+        m = bf16_to_f32(_mat(ptr, B * L, 3 * A, ld, 1, np.uint16)).reshape(B, L, 3, H, dh)
+        return m[:, :, 0].transpose(0, 2, 1, 3), m[:, :, 1].transpose(0, 2, 1, 3), m[:, :, 2].transpose(0, 2, 1, 3)
+
+    @staticmethod
+    def _attn_softmax(q, k, scale):
+        sc = np.einsum("bhid,bhjd->bhij", q, k).astype(np.float32) * F32(scale)
+        sc = sc - sc.max(axis=-1, keepdims=True)
+        e = np.exp(sc).astype(np.float32)
+        return (e / e.sum(axis=-1, keepdims=True, dtype=np.float32)).astype(np.float32)
+
+    def attn_fwd_bf16(self, qkv, ld, out, ldo, B, L, H, dh, scale, drop_p, seed_dev, salt, s):
+        if drop_p > 0:
+            raise NotImplementedError("the emulator does not reproduce the dropout hash; test with dropout=0")
+        if B <= 0:
+            return 0
+        q, k, v = self._attn_views_bf16(qkv, ld, B, L, H, dh)
+        p = self._attn_softmax(q, k, scale)
+        o = np.einsum("bhij,bhjd->bhid", p, v).astype(np.float32)
+        _mat(out, B * L, H * dh, ldo, 1, np.uint16)[...] = f32_to_bf16(o.transpose(0, 2, 1, 3).reshape(B * L, H * dh)).reshape(B * L, H * dh)
+        return 0
+
+    def attn_bwd_bf16(self, qkv, ld, dout, lddo, dqkv, lddq, B, L, H, dh, scale, drop_p, seed_dev, salt, s):
+        if drop_p > 0:
+            raise NotImplementedError("the emulator does not reproduce the dropout hash; test with dropout=0")
+        if B <= 0:
+            return 0
+        A = H * dh
+        q, k, v = self._attn_views_bf16(qkv, ld, B, L, H, dh)
+        p = self._attn_softmax(q, k, scale)
+        do = bf16_to_f32(_mat(dout, B * L, A, lddo, 1, np.uint16)).reshape(B, L, H, dh).transpose(0, 2, 1, 3)
+        dv = np.einsum("bhij,bhid->bhjd", p, do)
+        dp = np.einsum("bhid,bhjd->bhij", do, v)
+        ds = (p * (dp - (p * dp).sum(axis=-1, keepdims=True)) * F32(scale)).astype(np.float32)
+        dq = np.einsum("bhij,bhjd->bhid", ds, k)
+        dk = np.einsum("bhij,bhid->bhjd", ds, q)
+        g = _mat(dqkv, B * L, 3 * A, lddq, 1, np.uint16)
+        for idx, t in enumerate((dq, dk, dv)):
+            g[:, idx * A:(idx + 1) * A] = f32_to_bf16(t.astype(np.float32).transpose(0, 2, 1, 3).reshape(B * L, A)).reshape(B * L, A)
+        return 0
+
+    def attn_pool_fwd_bf16(self, z, w, lin, ld_lin, accumulate, B, n, s):
+        if B <= 0:
+            return 0
+        zz = bf16_to_f32(_mat(z, B, n, n, 1, np.uint16))
+        v = (np.maximum(zz, 0) @ _arr(w, n, np.float32)[:n]).astype(np.float32)
+        o = _mat(lin, B, 1, ld_lin)
+        o[:, 0] = (o[:, 0] + v) if accumulate else v
+        return 0
+
+    def attn_pool_bwd_bf16(self, z, w, dlin, ld_dlin, dz, dw, B, n, scratch, s):
+        if B <= 0:
+            _arr(dw, n, np.float32)[:n] = 0
+            return 0
+        zz = bf16_to_f32(_mat(z, B, n, n, 1, np.uint16))
+        ww = _arr(w, n, np.float32)[:n]
+        g = _mat(dlin, B, 1, ld_dlin)[:, 0]
+        _mat(dz, B, n, n, 1, np.uint16)[...] = f32_to_bf16(np.where(zz > 0, g[:, None] * ww[None, :], F32(0)).astype(np.float32)).reshape(B, n)
+        _arr(dw, n, np.float32)[:n] = (g.astype(np.float64)[:, None] * np.maximum(zz, 0).astype(np.float64)).sum(axis=0).astype(np.float32)
+        return 0

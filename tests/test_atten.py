@@ -180,3 +180,48 @@ def test_attention_dropout_statistics_gpu():
     frac = kept.sum() / (B * L * H * L)
     assert abs(frac - (1 - p)) < 0.01, frac
     assert np.allclose(pr.cpu().numpy(), 1.0 / L, atol=1e-6)                          # probs are saved before the dropout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,L,H,dh", [(5, 6, 2, 4), (300, 23, 2, 32), (64, 32, 4, 16), (1000, 26, 1, 64), (3, 1, 2, 8), (130, 16, 2, 40)])
+def test_attention_bf16_entry_points_gpu(B, L, H, dh):
+    """cdcmdr_attn_fwd_bf16 / _bwd_bf16 / _pool_fwd_bf16 / _pool_bwd_bf16 (the tensor-core path's token matrices are bf16; the
+    backward recomputes the softmax) against the numpy restatement on identical bf16 inputs: outputs within one bf16 ulp of the
+    tensor scale (fp32 arithmetic inside, summation order differs), head gradient as the fp32 kernels."""
+    from oracle.host_abi import f32_to_bf16, bf16_to_f32
+    lib, emu = cm._lib.load(), HostABI()
+    A = H * dh
+    qkv, dout, z, w, dlin, lin0 = _attn_case(B, L, H, dh, B + L + 1)
+    scale = 1.0 / np.sqrt(dh)
+    b16 = lambda a: f32_to_bf16(a).reshape(a.shape)                                  # noqa: E731
+    qkv16, dout16, z16 = b16(qkv), b16(dout), b16(z)
+    h_out, h_dqkv = np.zeros((B * L, A), np.uint16), np.zeros((B * L, 3 * A), np.uint16)
+    emu.attn_fwd_bf16(qkv16.ctypes.data, 3 * A, h_out.ctypes.data, A, B, L, H, dh, scale, 0.0, None, 0, 0)
+    emu.attn_bwd_bf16(qkv16.ctypes.data, 3 * A, dout16.ctypes.data, A, h_dqkv.ctypes.data, 3 * A, B, L, H, dh, scale, 0.0, None, 0, 0)
+    d = lambda a: torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).cuda()   # noqa: E731
+    g_qkv, g_dout = d(qkv16), d(dout16)
+    g_out = torch.zeros(B * L, A, dtype=torch.int16, device="cuda")
+    g_dqkv = torch.zeros(B * L, 3 * A, dtype=torch.int16, device="cuda")
+    lib.attn_fwd_bf16(g_qkv.data_ptr(), 3 * A, g_out.data_ptr(), A, B, L, H, dh, scale, 0.0, None, 0, 0)
+    lib.attn_bwd_bf16(g_qkv.data_ptr(), 3 * A, g_dout.data_ptr(), A, g_dqkv.data_ptr(), 3 * A, B, L, H, dh, scale, 0.0, None, 0, 0)
+    torch.cuda.synchronize()
+    for got, ref, what in ((g_out, h_out, "out"), (g_dqkv, h_dqkv, "dqkv")):
+        a, b = bf16_to_f32(got.cpu().numpy().view(np.uint16)), bf16_to_f32(ref)
+        sc_ = max(float(np.abs(b).max()), 1e-30)
+        assert float(np.abs(a - b).max()) <= 2 ** -7 * sc_, (what, float(np.abs(a - b).max()), sc_)
+        assert float((np.abs(a - b) > 2 ** -9 * sc_).mean()) < 0.02, what
+    # --- head
+    n = L * A
+    h_lin, h_dz, h_dw = lin0.copy(), np.zeros((B, n), np.uint16), np.zeros(n, np.float32)
+    emu.attn_pool_fwd_bf16(z16.ctypes.data, w.ctypes.data, h_lin.ctypes.data + 4, 3, 1, B, n, 0)
+    emu.attn_pool_bwd_bf16(z16.ctypes.data, w.ctypes.data, dlin.ctypes.data + 8, 3, h_dz.ctypes.data, h_dw.ctypes.data, B, n, None, 0)
+    g_z, g_w, g_lin, g_dlin = d(z16), d(w), d(lin0.copy()), d(dlin)
+    g_dz, g_dw = torch.zeros(B, n, dtype=torch.int16, device="cuda"), torch.zeros(n, device="cuda")
+    sc = torch.empty(lib.attn_pool_scratch_bytes(B, n), dtype=torch.uint8, device="cuda")
+    lib.attn_pool_fwd_bf16(g_z.data_ptr(), g_w.data_ptr(), g_lin.data_ptr() + 4, 3, 1, B, n, 0)
+    lib.attn_pool_bwd_bf16(g_z.data_ptr(), g_w.data_ptr(), g_dlin.data_ptr() + 8, 3, g_dz.data_ptr(), g_dw.data_ptr(), B, n, sc.data_ptr(), 0)
+    torch.cuda.synchronize()
+    ref_scale = max(1.0, float(np.abs(h_lin).max()))
+    assert np.abs(g_lin.cpu().numpy() - h_lin).max() <= 1e-5 * ref_scale * np.sqrt(n)
+    assert np.array_equal(g_dz.cpu().numpy().view(np.uint16), h_dz)
+    assert np.abs(g_dw.cpu().numpy() - h_dw).max() <= 1e-5 * max(1.0, float(np.abs(h_dw).max()))

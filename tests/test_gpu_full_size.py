@@ -272,3 +272,41 @@ def test_c2_dcnv2_full_shape_matches_oracle(mix):
         return cm.DCNv2(fd, E, 3, (512, 256, 128), dropout=0.0, use_low_rank_mixture=mix, config=cfg(precision), **L2)
     om = O.DCNv2(fd, E, 3, (512, 256, 128), use_low_rank_mixture=mix, **L2)
     _check_step_vs_oracle(build, om, x, y, lambda m: dict(mode="col", col=0), dict(mode="single"))
+
+
+def test_c4_stock_attention_block_bf16_matches_fp32_path():
+    """configs[3] with the reference's STOCK attention settings (config.py:24-28: 64-d, 2 heads, 3 layers, V_res) at batch 16384:
+    the bf16 path (token matrices bf16, projections on the tcgen05 GEMM, bf16 attention core) against the fp32 path on identical
+    weights - eval logits 2e-2, first training step's BCE 2e-2 - and the block's parameters train."""
+    F, E, T, nd, B = 23, 16, 4, 30, 16384
+    fd = np.full(F, 45_000, dtype=np.int64); fd[10] = nd
+    x, y, rng = data(fd, B, 15)
+    x[:, 10] = rng.integers(0, nd, size=B)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    att = dict(use_atten=True, atten_embed_dim=64, att_layer_num=3, att_head_num=2, att_res=True)
+    res, sd = {}, None
+    for prec in ("fp32", "bf16"):
+        torch.manual_seed(2000)
+        m = cm.CDC(fd, E, T, nd, "ple", ((256, 128), (64,)), (64, 32), 10, dropout=0.0, config=cfg(prec, **att), **L2)
+        if sd is None:
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+        else:
+            m.load_state_dict(sd, strict=True)
+        m = m.to("cuda")
+        m.set_groups([d % T for d in range(nd)])
+        m.eval()
+        with torch.no_grad():
+            p = m(xt, mode="split").cpu().numpy()
+        m.train()
+        opt = cm.Adam(m.parameters(), **ADAM)
+        w0 = m.base_model_instance.state_dict()["self_attns.1.in_proj_weight"].clone()
+        out = m.train_step(xt, yt, opt, mode="split", domain_i=None)
+        bce = m.step_losses(out)[1]
+        moved = float((m.base_model_instance.state_dict()["self_attns.1.in_proj_weight"] - w0).abs().max())
+        res[prec] = (logit(p), bce, moved)
+        del m, opt, out
+        torch.cuda.empty_cache()
+    l32, l16 = res["fp32"][0], res["bf16"][0]
+    assert np.abs(l16 - l32).max() <= 2e-2 * max(1.0, float(np.abs(l32).max())), float(np.abs(l16 - l32).max())
+    assert abs(res["bf16"][1] - res["fp32"][1]) <= 2e-2 * abs(res["fp32"][1])
+    assert res["fp32"][2] > 1e-4 and res["bf16"][2] > 1e-4

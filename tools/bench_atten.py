@@ -3,8 +3,9 @@
 
     python tools/bench_atten.py [--batch 65536] [--steps 5]
 
-CDC(base=PLE) as in bench.py, bf16 tensor-core path for experts / gates / towers; the attention block computes in fp32 this round
-(projections on the fp32 GEMM).  Times the fused training step with and without the block (CUDA events, 2 warm-ups) and the
+CDC(base=PLE) as in bench.py, bf16 tensor-core path for experts / gates / towers AND the attention block (bf16 token matrices,
+projections / input gradients / weight gradients on the tcgen05 GEMM, bf16-I/O attention core; CDCMDR_PRECISION=fp32 for the
+exact path).  Times the fused training step with and without the block (CUDA events, 2 warm-ups) and the
 block's own forward / backward launches.  Prints one JSON line."""
 import argparse
 import json
@@ -60,7 +61,7 @@ def main():
     x[:, DOM] = 7
     xt = torch.from_numpy(x).to(DEV)
     yt = torch.from_numpy((rng.random(B) < 0.05).astype(np.int16)).to(DEV)
-    out = dict(what="C4 fused step with the stock attention block (fp32 block on the bf16 path)", batch=B)
+    out = dict(what=f"C4 fused step with the stock attention block ({PREC} path)", batch=B)
     for atten in (False, True):
         torch.manual_seed(2000)
         m = cm.CDC(fd, E, T, ND, "ple", ((256, 128), (64,)), (64, 32), DOM, dropout=DROP, config=cfg(atten), l2_reg_embedding=1e-5,
@@ -76,7 +77,7 @@ def main():
             base = m.base_model_instance
             rt, att = base._rt, base._att
             ws = rt.ws(B)
-            X32 = ws.mat("X32", B, F * E) if PREC == "bf16" else ws.mat("X", B, F * E)
+            X32 = base._att_x(ws, base._x_mat(ws, B), B)          # bf16 tokens on the tensor-core path, fp32 embeddings otherwise
             lin = ws.mat("bench.lin", B, 1)
             dX = ws.mat("bench.dX", B, F * E)
             out[key]["block_fwd_ms"] = timed(lambda: att.fwd(ws, X32, B, lin, True), a.steps)
