@@ -80,6 +80,11 @@ class Adam:
             out["exp_avg_sq"] = model._rt.V.clone()
         if model is not None and model._table_state is not None:
             out["table_exp_avg"], out["table_exp_avg_sq"] = (t.clone() for t in model._table_state)
+        dp = getattr(model._rt, "dp", None) if model is not None else None
+        if dp is not None and dp.shard and dp._moments is not None:
+            # row-sharded table: the moments of the embedding rows live with their owner; each rank checkpoints its own row range
+            out["table_shard_rows"] = (dp.row0, dp.row1)
+            out["table_shard_exp_avg"], out["table_shard_exp_avg_sq"] = (t.clone() for t in dp._moments)
         return out
 
     def load_state_dict(self, sd):
@@ -93,4 +98,10 @@ class Adam:
             rt.M.copy_(sd["exp_avg"]); rt.V.copy_(sd["exp_avg_sq"])
         if "table_exp_avg" in sd:
             model._table_state = (sd["table_exp_avg"].to(rt.device).clone(), sd["table_exp_avg_sq"].to(rt.device).clone())
+        if "table_shard_rows" in sd:
+            dp = getattr(rt, "dp", None)
+            if dp is None or not dp.shard or tuple(sd["table_shard_rows"]) != (dp.row0, dp.row1):
+                raise RuntimeError("cdcmdr Adam: the checkpoint holds the embedding moments of row range "
+                                   f"{tuple(sd['table_shard_rows'])}; load it on the rank that owns those rows (same world size)")
+            dp._moments = (sd["table_shard_exp_avg"].to(rt.device).clone(), sd["table_shard_exp_avg_sq"].to(rt.device).clone())
         rt.ops.step_state_set(rt.step_state, self.steps)

@@ -68,6 +68,10 @@ class DataParallel:
         self._moments = None
         model._rt.dp = self
         model._dp = self
+        if self.shard:
+            # Only the owner updates its rows: a checkpoint (run.py:447-459 `torch.save(model.state_dict(), ...)`) must see every
+            # rank's rows.  state_dict() therefore became a COLLECTIVE under the sharded table - every rank has to call it.
+            self._sd_hook = model.register_state_dict_pre_hook(lambda module, prefix, keep_vars: self.gather_table())
 
     def _range_runs(self):
         if getattr(self, "_runs", None) is None:

@@ -195,3 +195,36 @@ def test_ple_launch_shapes_match_oracle(ns, nsh, levels):
                 continue
             tol = 2.1e-3 * (s + 1) if bias_before_bn("ple", k) or k.endswith("running_mean") else 2e-5
             assert np.abs(cur[k] - v).max() <= tol, (s, k, float(np.abs(cur[k] - v).max()))
+
+
+def test_workspaces_are_bounded_over_ragged_batch_sizes(emulator):
+    """The CDC probing loop concatenates 1..7 per-domain batches whose row total changes whenever a loader yields its short last
+    batch (run.py:528-594): every distinct total used to pin an activation workspace (and a plan scratch) for good.  Workspaces are
+    now an LRU bounded in entries and bytes, the plan scratch is one buffer; results do not depend on eviction."""
+    class C:
+        use_atten = False; use_dcn = False; ple_n_expert_specific = 2; ple_n_expert_shared = 1
+    torch.manual_seed(3)
+    rng = np.random.default_rng(3)
+    fd = np.array([7, 5, 11, 4, 9, 6], dtype=np.int64)
+    m = cm.PLE(fd, 4, 2, 2, 1, ((8, 4), (4,)), (4, 4), dropout=0.0, config=C(), l2_reg_embedding=1e-3, l2_reg_linear=1e-3, l2_reg_dnn=1e-3)
+    rt = m._rt
+    rt.WS_MAX_ENTRIES = 4
+    m.eval()
+    first = {}
+    for rep in range(2):
+        for B in (3, 17, 5, 40, 9, 23, 31, 2, 64, 12):
+            x = torch.from_numpy(np.stack([np.random.default_rng(B).integers(0, d, size=B) for d in fd], axis=1).astype(np.int32))
+            with torch.no_grad():
+                p = m(x).numpy().copy()
+            if rep == 0:
+                first[B] = p
+            else:
+                assert np.array_equal(p, first[B])               # a re-created workspace gives the same bits
+            assert len(rt._ws) <= 4
+    assert len([k for k in rt.ops._scratch if k.startswith("embed_plan")]) <= 1
+    rt.pin_ws(64)                                                # a captured graph's workspace is never evicted
+    for B in (3, 17, 5, 40, 9):
+        x = torch.from_numpy(np.stack([rng.integers(0, d, size=B) for d in fd], axis=1).astype(np.int32))
+        with torch.no_grad():
+            m(x)
+    assert 64 in rt._ws

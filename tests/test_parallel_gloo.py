@@ -76,7 +76,8 @@ def _worker(rank, world, port, kind, B, n_steps, path, fd=None):
         x, y, g = _data(B, FD=fd)
         lo, hi = rank * B // world, (rank + 1) * B // world
         outs = _steps(model, kind, x[lo:hi], y[lo:hi], g[lo:hi], n_steps)
-        dp.gather_table()
+        # no explicit dp.gather_table(): state_dict() itself is collective under the sharded table (a pre-hook gathers the owners'
+        # rows), which is what the reference's checkpoint path calls (run.py:447-459)
         sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
         np.savez(os.path.join(path, f"rank{rank}.npz"), **sd,
                  **{f"pred{i}": o[0] for i, o in enumerate(outs)}, **{f"loss{i}": np.array(o[1]) for i, o in enumerate(outs)})
