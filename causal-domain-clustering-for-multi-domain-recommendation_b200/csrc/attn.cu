@@ -321,6 +321,262 @@ attn_bwd_bf16_kernel(const uint16_t* __restrict__ qkv, int64_t ld, const uint16_
   }
 }
 
+// ------------------------------------------------------------------------------------------ bf16 core on mma.sync
+// One warp per (sample, head); L <= 32 tokens and dh in {16, 32, 64} make every product a handful of m16n8k16 tensor-core
+// instructions on registers: Q, K, V (and dO) are loaded once as 8x8 bf16 blocks - thread (g = lane/4, t = lane%4) holds elements
+// (row g, columns 2t, 2t+1) of each block, one 32-bit load - which is at once the A-fragment layout, the B-fragment layout of the
+// TRANSPOSED operand, and the packed C-fragment layout; where a product needs the other orientation (P V, dS K, dS^T Q, P^T dO)
+// the block goes through movmatrix.trans.  Scores, softmax, dropout and the softmax backward stay fp32 in the accumulator
+// fragments (row reductions = 8 local values + two quad shuffles).  The SIMT kernels above spent their time in ~2 k shared-memory
+// loads per pair (2.6 ms forward / 6.0 ms backward per layer at 65 536 x 23 tokens x 2 heads); this is ~100 instructions per pair.
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t blk_trans(uint32_t a) {
+  uint32_t d;
+  asm volatile("movmatrix.sync.aligned.m8n8.trans.b16 %0, %1;" : "=r"(d) : "r"(a));
+  return d;
+}
+// the [32 rows, DH columns] bf16 matrix at `base` (row pitch ld) as 8x8 blocks blk[rb][cb]; rows >= L read as zero
+template <int DH>
+__device__ __forceinline__ void load_blocks(const uint16_t* __restrict__ base, int64_t ld, int L, int g, int t, uint32_t (&blk)[4][DH / 8]) {
+#pragma unroll
+  for (int rb = 0; rb < 4; ++rb) {
+    const int row = 8 * rb + g;
+#pragma unroll
+    for (int cb = 0; cb < DH / 8; ++cb)
+      blk[rb][cb] = row < L ? __ldg(reinterpret_cast<const uint32_t*>(base + (int64_t)row * ld + 8 * cb + 2 * t)) : 0u;
+  }
+}
+// accumulator tiles acc[mt][nt] (rows 16mt + g (+8), columns 8nt + 2t, +1) -> bf16 rows of `base`
+template <int DH>
+__device__ __forceinline__ void store_tiles(uint16_t* __restrict__ base, int64_t ld, int L, int g, int t, const float (&acc)[2][DH / 8][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+      const int r0 = 16 * mt + g, r1 = r0 + 8;
+      if (r0 < L) *reinterpret_cast<uint32_t*>(base + (int64_t)r0 * ld + 8 * nt + 2 * t) = pack_bf16x2(acc[mt][nt][0], acc[mt][nt][1]);
+      if (r1 < L) *reinterpret_cast<uint32_t*>(base + (int64_t)r1 * ld + 8 * nt + 2 * t) = pack_bf16x2(acc[mt][nt][2], acc[mt][nt][3]);
+    }
+}
+// S = scale * Q K^T -> row softmax over the L valid columns (fp32, in the accumulator fragments p[mt][nt][4])
+template <int DH>
+__device__ __forceinline__ void softmax_tiles(const uint32_t (&Qb)[4][DH / 8], const uint32_t (&Kb)[4][DH / 8], int L, float scale, int t,
+                                              float (&p)[2][4][4]) {
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      p[mt][nt][0] = p[mt][nt][1] = p[mt][nt][2] = p[mt][nt][3] = 0.f;
+#pragma unroll
+      for (int kt = 0; kt < DH / 16; ++kt)
+        mma_bf16_16816(p[mt][nt], Qb[2 * mt][2 * kt], Qb[2 * mt + 1][2 * kt], Qb[2 * mt][2 * kt + 1], Qb[2 * mt + 1][2 * kt + 1],
+                       Kb[nt][2 * kt], Kb[nt][2 * kt + 1]);
+    }
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {                          // row 16mt + g + 8hh: its 32 columns live in this quad
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const int j = 8 * nt + 2 * t + c;
+          float v = p[mt][nt][2 * hh + c] * scale;
+          v = j < L ? v : -INFINITY;
+          p[mt][nt][2 * hh + c] = v;
+          mx = fmaxf(mx, v);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float sum = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          const float e = expf(p[mt][nt][2 * hh + c] - mx);      // exp(-inf) = 0 for the masked columns
+          p[mt][nt][2 * hh + c] = e;
+          sum += e;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      const float inv = 1.f / sum;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) p[mt][nt][2 * hh + c] *= inv;
+    }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_fwd_mma_kernel(const uint16_t* __restrict__ qkv, int64_t ld, uint16_t* __restrict__ out, int64_t ldo, int64_t B, int L, int H, float scale,
+                    float drop_p, const uint64_t* __restrict__ seed_dev, uint32_t salt) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int A = H * DH;
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u, thr = drop_thr16(drop_p);
+  const int64_t pairs = B * H;
+  for (int64_t pr = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); pr < pairs; pr += (int64_t)gridDim.x * 4) {
+    const int64_t b = pr / H;
+    const int h = (int)(pr - b * H);
+    const uint16_t* base = qkv + b * L * ld + h * DH;
+    uint32_t Qb[4][DH / 8], Kb[4][DH / 8], Vb[4][DH / 8];
+    load_blocks<DH>(base, ld, L, g, t, Qb);
+    load_blocks<DH>(base + A, ld, L, g, t, Kb);
+    load_blocks<DH>(base + 2 * A, ld, L, g, t, Vb);
+    float p[2][4][4];
+    softmax_tiles<DH>(Qb, Kb, L, scale, t, p);
+    uint32_t Pb[4][4];                                         // dropped, rescaled probabilities as bf16 blocks [row block][column block]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int i = 16 * mt + g + 8 * (e >> 1), j = 8 * nt + 2 * t + (e & 1);
+          v[e] = p[mt][nt][e] * attn_keep_scale(drop_p, s0, thr, (uint32_t)(pr * L + i), (uint32_t)j);
+        }
+        Pb[2 * mt][nt] = pack_bf16x2(v[0], v[1]);
+        Pb[2 * mt + 1][nt] = pack_bf16x2(v[2], v[3]);
+      }
+    float o[2][DH / 8][4];
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+      uint32_t vt[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) vt[rb] = blk_trans(Vb[rb][nt]);       // B[k = token j][n = d]
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        o[mt][nt][0] = o[mt][nt][1] = o[mt][nt][2] = o[mt][nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+          mma_bf16_16816(o[mt][nt], Pb[2 * mt][2 * kt], Pb[2 * mt + 1][2 * kt], Pb[2 * mt][2 * kt + 1], Pb[2 * mt + 1][2 * kt + 1],
+                         vt[2 * kt], vt[2 * kt + 1]);
+      }
+    }
+    store_tiles<DH>(out + b * L * ldo + h * DH, ldo, L, g, t, o);
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128)
+attn_bwd_mma_kernel(const uint16_t* __restrict__ qkv, int64_t ld, const uint16_t* __restrict__ dout, int64_t lddo, uint16_t* __restrict__ dqkv,
+                    int64_t lddq, int64_t B, int L, int H, float scale, float drop_p, const uint64_t* __restrict__ seed_dev, uint32_t salt) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int A = H * DH;
+  const uint32_t s0 = drop_p > 0.f ? drop_s0(*seed_dev, salt) : 0u, thr = drop_thr16(drop_p);
+  const int64_t pairs = B * H;
+  for (int64_t pr = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); pr < pairs; pr += (int64_t)gridDim.x * 4) {
+    const int64_t b = pr / H;
+    const int h = (int)(pr - b * H);
+    const uint16_t* base = qkv + b * L * ld + h * DH;
+    uint16_t* dbase = dqkv + b * L * lddq + h * DH;
+    uint32_t Qb[4][DH / 8], Kb[4][DH / 8], Vb[4][DH / 8], Gb[4][DH / 8];
+    load_blocks<DH>(base, ld, L, g, t, Qb);
+    load_blocks<DH>(base + A, ld, L, g, t, Kb);
+    load_blocks<DH>(base + 2 * A, ld, L, g, t, Vb);
+    load_blocks<DH>(dout + b * L * lddo + h * DH, lddo, L, g, t, Gb);
+    float p[2][4][4];
+    softmax_tiles<DH>(Qb, Kb, L, scale, t, p);                  // recomputed: the forward stores no probabilities
+    // dP = dO V^T (gradient w.r.t. the dropped probabilities), then the softmax backward row by row
+    uint32_t Sb[4][4], Pb[4][4];                               // dS and the dropped probabilities as bf16 blocks [i block][j block]
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt) {
+      float dp[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < DH / 16; ++kt)
+          mma_bf16_16816(dp[nt], Gb[2 * mt][2 * kt], Gb[2 * mt + 1][2 * kt], Gb[2 * mt][2 * kt + 1], Gb[2 * mt + 1][2 * kt + 1],
+                         Vb[nt][2 * kt], Vb[nt][2 * kt + 1]);
+      }
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int i = 16 * mt + g + 8 * hh;
+        float ks[4][2], dot = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            ks[nt][c] = attn_keep_scale(drop_p, s0, thr, (uint32_t)(pr * L + i), (uint32_t)(8 * nt + 2 * t + c));
+            dp[nt][2 * hh + c] *= ks[nt][c];
+            dot = fmaf(p[mt][nt][2 * hh + c], dp[nt][2 * hh + c], dot);
+          }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        dot += __shfl_xor_sync(0xffffffffu, dot, 2);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const float ds0 = p[mt][nt][2 * hh] * (dp[nt][2 * hh] - dot) * scale, ds1 = p[mt][nt][2 * hh + 1] * (dp[nt][2 * hh + 1] - dot) * scale;
+          Sb[2 * mt + hh][nt] = pack_bf16x2(ds0, ds1);
+          Pb[2 * mt + hh][nt] = pack_bf16x2(p[mt][nt][2 * hh] * ks[nt][0], p[mt][nt][2 * hh + 1] * ks[nt][1]);
+        }
+      }
+    }
+    float acc[2][DH / 8][4];
+    // dQ = dS K
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+      uint32_t kt_[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) kt_[rb] = blk_trans(Kb[rb][nt]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+          mma_bf16_16816(acc[mt][nt], Sb[2 * mt][2 * kt], Sb[2 * mt + 1][2 * kt], Sb[2 * mt][2 * kt + 1], Sb[2 * mt + 1][2 * kt + 1],
+                         kt_[2 * kt], kt_[2 * kt + 1]);
+      }
+    }
+    store_tiles<DH>(dbase, lddq, L, g, t, acc);
+    // dK = dS^T Q and dV = Pd^T dO: the transposed [j block][i block] operands are movmatrix images of the blocks above
+    uint32_t St[4][4], Pt[4][4];
+#pragma unroll
+    for (int jb = 0; jb < 4; ++jb)
+#pragma unroll
+      for (int ib = 0; ib < 4; ++ib) { St[jb][ib] = blk_trans(Sb[ib][jb]); Pt[jb][ib] = blk_trans(Pb[ib][jb]); }
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+      uint32_t qt[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) qt[rb] = blk_trans(Qb[rb][nt]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+          mma_bf16_16816(acc[mt][nt], St[2 * mt][2 * kt], St[2 * mt + 1][2 * kt], St[2 * mt][2 * kt + 1], St[2 * mt + 1][2 * kt + 1],
+                         qt[2 * kt], qt[2 * kt + 1]);
+      }
+    }
+    store_tiles<DH>(dbase + A, lddq, L, g, t, acc);
+#pragma unroll
+    for (int nt = 0; nt < DH / 8; ++nt) {
+      uint32_t gt[4];
+#pragma unroll
+      for (int rb = 0; rb < 4; ++rb) gt[rb] = blk_trans(Gb[rb][nt]);
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt)
+          mma_bf16_16816(acc[mt][nt], Pt[2 * mt][2 * kt], Pt[2 * mt + 1][2 * kt], Pt[2 * mt][2 * kt + 1], Pt[2 * mt + 1][2 * kt + 1],
+                         gt[2 * kt], gt[2 * kt + 1]);
+      }
+    }
+    store_tiles<DH>(dbase + 2 * A, lddq, L, g, t, acc);
+  }
+}
+
+static inline bool attn_mma_ok(int dh, int64_t ld, int64_t ld2, int H) {
+  return (dh == 16 || dh == 32 || dh == 64) && ld % 2 == 0 && ld2 % 2 == 0 && ((int64_t)H * dh) % 2 == 0;
+}
+
 // head on bf16 tokens: one warp per sample, 8 bf16 per 128-bit load
 __global__ void __launch_bounds__(256)
 attn_pool_fwd_bf16_kernel(const uint16_t* __restrict__ z, const float* __restrict__ w, float* __restrict__ lin, int64_t ld_lin, int accumulate,
@@ -451,6 +707,14 @@ extern "C" int cdcmdr_attn_fwd_bf16(const uint16_t* qkv, int64_t ld, uint16_t* o
   if (B <= 0) return 0;
   CDC_REQUIRE(qkv && out && ld >= 3 * (int64_t)H * dh && ldo >= (int64_t)H * dh && ld % 2 == 0 && ((uintptr_t)qkv & 3) == 0,
               "bad attention operands");
+  if (attn_mma_ok(dh, ld, ldo, H) && ((uintptr_t)out & 3) == 0) {
+    const int grid = attn_grid(B * H);
+    if (dh == 16) attn_fwd_mma_kernel<16><<<grid, 128, 0, to_stream(s)>>>(qkv, ld, out, ldo, B, L, H, scale, drop_p, seed_dev, salt);
+    else if (dh == 32) attn_fwd_mma_kernel<32><<<grid, 128, 0, to_stream(s)>>>(qkv, ld, out, ldo, B, L, H, scale, drop_p, seed_dev, salt);
+    else attn_fwd_mma_kernel<64><<<grid, 128, 0, to_stream(s)>>>(qkv, ld, out, ldo, B, L, H, scale, drop_p, seed_dev, salt);
+    CDC_LAUNCHED();
+    return 0;
+  }
   const size_t smem = (size_t)kAttnWarps * (3 * (size_t)L * (dh + 1) + (size_t)L * L) * sizeof(float);
   CDC_REQUIRE(smem <= 200 * 1024, "attention tile does not fit shared memory");
   CDC_CHECK(cudaFuncSetAttribute(attn_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -468,6 +732,14 @@ extern "C" int cdcmdr_attn_bwd_bf16(const uint16_t* qkv, int64_t ld, const uint1
   if (B <= 0) return 0;
   CDC_REQUIRE(qkv && dout && dqkv && ld >= 3 * (int64_t)H * dh && lddq >= 3 * (int64_t)H * dh && lddo >= (int64_t)H * dh && ld % 2 == 0 &&
               lddo % 2 == 0 && ((uintptr_t)qkv & 3) == 0 && ((uintptr_t)dout & 3) == 0, "bad attention operands");
+  if (attn_mma_ok(dh, ld, lddo, H) && lddq % 2 == 0 && ((uintptr_t)dqkv & 3) == 0) {
+    const int grid = attn_grid(B * H);
+    if (dh == 16) attn_bwd_mma_kernel<16><<<grid, 128, 0, to_stream(s)>>>(qkv, ld, dout, lddo, dqkv, lddq, B, L, H, scale, drop_p, seed_dev, salt);
+    else if (dh == 32) attn_bwd_mma_kernel<32><<<grid, 128, 0, to_stream(s)>>>(qkv, ld, dout, lddo, dqkv, lddq, B, L, H, scale, drop_p, seed_dev, salt);
+    else attn_bwd_mma_kernel<64><<<grid, 128, 0, to_stream(s)>>>(qkv, ld, dout, lddo, dqkv, lddq, B, L, H, scale, drop_p, seed_dev, salt);
+    CDC_LAUNCHED();
+    return 0;
+  }
   const size_t smem = (size_t)kAttnWarps * (4 * (size_t)L * (dh + 1) + 2 * (size_t)L * L) * sizeof(float);
   CDC_REQUIRE(smem <= 200 * 1024, "attention tile does not fit shared memory");
   CDC_CHECK(cudaFuncSetAttribute(attn_bwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

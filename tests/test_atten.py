@@ -209,7 +209,7 @@ def test_attention_bf16_entry_points_gpu(B, L, H, dh):
         a, b = bf16_to_f32(got.cpu().numpy().view(np.uint16)), bf16_to_f32(ref)
         sc_ = max(float(np.abs(b).max()), 1e-30)
         assert float(np.abs(a - b).max()) <= 2 ** -7 * sc_, (what, float(np.abs(a - b).max()), sc_)
-        assert float((np.abs(a - b) > 2 ** -9 * sc_).mean()) < 0.02, what
+        assert float((np.abs(a - b) > 2 ** -8 * sc_).mean()) < 0.02, what      # P and dS are rounded to bf16 for the tensor-core products
     # --- head
     n = L * A
     h_lin, h_dz, h_dw = lin0.copy(), np.zeros((B, n), np.uint16), np.zeros(n, np.float32)
