@@ -51,7 +51,7 @@ class GemmBf16(C.Structure):
                 ("accumulate", I32),
                 ("split_k", I32), ("aux_split_stride", I64),
                 ("block_n", I32),
-                ("cross_x0", P), ("cross_x", P), ("cross_xw", P), ("ld_cross", I64)]
+                ("cross_x0", P), ("cross_x", P), ("ld_cross", I64)]
 
 
 class MixDesc(C.Structure):

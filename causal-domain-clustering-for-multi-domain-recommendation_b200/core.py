@@ -237,7 +237,7 @@ class Ops:
     def gemm_tc(self, *, A, lda, a_rows, a_cols, a_mn, Bt, ldb, b_rows, b_cols, b_mn, M, N, K, G=1, a_gm=0, a_gk=0, b_gn=0, b_gk=0,
                 bias=None, bias_gs=0, n_main=0, out_main=None, ld_main=0, main_gn=0, out_aux=None, ld_aux=0, aux_gn=0, act=0,
                 mask=None, ld_mask=0, mask_gn=0, mask_scale=1.0, drop_p=0.0, seed_ptr=None, salt=0, accumulate=0, split_k=1,
-                cross_x0=None, cross_x=None, cross_xw=None, ld_cross=0):
+                cross_x0=None, cross_x=None, ld_cross=0):
         """A, Bt, outputs, bias, mask are raw addresses.  cross_*: the CrossNetV2 epilogue (cdcmdr.h).  split_k='auto' (weight gradients, n_main == 0): enough K slices to
         fill the machine, partials reduced into out_aux in a fixed order."""
         if M <= 0 or N <= 0 or G <= 0:
@@ -282,7 +282,7 @@ class Ops:
         d = GemmBf16(A, lda, a_rows, a_cols, Bt, ldb, b_rows, b_cols, M, N, K, G, a_gm, a_gk, b_gn, b_gk, 1 if a_mn else 0,
                      1 if b_mn else 0, bias, bias_gs, n_main, out_main, ld_main, main_gn, dst, ld_aux, aux_gn, act, mask, ld_mask,
                      mask_gn, mask_scale, drop_p, seed_ptr if drop_p > 0 else None, salt, accumulate if split == 1 else 0,
-                     split, stride, 0, cross_x0, cross_x, cross_xw, ld_cross)
+                     split, stride, 0, cross_x0, cross_x, ld_cross)
         self.lib.gemm_bf16_tc(C.byref(d), self.stream)
         if split > 1:
             self.lib.splitk_reduce(part, stride, split, out_aux, 1, stride, stride, stride, 1 if accumulate else 0, self.stream)
@@ -305,7 +305,7 @@ class Ops:
         stride = M * N
         part = self.scratch("tc_splitk", 4 * max(split, 1) * stride).data_ptr()
         d = GemmBf16(dY.ptr, dY.ld, B, M, X.ptr, X.ld, B, N, M, N, B, 1, 0, 0, 0, 0, 1, 1, None, 0, 0, None, 0, 0, part, N, 0, 0,
-                     None, 0, 0, 1.0, 0.0, None, 0, 0, split, stride, 0, None, None, None, 0)
+                     None, 0, 0, 1.0, 0.0, None, 0, 0, split, stride, 0, None, None, 0)
         self.lib.gemm_bf16_tc(C.byref(d), self.stream)
         self.lib.splitk_reduce(part, stride, split, gW_addr, M, K, N, K, 0, self.stream)
         self.lib.splitk_reduce(part + 4 * K, stride, split, gb_addr, M, 1, N, 1, 0, self.stream)

@@ -213,7 +213,7 @@ struct TcParams {
   int32_t a_res;                             // A-resident sweep: see the kernel comment
   int64_t tiles_lo; int32_t tiles_rem;       // a_res: CTA c owns tiles [c*lo + min(c, rem), +lo + (c < rem))
   unsigned long long* prof;                  // diagnostics: cycles spent in each pipeline wait, summed over CTAs (NULL = off)
-  const float* cross_x0; const float* cross_x; float* cross_xw; int64_t ld_cross;   // CrossNetV2 epilogue (see cdcmdr.h)
+  const uint16_t* cross_x0; const uint16_t* cross_x; int64_t ld_cross;   // CrossNetV2 epilogue (see cdcmdr.h): bf16 x0 / x boxes through map_m / map_x
   int32_t debug;                             // probe only (cdcmdr_gemm_bf16_tc_mode bits 4..6): 16 = epilogue drains nothing, 64 = tcgen05.ld only,
                                              // 32 = everything but the TMA store.  Results are garbage; never set by the product path.
 };
@@ -302,7 +302,7 @@ template <bool CTA2>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const __grid_constant__ CUtensorMap map_c, const __grid_constant__ CUtensorMap map_d,
-                    const __grid_constant__ CUtensorMap map_m, const TcParams p) {
+                    const __grid_constant__ CUtensorMap map_m, const __grid_constant__ CUtensorMap map_x, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];               // SWIZZLE_128B tiles need 1024-byte alignment
   // A-resident sweep (p.a_res; short K loops with several column tiles): a CTA owns a CONTIGUOUS range of tiles, column tile
   // fastest, so consecutive tiles share their 128 rows of A.  All k-blocks of that A panel sit in dedicated slots, loaded once per
@@ -339,7 +339,8 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_c) : "memory");
     if (p.tma_aux) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_d) : "memory");
-    if (p.tma_mask) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_m) : "memory");
+    if (p.tma_mask || p.cross_x0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_m) : "memory");
+    if (p.cross_x0) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
@@ -491,13 +492,22 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     const uint32_t my_stage_u32 = smem_u32(my_stage);
     // ReLU mask through TMA: the warp's next 32 x 32 mask box streams into its private buffer while the previous chunk is still in
     // the math / store phase (per-lane 64-byte global reads of 32 different rows cost ~5 k cycles per tile in the masked dgrad)
-    const uint8_t* my_mask = mask_s + ew * TC_STAGING_WARP_BYTES;
+    const uint8_t* my_mask = mask_s + ew * (p.cross_x0 ? 2 * TC_STAGING_WARP_BYTES : TC_STAGING_WARP_BYTES);   // cross: x0 box, then x box
     const uint32_t my_mask_u32 = smem_u32(my_mask), my_mbar = mbar0 + 8 * ew;
     uint32_t mask_phase = 0;
     // chunk (n0 + 32*ci) of this tile takes the TMA-store fast path AND carries a mask
     auto mask_by_tma = [&](int64_t n0_, int ci_) -> bool {
       const int64_t nb_ = n0_ + 32 * ci_;
       return p.tma_mask && ci_ < n_chunks_c && 32 * ci_ + 32 <= p.block_n && nb_ + 32 <= p.n_main;
+    };
+    // CrossNetV2 epilogue: the chunk's x0 and x boxes (32 rows x 32 bf16 each) land in the warp's buffer behind one barrier
+    auto cross_chunk = [&](int64_t n0_, int ci_) -> bool { return p.cross_x0 && ci_ < n_chunks_c && n0_ + 32 * ci_ < p.N; };
+    auto issue_cross = [&](int64_t mt_, int64_t nb_) {
+      if (lane == 0) {
+        mbar_expect_tx(my_mbar, 2 * TC_STAGING_WARP_BYTES);
+        tma_load_2d(my_mask_u32, &map_m, my_mbar, (int32_t)nb_, (int32_t)(mt_ * TC_BLOCK_M + q * 32));
+        tma_load_2d(my_mask_u32 + TC_STAGING_WARP_BYTES, &map_x, my_mbar, (int32_t)nb_, (int32_t)(mt_ * TC_BLOCK_M + q * 32));
+      }
     };
     auto issue_mask = [&](int g_, int64_t mt_, int64_t nb_) {
       if (lane == 0) {
@@ -527,6 +537,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int64_t n0 = (int64_t)nt * p.block_n;
       const bool use_bias = p.bias != nullptr && z == 0;
       if (mask_by_tma(n0, sub)) issue_mask(g, mt, n0 + 32 * sub);
+      if (cross_chunk(n0, sub)) issue_cross(mt, n0 + 32 * sub);
       { TC_PROF_T0();
         if (CTA2) mbar_wait_cluster(tfull0 + 8 * acc, acc_phase); else mbar_wait(tfull0 + 8 * acc, acc_phase);
         if (ew == 0 && lane == 0) TC_PROF_ADD(3); }
@@ -551,49 +562,59 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           __syncwarp();
         }
         if (p.cross_x0) {
-          // ---------------- CrossNetV2 layer: y = x0 * acc + b + x -> fp32 layer output, bf16 operand of the next layer, fp32 acc ----------------
-          // (layer.py:339-343).  Every stream is read / written by the row's own lane: 128 contiguous bytes per lane per fp32 stream.
+          // ---------------- CrossNetV2 layer (layer.py:339-343): y = x0 * acc + b + x ----------------
+          // x0 / x arrive as bf16 boxes by TMA (requested one chunk ahead), y leaves as bf16 and the raw product acc as fp32 (kept for
+          // the backward) by TMA stores from the warp's swizzled staging tile: no per-lane row accesses to global memory (a first cut
+          // with 128-byte per-lane loads / stores spent ~80 k cycles per tile in the LSU: 32 distinct lines per instruction).
+          mbar_wait(my_mbar, mask_phase);
+          mask_phase ^= 1;
+          uint4 xa[4], xb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            xa[j] = *reinterpret_cast<const uint4*>(my_mask + lane * 64 + ((j ^ swz) * 16));
+            xb[j] = *reinterpret_cast<const uint4*>(my_mask + TC_STAGING_WARP_BYTES + lane * 64 + ((j ^ swz) * 16));
+          }
+          __syncwarp();                                  // every lane has its rows: the buffer may take the next boxes
+          if (cross_chunk(n0, ci + 4)) issue_cross(mt, n0 + 32 * (ci + 4));
           tc_ld_wait();
-          if (m < p.M) {
-            const float* x0p = p.cross_x0 + m * p.ld_cross + nb;
-            const float* xp = p.cross_x + m * p.ld_cross + nb;
-            float* yp = p.out_aux + m * p.ld_aux + nb;
-            float* wp = p.cross_xw ? p.cross_xw + m * p.ld_cross + nb : nullptr;
-            uint16_t* bp = p.out_main ? p.out_main + m * p.ld_main + nb : nullptr;
-            const bool vec = cw == 32 && ((((uintptr_t)x0p) | ((uintptr_t)xp) | ((uintptr_t)yp) | ((uintptr_t)wp) | ((uintptr_t)bp)) & 15) == 0;
-            if (vec) {
-              float4 a[8], b[8];
+          const int32_t row0 = (int32_t)(mt * TC_BLOCK_M + q * 32);
+          if (p.out_aux) {                               // acc, fp32: two 16-column boxes
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { a[j] = __ldg(reinterpret_cast<const float4*>(x0p) + j); b[j] = __ldg(reinterpret_cast<const float4*>(xp) + j); }
-              uint32_t o[16];
+            for (int hh = 0; hh < 2; ++hh) {
+              if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
+              __syncwarp();
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bs = *reinterpret_cast<const float4*>(bias_t + 4 * j);
-                const float4 acc = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                float4 y;
-                y.x = fmaf(a[j].x, acc.x, bs.x) + b[j].x; y.y = fmaf(a[j].y, acc.y, bs.y) + b[j].y;
-                y.z = fmaf(a[j].z, acc.z, bs.z) + b[j].z; y.w = fmaf(a[j].w, acc.w, bs.w) + b[j].w;
-                reinterpret_cast<float4*>(yp)[j] = y;
-                if (wp) reinterpret_cast<float4*>(wp)[j] = acc;
-                o[2 * j] = pack_bf16x2(y.x, y.y); o[2 * j + 1] = pack_bf16x2(y.z, y.w);
+              for (int j = 0; j < 4; ++j) {
+                const int e = 16 * hh + 4 * j;
+                *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ swz) * 16)) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
               }
-              if (bp) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) reinterpret_cast<uint4*>(bp)[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                if (j < cw) {
-                  const float acc = __uint_as_float(v[j]);
-                  const float y = fmaf(x0p[j], acc, bias_t[j]) + xp[j];
-                  yp[j] = y;
-                  if (wp) wp[j] = acc;
-                  if (bp) bp[j] = f32_to_bf16(y);
-                }
-              }
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) { tma_store_2d(&map_d, my_stage_u32, (int32_t)(nb + 16 * hh), row0); tma_store_commit(); }
+              store_pending = true;
             }
           }
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t wa[4] = {xa[j].x, xa[j].y, xa[j].z, xa[j].w}, wb[4] = {xb[j].x, xb[j].y, xb[j].z, xb[j].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int e = 8 * j + 2 * k;
+              const float y0 = fmaf(__uint_as_float(wa[k] << 16), __uint_as_float(v[e]), bias_t[e]) + __uint_as_float(wb[k] << 16);
+              const float y1 = fmaf(__uint_as_float(wa[k] & 0xFFFF0000u), __uint_as_float(v[e + 1]), bias_t[e + 1]) + __uint_as_float(wb[k] & 0xFFFF0000u);
+              o[4 * j + k] = pack_bf16x2(y0, y1);
+            }
+          }
+          if (store_pending) { if (lane == 0) tma_store_wait_read0(); store_pending = false; }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<uint4*>(my_stage + lane * 64 + ((j ^ swz) * 16)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&map_c, my_stage_u32, (int32_t)nb, row0); tma_store_commit(); }
+          store_pending = true;
           continue;
         }
         const bool full_main = nb + 32 <= p.n_main && cw == 32;
@@ -868,6 +889,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
     const int64_t nt = ceil_div(p->N, TC_MAX_N);
     bn = (int)(ceil_div(ceil_div(p->N, nt), 16) * 16);
   }
+  if (p->cross_x0 && p->block_n <= 0) bn = (int)(ceil_div(bn, 32) * 32);   // whole 32-column chunks (the x0 / x boxes)
   if (q.b_mn_major) bn = (int)(ceil_div(bn, 64) * 64);            // whole 64-column boxes of the stored [K, N] matrix
   CDC_REQUIRE(bn >= 16 && bn <= TC_MAX_N && bn % 16 == 0, "block_n must be a multiple of 16 in [16, 256]");
   q.block_n = bn;
@@ -882,11 +904,15 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   q.out_aux = p->out_aux; q.ld_aux = p->ld_aux; q.aux_gn = p->aux_gn; q.aux_split_stride = p->aux_split_stride;
   q.act = p->act; q.mask = p->mask; q.ld_mask = p->ld_mask; q.mask_gn = p->mask_gn; q.mask_scale = p->mask_scale;
   q.drop_p = p->drop_p; q.seed_dev = p->seed_dev; q.salt = p->salt; q.accumulate = p->accumulate;
-  q.cross_x0 = p->cross_x0; q.cross_x = p->cross_x; q.cross_xw = p->cross_xw; q.ld_cross = p->ld_cross;
-  if (p->cross_x0) {
-    CDC_REQUIRE(p->cross_x && p->out_aux && p->bias && p->G == 1 && split == 1 && !p->mask && p->drop_p <= 0.f && !p->accumulate && p->act == 0,
-                "cross epilogue: needs x, a fp32 output and a bias; no groups / split-K / mask / dropout / accumulate / activation");
-    q.n_main = 0;                                                   // both outputs cover every column; the generic main / aux split is unused
+  q.cross_x0 = p->cross_x0; q.cross_x = p->cross_x; q.ld_cross = p->ld_cross;
+  const bool cross = p->cross_x0 != nullptr;
+  if (cross) {
+    CDC_REQUIRE(p->cross_x && p->out_main && p->bias && p->G == 1 && split == 1 && !p->mask && p->drop_p <= 0.f && !p->accumulate && p->act == 0,
+                "cross epilogue: needs x, a bf16 output and a bias; no groups / split-K / mask / dropout / accumulate / activation");
+    CDC_REQUIRE(p->N % 32 == 0 && p->n_main == p->N && p->ld_cross % 8 == 0 && p->ld_main % 8 == 0 && ((uintptr_t)p->cross_x0 % 16) == 0 &&
+                ((uintptr_t)p->cross_x % 16) == 0 && ((uintptr_t)p->out_main % 16) == 0 && p->M < (int64_t)1 << 31 &&
+                (!p->out_aux || (p->ld_aux % 4 == 0 && ((uintptr_t)p->out_aux % 16) == 0)),
+                "cross epilogue: N must be a multiple of 32 and every stream TMA-able (16-byte aligned base and pitch)");
   }
   CDC_REQUIRE(split == 1 || q.split_k == 1 || p->aux_split_stride > 0, "split-K needs aux_split_stride");
   if (q.split_k != split && split > 1) {
@@ -907,7 +933,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   if (int rc = make_map(&ma, p->A, p->a_rows, p->a_cols, p->lda, q.a_mn_major ? 64u : (uint32_t)TC_BLOCK_M)) return rc;
   if (int rc = make_map(&mb, p->Bt, p->b_rows, p->b_cols, p->ldb, q.b_mn_major ? 64u : (uint32_t)b_cols)) return rc;
   // bf16 output through TMA stores when its layout allows a tensor map (16-byte aligned base / pitch / group offsets)
-  q.tma_store = (!p->cross_x0 && p->n_main > 0 && ((uintptr_t)p->out_main % 16) == 0 && p->ld_main % 8 == 0 && p->main_gn % 8 == 0 &&
+  q.tma_store = (p->n_main > 0 && ((uintptr_t)p->out_main % 16) == 0 && p->ld_main % 8 == 0 && p->main_gn % 8 == 0 &&
                  (p->G - 1) * p->main_gn + p->n_main <= p->ld_main && p->M < (int64_t)1 << 31) ? 1 : 0;
   if (q.tma_store) {
     if (int rc = make_map(&mc, p->out_main, p->M, (p->G - 1) * p->main_gn + p->n_main, p->ld_main, 32u, false, true)) return rc;
@@ -916,7 +942,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   }
   CUtensorMap md = ma, mm = ma;
   const int64_t n_aux = p->N - p->n_main;
-  q.tma_aux = (!p->cross_x0 && n_aux > 0 && q.split_k == 1 && ((uintptr_t)p->out_aux % 16) == 0 && p->ld_aux % 4 == 0 && p->aux_gn % 4 == 0 &&
+  q.tma_aux = (n_aux > 0 && q.split_k == 1 && ((uintptr_t)p->out_aux % 16) == 0 && p->ld_aux % 4 == 0 && p->aux_gn % 4 == 0 &&
                p->n_main % 16 == 0 && (p->G - 1) * p->aux_gn + n_aux <= p->ld_aux && p->M < (int64_t)1 << 31) ? 1 : 0;
   if (q.tma_aux) {
     if (int rc = make_map(&md, p->out_aux, p->M, (p->G - 1) * p->aux_gn + n_aux, p->ld_aux, 32u, true, true)) return rc;
@@ -927,8 +953,15 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   if (q.tma_mask) {
     if (int rc = make_map(&mm, p->mask, p->M, (p->G - 1) * p->mask_gn + p->n_main, p->ld_mask, 32u, false, true)) return rc;
   }
+  CUtensorMap mx = ma;
+  if (cross) {
+    CDC_REQUIRE(q.tma_store && bn % 32 == 0, "cross epilogue: the bf16 output must be TMA-able");
+    if (int rc = make_map(&mm, p->cross_x0, p->M, p->N, p->ld_cross, 32u, false, true)) return rc;
+    if (int rc = make_map(&mx, p->cross_x, p->M, p->N, p->ld_cross, 32u, false, true)) return rc;
+    if (p->out_aux) { if (int rc = make_map(&md, p->out_aux, p->M, p->N, p->ld_aux, 32u, true, true)) return rc; }
+  }
   const int b_bytes = (q.b_mn_major ? (int)ceil_div(b_cols, 64) * 64 : b_cols) * TC_BLOCK_K * 2;
-  const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + (q.tma_mask ? TC_MASK_BYTES : 0);
+  const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + (cross ? 2 * TC_MASK_BYTES : (q.tma_mask ? TC_MASK_BYTES : 0));
   // A-resident sweep: K-major A, no split, a short K loop whose whole A panel fits next to >= 3 ring stages of B, and at least
   // two column tiles to sweep.  Mode bit 1 switches it off.
   const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
@@ -954,7 +987,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   }
   if (!cta2) {
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-    gemm_bf16_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, mm, q);
+    gemm_bf16_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, mm, mx, q);
     CDC_LAUNCHED();
     return 0;
   }
@@ -968,7 +1001,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  CDC_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<true>, ma, mb, mc, md, mm, q));
+  CDC_CHECK(cudaLaunchKernelEx(&cfg, gemm_bf16_tc_kernel<true>, ma, mb, mc, md, mm, mx, q));
   CDC_LAUNCHED();
   return 0;
 }

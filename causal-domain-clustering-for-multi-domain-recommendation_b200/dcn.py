@@ -228,32 +228,42 @@ class DCNv2(_CrossModel):
         """bf16 GEMM operand of the layer-l input: the gathered bf16 embeddings themselves for l = 0, else a bf16 copy of x_l"""
         if l == 0 and X is not None and X.is_bf16:
             return X
-        if l > 0:                                                  # written by layer l-1's fused epilogue (_v2_fwd)
-            return ws.mat(f"cv2.xop{l}", B, (self.embed_output_dim + 7) // 8 * 8, torch.bfloat16, zero=True)
         return self._rt.gemm_input(ws, f"cv2.xop{l}", cur, B, self.embed_output_dim)
+
+    def _v2_fused(self, X: Mat | None) -> bool:
+        """the layer's Hadamard / bias / residual stage runs inside the GEMM's epilogue (cdcmdr_gemm_bf16_t.cross_*): needs whole
+        32-column chunks and the bf16 gathered embeddings as x0"""
+        return self._v2_tc() and self.embed_output_dim % 32 == 0 and X is not None and X.is_bf16 and X.ld == self.embed_output_dim
 
     def _v2_fwd(self, ws, x0: Mat, B, X: Mat | None = None) -> Mat:
         rt, D = self._rt, self.embed_output_dim
+        if self._v2_fused(X):
+            # ONE launch per layer: the tcgen05 GEMM's epilogue applies x0 * acc + b + x (layer.py:339-343) on bf16 x0 / x boxes it
+            # fetches by TMA and leaves the bf16 layer output (= the next layer's GEMM operand, reused by the weight-gradient GEMM of
+            # the backward) and the raw fp32 product acc (the backward's dx0 += dx * acc) - no separate cast / Hadamard passes
+            cur = X
+            for l in range(self.n_cross_layers):
+                wname = f"crossnet.w.{l}.weight"
+                xw = ws.mat(f"cv2.xw{l}", B, D)
+                nxt = ws.mat(f"cv2.xop{l + 1}", B, D, torch.bfloat16, zero=True)
+                rt.ops.gemm_tc(A=cur.ptr, lda=cur.ld, a_rows=B, a_cols=D, a_mn=0, Bt=rt.Wb.data_ptr() + 2 * rt.o(wname), ldb=D,
+                               b_rows=D, b_cols=D, b_mn=0, M=B, N=D, K=D, bias=rt.w(f"crossnet.b.{l}"), n_main=D,
+                               out_main=nxt.ptr, ld_main=nxt.ld, out_aux=xw.ptr, ld_aux=xw.ld, cross_x0=X.ptr, cross_x=cur.ptr, ld_cross=D)
+                cur = nxt
+            return cur
         cur = x0
         for l in range(self.n_cross_layers):
             xw = ws.mat(f"cv2.xw{l}", B, D)
             wname = f"crossnet.w.{l}.weight"
-            nxt = ws.mat(f"cv2.x{l + 1}", B, D)
             if self._v2_tc():
-                # ONE launch per layer: the tcgen05 GEMM's epilogue applies x0 * acc + b + x (layer.py:339-343) and leaves the fp32 layer
-                # output, its bf16 copy (the next layer's GEMM operand, reused by the weight-gradient GEMM of the backward) and the raw
-                # product acc (the backward's dx0 += dx * acc) - no separate cast / Hadamard passes over [B, D]
                 cop = self._v2_operand(ws, l, cur, X, B)
-                last = l + 1 == self.n_cross_layers
-                nop = None if last else ws.mat(f"cv2.xop{l + 1}", B, (D + 7) // 8 * 8, torch.bfloat16, zero=True)
                 rt.ops.gemm_tc(A=cop.ptr, lda=cop.ld, a_rows=B, a_cols=D, a_mn=0, Bt=rt.Wb.data_ptr() + 2 * rt.o(wname), ldb=D,
-                               b_rows=D, b_cols=D, b_mn=0, M=B, N=D, K=D, bias=rt.w(f"crossnet.b.{l}"), n_main=0,
-                               out_main=nop.ptr if nop is not None else None, ld_main=nop.ld if nop is not None else 0,
-                               out_aux=nxt.ptr, ld_aux=nxt.ld, cross_x0=x0.ptr, cross_x=cur.ptr, cross_xw=xw.ptr, ld_cross=D)
+                               b_rows=D, b_cols=D, b_mn=0, M=B, N=D, K=D, n_main=0, out_aux=xw.ptr, ld_aux=xw.ld)
             else:
                 rt.ops.gemm_f32(A=cur.ptr, a_rs=cur.ld, a_cs=1, Bt=rt.w(wname), b_rs=D, b_cs=1, Cm=xw.ptr, c_rs=D,
                                 M=B, N=D, K=D)
-                rt.ops.cross_fuse_fwd(x0, cur, xw, D, rt.w(f"crossnet.b.{l}"), nxt, B, D)
+            nxt = ws.mat(f"cv2.x{l + 1}", B, D)
+            rt.ops.cross_fuse_fwd(x0, cur, xw, D, rt.w(f"crossnet.b.{l}"), nxt, B, D)
             cur = nxt
         return cur
 
@@ -435,14 +445,16 @@ class DCNv2(_CrossModel):
             logit = self._head_fwd(ws, "dnn_linear.weight", None, mlp_out, B)
         return logit, self._lin_fwd(ws, X, B)
 
-    def _cross_out(self, ws, B) -> Mat:
+    def _cross_out(self, ws, B, X: Mat | None = None) -> Mat:
         tag = "cmix" if self.use_low_rank_mixture else "cv2"
+        if not self.use_low_rank_mixture and self._v2_fused(X):     # the fused layers leave bf16 outputs (_v2_fwd)
+            return ws.mat(f"cv2.xop{self.n_cross_layers}", B, self.embed_output_dim, torch.bfloat16)
         return ws.mat(f"{tag}.x{self.n_cross_layers}", B, self.embed_output_dim)
 
     def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat):
         rt, D = self._rt, self.embed_output_dim
         x0 = ws.mat("X32", B, D) if X.is_bf16 else X
-        cross = self._cross_out(ws, B)
+        cross = self._cross_out(ws, B, X)
         mlp_out = self._mlp._act(ws, len(self.mlp_dims) - 1, B)
         cross_bwd = (lambda w, a, d, n: (self._mix_bwd if self.use_low_rank_mixture else self._v2_bwd)(w, a, d, n, X))
         dX = ws.mat("dX", B, D)

@@ -135,11 +135,13 @@ typedef struct {
   int32_t split_k; int64_t aux_split_stride;
   int32_t block_n;
   /* a11 CrossNetV2 layer fused into the epilogue (layer.py:339-343: x_{l+1} = x0 * (x_l W^T) + b + x_l), cross_x0 != NULL:
-   *   acc = A Bt^T (this GEMM, A = bf16 x_l, Bt = bf16 W_l) ; y = cross_x0[m, n] * acc + bias[n] + cross_x[m, n]
-   *   out_aux[m*ld_aux + n] = y (fp32, the layer output) ; out_main[m*ld_main + n] = bf16(y) (next layer's GEMM operand, may be NULL)
-   *   cross_xw[m*ld_cross + n] = acc (fp32, kept for the backward; may be NULL).
-   * Requires G == 1, bias, no mask / dropout / accumulate / split-K; n_main is ignored (both outputs cover all N columns). */
-  const float* cross_x0; const float* cross_x; float* cross_xw; int64_t ld_cross;
+   *   acc = A Bt^T (this GEMM: A = bf16 x_l, Bt = bf16 W_l) ; y = cross_x0[m, n] * acc + bias[n] + cross_x[m, n]
+   *   out_main[m*ld_main + n] = bf16(y)  (the layer output = next layer's GEMM operand; n_main must equal N)
+   *   out_aux[m*ld_aux + n]   = acc      (fp32, kept for the backward's dx0 += dx * acc; may be NULL)
+   * cross_x0 / cross_x are bf16 [M, N] with pitch ld_cross (x is normally the A operand itself); they are read as 32 x 32 boxes by
+   * TMA and both outputs leave by TMA stores.  Requires N % 32 == 0, 16-byte aligned bases and pitches, G == 1, a bias, and no
+   * mask / dropout / accumulate / split-K / activation. */
+  const uint16_t* cross_x0; const uint16_t* cross_x; int64_t ld_cross;
 } cdcmdr_gemm_bf16_t;
 int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t s);
 int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want);

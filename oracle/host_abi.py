@@ -243,16 +243,14 @@ class HostABI:
                 k0, k1 = z * per, min((z + 1) * per, p.K)
                 acc = (a[:, k0:k1].astype(np.float64) @ b[:, k0:k1].astype(np.float64).T).astype(np.float32)
                 if getattr(p, "cross_x0", None):
-                    # CrossNetV2 epilogue (cdcmdr.h; layer.py:339-343): y = x0 * acc + b + x, fp32 y, bf16 copy of y, fp32 acc
-                    x0 = _mat(p.cross_x0, p.M, p.N, p.ld_cross)
-                    xx = _mat(p.cross_x, p.M, p.N, p.ld_cross)
+                    # CrossNetV2 epilogue (cdcmdr.h; layer.py:339-343): y = x0 * acc + b + x on bf16 x0 / x; bf16 y, fp32 acc
+                    x0 = bf16_to_f32(_mat(p.cross_x0, p.M, p.N, p.ld_cross, 1, np.uint16))
+                    xx = bf16_to_f32(_mat(p.cross_x, p.M, p.N, p.ld_cross, 1, np.uint16))
                     bias = _arr(p.bias, p.N, np.float32)[None, :]
                     y = ((x0 * acc + bias) + xx).astype(np.float32)
-                    if p.cross_xw:
-                        _mat(p.cross_xw, p.M, p.N, p.ld_cross)[...] = acc
-                    _mat(p.out_aux, p.M, p.N, p.ld_aux)[...] = y
-                    if p.out_main:
-                        _mat(p.out_main, p.M, p.N, p.ld_main, 1, np.uint16)[...] = f32_to_bf16(y).reshape(p.M, p.N)
+                    if p.out_aux:
+                        _mat(p.out_aux, p.M, p.N, p.ld_aux)[...] = acc
+                    _mat(p.out_main, p.M, p.N, p.ld_main, 1, np.uint16)[...] = f32_to_bf16(y).reshape(p.M, p.N)
                     continue
                 if p.bias and z == 0:
                     acc = acc + _arr(p.bias + 4 * g * p.bias_gs, p.N, np.float32)[None, :]
