@@ -136,6 +136,8 @@ SIGNATURES = {
     "cdcmdr_attn_pool_fwd": (INT, [P, P, P, I64, INT, I64, I64, P]),
     "cdcmdr_attn_pool_scratch_bytes": (C.c_size_t, [I64, I64]),
     "cdcmdr_attn_pool_bwd": (INT, [P, P, P, I64, P, P, I64, I64, P, P]),
+    "cdcmdr_peer_allreduce_bytes": (SZ, [INT, I64]),
+    "cdcmdr_peer_allreduce_f64": (INT, [P, INT, INT, P, P, I64, I64, P, P]),
     "cdcmdr_attn_fwd_bf16": (INT, [P, I64, P, I64, I64, INT, INT, INT, F32, F32, P, U32, P]),
     "cdcmdr_attn_bwd_bf16": (INT, [P, I64, P, I64, P, I64, I64, INT, INT, INT, F32, F32, P, U32, P]),
     "cdcmdr_attn_pool_fwd_bf16": (INT, [P, P, P, I64, INT, I64, I64, P]),

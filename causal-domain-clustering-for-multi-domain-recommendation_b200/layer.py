@@ -527,12 +527,10 @@ class BaseModel(nn.Module):
         self._last = None
         if train:
             self._bump_batches_tracked(B)
-        rt.arm_input_grad(side is not None and not sharded)
+        rt.arm_input_grad(side is not None)
         dX = self._program_bwd(ws, X, B, train, Mat(dlogits, 0, T), **kw)
         dx_event = getattr(rt, "_dx_event", None)
         rt.arm_input_grad(False)
-        if dp is not None:
-            dp.all_reduce_sum(rt.G)                          # dense gradients: sum over replicas of d(global mean loss)
         l2t = self._l2_table()
 
         def dense_update():
@@ -548,29 +546,36 @@ class BaseModel(nn.Module):
                 rt.ops.reg_l2_sum(table, None, 1.0, table.numel(), sums[1:2], scratch="reduce_table")
             rt.ops.embed_bwd_adam(dX, plan, B, F, E, V, table, m, v, l2t, rt.step_state, None if lazy else sums[1:2], lazy=lazy)
 
-        if sharded:
-            # row gradients to the owners; owner-side segment sum + Adam (collectives stay on the main stream); the dense arena's
-            # regulariser + Adam do not touch the table: side branch
-            if side is not None:
-                main = torch.cuda.current_stream(rt.device)
-                side.wait_stream(main)
-                with torch.cuda.stream(side):
-                    dense_update()
+        def fork_side():
+            # The embedding backward goes to the side stream.  When the program marked its input gradient as final (PLE computes the
+            # level-0 input gradient before that layer's bias / weight gradients) it starts there, under the remaining tensor-bound
+            # GEMMs; otherwise after the whole backward.
+            main = torch.cuda.current_stream(rt.device)
+            if dx_event is not None:
+                side.wait_event(dx_event)
             else:
+                side.wait_stream(main)
+
+        if sharded:
+            # row gradients to the owners (all-to-all), owner-side segment sum + Adam over the owner's rows: on the side stream from
+            # the moment dX is final, so the exchange runs under the rest of the dense backward; the dense gradients' all-reduce and
+            # the dense arena's regulariser + Adam follow on the main stream.  (Host issue order = order on the process group's
+            # communicator: the row exchange first.)
+            if side is not None:
+                fork_side()
+                with torch.cuda.stream(side):
+                    dp.embed_backward(ws, dX, B, l2t, sums[1:2])
+                dp.all_reduce_sum(rt.G)                      # dense gradients: sum over replicas of d(global mean loss)
                 dense_update()
-            dp.embed_backward(ws, dX, B, l2t, sums[1:2])
+            else:
+                dp.all_reduce_sum(rt.G)
+                dense_update()
+                dp.embed_backward(ws, dX, B, l2t, sums[1:2])
         else:
             if dp is not None:
                 raise NotImplementedError("cdcmdr: data-parallel replicas need the row-sharded table (shard_embedding=True)")
             if side is not None:
-                # The embedding backward (segment sums + the HBM-bound sweep over table / m / v) goes to the side stream behind
-                # the plan.  When the program marked its input gradient as final (PLE level 0 computes it before that layer's bias
-                # / weight gradients) it starts there, under the remaining tensor-bound GEMMs; otherwise after the whole backward.
-                main = torch.cuda.current_stream(rt.device)
-                if dx_event is not None:
-                    side.wait_event(dx_event)
-                else:
-                    side.wait_stream(main)
+                fork_side()
                 with torch.cuda.stream(side):
                     table_update()
                 dense_update()

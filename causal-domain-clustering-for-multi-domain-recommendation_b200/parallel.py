@@ -17,6 +17,8 @@ produce exactly what the reference produces on the concatenated N*B-row batch (S
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -45,6 +47,33 @@ def field_runs(ranges):
     return runs
 
 
+class PeerReduce:
+    """The step's small all-reduces (cross-replica BatchNorm sums, loss sums: a few KB of doubles each, all on the critical path)
+    as ONE kernel over NVLink peer memory (cdcmdr_peer_allreduce_f64, csrc/peer.cu) instead of an NCCL call apiece.  torch's
+    symmetric-memory allocator only provides the buffer and its peer mappings (plumbing)."""
+    MAX_N = 4096
+
+    def __init__(self, group, device, lib):
+        import torch.distributed._symmetric_memory as symm
+        self.lib, self.world, self.rank = lib, dist.get_world_size(group), dist.get_rank(group)
+        nbytes = int(lib.peer_allreduce_bytes(self.world, self.MAX_N))
+        self.buf = symm.empty(nbytes, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group.group_name)
+        self.ptrs = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=device)
+        self.seq = torch.zeros(1, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                    # nobody signals into a buffer its owner has not zeroed yet
+
+    def usable(self, t: torch.Tensor) -> bool:
+        return t.dtype == torch.float64 and t.is_contiguous() and 0 < t.numel() <= self.MAX_N and t.device == self.buf.device
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        self.lib.peer_allreduce_f64(self.ptrs.data_ptr(), self.rank, self.world, t.data_ptr(), t.data_ptr(), t.numel(), self.MAX_N,
+                                    self.seq.data_ptr(), stream)
+
+
 class DataParallel:
     def __init__(self, model, group=None, shard_embedding=True):
         if not dist.is_initialized():
@@ -66,6 +95,15 @@ class DataParallel:
         self.row0, self.row1 = self.row_range[self.rank]
         self._dev_state = None
         self._moments = None
+        self.peer = None
+        dev = emb.embedding_dict.weight.device
+        if dev.type == "cuda" and self.world > 1 and os.environ.get("CDCMDR_PEER", "1") != "0":
+            try:
+                self.peer = PeerReduce(self.group, dev, model._rt.ops.lib)
+            except Exception as exc:                           # no peer access between these devices: NCCL carries everything
+                import warnings
+                warnings.warn(f"cdcmdr: NVLink peer all-reduce unavailable ({exc!r}); small all-reduces go through NCCL")
+                self.peer = None
         model._rt.dp = self
         model._dp = self
         if self.shard:
@@ -83,6 +121,9 @@ class DataParallel:
         return B * self.world
 
     def all_reduce_sum(self, t: torch.Tensor):
+        if self.peer is not None and self.peer.usable(t):
+            self.peer.all_reduce_sum(t)
+            return
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def _all_to_all(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits):
@@ -170,11 +211,26 @@ class DataParallel:
         ops, N, E, F = rt.ops, self.world, self.E, self.F
         nf_me = self.f1 - self.f0
         st = self._state(dX.t.device)
-        gsend = ws.get("dp.grad_send", (B * F * E,), torch.float32)
-        for (f0, n, cnt) in self._range_runs():
-            ops.copy2d_batched(dX.ptr + 4 * f0 * E, n * E, dX.ld, gsend.data_ptr() + 4 * B * f0 * E, B * n * E, n * E, cnt, B, n * E, 4)
+        # On the tensor-core path the row gradients travel as bf16 (half the bytes of the largest exchange of the step; the owner
+        # widens them back for the fp32 segment sums) - the same rounding the activations of that path carry anyway.
+        g16 = rt.bf16 and os.environ.get("CDCMDR_GRAD_EXCHANGE", "bf16") == "bf16"
+        gdt = torch.bfloat16 if g16 else torch.float32
+        gsend = ws.get("dp.grad_send16" if g16 else "dp.grad_send", (B * F * E,), gdt)
+        if g16:
+            for (f0, f1) in self.ranges:                      # owner o's block [B, n*E] at element offset B*f0*E, rounded on the way
+                if f1 > f0:
+                    ops.cast_f32_bf16(Mat(dX.t, dX.off + f0 * E, dX.ld), Mat(gsend, B * f0 * E, (f1 - f0) * E), B, (f1 - f0) * E)
+        else:
+            for (f0, n, cnt) in self._range_runs():
+                ops.copy2d_batched(dX.ptr + 4 * f0 * E, n * E, dX.ld, gsend.data_ptr() + 4 * B * f0 * E, B * n * E, n * E, cnt, B, n * E, 4)
         grecv = ws.get("dp.grad_recv", (N * B * max(nf_me, 1) * E,), torch.float32)
-        self._all_to_all(grecv[:N * B * nf_me * E], gsend[:B * F * E], [B * nf_me * E] * N, [B * n * E for n in self.nf])
+        if g16:
+            grecv16 = ws.get("dp.grad_recv16", (N * B * max(nf_me, 1) * E,), torch.bfloat16)
+            self._all_to_all(grecv16[:N * B * nf_me * E], gsend[:B * F * E], [B * nf_me * E] * N, [B * n * E for n in self.nf])
+            if nf_me:
+                ops.cast_bf16_f32(Mat(grecv16, 0, nf_me * E), Mat(grecv, 0, nf_me * E), N * B, nf_me * E)
+        else:
+            self._all_to_all(grecv[:N * B * nf_me * E], gsend[:B * F * E], [B * nf_me * E] * N, [B * n * E for n in self.nf])
         if not nf_me:
             sumsq_out.zero_()
             return

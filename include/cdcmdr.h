@@ -408,6 +408,19 @@ int cdcmdr_attn_pool_fwd_bf16(const uint16_t* z, const float* w, float* lin, int
 int cdcmdr_attn_pool_bwd_bf16(const uint16_t* z, const float* w, const float* dlin, int64_t ld_dlin, uint16_t* dz, float* dw,
                               int64_t B, int64_t n, void* scratch, cdcmdr_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------
+ * (e) multi-GPU: small all-reduce over NVLink peer memory (cross-replica BatchNorm statistics - the per-feature
+ *     (sum, sum of squares) between cdcmdr_bn_*_stats and cdcmdr_bn_*_apply - and the per-rank loss sums; the reference is a
+ *     single-device program, layer.py:187 / run.py:484).  peer_bufs: DEVICE array of `world` pointers, entry r = rank r's symmetric
+ *     buffer of cdcmdr_peer_allreduce_bytes(world, max_n) bytes, zero-initialised before the first call, mapped into this process
+ *     (the host side uses torch's symmetric-memory allocator for the mapping).  out[i] = sum over ranks (in rank order, identical
+ *     on every rank) of in[i], i < n <= max_n.  seq: device uint64, zero-initialised, private to this rank; every rank must issue
+ *     the same sequence of calls.  One kernel, no host synchronisation, CUDA-graph capturable.
+ * ------------------------------------------------------------------------------------------- */
+size_t cdcmdr_peer_allreduce_bytes(int world, int64_t max_n);
+int cdcmdr_peer_allreduce_f64(double* const* peer_bufs, int rank, int world, const double* in, double* out, int64_t n,
+                              int64_t max_n, uint64_t* seq, cdcmdr_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

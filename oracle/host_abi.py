@@ -857,3 +857,13 @@ class HostABI:
         _mat(dz, B, n, n, 1, np.uint16)[...] = f32_to_bf16(np.where(zz > 0, g[:, None] * ww[None, :], F32(0)).astype(np.float32)).reshape(B, n)
         _arr(dw, n, np.float32)[:n] = (g.astype(np.float64)[:, None] * np.maximum(zz, 0).astype(np.float64)).sum(axis=0).astype(np.float32)
         return 0
+
+    # ---- (e) peer-memory all-reduce: needs NVLink peer mappings between processes; the CPU tests exchange through gloo instead
+    def peer_allreduce_bytes(self, world, max_n):
+        return 2 * world * max_n * 8 + 2 * world * 8
+
+    def peer_allreduce_f64(self, peer_bufs, rank, world, inp, out, n, max_n, seq, s):
+        if world != 1:
+            raise NotImplementedError("the host emulator has no peer memory: multi-rank CPU tests use torch.distributed (gloo)")
+        _arr(out, n, np.float64)[:n] = _arr(inp, n, np.float64)[:n]
+        return 0
