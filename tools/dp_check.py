@@ -41,7 +41,7 @@ for _ in range(3):
     out = model.train_step(xt, yt, opt, mode="split", domain_i=7)
     losses.append(model.step_losses(out))
 pred = out["pred"].clone()
-dp.gather_table()
+sd = model.state_dict()                      # collective under the sharded table: every rank calls it (the hook gathers the owners' rows)
 torch.cuda.synchronize()
 ok = True
 if rank == 0:
@@ -51,7 +51,7 @@ if rank == 0:
         rout = ref.train_step(torch.from_numpy(xg).to(dev), torch.from_numpy(yg).to(dev), ropt, mode="split", domain_i=7)
         rl.append(ref.step_losses(rout))
     dpred = float((rout["pred"][lo:hi] - pred).abs().max())
-    sd, rsd = model.state_dict(), ref.state_dict()
+    rsd = ref.state_dict()
     worst = max(((float((sd[k].float() - rsd[k].float()).abs().max()), k) for k in sd if sd[k].dtype.is_floating_point), key=lambda t: t[0])
     # losses agree to fp32 rounding; predictions after 3 Adam steps carry the +-lr noise of the zero-gradient pre-BatchNorm biases
     tol = 2e-5 if Bn.Cfg.cdcmdr_precision == "fp32" else 2e-2
