@@ -26,6 +26,10 @@ import torch.distributed as dist
 from .core import Mat
 
 
+# timing probes (never set in production): comma-separated subset of {small, dense, a2a_ids, a2a_rows} switches those exchanges off
+_ABLATE = set(filter(None, os.environ.get("CDCMDR_DP_ABLATE", "").split(",")))
+
+
 def split_fields(n_fields: int, world: int):
     """Contiguous field ranges [(f0, f1)] per rank, sizes differing by at most one."""
     cuts = [(r * n_fields) // world for r in range(world + 1)]
@@ -121,12 +125,16 @@ class DataParallel:
         return B * self.world
 
     def all_reduce_sum(self, t: torch.Tensor):
+        if _ABLATE and (("small" in _ABLATE and t.numel() <= 4096) or ("dense" in _ABLATE and t.numel() > 4096)):
+            return                                             # timing probe only (tools/dp_ablate.sh): results are wrong
         if self.peer is not None and self.peer.usable(t):
             self.peer.all_reduce_sum(t)
             return
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def _all_to_all(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits):
+        if _ABLATE and (("a2a_ids" in _ABLATE and out.dtype == torch.int32) or ("a2a_rows" in _ABLATE and out.dtype != torch.int32)):
+            return                                             # timing probe only
         if out.device.type == "cuda":
             dist.all_to_all_single(out, inp, out_splits, in_splits, group=self.group)
             return
