@@ -54,6 +54,14 @@ class GemmBf16(C.Structure):
                 ("cross_x0", P), ("cross_x", P), ("ld_cross", I64)]
 
 
+class PleChain(C.Structure):
+    _fields_ = [("X", P), ("ldx", I64), ("B", I64), ("K0", I32),
+                ("W0", P), ("b0", P), ("W1", P), ("b1", P),
+                ("nE", I32), ("d0", I32), ("d1", I32), ("n_g", I32),
+                ("A0", P), ("lda0", I64), ("H", P), ("ldh", I64), ("Lg", P), ("ldg", I64),
+                ("drop_p", F32), ("seed_dev", P), ("salt0", U32), ("salt1", U32)]
+
+
 class MixDesc(C.Structure):
     _fields_ = [("n_gates", I32), ("n_experts", I32), ("h", I32), ("max_sel", I32),
                 ("gate_col", P), ("gate_n", P), ("gate_sel", P), ("n_pairs", I32)]
@@ -136,6 +144,8 @@ SIGNATURES = {
     "cdcmdr_attn_pool_fwd": (INT, [P, P, P, I64, INT, I64, I64, P]),
     "cdcmdr_attn_pool_scratch_bytes": (C.c_size_t, [I64, I64]),
     "cdcmdr_attn_pool_bwd": (INT, [P, P, P, I64, P, P, I64, I64, P, P]),
+    "cdcmdr_ple_chain_ok": (INT, [I32, I32, I32, I32]),
+    "cdcmdr_ple_chain_fwd": (INT, [C.POINTER(PleChain), P]),
     "cdcmdr_peer_allreduce_bytes": (SZ, [INT, I64]),
     "cdcmdr_peer_allreduce_f64": (INT, [P, INT, INT, P, P, I64, I64, P, P]),
     "cdcmdr_attn_fwd_bf16": (INT, [P, I64, P, I64, I64, INT, INT, INT, F32, F32, P, U32, P]),
@@ -145,7 +155,7 @@ SIGNATURES = {
 }
 
 # entry points that return a status code (everything that launches work)
-_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is INT and k not in ("cdcmdr_version", "cdcmdr_gemm_bf16_tc_splits", "cdcmdr_gemm_bf16_tc_mode")}
+_STATUS = {k for k, (r, _) in SIGNATURES.items() if r is INT and k not in ("cdcmdr_version", "cdcmdr_gemm_bf16_tc_splits", "cdcmdr_gemm_bf16_tc_mode", "cdcmdr_ple_chain_ok")}
 
 
 class CdcmdrError(RuntimeError):

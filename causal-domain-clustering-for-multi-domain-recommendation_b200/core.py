@@ -12,7 +12,7 @@ from dataclasses import dataclass
 import torch
 
 from . import _lib
-from ._lib import BnDesc, GemmBf16, GemmF32, MixDesc
+from ._lib import BnDesc, GemmBf16, GemmF32, MixDesc, PleChain
 
 
 def _addr(t: torch.Tensor, off: int = 0) -> int:
@@ -286,6 +286,19 @@ class Ops:
         self.lib.gemm_bf16_tc(C.byref(d), self.stream)
         if split > 1:
             self.lib.splitk_reduce(part, stride, split, out_aux, 1, stride, stride, stride, 1 if accumulate else 0, self.stream)
+
+    def ple_chain_ok(self, K0, d0, d1, n_g) -> bool:
+        return bool(self.lib.ple_chain_ok(int(K0), int(d0), int(d1), int(n_g)))
+
+    def ple_chain_fwd(self, X: Mat, B, K0, W0_addr, b0_addr, W1_addr, b1_addr, nE, d0, d1, n_g, A0: Mat | None, H: Mat, Lg: Mat | None,
+                      drop_p=0.0, seed_ptr=None, salt0=0, salt1=0):
+        """First CGC level of PLE in one launch (cdcmdr_ple_chain_fwd): expert layers 0 -> 1 chained through shared memory plus the
+        gate / wide-linear logits.  A0 None: inference, the [B, nE*d0] activation is never written."""
+        d = PleChain(X.ptr, X.ld, B, K0, W0_addr, b0_addr, W1_addr, b1_addr, nE, d0, d1, n_g,
+                     A0.ptr if A0 is not None else None, A0.ld if A0 is not None else 0, H.ptr, H.ld,
+                     Lg.ptr if Lg is not None else None, Lg.ld if Lg is not None else 0,
+                     drop_p, seed_ptr if drop_p > 0 else None, salt0, salt1)
+        self.lib.ple_chain_fwd(C.byref(d), self.stream)
 
     def wgrad_with_bias_tc(self, dY: Mat, X: Mat, K, M, B, gW_addr, gb_addr):
         """dW[m, k] = sum_b dY[b, m] * X[b, k] (-> gW_addr, [M, K] fp32) and db[m] = sum_b dY[b, m] (-> gb_addr) from ONE product:

@@ -152,6 +152,7 @@ class BaseModel(nn.Module):
         self.embedding_update = "dense_exact"      # or "sparse_lazy" (documented deviation)
         self.use_atten = False
         self._att = None
+        self._keep_acts = True                     # False only inside a no-grad forward: activations no backward will read may be skipped
 
     def build_atten(self, config, dropout):
         """layer.py:58-69 (config.use_atten): parameter holders of the field self-attention block; computed by atten.AttnBlock."""
@@ -433,7 +434,11 @@ class BaseModel(nn.Module):
             params = [p for _, p in self._autograd_params()]
             if any(p.requires_grad for p in params):
                 return _ForwardFn.apply(self, x, kw, *params)
-        return self._engine_forward(x, train=self.training, **kw).clone()
+        self._keep_acts = False                     # pure inference: nothing will differentiate this forward
+        try:
+            return self._engine_forward(x, train=self.training, **kw).clone()
+        finally:
+            self._keep_acts = True
 
     # ---------------------------------------------------------------- regulariser (layer.py:96-112)
     def _reg_value(self):

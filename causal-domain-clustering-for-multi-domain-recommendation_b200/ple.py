@@ -143,6 +143,10 @@ class PLE(BaseModel):
             lv.fused_bwd = (l == 0 and lv.experts.can_fuse_tail() and
                             rt.o(f"cgc{l}.gW") == rt.o(self._level_names[l]["W"][0]) + nE * d0 * lv.K and
                             rt.o(f"cgc{l}.gb") == rt.o(self._level_names[l]["b"][0]) + nE * d0)
+            # level 0 on the tensor-core path: expert layers 0 -> 1 and the gate logits in ONE launch (cdcmdr_ple_chain_fwd)
+            lv.chain = bool(l == 0 and rt.bf16 and lv.fused_bwd and len(self.expert_dims[0]) == 2 and
+                            rt.ops.ple_chain_ok(lv.K, self.expert_dims[0][0], self.expert_dims[0][1], lv.n_gcols) and
+                            __import__("os").environ.get("CDCMDR_PLE_CHAIN", "1") != "0")
             if lv.fused_bwd:
                 lv.experts.tail0 = lv.n_gcols
                 if rt.bf16 and rt.dp is None and self._att is None:
@@ -206,8 +210,26 @@ class PLE(BaseModel):
         rt = self._rt
         xin = X
         for l, lv in enumerate(self._levels):
-            H = lv.experts.fwd(ws, xin, B, train)
             Lg = ws.mat(f"cgc{l}.logits", B, lv.n_gcols)
+            if lv.chain and xin.is_bf16:
+                # experts' layer 0 -> layer 1 chained in-kernel, gate / wide-linear logits from the same resident X tile.  The
+                # [B, nE*d0] layer-0 activation is written only when a backward will read it.
+                ex = lv.experts
+                d0, d1 = ex.dims
+                drop = rt.dropout if train else 0.0
+                A0 = ex._act(ws, 0, B) if self._keep_acts else None
+                H = ex._act(ws, 1, B)
+                names = self._level_names[l]
+                rt.ops.ple_chain_fwd(xin, B, lv.K, rt.Wb.data_ptr() + 2 * rt.o(names["W"][0]), rt.w(names["b"][0]),
+                                     rt.Wb.data_ptr() + 2 * rt.o(names["W"][1]), rt.w(names["b"][1]), ex.G, d0, d1, lv.n_gcols,
+                                     A0, H, Lg, drop_p=drop, seed_ptr=rt.seed_ptr if drop > 0 else None, salt0=ex.salts[0],
+                                     salt1=ex.salts[1])
+                out = ws.mat(f"cgc{l}.out", B, lv.n_gates * lv.h, rt.act_dtype)
+                probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
+                rt.ops.gate_mix_fwd(lv.desc, H, Lg, out, probs, B)
+                xin = out
+                continue
+            H = lv.experts.fwd(ws, xin, B, train)
             if l > 0:
                 self._pack_gates(l, lv)
                 rt.lin_fwd(xin, lv.n_in * lv.K, rt.o(f"cgc{l}.Wbd"), lv.n_gcols, rt.o(f"cgc{l}.bbd"), Lg, B)

@@ -409,6 +409,32 @@ int cdcmdr_attn_pool_bwd_bf16(const uint16_t* z, const float* w, const float* dl
                               int64_t B, int64_t n, void* scratch, cdcmdr_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
+ * a5/a6  first CGC level of PLE chained in ONE kernel (ple.py:54,96-124; layer.py:184-190): every expert's
+ *   A0_e = dropout(relu(X W0_e^T + b0_e))   [B, d0]      H_e = dropout(relu(A0_e W1_e^T + b1_e))   [B, d1]
+ * with A0_e handed from the first GEMM's epilogue to the second GEMM through shared memory, plus the gate / wide-linear logits
+ * Lg = X Wg^T + bg (fp32) that read the same X.  bf16 operands, fp32 accumulation in TMEM (tcgen05).
+ *   X  bf16 [B, K0] (pitch ldx);  W0 bf16 [nE*d0 + n_g, K0] row-major: the experts' layer-0 weights followed by the n_g gate rows;
+ *   b0 fp32 [nE*d0 + n_g];  W1 bf16 [nE*d1, d0];  b1 fp32 [nE*d1].
+ *   H  bf16 [B, nE*d1] (pitch ldh), always written.  A0 bf16 [B, nE*d0] (pitch lda0): written for the backward when non-NULL;
+ *   NULL (inference) = the layer-0 activation never leaves the SM.  Lg fp32 [B, n_g] (pitch ldg), required when n_g > 0.
+ *   drop_p > 0: nn.Dropout on both layers (the library's stateless generator, seed *seed_dev, salts salt0 / salt1).
+ * Geometry (cdcmdr_ple_chain_ok): K0 % 8 == 0 and K0 <= 384, d0 in {128, 256}, d1 in {64, 128}, n_g <= 128; bases and pitches
+ * 16-byte aligned.  Other shapes use the per-layer GEMM entry points.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  const uint16_t* X; int64_t ldx; int64_t B; int32_t K0;
+  const uint16_t* W0; const float* b0;
+  const uint16_t* W1; const float* b1;
+  int32_t nE, d0, d1, n_g;
+  uint16_t* A0; int64_t lda0;
+  uint16_t* H; int64_t ldh;
+  float* Lg; int64_t ldg;
+  float drop_p; const uint64_t* seed_dev; uint32_t salt0, salt1;
+} cdcmdr_ple_chain_t;
+int cdcmdr_ple_chain_ok(int32_t K0, int32_t d0, int32_t d1, int32_t n_g);
+int cdcmdr_ple_chain_fwd(const cdcmdr_ple_chain_t* p, cdcmdr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
  * (e) multi-GPU: small all-reduce over NVLink peer memory (cross-replica BatchNorm statistics - the per-feature
  *     (sum, sum of squares) between cdcmdr_bn_*_stats and cdcmdr_bn_*_apply - and the per-rank loss sums; the reference is a
  *     single-device program, layer.py:187 / run.py:484).  peer_bufs: DEVICE array of `world` pointers, entry r = rank r's symmetric

@@ -867,3 +867,32 @@ class HostABI:
             raise NotImplementedError("the host emulator has no peer memory: multi-rank CPU tests use torch.distributed (gloo)")
         _arr(out, n, np.float64)[:n] = _arr(inp, n, np.float64)[:n]
         return 0
+
+    # ---- a5/a6: first CGC level of PLE chained in one kernel (cdcmdr_ple_chain_fwd; ple.py:54,96-124, layer.py:184-190)
+    def ple_chain_ok(self, K0, d0, d1, n_g):
+        return 1 if (K0 >= 8 and K0 % 8 == 0 and -(-K0 // 64) <= 6 and d0 in (128, 256) and d1 in (64, 128) and 0 <= n_g <= 128) else 0
+
+    def ple_chain_fwd(self, ref, s):
+        p = _obj(ref)
+        if p.drop_p > 0:
+            raise NotImplementedError("the emulator does not reproduce the dropout hash; test with dropout=0")
+        B, K0, nE, d0, d1, ng = int(p.B), int(p.K0), int(p.nE), int(p.d0), int(p.d1), int(p.n_g)
+        if B == 0:
+            return 0
+        X = bf16_to_f32(_mat(p.X, B, K0, p.ldx, 1, np.uint16)).astype(np.float64)
+        W0 = bf16_to_f32(_mat(p.W0, nE * d0 + ng, K0, K0, 1, np.uint16)).astype(np.float64)
+        b0 = _arr(p.b0, nE * d0 + ng, np.float32)[:nE * d0 + ng]
+        W1 = bf16_to_f32(_mat(p.W1, nE * d1, d0, d0, 1, np.uint16)).astype(np.float64)
+        b1 = _arr(p.b1, nE * d1, np.float32)[:nE * d1]
+        Z0 = (X @ W0.T).astype(np.float32) + b0[None, :]
+        A0 = f32_to_bf16(np.maximum(Z0[:, :nE * d0], F32(0))).reshape(B, nE * d0)      # the second GEMM reads the bf16-rounded tile
+        if p.A0:
+            _mat(p.A0, B, nE * d0, p.lda0, 1, np.uint16)[...] = A0
+        if ng:
+            _mat(p.Lg, B, ng, p.ldg)[...] = Z0[:, nE * d0:]
+        A0f = bf16_to_f32(A0).astype(np.float64)
+        H = _mat(p.H, B, nE * d1, p.ldh, 1, np.uint16)
+        for e in range(nE):
+            z1 = (A0f[:, e * d0:(e + 1) * d0] @ W1[e * d1:(e + 1) * d1].T).astype(np.float32) + b1[None, e * d1:(e + 1) * d1]
+            H[:, e * d1:(e + 1) * d1] = f32_to_bf16(np.maximum(z1, F32(0))).reshape(B, d1)
+        return 0

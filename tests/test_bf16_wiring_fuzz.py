@@ -92,3 +92,48 @@ def test_bf16_path_wiring_agrees_with_fp32_path(block, emulator):
         assert np.abs(l32 - l16).max() <= 4e-2 * max(1.0, float(np.abs(l32).max())), (what, "eval logits")
         assert abs(res["fp32"][1] - res["bf16"][1]) <= 3e-2 * max(abs(res["fp32"][1]), 1e-3), (what, "first step")
         assert abs(res["fp32"][2] - res["bf16"][2]) <= 4e-2 * max(abs(res["fp32"][2]), 1e-3), (what, "second step")
+
+
+@pytest.mark.parametrize("dims,ns,nsh", [(((128, 64), (16,)), 2, 1), (((256, 128), (64,)), 1, 2), (((128, 128),), 2, 2)])
+def test_ple_chain_kernel_wiring_matches_per_layer_path(dims, ns, nsh, emulator, monkeypatch):
+    """PLE level 0 through cdcmdr_ple_chain_fwd (expert layers 0 -> 1 chained in one launch + the gate logits; geometry d0 in
+    {128, 256}, d1 in {64, 128}) against the per-layer GEMM launches of the same bf16 path on identical weights, through the
+    emulator: eval predictions (where the chain skips the layer-0 activation store), two fused training steps, and the fp32 path
+    as the outer reference."""
+    rng = np.random.default_rng(7)
+    E, F, T, B = 8, 5, 3, 70
+    fd = rng.integers(3, 12, size=F).astype(np.int64)
+    x = torch.from_numpy(np.stack([rng.integers(0, d, size=B) for d in fd], axis=1).astype(np.int32))
+    y = torch.from_numpy((rng.random((B, 1)) < 0.4).astype(np.int16))
+    g = torch.from_numpy(rng.integers(0, T, size=(B, 1)).astype(np.int64))
+    res, sd = {}, None
+    for tag, prec, chain in (("fp32", "fp32", "1"), ("chain", "bf16", "1"), ("layers", "bf16", "0")):
+        monkeypatch.setenv("CDCMDR_PLE_CHAIN", chain)
+
+        class Cfg:
+            use_atten = False; use_dcn = False; cdcmdr_precision = prec
+        torch.manual_seed(3)
+        m = cm.PLE(fd, E, T, ns, nsh, dims, (16, 8), dropout=0.0, config=Cfg(), **L2)
+        if sd is None:
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+        else:
+            m.load_state_dict(sd, strict=True)
+        assert m._levels[0].chain == (tag == "chain")
+        m.eval()
+        with torch.no_grad():
+            pe = m(x).numpy().copy()
+        m.train()
+        opt = cm.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+        b1 = m.step_losses(m.train_step(x, y, opt, mode="gather", sel=g))[1]
+        b2 = m.step_losses(m.train_step(x, y, opt, mode="gather", sel=g))[1]
+        w = m.state_dict()["cgc_layers.0.experts_specific.0.layers.3.weight"].numpy().copy()
+        res[tag] = (pe, b1, b2, w)
+    logit = lambda p: np.log(np.clip(p, 1e-7, 1 - 1e-7)) - np.log1p(-np.clip(p, 1e-7, 1 - 1e-7))   # noqa: E731
+    lc, ll, l32 = (logit(res[k][0].astype(np.float64)) for k in ("chain", "layers", "fp32"))
+    scale = max(1.0, float(np.abs(l32).max()))
+    assert np.abs(lc - ll).max() <= 5e-3 * scale                 # same bf16 roundings, different accumulation order
+    assert np.abs(lc - l32).max() <= 4e-2 * scale
+    for i in (1, 2):
+        assert abs(res["chain"][i] - res["layers"][i]) <= 5e-3 * abs(res["layers"][i])
+        assert abs(res["chain"][i] - res["fp32"][i]) <= 4e-2 * abs(res["fp32"][i])
+    assert np.abs(res["chain"][3] - res["layers"][3]).max() <= 2.1e-3    # two Adam steps: +-lr sign noise at most

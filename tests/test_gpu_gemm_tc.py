@@ -194,3 +194,83 @@ def test_gemm_bf16_tc_cross_epilogue(M, D, tc_mode):
     b = (gpu[1].view(np.uint16).astype(np.uint32) << 16).view(np.float32)
     scale = float(np.abs(a).max())
     assert float(np.abs(a - b).max()) <= 2 ** -7 * scale
+
+
+CHAIN_CASES = {
+    # name: B, K0, nE, d0, d1, n_g, store_a0
+    "c4_shape": (1000, 368, 10, 256, 128, 27, True),
+    "c4_inference": (1000, 368, 10, 256, 128, 27, False),
+    "small_units": (300, 64, 3, 128, 64, 0, True),
+    "one_expert_tail_rows": (129, 40, 1, 256, 64, 5, True),
+    "many_tiles": (128 * 150 + 17, 128, 2, 128, 128, 9, True),
+    "wide_gates": (260, 256, 4, 256, 128, 100, False),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CHAIN_CASES))
+def test_ple_chain_fwd(name):
+    """cdcmdr_ple_chain_fwd (PLE level 0: expert layers 0 -> 1 chained through shared memory + gate logits in one tcgen05 kernel)
+    against the host restatement on identical bf16 operands: layer-0 activation and expert outputs within one bf16 ulp of the
+    tensor scale, logits 3e-5."""
+    B, K0, nE, d0, d1, ng, keep_a0 = CHAIN_CASES[name]
+
+    def fn(lib, e):
+        b16 = lambda a: e.put(f32_to_bf16(a.astype(np.float32)).reshape(a.shape).view(np.int16))   # noqa: E731
+        ldx = K0 + 8
+        X = b16(e.rng.standard_normal((B, ldx)))
+        W0 = b16(e.rng.standard_normal((nE * d0 + ng, K0)) / np.sqrt(K0))
+        W1 = b16(e.rng.standard_normal((nE * d1, d0)) / np.sqrt(d0))
+        b0, b1 = e.f32(nE * d0 + ng, scale=0.3), e.f32(nE * d1, scale=0.3)
+        A0 = e.zeros(B, nE * d0, dtype=torch.int16)
+        H = e.zeros(B, nE * d1 + 8, dtype=torch.int16)
+        Lg = e.zeros(B, max(ng, 1) + 3)
+        d = L.PleChain(X.data_ptr(), ldx, B, K0, W0.data_ptr(), b0.data_ptr(), W1.data_ptr(), b1.data_ptr(), nE, d0, d1, ng,
+                       A0.data_ptr() if keep_a0 else None, nE * d0, H.data_ptr(), nE * d1 + 8, Lg.data_ptr() if ng else None, max(ng, 1) + 3,
+                       0.0, None, 0, 0)
+        lib.ple_chain_fwd(C.byref(d), 0)
+        return [A0, H, Lg]
+    cpu, gpu = Env(31).run(fn)
+    for i, what in ((0, "A0"), (1, "H")):
+        a = (cpu[i].view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+        b = (gpu[i].view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+        if what == "A0" and not keep_a0:
+            assert not b.any()                                     # inference: the layer-0 activation is never written
+            continue
+        scale = max(float(np.abs(a).max()), 1e-30)
+        assert float(np.abs(a - b).max()) <= 2 ** -7 * scale, (name, what, float(np.abs(a - b).max()), scale)
+        assert float((np.abs(a - b) > 2 ** -8 * scale).mean()) < 0.02, (name, what)
+    if ng:
+        check(cpu[2], gpu[2], tol=3e-5, what=f"{name} logits")
+
+
+def test_ple_chain_dropout_statistics():
+    """nn.Dropout on both chained layers: with X = 0 and positive biases every kept entry equals bias/(1-p); keep rates, the
+    1/(1-p) scale (layer 1 sees the dropped layer-0 tile), bit-repeatability and salt dependence."""
+    lib = cm._lib.load()
+    dev = torch.device("cuda")
+    B, K0, nE, d0, d1, p = 2048, 64, 2, 256, 128, 0.25
+    X = torch.zeros(B, K0, dtype=torch.bfloat16, device=dev)
+    W0 = torch.zeros(nE * d0, K0, dtype=torch.bfloat16, device=dev)
+    W1 = torch.zeros(nE * d1, d0, dtype=torch.bfloat16, device=dev)
+    b0, b1 = torch.ones(nE * d0, device=dev), torch.ones(nE * d1, device=dev)
+    st = torch.zeros(48, dtype=torch.uint8, device=dev)
+    lib.step_state_init(st.data_ptr(), 3, 0)
+    lib.step_tick(st.data_ptr(), 1e-3, 0.9, 0.99, 1e-8, 0.0, 2000, 0)
+
+    def run(salt):
+        A0 = torch.zeros(B, nE * d0, dtype=torch.bfloat16, device=dev)
+        H = torch.zeros(B, nE * d1, dtype=torch.bfloat16, device=dev)
+        d = L.PleChain(X.data_ptr(), K0, B, K0, W0.data_ptr(), b0.data_ptr(), W1.data_ptr(), b1.data_ptr(), nE, d0, d1, 0,
+                       A0.data_ptr(), nE * d0, H.data_ptr(), nE * d1, None, 0, p, st.data_ptr() + 8, salt, salt + 1)
+        lib.ple_chain_fwd(C.byref(d), 0)
+        torch.cuda.synchronize()
+        return A0.float().cpu().numpy(), H.float().cpu().numpy()
+    (a, h), (a2, h2), (a3, h3) = run(5), run(5), run(9)
+    assert np.array_equal(a, a2) and np.array_equal(h, h2)
+    for t in (a, h):
+        vals = set(np.unique(t).tolist())
+        assert vals == {0.0, float(torch.tensor(1 / (1 - p)).bfloat16())}, vals
+        assert abs((t > 0).mean() - (1 - p)) < 4e-3
+        k = (t > 0).astype(np.float64) - (t > 0).mean()
+        assert abs((k[:, 1:] * k[:, :-1]).mean()) < 2e-3 and abs((k[1:] * k[:-1]).mean()) < 2e-3
+    assert 0.30 < ((a > 0) != (a3 > 0)).mean() < 0.45              # independent masks differ on 2p(1-p) = 37.5 %
