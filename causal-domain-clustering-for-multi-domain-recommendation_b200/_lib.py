@@ -92,6 +92,8 @@ SIGNATURES = {
     "cdcmdr_embed_bwd_dense": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P]),
     "cdcmdr_embed_bwd_adam_dense_exact": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P, P]),
     "cdcmdr_embed_bwd_adam_sparse_lazy": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P]),
+    "cdcmdr_embed_bwd_adam_sparse_lazy_reg": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P, P, P]),
+    "cdcmdr_embed_gather_peer": (INT, [P, P, P, I64, P, P, I64, I64, INT, INT, I64, P, P]),
     "cdcmdr_gemm_f32": (INT, [C.POINTER(GemmF32), P]),
     "cdcmdr_gemm_bf16_tc": (INT, [C.POINTER(GemmBf16), P]),
     "cdcmdr_gemm_bf16_tc_splits": (INT, [I64, I32]),

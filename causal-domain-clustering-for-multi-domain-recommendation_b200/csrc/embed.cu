@@ -160,6 +160,38 @@ embed_gather_rows_kernel(const int32_t* __restrict__ x, const int64_t* __restric
   }
 }
 
+// Row-range sharded table over NVLink peer memory (SURVEY 8e / BASELINE configs[4]: 500 M x 64 rows over 8 GPUs): rank r owns rows
+// [r*rows_per, (r+1)*rows_per) of the concatenated table (layer.py:140) in its own HBM and nothing else; every shard is mapped into
+// every process, so the lookup is ONE kernel that reads each row where it lives - no index exchange, no row exchange, no packing,
+// static shapes whatever the id distribution.  E/4 lanes per row (a 256-byte row of E = 64 is one contiguous 16-lane load: remote
+// reads move whole 32-byte sectors), index loaded once per row group and broadcast by shuffle.  Same bytes as a local gather:
+// bit-exact.
+template <int LANES>
+__global__ void __launch_bounds__(256)
+embed_gather_peer_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ offsets, const float* const* __restrict__ shards,
+                         int64_t rows_per, float* __restrict__ out_f32, uint16_t* __restrict__ out_bf16, int64_t ld_bf16, int64_t B,
+                         int F, int E, int64_t V, int* __restrict__ oob) {
+  const int64_t total = B * (int64_t)F * LANES;
+  const int q = threadIdx.x % LANES;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bf = i / LANES;
+    int64_t b, f;
+    split_idx(bf, F, b, f);
+    const int64_t row = (int64_t)__ldg(x + bf) + __ldg(offsets + f);
+    const bool ok = row >= 0 && row < V;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      const int64_t owner = row / rows_per;
+      const float* src = shards[owner] + (row - owner * rows_per) * E + 4 * q;
+      t = *reinterpret_cast<const float4*>(src);            // peer memory: plain (coherent) load, not the read-only path
+    } else if (oob) {
+      *oob = 1;
+    }
+    if (out_f32) *reinterpret_cast<float4*>(out_f32 + bf * E + 4 * q) = t;
+    if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + b * ld_bf16 + f * E + 4 * q) = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+}
+
 // ------------------------------------------------------------------------------------------ plan
 __global__ void plan_keys_kernel(const int32_t* __restrict__ x, const int64_t* __restrict__ offsets, int64_t n, int F,
                                  int64_t V, uint32_t* __restrict__ keys, int32_t* __restrict__ vals) {
@@ -329,7 +361,7 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
   const int64_t rows = DENSE ? V : (int64_t)(*nuniq);
   const int64_t total = rows * lanes;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  double sq = 0.0;
+  double sq = 0.0, sqn = 0.0;                      // sum of squares of the rows before / (lazy mode) after the update
   if (VEC == 4) {
     // The sweep is bound by memory latency (ncu: long-scoreboard stalls, 29 % of DRAM bandwidth at one row per thread in flight):
     // every thread keeps TWO independent rows in flight - all six 128-bit loads are issued before either row is touched.
@@ -362,6 +394,7 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
         sq += (double)w[u].x * w[u].x + (double)w[u].y * w[u].y + (double)w[u].z * w[u].z + (double)w[u].w * w[u].w;
         adam_elem(w[u].x, m[u].x, v[u].x, acc[0], k); adam_elem(w[u].y, m[u].y, v[u].y, acc[1 % VEC], k);
         adam_elem(w[u].z, m[u].z, v[u].z, acc[2 % VEC], k); adam_elem(w[u].w, m[u].w, v[u].w, acc[3 % VEC], k);
+        if (!DENSE) sqn += (double)w[u].x * w[u].x + (double)w[u].y * w[u].y + (double)w[u].z * w[u].z + (double)w[u].w * w[u].w;
         *reinterpret_cast<float4*>(table + o[u]) = w[u]; *reinterpret_cast<float4*>(mom + o[u]) = m[u];
         *reinterpret_cast<float4*>(var + o[u]) = v[u];
       }
@@ -379,11 +412,13 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
       float w = table[o], m = mom[o], v = var[o];
       sq += (double)w * w;
       adam_elem(w, m, v, acc[0], k);
+      if (!DENSE) sqn += (double)w * w;
       table[o] = w; mom[o] = m; var[o] = v;
     }
   }
   if (reg_partials) {                              // deterministic: fixed grid, fixed in-block tree
     __shared__ double red[8];
+    if (!DENSE) sq = sqn - sq;                     // lazy mode: the CHANGE of the touched rows' sum of squares
     sq = warp_sum(sq);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
     __syncthreads();
@@ -456,6 +491,23 @@ __global__ void reg_finalize_kernel(const double* __restrict__ partials, int n, 
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
   __syncthreads();
   if (threadIdx.x == 0) { double s = 0; for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w]; *out = s; }
+}
+
+// lazy regulariser: *before = running total (the value the step's loss uses), then running += sum of the partial deltas
+__global__ void reg_running_kernel(const double* __restrict__ partials, int n, double* __restrict__ running, double* __restrict__ before) {
+  __shared__ double red[32];
+  double t = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) t += partials[i];
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    const double r = *running;
+    if (before) *before = r;
+    *running = r + s;
+  }
 }
 
 static int grid_for(int64_t work, int threads, int max_ctas_per_sm = 8) {
@@ -570,7 +622,7 @@ extern "C" int cdcmdr_embed_bwd_dense(const float* grad_out, int64_t ldg, const 
 
 static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F, int E,
                            int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h, double* reg_sumsq,
-                           cdcmdr_stream_t s) {
+                           cdcmdr_stream_t s, double* reg_running = nullptr) {
   CDC_REQUIRE(E <= E_max, "E exceeds the plan's E_max");
   CDC_REQUIRE(h, "Adam needs the device step state");
   EmbedPlan L = make_layout(B * F, V, E_max);
@@ -580,7 +632,7 @@ static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const
   const int64_t rows = dense ? V : B * F;
   int grid = grid_for(rows * lanes, 256);
   if (grid > kRegPartials) grid = kRegPartials;
-  double* partials = (reg_sumsq && dense) ? at<double>(plan, L.off_reg) : nullptr;
+  double* partials = ((reg_sumsq && dense) || (reg_running && !dense)) ? at<double>(plan, L.off_reg) : nullptr;
 #define ARGS grad_out, ldg, F, E, V, at<int32_t>(plan, L.off_seg_of_row), at<uint32_t>(plan, L.off_uniq), at<int32_t>(plan, L.off_nuniq), \
              at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start), at<int32_t>(plan, L.off_cnt),                                  \
              at<int32_t>(plan, L.off_long_slot), at<float>(plan, L.off_long_sum), table, m, v, h, l2, partials
@@ -599,7 +651,10 @@ static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const
   }
 #undef ARGS
   CDC_LAUNCHED();
-  if (partials) {
+  if (partials && !dense) {
+    reg_running_kernel<<<1, 256, 0, st>>>(partials, grid, reg_running, reg_sumsq);
+    CDC_LAUNCHED();
+  } else if (partials) {
     reg_finalize_kernel<<<1, 256, 0, st>>>(partials, grid, reg_sumsq);
     CDC_LAUNCHED();
   }
@@ -615,4 +670,37 @@ extern "C" int cdcmdr_embed_bwd_adam_sparse_lazy(const float* grad_out, int64_t 
                                                  int E, int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h,
                                                  cdcmdr_stream_t s) {
   return embed_adam_impl(false, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, h, nullptr, s);
+}
+
+// sparse_lazy with an incrementally maintained regulariser: a full-table sum of squares per step is 16 GB of reads per GPU at the
+// 500 M x 64 scale.  reg_running (device double) holds sum(w^2) over the table (the caller initialises it once with
+// cdcmdr_reg_l2_sum); this call writes its value BEFORE the update to reg_before (what the step's loss uses, may be NULL) and adds
+// the change of the touched rows.
+extern "C" int cdcmdr_embed_bwd_adam_sparse_lazy_reg(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
+                                                     int E, int64_t V, float* table, float* m, float* v, float l2,
+                                                     const cdcmdr_step_state_t* h, double* reg_running, double* reg_before,
+                                                     cdcmdr_stream_t s) {
+  CDC_REQUIRE(reg_running, "lazy regulariser: running total missing");
+  return embed_adam_impl(false, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, h, reg_before, s, reg_running);
+}
+
+extern "C" int cdcmdr_embed_gather_peer(const int32_t* x, const int64_t* offsets, const float* const* shards, int64_t rows_per,
+                                        float* out_f32, uint16_t* out_bf16, int64_t ld_bf16, int64_t B, int F, int E, int64_t V,
+                                        int* oob_flag, cdcmdr_stream_t s) {
+  CDC_REQUIRE(B >= 0 && F > 0 && E > 0 && V > 0 && rows_per > 0 && shards, "bad peer gather arguments");
+  if (B == 0) return 0;
+  CDC_REQUIRE(out_f32 || out_bf16, "gather needs an output");
+  CDC_REQUIRE(E % 4 == 0 && (E == 4 || E == 8 || E == 16 || E == 32 || E == 64 || E == 128), "peer gather: embed_dim must be 4..128, a power of two");
+  CDC_REQUIRE((!out_f32 || ((uintptr_t)out_f32 % 16) == 0) && (!out_bf16 || (ld_bf16 % 4 == 0 && ((uintptr_t)out_bf16 % 8) == 0)),
+              "peer gather: misaligned output");
+  const int lanes = E / 4;
+  const int grid = grid_for(B * F * lanes, 256, 16);
+  cudaStream_t st = to_stream(s);
+#define PG(L) embed_gather_peer_kernel<L><<<grid, 256, 0, st>>>(x, offsets, shards, rows_per, out_f32, out_bf16, ld_bf16, B, F, E, V, oob_flag)
+  switch (lanes) {
+    case 1: PG(1); break; case 2: PG(2); break; case 4: PG(4); break; case 8: PG(8); break; case 16: PG(16); break; default: PG(32); break;
+  }
+#undef PG
+  CDC_LAUNCHED();
+  return 0;
 }

@@ -79,6 +79,21 @@ int cdcmdr_embed_bwd_adam_dense_exact(const float* grad_out, int64_t ldg, const 
 int cdcmdr_embed_bwd_adam_sparse_lazy(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
                                       int E, int64_t V, float* table, float* m, float* v, float l2,
                                       const cdcmdr_step_state_t* st, cdcmdr_stream_t s);
+/* sparse_lazy with an incrementally maintained regulariser value (a full sum of squares per step would read the whole shard:
+ * 16 GB per GPU at 500 M x 64 over 8 GPUs).  reg_running (device double): sum(w^2) over the table, initialised once by the caller
+ * (cdcmdr_reg_l2_sum); the call writes its value BEFORE this update to reg_before (what the step's loss uses; may be NULL) and
+ * adds the change of the touched rows (fixed reduction order). */
+int cdcmdr_embed_bwd_adam_sparse_lazy_reg(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
+                                          int E, int64_t V, float* table, float* m, float* v, float l2,
+                                          const cdcmdr_step_state_t* h, double* reg_running, double* reg_before,
+                                          cdcmdr_stream_t s);
+/* a1 over a ROW-RANGE sharded table in NVLink peer memory (BASELINE configs[4]): rank r owns rows
+ * [r*rows_per, (r+1)*rows_per) of the concatenated table; shards = DEVICE array of every rank's shard base pointer (mapped into
+ * this process; the host side uses torch's symmetric-memory allocator for the mapping).  One kernel reads every row where it
+ * lives - no index / row exchange.  x, offsets, outputs as cdcmdr_embed_gather_fwd (global offsets, V = total rows).  Bit-exact. */
+int cdcmdr_embed_gather_peer(const int32_t* x, const int64_t* offsets, const float* const* shards, int64_t rows_per,
+                             float* out_f32, uint16_t* out_bf16, int64_t ld_bf16, int64_t B, int F, int E, int64_t V,
+                             int* oob_flag, cdcmdr_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------
  * a3/a4/a5/a9/a11  nn.Linear / F.linear / torch.matmul call sites      layer.py:119,185,193,275,336
