@@ -45,7 +45,21 @@ struct ChainParams {
   float* Lg; int64_t ldg;
   int32_t store_a0;
   float drop_p; const uint64_t* seed_dev; uint32_t salt0, salt1;
+  unsigned long long* prof;                  // cdcmdr_ple_chain_profile: cycles per pipeline wait, summed over CTAs (NULL = off)
 };
+
+// counters: [0] producer waits for a free weight slot, [1] MMA waits for a free accumulator slot, [2] MMA waits for weights,
+// [3] MMA waits for activation blocks, [4] epilogue warp 0 waits for an accumulator, [5] epilogue warp 0 waits for a free
+// activation block, [6] epilogue warp 0 lifetime, [7] CTAs, [8] MMA warp lifetime, [9] producer lifetime
+// The counters are compiled in only with -DCDCMDR_CHAIN_PROF (tools/probe_chain.py --prof builds that variant): even the untaken
+// `if (prof)` branches around every barrier wait of the MMA warp cost 40 us per launch at the C4 shape.
+#ifdef CDCMDR_CHAIN_PROF
+#define CH_PROF(ptr) (ptr)
+#else
+#define CH_PROF(ptr) ((unsigned long long*)nullptr)
+#endif
+#define CH_T0() const long long ch_t0 = CH_PROF(p.prof) ? clock64() : 0
+#define CH_ADD(i) do { if (CH_PROF(p.prof)) atomicAdd(p.prof + (i), (unsigned long long)(clock64() - ch_t0)); } while (0)
 
 __device__ __forceinline__ void pair_bar_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
@@ -90,13 +104,22 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 
   const int64_t n_tiles = ceil_div(p.B, 128);
   const int nkb = p.num_kb0, nE = p.nE, nU = p.nU, KB1 = p.KB1;
+  // Every CTA walks the experts of a tile in the same cyclic order but STARTS at a different one: all 148 CTAs run in near lockstep,
+  // and without the rotation they all request the same 16 KB weight block (the same 128 L2 lines) at the same moment.
+  const int rot = (int)(blockIdx.x % (unsigned)nE);
+  auto pe = [&](int e) -> int { const int r = e + rot; return r >= nE ? r - nE : r; };
+  // ... and the CTAs that share a starting expert walk the k-blocks of a layer-0 unit from different starting points (the fp32
+  // accumulation order of a row then depends on the CTA that owns its tile - fixed for a given B, bit-repeatable)
+  const int krot = (int)((blockIdx.x / (unsigned)nE) % (unsigned)nkb);
+  auto kbo = [&](int kb) -> int { const int r = kb + krot; return r >= nkb ? r - nkb : r; };
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int ws = 0; uint32_t wph = 0, xph = 0;
+      const long long prod_t0 = CH_PROF(p.prof) ? clock64() : 0;
       auto load_w = [&](const CUtensorMap* map, int32_t col, int32_t row, uint32_t bytes) {
-        mbar_wait(wempty0 + 8 * ws, wph ^ 1);
+        { CH_T0(); mbar_wait(wempty0 + 8 * ws, wph ^ 1); CH_ADD(0); }
         mbar_expect_tx(wfull0 + 8 * ws, bytes);
         tma_load_2d(smem_u32(wr + ws * CH_BLK), map, wfull0 + 8 * ws, col, row);
         if (++ws == CH_W_SLOTS) { ws = 0; wph ^= 1; }
@@ -110,18 +133,19 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
         xph ^= 1;
         if (p.n_g > 0)
-          for (int kb = 0; kb < nkb; ++kb) load_w(&map_wg, kb * 64, nE * p.d0, (uint32_t)p.n_g16 * 128u);
+          for (int kb = 0; kb < nkb; ++kb) load_w(&map_wg, kbo(kb) * 64, nE * p.d0, (uint32_t)p.n_g16 * 128u);
         for (int u = 0; u < nU; ++u)
-          for (int kb = 0; kb < nkb; ++kb) load_w(&map_w0, kb * 64, u * 128, CH_BLK);
+          for (int kb = 0; kb < nkb; ++kb) load_w(&map_w0, kbo(kb) * 64, pe(0) * p.d0 + u * 128, CH_BLK);
         for (int e = 0; e < nE; ++e) {
           if (e + 1 < nE)
-            for (int kb = 0; kb < nkb; ++kb) load_w(&map_w0, kb * 64, (e + 1) * p.d0, CH_BLK);
-          for (int kb = 0; kb < KB1; ++kb) load_w(&map_w1, kb * 64, e * p.d1, (uint32_t)p.d1 * 128u);
+            for (int kb = 0; kb < nkb; ++kb) load_w(&map_w0, kbo(kb) * 64, pe(e + 1) * p.d0, CH_BLK);
+          for (int kb = 0; kb < KB1; ++kb) load_w(&map_w1, kb * 64, pe(e) * p.d1, (uint32_t)p.d1 * 128u);
           if (e + 1 < nE)
             for (int u = 1; u < nU; ++u)
-              for (int kb = 0; kb < nkb; ++kb) load_w(&map_w0, kb * 64, (e + 1) * p.d0 + u * 128, CH_BLK);
+              for (int kb = 0; kb < nkb; ++kb) load_w(&map_w0, kbo(kb) * 64, pe(e + 1) * p.d0 + u * 128, CH_BLK);
         }
       }
+      if (CH_PROF(p.prof)) atomicAdd(p.prof + 9, (unsigned long long)(clock64() - prod_t0));
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
@@ -135,9 +159,10 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     int ws = 0; uint32_t wph = 0, xph = 0;
     uint32_t job = 0, ae = 0;                                      // accumulator-ring position; experts done (parity of the activation blocks)
     uint32_t slot = 0;
+    const long long mma_t0 = CH_PROF(p.prof) ? clock64() : 0;
     auto begin_job = [&]() -> uint32_t {
       slot = job & 3u;
-      mbar_wait(tempty0 + 8 * slot, ((job >> 2) & 1u) ^ 1u);
+      { CH_T0(); mbar_wait(tempty0 + 8 * slot, ((job >> 2) & 1u) ^ 1u); if (lane == 0) CH_ADD(1); }
       tc_fence_after();
       return tmem_base + slot * 128u;
     };
@@ -161,10 +186,11 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     auto x_job = [&](uint32_t idesc, bool last_x_use) {
       const uint32_t d = begin_job();
       for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(xfull0 + 8 * kb, xph);
-        mbar_wait(wfull0 + 8 * ws, wph);
+        const int xb = kbo(kb);
+        mbar_wait(xfull0 + 8 * xb, xph);
+        { CH_T0(); mbar_wait(wfull0 + 8 * ws, wph); if (lane == 0) CH_ADD(2); }
         tc_fence_after();
-        mma_block(d, x_lo0 + (uint32_t)kb * (CH_BLK >> 4), w_lo0 + (uint32_t)ws * (CH_BLK >> 4), idesc, kb == 0, wempty0 + 8 * ws,
+        mma_block(d, x_lo0 + (uint32_t)xb * (CH_BLK >> 4), w_lo0 + (uint32_t)ws * (CH_BLK >> 4), idesc, kb == 0, wempty0 + 8 * ws,
                   (last_x_use && kb == nkb - 1) ? xempty : 0u);
         if (++ws == CH_W_SLOTS) { ws = 0; wph ^= 1; }
       }
@@ -178,8 +204,8 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         {                                                          // M2(e): A = the activation blocks the epilogue wrote
           const uint32_t d = begin_job();
           for (int kb = 0; kb < KB1; ++kb) {
-            mbar_wait(afull0 + 8 * kb, ae & 1u);
-            mbar_wait(wfull0 + 8 * ws, wph);
+            { CH_T0(); mbar_wait(afull0 + 8 * kb, ae & 1u); if (lane == 0) CH_ADD(3); }
+            { CH_T0(); mbar_wait(wfull0 + 8 * ws, wph); if (lane == 0) CH_ADD(2); }
             tc_fence_after();
             mma_block(d, a_lo0 + (uint32_t)kb * (CH_BLK >> 4), w_lo0 + (uint32_t)ws * (CH_BLK >> 4), idesc_m2, kb == 0, wempty0 + 8 * ws,
                       aempty0 + 8 * kb);
@@ -193,6 +219,7 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
       }
       xph ^= 1;
     }
+    if (CH_PROF(p.prof) && lane == 0) atomicAdd(p.prof + 8, (unsigned long long)(clock64() - mma_t0));
   } else {
     // =============================== epilogue (warps 2..17) ===============================
     const int ew = warp - 2;
@@ -209,9 +236,10 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
     uint32_t ejob = 0, ae = 0;
     uint32_t slot = 0;
     bool store_pending = false;
+    const long long epi_t0 = CH_PROF(p.prof) ? clock64() : 0;
     auto wait_job = [&]() -> uint32_t {
       slot = ejob & 3u;
-      mbar_wait(tfull0 + 8 * slot, (ejob >> 2) & 1u);
+      { CH_T0(); mbar_wait(tfull0 + 8 * slot, (ejob >> 2) & 1u); if (ew == 0 && lane == 0) CH_ADD(4); }
       tc_fence_after();
       return tmem_base + ((uint32_t)(q * 32) << 16) + slot * 128u;
     };
@@ -294,7 +322,7 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         tc_ld_wait();
         uint32_t o[16];
         act32(v, p.b0 + gcol, s00, (uint32_t)m, (uint32_t)gcol, o);
-        mbar_wait(aempty0 + 8 * kb, (gi & 1u) ^ 1u);               // the previous expert's layer-1 MMAs have read block kb
+        { CH_T0(); mbar_wait(aempty0 + 8 * kb, (gi & 1u) ^ 1u); if (ew == 0 && lane == 0) CH_ADD(5); }   // the previous expert's layer-1 MMAs have read block kb
         write_block(kb, o, p.store_a0 ? &map_a0 : nullptr, (int32_t)(e * p.d0 + 64 * kb), grow, afull0 + 8 * kb);
         done_job();
       };
@@ -311,16 +339,17 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
         }
         done_job();
       };
-      for (int u = 0; u < nU; ++u) e1(0, u, ae);
+      for (int u = 0; u < nU; ++u) e1(pe(0), u, ae);
       for (int e = 0; e < nE; ++e) {
-        if (e + 1 < nE) e1(e + 1, 0, ae + 1);
-        e2(e);
+        if (e + 1 < nE) e1(pe(e + 1), 0, ae + 1);
+        e2(pe(e));
         ++ae;
         if (e + 1 < nE)
-          for (int u = 1; u < nU; ++u) e1(e + 1, u, ae);
+          for (int u = 1; u < nU; ++u) e1(pe(e + 1), u, ae);
       }
     }
     if (issuer && lane == 0) tma_store_wait_all();
+    if (CH_PROF(p.prof) && ew == 0 && lane == 0) { atomicAdd(p.prof + 6, (unsigned long long)(clock64() - epi_t0)); atomicAdd(p.prof + 7, 1ull); }
   }
   tc_fence_before();
   __syncthreads();
@@ -333,6 +362,12 @@ ple_chain_fwd_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_con
 }  // namespace cdcmdr
 
 using namespace cdcmdr;
+
+static std::atomic<unsigned long long*> g_chain_prof{nullptr};
+extern "C" int cdcmdr_ple_chain_profile(uint64_t* counters16) {
+  g_chain_prof.store(reinterpret_cast<unsigned long long*>(counters16), std::memory_order_relaxed);
+  return 0;
+}
 
 extern "C" int cdcmdr_ple_chain_ok(int32_t K0, int32_t d0, int32_t d1, int32_t n_g) {
   return (K0 >= 8 && K0 % 8 == 0 && ceil_div(K0, 64) <= CH_MAX_KB0 && (d0 == 128 || d0 == 256) && (d1 == 64 || d1 == 128) && n_g >= 0 &&
@@ -355,6 +390,7 @@ extern "C" int cdcmdr_ple_chain_fwd(const cdcmdr_ple_chain_t* c, cdcmdr_stream_t
   q.nU = c->d0 / 128; q.KB1 = c->d0 / 64;
   q.b0 = c->b0; q.b1 = c->b1; q.Lg = c->Lg; q.ldg = c->ldg; q.store_a0 = c->A0 ? 1 : 0;
   q.drop_p = c->drop_p; q.seed_dev = c->seed_dev; q.salt0 = c->salt0; q.salt1 = c->salt1;
+  q.prof = g_chain_prof.load(std::memory_order_relaxed);
   const int64_t w0_rows = (int64_t)c->nE * c->d0 + c->n_g;
   CUtensorMap mx, mw0, mwg, mw1, ma0, mh;
   if (int rc = make_map_sw128(&mx, c->X, c->B, c->K0, c->ldx, 128u)) return rc;

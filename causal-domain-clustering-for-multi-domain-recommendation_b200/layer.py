@@ -30,7 +30,23 @@ class FeaturesEmbedding(nn.Module):
         self.field_num = len(fd)
         self.output_dim0 = self.field_num
         self.embed_dim = embed_dim
-        self.embedding_dict = nn.Embedding(int(fd.sum()), embed_dim)
+        self.total_rows = int(fd.sum())
+        from . import parallel
+        shard = parallel.current_table_shard()
+        if shard is None:
+            self.rows_per, self.shard = self.total_rows, None
+            self.embedding_dict = nn.Embedding(self.total_rows, embed_dim)
+        else:
+            # Row-range sharded table (parallel.sharded_table): this process allocates ONLY its own rows
+            # [rank*rows_per, (rank+1)*rows_per) of the concatenated table - on the target device directly, a 500 M x 64 table never
+            # exists in one piece anywhere.  state_dict() then holds the local shard.
+            rank, world, device = shard
+            self.rows_per = -(-self.total_rows // world)
+            self.shard = (rank, world)
+            self.embedding_dict = nn.Embedding(self.rows_per, embed_dim, device=device)
+            with torch.no_grad():
+                valid = max(0, min(self.rows_per, self.total_rows - rank * self.rows_per))
+                self.embedding_dict.weight[valid:].zero_()       # padding rows past the end of the table
         self.offsets = np.array((0, *np.cumsum(fd)[:-1]), dtype=np.int64)
         self.register_buffer("offsets_dev", torch.from_numpy(self.offsets.copy()), persistent=False)
 

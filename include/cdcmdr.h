@@ -448,6 +448,12 @@ typedef struct {
 } cdcmdr_ple_chain_t;
 int cdcmdr_ple_chain_ok(int32_t K0, int32_t d0, int32_t d1, int32_t n_g);
 int cdcmdr_ple_chain_fwd(const cdcmdr_ple_chain_t* p, cdcmdr_stream_t s);
+/* Diagnostics: while `counters16` (device, 16 x uint64, zeroed by the caller) is installed every cdcmdr_ple_chain_fwd launch adds
+ * SM cycles spent per pipeline wait, summed over CTAs: [0] producer waiting for a free weight slot, [1] MMA issuer waiting for a
+ * free accumulator slot, [2] for weights, [3] for activation blocks, [4] epilogue warp 0 waiting for an accumulator, [5] for a
+ * free activation block, [6] epilogue warp 0 lifetime, [7] CTAs, [8] MMA warp lifetime, [9] producer lifetime.  NULL = off.  The counters exist only in a
+ * library built with -DCDCMDR_CHAIN_PROF (they cost ~15 % of the kernel); otherwise the call is accepted and nothing is counted. */
+int cdcmdr_ple_chain_profile(uint64_t* counters16);
 
 /* ---------------------------------------------------------------------------------------------
  * (e) multi-GPU: small all-reduce over NVLink peer memory (cross-replica BatchNorm statistics - the per-feature

@@ -183,6 +183,38 @@ class HostABI:
         tab[touched], mm[touched], vv[touched] = w, a, b
         return 0
 
+    def embed_bwd_adam_sparse_lazy_reg(self, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, st, reg_running, reg_before, s):
+        """lazy update + incrementally maintained sum of squares: *reg_before = running ; running += change of the touched rows"""
+        g, touched = self._segment_sums(grad_out, ldg, plan, B, F, E, V)
+        tab, mm, vv = _mat(table, V, E, E), _mat(m, V, E, E), _mat(v, V, E, E)
+        w, a, b = tab[touched], mm[touched], vv[touched]
+        old = np.square(w.astype(np.float64)).sum()
+        self._adam(w, g[touched], a, b, st, F32(2.0) * F32(l2))
+        tab[touched], mm[touched], vv[touched] = w, a, b
+        run = _arr(reg_running, 1, np.float64)
+        if reg_before:
+            _arr(reg_before, 1, np.float64)[0] = run[0]
+        run[0] = run[0] + (np.square(w.astype(np.float64)).sum() - old)
+        return 0
+
+    def embed_gather_peer(self, x, offsets, shards, rows_per, out_f32, out_bf16, ld_bf16, B, F, E, V, oob, s):
+        """cdcmdr_embed_gather_peer: row r lives in shard r // rows_per (host pointers inside this process)"""
+        xs = _mat(x, B, F, F, 1, np.int32)
+        off = _arr(offsets, F, np.int64)
+        idx = xs.astype(np.int64) + off[None, :]
+        ok = (idx >= 0) & (idx < V)
+        n_shard = -(-int(V) // int(rows_per))
+        ptrs = _arr(shards, n_shard, np.int64)
+        full = np.concatenate([_mat(int(ptrs[r]), rows_per, E, E) for r in range(n_shard)], axis=0)
+        rows = np.where(ok[..., None], full[np.clip(idx, 0, V - 1)], F32(0)).reshape(B, F * E)
+        if oob and not ok.all():
+            _arr(oob, 1, np.int32)[0] = 1
+        if out_f32:
+            _mat(out_f32, B, F * E, F * E)[...] = rows
+        if out_bf16:
+            _mat(out_bf16, B, F * E, ld_bf16, 1, np.uint16)[...] = f32_to_bf16(rows).reshape(B, F * E)
+        return 0
+
     # ------------------------------------------------------------------ fp32 GEMM (nn.Linear call sites)
     def gemm_f32(self, ref, s):
         p = _obj(ref)
@@ -871,6 +903,9 @@ class HostABI:
     # ---- a5/a6: first CGC level of PLE chained in one kernel (cdcmdr_ple_chain_fwd; ple.py:54,96-124, layer.py:184-190)
     def ple_chain_ok(self, K0, d0, d1, n_g):
         return 1 if (K0 >= 8 and K0 % 8 == 0 and -(-K0 // 64) <= 6 and d0 in (128, 256) and d1 in (64, 128) and 0 <= n_g <= 128) else 0
+
+    def ple_chain_profile(self, counters):
+        return 0
 
     def ple_chain_fwd(self, ref, s):
         p = _obj(ref)

@@ -56,3 +56,14 @@ for name, train in (("chain_train", True), ("chain_inference", False)):
     us = timed(lambda: chain(train))
     byt = B * (K0 * 2 + nE * d1 * 2 + ng * 4 + (nE * d0 * 2 if train else 0))
     print(json.dumps(dict(name=name, B=B, us=round(us, 1), tflops=round(flops / us / 1e6, 1), hbm_gbs=round(byt / us / 1e3, 1))), flush=True)
+# wait counters of the training form (fractions of the CTA lifetime)
+ctr = torch.zeros(16, dtype=torch.int64, device=dev)
+lib.ple_chain_profile(ctr.data_ptr())
+chain(True)
+torch.cuda.synchronize()
+lib.ple_chain_profile(None)
+c = ctr.cpu().tolist()
+n = max(c[7], 1)
+names = ["producer_wait_slot", "mma_wait_accum", "mma_wait_weights", "mma_wait_act", "epi_wait_accum", "epi_wait_actblock"]
+life = dict(epi=c[6] / n, mma=c[8] / n, producer=c[9] / n)
+print(json.dumps(dict(name="chain_train_waits", cycles_per_cta=life, frac={k: round(c[i] / n / max(life["epi"], 1), 3) for i, k in enumerate(names)})))
