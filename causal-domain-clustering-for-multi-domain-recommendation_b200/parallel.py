@@ -30,6 +30,39 @@ from .core import Mat
 _ABLATE = set(filter(None, os.environ.get("CDCMDR_DP_ABLATE", "").split(",")))
 
 
+# ------------------------------------------------------------------------------------------------ row-range sharded construction
+_TABLE_SHARD = None
+
+
+class sharded_table:
+    """Context manager for CONSTRUCTING a model whose embedding table is row-range sharded (BASELINE configs[4]: 500 M x 64 rows
+    over 8 GPUs = 16 GB of fp32 rows per GPU): inside it FeaturesEmbedding allocates only this rank's rows
+    [rank*rows_per, (rank+1)*rows_per), directly on `device`.
+
+        with cm.parallel.sharded_table(rank, world, device):
+            model = cm.CDC(field_dims, ...)                     # or STAR / PLE / ...
+        model = model.to(device)
+        cm.parallel.attach_data_parallel(model, shard_embedding="rows")
+    """
+
+    def __init__(self, rank, world, device):
+        self.shard = (int(rank), int(world), torch.device(device))
+
+    def __enter__(self):
+        global _TABLE_SHARD
+        self._old, _TABLE_SHARD = _TABLE_SHARD, self.shard
+        return self
+
+    def __exit__(self, *exc):
+        global _TABLE_SHARD
+        _TABLE_SHARD = self._old
+        return False
+
+
+def current_table_shard():
+    return _TABLE_SHARD
+
+
 def split_fields(n_fields: int, world: int):
     """Contiguous field ranges [(f0, f1)] per rank, sizes differing by at most one."""
     cuts = [(r * n_fields) // world for r in range(world + 1)]
@@ -90,7 +123,7 @@ class DataParallel:
         emb = model.embedding
         self.F, self.E = emb.field_num, emb.embed_dim
         off = np.asarray(emb.offsets, dtype=np.int64)
-        V = int(emb.embedding_dict.weight.shape[0])
+        V = int(emb.total_rows)
         self.ranges = split_fields(self.F, self.world)
         self.nf = [f1 - f0 for f0, f1 in self.ranges]
         bounds = np.concatenate([off, [V]])
@@ -266,7 +299,126 @@ class DataParallel:
                 dist.broadcast(w[r0:r1], dist.get_global_rank(self.group, r), group=self.group)
 
 
+class RowRangeParallel(DataParallel):
+    """Data-parallel replicas over a ROW-RANGE sharded table in NVLink peer memory (BASELINE configs[4]).
+
+    Rank r owns rows [r*rows_per, (r+1)*rows_per) of the single concatenated table (layer.py:140) whatever field they belong to -
+    one 400 M-row field is as good as 23 equal ones - together with their Adam moments, and allocates nothing else (the model is
+    built inside `sharded_table`).  Every shard lives in symmetric memory mapped into every process, so
+      forward : ONE gather kernel reads each row where it lives (cdcmdr_embed_gather_peer) - no index exchange, no row exchange,
+                no packing, static shapes whatever the id distribution;
+      backward: the ranks all-gather their indices and bf16 row gradients (NCCL; static sizes); every owner runs the usual
+                sorted-segment plan over ALL N*B samples with offsets shifted by its first row - rows outside its range fall out
+                as the plan's out-of-range sentinel - and applies the touched-row ("sparse_lazy") Adam to its own rows.  The
+                regulariser's table term is maintained incrementally (cdcmdr_embed_bwd_adam_sparse_lazy_reg): a full sum of
+                squares per step would read the whole 16 GB shard.
+    Ordering between ranks: the all-gather separates every rank's forward reads of step i from the owners' updates of step i; the
+    all-reduce of the loss sums that ends every step (after the update joined the main stream) separates the updates from the
+    reads of step i+1.  The dense-exact update (every row, every step: SURVEY G6) is not offered here: 96 GB of sweep per GPU per
+    step at this scale."""
+
+    def __init__(self, model, group=None):
+        emb = model.embedding
+        if emb.shard is None:
+            raise RuntimeError("cdcmdr: build the model inside parallel.sharded_table(rank, world, device) for shard_embedding='rows'")
+        super().__init__(model, group, shard_embedding=True)
+        if emb.shard != (self.rank, self.world):
+            raise RuntimeError(f"cdcmdr: table built as shard {emb.shard}, process is rank {self.rank} of {self.world}")
+        self.shard = True                                        # also for world == 1 (the table then has one shard)
+        self.rows_per, self.V = int(emb.rows_per), int(emb.total_rows)
+        self.row0, self.row1 = self.rank * self.rows_per, min(self.V, (self.rank + 1) * self.rows_per)
+        if hasattr(self, "_sd_hook"):
+            self._sd_hook.remove()                               # state_dict() holds the local shard: nothing to gather
+        model.embedding_update = "sparse_lazy"
+        w = emb.embedding_dict.weight
+        dev = w.device
+        self._running = None
+        self._peer_ptrs = None
+        if dev.type == "cuda":
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty((self.rows_per, self.E), dtype=torch.float32, device=dev)
+            buf.copy_(w.data)
+            w.data = buf                                         # the parameter now lives in symmetric memory
+            self._table_handle = symm.rendezvous(buf, self.group.group_name)
+            self._peer_ptrs = torch.tensor([int(p) for p in self._table_handle.buffer_ptrs], dtype=torch.int64, device=dev)
+            torch.cuda.synchronize(dev)
+            dist.barrier(self.group)
+        off = torch.as_tensor(np.asarray(emb.offsets, dtype=np.int64) - self.row0, device=dev)
+        self._offsets_local = off
+
+    def shard_view(self):
+        return self.model.embedding.embedding_dict.weight.data
+
+    def gather_table(self):
+        return None
+
+    def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False):
+        rt = self.model._rt
+        ops, N, E, F = rt.ops, self.world, self.E, self.F
+        emb = self.model.embedding
+        out32, out16 = (None, X) if rt.bf16 else (X, None)
+        if self._peer_ptrs is not None:
+            ops.lib.embed_gather_peer(x.data_ptr(), emb.offsets_dev.data_ptr(), self._peer_ptrs.data_ptr(), self.rows_per,
+                                      out32.ptr if out32 is not None else None, out16.ptr if out16 is not None else None,
+                                      out16.ld if out16 is not None else 0, B, F, E, self.V, None, ops.stream)
+        else:
+            # CPU test path (gloo, host emulator): no peer memory - assemble the table from the shards and gather locally
+            full = ws.get("dp.full_table", (N * self.rows_per, E), torch.float32)
+            dist.all_gather_into_tensor(full[:N * self.rows_per * E].view(N * self.rows_per, E), self.shard_view().contiguous(),
+                                        group=self.group)
+            ops.embed_gather(x, emb.offsets_dev, full, out32, out16, B, F, E, self.V)
+        # the owners need every rank's indices for the backward: gather them now, plan on the side stream under the model program
+        self._all_ids = ws.get("dp.all_ids", (N * B * F,), torch.int32)
+        self._plan, self._plan_event = None, None
+        if plan_ahead:
+            dist.all_gather_into_tensor(self._all_ids[:N * B * F], x.reshape(-1), group=self.group)
+            side = rt.side_stream()
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(rt.device))
+                with torch.cuda.stream(side):
+                    self._plan = ops.embed_plan(self._all_ids, self._offsets_local, N * B, F, self.rows_per, E)
+                    self._plan_event = side.record_event()
+            else:
+                self._plan = ops.embed_plan(self._all_ids, self._offsets_local, N * B, F, self.rows_per, E)
+        return None
+
+    def embed_backward(self, ws, dX: Mat, B, l2, sumsq_out):
+        rt = self.model._rt
+        ops, N, E, F = rt.ops, self.world, self.E, self.F
+        D = F * E
+        g16 = rt.bf16
+        gall = ws.get("dp.grad_all", (N * B * D,), torch.float32)
+        if g16:
+            gsend = ws.get("dp.grad_send16", (B * D,), torch.bfloat16)
+            ops.cast_f32_bf16(dX, Mat(gsend, 0, D), B, D)
+            gall16 = ws.get("dp.grad_all16", (N * B * D,), torch.bfloat16)
+            dist.all_gather_into_tensor(gall16[:N * B * D], gsend[:B * D], group=self.group)
+            ops.cast_bf16_f32(Mat(gall16, 0, D), Mat(gall, 0, D), N * B, D)
+        else:
+            gsend = ws.get("dp.grad_send", (B * D,), torch.float32)
+            ops.copy2d(dX.ptr, dX.ld, gsend.data_ptr(), D, B, D, 4)
+            dist.all_gather_into_tensor(gall[:N * B * D], gsend[:B * D], group=self.group)
+        plan = self._plan
+        if plan is None:
+            raise RuntimeError("cdcmdr: the row-range table trains through model.train_step (the plan is built with the forward)")
+        if self._plan_event is not None:
+            torch.cuda.current_stream(rt.device).wait_event(self._plan_event)
+        self._plan, self._plan_event = None, None
+        shard = self.shard_view()
+        m, v = self.moments()
+        if self._running is None:                                # sum of squares of the shard, once; maintained incrementally after
+            self._running = torch.zeros(1, dtype=torch.float64, device=shard.device)
+            ops.reg_l2_sum(shard, None, 1.0, shard.numel(), self._running, scratch="reduce_table")
+        ops.lib.embed_bwd_adam_sparse_lazy_reg(gall.data_ptr(), D, plan.data_ptr(), E, N * B, F, E, self.rows_per, shard.data_ptr(),
+                                               m.data_ptr(), v.data_ptr(), l2, rt.step_state.data_ptr(), self._running.data_ptr(),
+                                               sumsq_out.data_ptr(), ops.stream)
+
+
 def attach_data_parallel(model, group=None, shard_embedding=True) -> DataParallel:
-    """Make `model` (a cdcmdr BaseModel, or a CDC wrapper) one replica of a data-parallel group."""
+    """Make `model` (a cdcmdr BaseModel, or a CDC wrapper) one replica of a data-parallel group.
+    shard_embedding=True: table cut at field boundaries, all-to-all exchange (small rows, large batches: C4).
+    shard_embedding="rows": row-range shards in NVLink peer memory, owner-only allocation (huge tables: C5; see RowRangeParallel)."""
     base = getattr(model, "base_model_instance", model)
+    if shard_embedding == "rows":
+        return RowRangeParallel(base, group)
     return DataParallel(base, group, shard_embedding)

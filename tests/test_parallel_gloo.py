@@ -172,3 +172,69 @@ def test_field_runs_pack_like_per_owner_copies(n_fields, world):
         abi.copy2d_batched(packed.ctypes.data + 4 * B * f0 * E, B * n * E, n * E, back.ctypes.data + 4 * f0 * E, n * E, n_fields * E, cnt, B,
                            n * E, 4, 0)
     assert np.array_equal(back, X)
+
+
+# ------------------------------------------------------------------------------------------------ row-range sharded table (C5)
+def _rows_worker(rank, world, port, kind, B, n_steps, path, full_sd):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cm._lib.install(HostABI())
+        with cm.parallel.sharded_table(rank, world, "cpu"):
+            model = _build(kind)
+        emb = model.base_model_instance.embedding if kind == "cdc" else model.embedding
+        rows_per = emb.rows_per
+        assert emb.embedding_dict.weight.shape[0] == rows_per == -(-int(FD.sum()) // world)     # only this rank's rows exist
+        sd = {k: torch.from_numpy(v) for k, v in np.load(full_sd).items()}
+        key = [k for k in sd if k.endswith("embedding.embedding_dict.weight")][0]
+        full = sd[key]
+        local = torch.zeros(rows_per, full.shape[1])
+        r0, r1 = rank * rows_per, min(full.shape[0], (rank + 1) * rows_per)
+        local[:r1 - r0] = full[r0:r1]
+        sd[key] = local
+        model.load_state_dict(sd, strict=True)
+        cm.parallel.attach_data_parallel(model, shard_embedding="rows")
+        x, y, g = _data(B)
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        outs = _steps(model, kind, x[lo:hi], y[lo:hi], g[lo:hi], n_steps)
+        out = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        out["__rows"] = np.array([r0, r1])
+        np.savez(os.path.join(path, f"rank{rank}.npz"), **out,
+                 **{f"pred{i}": o[0] for i, o in enumerate(outs)}, **{f"loss{i}": np.array(o[1]) for i, o in enumerate(outs)})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,world", [("ple", 2), ("cdc", 3)])
+def test_row_range_sharded_table_matches_one_process(kind, world):
+    """BASELINE configs[4] mechanism on CPU: every rank constructs ONLY its own row range of the table (parallel.sharded_table),
+    the forward reads rows where they live, the owners update their rows from the all-gathered indices / row gradients with the
+    touched-row Adam and the incrementally maintained regulariser - against ONE process with the whole table and
+    embedding_update='sparse_lazy' on the concatenated batch: predictions, losses (incl. the regulariser), every rank's rows."""
+    B, n_steps = 96, 3
+    old = cm._lib._LIB
+    cm._lib.install(HostABI())
+    try:
+        ref = _build(kind)
+        base = ref.base_model_instance if kind == "cdc" else ref
+        base.embedding_update = "sparse_lazy"
+        sd0 = {k: v.detach().numpy().copy() for k, v in ref.state_dict().items()}
+        with tempfile.TemporaryDirectory() as tmp:
+            full_sd = os.path.join(tmp, "sd0.npz")
+            np.savez(full_sd, **sd0)
+            mp.spawn(_rows_worker, args=(world, _free_port(), kind, B, n_steps, tmp, full_sd), nprocs=world, join=True)
+            ranks = [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
+        x, y, g = _data(B)
+        want = _steps(ref, kind, x, y, g, n_steps)
+        sd = {k: v.detach().numpy() for k, v in ref.state_dict().items()}
+    finally:
+        cm._lib.install(old)
+    for i in range(n_steps):
+        pred = np.concatenate([ranks[r][f"pred{i}"] for r in range(world)], axis=0)
+        assert np.abs(pred - want[i][0]).max() <= 2e-6, (i, float(np.abs(pred - want[i][0]).max()))
+        for r in range(world):
+            assert np.allclose(ranks[r][f"loss{i}"], np.array(want[i][1]), rtol=1e-5, atol=1e-7), (i, r, ranks[r][f"loss{i}"], want[i][1])
+    key = [k for k in sd if k.endswith("embedding.embedding_dict.weight")][0]
+    for r in range(world):
+        r0, r1 = ranks[r]["__rows"]
+        assert np.abs(ranks[r][key][:r1 - r0] - sd[key][r0:r1]).max() <= 2e-6, r
