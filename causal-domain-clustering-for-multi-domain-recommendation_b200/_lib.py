@@ -125,6 +125,7 @@ SIGNATURES = {
     "cdcmdr_cast_f32_bf16": (INT, [P, I64, P, I64, I64, I64, P]),
     "cdcmdr_cast_bf16_f32": (INT, [P, I64, P, I64, I64, I64, INT, P]),
     "cdcmdr_ewise_f32": (INT, [P, P, P, I64, INT, P]),
+    "cdcmdr_ewise_group_f32": (INT, [P, P, P, I64, INT, INT, P]),
     "cdcmdr_add2d_f32": (INT, [P, I64, P, I64, I64, I64, INT, P]),
     "cdcmdr_cross_fuse_fwd": (INT, [P, P, P, INT, P, P, I64, I64, P]),
     "cdcmdr_cross_fuse_bwd": (INT, [P, P, INT, P, P, P, I64, I64, P]),

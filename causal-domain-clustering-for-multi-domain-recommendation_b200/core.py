@@ -408,5 +408,8 @@ class Ops:
     def ewise(self, a, b, out, n, op):
         self.lib.ewise_f32(a, b, out, n, op, self.stream)
 
+    def ewise_group(self, a, b, out, n, G, op):
+        self.lib.ewise_group_f32(a, b, out, n, G, op, self.stream)
+
     def add2d(self, a: Mat, out: Mat, rows, cols, accumulate):
         self.lib.add2d_f32(a.ptr, a.ld, out.ptr, out.ld, rows, cols, 1 if accumulate else 0, self.stream)

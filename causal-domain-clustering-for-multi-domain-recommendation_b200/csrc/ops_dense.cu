@@ -923,6 +923,26 @@ __global__ void ewise_kernel(const float* __restrict__ a, const float* __restric
     out[i] = v;
   }
 }
+// STAR's star-topology factors over all T towers in one launch (star.py:91-92, 100-101): a, out are [G, n] blocks, b is either one
+// shared [n] block (broadcast over the towers) or a [G, n] block.
+//   op 0: out[g, i] = a[g, i] * b[i]          op 1: out[g, i] = a[g, i] + b[i]
+//   op 2: out[i]    = sum_g a[g, i] * b[g, i]  op 3: out[i]   += sum_g a[g, i]      op 4: out[g, i] += a[g, i]
+// (fixed g order: deterministic)
+__global__ void ewise_group_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int64_t n, int G, int op) {
+  if (op == 0 || op == 1 || op == 4) {
+    const int64_t total = n * G;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      int64_t g, j; split_idx(i, n, g, j);
+      out[i] = op == 0 ? a[i] * b[j] : (op == 1 ? a[i] + b[j] : out[i] + a[i]);
+    }
+    return;
+  }
+  for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n; j += (int64_t)gridDim.x * blockDim.x) {
+    float acc = 0.f;
+    for (int g = 0; g < G; ++g) acc += op == 2 ? a[g * n + j] * b[g * n + j] : a[g * n + j];
+    out[j] = op == 2 ? acc : out[j] + acc;
+  }
+}
 __global__ void add2d_kernel(const float* __restrict__ a, int64_t lda, float* __restrict__ out, int64_t ldo, int64_t rows, int64_t cols, int accumulate) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1416,6 +1436,14 @@ extern "C" int cdcmdr_ewise_f32(const float* a, const float* b, float* out, int6
   CDC_REQUIRE(op >= 0 && op <= 3, "bad elementwise op");
   if (n <= 0) return 0;
   ewise_kernel<<<grid_1d(n, 256), 256, 0, to_stream(s)>>>(a, b, out, n, op);
+  CDC_LAUNCHED();
+  return 0;
+}
+extern "C" int cdcmdr_ewise_group_f32(const float* a, const float* b, float* out, int64_t n, int G, int op, cdcmdr_stream_t s) {
+  CDC_REQUIRE(op >= 0 && op <= 4 && G >= 1, "bad grouped elementwise op");
+  if (n <= 0) return 0;
+  const int64_t work = (op == 2 || op == 3) ? n : n * G;
+  ewise_group_kernel<<<grid_1d(work, 256), 256, 0, to_stream(s)>>>(a, b, out, n, G, op);
   CDC_LAUNCHED();
   return 0;
 }

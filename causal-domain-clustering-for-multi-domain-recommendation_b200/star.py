@@ -102,45 +102,48 @@ class STAR(BaseModel):
         rt = self._rt
         self._towers = [MlpGroup(rt, f"star.t{t}", 1, self.embed_output_dim, self.tower_dims, self._names, bn=True, out_layer=True,
                                  in_groups=None, g0=t) for t in range(self.n_tower)]
+        # all-rows mode (no x_group: every tower sees every row, star.py:84 / CDC over STAR): the T towers are ONE group of MLPs
+        # over the T partitioned-norm outputs laid side by side [B, T*D] - one grouped GEMM / BatchNorm / head launch per layer
+        # instead of T (the routed mode keeps per-tower launches: its towers see different row counts)
+        self._towers_all = MlpGroup(rt, "star.all", self.n_tower, self.embed_output_dim, self.tower_dims, self._names, bn=True,
+                                    out_layer=True, in_groups=None)
 
     # ---------------------------------------------------------------- derived operands (star.py:91-92, 100-101)
     def _derive(self):
+        """W_eff[t] = W_t * W_s, b_eff[t] = b_t + b_s for every tower in one launch per block (star.py:91-92, 100-101)"""
         rt, T = self._rt, self.n_tower
         ops = rt.ops
         lo = rt.o("star.W_eff0")
         for i, d in enumerate(self.tower_dims):
             n = d * self._dims_in[i]
-            for t in range(T):
-                ops.ewise(rt.w(f"star.Wd{i}", t * n), rt.w(f"shared_dnn.linears.{i}.weight"), rt.w(f"star.W_eff{i}", t * n), n, 0)
-                ops.ewise(rt.w(f"star.bd{i}", t * d), rt.w(f"shared_dnn.linears.{i}.bias"), rt.w(f"star.b_eff{i}", t * d), d, 1)
+            ops.ewise_group(rt.w(f"star.Wd{i}"), rt.w(f"shared_dnn.linears.{i}.weight"), rt.w(f"star.W_eff{i}"), n, T, 0)
+            ops.ewise_group(rt.w(f"star.bd{i}"), rt.w(f"shared_dnn.linears.{i}.bias"), rt.w(f"star.b_eff{i}"), d, T, 1)
         h = self.tower_dims[-1]
-        for t in range(T):
-            ops.ewise(rt.w("star.Wdout", t * h), rt.w("shared_dnn_linear.weight"), rt.w("star.Wout_eff", t * h), h, 0)
-            ops.ewise(rt.w("star.bdout", t), rt.w("shared_dnn_linear.bias"), rt.w("star.bout_eff", t), 1, 1)
+        ops.ewise_group(rt.w("star.Wdout"), rt.w("shared_dnn_linear.weight"), rt.w("star.Wout_eff"), h, T, 0)
+        ops.ewise_group(rt.w("star.bdout"), rt.w("shared_dnn_linear.bias"), rt.w("star.bout_eff"), 1, T, 1)
         if rt.bf16:                                          # bf16 operand copy of the derived weights (the arena cast ran earlier)
             hi = rt.o("star.bout_eff") + T
             ops.cast_f32_bf16(Mat(rt.W, lo, hi - lo), Mat(rt.Wb, lo, hi - lo), 1, hi - lo)
 
     def _chain(self, active):
-        """dW_eff, db_eff -> gradients of the domain and shared factors.  Towers that saw no rows contribute zeros."""
+        """dW_eff, db_eff -> gradients of the domain and shared factors, all towers per launch (fixed tower order in the sums).
+        Towers that saw no rows contribute zeros (the gradient arena was zeroed)."""
         rt, T = self._rt, self.n_tower
         ops = rt.ops
         for i, d in enumerate(self.tower_dims):
             n = d * self._dims_in[i]
             sW, sb = f"shared_dnn.linears.{i}.weight", f"shared_dnn.linears.{i}.bias"
-            for t in range(T):
-                ge, gbe = rt.g(f"star.W_eff{i}", t * n), rt.g(f"star.b_eff{i}", t * d)
-                ops.ewise(ge, rt.w(sW), rt.g(f"star.Wd{i}", t * n), n, 0)                    # dW_t = dW_eff * W_s
-                ops.ewise(ge, rt.w(f"star.Wd{i}", t * n), rt.g(sW), n, 0 if t == 0 else 2)     # dW_s (+)= dW_eff * W_t
-                ops.ewise(gbe, gbe, rt.g(f"star.bd{i}", t * d), d, 3)                           # db_t = db_eff (target zeroed below)
-                ops.ewise(gbe, gbe, rt.g(sb), d, 3)                                             # db_s += db_eff
+            ge, gbe = rt.g(f"star.W_eff{i}"), rt.g(f"star.b_eff{i}")
+            ops.ewise_group(ge, rt.w(sW), rt.g(f"star.Wd{i}"), n, T, 0)                       # dW_t = dW_eff_t * W_s
+            ops.ewise_group(ge, rt.w(f"star.Wd{i}"), rt.g(sW), n, T, 2)                       # dW_s = sum_t dW_eff_t * W_t
+            ops.ewise_group(gbe, None, rt.g(f"star.bd{i}"), d, T, 4)                          # db_t += db_eff_t (target zeroed)
+            ops.ewise_group(gbe, None, rt.g(sb), d, T, 3)                                     # db_s += sum_t db_eff_t
         h = self.tower_dims[-1]
-        for t in range(T):
-            ge, gbe = rt.g("star.Wout_eff", t * h), rt.g("star.bout_eff", t)
-            ops.ewise(ge, rt.w("shared_dnn_linear.weight"), rt.g("star.Wdout", t * h), h, 0)
-            ops.ewise(ge, rt.w("star.Wdout", t * h), rt.g("shared_dnn_linear.weight"), h, 0 if t == 0 else 2)
-            ops.ewise(gbe, gbe, rt.g("star.bdout", t), 1, 3)
-            ops.ewise(gbe, gbe, rt.g("shared_dnn_linear.bias"), 1, 3)
+        ge, gbe = rt.g("star.Wout_eff"), rt.g("star.bout_eff")
+        ops.ewise_group(ge, rt.w("shared_dnn_linear.weight"), rt.g("star.Wdout"), h, T, 0)
+        ops.ewise_group(ge, rt.w("star.Wdout"), rt.g("shared_dnn_linear.weight"), h, T, 2)
+        ops.ewise_group(gbe, None, rt.g("star.bdout"), 1, T, 4)
+        ops.ewise_group(gbe, None, rt.g("shared_dnn_linear.bias"), 1, T, 3)
 
     # ---------------------------------------------------------------- routing (star.py:84-87)
     def _route_rows(self, ws, X: Mat, B, x_group):
@@ -243,6 +246,15 @@ class STAR(BaseModel):
             # star.py:70-72, 103-107: atten_forward(embed_x) is per-row, `other[mask]` picks the tower's rows - the same as running
             # the block on the routed rows
             self._att.fwd(ws, x32, n_rows, lin, train)
+        if x_group is None:
+            hall = ws.mat("star.pn_all", B, T * D, rt.act_dtype)
+            for t in range(T):
+                blk = Mat(hall.t, t * D, T * D)
+                if B == 1:                                   # star.py:134-135: PN is the identity on a single row
+                    ops.copy2d(Xs.ptr, Xs.ld, blk.ptr, blk.ld, B, D, Xs.t.element_size())
+                else:
+                    rt.bn_fwd(self._pn_desc(ws, t, train, True), x32, blk, B, D)
+            return self._towers_all.fwd(ws, hall, B, train), lin
         for t, (r0, n) in enumerate(slices):
             if n == 0:
                 continue
@@ -272,6 +284,24 @@ class STAR(BaseModel):
         x32 = ws.mat("X32", n_rows, D) if Xs.is_bf16 else Xs
         dXs = ws.mat("star.dXs", max(n_rows, 1), D)
         first = True
+        if not routed:
+            hall = ws.mat("star.pn_all", B, T * D, rt.act_dtype)
+            dhall = ws.mat("star.dh_all", B, T * D)
+            self._towers_all.bwd(ws, hall, dlogits, B, train, dhall)
+            for t in range(T):
+                dh = Mat(dhall.t, t * D, T * D)
+                if B == 1:
+                    ops.add2d(dh, dXs, B, D, t > 0)
+                    continue
+                dprod = rt.w("star.pn_dprod")
+                dz = ws.mat("star.dpn", B, D) if t > 0 else dXs
+                rt.bn_bwd(self._pn_desc(ws, t, train, False), x32, None, dh, dz, dprod, rt.g("star.pn_beta", t * D), False, B, D)
+                if t > 0:
+                    ops.add2d(dz, dXs, B, D, True)
+                ops.ewise(dprod, rt.w("shared_bn_weight"), rt.g("star.pn_gamma", t * D), D, 0)          # dgamma_t = dprod * gamma_s
+                ops.ewise(dprod, rt.w("star.pn_gamma", t * D), rt.g("shared_bn_weight"), D, 2)           # dgamma_s += dprod * gamma_t
+                ops.ewise(rt.g("star.pn_beta", t * D), dprod, rt.g("shared_bn_bias"), D, 3)              # dbeta_s += dbeta_t
+            slices = []
         for t, (r0, n) in enumerate(slices):
             if n == 0:
                 continue

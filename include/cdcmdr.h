@@ -318,6 +318,10 @@ int cdcmdr_cast_bf16_f32(const uint16_t* src, int64_t lds, float* dst, int64_t l
 /* out = a*b (op 0), a+b (op 1), out += a*b (op 2), out += a (op 3; b ignored) over n contiguous floats:
  * STAR W_d*W_s, b_d+b_s and their gradients  star.py:91-92 */
 int cdcmdr_ewise_f32(const float* a, const float* b, float* out, int64_t n, int op, cdcmdr_stream_t s);
+/* the same factors for all G towers in one launch: a, out [G, n] blocks, b one shared [n] block (ops 0, 1) or [G, n] (op 2)
+ *   op 0: out[g,i] = a[g,i]*b[i]   op 1: out[g,i] = a[g,i]+b[i]   op 2: out[i] = sum_g a[g,i]*b[g,i]   op 3: out[i] += sum_g a[g,i]
+ *   op 4: out[g,i] += a[g,i]                                                                            star.py:91-92, 100-101 */
+int cdcmdr_ewise_group_f32(const float* a, const float* b, float* out, int64_t n, int G, int op, cdcmdr_stream_t s);
 /* out[r, c] (+)= a[r*lda + c] (op 1: * b[r*ldb + c]) for a strided 2-D block */
 int cdcmdr_add2d_f32(const float* a, int64_t lda, float* out, int64_t ldo, int64_t rows, int64_t cols,
                      int accumulate, cdcmdr_stream_t s);

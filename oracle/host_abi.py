@@ -607,6 +607,27 @@ class HostABI:
         d[...] = d + v if accumulate else v
         return 0
 
+    def ewise_group_f32(self, a, b, out, n, G, op, s):
+        aa = _arr(a, n * G, np.float32)[:n * G].reshape(G, n)
+        if op in (0, 1, 4):
+            o = _arr(out, n * G, np.float32)[:n * G].reshape(G, n)
+            bb = _arr(b, n, np.float32)[:n] if b else None
+            o[...] = aa * bb[None, :] if op == 0 else (aa + bb[None, :] if op == 1 else o + aa)
+            return 0
+        o = _arr(out, n, np.float32)[:n]
+        if op == 2:
+            bb = _arr(b, n * G, np.float32)[:n * G].reshape(G, n)
+            acc = np.zeros(n, dtype=np.float32)
+            for g in range(G):
+                acc = acc + aa[g] * bb[g]
+            o[...] = acc
+        else:
+            acc = np.zeros(n, dtype=np.float32)
+            for g in range(G):
+                acc = acc + aa[g]
+            o[...] = o + acc
+        return 0
+
     def ewise_f32(self, a, b, out, n, op, s):
         aa, o = _arr(a, n, np.float32), _arr(out, n, np.float32)
         bb = _arr(b, n, np.float32) if b else None
