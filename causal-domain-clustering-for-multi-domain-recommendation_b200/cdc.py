@@ -11,8 +11,6 @@ host-side NumPy / SciPy / scikit-learn in the reference and runs once per `updat
 restated on the host in cdc_group.py so that run.py::train_cdc works unchanged."""
 from __future__ import annotations
 
-import copy
-import re
 
 import numpy as np
 import torch
@@ -261,11 +259,33 @@ class CDC(BaseModel):
 
     # ---------------------------------------------------------------- snapshot / restore (cdc.py:343-354)
     def save_model_state(self):
-        pattern = re.compile('^(base_model_instance)')
-        self.model_state = copy.deepcopy({k: v for k, v in self.state_dict().items() if pattern.match(k)})
+        """cdc.py:343-351: upstream deep-copies every `base_model_instance.*` entry of the state_dict (parameters and buffers, not the
+        optimizer's moments).  Same content here, kept ON the device as three flat copies - the dense parameter arena, the BatchNorm
+        buffer arena and the embedding table - plus the handful of integer `num_batches_tracked` counters: the probing loop restores
+        115 times per update (run.py:560-592), and a state_dict round trip per restore was a quarter of its time.  (Every row of the
+        table moves every step under the reference's dense Adam + full-table L2 - SURVEY G6 - so the table copy is the exact
+        snapshot; it is one 64 MB device copy at the C4 shape.)"""
+        base = self.base_model_instance
+        rt = base._rt
+        table = base.embedding.embedding_dict.weight
+        ints = [b for n, b in base.named_buffers() if not b.dtype.is_floating_point and b.device == rt.device and n != "embedding.offsets_dev"]
+        self.model_state = dict(W=rt.W.clone(), Bf=rt.Bf.clone(), table=table.detach().clone(), ints=ints,
+                                int_vals=[b.clone() for b in ints], rt=rt)
 
     def load_model_state(self):
-        self.load_state_dict(self.model_state, strict=False)
+        st = self.model_state
+        base = self.base_model_instance
+        rt = base._rt
+        if st is None:
+            raise RuntimeError("cdcmdr: load_model_state() before save_model_state()")
+        if st["rt"] is not rt:
+            raise RuntimeError("cdcmdr: the model moved to another device since save_model_state()")
+        with torch.no_grad():
+            rt.W.copy_(st["W"])
+            rt.Bf.copy_(st["Bf"])
+            base.embedding.embedding_dict.weight.copy_(st["table"])
+            if st["ints"]:
+                torch._foreach_copy_(st["ints"], st["int_vals"])
 
     def update_group(self, mode='iterative'):
         """cdc.py:121-238: turn the probed affinity matrices (matrix_A / matrix_B / matrix_mask, filled row by row by
