@@ -403,6 +403,11 @@ def ours_arm(args):
         ms_e2e = max(ms_e2e, wall_e2e)
     roof = dominant_kernel_roofline(base, B, torch) if rank == 0 else None
     emb = embedding_bandwidth(base, dev_batches[0][0], B, torch) if rank == 0 else None
+    amort = None
+    if world == 1 and not args.no_amortised:
+        steps_by_col.clear()                                   # the probing loop regroups: the recorded graphs are stale anyway
+        proto = g = None
+        amort = cdc_amortised(model, opt, B, ms / args.steps, torch)
     if world > 1:
         # tear-down of a process group while CUDA graphs that recorded its collectives are alive hangs (seen on 2 x B200):
         # drop the graphs, meet once more, and leave without the group destructor
@@ -441,7 +446,7 @@ def ours_arm(args):
                     "h2d_bytes_per_step": B * F * 4 + B * 2, "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps, "launches_per_step": launches_per_step,
             "step_tflops": flops_step / (ms / args.steps * 1e-3) / 1e12, "loss_last": loss_last,
-            "roofline": roof, "embedding": emb, "cpu_baseline": cpu, "lib": lib.path}
+            "roofline": roof, "embedding": emb, "cdc_amortised": amort, "cpu_baseline": cpu, "lib": lib.path}
     if roof is not None and peaks:
         roof["peak_source"] = "MEASURED_PEAKS.json (driver-measured on this pool)"
     emit(line)
@@ -450,63 +455,124 @@ def ours_arm(args):
         os._exit(0)
 
 
+def _time_launch(fn, torch, n=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / n
+
+
+def _ncu_traffic(name, shape):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel from the committed `ncu --set full` capture
+    (profiles/r2_ncu_traffic.json: kernel -> {shape, dram_bytes_read, dram_bytes_write, report}); None when no capture of this
+    launch shape is committed."""
+    path = os.path.join(ROOT, "profiles", "r2_ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    rec = json.load(open(path)).get(name)
+    if not rec or list(rec.get("shape", [])) != list(shape):
+        return None
+    return float(rec["dram_bytes_read"] + rec["dram_bytes_write"])
+
+
 def dominant_kernel_roofline(base, B, torch):
-    """Level-0 expert GEMM (X[B,368] x W^T[368, 10*256], bias+ReLU+dropout epilogue): 67% of the step's FLOPs.
-    Timed alone with CUDA events on the launching stream; algorithmic FLOPs = 2*B*K*N."""
+    """The dominant kernel of the step: PLE level 0 - every expert's layer 0 -> layer 1 chained in one tcgen05 kernel plus the gate
+    logits (cdcmdr_ple_chain_fwd, training form: layer-0 activation stored for the backward, dropout 0.2) = 31 % of the step's
+    algorithmic FLOPs in one launch.  Timed alone with CUDA events on the launching stream; algorithmic FLOPs
+    2*B*(K0*(nE*d0 + n_g) + nE*d0*d1).  When the chain kernel is not in use (CDCMDR_PLE_CHAIN=0) the concatenated-N layer-0 GEMM
+    is timed instead, as in round 1.  `l0_gemm` carries that GEMM's own number either way."""
     rt = base._rt
     ws = rt.ws(B)
     lv = base._levels[0]
     D, N = base.embed_output_dim, lv.experts.G * lv.experts.dims[0]
     X = base._x_mat(ws, B)                                        # the step's own gathered-embedding buffer (same pitch)
-    fn = lambda: lv.experts.fwd_layer0_only(ws, X, B)            # noqa: E731
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10
-    e0.record()
-    for _ in range(n):
-        fn()
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3 / n
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks_path))["bf16_tflops"] if os.path.exists(peaks_path) else 1590.0
-    ach = 2.0 * B * D * N / sec / 1e12
-    # traffic: dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the committed ncu --set full capture
-    # (profiles/r1_ncu_gemm_l0_fwd.md, third capture: 59.2 MB + 286.0 MB; the algorithmic bytes are 385.7 MB, the tail of the
-    # output is still dirty in L2 when the kernel ends)
-    traffic = 345.3e6 if (B, D, N) == (65536, 368, 2560) else None
+    sec_l0 = _time_launch(lambda: lv.experts.fwd_layer0_only(ws, X, B), torch)
+    l0 = {"kernel": "level-0 expert GEMM fwd alone (concat-N, bias+ReLU+dropout epilogue)", "achieved": 2.0 * B * D * N / sec_l0 / 1e12,
+          "us_per_launch": sec_l0 * 1e6, "frac": 2.0 * B * D * N / sec_l0 / 1e12 / peak}
+    if getattr(lv, "chain", False):
+        d0, d1 = lv.experts.dims
+        flops = 2.0 * B * (D * (N + lv.n_gcols) + lv.experts.G * d0 * d1)
+        base.train()
+        sec = _time_launch(lambda: base._chain_launch(ws, 0, X, B, True, True), torch)
+        sec_inf = _time_launch(lambda: base._chain_launch(ws, 0, X, B, False, False), torch)
+        ach = flops / sec / 1e12
+        return {"kernel": "cdcmdr_ple_chain_fwd: PLE level 0, expert layers 0->1 chained in-kernel + gate logits (training form)",
+                "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+                "traffic": _ncu_traffic("ple_chain_fwd_kernel", [B, D, lv.experts.G, d0, d1, lv.n_gcols]),
+                "us_per_launch": sec * 1e6, "algorithmic_flops": flops,
+                "algorithmic_bytes": B * (D * 2 + N * 2 + lv.experts.G * d1 * 2 + lv.n_gcols * 4),
+                "inference_form": {"us_per_launch": sec_inf * 1e6, "achieved": flops / sec_inf / 1e12,
+                                   "note": "no layer-0 activation store, no dropout: [B, nE*d0] never reaches HBM"},
+                "l0_gemm": l0,
+                "note": "bound by shared-memory bandwidth (profiles/r2_chain_waits.md): N=128 UMMAs read 128 B/clk of operands, the "
+                        "weight-ring fills and the epilogue's activation blocks share the pipe"}
+    ach = 2.0 * B * D * N / sec_l0 / 1e12
     return {"kernel": "level-0 expert GEMM fwd (concat-N, bias+ReLU+dropout epilogue)", "bound": "tensor", "achieved": ach,
-            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "us_per_launch": sec * 1e6,
-            "algorithmic_flops": 2.0 * B * D * N}
+            "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": _ncu_traffic("gemm_bf16_tc_kernel_l0", [B, D, N]),
+            "us_per_launch": sec_l0 * 1e6, "algorithmic_flops": 2.0 * B * D * N}
+
+
+def cdc_amortised(model, opt, B, ms_step, torch):
+    """the amortised CDC number next to the steady-state one.  run.py:601-604: at batch size bs the affinity matrices are
+    re-probed every update_interval = 1000*1024//bs steps (15 at 65 536) with k = max(1, 2*1024//bs) steps per probe; one
+    `update_matrix_cdc` = 50 treatment rows + matrix A + matrix B = ~115 probes, each {k fused steps, one batched evaluation of
+    all 30 domains, restore}, + update_group.  Times ONE call (after a warm call) on per-domain batches of the bench's size."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from bench_probe import Provider
+    np.random.seed(SEED)
+    get = Provider(field_dims(), B, 2, 11)
+    k = max(1, 2 * 1024 // B)
+    interval = max(1, 1000 * 1024 // B)
+    model.update_matrix_cdc(get, opt, k)                                  # warm call: workspaces of every probe batch size
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model.update_matrix_cdc(get, opt, k)
+    torch.cuda.synchronize()
+    sec = time.perf_counter() - t0
+    model.train()
+    amort = interval * B / (interval * ms_step * 1e-3 + sec)
+    return {"update_matrix_cdc_s": sec, "update_interval_steps": interval, "k": k, "samples_per_s": amort,
+            "note": "steady-state steps + one update_matrix_cdc per update_interval (run.py:596-645); probe rows are not counted as samples"}
 
 
 def embedding_bandwidth(base, x, B, torch):
-    """Gather kernel alone: algorithmic bytes F*(4 + E*4 + E*4) per sample."""
+    """The gather kernel alone: algorithmic bytes F*(4 + E*4 + E*s_out) per sample, two ways:
+    `achieved` - the workload's own table (64 MB < the 126 MB L2) and Zipf ids: hot rows are L2 hits, so this is NOT a DRAM number;
+    `uniform_big_table` - uniform ids over a 2 GiB table (>> L2): every 64-byte row comes from HBM - the worst case SURVEY 8d asks
+    for, and the figure to hold against the measured HBM peak."""
     rt = base._rt
     ws = rt.ws(B)
     table = base.embedding.embedding_dict.weight
     X = ws.mat("probe.X", B, F * E, rt.act_dtype)
-
-    def gather():                                     # the gather kernel alone (no exchange), on this rank's memory
-        rt.ops.embed_gather(x, base.embedding.offsets_dev, table, None if rt.bf16 else X, X if rt.bf16 else None, B, F, E, table.shape[0])
-    for _ in range(3):
-        gather()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 20
-    e0.record()
-    for _ in range(n):
-        gather()
-    e1.record()
-    torch.cuda.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3 / n
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
-    gbs = B * F * (4 + E * 4 + E * (2 if rt.bf16 else 4)) / sec / 1e9
-    return {"kernel": "embed_gather_fwd", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
-            "us_per_launch": sec * 1e6, "note": "Zipf ids: hot rows hit L2, so this can exceed the DRAM copy peak"}
+    nbytes = B * F * (4 + E * 4 + E * (2 if rt.bf16 else 4))
+
+    def run(xi, off, tab):
+        fn = lambda: rt.ops.embed_gather(xi, off, tab, None if rt.bf16 else X, X if rt.bf16 else None, B, F, E, tab.shape[0])   # noqa: E731
+        return _time_launch(fn, torch, n=20)
+    sec = run(x, base.embedding.offsets_dev, table)
+    gbs = nbytes / sec / 1e9
+    out = {"kernel": "embed_gather_fwd", "bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+           "us_per_launch": sec * 1e6, "note": "workload table (64 MB) + Zipf ids: hot rows hit L2, so this can exceed the DRAM copy peak"}
+    rows_big = (2 << 30) // (E * 4)
+    big = torch.empty(rows_big, E, dtype=torch.float32, device=x.device).normal_()
+    per = rows_big // F
+    xu = torch.randint(0, per, (B, F), dtype=torch.int32, device=x.device)
+    offu = torch.arange(F, dtype=torch.int64, device=x.device) * per
+    secu = run(xu, offu, big)
+    out["uniform_big_table"] = {"achieved": nbytes / secu / 1e9, "frac": nbytes / secu / 1e9 / peak, "us_per_launch": secu * 1e6,
+                                "table_bytes": rows_big * E * 4, "note": "uniform ids over a 2 GiB table: every row read is a DRAM access"}
+    del big
+    return out
 
 
 _OUT = None
@@ -532,6 +598,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cpu-batch", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-amortised", action="store_true", help="skip the update_matrix_cdc timing behind cdc_amortised")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: stop timing after this many seconds")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -206,24 +206,30 @@ class PLE(BaseModel):
         n = self._levels[0].n_gcols
         return ws.mat("cgc0.dlogits", B, n, zero=True).cols(n - 1)
 
+    def _chain_launch(self, ws, l, xin: Mat, B, train, keep_acts) -> Mat:
+        """Level l's experts (layer 0 -> layer 1 chained in-kernel) and its gate / wide-linear logits from the same resident X tile
+        in ONE launch (cdcmdr_ple_chain_fwd).  The [B, nE*d0] layer-0 activation is written only when a backward will read it
+        (keep_acts).  Returns the expert outputs H [B, nE*d1]; the logits land in cgc{l}.logits."""
+        rt, lv = self._rt, self._levels[l]
+        ex = lv.experts
+        d0, d1 = ex.dims
+        drop = rt.dropout if train else 0.0
+        A0 = ex._act(ws, 0, B) if keep_acts else None
+        H = ex._act(ws, 1, B)
+        Lg = ws.mat(f"cgc{l}.logits", B, lv.n_gcols)
+        names = self._level_names[l]
+        rt.ops.ple_chain_fwd(xin, B, lv.K, rt.Wb.data_ptr() + 2 * rt.o(names["W"][0]), rt.w(names["b"][0]),
+                             rt.Wb.data_ptr() + 2 * rt.o(names["W"][1]), rt.w(names["b"][1]), ex.G, d0, d1, lv.n_gcols,
+                             A0, H, Lg, drop_p=drop, seed_ptr=rt.seed_ptr if drop > 0 else None, salt0=ex.salts[0], salt1=ex.salts[1])
+        return H
+
     def _program_fwd(self, ws, X: Mat, B, train):
         rt = self._rt
         xin = X
         for l, lv in enumerate(self._levels):
             Lg = ws.mat(f"cgc{l}.logits", B, lv.n_gcols)
             if lv.chain and xin.is_bf16:
-                # experts' layer 0 -> layer 1 chained in-kernel, gate / wide-linear logits from the same resident X tile.  The
-                # [B, nE*d0] layer-0 activation is written only when a backward will read it.
-                ex = lv.experts
-                d0, d1 = ex.dims
-                drop = rt.dropout if train else 0.0
-                A0 = ex._act(ws, 0, B) if self._keep_acts else None
-                H = ex._act(ws, 1, B)
-                names = self._level_names[l]
-                rt.ops.ple_chain_fwd(xin, B, lv.K, rt.Wb.data_ptr() + 2 * rt.o(names["W"][0]), rt.w(names["b"][0]),
-                                     rt.Wb.data_ptr() + 2 * rt.o(names["W"][1]), rt.w(names["b"][1]), ex.G, d0, d1, lv.n_gcols,
-                                     A0, H, Lg, drop_p=drop, seed_ptr=rt.seed_ptr if drop > 0 else None, salt0=ex.salts[0],
-                                     salt1=ex.salts[1])
+                H = self._chain_launch(ws, l, xin, B, train, self._keep_acts)
                 out = ws.mat(f"cgc{l}.out", B, lv.n_gates * lv.h, rt.act_dtype)
                 probs = ws.get(f"cgc{l}.probs", (B, lv.n_gates * lv.max_sel))
                 rt.ops.gate_mix_fwd(lv.desc, H, Lg, out, probs, B)
