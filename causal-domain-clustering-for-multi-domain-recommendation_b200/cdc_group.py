@@ -47,6 +47,7 @@ class Grouping:
 
     def __init__(self, n_domain, n_cluster, domain_cnt_weight, config, use_metric="loss"):
         self.n_domain, self.n_cluster = n_domain, n_cluster
+        self._all_domains = torch.arange(n_domain, dtype=torch.int64)
         self.w = np.asarray(domain_cnt_weight, dtype=F32)
         self.w_t = torch.tensor([float(v) for v in domain_cnt_weight], dtype=torch.float32)      # cdc.py:62
         self.affinity_func = getattr(config, "affinity_func", "minus")
@@ -85,12 +86,23 @@ class Grouping:
     # ---------------------------------------------------------------- cdc.py:321-341
     def _lambda(self, group, domain=None):
         """lambda_d = clamp(0.5 (|G|-1) sum_{g in G} dist[g, d] / (sum_{GxG} dist - sum_{g in G} dist[g, d]), 0, 1)"""
-        g = list(group)
-        dom = list(range(self.n_domain)) if domain is None else list(domain)
-        total = torch.sum(self.causal_t[np.ix_(g, g)])
-        related = torch.sum(self.causal_t[np.ix_(g, dom)], dim=0)
+        g = torch.as_tensor(list(group), dtype=torch.int64)
+        dom = self._all_domains if domain is None else torch.as_tensor(list(domain), dtype=torch.int64)
+        total = torch.sum(self.causal_t[g[:, None], g[None, :]])
+        related = torch.sum(self.causal_t[g[:, None], dom[None, :]], dim=0)
         vals = (len(g) - 1) * related / (total - related) * 0.5
         return torch.clamp(vals, min=0, max=1)                  # NaN (0/0) stays NaN
+
+    def _lambda_candidates(self, s_group, cands, domain):
+        """_lambda(s_group + [d], domain) for every candidate d at once -> [len(cands), len(domain)].  One gather and one reduction
+        per term instead of one pair per candidate; every slice reduces the same elements in the same order as the single call
+        (checked bit for bit against it: torch reduces each [m, m] / [m, n] slice of the stacked tensor like the lone matrix)."""
+        idx = torch.as_tensor([list(s_group) + [d] for d in cands], dtype=torch.int64)          # [k, m+1]
+        dom = torch.as_tensor(list(domain), dtype=torch.int64)
+        total = self.causal_t[idx[:, :, None], idx[:, None, :]].sum(dim=(1, 2))                 # [k]
+        related = self.causal_t[idx[:, :, None], dom[None, None, :]].sum(dim=1)                 # [k, n]
+        vals = (idx.shape[1] - 1) * related / (total[:, None] - related) * 0.5
+        return torch.clamp(vals, min=0, max=1)
 
     # ---------------------------------------------------------------- cdc.py:314-319
     def _centers(self, group, center_num=1):
@@ -108,20 +120,21 @@ class Grouping:
         nd = self.n_domain
         s_group = self._centers(t_group, center_num=2)
         useful = True
+        P = None
+        if self.initial_s_group2domain_list is not None:           # constant over the growth loop
+            P = (1 - 2 * self._lambda(self.initial_s_group2domain_list[group_idx])) * torch.pow(self.w_t, 0.5)
         while useful and len(s_group) < nd:
-            rows = []
-            for d in range(nd):
-                rows.append(torch.zeros(len(t_group), dtype=torch.float32) if d in s_group else self._lambda(s_group + [d], t_group))
-            lam = torch.stack(rows, dim=0)
+            lam = torch.zeros(nd, len(t_group), dtype=torch.float32)
+            cands = [d for d in range(nd) if d not in s_group]
+            lam[cands] = self._lambda_candidates(s_group, cands, t_group)
             wt = self.w_t[t_group]
             sw = wt.sum()
             if sw != 0:
                 wt = wt / sw
             J = (((1 - lam) * self.A_t[:nd, t_group] + lam * self.B_t[:nd, t_group]) * wt).sum(dim=1)
-            if self.initial_s_group2domain_list is None:
+            if P is None:
                 result = J
             else:
-                P = (1 - 2 * self._lambda(self.initial_s_group2domain_list[group_idx])) * torch.pow(self.w_t, 0.5)
                 result = J + self.p_weight * P if self.max_better else J - self.p_weight * P
             result[s_group] = float(self.default_metric_value)
             best_value, best = torch.max(result, 0) if self.max_better else torch.min(result, 0)
