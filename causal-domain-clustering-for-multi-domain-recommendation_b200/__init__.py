@@ -10,9 +10,10 @@ from .ple import PLE, CGC  # noqa: F401
 from .mmoe import MMoE  # noqa: F401
 from .dcn import DCN, DCNv2, CrossNetwork, CrossNetV2, CrossNetMix  # noqa: F401
 from .star import STAR, MDR_BatchNorm, DNN  # noqa: F401
+from .autoint import AutoInt  # noqa: F401
 from .cdc import CDC  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from .data import DeviceLoader  # noqa: F401
 from . import parallel  # noqa: F401
 
-__all__ = ["PLE", "CGC", "MMoE", "DCN", "DCNv2", "STAR", "CDC", "Adam", "BaseModel", "GraphedTrainStep", "DeviceLoader"]
+__all__ = ["PLE", "CGC", "MMoE", "DCN", "DCNv2", "STAR", "AutoInt", "CDC", "Adam", "BaseModel", "GraphedTrainStep", "DeviceLoader"]

@@ -50,6 +50,9 @@ class AttnBlock:
         self.res = bool(model.att_res)
         self.scale = 1.0 / math.sqrt(self.dh)
         self.salts = [0xA77E0000 + i for i in range(self.n_layer)]
+        # the bias-free Linear over relu(block output).view(B, F*A): `atten_linear` for BaseModel.atten_forward (layer.py:82-83), the
+        # first F*A columns of `dnn_linear` for AutoInt (autoint.py:60-62)
+        self.head_name, self.head_off = getattr(model, "_att_head", ("atten_linear.weight", 0))
         # tensor-core path: TMA needs 16-byte aligned bf16 pitches (E, A multiples of 8), the core loads bf16 pairs
         self.can_bf16 = bool(rt.bf16 and self.E % 8 == 0 and self.A % 8 == 0 and self.dh % 2 == 0)
 
@@ -90,7 +93,7 @@ class AttnBlock:
             else:
                 rt.lin_fwd(o, A, rt.o(pre + "out_proj.weight"), A, rt.o(pre + "out_proj.bias"), y, M)
             cur = y
-        ops.lib.attn_pool_fwd(cur.ptr, rt.w("atten_linear.weight"), lin.ptr, lin.ld, 1, B, F * A, ops.stream)
+        ops.lib.attn_pool_fwd(cur.ptr, rt.w(self.head_name, self.head_off), lin.ptr, lin.ld, 1, B, F * A, ops.stream)
 
     # ---------------------------------------------------------------- backward: parameter gradients; dX += d(embed_x)
     def bwd(self, ws, X32: Mat, B, dlin: Mat, dX: Mat, train):
@@ -107,7 +110,7 @@ class AttnBlock:
         z = ws.mat(f"att.y{self.n_layer - 1}", M, A)
         dy = ws.mat("att.dz", M, A)
         sc = ops.scratch("attn_pool", ops.lib.attn_pool_scratch_bytes(B, F * A))
-        ops.lib.attn_pool_bwd(z.ptr, rt.w("atten_linear.weight"), dlin.ptr, dlin.ld, dy.ptr, rt.g("atten_linear.weight"), B, F * A,
+        ops.lib.attn_pool_bwd(z.ptr, rt.w(self.head_name, self.head_off), dlin.ptr, dlin.ld, dy.ptr, rt.g(self.head_name, self.head_off), B, F * A,
                               sc.data_ptr(), ops.stream)
         if self.res:
             ops.colsum(dy, M, A, rt.g("V_res_embedding.bias"))
@@ -158,7 +161,7 @@ class AttnBlock:
             else:
                 rt.lin_fwd(o, A, rt.o(pre + "out_proj.weight"), A, rt.o(pre + "out_proj.bias"), y, M)
             cur = y
-        ops.lib.attn_pool_fwd_bf16(cur.ptr, rt.w("atten_linear.weight"), lin.ptr, lin.ld, 1, B, F * A, ops.stream)
+        ops.lib.attn_pool_fwd_bf16(cur.ptr, rt.w(self.head_name, self.head_off), lin.ptr, lin.ld, 1, B, F * A, ops.stream)
 
     def _bwd_bf16(self, ws, X: Mat, B, dlin: Mat, dX: Mat, train):
         import torch
@@ -173,7 +176,7 @@ class AttnBlock:
         z = ws.mat(f"att.y{self.n_layer - 1}", M, A, bf)
         dy = ws.mat("att.dz", M, A, bf)
         sc = ops.scratch("attn_pool", ops.lib.attn_pool_scratch_bytes(B, F * A))
-        ops.lib.attn_pool_bwd_bf16(z.ptr, rt.w("atten_linear.weight"), dlin.ptr, dlin.ld, dy.ptr, rt.g("atten_linear.weight"), B, F * A,
+        ops.lib.attn_pool_bwd_bf16(z.ptr, rt.w(self.head_name, self.head_off), dlin.ptr, dlin.ld, dy.ptr, rt.g(self.head_name, self.head_off), B, F * A,
                                    sc.data_ptr(), ops.stream)
         if self.res:
             ops.colsum(dy, M, A, rt.g("V_res_embedding.bias"))

@@ -211,10 +211,12 @@ class Base:
         self._att_cache = None
 
     # ---------------------------------------------------------------- field self-attention (model/layer.py:58-84)
-    def enable_atten(self, atten_embed_dim, att_layer_num, att_head_num, att_res=True):
+    def enable_atten(self, atten_embed_dim, att_layer_num, att_head_num, att_res=True, head=("atten_linear.weight", 0)):
         """config.use_atten with config.atten_embed_dim / att_layer_num / att_head_num / att_res (config.py:24-28).  The block is
-        not regularised (none of the models registers its parameters, ple.py:42-48)."""
-        self.atten = dict(A=int(atten_embed_dim), n_layer=int(att_layer_num), H=int(att_head_num), res=bool(att_res))
+        not regularised (none of the models registers its parameters, ple.py:42-48).  head: (key, first column) of the bias-free
+        Linear over relu(block output).view(B, F*A) - `atten_linear` for BaseModel.atten_forward, the first F*A columns of
+        `dnn_linear` for AutoInt (autoint.py:60-62)."""
+        self.atten = dict(A=int(atten_embed_dim), n_layer=int(att_layer_num), H=int(att_head_num), res=bool(att_res), head=head)
         return self
 
     def atten_fwd(self, sd, e):
@@ -242,7 +244,8 @@ class Base:
         if a["res"]:
             cur = cur + linear_fwd(tok, sd["V_res_embedding.weight"], sd["V_res_embedding.bias"])
         r = np.maximum(cur, 0).reshape(B, F * A)
-        out = linear_fwd(r, sd["atten_linear.weight"])
+        hk, h0 = a["head"]
+        out = linear_fwd(r, sd[hk][:, h0:h0 + F * A])
         return out, dict(tok=tok, layers=layers, z=cur, r=r)
 
     def atten_bwd(self, sd, c, dout, grads):
@@ -253,8 +256,11 @@ class Base:
         tok = c["tok"]
         M = tok.shape[0]
         B = M // self.F
-        dr, dW, _ = linear_bwd(c["r"], sd["atten_linear.weight"], dout, has_bias=False)
-        _acc(grads, "atten_linear.weight", dW)
+        hk, h0 = a["head"]
+        dr, dW, _ = linear_bwd(c["r"], sd[hk][:, h0:h0 + self.F * A], dout, has_bias=False)
+        dfull = np.zeros_like(sd[hk])
+        dfull[:, h0:h0 + self.F * A] = dW
+        _acc(grads, hk, dfull)
         dy = (dr.reshape(M, A) * (c["z"] > 0)).astype(F32)
         dtok = np.zeros_like(tok)
         if a["res"]:
@@ -614,6 +620,44 @@ class DCN(Base):
         D = self.D
         dembed = cross_v1_bwd(sd, "cn", self.L, cache["xs"], dst[:, :D], grads)
         dembed = dembed + self.mlp.backward(sd, cache["mc"], dst[:, D:], grads)
+        self.embed_bwd(sd, cache["idx"], e, dembed, dz, grads)
+        return grads
+
+
+class AutoInt(Base):
+    """model/autoint.py:10-64: the field self-attention block (same stages as BaseModel.atten_forward, layer.py:71-84) whose
+    relu(output).view(B, F*A) is concatenated with an MLP over the flat embeddings; one bias-free Linear over the concatenation,
+    plus FeaturesLinear, sigmoid."""
+
+    def __init__(self, field_dims, embed_dim, atten_embed_dim=None, att_layer_num=3, att_head_num=2, att_res=True, mlp_dims=(256, 128),
+                 l2_reg_embedding=1e-5, l2_reg_linear=1e-5, l2_reg_dnn=1e-5, **_):
+        super().__init__(field_dims, embed_dim, l2_reg_embedding, l2_reg_linear)
+        A = embed_dim if atten_embed_dim is None else atten_embed_dim
+        self.enable_atten(A, att_layer_num, att_head_num, att_res, head=("dnn_linear.weight", 0))
+        self.FA = self.F * A
+        self.dnn = MLP("dnn", len(mlp_dims), True, False)
+        self.reg_prefixes = (("dnn", l2_reg_dnn),)
+
+    def forward(self, sd, x, train=True):
+        bufs = {}
+        e, idx = self.embed(sd, x)
+        att, ac = self.atten_fwd(sd, e)                                   # relu(cross_term) . dnn_linear.weight[:, :F*A]
+        mo, mc = self.dnn.forward(sd, e, train, bufs, self.drop)
+        lin = linear_fwd(e, sd["linear.fc.weight"], sd["linear.fc.bias"])
+        y = sigmoid(lin + att + mo @ sd["dnn_linear.weight"][:, self.FA:].T)
+        return y[:, 0], dict(idx=idx, e=e, ac=ac, mc=mc, mo=mo, y=y, bufs=bufs)
+
+    def backward(self, sd, cache, dy):
+        grads = {}
+        y, e = cache["y"], cache["e"]
+        dz = (dy.reshape(-1, 1) * y * (1 - y)).astype(e.dtype)
+        dmo, dW, _ = linear_bwd(cache["mo"], sd["dnn_linear.weight"][:, self.FA:], dz, has_bias=False)
+        dfull = np.zeros_like(sd["dnn_linear.weight"])
+        dfull[:, self.FA:] = dW
+        _acc(grads, "dnn_linear.weight", dfull)
+        dembed = self.dnn.backward(sd, cache["mc"], dmo, grads)
+        dembed = dembed + self.atten_bwd(sd, cache["ac"], dz, grads)
+        self._att_cache = None
         self.embed_bwd(sd, cache["idx"], e, dembed, dz, grads)
         return grads
 

@@ -30,7 +30,10 @@ ATTEN = {"ple_atten": dict(atten_embed_dim=8, att_layer_num=2, att_head_num=2, a
          "star_grouped_atten": dict(atten_embed_dim=8, att_layer_num=2, att_head_num=2, att_res=True)}
 ATTEN_CASES = {"ple_atten": CASES["ple"], "mmoe_atten": CASES["mmoe"], "star_atten": CASES["star"],
                "star_grouped_atten": CASES["star_grouped"]}
-ALL_CASES = {**CASES, **ATTEN_CASES}
+# AutoInt (model/autoint.py; tests/golden/make_golden_autoint.py): its L2 set has no l2_reg_cross
+AUTOINT_CASES = {"autoint": ("autoint", dict(atten_embed_dim=8, att_layer_num=3, att_head_num=2, att_res=True, mlp_dims=(16, 8)), "single", 3),
+                 "autoint_nores": ("autoint", dict(atten_embed_dim=None, att_layer_num=2, att_head_num=1, att_res=False, mlp_dims=(16,)), "single", 3)}
+ALL_CASES = {**CASES, **ATTEN_CASES, **AUTOINT_CASES}
 
 
 def load(name):

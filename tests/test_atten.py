@@ -8,7 +8,7 @@ import torch
 
 import cdcmdr_b200 as cm
 from oracle.host_abi import HostABI
-from tests.golden_cases import ATTEN, load, state
+from tests.golden_cases import ATTEN, AUTOINT_CASES, load, state
 from tests.util import build_model, run_golden_case
 
 
@@ -42,6 +42,56 @@ def test_attention_state_dict_keys_match_reference(name, emulator):
 @pytest.mark.parametrize("name", sorted(ATTEN))
 def test_attention_block_gpu(name, path):
     run_golden_case(name, "cuda", path=path)
+
+
+# ---- AutoInt (model/autoint.py:10-64): the same attention stack + an MLP branch under one bias-free Linear; fixtures from the
+# unmodified reference (tests/golden/make_golden_autoint.py)
+@pytest.mark.parametrize("path", ["fused", "autograd"])
+@pytest.mark.parametrize("name", sorted(AUTOINT_CASES))
+def test_autoint_host_logic(name, path, emulator):
+    run_golden_case(name, "cpu", path=path)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ["fused", "autograd"])
+@pytest.mark.parametrize("name", sorted(AUTOINT_CASES))
+def test_autoint_gpu(name, path):
+    run_golden_case(name, "cuda", path=path)
+
+
+@pytest.mark.gpu
+def test_autoint_bf16_path_gpu():
+    """AutoInt on the tensor-core path (bf16 token matrices, tcgen05 projections, mma.sync attention core) against its fp32 path on
+    identical weights: eval logits 2e-2, first step's BCE 2e-2, attention and head weights train."""
+    from tests.golden_cases import FIELD_DIMS
+    res, sd = {}, None
+    rng = np.random.default_rng(6)
+    B = 300
+    x = torch.from_numpy(np.stack([rng.integers(0, d, size=B) for d in FIELD_DIMS], axis=1).astype(np.int32)).cuda()
+    y = torch.from_numpy((rng.random(B) < 0.3).astype(np.int16)).cuda()
+    for prec in ("fp32", "bf16"):
+        class Cfg:
+            cdcmdr_precision = prec
+        torch.manual_seed(12)
+        m = cm.AutoInt(FIELD_DIMS, 8, atten_embed_dim=32, att_layer_num=2, att_head_num=2, att_res=True, mlp_dims=(32, 16), dropout=0.0,
+                       l2_reg_embedding=1e-3, l2_reg_linear=1e-3, l2_reg_dnn=1e-3, config=Cfg())
+        if sd is None:
+            sd = {k: v.clone() for k, v in m.state_dict().items()}
+        else:
+            m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        with torch.no_grad():
+            p = m(x).cpu().numpy().astype(np.float64)
+        m.train()
+        opt = cm.Adam(m.parameters(), lr=1e-3, betas=(0.9, 0.99), eps=1e-8, weight_decay=1e-8)
+        w0 = m.state_dict()["dnn_linear.weight"].clone()
+        bce = m.step_losses(m.train_step(x, y, opt, mode="col", col=0))[1]
+        moved = float((m.state_dict()["dnn_linear.weight"] - w0).abs().min())
+        res[prec] = (np.log(p) - np.log1p(-p), bce, moved)
+    l32, l16 = res["fp32"][0], res["bf16"][0]
+    assert np.abs(l16 - l32).max() <= 2e-2 * max(1.0, float(np.abs(l32).max()))
+    assert abs(res["bf16"][1] - res["fp32"][1]) <= 2e-2 * abs(res["fp32"][1])
+    assert res["fp32"][2] > 1e-5 and res["bf16"][2] > 1e-5          # every column of the head (attention part and MLP part) moved
 
 
 def _bf16_pair(kind, device):

@@ -5,7 +5,7 @@ import pytest
 from oracle import cdcmdr_oracle as O
 from tests.golden_cases import ALL_CASES as CASES, ATTEN, FIELD_DIMS, E, L2, load, state, strip
 
-KINDS = {"ple": O.PLE, "mmoe": O.MMoE, "dcn": O.DCN, "dcnv2": O.DCNv2, "star": O.STAR}
+KINDS = {"ple": O.PLE, "mmoe": O.MMoE, "dcn": O.DCN, "dcnv2": O.DCNv2, "star": O.STAR, "autoint": O.AutoInt}
 RTOL, ATOL = 1e-4, 2e-6      # north_star: fp32 logits and gradients within 1e-4 relative
 
 
@@ -16,7 +16,7 @@ def bias_before_bn(kind, k):
         return False
     if kind in ("ple", "mmoe") and k.startswith(("towers.", "experts.")):
         return int(k.split(".")[-2]) % 4 == 0 and not k.endswith("layers.8.bias")
-    if kind in ("dcn", "dcnv2") and k.startswith(("mlp.", "dnn.")):
+    if kind in ("dcn", "dcnv2", "autoint") and k.startswith(("mlp.", "dnn.")):
         return int(k.split(".")[-2]) % 4 == 0
     if kind == "star":      # PN beta (shared and per-domain) is also cancelled by the BN after the first FC
         return ".linears." in k or k == "shared_bn_bias" or k.startswith("domain_norm.")
@@ -43,7 +43,7 @@ def test_embedding_bit_exact():
 def test_train_steps_match_reference(name):
     kind, kw, mode, steps = CASES[name]
     gold = load(name)
-    model = KINDS[kind](FIELD_DIMS, E, **kw, **L2)
+    model = KINDS[kind](FIELD_DIMS, E, **kw, **{k: v for k, v in L2.items() if kind != "autoint" or k != "l2_reg_cross"})
     if name in ATTEN:                                        # config.use_atten (tests/golden/make_golden_atten.py)
         model.enable_atten(**ATTEN[name])
     sd = state(gold, 0)

@@ -18,7 +18,7 @@ class Cfg:
     ple_n_expert_shared = 1
 
 
-KIND_CLS = {"ple": "PLE", "mmoe": "MMoE", "dcn": "DCN", "dcnv2": "DCNv2", "star": "STAR"}
+KIND_CLS = {"ple": "PLE", "mmoe": "MMoE", "dcn": "DCN", "dcnv2": "DCNv2", "star": "STAR", "autoint": "AutoInt"}
 DOMAIN_IDX = 3
 
 
@@ -53,6 +53,8 @@ def build_model(name, probe=False, precision="fp32"):
         extra["config"] = cfg
     if kind == "star":
         extra["domain_idx"] = DOMAIN_IDX
+    if kind == "autoint":
+        return cls(FIELD_DIMS, E, dropout=0.0, config=cfg, **kw, **{k: v for k, v in L2.items() if k != "l2_reg_cross"})
     return cls(FIELD_DIMS, E, dropout=0.0, **kw, **extra, **L2)
 
 
