@@ -15,5 +15,6 @@ from .cdc import CDC  # noqa: F401
 from .graph import GraphedTrainStep  # noqa: F401
 from .data import DeviceLoader  # noqa: F401
 from . import parallel  # noqa: F401
+from . import metrics  # noqa: F401
 
 __all__ = ["PLE", "CGC", "MMoE", "DCN", "DCNv2", "STAR", "AutoInt", "CDC", "Adam", "BaseModel", "GraphedTrainStep", "DeviceLoader"]

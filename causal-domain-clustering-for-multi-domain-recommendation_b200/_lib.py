@@ -150,6 +150,8 @@ SIGNATURES = {
     "cdcmdr_ple_chain_ok": (INT, [I32, I32, I32, I32]),
     "cdcmdr_ple_chain_fwd": (INT, [C.POINTER(PleChain), P]),
     "cdcmdr_ple_chain_profile": (INT, [P]),
+    "cdcmdr_auc_logloss_scratch_bytes": (SZ, [I64, I32]),
+    "cdcmdr_auc_logloss": (INT, [P, P, INT, P, INT, I64, I32, P, P, P]),
     "cdcmdr_peer_allreduce_bytes": (SZ, [INT, I64]),
     "cdcmdr_peer_allreduce_f64": (INT, [P, INT, INT, P, P, I64, I64, P, P]),
     "cdcmdr_attn_fwd_bf16": (INT, [P, I64, P, I64, I64, INT, INT, INT, F32, F32, P, U32, P]),

@@ -460,6 +460,18 @@ int cdcmdr_ple_chain_fwd(const cdcmdr_ple_chain_t* p, cdcmdr_stream_t s);
 int cdcmdr_ple_chain_profile(uint64_t* counters16);
 
 /* ---------------------------------------------------------------------------------------------
+ * N4  evaluation metrics on the device (Run.test / evaluate_multi_domain, run.py:647-711: scikit-learn roc_auc_score and
+ *     log_loss over the whole set and per domain).  pred fp32 [n] probabilities; target int16 (or fp32) [n]; domain int32 (or
+ *     int64) [n] in [0, n_domain), or NULL = one set.  out double [n_domain, 4] = {AUC, log loss, positives, samples} per
+ *     domain: AUC = Mann-Whitney statistic with midranks for tied predictions (= the trapezoidal ROC integral), log loss with p
+ *     clipped to [FLT_EPSILON, 1 - FLT_EPSILON] as sklearn does for fp32 predictions; both NaN for a set with one class only (the
+ *     reference's `except ValueError` branch).  One stable sort by (domain, prediction) + fixed-order reductions: deterministic.
+ * ------------------------------------------------------------------------------------------- */
+size_t cdcmdr_auc_logloss_scratch_bytes(int64_t n, int32_t n_domain);
+int cdcmdr_auc_logloss(const float* pred, const void* target, int target_is_f32, const void* domain, int domain_is_i64,
+                       int64_t n, int32_t n_domain, double* out, void* scratch, cdcmdr_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------
  * (e) multi-GPU: small all-reduce over NVLink peer memory (cross-replica BatchNorm statistics - the per-feature
  *     (sum, sum of squares) between cdcmdr_bn_*_stats and cdcmdr_bn_*_apply - and the per-rank loss sums; the reference is a
  *     single-device program, layer.py:187 / run.py:484).  peer_bufs: DEVICE array of `world` pointers, entry r = rank r's symmetric

@@ -952,3 +952,37 @@ class HostABI:
             z1 = (A0f[:, e * d0:(e + 1) * d0] @ W1[e * d1:(e + 1) * d1].T).astype(np.float32) + b1[None, e * d1:(e + 1) * d1]
             H[:, e * d1:(e + 1) * d1] = f32_to_bf16(np.maximum(z1, F32(0))).reshape(B, d1)
         return 0
+
+    # ---- N4: AUC (midrank Mann-Whitney) + log loss per domain (cdcmdr_auc_logloss; run.py:677-711)
+    def auc_logloss_scratch_bytes(self, n, n_domain):
+        return 256
+
+    def auc_logloss(self, pred, target, target_is_f32, domain, domain_is_i64, n, n_domain, out, scratch, s):
+        o = _arr(out, n_domain * 4, np.float64)[:n_domain * 4].reshape(n_domain, 4)
+        o[...] = np.nan
+        if n == 0:
+            return 0
+        p = _arr(pred, n, np.float32)[:n]
+        y = _arr(target, n, np.float32 if target_is_f32 else np.int16)[:n].astype(np.float32)
+        d = _arr(domain, n, np.int64 if domain_is_i64 else np.int32)[:n].astype(np.int64) if domain else np.zeros(n, np.int64)
+        eps = np.finfo(np.float32).eps
+        pc = np.clip(p, eps, np.float32(1) - eps).astype(np.float64)
+        for k in range(n_domain):
+            m = d == k
+            cnt = int(m.sum())
+            pos = y[m] > 0
+            npos = int(pos.sum())
+            o[k, 2], o[k, 3] = npos, cnt
+            if npos == 0 or npos == cnt:
+                continue
+            pk = p[m]
+            order = np.argsort(pk, kind="stable")
+            sp = pk[order]
+            starts = np.flatnonzero(np.concatenate([[True], sp[1:] != sp[:-1]]))
+            lens = np.diff(np.concatenate([starts, [cnt]]))
+            mid = np.repeat(starts + 0.5 * (lens + 1), lens)                    # 1-based midranks in sorted order
+            ranks = np.empty(cnt)
+            ranks[order] = mid
+            o[k, 0] = (ranks[pos].sum() - npos * (npos + 1) / 2.0) / (npos * (cnt - npos))
+            o[k, 1] = -(np.log(pc[m][pos]).sum() + np.log(1.0 - pc[m][~pos]).sum()) / cnt
+        return 0
