@@ -73,6 +73,13 @@ class CDC(BaseModel):
         self.domain2group_list = d2g
         self._install_domain2group(d2g)
         self._grouping.domain2group_list = list(d2g)
+        # the source / target domain sets that go with an assignment installed by hand: every cluster trains on its own members
+        # (what update_group leaves behind when no cluster borrows domains; run.py:580-592 indexes these lists by cluster id)
+        members = [[d for d in range(self.n_domain) if d2g[d] == g] for g in range(self.n_cluster)]
+        self.s_group2domain_list = [list(m) for m in members]
+        self.t_group2domain_list = [list(m) for m in members]
+        self._grouping.s_group2domain_list = [list(m) for m in members]
+        self._grouping.t_group2domain_list = [list(m) for m in members]
 
     def _install_domain2group(self, d2g):
         """In place: a captured CUDA graph (mode 'gather') addresses this tensor; the generation counter tells GraphedTrainStep
