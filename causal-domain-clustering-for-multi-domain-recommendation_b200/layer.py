@@ -391,6 +391,10 @@ class BaseModel(nn.Module):
     def _shape_pred(self, pred, **kw):
         return pred
 
+    def _global_rows(self, B, R, **kw):
+        """rows the mean of the loss runs over: the routed rows R on one device, the GLOBAL batch under data-parallel replicas"""
+        return self._rt.dp.global_rows(B) if self._rt.dp is not None else R
+
     def _head_shape(self, B, **kw):
         """(rows, columns) of the logits the program produced for a B-row batch.  Called after _program_fwd: STAR with row
         routing produces one column and only the routed rows (star.py:112-114)."""
@@ -536,9 +540,7 @@ class BaseModel(nn.Module):
         psel = ws.get("psel", (B,))
         sums = ws.get("loss_sums", (4,), torch.float64)      # [bce_sum, table_sumsq, reg_dense, -]; [0:2] are per-rank partial sums
         dp = rt.dp
-        if dp is not None and R != B:
-            raise NotImplementedError("cdcmdr: row routing is single-device")
-        n_global = dp.global_rows(B) if dp is not None else R
+        n_global = self._global_rows(B, R, **kw)
         dlogits = ws.get("dlogits", (R, T))
         dlin = self._dlin_mat(ws, B)
         y, sel = self._route_targets(ws, y, sel, B, **kw)
@@ -556,7 +558,8 @@ class BaseModel(nn.Module):
 
         def dense_update():
             rt.ops.reg_l2_sum(rt.W, rt.L2, 0.0, rt.W.numel(), sums[2:3])
-            rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present_b1 if B == 1 else rt.present, rt.W.numel(), rt.step_state)
+            rt.ops.adam_dense(rt.W, rt.G, rt.M, rt.V, rt.L2, rt.present_b1 if rt.batch_rows(B) == 1 else rt.present, rt.W.numel(),
+                              rt.step_state)
 
         def table_update():
             if self._table_state is None:

@@ -132,6 +132,7 @@ class DataParallel:
         self.row0, self.row1 = self.row_range[self.rank]
         self._dev_state = None
         self._moments = None
+        self.rows_override = None
         self.peer = None
         dev = emb.embedding_dict.weight.device
         if dev.type == "cuda" and self.world > 1 and os.environ.get("CDCMDR_PEER", "1") != "0":
@@ -155,6 +156,10 @@ class DataParallel:
 
     # ---------------------------------------------------------------- collectives (plumbing only)
     def global_rows(self, B):
+        """rows of the single-device batch this rank's B rows are a slice of.  A model whose towers see different row counts per
+        rank (STAR with row routing) announces the tower's GLOBAL count through `rows_override` around that tower's launches."""
+        if self.rows_override is not None:
+            return int(self.rows_override)
         return B * self.world
 
     def all_reduce_sum(self, t: torch.Tensor):

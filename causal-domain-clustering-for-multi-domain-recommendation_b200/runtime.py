@@ -188,6 +188,11 @@ class Runtime:
         self.ops.cast_f32_bf16(m, out, rows, cols)
         return out
 
+    def batch_rows(self, B) -> int:
+        """rows of the single-device batch behind this rank's B rows: BatchNorm is skipped on a ONE-row batch (layer.py:202-204) -
+        under data-parallel replicas that is a statement about the global batch"""
+        return self.dp.global_rows(B) if self.dp is not None else B
+
     # ---------------------------------------------------------------- BatchNorm (cross-replica when data-parallel)
     def bn_fwd(self, desc, Z: Mat, A: Mat, B, Cn):
         if self.dp is not None and desc.train:
@@ -221,6 +226,9 @@ class Runtime:
 
     def lin_bwd_w(self, dY: Mat, X: Mat, K, w_off, N, M, *, G=1, x_gs=0):
         """dW[g][n, k] = sum_m dY[g][m, n] * X[g][m, k]  -> gradient arena at w_off (+ g*N*K)."""
+        if M == 0:                                               # a replica without rows for this group (routed STAR tower): zero gradient
+            self.G[w_off:w_off + G * N * K].zero_()
+            return
         gaddr = self.G.data_ptr() + 4 * w_off
         if X.is_bf16:
             assert dY.is_bf16
@@ -326,7 +334,7 @@ class MlpGroup:
 
     def fwd(self, ws: Workspace, X: Mat, B, train) -> Mat:
         rt, G = self.rt, self.G
-        use_bn = self.bn and B != 1                              # layer.py:202-204
+        use_bn = self.bn and rt.batch_rows(B) != 1               # layer.py:202-204
         drop = rt.dropout if train else 0.0
         prev, prev_d = X, self.in_dim
         for j, d in enumerate(self.dims):
@@ -359,7 +367,7 @@ class MlpGroup:
         post_act_grad: the caller always hands the post-activation gradient (DCN / DCNv2 heads); a BatchNorm group that skips its
         BatchNorm on a single row (layer.py:202-204) then applies the ReLU / dropout mask itself."""
         rt, G, nl = self.rt, self.G, len(self.dims)
-        use_bn = self.bn and B != 1
+        use_bn = self.bn and rt.batch_rows(B) != 1
         drop = rt.dropout if train else 0.0
         keep = 1.0 / (1.0 - drop) if drop > 0 else 1.0
         d_last = self.dims[-1]

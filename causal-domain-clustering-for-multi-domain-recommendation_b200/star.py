@@ -163,7 +163,15 @@ class STAR(BaseModel):
         n = st[T]
         esz = X.t.element_size()
         rt.ops.lib.permute_rows(X.ptr, X.ld, perm.data_ptr(), n, D, esz, Xp.ptr, Xp.ld, 0, rt.ops.stream)
-        return dict(perm=perm, starts=st, n=n, Xp=Xp)
+        gcount = [st[t + 1] - st[t] for t in range(T)]
+        if rt.dp is not None:
+            # data-parallel replicas route their own rows; a tower's BatchNorm statistics, its one-row rule (star.py:94, 134) and
+            # the mean of the loss are statements about the GLOBAL batch: the towers' row counts summed over the ranks
+            import torch.distributed as dist
+            cg = torch.tensor(gcount, dtype=torch.int64, device=counts.device)
+            dist.all_reduce(cg, group=rt.dp.group)
+            gcount = [int(v) for v in cg.tolist()]
+        return dict(perm=perm, starts=st, n=n, Xp=Xp, gcount=gcount, n_global=sum(gcount))
 
     def _head_shape(self, B, x_group=None):
         if x_group is None:
@@ -186,9 +194,13 @@ class STAR(BaseModel):
             y = self._permute_targets(y)
         return y, sel
 
+    def _global_rows(self, B, R, x_group=None):
+        if x_group is not None and self._rt.dp is not None:
+            return self._route["n_global"]
+        return super()._global_rows(B, R)
+
     def _bump_batches_tracked(self, B):
-        rows = [B] * self.n_tower if self._route is None else [self._route["starts"][t + 1] - self._route["starts"][t]
-                                                                for t in range(self.n_tower)]
+        rows = [self._rt.batch_rows(B)] * self.n_tower if self._route is None else list(self._route["gcount"])
         for t, n in enumerate(rows):
             if n <= 1:                                        # star.py:134 (one row: PN returns its input), star.py:94; no rows: tower idle
                 continue
@@ -250,23 +262,29 @@ class STAR(BaseModel):
             hall = ws.mat("star.pn_all", B, T * D, rt.act_dtype)
             for t in range(T):
                 blk = Mat(hall.t, t * D, T * D)
-                if B == 1:                                   # star.py:134-135: PN is the identity on a single row
+                if rt.batch_rows(B) == 1:                    # star.py:134-135: PN is the identity on a single row
                     ops.copy2d(Xs.ptr, Xs.ld, blk.ptr, blk.ld, B, D, Xs.t.element_size())
                 else:
                     rt.bn_fwd(self._pn_desc(ws, t, train, True), x32, blk, B, D)
             return self._towers_all.fwd(ws, hall, B, train), lin
-        for t, (r0, n) in enumerate(slices):
-            if n == 0:
-                continue
-            xin32 = x32.rows(r0)
-            if n == 1:                                       # star.py:134-135: PN is the identity on a single row
-                hin = Xs.rows(r0)
-            else:
-                hin = ws.mat(f"star.pn{t}", n, D, rt.act_dtype)
-                rt.bn_fwd(self._pn_desc(ws, t, train, True), xin32, hin, n, D)
-            lt = self._towers[t].fwd(ws, hin, n, train)
-            dst = Mat(logits.t, t, T) if x_group is None else logits.rows(r0)
-            ops.add2d(lt, dst, n, 1, False)
+        gcount = self._route["gcount"]
+        try:
+            for t, (r0, n) in enumerate(slices):
+                if gcount[t] == 0:                           # nobody has a row for this tower
+                    continue
+                if rt.dp is not None:
+                    rt.dp.rows_override = gcount[t]          # the tower's rows over all replicas (a replica may hold none of them)
+                xin32 = x32.rows(r0)
+                if gcount[t] == 1:                           # star.py:134-135: PN is the identity on a single row
+                    hin = Xs.rows(r0)
+                else:
+                    hin = ws.mat(f"star.pn{t}", n, D, rt.act_dtype)
+                    rt.bn_fwd(self._pn_desc(ws, t, train, True), xin32, hin, n, D)
+                lt = self._towers[t].fwd(ws, hin, n, train)
+                ops.add2d(lt, logits.rows(r0), n, 1, False)
+        finally:
+            if rt.dp is not None:
+                rt.dp.rows_override = None
         return logits, lin
 
     def _program_bwd(self, ws, X: Mat, B, train, dlogits: Mat, x_group=None):
@@ -290,7 +308,7 @@ class STAR(BaseModel):
             self._towers_all.bwd(ws, hall, dlogits, B, train, dhall)
             for t in range(T):
                 dh = Mat(dhall.t, t * D, T * D)
-                if B == 1:
+                if rt.batch_rows(B) == 1:
                     ops.add2d(dh, dXs, B, D, t > 0)
                     continue
                 dprod = rt.w("star.pn_dprod")
@@ -302,27 +320,30 @@ class STAR(BaseModel):
                 ops.ewise(dprod, rt.w("star.pn_gamma", t * D), rt.g("shared_bn_weight"), D, 2)           # dgamma_s += dprod * gamma_t
                 ops.ewise(rt.g("star.pn_beta", t * D), dprod, rt.g("shared_bn_bias"), D, 3)              # dbeta_s += dbeta_t
             slices = []
-        for t, (r0, n) in enumerate(slices):
-            if n == 0:
-                continue
-            dl = Mat(dlogits.t, t, T) if not routed else dlogits.rows(r0)
-            hin = Xs.rows(r0) if n == 1 else ws.mat(f"star.pn{t}", n, D, rt.act_dtype)
-            dh = ws.mat("star.dh", n, D)
-            self._towers[t].bwd(ws, hin, dl, n, train, dh)
-            tgt = dXs.rows(r0)
-            acc = (not routed) and not first
-            if n == 1:
-                ops.add2d(dh, tgt, n, D, acc)
-            else:
-                dprod = rt.w("star.pn_dprod")
-                dz = ws.mat("star.dpn", n, D) if acc else tgt
-                rt.bn_bwd(self._pn_desc(ws, t, train, False), x32.rows(r0), None, dh, dz, dprod, rt.g("star.pn_beta", t * D), False, n, D)
-                if acc:
-                    ops.add2d(dz, tgt, n, D, True)
-                ops.ewise(dprod, rt.w("shared_bn_weight"), rt.g("star.pn_gamma", t * D), D, 0)          # dgamma_t = dprod * gamma_s
-                ops.ewise(dprod, rt.w("star.pn_gamma", t * D), rt.g("shared_bn_weight"), D, 2)           # dgamma_s += dprod * gamma_t
-                ops.ewise(rt.g("star.pn_beta", t * D), dprod, rt.g("shared_bn_bias"), D, 3)              # dbeta_s += dbeta_t
-            first = False
+        gcount = self._route["gcount"] if routed else []
+        try:
+            for t, (r0, n) in enumerate(slices):
+                if gcount[t] == 0:
+                    continue
+                if rt.dp is not None:
+                    rt.dp.rows_override = gcount[t]
+                one = gcount[t] == 1
+                dl = dlogits.rows(r0)
+                hin = Xs.rows(r0) if one else ws.mat(f"star.pn{t}", n, D, rt.act_dtype)
+                dh = ws.mat("star.dh", n, D)
+                self._towers[t].bwd(ws, hin, dl, n, train, dh)
+                tgt = dXs.rows(r0)
+                if one:
+                    ops.add2d(dh, tgt, n, D, False)
+                else:
+                    dprod = rt.w("star.pn_dprod")
+                    rt.bn_bwd(self._pn_desc(ws, t, train, False), x32.rows(r0), None, dh, tgt, dprod, rt.g("star.pn_beta", t * D), False, n, D)
+                    ops.ewise(dprod, rt.w("shared_bn_weight"), rt.g("star.pn_gamma", t * D), D, 0)          # dgamma_t = dprod * gamma_s
+                    ops.ewise(dprod, rt.w("star.pn_gamma", t * D), rt.g("shared_bn_weight"), D, 2)           # dgamma_s += dprod * gamma_t
+                    ops.ewise(rt.g("star.pn_beta", t * D), dprod, rt.g("shared_bn_bias"), D, 3)              # dbeta_s += dbeta_t
+        finally:
+            if rt.dp is not None:
+                rt.dp.rows_override = None
         self._chain(slices)
         # wide linear (layer.py:115-126) on the rows the towers saw
         dlin = self._dlin_mat(ws, B)

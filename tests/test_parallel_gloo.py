@@ -238,3 +238,92 @@ def test_row_range_sharded_table_matches_one_process(kind, world):
     for r in range(world):
         r0, r1 = ranks[r]["__rows"]
         assert np.abs(ranks[r][key][:r1 - r0] - sd[key][r0:r1]).max() <= 2e-6, r
+
+
+# ------------------------------------------------------------------------------------------------ row-routed STAR on replicas
+def _star_build():
+    torch.manual_seed(5)
+    cfg = Cfg(); cfg.cdcmdr_precision = "fp32"
+    m = cm.STAR(FD, E, T, (16, 8), domain_idx=DOM, dropout=0.0, config=cfg, **L2)
+    with torch.no_grad():
+        m.shared_bn_weight.uniform_(0.5, 1.5); m.shared_bn_bias.normal_(0, 0.1)
+    return m
+
+
+def _star_groups(B):
+    rng = np.random.default_rng(9)
+    g = rng.integers(-1, T, size=B).astype(np.int64)          # -1: rows outside every tower are dropped (star.py:85-87)
+    g[: B // 2][g[: B // 2] == 2] = 0                         # tower 2 has rows on the second rank only
+    return g
+
+
+def _star_steps(model, x, y, g, n):
+    opt = cm.Adam(model.parameters(), **ADAM)
+    model.train()
+    outs = []
+    for _ in range(n):
+        out = model.train_step(torch.from_numpy(x), torch.from_numpy(y), opt, mode="col", col=0, x_group=torch.from_numpy(g).view(-1, 1))
+        outs.append((out["pred"].clone().numpy().reshape(-1), model.step_losses(out)))
+    return outs
+
+
+def _star_worker(rank, world, port, B, n_steps, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cm._lib.install(HostABI())
+        model = _star_build()
+        cm.parallel.attach_data_parallel(model)
+        x, y, _ = _data(B)
+        g = _star_groups(B)
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        outs = _star_steps(model, x[lo:hi], y[lo:hi], g[lo:hi], n_steps)
+        sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        np.savez(os.path.join(path, f"rank{rank}.npz"), **sd,
+                 **{f"pred{i}": o[0] for i, o in enumerate(outs)}, **{f"loss{i}": np.array(o[1]) for i, o in enumerate(outs)})
+    finally:
+        dist.destroy_process_group()
+
+
+def test_row_routed_star_on_two_replicas_matches_one_process():
+    """STAR's row-routed mode (star.py:84-114: tower t sees only the rows of group t) on data-parallel replicas: every rank
+    partitions its own rows, a tower's partitioned-norm / BatchNorm statistics and the loss mean run over the tower's rows on ALL
+    ranks (one tower has rows on one rank only, some rows belong to no tower) - against one process on the concatenated batch."""
+    B, n_steps, world = 96, 3, 2
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_star_worker, args=(world, _free_port(), B, n_steps, tmp), nprocs=world, join=True)
+        ranks = [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
+    old = cm._lib._LIB
+    cm._lib.install(HostABI())
+    try:
+        model = _star_build()
+        x, y, _ = _data(B)
+        g = _star_groups(B)
+        ref = _star_steps(model, x, y, g, n_steps)
+        sd = {k: v.detach().numpy() for k, v in model.state_dict().items()}
+    finally:
+        cm._lib.install(old)
+
+    def order(gv):                                            # sample indices in partition order
+        return np.concatenate([np.flatnonzero(gv == t) for t in range(T)])
+    whole = order(g)
+    for i in range(n_steps):
+        want = dict(zip(whole.tolist(), ref[i][0].tolist()))
+        for r in range(world):
+            lo, hi = r * B // world, (r + 1) * B // world
+            mine = lo + order(g[lo:hi])
+            got = ranks[r][f"pred{i}"]
+            assert len(got) == len(mine)
+            assert max(abs(got[k] - want[int(s)]) for k, s in enumerate(mine)) <= 2e-6
+            assert np.allclose(ranks[r][f"loss{i}"], np.array(ref[i][1]), rtol=1e-5, atol=1e-7), (i, r)
+    for k, v in sd.items():
+        for r in range(world):
+            got = ranks[r][k]
+            if k.endswith("num_batches_tracked"):
+                assert int(got) == int(v), k
+                continue
+            assert np.array_equal(got, ranks[0][k]), k
+            if bias_before_bn("star", k) or k.endswith("running_mean"):
+                assert np.abs(got - v).max() <= 2.1e-3 * n_steps, k
+                continue
+            assert np.abs(got - v).max() <= 2e-5 * max(1.0, float(np.abs(v).max())), (k, float(np.abs(got - v).max()))
