@@ -208,6 +208,11 @@ class CDC(BaseModel):
                          out.data_ptr(), sc.data_ptr(), rt.ops.stream)
 
     # ---------------------------------------------------------------- the affinity-matrix probing loop (run.py:528-594)
+    # default cap on the rows of one batched probe evaluation: the activations of 30 x 65 536 rows are ~25 GB, which together with
+    # the training workspaces of the probe steps overflows the workspace budget (Runtime.WS_MAX_BYTES) and turns every probe into
+    # a re-allocation; 2^19 rows keep one probe evaluation at ~7 GB with identical numbers
+    PROBE_ROWS = 1 << 19
+
     def update_matrix_cdc(self, get_domain_data, optimizer, update_matrix_step, rng=None, probe_rows=None):
         """`Run.update_matrix_cdc` (run.py:528-594) as one call: snapshot -> for every probe {k fused training steps on a domain
         (multi)set -> one batched evaluation of all domains -> restore} -> update_group().  Returns the new domain2group_list
@@ -238,7 +243,8 @@ class CDC(BaseModel):
 
         def probe():                                                 # cdc_test_all_domain (run.py:550-558)
             self.eval()
-            return self.probe_all_domains([get_domain_data(d) for d in range(n_domain)], max_rows=probe_rows)
+            return self.probe_all_domains([get_domain_data(d) for d in range(n_domain)],
+                                          max_rows=probe_rows if probe_rows is not None else self.PROBE_ROWS)
 
         self.save_model_state()
         for line_i in range(self.n_causal_mask):                     # treatment rows (run.py:563-569)
