@@ -153,6 +153,8 @@ class CDC(BaseModel):
         Returns a float32 tensor [len(batches)] on the model's device; the caller assigns it to matrix_mask / matrix_A / matrix_B."""
         if self.use_metric != 'loss':
             return self._probe_per_domain(batches)                # 'auc': scikit-learn on the host per domain, as upstream
+        if max_rows is None:
+            max_rows = self.PROBE_ROWS
         n_seg = len(batches)
         dev = batches[0][0].device
         out = torch.empty(n_seg, dtype=torch.float32, device=dev)
