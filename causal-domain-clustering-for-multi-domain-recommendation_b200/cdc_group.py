@@ -99,8 +99,10 @@ class Grouping:
         (checked bit for bit against it: torch reduces each [m, m] / [m, n] slice of the stacked tensor like the lone matrix)."""
         idx = torch.as_tensor([list(s_group) + [d] for d in cands], dtype=torch.int64)          # [k, m+1]
         dom = torch.as_tensor(list(domain), dtype=torch.int64)
-        total = self.causal_t[idx[:, :, None], idx[:, None, :]].sum(dim=(1, 2))                 # [k]
-        related = self.causal_t[idx[:, :, None], dom[None, None, :]].sum(dim=1)                 # [k, n]
+        k, m1 = idx.shape
+        rows = self.causal_t.index_select(0, idx.reshape(-1)).view(k, m1, self.n_domain)        # rows of every candidate group
+        total = torch.gather(rows, 2, idx[:, None, :].expand(k, m1, m1)).sum(dim=(1, 2))        # [k]
+        related = rows.index_select(2, dom).sum(dim=1)                                          # [k, n]
         vals = (idx.shape[1] - 1) * related / (total[:, None] - related) * 0.5
         return torch.clamp(vals, min=0, max=1)
 
