@@ -401,6 +401,8 @@ def ours_arm(args):
         ms, ms_e2e = float(t[0]), float(t[1])
     else:
         ms_e2e = max(ms_e2e, wall_e2e)
+    if args.trace:
+        kernel_trace(args.trace, run_resident, barrier, rank, torch)
     roof = dominant_kernel_roofline(base, B, torch) if rank == 0 else None
     emb = embedding_bandwidth(base, dev_batches[0][0], B, torch) if rank == 0 else None
     amort = None
@@ -453,6 +455,45 @@ def ours_arm(args):
     if world > 1:
         sys.stdout.flush(); sys.stderr.flush()
         os._exit(0)
+
+
+def kernel_trace(path, run_resident, barrier, rank, torch, steps=4):
+    """Diagnostic (not a bench value): CUPTI kernel records of a few resident steps on every rank, rank 0 writes per-kernel totals
+    per stream and the busy / idle time of the step's span.  This is how an N-rank step is read when ncu cannot be used on it."""
+    from torch.profiler import profile, ProfilerActivity
+    barrier()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        run_resident(steps)
+        barrier()
+    if rank != 0:
+        return
+    prof.export_chrome_trace(path + ".chrome.json")
+    ev = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+    rows = {}
+    spans = []
+    for e in ev:
+        t0, t1 = e.time_range.start, e.time_range.end
+        spans.append((t0, t1))
+        k = (e.name[:90])
+        r = rows.setdefault(k, [0, 0.0])
+        r[0] += 1; r[1] += (t1 - t0)
+    spans.sort()
+    busy, cur0, cur1 = 0.0, None, None
+    for t0, t1 in spans:
+        if cur1 is None or t0 > cur1:
+            if cur1 is not None:
+                busy += cur1 - cur0
+            cur0, cur1 = t0, t1
+        else:
+            cur1 = max(cur1, t1)
+    if cur1 is not None:
+        busy += cur1 - cur0
+    total = spans[-1][1] - spans[0][0] if spans else 0.0
+    with open(path, "w") as f:
+        f.write(f"# {steps} steps: span {total:.1f} us, union of kernel intervals {busy:.1f} us, sum of kernel times "
+                f"{sum(r[1] for r in rows.values()):.1f} us\n")
+        for k, (n, t) in sorted(rows.items(), key=lambda kv: -kv[1][1]):
+            f.write(f"{t / steps:10.1f} us/step {n / steps:6.1f} launches/step  {k}\n")
 
 
 def _time_launch(fn, torch, n=10, warm=3):
@@ -598,6 +639,7 @@ def main():
     ap.add_argument("--batch", type=int, default=65536)
     ap.add_argument("--cpu-batch", type=int, default=8192)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--trace", default=None, help="diagnostic: write per-kernel CUPTI totals of a few steps to this file")
     ap.add_argument("--no-amortised", action="store_true", help="skip the update_matrix_cdc timing behind cdc_amortised")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="--impl reference: stop timing after this many seconds")
     args = ap.parse_args()
