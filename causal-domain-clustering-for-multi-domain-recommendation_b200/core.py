@@ -47,6 +47,7 @@ class Workspace:
     def __init__(self, device):
         self.device = device
         self.bufs = {}
+        self.marks = set()                                      # one-time initialisations done on these buffers
 
     def get(self, name, shape, dtype=torch.float32, zero=False) -> torch.Tensor:
         key = name

@@ -905,6 +905,30 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, int64_t lds,
     dst[r * ldd + c] = f32_to_bf16(src[r * lds + c]);
   }
 }
+// four elements per thread (128-bit fp32 side, 64-bit bf16 side): the scalar kernels above spend a 64-bit division per element
+__global__ void __launch_bounds__(256)
+cast_f32_bf16_vec4_kernel(const float* __restrict__ src, int64_t lds, uint16_t* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols4) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r, c; split_idx(i, cols4, r, c);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src + r * lds) + c);
+    *reinterpret_cast<uint2*>(dst + r * ldd + 4 * c) = make_uint2(pack_bf16x2(t.x, t.y), pack_bf16x2(t.z, t.w));
+  }
+}
+__global__ void __launch_bounds__(256)
+cast_bf16_f32_vec4_kernel(const uint16_t* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols4,
+                          int accumulate) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r, c; split_idx(i, cols4, r, c);
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(src + r * lds) + c);
+    float4 t = make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16),
+                           __uint_as_float(u.y & 0xffff0000u));
+    float4* o = reinterpret_cast<float4*>(dst + r * ldd) + c;
+    if (accumulate) { const float4 a = *o; t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w; }
+    *o = t;
+  }
+}
 __global__ void cast_bf16_f32_kernel(const uint16_t* __restrict__ src, int64_t lds, float* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols, int accumulate) {
   const int64_t total = rows * cols;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -1421,14 +1445,20 @@ extern "C" int cdcmdr_adam_dense(float* w, const float* grad, float* m, float* v
 
 extern "C" int cdcmdr_cast_f32_bf16(const float* src, int64_t lds, uint16_t* dst, int64_t ldd, int64_t rows, int64_t cols, cdcmdr_stream_t s) {
   if (rows <= 0 || cols <= 0) return 0;
-  cast_f32_bf16_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols);
+  if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src % 16) == 0 && ((uintptr_t)dst % 8) == 0)
+    cast_f32_bf16_vec4_kernel<<<grid_1d(rows * (cols / 4), 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols / 4);
+  else
+    cast_f32_bf16_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols);
   CDC_LAUNCHED();
   return 0;
 }
 extern "C" int cdcmdr_cast_bf16_f32(const uint16_t* src, int64_t lds, float* dst, int64_t ldd, int64_t rows, int64_t cols, int accumulate,
                                     cdcmdr_stream_t s) {
   if (rows <= 0 || cols <= 0) return 0;
-  cast_bf16_f32_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols, accumulate);
+  if (cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ((uintptr_t)src % 8) == 0 && ((uintptr_t)dst % 16) == 0)
+    cast_bf16_f32_vec4_kernel<<<grid_1d(rows * (cols / 4), 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols / 4, accumulate);
+  else
+    cast_bf16_f32_kernel<<<grid_1d(rows * cols, 256), 256, 0, to_stream(s)>>>(src, lds, dst, ldd, rows, cols, accumulate);
   CDC_LAUNCHED();
   return 0;
 }

@@ -328,10 +328,12 @@ class BaseModel(nn.Module):
         if not (rt.bf16 and getattr(self, "_x_ones_col", False)):
             return ws.mat("X", B, D, rt.act_dtype)
         ld = D + 8
-        fresh = "X" not in ws.bufs or ws.bufs["X"].numel() < B * ld
+        if "X" not in ws.bufs or ws.bufs["X"].numel() < B * ld:
+            ws.marks.discard("X.ones")
         X = ws.mat("X", B, ld, rt.act_dtype, zero=True)
-        if fresh:
+        if "X.ones" not in ws.marks:
             X.t[:B * ld].view(B, ld)[:, D] = 1.0
+            ws.marks.add("X.ones")
         return X
 
     def _gather(self, ws, x, B, plan_ahead=False):
@@ -340,6 +342,8 @@ class BaseModel(nn.Module):
         table = self.embedding.embedding_dict.weight
         if rt.bf16 and (F * E) % 8:
             raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
+        if rt.dp is not None and rt.dp.shard:
+            rt.dp.prepare_ws(ws, B)                            # peer exchange: X is the symmetric buffer the owners store into
         X = self._x_mat(ws, B)
         if rt.dp is not None and rt.dp.shard:
             rt.dp.embed_forward(ws, x, B, X, plan_ahead)   # row-sharded table: indices to the owners, rows back (parallel.py)

@@ -111,6 +111,51 @@ class PeerReduce:
                                     self.seq.data_ptr(), stream)
 
 
+class PeerExchange:
+    """The embedding exchange of one batch size over NVLink peer memory (csrc/dp_exchange.cu): every rank's index inbox, gathered
+    matrix X and gradient inbox live in ONE symmetric allocation; owners store rows straight into the requesters' X, requesters
+    store indices / row gradients straight into the owners' inboxes; `cdcmdr_peer_barrier` orders the phases.  torch's
+    symmetric-memory allocator only provides the buffer and its peer mappings (plumbing).
+
+    Slots of the barrier: 0 = everybody finished the previous use of the inboxes, 1 = indices landed, 2 = rows landed,
+    3 = row gradients landed."""
+    N_SLOTS = 4
+
+    def __init__(self, dp, B, device, lib):
+        import torch.distributed._symmetric_memory as symm
+        self.lib, self.B = lib, int(B)
+        N, E, F = dp.world, dp.E, dp.F
+        self.world, self.rank = N, dp.rank
+        nf_max = max(max(dp.nf), 1)
+        a256 = lambda n: (int(n) + 255) & ~255
+        self.x_cols = F * E + 8                                 # room for either pitch of BaseModel._x_mat
+        sizes = dict(flags=a256(self.N_SLOTS * N * 8), ids=a256(N * B * nf_max * 4), x=a256(B * self.x_cols * 4),
+                     grads=a256(N * B * nf_max * E * 4))
+        self.off, o = {}, 0
+        for k, v in sizes.items():
+            self.off[k] = o
+            o += v
+        self.buf = symm.empty(o, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, dp.group.group_name)
+        bases = [int(p) for p in self.handle.buffer_ptrs]
+        dev_ptrs = lambda key: torch.tensor([b + self.off[key] for b in bases], dtype=torch.int64, device=device)
+        self.flag_ptrs, self.ids_ptrs, self.x_ptrs, self.grad_ptrs = (dev_ptrs(k) for k in ("flags", "ids", "x", "grads"))
+        self.seqs = torch.zeros(self.N_SLOTS, dtype=torch.int64, device=device)
+        self.fbound = torch.tensor([f0 for f0, _ in dp.ranges] + [dp.ranges[-1][1]], dtype=torch.int32, device=device)
+        self.sizes = sizes
+        torch.cuda.synchronize(device)
+        dist.barrier(dp.group)                                  # nobody stores into a buffer its owner has not zeroed yet
+
+    def view(self, key, dtype, numel):
+        esz = torch.empty(0, dtype=dtype).element_size()
+        assert numel * esz <= self.sizes[key]
+        return self.buf[self.off[key]:self.off[key] + numel * esz].view(dtype)
+
+    def barrier(self, slot, stream):
+        self.lib.peer_barrier(self.flag_ptrs.data_ptr(), self.rank, self.world, slot, self.N_SLOTS, self.seqs.data_ptr(), stream)
+
+
 class DataParallel:
     def __init__(self, model, group=None, shard_embedding=True):
         if not dist.is_initialized():
@@ -134,6 +179,8 @@ class DataParallel:
         self._moments = None
         self.rows_override = None
         self.peer = None
+        self._px_used = None
+        self._px = {}                                           # batch size -> PeerExchange (or None: NCCL path)
         dev = emb.embedding_dict.weight.device
         if dev.type == "cuda" and self.world > 1 and os.environ.get("CDCMDR_PEER", "1") != "0":
             try:
@@ -212,11 +259,114 @@ class DataParallel:
             self._moments = (torch.zeros_like(sv), torch.zeros_like(sv))
         return self._moments
 
+    MAX_PEER_EXCHANGES = 3
+
+    def peer_exchange(self, B):
+        """The peer-memory exchange for batch size B, created on first use (a COLLECTIVE: replicas run in lockstep, so every rank
+        meets here with the same B), or None - the NCCL all-to-all path - when peer memory is unavailable, the embedding width is
+        not one the fused kernels cover, or MAX_PEER_EXCHANGES batch sizes already hold symmetric buffers."""
+        if B in self._px:
+            return self._px[B]
+        px = None
+        dev = self.model.embedding.embedding_dict.weight.device
+        usable = (self.shard and dev.type == "cuda" and self.peer is not None and self.E in (4, 8, 16, 32, 64)
+                  and os.environ.get("CDCMDR_PEER_EXCHANGE", "1") != "0" and not _ABLATE
+                  and sum(v is not None for v in self._px.values()) < self.MAX_PEER_EXCHANGES)
+        if usable:
+            try:
+                px = PeerExchange(self, B, dev, self.model._rt.ops.lib)
+            except Exception as exc:
+                import warnings
+                warnings.warn(f"cdcmdr: NVLink peer exchange unavailable ({exc!r}); the embedding exchange goes through NCCL")
+                px = None
+        self._px[B] = px
+        return px
+
+    def prepare_ws(self, ws, B):
+        """Called before the model asks its workspace for X: with the peer exchange, X IS the symmetric buffer the owners store into."""
+        px = self.peer_exchange(B)
+        if px is None:
+            return
+        rt = self.model._rt
+        xt = px.view("x", rt.act_dtype, B * px.x_cols)
+        cur = ws.bufs.get("X")
+        if cur is None or cur.data_ptr() != xt.data_ptr() or cur.dtype != xt.dtype:
+            xt.zero_()
+            ws.bufs["X"] = xt
+            ws.marks.discard("X.ones")
+
+    def _embed_forward_peer(self, px, ws, x, B, X: Mat, plan_ahead):
+        rt = self.model._rt
+        ops, N, E = rt.ops, self.world, self.E
+        nf_me = self.f1 - self.f0
+        st = self._state(x.device)
+        lib, stream = ops.lib, ops.stream
+        px.barrier(0, stream)                                   # every owner is done with the previous step's inboxes
+        lib.dp_push_ids(x.data_ptr(), B, self.F, px.ids_ptrs.data_ptr(), px.fbound.data_ptr(), self.rank, N, stream)
+        px.barrier(1, stream)
+        recv_ids = px.view("ids", torch.int32, N * B * max(nf_me, 1))
+        self._plan, self._plan_event = None, None
+        side = rt.side_stream() if plan_ahead else None
+        if nf_me and plan_ahead:
+            Vl = self.shard_view().shape[0]
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(rt.device))
+                with torch.cuda.stream(side):
+                    self._plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+                    self._plan_event = side.record_event()
+            else:
+                self._plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+        if nf_me:
+            shard = self.shard_view()
+            lib.dp_gather_push(recv_ids.data_ptr(), st["offsets_local"].data_ptr(), shard.data_ptr(), shard.shape[0],
+                               px.x_ptrs.data_ptr(), 1 if rt.bf16 else 0, X.ld, self.f0 * E, B, nf_me, E, N, None, stream)
+        px.barrier(2, stream)
+        self._px_used = px                                      # the backward of this forward takes the same road
+        return recv_ids
+
+    def _embed_backward_peer(self, px, ws, dX: Mat, B, l2, sumsq_out):
+        rt = self.model._rt
+        ops, N, E = rt.ops, self.world, self.E
+        nf_me = self.f1 - self.f0
+        st = self._state(dX.t.device)
+        lib, stream = ops.lib, ops.stream
+        g16 = rt.bf16 and os.environ.get("CDCMDR_GRAD_EXCHANGE", "bf16") == "bf16"
+        lib.dp_push_grads(dX.ptr, dX.ld, B, self.F, E, px.grad_ptrs.data_ptr(), 1 if g16 else 0, px.fbound.data_ptr(), self.rank, N,
+                          stream)
+        px.barrier(3, stream)
+        if not nf_me:
+            sumsq_out.zero_()
+            return
+        n = N * B * nf_me * E
+        if g16:
+            grecv = ws.get("dp.grad_recv", (n,), torch.float32)
+            ops.cast_bf16_f32(Mat(px.view("grads", torch.bfloat16, n), 0, nf_me * E), Mat(grecv, 0, nf_me * E), N * B, nf_me * E)
+        else:
+            grecv = px.view("grads", torch.float32, n)
+        shard = self.shard_view()
+        Vl = shard.shape[0]
+        plan = getattr(self, "_plan", None)
+        if plan is None:
+            plan = ops.embed_plan(px.view("ids", torch.int32, N * B * nf_me), st["offsets_local"], N * B, nf_me, Vl, E)
+        elif self._plan_event is not None:
+            torch.cuda.current_stream(rt.device).wait_event(self._plan_event)
+        self._plan, self._plan_event = None, None
+        m, v = self.moments()
+        lazy = self.model.embedding_update == "sparse_lazy"
+        if lazy:
+            ops.reg_l2_sum(shard, None, 1.0, shard.numel(), sumsq_out, scratch="reduce_table")
+        ops.embed_bwd_adam(Mat(grecv, 0, nf_me * E), plan, N * B, nf_me, E, Vl, shard, m, v, l2, rt.step_state,
+                           None if lazy else sumsq_out, lazy=lazy)
+
     def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False):
         """x: this rank's [B, F] int32 indices -> X[B, F*E] (activation dtype) through the owners of each field.
         plan_ahead (training step): the owner-side backward plan over the received indices starts on the side stream as soon as
         they have arrived and runs next to the model program."""
         rt = self.model._rt
+        px = self._px.get(B)
+        if px is not None and ws.bufs.get("X") is not None and X.t.data_ptr() == px.view("x", rt.act_dtype, 1).data_ptr() and X.off == 0:
+            return self._embed_forward_peer(px, ws, x, B, X, plan_ahead)
+        self._px_used = None
         ops, N, E, F = rt.ops, self.world, self.E, self.F
         nf_me = self.f1 - self.f0
         st = self._state(x.device)
@@ -254,6 +404,9 @@ class DataParallel:
         """dX: fp32 [B, F*E] gradient of this rank's gathered rows -> owner-side segment sum + Adam on the owner's rows.
         sumsq_out (device double[1]): sum of squares of the owner's rows before the update (regulariser value)."""
         rt = self.model._rt
+        px = self._px.get(B)
+        if px is not None and getattr(self, "_px_used", None) is px:
+            return self._embed_backward_peer(px, ws, dX, B, l2, sumsq_out)
         ops, N, E, F = rt.ops, self.world, self.E, self.F
         nf_me = self.f1 - self.f0
         st = self._state(dX.t.device)
@@ -356,6 +509,9 @@ class RowRangeParallel(DataParallel):
 
     def gather_table(self):
         return None
+
+    def prepare_ws(self, ws, B):
+        pass                                                     # rows are read from their owners' shards: no exchange buffers
 
     def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False):
         rt = self.model._rt

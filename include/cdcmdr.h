@@ -484,6 +484,32 @@ size_t cdcmdr_peer_allreduce_bytes(int world, int64_t max_n);
 int cdcmdr_peer_allreduce_f64(double* const* peer_bufs, int rank, int world, const double* in, double* out, int64_t n,
                               int64_t max_n, uint64_t* seq, cdcmdr_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------
+ * (e) multi-GPU: the embedding exchange of the replica step fused into its producers / consumers over NVLink peer memory
+ *     (replaces the index / row / row-gradient all-to-alls around a1 and a2 - model/layer.py:147-157 and its autograd -
+ *     when the table is sharded at field boundaries: owner o holds the rows of fields [fbound[o], fbound[o+1])).
+ *     Every pointer array is a DEVICE array of `world` pointers, entry r = rank r's buffer, mapped into this process (symmetric
+ *     memory).  All calls are one kernel, never synchronise with the host, and are CUDA-graph capturable.
+ *
+ * cdcmdr_peer_barrier     peer_flags[r]: rank r's uint64[n_slots][world], zero-initialised; seqs: uint64[n_slots] private to the rank,
+ *                         zero-initialised.  Returns (on the stream) once every rank has issued its matching call on `slot`; all
+ *                         device writes a rank issued on the stream before its call are visible to every rank after theirs.
+ * cdcmdr_dp_push_ids      x [B, F] int32 (this rank's indices) -> recv_ids[o][(rank*B + b)*nf_o + j] = x[b, fbound[o] + j].
+ * cdcmdr_dp_gather_push   owner side: for every received index (requester p, sample b, owned field j) the table row
+ *                         shard[recv_ids[(p*B + b)*nf + j] + off_local[j]] -> xs[p][b*ldx + col0 + j*E ...] as fp32 or bf16
+ *                         (out_bf16); an index outside [0, Vl) reads as zeros and sets *oob_flag (as cdcmdr_embed_gather_fwd).
+ *                         Bit-exact.
+ * cdcmdr_dp_push_grads    dX [B, ldg] fp32 (gradient of this rank's gathered rows) -> grad_recv[o][(rank*B + b)*nf_o*E + c] =
+ *                         dX[b, fbound[o]*E + c], as fp32 or rounded to bf16 (out_bf16).
+ * ------------------------------------------------------------------------------------------- */
+int cdcmdr_peer_barrier(uint64_t* const* peer_flags, int rank, int world, int slot, int n_slots, uint64_t* seqs, cdcmdr_stream_t s);
+int cdcmdr_dp_push_ids(const int32_t* x, int64_t B, int F, int32_t* const* recv_ids, const int32_t* fbound, int rank, int world,
+                       cdcmdr_stream_t s);
+int cdcmdr_dp_gather_push(const int32_t* recv_ids, const int64_t* off_local, const float* shard, int64_t Vl, void* const* xs,
+                          int out_bf16, int64_t ldx, int col0, int64_t B, int nf, int E, int world, int* oob_flag, cdcmdr_stream_t s);
+int cdcmdr_dp_push_grads(const float* dX, int64_t ldg, int64_t B, int F, int E, void* const* grad_recv, int out_bf16,
+                         const int32_t* fbound, int rank, int world, cdcmdr_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -921,6 +921,60 @@ class HostABI:
         _arr(out, n, np.float64)[:n] = _arr(inp, n, np.float64)[:n]
         return 0
 
+    # ---- (e) fused embedding exchange: the "peers" are host buffers inside this process (one emulator call per rank, in any order)
+    def peer_barrier(self, peer_flags, rank, world, slot, n_slots, seqs, s):
+        if world != 1:
+            raise NotImplementedError("the host emulator has no peer memory: a barrier between ranks cannot be emulated in one call")
+        q = _arr(seqs, n_slots, np.uint64)
+        q[slot] += 1
+        _arr(_arr(peer_flags, 1, np.int64)[0], n_slots * world, np.uint64)[slot * world + rank] = q[slot]
+        return 0
+
+    def dp_push_ids(self, x, B, F, recv_ids, fbound, rank, world, s):
+        if B == 0:
+            return 0
+        xs = _mat(x, B, F, F, 1, np.int32)
+        fb = _arr(fbound, world + 1, np.int32)
+        ptrs = _arr(recv_ids, world, np.int64)
+        for o in range(world):
+            f0, nf = int(fb[o]), int(fb[o + 1] - fb[o])
+            if nf > 0:
+                _arr(int(ptrs[o]) + 4 * rank * B * nf, B * nf, np.int32)[...] = xs[:, f0:f0 + nf].reshape(-1)
+        return 0
+
+    def dp_gather_push(self, recv_ids, off_local, shard, Vl, xs, out_bf16, ldx, col0, B, nf, E, world, oob, s):
+        if B == 0 or nf == 0:
+            return 0
+        ids = _arr(recv_ids, world * B * nf, np.int32).reshape(world, B, nf).astype(np.int64) + _arr(off_local, nf, np.int64)[None, None, :]
+        ok = (ids >= 0) & (ids < Vl)
+        tab = _mat(shard, Vl, E, E)
+        rows = np.where(ok[..., None], tab[np.clip(ids, 0, Vl - 1)], F32(0)).reshape(world, B, nf * E)
+        if oob and not ok.all():
+            _arr(oob, 1, np.int32)[0] = 1
+        ptrs = _arr(xs, world, np.int64)
+        for p in range(world):
+            if out_bf16:
+                _mat(int(ptrs[p]) + 2 * col0, B, nf * E, ldx, 1, np.uint16)[...] = f32_to_bf16(rows[p]).reshape(B, nf * E)
+            else:
+                _mat(int(ptrs[p]) + 4 * col0, B, nf * E, ldx)[...] = rows[p]
+        return 0
+
+    def dp_push_grads(self, dX, ldg, B, F, E, grad_recv, out_bf16, fbound, rank, world, s):
+        if B == 0:
+            return 0
+        fb = _arr(fbound, world + 1, np.int32)
+        ptrs = _arr(grad_recv, world, np.int64)
+        for o in range(world):
+            f0, nf = int(fb[o]), int(fb[o + 1] - fb[o])
+            if nf <= 0 or B == 0:
+                continue
+            g = _mat(dX + 4 * f0 * E, B, nf * E, ldg)
+            if out_bf16:
+                _mat(int(ptrs[o]) + 2 * rank * B * nf * E, B, nf * E, nf * E, 1, np.uint16)[...] = f32_to_bf16(g).reshape(B, nf * E)
+            else:
+                _mat(int(ptrs[o]) + 4 * rank * B * nf * E, B, nf * E, nf * E)[...] = g
+        return 0
+
     # ---- a5/a6: first CGC level of PLE chained in one kernel (cdcmdr_ple_chain_fwd; ple.py:54,96-124, layer.py:184-190)
     def ple_chain_ok(self, K0, d0, d1, n_g):
         return 1 if (K0 >= 8 and K0 % 8 == 0 and -(-K0 // 64) <= 6 and d0 in (128, 256) and d1 in (64, 128) and 0 <= n_g <= 128) else 0
