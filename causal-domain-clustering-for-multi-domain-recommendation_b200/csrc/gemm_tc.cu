@@ -60,6 +60,7 @@ struct TcParams {
   int32_t tma_aux;                           // out_aux (fp32) is written through map_d
   int32_t tma_mask;                          // the ReLU mask (forward activation) is read through map_m into shared memory
   int32_t a_res;                             // A-resident sweep: see the kernel comment
+  int32_t epi_subs;                          // epilogue warps per TMEM lane quarter: 4 (576 threads) or 1 (lean: 192 threads)
   int64_t tiles_lo; int32_t tiles_rem;       // a_res: CTA c owns tiles [c*lo + min(c, rem), +lo + (c < rem))
   unsigned long long* prof;                  // diagnostics: cycles spent in each pipeline wait, summed over CTAs (NULL = off)
   const uint16_t* cross_x0; const uint16_t* cross_x; int64_t ld_cross;   // CrossNetV2 epilogue (see cdcmdr.h): bf16 x0 / x boxes through map_m / map_x
@@ -161,7 +162,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const uint32_t b_in_stage = p.a_res ? 0u : (uint32_t)TC_A_BYTES;              // B's offset inside a ring stage
   uint8_t* ring = smem + a_region;
   uint8_t* staging = ring + p.stages * p.stage_bytes;
-  float* bias_s = (float*)(staging + TC_STAGING_BYTES);
+  float* bias_s = (float*)(staging + 4 * p.epi_subs * TC_STAGING_WARP_BYTES);
   uint64_t* bars = (uint64_t*)((uint8_t*)bias_s + TC_BIAS_BYTES);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + TC_MAX_STAGES);
   const uint32_t tfull0 = smem_u32(bars + 2 * TC_MAX_STAGES), tempty0 = smem_u32(bars + 2 * TC_MAX_STAGES + 2);
@@ -180,7 +181,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();                          // the swizzle atoms below assume it
     for (int i = 0; i < p.stages; ++i) { mbar_init(full0 + 8 * i, 1); mbar_init(empty0 + 8 * i, 1); mbar_init(pfull0 + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, CTA2 ? 2 * TC_EPI_WARPS : TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(tfull0 + 8 * i, 1); mbar_init(tempty0 + 8 * i, (CTA2 ? 8 : 4) * p.epi_subs); }
     for (int i = 0; i < TC_EPI_WARPS; ++i) mbar_init(mbar0 + 8 * i, 1);
     for (int i = 0; i < 8; ++i) { mbar_init(afull0 + 8 * i, 1); mbar_init(aempty0 + 8 * i, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -392,7 +393,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         if (ew == 0 && lane == 0) TC_PROF_ADD(3); }
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TC_MAX_N);
-      for (int ci = sub; ci < n_chunks; ci += 4) {
+      for (int ci = sub; ci < n_chunks; ci += p.epi_subs) {
         if (p.debug & 16) break;
         const int c0 = ci * 32;
         const int64_t nb = n0 + c0;                      // first global column of the chunk
@@ -424,7 +425,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             xb[j] = *reinterpret_cast<const uint4*>(my_mask + TC_STAGING_WARP_BYTES + lane * 64 + ((j ^ swz) * 16));
           }
           __syncwarp();                                  // every lane has its rows: the buffer may take the next boxes
-          if (cross_chunk(n0, ci + 4)) issue_cross(mt, n0 + 32 * (ci + 4));
+          if (cross_chunk(n0, ci + p.epi_subs)) issue_cross(mt, n0 + 32 * (ci + p.epi_subs));
           tc_ld_wait();
           const int32_t row0 = (int32_t)(mt * TC_BLOCK_M + q * 32);
           if (p.out_aux) {                               // acc, fp32: two 16-column boxes
@@ -479,7 +480,7 @@ gemm_bf16_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int j = 0; j < 4; ++j) mk[j] = *reinterpret_cast<const uint4*>(my_mask + lane * 64 + ((j ^ swz) * 16));
             __syncwarp();                                // every lane has its row: the buffer may take the next box
-            if (mask_by_tma(n0, ci + 4)) issue_mask(g, mt, n0 + 32 * (ci + 4));
+            if (mask_by_tma(n0, ci + p.epi_subs)) issue_mask(g, mt, n0 + 32 * (ci + p.epi_subs));
           } else if (ec.has_mask && m < p.M) {
             const uint4* mp = reinterpret_cast<const uint4*>(p.mask + m * p.ld_mask + g * p.mask_gn + nb);
 #pragma unroll
@@ -659,6 +660,34 @@ __global__ void tc_splitk_reduce_kernel(const float* __restrict__ part, int64_t 
   }
 }
 
+// the same sums (same order per element) four columns per thread, the slices' loads issued four at a time before their adds: the
+// scalar kernel walked the slices one dependent 4-byte load after the other (24 us for the 27 MB of the level-0 weight gradient)
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_vec4_kernel(const float* __restrict__ part, int64_t stride, int splits, float* __restrict__ out, int64_t rows,
+                             int64_t cols4, int64_t ld_part, int64_t ld_out, int accumulate) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r, c; split_idx(i, cols4, r, c);
+    const float* src = part + r * ld_part + 4 * c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)(z + u) * stride));
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { v.x += t[u].x; v.y += t[u].y; v.z += t[u].z; v.w += t[u].w; }
+    }
+    for (; z < splits; ++z) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(src + (int64_t)z * stride));
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    float4* o = reinterpret_cast<float4*>(out + r * ld_out + 4 * c);
+    if (accumulate) { const float4 a = *o; v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w; }
+    *o = v;
+  }
+}
+
 // tiled transpose of a bf16 matrix: dst[c, r] = src[r, c]
 __global__ void transpose_bf16_kernel(const uint16_t* __restrict__ src, int64_t lds, uint16_t* __restrict__ dst, int64_t ldd, int64_t rows, int64_t cols) {
   __shared__ uint16_t tile[32][33];
@@ -674,7 +703,8 @@ __global__ void transpose_bf16_kernel(const uint16_t* __restrict__ src, int64_t 
   }
 }
 
-// bit 0: single-CTA tiles only; bit 1: no A-resident sweep; bit 2: CTA pairs whenever legal (default 0: pairs only for long K loops)
+// bit 0: single-CTA tiles only; bit 1: no A-resident sweep; bit 2: CTA pairs whenever legal (default 0: pairs only for long K loops);
+// bit 3: no lean epilogue for long split-K slices
 static std::atomic<int> g_tc_mode{0};
 static std::atomic<unsigned long long*> g_tc_prof{nullptr};
 
@@ -777,7 +807,13 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
     if (p->out_aux) { if (int rc = make_map(&md, p->out_aux, p->M, p->N, p->ld_aux, 32u, true, true)) return rc; }
   }
   const int b_bytes = (q.b_mn_major ? (int)ceil_div(b_cols, 64) * 64 : b_cols) * TC_BLOCK_K * 2;
-  const int fixed = TC_STAGING_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES + (cross ? 2 * TC_MASK_BYTES : (q.tma_mask ? TC_MASK_BYTES : 0));
+  // Lean epilogue: a split-K slice with a long K loop (weight gradients: K = batch) spends > 90 % of its time in the main loop, so
+  // one epilogue warp per TMEM lane quarter drains it as well as four.  192 threads and 24 KB less staging leave registers and
+  // shared memory for ~4 small CTAs per SM next to this one: the HBM-bound kernels of the step's side branch (embedding backward)
+  // run UNDER the weight-gradient GEMM instead of after it (a 576-thread CTA with 227 KB fills the SM on its own).  Mode bit 3 off.
+  q.epi_subs = (!cta2 && !(mode & 8) && q.split_k > 1 && q.kb_per_split >= 48 && !cross && !q.tma_mask) ? 1 : 4;
+  const int fixed = 4 * q.epi_subs * TC_STAGING_WARP_BYTES + TC_BIAS_BYTES + TC_BAR_BYTES +
+                    (cross ? 2 * TC_MASK_BYTES : (q.tma_mask ? TC_MASK_BYTES : 0));
   // A-resident sweep: K-major A, no split, a short K loop whose whole A panel fits next to >= 3 ring stages of B, and at least
   // two column tiles to sweep.  Mode bit 1 switches it off.
   const int64_t total = (int64_t)q.n_tiles_m * q.n_tiles_n * q.split_k * q.G;
@@ -785,7 +821,8 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
              q.num_kb * TC_A_BYTES + 3 * b_bytes + fixed <= TC_SMEM_LIMIT) ? 1 : 0;
   const int a_region = q.a_res ? q.num_kb * TC_A_BYTES : 0;
   q.stage_bytes = (q.a_res ? 0 : TC_A_BYTES) + b_bytes;
-  int stages = (TC_SMEM_LIMIT - fixed - a_region) / q.stage_bytes;
+  const int smem_limit = q.epi_subs == 1 ? TC_SMEM_LIMIT - 24576 : TC_SMEM_LIMIT;      // lean: room for the co-resident CTAs
+  int stages = (smem_limit - fixed - a_region) / q.stage_bytes;
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   CDC_REQUIRE(stages >= 2, "shared memory budget too small for a 2-stage pipeline");
   q.stages = stages;
@@ -803,7 +840,7 @@ extern "C" int cdcmdr_gemm_bf16_tc(const cdcmdr_gemm_bf16_t* p, cdcmdr_stream_t 
   }
   if (!cta2) {
     const int grid = (int)(total < kNumSMs ? total : kNumSMs);
-    gemm_bf16_tc_kernel<false><<<grid, TC_THREADS, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, mm, mx, q);
+    gemm_bf16_tc_kernel<false><<<grid, 64 + 128 * q.epi_subs, smem_bytes, to_stream(s)>>>(ma, mb, mc, md, mm, mx, q);
     CDC_LAUNCHED();
     return 0;
   }
@@ -829,7 +866,7 @@ extern "C" int cdcmdr_gemm_bf16_tc_profile(uint64_t* counters8) {
 
 extern "C" int cdcmdr_gemm_bf16_tc_mode(int mode) {
   const int old = g_tc_mode.load(std::memory_order_relaxed);
-  if (mode >= 0) g_tc_mode.store(mode & 0x77, std::memory_order_relaxed);
+  if (mode >= 0) g_tc_mode.store(mode & 0x7f, std::memory_order_relaxed);
   return old;
 }
 
@@ -847,7 +884,13 @@ extern "C" int cdcmdr_splitk_reduce(const float* part, int64_t stride, int32_t s
   if (rows <= 0 || cols <= 0) return 0;
   int64_t g = ceil_div(rows * cols, 256);
   if (g > 8 * kNumSMs) g = 8 * kNumSMs;
-  tc_splitk_reduce_kernel<<<(int)g, 256, 0, to_stream(s)>>>(part, stride, splits, out, rows, cols, ld_part, ld_out, accumulate);
+  if (cols % 4 == 0 && ld_part % 4 == 0 && ld_out % 4 == 0 && stride % 4 == 0 && ((uintptr_t)part % 16) == 0 && ((uintptr_t)out % 16) == 0) {
+    g = ceil_div(rows * (cols / 4), 256);
+    if (g > 8 * kNumSMs) g = 8 * kNumSMs;
+    tc_splitk_reduce_vec4_kernel<<<(int)g, 256, 0, to_stream(s)>>>(part, stride, splits, out, rows, cols / 4, ld_part, ld_out, accumulate);
+  } else {
+    tc_splitk_reduce_kernel<<<(int)g, 256, 0, to_stream(s)>>>(part, stride, splits, out, rows, cols, ld_part, ld_out, accumulate);
+  }
   CDC_LAUNCHED();
   return 0;
 }

@@ -163,8 +163,12 @@ int cdcmdr_gemm_bf16_tc_splits(int64_t K, int32_t want);
 /* Tuning switches of cdcmdr_gemm_bf16_tc (bit mask; mode < 0 only queries; returns the previous mask).  Every combination computes
  * the same values (same K order per output element):
  *   bit 0  single-CTA 128 x block_n tiles only
+ *   bit 1  no A-resident column sweep (every tile streams its A k-blocks through the ring)
  *   bit 2  CTA pairs (tcgen05 cta_group::2: 256 x block_n tiles, B operand split between the two SMs of a pair) whenever the tile
  *          shape allows; default (neither bit): pairs only when a tile's K loop has >= 32 k-blocks
+ *   bit 3  no lean epilogue: by default a split-K launch whose slices run >= 48 k-blocks uses 192 threads (one epilogue warp per
+ *          TMEM lane quarter instead of four) and 24 KB less shared memory, so that small HBM-bound CTAs of a concurrent stream
+ *          fit on the SM next to it (the embedding backward runs under the weight-gradient GEMM)
  * (Measured on B200: pairs +8 % at 128 k-blocks per tile, -20 % at 6; reading staged tiles back for coalesced st.global instead of
  * TMA stores was 15-25 % slower and was removed.) */
 int cdcmdr_gemm_bf16_tc_mode(int mode);

@@ -26,6 +26,10 @@ CASES = {
     "grouped_b_mn_major": (400, 256, 128, 3, 0, 1, -1, dict(mask=True, a_gk=128, b_gk=128, main_gn=256)),
     "wgrad_both_mn_major": (2587, 368, 4096, 1, 1, 1, 0, {}),
     "wgrad_split_k": (200, 130, 8192, 1, 1, 1, 0, dict(split_k=6)),
+    # long split-K slices (>= 48 k-blocks each): the lean-epilogue launch (192 threads) - plain, ragged, and grouped
+    "wgrad_lean": (300, 376, 16384, 1, 1, 1, 0, dict(split_k=4)),
+    "wgrad_lean_ragged": (2587, 376, 8192 + 64 * 5 + 24, 1, 1, 1, 0, dict(split_k=2)),
+    "wgrad_lean_grouped": (128, 256, 8192, 3, 1, 1, 0, dict(a_gm=128, b_gn=256, aux_gn=256 * 128, split_k=2, group_rows=True)),
     "wgrad_grouped": (128, 256, 2048, 4, 1, 1, 0, dict(a_gm=128, b_gn=256, aux_gn=256 * 128, split_k=3, group_rows=True)),
     "tiny": (5, 16, 8, 1, 0, 0, -1, {}),
     "pair_odd_row_tiles": (128 * 5 + 17, 256, 200, 1, 0, 0, -1, dict(bias=True, act=1)),
@@ -37,7 +41,7 @@ CASES = {
 }
 
 
-@pytest.fixture(params=[4, 1, 3, 0], ids=["cta_pairs", "single_cta", "single_cta_streamed_a", "auto"])
+@pytest.fixture(params=[4, 1, 3, 0, 9], ids=["cta_pairs", "single_cta", "single_cta_streamed_a", "auto", "single_cta_full_epilogue"])
 def tc_mode(request):
     """cdcmdr_gemm_bf16_tc tile mode: CTA pairs (cta_group::2) where the shape allows / single-CTA tiles only."""
     lib = cm._lib.load()
