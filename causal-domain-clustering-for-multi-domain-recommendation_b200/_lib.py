@@ -154,6 +154,8 @@ SIGNATURES = {
     "cdcmdr_auc_logloss": (INT, [P, P, INT, P, INT, I64, I32, P, P, P]),
     "cdcmdr_peer_allreduce_bytes": (SZ, [INT, I64]),
     "cdcmdr_peer_allreduce_f64": (INT, [P, INT, INT, P, P, I64, I64, P, P]),
+    "cdcmdr_peer_allreduce_f32_chunk": (I64, [INT, I64]),
+    "cdcmdr_peer_allreduce_f32": (INT, [P, P, P, P, P, INT, INT, P, P, I64, P, P]),
     "cdcmdr_peer_barrier": (INT, [P, INT, INT, INT, INT, P, P]),
     "cdcmdr_dp_push_ids": (INT, [P, I64, INT, P, P, INT, INT, P]),
     "cdcmdr_dp_gather_push": (INT, [P, P, P, I64, P, INT, I64, INT, I64, INT, INT, INT, P, P]),

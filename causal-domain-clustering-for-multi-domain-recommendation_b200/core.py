@@ -316,13 +316,14 @@ class Ops:
             if best is None or cost < best:
                 best, want = cost, cand
         split = self.lib.gemm_bf16_tc_splits(B, want)
-        stride = M * N
+        ldp = (N + 3) & ~3                                     # partial rows 16-byte aligned: the reduce reads them 128 bits at a time
+        stride = M * ldp
         part = self.scratch("tc_splitk", 4 * max(split, 1) * stride).data_ptr()
-        d = GemmBf16(dY.ptr, dY.ld, B, M, X.ptr, X.ld, B, N, M, N, B, 1, 0, 0, 0, 0, 1, 1, None, 0, 0, None, 0, 0, part, N, 0, 0,
+        d = GemmBf16(dY.ptr, dY.ld, B, M, X.ptr, X.ld, B, N, M, N, B, 1, 0, 0, 0, 0, 1, 1, None, 0, 0, None, 0, 0, part, ldp, 0, 0,
                      None, 0, 0, 1.0, 0.0, None, 0, 0, split, stride, 0, None, None, 0)
         self.lib.gemm_bf16_tc(C.byref(d), self.stream)
-        self.lib.splitk_reduce(part, stride, split, gW_addr, M, K, N, K, 0, self.stream)
-        self.lib.splitk_reduce(part + 4 * K, stride, split, gb_addr, M, 1, N, 1, 0, self.stream)
+        self.lib.splitk_reduce(part, stride, split, gW_addr, M, K, ldp, K, 0, self.stream)
+        self.lib.splitk_reduce(part + 4 * K, stride, split, gb_addr, M, 1, ldp, 1, 0, self.stream)
 
     # ---------------------------------------------------------------- loss
     def sigmoid_select_bce(self, logits, lin: Mat | None, B, T, mode, sel, col, target, pred, psel, loss_sum, dlogits,

@@ -111,6 +111,34 @@ class PeerReduce:
                                     self.seq.data_ptr(), stream)
 
 
+class PeerReduceF32:
+    """The dense gradient arena's all-reduce (one fp32 vector of a fixed length per step) as a two-shot exchange over NVLink peer
+    memory (cdcmdr_peer_allreduce_f32, csrc/peer.cu) instead of an NCCL ring.  Created on first use for that length (a collective:
+    replicas run in lockstep)."""
+
+    def __init__(self, group, device, lib, n):
+        import torch.distributed._symmetric_memory as symm
+        self.lib, self.world, self.rank, self.n = lib, dist.get_world_size(group), dist.get_rank(group), int(n)
+        chunk = int(lib.peer_allreduce_f32_chunk(self.world, self.n))
+        box = (self.world * chunk * 4 + 255) & ~255
+        self.off_out, self.off_flags = box, 2 * box
+        self.buf = symm.empty(2 * box + 2 * self.world * 8, dtype=torch.uint8, device=device)
+        self.buf.zero_()
+        self.handle = symm.rendezvous(self.buf, group.group_name)
+        bases = [int(p) for p in self.handle.buffer_ptrs]
+        mk = lambda off: torch.tensor([b + off for b in bases], dtype=torch.int64, device=device)
+        self.inbox, self.outbox, self.flags = mk(0), mk(self.off_out), mk(self.off_flags)
+        self.my_inbox, self.my_outbox = bases[self.rank], bases[self.rank] + self.off_out
+        self.seqs = torch.zeros(2, dtype=torch.int64, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def all_reduce_sum(self, t: torch.Tensor):
+        stream = torch.cuda.current_stream(t.device).cuda_stream
+        self.lib.peer_allreduce_f32(self.inbox.data_ptr(), self.outbox.data_ptr(), self.flags.data_ptr(), self.my_inbox, self.my_outbox,
+                                    self.rank, self.world, t.data_ptr(), t.data_ptr(), self.n, self.seqs.data_ptr(), stream)
+
+
 class PeerExchange:
     """The embedding exchange of one batch size over NVLink peer memory (csrc/dp_exchange.cu): every rank's index inbox, gathered
     matrix X and gradient inbox live in ONE symmetric allocation; owners store rows straight into the requesters' X, requesters
@@ -180,6 +208,7 @@ class DataParallel:
         self.rows_override = None
         self.peer = None
         self._px_used = None
+        self._peer_f32 = {}
         self._px = {}                                           # batch size -> PeerExchange (or None: NCCL path)
         dev = emb.embedding_dict.weight.device
         if dev.type == "cuda" and self.world > 1 and os.environ.get("CDCMDR_PEER", "1") != "0":
@@ -215,6 +244,15 @@ class DataParallel:
         if self.peer is not None and self.peer.usable(t):
             self.peer.all_reduce_sum(t)
             return
+        if (self.peer is not None and t.dtype == torch.float32 and t.is_contiguous() and t.numel() >= (1 << 16)
+                and os.environ.get("CDCMDR_PEER_DENSE", "1") != "0"):
+            # the dense gradient arena: one length per model, at most two symmetric buffers are ever made
+            pr = self._peer_f32.get(t.numel())
+            if pr is None and len(self._peer_f32) < 2:
+                pr = self._peer_f32[t.numel()] = PeerReduceF32(self.group, t.device, self.model._rt.ops.lib, t.numel())
+            if pr is not None:
+                pr.all_reduce_sum(t)
+                return
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
     def _all_to_all(self, out: torch.Tensor, inp: torch.Tensor, out_splits, in_splits):

@@ -488,6 +488,17 @@ size_t cdcmdr_peer_allreduce_bytes(int world, int64_t max_n);
 int cdcmdr_peer_allreduce_f64(double* const* peer_bufs, int rank, int world, const double* in, double* out, int64_t n,
                               int64_t max_n, uint64_t* seq, cdcmdr_stream_t s);
 
+/* The dense gradient arena between replicas (sum over replicas of d(global mean loss), a few MB of fp32): two-shot
+ * all-reduce over peer memory - chunk c of `in` is pushed to rank c's inbox, rank c sums its inbox slots in rank order and stores the
+ * sums into every rank's outbox, outbox -> out (in == out allowed).  Every element is summed by ONE rank: replicas stay bit identical.
+ *   chunk = cdcmdr_peer_allreduce_f32_chunk(world, n) floats; inbox[r]: rank r's world*chunk floats; outbox[r]: rank r's world*chunk
+ *   floats; peer_flags[r]: rank r's uint64[2][world], zero-initialised; my_inbox / my_outbox = inbox[rank] / outbox[rank];
+ *   seqs2: uint64[2], zero-initialised, private to the rank.  Five launches, no host synchronisation, CUDA-graph capturable. */
+int64_t cdcmdr_peer_allreduce_f32_chunk(int world, int64_t n);
+int cdcmdr_peer_allreduce_f32(float* const* inbox, float* const* outbox, uint64_t* const* peer_flags, float* my_inbox,
+                              const float* my_outbox, int rank, int world, const float* in, float* out, int64_t n, uint64_t* seqs2,
+                              cdcmdr_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------
  * (e) multi-GPU: the embedding exchange of the replica step fused into its producers / consumers over NVLink peer memory
  *     (replaces the index / row / row-gradient all-to-alls around a1 and a2 - model/layer.py:147-157 and its autograd -

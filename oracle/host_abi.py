@@ -921,6 +921,15 @@ class HostABI:
         _arr(out, n, np.float64)[:n] = _arr(inp, n, np.float64)[:n]
         return 0
 
+    def peer_allreduce_f32_chunk(self, world, n):
+        return 0 if (world < 1 or n < 1) else ((-(-n // world)) + 3) & ~3
+
+    def peer_allreduce_f32(self, inbox, outbox, peer_flags, my_inbox, my_outbox, rank, world, inp, out, n, seqs2, s):
+        if world != 1:
+            raise NotImplementedError("the host emulator has no peer memory: multi-rank CPU tests use torch.distributed (gloo)")
+        _arr(out, n, np.float32)[:n] = _arr(inp, n, np.float32)[:n]
+        return 0
+
     # ---- (e) fused embedding exchange: the "peers" are host buffers inside this process (one emulator call per rank, in any order)
     def peer_barrier(self, peer_flags, rank, world, slot, n_slots, seqs, s):
         if world != 1:
