@@ -2,6 +2,8 @@
 no host synchronisation, all state device-resident) is recorded once per batch size and replayed with one launch."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 
@@ -45,7 +47,11 @@ class GraphedTrainStep:
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = lib.launch_count()
-        with torch.cuda.graph(self.graph):
+        # The main branch is captured on a HIGH-priority stream (the side branch's stream has the default, lowest priority): kernel
+        # nodes inherit it, so whenever both branches have CTAs waiting for an SM the model program's go first - the side branch fills
+        # what is left (it used to hold the split-K reduce behind the table sweep for ~30 us at the end of the step).
+        cap = torch.cuda.Stream(device=self.x.device, priority=-1) if os.environ.get("CDCMDR_GRAPH_PRIORITY", "1") != "0" else None
+        with torch.cuda.graph(self.graph, stream=cap):
             self.out = self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
         self.launches_per_step = int(lib.launch_count() - n0)
         self.optimizer.steps -= 1          # capture records the step but does not execute it
