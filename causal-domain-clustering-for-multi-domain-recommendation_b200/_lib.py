@@ -158,7 +158,7 @@ SIGNATURES = {
     "cdcmdr_peer_allreduce_f32": (INT, [P, P, P, P, P, INT, INT, P, P, I64, P, P]),
     "cdcmdr_peer_barrier": (INT, [P, INT, INT, INT, INT, P, P]),
     "cdcmdr_dp_push_ids": (INT, [P, I64, INT, P, P, INT, INT, P]),
-    "cdcmdr_dp_gather_push": (INT, [P, P, P, I64, P, INT, I64, INT, I64, INT, INT, INT, P, P]),
+    "cdcmdr_dp_gather_push": (INT, [P, P, P, I64, P, INT, I64, INT, I64, INT, INT, INT, INT, P, P]),
     "cdcmdr_dp_push_grads": (INT, [P, I64, I64, INT, INT, P, INT, P, INT, INT, P]),
     "cdcmdr_attn_fwd_bf16": (INT, [P, I64, P, I64, I64, INT, INT, INT, F32, F32, P, U32, P]),
     "cdcmdr_attn_bwd_bf16": (INT, [P, I64, P, I64, P, I64, I64, INT, INT, INT, F32, F32, P, U32, P]),

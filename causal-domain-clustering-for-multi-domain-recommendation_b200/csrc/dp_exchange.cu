@@ -98,7 +98,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256)
 dp_gather_push_kernel(const int32_t* __restrict__ recv_ids, const int64_t* __restrict__ off_local, const float* __restrict__ shard,
                       int64_t Vl, OutT* const* __restrict__ xs, int64_t ldx, int col0, int64_t B, int nf, int E, int world,
-                      int* __restrict__ oob) {
+                      int packed, int* __restrict__ oob) {
   constexpr int kEl = Chunk<OutT>::kEl;
   const int cpr = E / kEl;                                    // chunks per row
   const int64_t cps = (int64_t)nf * cpr;                      // chunks per sample
@@ -111,7 +111,10 @@ dp_gather_push_kernel(const int32_t* __restrict__ recv_ids, const int64_t* __res
     const int64_t row = (int64_t)__ldg(recv_ids + pb * nf + j) + __ldg(off_local + j);
     const bool ok = row >= 0 && row < Vl;
     if (!ok && oob) *oob = 1;
-    Chunk<OutT>::copy(xs[p] + b * ldx + col0 + c * kEl, shard + (ok ? row : 0) * E + h * kEl, ok);
+    // packed: this owner's [B, nf*E] block is contiguous at the requester (element offset B*col0) - whole warps store 512
+    // contiguous bytes; otherwise straight into the requester's [B, ldx] matrix (runs of nf*E elements)
+    OutT* dst = packed ? xs[p] + B * col0 + (b * cps + c) * kEl : xs[p] + b * ldx + col0 + c * kEl;
+    Chunk<OutT>::copy(dst, shard + (ok ? row : 0) * E + h * kEl, ok);
   }
 }
 
@@ -120,7 +123,7 @@ template <int EV, typename OutT>
 __global__ void __launch_bounds__(256)
 dp_gather_push_rows_kernel(const int32_t* __restrict__ recv_ids, const int64_t* __restrict__ off_local, const float* __restrict__ shard,
                            int64_t Vl, OutT* const* __restrict__ xs, int64_t ldx, int col0, int64_t B, int nf, int world,
-                           int* __restrict__ oob) {
+                           int packed, int* __restrict__ oob) {
   constexpr int E = 4 * EV;
   const int64_t total = (int64_t)world * B * nf;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -138,7 +141,7 @@ dp_gather_push_rows_kernel(const int32_t* __restrict__ recv_ids, const int64_t* 
 #pragma unroll
       for (int k = 0; k < EV; ++k) t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    OutT* o = xs[p] + b * ldx + col0 + j * E;
+    OutT* o = packed ? xs[p] + B * col0 + (b * nf + j) * E : xs[p] + b * ldx + col0 + j * E;
 #pragma unroll
     for (int k = 0; k < EV; ++k) Store4<OutT>::put(o + 4 * k, t[k]);
   }
@@ -216,26 +219,26 @@ extern "C" int cdcmdr_dp_push_ids(const int32_t* x, int64_t B, int F, int32_t* c
 }
 
 extern "C" int cdcmdr_dp_gather_push(const int32_t* recv_ids, const int64_t* off_local, const float* shard, int64_t Vl, void* const* xs,
-                                     int out_bf16, int64_t ldx, int col0, int64_t B, int nf, int E, int world, int* oob_flag,
-                                     cdcmdr_stream_t s) {
+                                     int out_bf16, int64_t ldx, int col0, int64_t B, int nf, int E, int world, int packed,
+                                     int* oob_flag, cdcmdr_stream_t s) {
   if (B == 0 || nf == 0) return 0;
   CDC_REQUIRE(recv_ids && off_local && shard && xs && Vl > 0 && B > 0 && nf > 0 && world >= 1, "dp_gather_push: bad arguments");
   CDC_REQUIRE(E == 4 || E == 8 || E == 16 || E == 32 || E == 64, "dp_gather_push: embed_dim must be 4, 8, 16, 32 or 64");
-  CDC_REQUIRE(ldx % 4 == 0 && col0 % 4 == 0, "dp_gather_push: misaligned destination");
+  CDC_REQUIRE((packed || ldx % 4 == 0) && col0 % 4 == 0, "dp_gather_push: misaligned destination");
   cudaStream_t st = to_stream(s);
-  if (out_bf16 ? (E % 8 == 0 && ldx % 8 == 0 && col0 % 8 == 0) : true) {
+  if (out_bf16 ? (E % 8 == 0 && (packed || ldx % 8 == 0) && col0 % 8 == 0) : true) {
     const int grid = grid_for((int64_t)world * B * nf * (E / (out_bf16 ? 8 : 4)), 256, 8);
     if (out_bf16) dp_gather_push_kernel<uint16_t><<<grid, 256, 0, st>>>(recv_ids, off_local, shard, Vl, reinterpret_cast<uint16_t* const*>(xs),
-                                                                        ldx, col0, B, nf, E, world, oob_flag);
+                                                                        ldx, col0, B, nf, E, world, packed, oob_flag);
     else dp_gather_push_kernel<float><<<grid, 256, 0, st>>>(recv_ids, off_local, shard, Vl, reinterpret_cast<float* const*>(xs), ldx, col0,
-                                                            B, nf, E, world, oob_flag);
+                                                            B, nf, E, world, packed, oob_flag);
     CDC_LAUNCHED();
     return 0;
   }
   const int grid = grid_for((int64_t)world * B * nf, 256, 16);
 #define GP(EV)                                                                                                                      \
   dp_gather_push_rows_kernel<EV, uint16_t><<<grid, 256, 0, st>>>(recv_ids, off_local, shard, Vl, reinterpret_cast<uint16_t* const*>(xs), \
-                                                                 ldx, col0, B, nf, world, oob_flag)
+                                                                 ldx, col0, B, nf, world, packed, oob_flag)
   switch (E / 4) {
     case 1: GP(1); break; case 2: GP(2); break; case 4: GP(4); break; case 8: GP(8); break; default: GP(16); break;
   }

@@ -141,8 +141,8 @@ class PeerReduceF32:
 
 class PeerExchange:
     """The embedding exchange of one batch size over NVLink peer memory (csrc/dp_exchange.cu): every rank's index inbox, gathered
-    matrix X and gradient inbox live in ONE symmetric allocation; owners store rows straight into the requesters' X, requesters
-    store indices / row gradients straight into the owners' inboxes; `cdcmdr_peer_barrier` orders the phases.  torch's
+    row inbox and gradient inbox live in ONE symmetric allocation; owners store rows straight into the requesters' row inbox,
+    requesters store indices / row gradients straight into the owners' inboxes; `cdcmdr_peer_barrier` orders the phases.  torch's
     symmetric-memory allocator only provides the buffer and its peer mappings (plumbing).
 
     Slots of the barrier: 0 = everybody finished the previous use of the inboxes, 1 = indices landed, 2 = rows landed,
@@ -321,17 +321,8 @@ class DataParallel:
         return px
 
     def prepare_ws(self, ws, B):
-        """Called before the model asks its workspace for X: with the peer exchange, X IS the symmetric buffer the owners store into."""
-        px = self.peer_exchange(B)
-        if px is None:
-            return
-        rt = self.model._rt
-        xt = px.view("x", rt.act_dtype, B * px.x_cols)
-        cur = ws.bufs.get("X")
-        if cur is None or cur.data_ptr() != xt.data_ptr() or cur.dtype != xt.dtype:
-            xt.zero_()
-            ws.bufs["X"] = xt
-            ws.marks.discard("X.ones")
+        """Called before the first exchange of a batch size: the symmetric buffers are made here (a collective)."""
+        self.peer_exchange(B)
 
     def _embed_forward_peer(self, px, ws, x, B, X: Mat, plan_ahead):
         rt = self.model._rt
@@ -354,11 +345,19 @@ class DataParallel:
                     self._plan_event = side.record_event()
             else:
                 self._plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+        # rows: every owner stores its [B, nf*E] block CONTIGUOUSLY into the requester's staging buffer (whole 512-byte warp stores
+        # over NVLink; storing straight into X's rows meant runs of nf*E*2 = 96 bytes at 8 ranks and ~250 GB/s), the requester
+        # unpacks the blocks into its X columns (one strided-batch copy per run of equally sized owners)
         if nf_me:
             shard = self.shard_view()
             lib.dp_gather_push(recv_ids.data_ptr(), st["offsets_local"].data_ptr(), shard.data_ptr(), shard.shape[0],
-                               px.x_ptrs.data_ptr(), 1 if rt.bf16 else 0, X.ld, self.f0 * E, B, nf_me, E, N, None, stream)
+                               px.x_ptrs.data_ptr(), 1 if rt.bf16 else 0, 0, self.f0 * E, B, nf_me, E, N, 1, None, stream)
         px.barrier(2, stream)
+        esz = 2 if rt.bf16 else 4
+        rows_in = px.view("x", rt.act_dtype, B * self.F * E)
+        for (f0, n, cnt) in self._range_runs():
+            ops.copy2d_batched(rows_in.data_ptr() + esz * B * f0 * E, B * n * E, n * E, X.ptr + esz * f0 * E, n * E, X.ld, cnt, B, n * E,
+                               esz)
         self._px_used = px                                      # the backward of this forward takes the same road
         return recv_ids
 
@@ -402,7 +401,7 @@ class DataParallel:
         they have arrived and runs next to the model program."""
         rt = self.model._rt
         px = self._px.get(B)
-        if px is not None and ws.bufs.get("X") is not None and X.t.data_ptr() == px.view("x", rt.act_dtype, 1).data_ptr() and X.off == 0:
+        if px is not None:
             return self._embed_forward_peer(px, ws, x, B, X, plan_ahead)
         self._px_used = None
         ops, N, E, F = rt.ops, self.world, self.E, self.F

@@ -511,9 +511,12 @@ int cdcmdr_peer_allreduce_f32(float* const* inbox, float* const* outbox, uint64_
  *                         device writes a rank issued on the stream before its call are visible to every rank after theirs.
  * cdcmdr_dp_push_ids      x [B, F] int32 (this rank's indices) -> recv_ids[o][(rank*B + b)*nf_o + j] = x[b, fbound[o] + j].
  * cdcmdr_dp_gather_push   owner side: for every received index (requester p, sample b, owned field j) the table row
- *                         shard[recv_ids[(p*B + b)*nf + j] + off_local[j]] -> xs[p][b*ldx + col0 + j*E ...] as fp32 or bf16
- *                         (out_bf16); an index outside [0, Vl) reads as zeros and sets *oob_flag (as cdcmdr_embed_gather_fwd).
- *                         Bit-exact.
+ *                         shard[recv_ids[(p*B + b)*nf + j] + off_local[j]] -> as fp32 or bf16 (out_bf16) either straight into the
+ *                         requester's matrix, xs[p][b*ldx + col0 + j*E ...] (packed = 0: runs of nf*E elements cross NVLink), or into
+ *                         the requester's staging buffer where this owner's [B, nf*E] block is contiguous,
+ *                         xs[p][B*col0 + (b*nf + j)*E ...] (packed = 1: whole 512-byte warp stores; the requester unpacks with
+ *                         cdcmdr_copy2d_batched).  An index outside [0, Vl) reads as zeros and sets *oob_flag (as
+ *                         cdcmdr_embed_gather_fwd).  Bit-exact.
  * cdcmdr_dp_push_grads    dX [B, ldg] fp32 (gradient of this rank's gathered rows) -> grad_recv[o][(rank*B + b)*nf_o*E + c] =
  *                         dX[b, fbound[o]*E + c], as fp32 or rounded to bf16 (out_bf16).
  * ------------------------------------------------------------------------------------------- */
@@ -521,7 +524,8 @@ int cdcmdr_peer_barrier(uint64_t* const* peer_flags, int rank, int world, int sl
 int cdcmdr_dp_push_ids(const int32_t* x, int64_t B, int F, int32_t* const* recv_ids, const int32_t* fbound, int rank, int world,
                        cdcmdr_stream_t s);
 int cdcmdr_dp_gather_push(const int32_t* recv_ids, const int64_t* off_local, const float* shard, int64_t Vl, void* const* xs,
-                          int out_bf16, int64_t ldx, int col0, int64_t B, int nf, int E, int world, int* oob_flag, cdcmdr_stream_t s);
+                          int out_bf16, int64_t ldx, int col0, int64_t B, int nf, int E, int world, int packed, int* oob_flag,
+                          cdcmdr_stream_t s);
 int cdcmdr_dp_push_grads(const float* dX, int64_t ldg, int64_t B, int F, int E, void* const* grad_recv, int out_bf16,
                          const int32_t* fbound, int rank, int world, cdcmdr_stream_t s);
 

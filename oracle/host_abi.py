@@ -951,7 +951,7 @@ class HostABI:
                 _arr(int(ptrs[o]) + 4 * rank * B * nf, B * nf, np.int32)[...] = xs[:, f0:f0 + nf].reshape(-1)
         return 0
 
-    def dp_gather_push(self, recv_ids, off_local, shard, Vl, xs, out_bf16, ldx, col0, B, nf, E, world, oob, s):
+    def dp_gather_push(self, recv_ids, off_local, shard, Vl, xs, out_bf16, ldx, col0, B, nf, E, world, packed, oob, s):
         if B == 0 or nf == 0:
             return 0
         ids = _arr(recv_ids, world * B * nf, np.int32).reshape(world, B, nf).astype(np.int64) + _arr(off_local, nf, np.int64)[None, None, :]
@@ -961,11 +961,13 @@ class HostABI:
         if oob and not ok.all():
             _arr(oob, 1, np.int32)[0] = 1
         ptrs = _arr(xs, world, np.int64)
+        esz = 2 if out_bf16 else 4
         for p in range(world):
+            base, ld = (int(ptrs[p]) + esz * B * col0, nf * E) if packed else (int(ptrs[p]) + esz * col0, ldx)
             if out_bf16:
-                _mat(int(ptrs[p]) + 2 * col0, B, nf * E, ldx, 1, np.uint16)[...] = f32_to_bf16(rows[p]).reshape(B, nf * E)
+                _mat(base, B, nf * E, ld, 1, np.uint16)[...] = f32_to_bf16(rows[p]).reshape(B, nf * E)
             else:
-                _mat(int(ptrs[p]) + 4 * col0, B, nf * E, ldx)[...] = rows[p]
+                _mat(base, B, nf * E, ld)[...] = rows[p]
         return 0
 
     def dp_push_grads(self, dX, ldg, B, F, E, grad_recv, out_bf16, fbound, rank, world, s):

@@ -29,7 +29,7 @@ def _setup(world, B, F, E, seed, device):
                 nf=[f1 - f0 for f0, f1 in ranges], fbound=np.array([r[0] for r in ranges] + [ranges[-1][1]], dtype=np.int32))
 
 
-def _run(lib, c, device, out_bf16, stream=0):
+def _run(lib, c, device, out_bf16, stream=0, packed=0):
     """Every rank's calls in sequence (no barrier needed inside one stream) -> (X per rank, gradient inbox per owner, oob flags)"""
     W, B, F, E, t = c["world"], c["B"], c["F"], c["E"], c["t"]
     nf_max = max(max(c["nf"]), 1)
@@ -54,12 +54,20 @@ def _run(lib, c, device, out_bf16, stream=0):
         shard = t(c["table"][r0:r1]); keep.append(shard)
         offl = t(c["off"][f0:f1] - r0); keep.append(offl)
         lib.dp_gather_push(ids_in[o].data_ptr(), offl.data_ptr(), shard.data_ptr(), r1 - r0, x_p.data_ptr(), 1 if out_bf16 else 0, ldx,
-                           f0 * E, B, f1 - f0, E, W, oob[o:].data_ptr(), stream)
+                           f0 * E, B, f1 - f0, E, W, packed, oob[o:].data_ptr(), stream)
     for r in range(W):
         dX = t(c["dXs"][r]); keep.append(dX)
         lib.dp_push_grads(dX.data_ptr(), ldx, B, F, E, g_p.data_ptr(), 1 if out_bf16 else 0, fb.data_ptr(), r, W, stream)
     if device != "cpu":
         torch.cuda.synchronize()
+    if packed:                                                 # the requester's unpack: owner o's contiguous [B, nf*E] block -> its columns
+        for r in range(W):
+            flat = X[r].reshape(-1)
+            out = torch.zeros_like(X[r])
+            for o, (f0, f1) in enumerate(c["ranges"]):
+                if f1 > f0 and B:
+                    out[:B, f0 * E:f1 * E] = flat[B * f0 * E:B * f1 * E].view(B, (f1 - f0) * E)
+            X[r] = out
     return X, G, oob, ids_in
 
 
@@ -111,9 +119,10 @@ CASES = [(1, 33, 5, 16), (2, 64, 7, 16), (3, 50, 7, 8), (4, 17, 3, 32), (2, 40, 
 
 @pytest.mark.parametrize("world,B,F,E", CASES)
 @pytest.mark.parametrize("out_bf16", [False, True])
-def test_exchange_emulator_matches_definition(world, B, F, E, out_bf16):
+@pytest.mark.parametrize("packed", [0, 1])
+def test_exchange_emulator_matches_definition(world, B, F, E, out_bf16, packed):
     c = _setup(world, B, F, E, 11 * world + B, "cpu")
-    _check(c, *_run(HostABI(), c, "cpu", out_bf16), out_bf16)
+    _check(c, *_run(HostABI(), c, "cpu", out_bf16, packed=packed), out_bf16)
 
 
 def test_barrier_emulator_counts_calls():
@@ -131,10 +140,11 @@ def test_barrier_emulator_counts_calls():
 @pytest.mark.gpu
 @pytest.mark.parametrize("world,B,F,E", CASES + [(8, 4096, 23, 16), (2, 8192, 26, 32)])
 @pytest.mark.parametrize("out_bf16", [False, True])
-def test_exchange_kernels_match_definition_gpu(world, B, F, E, out_bf16):
+@pytest.mark.parametrize("packed", [0, 1])
+def test_exchange_kernels_match_definition_gpu(world, B, F, E, out_bf16, packed):
     lib = cm._lib.load()
     c = _setup(world, B, F, E, 11 * world + B, "cuda")
-    _check(c, *_run(lib, c, "cuda", out_bf16, torch.cuda.current_stream().cuda_stream), out_bf16)
+    _check(c, *_run(lib, c, "cuda", out_bf16, torch.cuda.current_stream().cuda_stream, packed=packed), out_bf16)
 
 
 @pytest.mark.gpu
