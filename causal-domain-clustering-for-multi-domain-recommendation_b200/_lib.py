@@ -91,6 +91,7 @@ SIGNATURES = {
     "cdcmdr_embed_plan_build": (INT, [P, P, I64, INT, I64, INT, P, SZ, P]),
     "cdcmdr_embed_bwd_dense": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P]),
     "cdcmdr_embed_bwd_adam_dense_exact": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P, P]),
+    "cdcmdr_embed_bwd_adam_dense_exact_g16": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P, P]),
     "cdcmdr_embed_bwd_adam_sparse_lazy": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P]),
     "cdcmdr_embed_bwd_adam_sparse_lazy_reg": (INT, [P, I64, P, INT, I64, INT, INT, I64, P, P, P, F32, P, P, P, P]),
     "cdcmdr_embed_gather_peer": (INT, [P, P, P, I64, P, P, I64, I64, INT, INT, I64, P, P]),

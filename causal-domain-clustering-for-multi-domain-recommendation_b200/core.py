@@ -129,13 +129,14 @@ class Ops:
         self.lib.embed_bwd_dense(grad_out.ptr, grad_out.ld, plan.data_ptr(), E, B, F, E, V, grad_table.data_ptr(), self.stream)
 
     def embed_bwd_adam(self, grad_out: Mat, plan, B, F, E, V, table, m, v, l2, st, reg_sumsq=None, lazy=False):
+        """grad_out: fp32, or (dense-exact update only) the bf16 row gradients of the replicas' exchange"""
         if lazy:
             self.lib.embed_bwd_adam_sparse_lazy(grad_out.ptr, grad_out.ld, plan.data_ptr(), E, B, F, E, V, table.data_ptr(),
                                                 m.data_ptr(), v.data_ptr(), l2, st.data_ptr(), self.stream)
         else:
-            self.lib.embed_bwd_adam_dense_exact(grad_out.ptr, grad_out.ld, plan.data_ptr(), E, B, F, E, V, table.data_ptr(),
-                                                m.data_ptr(), v.data_ptr(), l2, st.data_ptr(),
-                                                reg_sumsq.data_ptr() if reg_sumsq is not None else None, self.stream)
+            fn = self.lib.embed_bwd_adam_dense_exact_g16 if grad_out.is_bf16 else self.lib.embed_bwd_adam_dense_exact
+            fn(grad_out.ptr, grad_out.ld, plan.data_ptr(), E, B, F, E, V, table.data_ptr(), m.data_ptr(), v.data_ptr(), l2, st.data_ptr(),
+               reg_sumsq.data_ptr() if reg_sumsq is not None else None, self.stream)
 
     # ---------------------------------------------------------------- fp32 GEMM
     def gemm_f32(self, *, A, a_rs, a_cs, Bt, b_rs, b_cs, Cm, c_rs, M, N, K, G=1, a_gs=0, b_gs=0, c_gs=0,

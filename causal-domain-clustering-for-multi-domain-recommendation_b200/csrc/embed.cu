@@ -3,6 +3,7 @@
 // E/4 lanes per row so a warp touches 32/(E/4) consecutive rows of w/m/v (fully coalesced sweep).
 #include "common.cuh"
 #include <cub/cub.cuh>
+#include <type_traits>
 
 namespace cdcmdr {
 
@@ -223,10 +224,22 @@ __global__ void plan_segments_kernel(const uint32_t* __restrict__ uniq, const in
   }
 }
 
+// gradient rows arrive as fp32 (the model program's own input gradient) or as bf16 (the replicas' row-gradient exchange, widened here
+// instead of by a separate cast pass over the whole inbox): four consecutive elements of either as a float4
+template <typename GT> __device__ __forceinline__ float4 ld_grad4(const GT* p);
+template <> __device__ __forceinline__ float4 ld_grad4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ float4 ld_grad4<uint16_t>(const uint16_t* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u), __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+template <typename GT> __device__ __forceinline__ float ld_grad1(const GT* p);
+template <> __device__ __forceinline__ float ld_grad1<float>(const float* p) { return *p; }
+template <> __device__ __forceinline__ float ld_grad1<uint16_t>(const uint16_t* p) { return bf16_to_f32(*p); }
+
 // one CTA per piece of a long segment: lane-group j sums entries j, j+G, j+2G, ... in order; fixed smem tree afterwards
-template <int VEC>
+template <int VEC, typename GT>
 __global__ void __launch_bounds__(kLongThreads)
-long_segment_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, const int32_t* __restrict__ vals,
+long_segment_kernel(const GT* __restrict__ grad_out, int64_t ldg, int F, int E, const int32_t* __restrict__ vals,
                     const int32_t* __restrict__ start, const int32_t* __restrict__ cnt, const int32_t* __restrict__ long_seg,
                     const int32_t* __restrict__ long_off, const int32_t* __restrict__ nlong, float* __restrict__ long_sum) {
   extern __shared__ float sm[];                    // [groups][E]
@@ -242,9 +255,9 @@ long_segment_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int 
     if (g < groups) {
       for (int i = g; i < c; i += groups) {
         const int pos = vals[s0 + i];
-        const float* src = grad_out + (int64_t)(pos / F) * ldg + (int64_t)(pos % F) * E + q * VEC;
-        if (VEC == 4) { const float4 t = *reinterpret_cast<const float4*>(src); acc[0] += t.x; acc[1 % VEC] += t.y; acc[2 % VEC] += t.z; acc[3 % VEC] += t.w; }
-        else acc[0] += src[0];
+        const GT* src = grad_out + (int64_t)(pos / F) * ldg + (int64_t)(pos % F) * E + q * VEC;
+        if (VEC == 4) { const float4 t = ld_grad4<GT>(src); acc[0] += t.x; acc[1 % VEC] += t.y; acc[2 % VEC] += t.z; acc[3 % VEC] += t.w; }
+        else acc[0] += ld_grad1<GT>(src);
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) sm[g * E + q * VEC + j] = acc[j];
@@ -265,8 +278,8 @@ long_segment_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int 
   }
 }
 
-template <int VEC>
-__device__ __forceinline__ void segment_sum(float (&acc)[VEC], const float* __restrict__ grad_out, int64_t ldg, int F, int E,
+template <int VEC, typename GT>
+__device__ __forceinline__ void segment_sum(float (&acc)[VEC], const GT* __restrict__ grad_out, int64_t ldg, int F, int E,
                                             int q, int seg, const int32_t* __restrict__ vals, const int32_t* __restrict__ start,
                                             const int32_t* __restrict__ cnt, const int32_t* __restrict__ long_slot,
                                             const float* __restrict__ long_sum) {
@@ -297,7 +310,7 @@ __device__ __forceinline__ void segment_sum(float (&acc)[VEC], const float* __re
         t[u] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pos[u] >= 0) {
           const uint32_t b = (uint32_t)pos[u] / (uint32_t)F, f = (uint32_t)pos[u] - b * (uint32_t)F;
-          t[u] = __ldg(reinterpret_cast<const float4*>(grad_out + (int64_t)b * ldg + (int64_t)f * E + q * VEC));
+          t[u] = ld_grad4<GT>(grad_out + (int64_t)b * ldg + (int64_t)f * E + q * VEC);
         }
       }
 #pragma unroll
@@ -308,8 +321,8 @@ __device__ __forceinline__ void segment_sum(float (&acc)[VEC], const float* __re
   }
   for (int i = 0; i < c; ++i) {
     const int pos = vals[s0 + i];
-    const float* src = grad_out + (int64_t)(pos / F) * ldg + (int64_t)(pos % F) * E + q * VEC;
-    acc[0] += src[0];
+    const GT* src = grad_out + (int64_t)(pos / F) * ldg + (int64_t)(pos % F) * E + q * VEC;
+    acc[0] += ld_grad1<GT>(src);
   }
 }
 
@@ -326,7 +339,7 @@ __global__ void embed_dense_grad_kernel(const float* __restrict__ grad_out, int6
     split_idx(i, lanes, r, q64);
     const int q = (int)q64;
     float acc[VEC];
-    segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg_of_row[r], vals, start, cnt, long_slot, long_sum);
+    segment_sum<VEC, float>(acc, grad_out, ldg, F, E, q, seg_of_row[r], vals, start, cnt, long_slot, long_sum);
     float* o = grad_table + r * E + q * VEC;
     if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
     else o[0] = acc[0];
@@ -390,7 +403,7 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
       for (int u = 0; u < 2; ++u) {
         if (!ok[u]) continue;
         float acc[VEC];
-        segment_sum<VEC>(acc, grad_out, ldg, F, E, q[u], seg[u], vals, start, cnt, long_slot, long_sum);
+        segment_sum<VEC, float>(acc, grad_out, ldg, F, E, q[u], seg[u], vals, start, cnt, long_slot, long_sum);
         sq += (double)w[u].x * w[u].x + (double)w[u].y * w[u].y + (double)w[u].z * w[u].z + (double)w[u].w * w[u].w;
         adam_elem(w[u].x, m[u].x, v[u].x, acc[0], k); adam_elem(w[u].y, m[u].y, v[u].y, acc[1 % VEC], k);
         adam_elem(w[u].z, m[u].z, v[u].z, acc[2 % VEC], k); adam_elem(w[u].w, m[u].w, v[u].w, acc[3 % VEC], k);
@@ -407,7 +420,7 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
       if (DENSE) { seg = seg_of_row[r]; }
       else { seg = (int)r; r = uniq[seg]; if (r >= V) continue; }
       float acc[VEC];
-      segment_sum<VEC>(acc, grad_out, ldg, F, E, q, seg, vals, start, cnt, long_slot, long_sum);
+      segment_sum<VEC, float>(acc, grad_out, ldg, F, E, q, seg, vals, start, cnt, long_slot, long_sum);
       const int64_t o = r * E + q * VEC;
       float w = table[o], m = mom[o], v = var[o];
       sq += (double)w * w;
@@ -431,9 +444,9 @@ embed_adam_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E,
 // Pass 2 (embed_adam_dense4_kernel) is then a pure stream over table / m / v: the only dependent load is seg_of_row -> gsum row,
 // and consecutive touched rows read consecutive gsum rows.  The fused single pass interleaved the segment walks with the sweep:
 // ncu showed long-scoreboard stalls at 29 % of DRAM bandwidth (every warp waited for its slowest segment).
-template <int VEC>
+template <int VEC, typename GT>
 __global__ void __launch_bounds__(256)
-embed_segsum_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int E, const int32_t* __restrict__ nuniq,
+embed_segsum_kernel(const GT* __restrict__ grad_out, int64_t ldg, int F, int E, const int32_t* __restrict__ nuniq,
                     const int32_t* __restrict__ vals, const int32_t* __restrict__ start, const int32_t* __restrict__ cnt,
                     const int32_t* __restrict__ long_slot, const float* __restrict__ long_sum, float* __restrict__ gsum) {
   const int lanes = E / VEC;
@@ -443,7 +456,7 @@ embed_segsum_kernel(const float* __restrict__ grad_out, int64_t ldg, int F, int 
     split_idx(i, lanes, seg, q64);
     const int q = (int)q64;
     float acc[VEC];
-    segment_sum<VEC>(acc, grad_out, ldg, F, E, q, (int)seg, vals, start, cnt, long_slot, long_sum);
+    segment_sum<VEC, GT>(acc, grad_out, ldg, F, E, q, (int)seg, vals, start, cnt, long_slot, long_sum);
     float* o = gsum + seg * E + q * VEC;
     if (VEC == 4) *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
     else o[0] = acc[0];
@@ -584,18 +597,19 @@ extern "C" int cdcmdr_embed_plan_build(const int32_t* x, const int64_t* offsets,
 
 namespace cdcmdr {
 // host copy of the layout is recomputed from (B*F, V, E_max) - the plan header on the device is informational
-static int launch_long(const float* grad_out, int64_t ldg, const void* plan, const EmbedPlan& L, int F, int E, cudaStream_t st) {
+template <typename GT>
+static int launch_long(const GT* grad_out, int64_t ldg, const void* plan, const EmbedPlan& L, int F, int E, cudaStream_t st) {
   const int lanes = (E % 4 == 0) ? E / 4 : E;
   CDC_REQUIRE(lanes <= kLongThreads, "embed_dim too large for the long-segment kernel");
   const size_t smem = (size_t)(kLongThreads / lanes) * E * sizeof(float);
   CDC_REQUIRE(smem <= 48 * 1024, "embed_dim too large for the long-segment kernel");
   const int grid = (int)(L.n_long_max < 8 * kNumSMs ? L.n_long_max : 8 * kNumSMs);
   if (E % 4 == 0)
-    long_segment_kernel<4><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
+    long_segment_kernel<4, GT><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
         at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_long_off), at<int32_t>(plan, L.off_nlong),
         at<float>(plan, L.off_long_sum));
   else
-    long_segment_kernel<1><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
+    long_segment_kernel<1, GT><<<grid, kLongThreads, smem, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start),
         at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_seg), at<int32_t>(plan, L.off_long_off), at<int32_t>(plan, L.off_nlong),
         at<float>(plan, L.off_long_sum));
   CDC_LAUNCHED();
@@ -620,7 +634,8 @@ extern "C" int cdcmdr_embed_bwd_dense(const float* grad_out, int64_t ldg, const 
   return 0;
 }
 
-static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F, int E,
+template <typename GT>
+static int embed_adam_impl(bool dense, const GT* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F, int E,
                            int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h, double* reg_sumsq,
                            cdcmdr_stream_t s, double* reg_running = nullptr) {
   CDC_REQUIRE(E <= E_max, "E exceeds the plan's E_max");
@@ -638,16 +653,17 @@ static int embed_adam_impl(bool dense, const float* grad_out, int64_t ldg, const
              at<int32_t>(plan, L.off_long_slot), at<float>(plan, L.off_long_sum), table, m, v, h, l2, partials
   if (dense && E % 4 == 0) {
     float* gsum = at<float>(plan, L.off_gsum);
-    embed_segsum_kernel<4><<<grid_for(B * F * lanes, 256), 256, 0, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_nuniq),
+    embed_segsum_kernel<4, GT><<<grid_for(B * F * lanes, 256), 256, 0, st>>>(grad_out, ldg, F, E, at<int32_t>(plan, L.off_nuniq),
         at<int32_t>(plan, L.off_vals), at<int32_t>(plan, L.off_start), at<int32_t>(plan, L.off_cnt), at<int32_t>(plan, L.off_long_slot),
         at<float>(plan, L.off_long_sum), gsum);
     CDC_LAUNCHED();
     embed_adam_dense4_kernel<<<grid, 256, 0, st>>>(E, V, at<int32_t>(plan, L.off_seg_of_row), gsum, table, m, v, h, l2, partials);
-  } else if (dense) {
-    embed_adam_kernel<1, true><<<grid, 256, 0, st>>>(ARGS);
-  } else {
-    if (E % 4 == 0) embed_adam_kernel<4, false><<<grid, 256, 0, st>>>(ARGS);
+  } else if constexpr (std::is_same<GT, float>::value) {
+    if (dense) embed_adam_kernel<1, true><<<grid, 256, 0, st>>>(ARGS);
+    else if (E % 4 == 0) embed_adam_kernel<4, false><<<grid, 256, 0, st>>>(ARGS);
     else embed_adam_kernel<1, false><<<grid, 256, 0, st>>>(ARGS);
+  } else {
+    CDC_REQUIRE(false, "bf16 row gradients: only the dense-exact update with embed_dim % 4 == 0 reads them directly");
   }
 #undef ARGS
   CDC_LAUNCHED();
@@ -665,6 +681,13 @@ extern "C" int cdcmdr_embed_bwd_adam_dense_exact(const float* grad_out, int64_t 
                                                  int E, int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h,
                                                  double* reg_sumsq, cdcmdr_stream_t s) {
   return embed_adam_impl(true, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, h, reg_sumsq, s);
+}
+// the same update from bf16 row gradients (what the replicas' gradient exchange delivers): the segment sums widen them on the fly
+extern "C" int cdcmdr_embed_bwd_adam_dense_exact_g16(const uint16_t* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
+                                                     int E, int64_t V, float* table, float* m, float* v, float l2,
+                                                     const cdcmdr_step_state_t* h, double* reg_sumsq, cdcmdr_stream_t s) {
+  CDC_REQUIRE(E % 4 == 0 && ldg % 4 == 0 && ((uintptr_t)grad_out % 8) == 0, "bf16 row gradients: embed_dim and pitch must be multiples of 4");
+  return embed_adam_impl<uint16_t>(true, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, h, reg_sumsq, s);
 }
 extern "C" int cdcmdr_embed_bwd_adam_sparse_lazy(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
                                                  int E, int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h,

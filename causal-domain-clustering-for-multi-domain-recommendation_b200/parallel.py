@@ -375,7 +375,10 @@ class DataParallel:
             sumsq_out.zero_()
             return
         n = N * B * nf_me * E
-        if g16:
+        lazy = self.model.embedding_update == "sparse_lazy"
+        if g16 and not lazy and E % 4 == 0:
+            grecv = px.view("grads", torch.bfloat16, n)        # the segment sums widen the inbox on the fly: no cast pass
+        elif g16:
             grecv = ws.get("dp.grad_recv", (n,), torch.float32)
             ops.cast_bf16_f32(Mat(px.view("grads", torch.bfloat16, n), 0, nf_me * E), Mat(grecv, 0, nf_me * E), N * B, nf_me * E)
         else:

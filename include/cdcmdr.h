@@ -76,6 +76,11 @@ int cdcmdr_embed_bwd_adam_dense_exact(const float* grad_out, int64_t ldg, const 
                                       int E, int64_t V, float* table, float* m, float* v, float l2,
                                       const cdcmdr_step_state_t* st, double* reg_sumsq /* device scalar or NULL */,
                                       cdcmdr_stream_t s);
+/* The same update from BF16 row gradients (the replicas' row-gradient exchange delivers bf16): grad_out bf16 [B, ldg],
+ * widened inside the segment sums - no separate cast pass over the inbox.  Requires E % 4 == 0, ldg % 4 == 0. */
+int cdcmdr_embed_bwd_adam_dense_exact_g16(const uint16_t* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F, int E,
+                                          int64_t V, float* table, float* m, float* v, float l2, const cdcmdr_step_state_t* h,
+                                          double* reg_sumsq, cdcmdr_stream_t s);
 int cdcmdr_embed_bwd_adam_sparse_lazy(const float* grad_out, int64_t ldg, const void* plan, int E_max, int64_t B, int F,
                                       int E, int64_t V, float* table, float* m, float* v, float l2,
                                       const cdcmdr_step_state_t* st, cdcmdr_stream_t s);

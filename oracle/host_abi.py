@@ -135,11 +135,14 @@ class HostABI:
         self._plans[int(plan)] = idx.copy()
         return 0
 
-    def _segment_sums(self, grad_out, ldg, plan, B, F, E, V):
+    def _segment_sums(self, grad_out, ldg, plan, B, F, E, V, g16=False):
         """Sorted-segment scatter-add, ascending (b, f) order inside a row (autograd of nn.Embedding, layer.py:140)."""
         idx = self._plans[int(plan)]
-        go = _mat(grad_out, B, F * E, ldg).reshape(B * F, E) if ldg == F * E else \
-            np.ascontiguousarray(_mat(grad_out, B, F * E, ldg)).reshape(B * F, E)
+        if g16:                                                  # bf16 row gradients, widened exactly
+            go = bf16_to_f32(np.ascontiguousarray(_mat(grad_out, B, F * E, ldg, 1, np.uint16))).reshape(B * F, E)
+        else:
+            go = _mat(grad_out, B, F * E, ldg).reshape(B * F, E) if ldg == F * E else \
+                np.ascontiguousarray(_mat(grad_out, B, F * E, ldg)).reshape(B * F, E)
         g = np.zeros((V + 1, E), dtype=np.float32)
         order = np.argsort(idx, kind="stable")
         rows = idx[order]
@@ -169,6 +172,14 @@ class HostABI:
 
     def embed_bwd_adam_dense_exact(self, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, st, reg_sumsq, s):
         g, _ = self._segment_sums(grad_out, ldg, plan, B, F, E, V)
+        tab, mm, vv = _mat(table, V, E, E), _mat(m, V, E, E), _mat(v, V, E, E)
+        if reg_sumsq:
+            _arr(reg_sumsq, 1, np.float64)[0] = np.square(tab.astype(np.float64)).sum()
+        self._adam(tab, g, mm, vv, st, F32(2.0) * F32(l2))
+        return 0
+
+    def embed_bwd_adam_dense_exact_g16(self, grad_out, ldg, plan, E_max, B, F, E, V, table, m, v, l2, st, reg_sumsq, s):
+        g, _ = self._segment_sums(grad_out, ldg, plan, B, F, E, V, g16=True)
         tab, mm, vv = _mat(table, V, E, E), _mat(m, V, E, E), _mat(v, V, E, E)
         if reg_sumsq:
             _arr(reg_sumsq, 1, np.float64)[0] = np.square(tab.astype(np.float64)).sum()

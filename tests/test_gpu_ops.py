@@ -111,8 +111,10 @@ def test_embed_gather_out_of_range_rows_read_zero():
 
 @pytest.mark.parametrize("B,F,E,V,skew", [(64, 4, 16, 50, False), (3000, 16, 16, 2000, True), (5000, 23, 16, 100000, True),
                                             (777, 6, 3, 40, True), (4096, 8, 64, 300, True)])
-@pytest.mark.parametrize("mode", ["dense_grad", "adam_dense", "adam_lazy"])
+@pytest.mark.parametrize("mode", ["dense_grad", "adam_dense", "adam_dense_g16", "adam_lazy"])
 def test_embed_backward(B, F, E, V, skew, mode):
+    if mode == "adam_dense_g16" and E % 4:
+        pytest.skip("bf16 row gradients need embed_dim % 4 == 0")
     per = V // F
     off = (np.arange(F) * per).astype(np.int64)
 
@@ -141,6 +143,13 @@ def test_embed_backward(B, F, E, V, skew, mode):
             ss = e.zeros(1, dtype=torch.float64)
             lib.embed_bwd_adam_dense_exact(go.data_ptr(), ldg, plan.data_ptr(), E, B, F, E, V, table.data_ptr(), m.data_ptr(),
                                            v.data_ptr(), 1e-3, st.data_ptr(), ss.data_ptr(), 0)
+            return [table, m, v, ss]
+        if mode == "adam_dense_g16":                               # the replicas' exchange delivers bf16 row gradients
+            ss = e.zeros(1, dtype=torch.float64)
+            go16 = go.to(torch.bfloat16)
+            e.keep.append(go16)
+            lib.embed_bwd_adam_dense_exact_g16(go16.data_ptr(), ldg, plan.data_ptr(), E, B, F, E, V, table.data_ptr(), m.data_ptr(),
+                                               v.data_ptr(), 1e-3, st.data_ptr(), ss.data_ptr(), 0)
             return [table, m, v, ss]
         lib.embed_bwd_adam_sparse_lazy(go.data_ptr(), ldg, plan.data_ptr(), E, B, F, E, V, table.data_ptr(), m.data_ptr(),
                                        v.data_ptr(), 1e-3, st.data_ptr(), 0)
