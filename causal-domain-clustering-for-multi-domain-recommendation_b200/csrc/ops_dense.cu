@@ -797,18 +797,22 @@ sigmoid_select_bce_kernel(const float* __restrict__ logits, const float* __restr
       else if (t == c) { ps = y; ys = y; }
     }
     if (mode == 2) ps = ps / (float)T;
+    // a selection outside [0, T) (a domain id outside the table gives -1 from domain_to_group): the reference's gather raises; here
+    // the row's prediction and the step's loss become NaN - loud in step_losses() - and the row contributes no gradient
+    const bool bad_sel = mode == 0 && (unsigned)c >= (unsigned)T;
+    if (bad_sel) ps = __int_as_float(0x7fc00000);
     if (psel) psel[b] = ps;
     if (target) {
       const float tg = (float)target[b];
       const float lp = fmaxf(logf(ps), -100.f), l1p = fmaxf(log1pf(-ps), -100.f);
-      loss += (double)(-(tg * lp + (1.f - tg) * l1p));
+      loss += bad_sel ? (double)ps : (double)(-(tg * lp + (1.f - tg) * l1p));
       if (dlogits) {
         const float dps = (ps - tg) / fmaxf((1.f - ps) * ps, 1e-12f) * inv_batch;
         float dsum = 0.f;
         for (int t = 0; t < T; ++t) {
           float dz;
           if (mode == 2) { const float y = pred[b * T + t]; dz = dps / (float)T * y * (1.f - y); }
-          else dz = (t == c) ? dps * ys * (1.f - ys) : 0.f;
+          else dz = (t == c && !bad_sel) ? dps * ys * (1.f - ys) : 0.f;
           dlogits[b * T + t] = dz;
           dsum += dz;
         }

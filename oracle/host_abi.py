@@ -522,9 +522,12 @@ class HostABI:
         y = (F32(1) / (F32(1) + np.exp(-z))).astype(np.float32)
         _mat(pred, B, T, T)[...] = y
         ar = np.arange(B)
+        bad = np.zeros(B, dtype=bool)
         if mode == 0:
             c = _arr(sel, B, np.int64).astype(np.int64)
-            ps = y[ar, c]
+            bad = (c < 0) | (c >= T)                              # out-of-range selection: NaN prediction / loss, no gradient
+            c = np.where(bad, 0, c)
+            ps = np.where(bad, F32(np.nan), y[ar, c]).astype(np.float32)
         elif mode == 1:
             c = np.full(B, col, dtype=np.int64)
             ps = y[ar, c]
@@ -539,7 +542,8 @@ class HostABI:
             with np.errstate(divide="ignore"):
                 lp = np.maximum(np.log(ps), F32(-100))
                 l1p = np.maximum(np.log1p(-ps), F32(-100))
-            _arr(loss_sum, 1, np.float64)[0] = (-(tg * lp + (F32(1) - tg) * l1p)).astype(np.float64).sum()
+            with np.errstate(invalid="ignore"):
+                _arr(loss_sum, 1, np.float64)[0] = np.where(bad, np.nan, -(tg * lp + (F32(1) - tg) * l1p)).astype(np.float64).sum()
             if dlogits:
                 dps = (ps - tg) / np.maximum((F32(1) - ps) * ps, F32(1e-12)) * F32(inv_batch)
                 dz = np.zeros((B, T), dtype=np.float32)
@@ -547,7 +551,8 @@ class HostABI:
                     dz = (dps / F32(T))[:, None] * y * (F32(1) - y)
                 else:
                     ys = y[ar, c]
-                    dz[ar, c] = dps * ys * (F32(1) - ys)
+                    with np.errstate(invalid="ignore"):
+                        dz[ar, c] = np.where(bad, F32(0), dps * ys * (F32(1) - ys))
                 _mat(dlogits, B, T, T)[...] = dz
                 if dlin:
                     _mat(dlin, B, 1, ld_dlin)[:, 0] = dz.sum(1)

@@ -382,6 +382,28 @@ def test_bce_saturated_probabilities_are_clamped():
     both(fn, tol=1e-5)
 
 
+def test_out_of_range_tower_selection_is_loud():
+    """mode 0 with a selection outside [0, T) (domain_to_group gives -1 for an unknown domain id): the reference's y_cat.gather
+    raises; here the row's prediction and the loss are NaN and the row contributes no gradient."""
+    def fn(lib, e):
+        logits = e.f32(6, 3)
+        sel = e.put(np.array([0, 2, -1, 1, 3, 2], dtype=np.int64))
+        tg = e.put(np.array([0, 1, 1, 0, 1, 0], dtype=np.int16))
+        pred, ps, ls, dl = e.zeros(6, 3), e.zeros(6), e.zeros(1, dtype=torch.float64), e.zeros(6, 3)
+        sc = e.scratch(lib.reduce_scratch_bytes())
+        lib.sigmoid_select_bce(logits.data_ptr(), None, 0, 6, 3, 0, sel.data_ptr(), 0, tg.data_ptr(), 0, pred.data_ptr(), ps.data_ptr(),
+                               ls.data_ptr(), dl.data_ptr(), None, 0, 1 / 6, sc.data_ptr(), 0)
+        return [pred, ps, ls, dl]
+    cpu, gpu = Env(3).run(fn)
+    for out in (cpu, gpu):
+        pred, ps, ls, dl = out
+        assert np.isnan(ps[[2, 4]]).all() and not np.isnan(ps[[0, 1, 3, 5]]).any()
+        assert np.isnan(ls[0])
+        assert not dl[[2, 4]].any() and not np.isnan(dl).any() and np.abs(dl[[0, 1, 3, 5]]).sum() > 0
+    check(cpu[0], gpu[0], tol=1e-6)
+    check(cpu[3], gpu[3], tol=1e-5)
+
+
 # ------------------------------------------------------------------------------------------------ regulariser / Adam / reductions
 def test_reg_adam_colsum_and_elementwise():
     n = 100003
