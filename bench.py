@@ -313,15 +313,18 @@ def ours_arm(args):
     dev_batches = [(torch.from_numpy(x).to(dev), torch.from_numpy(y).to(dev), d) for x, y, d in batches]
     pin_batches = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory(), d) for x, y, d in batches]
     # one CUDA graph per cluster column (the selected tower is a kernel argument), sharing the static input buffers
+    # N > 1: the recorded step issues the NEXT batch's embedding exchange behind its own table update (GraphedTrainStep prefetch=True;
+    # the loops below hand it batch i+1 with batch i, as a prefetching loader would) - every step still performs exactly one exchange
+    pipelined = world > 1 and os.environ.get("CDCMDR_PREFETCH_EXCHANGE", "1") != "0"
     steps_by_col = {}
     proto = None
     for x, y, d in dev_batches:
         col = d2g[d]
         if col in steps_by_col:
             continue
-        g = cm.GraphedTrainStep(model, opt, B, F, mode="split", domain_i=d)
+        g = cm.GraphedTrainStep(model, opt, B, F, mode="split", domain_i=d, prefetch=pipelined)
         if proto is not None:
-            g.x, g.y = proto.x, proto.y
+            g.x, g.y, g.x_next = proto.x, proto.y, proto.x_next
         proto = proto or g
         g.x.copy_(x); g.y.copy_(y)
         g.capture()
@@ -333,12 +336,20 @@ def ours_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    resident_it = [0]
+
     def run_resident(n):
-        for i in range(n):
+        for _ in range(n):
+            i = resident_it[0]
             x, y, d = dev_batches[i % nb]
             g = steps_by_col[d2g[d]]
             g.x.copy_(x); g.y.copy_(y)
+            if pipelined:
+                if i == 0:
+                    g.prime()                                   # pipeline fill: the first batch's exchange, once
+                g.x_next.copy_(dev_batches[(i + 1) % nb][0])
             g()
+            resident_it[0] = i + 1
 
     sums_host = torch.zeros(4, dtype=torch.float64).pin_memory()
 
@@ -346,9 +357,41 @@ def ours_arm(args):
     # copy stream into one of two staging buffers while step i computes (the way a DataLoader with pin_memory + non_blocking
     # copies is meant to be used); the step's static input buffers are then filled device-to-device.
     copy_stream = torch.cuda.Stream()
-    stage = [(torch.empty_like(proto.x), torch.empty_like(proto.y)) for _ in range(2)]
+    stage = [(torch.empty_like(proto.x), torch.empty_like(proto.y)) for _ in range(3 if pipelined else 2)]
+
+    def run_e2e_pipelined(n):
+        """The same, one batch deeper: step i needs batch i (its inputs) AND batch i+1's indices (exchanged behind step i's table
+        update), so the upload of batch i+2 is what runs while step i computes.  Every batch still crosses H2D inside the timed
+        region, every step's loss is read back before the next step is launched."""
+        main = torch.cuda.current_stream()
+
+        def upload(i):
+            x, y, _ = pin_batches[i % nb]
+            sx, sy = stage[i % 3]
+            copy_stream.wait_stream(main)                       # the staging buffer's previous readers (step i-3, i-2) are behind us
+            with torch.cuda.stream(copy_stream):
+                sx.copy_(x, non_blocking=True); sy.copy_(y, non_blocking=True)
+                ev = torch.cuda.Event(); ev.record(copy_stream)
+            return ev
+        evs = {0: upload(0), 1: upload(1)}
+        for i in range(n):
+            _, _, d = pin_batches[i % nb]
+            g = steps_by_col[d2g[d]]
+            main.wait_event(evs.pop(i))
+            sx, sy = stage[i % 3]
+            g.x.copy_(sx); g.y.copy_(sy)
+            if i == 0:
+                g.prime()
+            main.wait_event(evs[i + 1])
+            g.x_next.copy_(stage[(i + 1) % 3][0])
+            evs[i + 2] = upload(i + 2)
+            out = g()
+            sums_host.copy_(out["sums"], non_blocking=True)
+            main.synchronize()                                  # the reference reads loss.item() every step (run.py:641)
 
     def run_e2e(n):
+        if pipelined:
+            return run_e2e_pipelined(n)
         main = torch.cuda.current_stream()
 
         def upload(i):
@@ -451,6 +494,9 @@ def ours_arm(args):
             "roofline": roof, "embedding": emb, "cdc_amortised": amort, "cpu_baseline": cpu, "lib": lib.path}
     if roof is not None and peaks:
         roof["peak_source"] = "MEASURED_PEAKS.json (driver-measured on this pool)"
+    if pipelined:
+        line["config"]["embedding_exchange"] = ("pipelined: each step issues the NEXT batch's index / row exchange behind its own table "
+                                                "update (one exchange per step; CDCMDR_PREFETCH_EXCHANGE=0 runs it at the head of the step)")
     emit(line)
     if world > 1:
         sys.stdout.flush(); sys.stderr.flush()

@@ -116,17 +116,18 @@ class CDC(BaseModel):
                                    groups.data_ptr(), rt.ops.stream)
         return groups
 
-    def train_step(self, x, y, optimizer, mode='split', domain_i=None):
-        """run.py:616-622 (warmup) / 635-640 (split), fused."""
+    def train_step(self, x, y, optimizer, mode='split', domain_i=None, x_next=None, prefetched=False):
+        """run.py:616-622 (warmup) / 635-640 (split), fused.  x_next / prefetched: BaseModel.train_step (exchange pipelining)."""
         base = self.base_model_instance
+        pf = dict(x_next=x_next, prefetched=prefetched)
         if mode == 'warmup':
-            return base.train_step(x, y, optimizer, mode="mean")
+            return base.train_step(x, y, optimizer, mode="mean", **pf)
         if mode != 'split':
             raise ValueError(f"unknown CDC mode {mode!r}")
         if domain_i is None:
             base._check_device(x)
-            return base.train_step(x, y, optimizer, mode="gather", sel=self._groups_of(x.contiguous()))
-        return base.train_step(x, y, optimizer, mode="col", col=self.domain2group_list[domain_i])
+            return base.train_step(x, y, optimizer, mode="gather", sel=self._groups_of(x.contiguous()), **pf)
+        return base.train_step(x, y, optimizer, mode="col", col=self.domain2group_list[domain_i], **pf)
 
     step_losses = staticmethod(BaseModel.step_losses)
 

@@ -12,15 +12,22 @@ class GraphedTrainStep:
 
     usage:  step = GraphedTrainStep(model, optimizer, B, F, mode='split', domain_i=3)
             step.x.copy_(batch_x, non_blocking=True); step.y.copy_(batch_y, non_blocking=True); out = step()
+
+    prefetch=True (data-parallel replicas with the field-sharded table): the recorded step skips its own embedding exchange and
+    instead issues the exchange of `step.x_next` - the NEXT batch's indices, which the caller fills before every replay - behind
+    its table update (BaseModel.train_step).  `step.prime()` runs the exchange of `step.x` once, eagerly; it is needed before the
+    first replay (capture() does it) and after anything else ran a forward at this batch size.
     """
 
-    def __init__(self, model, optimizer, B, F, y_dtype=torch.int16, warmup=2, **kw):
+    def __init__(self, model, optimizer, B, F, y_dtype=torch.int16, warmup=2, prefetch=False, **kw):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("CUDA graphs need a CUDA device")
         self.model, self.optimizer, self.kw = model, optimizer, kw
         self.x = torch.zeros(B, F, dtype=torch.int32, device=dev)
         self.y = torch.zeros(B, dtype=y_dtype, device=dev)
+        self.prefetch = bool(prefetch)
+        self.x_next = torch.zeros(B, F, dtype=torch.int32, device=dev) if self.prefetch else None
         self.graph = None
         self.out = None
         self.warmup = warmup
@@ -44,19 +51,29 @@ class GraphedTrainStep:
                 for _ in range(self.warmup):
                     self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
             torch.cuda.current_stream().wait_stream(side)
+        if self.prefetch:
+            self.prime()                                # X of the first replay; the recorded step consumes it and prefetches x_next
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = lib.launch_count()
+        step_kw = dict(self.kw, x_next=self.x_next, prefetched=True) if self.prefetch else self.kw
         # The main branch is captured on a HIGH-priority stream (the side branch's stream has the default, lowest priority): kernel
         # nodes inherit it, so whenever both branches have CTAs waiting for an SM the model program's go first - the side branch fills
         # what is left (it used to hold the split-K reduce behind the table sweep for ~30 us at the end of the step).
         cap = torch.cuda.Stream(device=self.x.device, priority=-1) if os.environ.get("CDCMDR_GRAPH_PRIORITY", "1") != "0" else None
         with torch.cuda.graph(self.graph, stream=cap):
-            self.out = self.model.train_step(self.x, self.y, self.optimizer, **self.kw)
+            self.out = self.model.train_step(self.x, self.y, self.optimizer, **step_kw)
         self.launches_per_step = int(lib.launch_count() - n0)
         self.optimizer.steps -= 1          # capture records the step but does not execute it
         self._gen = self._routing_generation()
         return self
+
+    def prime(self):
+        """Eager exchange of `self.x` (indices to the owners, rows back into X): what the previous step's prefetch would have left."""
+        base = self.model_base()
+        rt = base._rt
+        B = self.x.shape[0]
+        base._gather(rt.ws(B), self.x, B, phase="exchange")
 
     def model_base(self):
         return getattr(self.model, "base_model_instance", self.model)

@@ -336,7 +336,9 @@ class BaseModel(nn.Module):
             ws.marks.add("X.ones")
         return X
 
-    def _gather(self, ws, x, B, plan_ahead=False):
+    def _gather(self, ws, x, B, plan_ahead=False, phase="all"):
+        """phase (replicas with the field-sharded table only): "exchange" = fill X for `x` without planning (the prefetch of the NEXT
+        step's batch), "consume" = X was prefetched by the previous step."""
         rt = self._rt
         E, F = self.embed_dim, self.field_num
         table = self.embedding.embedding_dict.weight
@@ -345,8 +347,15 @@ class BaseModel(nn.Module):
         if rt.dp is not None and rt.dp.shard:
             rt.dp.prepare_ws(ws, B)                            # peer exchange: X is the symmetric buffer the owners store into
         X = self._x_mat(ws, B)
+        if phase != "all" and not (rt.dp is not None and rt.dp.shard):
+            raise ValueError("cdcmdr: x_next / prefetched apply to data-parallel replicas with the field-sharded table")
         if rt.dp is not None and rt.dp.shard:
-            rt.dp.embed_forward(ws, x, B, X, plan_ahead)   # row-sharded table: indices to the owners, rows back (parallel.py)
+            if phase == "consume" and rt.dp._pref != B:
+                raise RuntimeError("cdcmdr: prefetched=True but no prefetched exchange is pending for this batch size (another forward "
+                                   "ran in between, or the previous step had no x_next): call train_step without prefetched once")
+            rt.dp.embed_forward(ws, x, B, X, plan_ahead, phase)   # row-sharded table: indices to the owners, rows back (parallel.py)
+            if phase == "consume":
+                rt.dp._pref = None
             if rt.bf16 and self._att_needs_x32():
                 # the rows travel in bf16 on this path: a block that computes in fp32 reads them widened back
                 rt.ops.cast_bf16_f32(X, ws.mat("X32", B, F * E), B, F * E)
@@ -505,12 +514,21 @@ class BaseModel(nn.Module):
     # ---------------------------------------------------------------- fused training step
     SEL_MODES = {"gather": 0, "col": 1, "mean": 2}
 
-    def train_step(self, x, y, optimizer, mode="gather", sel=None, col=0, **kw):
+    def train_step(self, x, y, optimizer, mode="gather", sel=None, col=0, x_next=None, prefetched=False, **kw):
         """One pass of run.py:483-492 entirely on the device, no host synchronisation:
         gather -> model -> sigmoid -> tower selection -> BCE(mean) -> backward -> regulariser -> Adam (dense arena and
         embedding table).  `optimizer` is a cdcmdr Adam (optim.py).  Returns a dict of device tensors:
-        loss (= bce + reg), bce, reg, pred (B, T)."""
+        loss (= bce + reg), bce, reg, pred (B, T).
+
+        Replicas with the field-sharded table can pipeline the embedding exchange across steps (what a prefetching loader does for
+        the batch itself): `x_next` = the NEXT step's indices - their exchange (indices to the owners, rows back) is issued behind
+        this step's table update, next to the dense all-reduce and optimizer, and the next call passes `prefetched=True` to skip
+        its own exchange.  The rows are gathered AFTER this step's update, so the numbers are those of the unpipelined loop."""
         self._check_device(x)
+        if x_next is not None:
+            self._check_device(x_next)
+            if x_next.shape != x.shape:
+                raise ValueError("cdcmdr: x_next must have the shape of x")
         # model.eval() + a training step is legal in the reference and HAPPENS there: cdc_test_all_domain (run.py:551) leaves the
         # model in eval mode, so most probe steps of update_matrix_cdc - and the rest of that epoch - run BatchNorm on its running
         # statistics (gradients flow through the fixed affine map) with dropout off.
@@ -523,7 +541,7 @@ class BaseModel(nn.Module):
         rt.ensure_opt_state()
         optimizer.tick(rt)                                   # t += 1, dropout seed, Adam scalars
         rt.refresh_operands()
-        X = self._gather(ws, x, B, plan_ahead=True)
+        X = self._gather(ws, x, B, plan_ahead=True, phase="consume" if prefetched else "all")
         # The backward plan of the embedding (sort of the step's indices into segments) only needs x: it runs on a side stream
         # next to the model program (a parallel branch of the CUDA graph) and is joined before the segment sums.
         table = self.embedding.embedding_dict.weight
@@ -590,15 +608,24 @@ class BaseModel(nn.Module):
             # the dense arena's regulariser + Adam follow on the main stream.  (Host issue order = order on the process group's
             # communicator: the row exchange first.)
             if side is not None:
+                bwd_done = torch.cuda.current_stream(rt.device).record_event()   # X's last reader (level-0 weight gradient) is behind this
                 fork_side()
                 with torch.cuda.stream(side):
                     dp.embed_backward(ws, dX, B, l2t, sums[1:2])
                 dp.all_reduce_sum(rt.G)                      # dense gradients: sum over replicas of d(global mean loss)
                 dense_update()
+                if x_next is not None:
+                    # the NEXT step's exchange, behind this step's table update (same stream) and next to the dense all-reduce /
+                    # optimizer above: its rows are the updated ones, and the next step starts with X in place
+                    with torch.cuda.stream(side):
+                        side.wait_event(bwd_done)
+                        self._gather(ws, x_next.contiguous(), B, phase="exchange")
             else:
                 dp.all_reduce_sum(rt.G)
                 dense_update()
                 dp.embed_backward(ws, dX, B, l2t, sums[1:2])
+                if x_next is not None:
+                    self._gather(ws, x_next.contiguous(), B, phase="exchange")
         else:
             if dp is not None:
                 raise NotImplementedError("cdcmdr: data-parallel replicas need the row-sharded table (shard_embedding=True)")

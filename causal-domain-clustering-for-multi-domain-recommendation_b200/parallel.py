@@ -208,6 +208,7 @@ class DataParallel:
         self.rows_override = None
         self.peer = None
         self._px_used = None
+        self._pref = None                                       # batch size whose X / index inbox hold a prefetched exchange
         self._peer_f32 = {}
         self._px = {}                                           # batch size -> PeerExchange (or None: NCCL path)
         dev = emb.embedding_dict.weight.device
@@ -324,19 +325,41 @@ class DataParallel:
         """Called before the first exchange of a batch size: the symmetric buffers are made here (a collective)."""
         self.peer_exchange(B)
 
-    def _embed_forward_peer(self, px, ws, x, B, X: Mat, plan_ahead):
+    def _plan_ahead(self, recv_ids, B, plan_ahead):
+        """The owner-side backward plan over the received indices, on the side stream next to the model program."""
         rt = self.model._rt
         ops, N, E = rt.ops, self.world, self.E
         nf_me = self.f1 - self.f0
-        st = self._state(x.device)
-        lib, stream = ops.lib, ops.stream
-        px.barrier(0, stream)                                   # every owner is done with the previous step's inboxes
-        lib.dp_push_ids(x.data_ptr(), B, self.F, px.ids_ptrs.data_ptr(), px.fbound.data_ptr(), self.rank, N, stream)
-        px.barrier(1, stream)
-        recv_ids = px.view("ids", torch.int32, N * B * max(nf_me, 1))
+        st = self._state(recv_ids.device)
         self._plan, self._plan_event = None, None
         side = rt.side_stream() if plan_ahead else None
         if nf_me and plan_ahead:
+            Vl = self.shard_view().shape[0]
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream(rt.device))
+                with torch.cuda.stream(side):
+                    self._plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+                    self._plan_event = side.record_event()
+            else:
+                self._plan = ops.embed_plan(recv_ids, st["offsets_local"], N * B, nf_me, Vl, E)
+
+    def _embed_forward_peer(self, px, ws, x, B, X: Mat, plan_ahead, phase="all"):
+        rt = self.model._rt
+        ops, N, E = rt.ops, self.world, self.E
+        nf_me = self.f1 - self.f0
+        st = self._state(X.t.device)
+        lib, stream = ops.lib, ops.stream
+        recv_ids = px.view("ids", torch.int32, N * B * max(nf_me, 1))
+        if phase == "consume":                                  # X and the index inbox were filled by the previous step's prefetch
+            self._plan_ahead(recv_ids, B, plan_ahead)
+            self._px_used = px
+            return recv_ids
+        px.barrier(0, stream)                                   # every owner is done with the previous step's inboxes
+        lib.dp_push_ids(x.data_ptr(), B, self.F, px.ids_ptrs.data_ptr(), px.fbound.data_ptr(), self.rank, N, stream)
+        px.barrier(1, stream)
+        self._plan, self._plan_event = None, None
+        side = rt.side_stream() if (plan_ahead and phase == "all") else None
+        if nf_me and plan_ahead and phase == "all":
             Vl = self.shard_view().shape[0]
             if side is not None:
                 side.wait_stream(torch.cuda.current_stream(rt.device))
@@ -398,26 +421,37 @@ class DataParallel:
         ops.embed_bwd_adam(Mat(grecv, 0, nf_me * E), plan, N * B, nf_me, E, Vl, shard, m, v, l2, rt.step_state,
                            None if lazy else sumsq_out, lazy=lazy)
 
-    def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False):
+    def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False, phase="all"):
         """x: this rank's [B, F] int32 indices -> X[B, F*E] (activation dtype) through the owners of each field.
         plan_ahead (training step): the owner-side backward plan over the received indices starts on the side stream as soon as
-        they have arrived and runs next to the model program."""
+        they have arrived and runs next to the model program.
+        phase: "all" = exchange + plan; "exchange" = only fill X and the index inbox (the PREFETCH of the next step's batch, issued
+        behind this step's table update); "consume" = X and the inbox were prefetched: only the plan."""
         rt = self.model._rt
+        if phase != "consume":
+            self._pref = None                                   # any other exchange at this batch size overwrites X and the inbox
         px = self._px.get(B)
         if px is not None:
-            return self._embed_forward_peer(px, ws, x, B, X, plan_ahead)
+            out = self._embed_forward_peer(px, ws, x, B, X, plan_ahead, phase)
+            if phase == "exchange":
+                self._pref = B
+            return out
         self._px_used = None
         ops, N, E, F = rt.ops, self.world, self.E, self.F
         nf_me = self.f1 - self.f0
-        st = self._state(x.device)
+        st = self._state(X.t.device)
+        if phase == "consume":
+            recv_ids = ws.get("dp.recv_ids", (N * B * max(nf_me, 1),), torch.int32)
+            self._plan_ahead(recv_ids, B, plan_ahead)
+            return recv_ids
         send_ids = ws.get("dp.send_ids", (B * F,), torch.int32)
         for (f0, n, cnt) in self._range_runs():               # owner o's block: [B, n] at element offset B*f0
             ops.copy2d_batched(x.data_ptr() + 4 * f0, n, F, send_ids.data_ptr() + 4 * B * f0, B * n, n, cnt, B, n, 4)
         recv_ids = ws.get("dp.recv_ids", (N * B * max(nf_me, 1),), torch.int32)
         self._all_to_all(recv_ids[:N * B * nf_me], send_ids[:B * F], [B * nf_me] * N, [B * n for n in self.nf])
         self._plan, self._plan_event = None, None
-        side = rt.side_stream() if plan_ahead else None
-        if nf_me and plan_ahead:
+        side = rt.side_stream() if (plan_ahead and phase == "all") else None
+        if nf_me and plan_ahead and phase == "all":
             Vl = self.shard_view().shape[0]
             if side is not None:
                 side.wait_stream(torch.cuda.current_stream(rt.device))
@@ -438,6 +472,8 @@ class DataParallel:
         for (f0, n, cnt) in self._range_runs():
             ops.copy2d_batched(rows_recv.data_ptr() + esz * B * f0 * E, B * n * E, n * E, X.ptr + esz * f0 * E, n * E, X.ld, cnt, B, n * E,
                                esz)
+        if phase == "exchange":
+            self._pref = B
         return recv_ids
 
     def embed_backward(self, ws, dX: Mat, B, l2, sumsq_out):
@@ -553,7 +589,9 @@ class RowRangeParallel(DataParallel):
     def prepare_ws(self, ws, B):
         pass                                                     # rows are read from their owners' shards: no exchange buffers
 
-    def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False):
+    def embed_forward(self, ws, x, B, X: Mat, plan_ahead=False, phase="all"):
+        if phase != "all":
+            raise NotImplementedError("cdcmdr: the row-range layout reads rows from their owners - there is no exchange to prefetch")
         rt = self.model._rt
         ops, N, E, F = rt.ops, self.world, self.E, self.F
         emb = self.model.embedding

@@ -327,3 +327,63 @@ def test_row_routed_star_on_two_replicas_matches_one_process():
                 assert np.abs(got - v).max() <= 2.1e-3 * n_steps, k
                 continue
             assert np.abs(got - v).max() <= 2e-5 * max(1.0, float(np.abs(v).max())), (k, float(np.abs(got - v).max()))
+
+
+# ---------------------------------------------------------------- the next step's exchange issued behind this step's table update
+def _worker_prefetch(rank, world, port, kind, B, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cm._lib.install(HostABI())
+        rng = np.random.default_rng(17)
+        xs = [np.stack([rng.integers(0, d, size=B) for d in FD], axis=1).astype(np.int32) for _ in range(4)]
+        ys = [(rng.random(B) < 0.3).astype(np.int16) for _ in range(4)]
+        gs = [rng.integers(0, T, size=B).astype(np.int64) for _ in range(4)]
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        res = {}
+        for variant in ("plain", "pipelined"):
+            model = _build(kind)
+            cm.parallel.attach_data_parallel(model)
+            opt = cm.Adam(model.parameters(), **ADAM)
+            model.train()
+            for k in range(4):
+                xt, yt, gt = (torch.from_numpy(a[k][lo:hi]) for a in (xs, ys, gs))
+                kw = dict(mode="split", domain_i=None) if kind == "cdc" else dict(mode="gather", sel=gt)
+                if variant == "pipelined":                      # step k exchanges batch k+1 behind its own table update
+                    kw.update(x_next=torch.from_numpy(xs[k + 1][lo:hi]) if k < 3 else None, prefetched=k > 0)
+                out = model.train_step(xt, yt, opt, **kw)
+                res[f"{variant}.pred{k}"] = out["pred"].clone().numpy()
+                res[f"{variant}.loss{k}"] = np.array(model.step_losses(out))
+            for k_, v in model.state_dict().items():
+                res[f"{variant}.{k_}"] = v.detach().numpy().copy()
+            if variant == "pipelined":                          # a forward in between invalidates a pending prefetch: the next consume refuses
+                xt, yt, gt = (torch.from_numpy(a[0][lo:hi]) for a in (xs, ys, gs))
+                kw = dict(mode="split", domain_i=None) if kind == "cdc" else dict(mode="gather", sel=gt)
+                model.train_step(xt, yt, opt, x_next=xt, **kw)
+                with torch.no_grad():
+                    model(xt)
+                try:
+                    model.train_step(xt, yt, opt, prefetched=True, **kw)
+                    res["refused"] = np.array(0)
+                except RuntimeError:
+                    res["refused"] = np.array(1)
+        np.savez(os.path.join(path, f"rank{rank}.npz"), **res)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,world", [("ple", 2), ("cdc", 3)])
+def test_pipelined_exchange_is_bit_identical_to_the_plain_loop(kind, world):
+    """train_step(x_next=...) / train_step(prefetched=True): the next batch's index / row exchange is issued behind this step's table
+    update.  Four steps over four different batches: predictions, losses and every parameter are BIT identical to the plain loop
+    (the prefetched rows are the updated ones), and a forward in between makes the next `prefetched=True` raise."""
+    B = 96
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker_prefetch, args=(world, _free_port(), kind, B, tmp), nprocs=world, join=True)
+        ranks = [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
+    for r in range(world):
+        keys = [k[len("plain."):] for k in ranks[r] if k.startswith("plain.")]
+        assert len(keys) > 10
+        for k in keys:
+            assert np.array_equal(ranks[r]["plain." + k], ranks[r]["pipelined." + k], equal_nan=True), (r, k)
+        assert int(ranks[r]["refused"]) == 1
