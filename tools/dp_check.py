@@ -41,9 +41,6 @@ pf = os.environ.get("CHECK_PREFETCH") == "1"      # the next step's exchange iss
 for k in range(3):
     out = model.train_step(xt, yt, opt, mode="split", domain_i=7, x_next=xt if pf else None, prefetched=pf and k > 0)
     losses.append(model.step_losses(out))
-if pf:                                             # the exchange left pending for a step that never comes: consume it with a forward
-    with torch.no_grad():
-        model(xt, mode="split", domain_i=7)
 pred = out["pred"].clone()
 sd = model.state_dict()                      # collective under the sharded table: every rank calls it (the hook gathers the owners' rows)
 torch.cuda.synchronize()
