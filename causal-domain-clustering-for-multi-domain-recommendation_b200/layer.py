@@ -356,6 +356,8 @@ class BaseModel(nn.Module):
             rt.dp.embed_forward(ws, x, B, X, plan_ahead, phase)   # row-sharded table: indices to the owners, rows back (parallel.py)
             if phase == "consume":
                 rt.dp._pref = None
+            if phase == "ids":
+                return X
             if rt.bf16 and self._att_needs_x32():
                 # the rows travel in bf16 on this path: a block that computes in fp32 reads them widened back
                 rt.ops.cast_bf16_f32(X, ws.mat("X32", B, F * E), B, F * E)
@@ -542,6 +544,17 @@ class BaseModel(nn.Module):
         optimizer.tick(rt)                                   # t += 1, dropout seed, Adam scalars
         rt.refresh_operands()
         X = self._gather(ws, x, B, plan_ahead=True, phase="consume" if prefetched else "all")
+        if x_next is not None:
+            # the next batch's indices travel to their owners now (the index inbox is free once this step's plan is built): on the
+            # side stream behind the plan, under the forward
+            x_next = x_next.contiguous()
+            side_ = rt.side_stream()
+            if side_ is not None:
+                side_.wait_stream(torch.cuda.current_stream(rt.device))   # (also makes the side stream part of a graph capture)
+                with torch.cuda.stream(side_):
+                    self._gather(ws, x_next, B, phase="ids")
+            else:
+                self._gather(ws, x_next, B, phase="ids")
         # The backward plan of the embedding (sort of the step's indices into segments) only needs x: it runs on a side stream
         # next to the model program (a parallel branch of the CUDA graph) and is joined before the segment sums.
         table = self.embedding.embedding_dict.weight
@@ -619,13 +632,13 @@ class BaseModel(nn.Module):
                     # optimizer above: its rows are the updated ones, and the next step starts with X in place
                     with torch.cuda.stream(side):
                         side.wait_event(bwd_done)
-                        self._gather(ws, x_next.contiguous(), B, phase="exchange")
+                        self._gather(ws, x_next, B, phase="rows")
             else:
                 dp.all_reduce_sum(rt.G)
                 dense_update()
                 dp.embed_backward(ws, dX, B, l2t, sums[1:2])
                 if x_next is not None:
-                    self._gather(ws, x_next.contiguous(), B, phase="exchange")
+                    self._gather(ws, x_next, B, phase="rows")
         else:
             if dp is not None:
                 raise NotImplementedError("cdcmdr: data-parallel replicas need the row-sharded table (shard_embedding=True)")

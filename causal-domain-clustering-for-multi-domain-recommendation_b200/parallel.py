@@ -209,6 +209,7 @@ class DataParallel:
         self.peer = None
         self._px_used = None
         self._pref = None                                       # batch size whose X / index inbox hold a prefetched exchange
+        self._ids_pending = None                                # ... whose index inbox holds the next batch, rows still to come
         self._peer_f32 = {}
         self._px = {}                                           # batch size -> PeerExchange (or None: NCCL path)
         dev = emb.embedding_dict.weight.device
@@ -354,9 +355,12 @@ class DataParallel:
             self._plan_ahead(recv_ids, B, plan_ahead)
             self._px_used = px
             return recv_ids
-        px.barrier(0, stream)                                   # every owner is done with the previous step's inboxes
-        lib.dp_push_ids(x.data_ptr(), B, self.F, px.ids_ptrs.data_ptr(), px.fbound.data_ptr(), self.rank, N, stream)
-        px.barrier(1, stream)
+        if phase != "rows":
+            px.barrier(0, stream)                               # every owner is done with the previous step's index inbox
+            lib.dp_push_ids(x.data_ptr(), B, self.F, px.ids_ptrs.data_ptr(), px.fbound.data_ptr(), self.rank, N, stream)
+            px.barrier(1, stream)
+        if phase == "ids":
+            return recv_ids
         self._plan, self._plan_event = None, None
         side = rt.side_stream() if (plan_ahead and phase == "all") else None
         if nf_me and plan_ahead and phase == "all":
@@ -425,15 +429,20 @@ class DataParallel:
         """x: this rank's [B, F] int32 indices -> X[B, F*E] (activation dtype) through the owners of each field.
         plan_ahead (training step): the owner-side backward plan over the received indices starts on the side stream as soon as
         they have arrived and runs next to the model program.
-        phase: "all" = exchange + plan; "exchange" = only fill X and the index inbox (the PREFETCH of the next step's batch, issued
-        behind this step's table update); "consume" = X and the inbox were prefetched: only the plan."""
+        phase: "all" = exchange + plan; "exchange" = only fill X and the index inbox (the PREFETCH of a batch); "consume" = X and
+        the inbox were prefetched: only the plan.  A training step splits the prefetch of the NEXT batch in two: "ids" (indices to
+        the owners - the index inbox is free as soon as this step's plan is built, so this runs under the forward) and "rows"
+        (gather + rows back + unpack into X - behind this step's table update)."""
         rt = self.model._rt
-        if phase != "consume":
+        if phase not in ("consume", "rows"):
             self._pref = None                                   # any other exchange at this batch size overwrites X and the inbox
+        if phase == "rows" and self._ids_pending != B:
+            raise RuntimeError("cdcmdr: the row phase of a prefetched exchange without its index phase")
+        self._ids_pending = B if phase == "ids" else None
         px = self._px.get(B)
         if px is not None:
             out = self._embed_forward_peer(px, ws, x, B, X, plan_ahead, phase)
-            if phase == "exchange":
+            if phase in ("exchange", "rows"):
                 self._pref = B
             return out
         self._px_used = None
@@ -444,11 +453,14 @@ class DataParallel:
             recv_ids = ws.get("dp.recv_ids", (N * B * max(nf_me, 1),), torch.int32)
             self._plan_ahead(recv_ids, B, plan_ahead)
             return recv_ids
-        send_ids = ws.get("dp.send_ids", (B * F,), torch.int32)
-        for (f0, n, cnt) in self._range_runs():               # owner o's block: [B, n] at element offset B*f0
-            ops.copy2d_batched(x.data_ptr() + 4 * f0, n, F, send_ids.data_ptr() + 4 * B * f0, B * n, n, cnt, B, n, 4)
         recv_ids = ws.get("dp.recv_ids", (N * B * max(nf_me, 1),), torch.int32)
-        self._all_to_all(recv_ids[:N * B * nf_me], send_ids[:B * F], [B * nf_me] * N, [B * n for n in self.nf])
+        if phase != "rows":
+            send_ids = ws.get("dp.send_ids", (B * F,), torch.int32)
+            for (f0, n, cnt) in self._range_runs():           # owner o's block: [B, n] at element offset B*f0
+                ops.copy2d_batched(x.data_ptr() + 4 * f0, n, F, send_ids.data_ptr() + 4 * B * f0, B * n, n, cnt, B, n, 4)
+            self._all_to_all(recv_ids[:N * B * nf_me], send_ids[:B * F], [B * nf_me] * N, [B * n for n in self.nf])
+        if phase == "ids":
+            return recv_ids
         self._plan, self._plan_event = None, None
         side = rt.side_stream() if (plan_ahead and phase == "all") else None
         if nf_me and plan_ahead and phase == "all":
@@ -472,7 +484,7 @@ class DataParallel:
         for (f0, n, cnt) in self._range_runs():
             ops.copy2d_batched(rows_recv.data_ptr() + esz * B * f0 * E, B * n * E, n * E, X.ptr + esz * f0 * E, n * E, X.ld, cnt, B, n * E,
                                esz)
-        if phase == "exchange":
+        if phase in ("exchange", "rows"):
             self._pref = B
         return recv_ids
 
