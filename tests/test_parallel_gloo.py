@@ -330,19 +330,20 @@ def test_row_routed_star_on_two_replicas_matches_one_process():
 
 
 # ---------------------------------------------------------------- the next step's exchange issued behind this step's table update
-def _worker_prefetch(rank, world, port, kind, B, path):
+def _worker_prefetch(rank, world, port, kind, B, path, fd=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         cm._lib.install(HostABI())
+        fd = FD if fd is None else np.asarray(fd, dtype=np.int64)
         rng = np.random.default_rng(17)
-        xs = [np.stack([rng.integers(0, d, size=B) for d in FD], axis=1).astype(np.int32) for _ in range(4)]
+        xs = [np.stack([rng.integers(0, d, size=B) for d in fd], axis=1).astype(np.int32) for _ in range(4)]
         ys = [(rng.random(B) < 0.3).astype(np.int16) for _ in range(4)]
         gs = [rng.integers(0, T, size=B).astype(np.int64) for _ in range(4)]
         lo, hi = rank * B // world, (rank + 1) * B // world
         res = {}
         for variant in ("plain", "pipelined"):
-            model = _build(kind)
+            model = _build(kind, FD=fd)
             cm.parallel.attach_data_parallel(model)
             opt = cm.Adam(model.parameters(), **ADAM)
             model.train()
@@ -372,14 +373,15 @@ def _worker_prefetch(rank, world, port, kind, B, path):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,world", [("ple", 2), ("cdc", 3)])
-def test_pipelined_exchange_is_bit_identical_to_the_plain_loop(kind, world):
+@pytest.mark.parametrize("kind,world,fields", [("ple", 2, None), ("cdc", 3, None), ("ple", 4, [11, 7, 13])])
+def test_pipelined_exchange_is_bit_identical_to_the_plain_loop(kind, world, fields):
     """train_step(x_next=...) / train_step(prefetched=True): the next batch's index / row exchange is issued behind this step's table
     update.  Four steps over four different batches: predictions, losses and every parameter are BIT identical to the plain loop
-    (the prefetched rows are the updated ones), and a forward in between makes the next `prefetched=True` raise."""
+    (the prefetched rows are the updated ones), and a forward in between makes the next `prefetched=True` raise.  The 4-rank case has
+    three fields: rank 0 owns no rows at all and still takes part in every phase."""
     B = 96
     with tempfile.TemporaryDirectory() as tmp:
-        mp.spawn(_worker_prefetch, args=(world, _free_port(), kind, B, tmp), nprocs=world, join=True)
+        mp.spawn(_worker_prefetch, args=(world, _free_port(), kind, B, tmp, fields), nprocs=world, join=True)
         ranks = [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
     for r in range(world):
         keys = [k[len("plain."):] for k in ranks[r] if k.startswith("plain.")]
