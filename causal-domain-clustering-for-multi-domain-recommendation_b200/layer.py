@@ -337,15 +337,16 @@ class BaseModel(nn.Module):
         return X
 
     def _gather(self, ws, x, B, plan_ahead=False, phase="all"):
-        """phase (replicas with the field-sharded table only): "exchange" = fill X for `x` without planning (the prefetch of the NEXT
-        step's batch), "consume" = X was prefetched by the previous step."""
+        """phase (replicas with the field-sharded table only; DataParallel.embed_forward): "exchange" = fill X for `x` without
+        planning, "ids" / "rows" = the two halves of that (the prefetch of the NEXT step's batch: indices under the forward, rows
+        behind the table update), "consume" = X was prefetched by the previous step."""
         rt = self._rt
         E, F = self.embed_dim, self.field_num
         table = self.embedding.embedding_dict.weight
         if rt.bf16 and (F * E) % 8:
             raise ValueError("the bf16 tensor-core path needs field_num*embed_dim to be a multiple of 8 (TMA alignment)")
         if rt.dp is not None and rt.dp.shard:
-            rt.dp.prepare_ws(ws, B)                            # peer exchange: X is the symmetric buffer the owners store into
+            rt.dp.prepare_ws(ws, B)                            # peer exchange: the symmetric inboxes of this batch size (made once)
         X = self._x_mat(ws, B)
         if phase != "all" and not (rt.dp is not None and rt.dp.shard):
             raise ValueError("cdcmdr: x_next / prefetched apply to data-parallel replicas with the field-sharded table")
