@@ -68,6 +68,7 @@ class Grouping:
             self.default_metric_value, self.max_better = F32(-1e6), True
         self.A = self.B = self.causal = None
         self.A_t = self.B_t = self.causal_t = None
+        self._memo = {}
 
     # ---------------------------------------------------------------- cdc.py:296-306
     def _update_p_weight(self):
@@ -84,7 +85,18 @@ class Grouping:
     # so its decisions hang on the last bit of a float32 reduction - only torch's own reduction order reproduces them (found by
     # differential fuzzing against the reference: 3 of 480 calls disagreed with NumPy sums, 0 with these).
     # ---------------------------------------------------------------- cdc.py:321-341
+    # Within ONE update() the matrices, p_weight and the initial source groups are fixed, so the three helpers below are pure
+    # functions of their (small, hashable) arguments - and the regrouping asks the same questions again and again (30-domain case:
+    # 76 source-group growths over 30 distinct target groups, 1 004 metrics over 410 distinct pairs).  update() clears `_memo`;
+    # a hit returns the very tensor the first call computed, so nothing about the arithmetic or its order changes.
     def _lambda(self, group, domain=None):
+        key = ("lam", tuple(group), None if domain is None else tuple(domain))
+        hit = self._memo.get(key)
+        if hit is None:
+            hit = self._memo[key] = self._lambda_uncached(group, domain)
+        return hit
+
+    def _lambda_uncached(self, group, domain=None):
         """lambda_d = clamp(0.5 (|G|-1) sum_{g in G} dist[g, d] / (sum_{GxG} dist - sum_{g in G} dist[g, d]), 0, 1)"""
         g = torch.as_tensor(list(group), dtype=torch.int64)
         dom = self._all_domains if domain is None else torch.as_tensor(list(domain), dtype=torch.int64)
@@ -114,11 +126,22 @@ class Grouping:
 
     # ---------------------------------------------------------------- cdc.py:308-312
     def _metric_in_source_group(self, target, s_group):
-        lam = self._lambda(s_group, [target])
-        return torch.sum((1 - lam) * self.A_t[s_group, target] + lam * self.B_t[s_group, target])
+        key = ("met", int(target), tuple(s_group))
+        hit = self._memo.get(key)
+        if hit is None:
+            lam = self._lambda(s_group, [target])
+            hit = self._memo[key] = torch.sum((1 - lam) * self.A_t[s_group, target] + lam * self.B_t[s_group, target])
+        return hit
 
     # ---------------------------------------------------------------- cdc.py:240-294
     def _source_domains(self, t_group, group_idx):
+        key = ("src", tuple(t_group), int(group_idx), self.initial_s_group2domain_list is None)
+        hit = self._memo.get(key)
+        if hit is None:
+            hit = self._memo[key] = self._source_domains_uncached(t_group, group_idx)
+        return list(hit)                                         # callers own (and may extend) the list
+
+    def _source_domains_uncached(self, t_group, group_idx):
         nd = self.n_domain
         s_group = self._centers(t_group, center_num=2)
         useful = True
@@ -150,6 +173,7 @@ class Grouping:
         """matrix_A (n_domain+1, n_domain), matrix_B (n_domain+n_cluster, n_domain), matrix_mask (n_mask, n_domain): float32.
         Returns dict(A, B, mask, causal) - the transformed matrices the reference leaves on the module - and updates the lists."""
         nd, nc = self.n_domain, self.n_cluster
+        self._memo = {}
         self.call_update_group += 1
         self._update_p_weight()
         A, B, M = (np.array(t, dtype=F32, copy=True) for t in (matrix_A, matrix_B, matrix_mask))
