@@ -148,15 +148,17 @@ class Grouping:
         P = None
         if self.initial_s_group2domain_list is not None:           # constant over the growth loop
             P = (1 - 2 * self._lambda(self.initial_s_group2domain_list[group_idx])) * torch.pow(self.w_t, 0.5)
+        # constant over the growth loop (they depend on the target group only): the normalised weights and the two affinity blocks
+        wt = self.w_t[t_group]
+        sw = wt.sum()
+        if sw != 0:
+            wt = wt / sw
+        A_blk, B_blk = self.A_t[:nd, t_group], self.B_t[:nd, t_group]
         while useful and len(s_group) < nd:
             lam = torch.zeros(nd, len(t_group), dtype=torch.float32)
             cands = [d for d in range(nd) if d not in s_group]
             lam[cands] = self._lambda_candidates(s_group, cands, t_group)
-            wt = self.w_t[t_group]
-            sw = wt.sum()
-            if sw != 0:
-                wt = wt / sw
-            J = (((1 - lam) * self.A_t[:nd, t_group] + lam * self.B_t[:nd, t_group]) * wt).sum(dim=1)
+            J = (((1 - lam) * A_blk + lam * B_blk) * wt).sum(dim=1)
             if P is None:
                 result = J
             else:
