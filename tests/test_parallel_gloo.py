@@ -389,3 +389,64 @@ def test_pipelined_exchange_is_bit_identical_to_the_plain_loop(kind, world, fiel
         for k in keys:
             assert np.array_equal(ranks[r]["plain." + k], ranks[r]["pipelined." + k], equal_nan=True), (r, k)
         assert int(ranks[r]["refused"]) == 1
+
+
+# ---------------------------------------------------------------- the tensor-core path's host wiring on replicas (bf16 rows / row gradients)
+E16 = 8                                                        # field_num * embed_dim must be a multiple of 8 on the bf16 path
+
+
+def _build_bf16(kind):
+    torch.manual_seed(5)
+    cfg = Cfg(); cfg.cdcmdr_precision = "bf16"
+    if kind == "ple":
+        return cm.PLE(FD, E16, T, 2, 1, ((16, 8), (8,)), (8, 8), dropout=0.0, config=cfg, **L2)
+    m = cm.CDC(FD, E16, T, ND, "ple", ((16, 8), (8,)), (8, 8), DOM, dropout=0.0, config=cfg, **L2)
+    m.set_groups([d % T for d in range(ND)])
+    return m
+
+
+def _worker_bf16(rank, world, port, kind, B, n_steps, path):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        cm._lib.install(HostABI())
+        model = _build_bf16(kind)
+        cm.parallel.attach_data_parallel(model)
+        x, y, g = _data(B)
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        outs = _steps(model, kind, x[lo:hi], y[lo:hi], g[lo:hi], n_steps)
+        sd = {k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+        np.savez(os.path.join(path, f"rank{rank}.npz"), **sd,
+                 **{f"pred{i}": o[0] for i, o in enumerate(outs)}, **{f"loss{i}": np.array(o[1]) for i, o in enumerate(outs)})
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("kind,world", [("ple", 2), ("cdc", 3)])
+def test_bf16_path_on_replicas_tracks_one_process(kind, world):
+    """The bf16 path under data parallelism (bf16 rows and bf16 row gradients between replicas, cross-replica BatchNorm on bf16
+    activations): N ranks against ONE process running the same bf16 path on the concatenated batch.  The only extra rounding is the
+    row gradients' trip through bf16, so the bar is the bf16 path's own (2e-2 on predictions, 1e-2 relative on the loss) - and the
+    replicas must still be bit-identical to each other."""
+    B, n_steps = 96, 3
+    with tempfile.TemporaryDirectory() as tmp:
+        mp.spawn(_worker_bf16, args=(world, _free_port(), kind, B, n_steps, tmp), nprocs=world, join=True)
+        ranks = [dict(np.load(os.path.join(tmp, f"rank{r}.npz"))) for r in range(world)]
+    old = cm._lib._LIB
+    cm._lib.install(HostABI())
+    try:
+        model = _build_bf16(kind)
+        x, y, g = _data(B)
+        ref = _steps(model, kind, x, y, g, n_steps)
+    finally:
+        cm._lib.install(old)
+    for i in range(n_steps):
+        pred = np.concatenate([ranks[r][f"pred{i}"] for r in range(world)], axis=0)
+        assert np.abs(pred - ref[i][0]).max() <= 2e-2, (i, float(np.abs(pred - ref[i][0]).max()))
+        for r in range(world):
+            assert np.allclose(ranks[r][f"loss{i}"], np.array(ref[i][1]), rtol=1e-2, atol=1e-4), (i, r, ranks[r][f"loss{i}"], ref[i][1])
+    for k in ranks[0]:
+        if k.startswith(("pred", "loss")):
+            continue
+        for r in range(1, world):
+            assert np.array_equal(ranks[r][k], ranks[0][k]), k
