@@ -373,7 +373,7 @@ def _worker_prefetch(rank, world, port, kind, B, path, fd=None):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("kind,world,fields", [("ple", 2, None), ("cdc", 3, None), ("ple", 4, [11, 7, 13])])
+@pytest.mark.parametrize("kind,world,fields", [("ple", 2, None), ("cdc", 3, None), ("mmoe", 2, None), ("ple", 4, [11, 7, 13])])
 def test_pipelined_exchange_is_bit_identical_to_the_plain_loop(kind, world, fields):
     """train_step(x_next=...) / train_step(prefetched=True): the next batch's index / row exchange is issued behind this step's table
     update.  Four steps over four different batches: predictions, losses and every parameter are BIT identical to the plain loop
